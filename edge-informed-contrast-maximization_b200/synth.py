@@ -1,0 +1,149 @@
+"""Seeded synthetic event windows shaped like the reference's dataloader output.
+
+The reference's datasets (DSEC / MVSEC / ECD) are not available offline, so tests, smoke and the
+benchmark use windows synthesised here.  The output contract is the one
+``EINCMExperiment.stage_datasample`` hands the solver (reference src/experiments/e00/exp_mgr.py:283-327,
+379-388): ``xs, ys`` int16 in-sensor pixel coordinates, ``ts`` float64 normalised to ~[0, 1] and sorted
+ascending, ``edges`` float64 (R, H, W) in [0, 1] (min-max normalised, exp_mgr.py:343-350) and ``edge_ts``
+float64 (R,).
+
+Scene: K random line segments carry a smooth "truth" flow (a random coarse tile field, bilinearly
+upsampled).  Events fire on edge points at t ~ U(0, 1) displaced by ``flow * t``; 10 % are uniform noise.
+Edge maps are the same edge points displaced to each reference time, box-blurred and normalised.
+Timestamps and flows are drawn from continuous distributions so rint() ties have measure zero.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+# name -> (H, W, N, edge_ts, alpha, beta, gamma)   [reference run.sh:17-121, SURVEY.md §8d]
+WORKLOADS = {
+    'e00_single': dict(H=480, W=640, N=1_000_000, edge_ts=(0.0,), alpha=2000.0, beta=4000.0, gamma=0.0),
+    'e00_single_r3': dict(H=480, W=640, N=1_000_000, edge_ts=(0.0, 0.5, 1.0), alpha=2000.0, beta=4000.0, gamma=0.0),
+    'dsec_shipped': dict(H=480, W=640, N=1_500_000, edge_ts=(0.0, 0.5, 1.0), alpha=2000.0, beta=4000.0, gamma=0.0),
+    'dsec': dict(H=480, W=640, N=2_000_000, edge_ts=(0.0, 0.5, 1.0), alpha=2000.0, beta=4000.0, gamma=0.0),
+    'dsec_5m': dict(H=480, W=640, N=5_000_000, edge_ts=(0.0, 0.5, 1.0), alpha=2000.0, beta=4000.0, gamma=0.0),
+    'mvsec_dt1': dict(H=256, W=336, N=30_000, edge_ts=(0.0, 1.0), alpha=20.0, beta=35.0, gamma=0.0),
+    'mvsec_dt4': dict(H=256, W=336, N=30_000, edge_ts=(0.0, 0.25, 0.5, 0.75, 1.0), alpha=20.0, beta=35.0, gamma=0.0),
+    'mvsec_raw_dt4': dict(H=260, W=346, N=30_000, edge_ts=(0.0, 0.25, 0.5, 0.75, 1.0), alpha=20.0, beta=35.0, gamma=0.0),
+    'mvsec_outdoor': dict(H=256, W=336, N=40_000, edge_ts=(0.0, 0.25, 0.5, 0.75, 1.0), alpha=20.0, beta=35.0, gamma=0.0025),
+    'ecd': dict(H=176, W=240, N=30_000, edge_ts=(0.0, 0.5, 1.0), alpha=60.0, beta=60.0, gamma=0.0),
+    'large': dict(H=720, W=1280, N=50_000_000, edge_ts=(0.0, 0.5, 1.0), alpha=2000.0, beta=4000.0, gamma=0.0),
+    'tiny': dict(H=48, W=64, N=4_000, edge_ts=(0.0, 0.5, 1.0), alpha=20.0, beta=35.0, gamma=0.0),
+}
+
+
+@dataclass
+class Window:
+    xs: np.ndarray        # int16 (N,)
+    ys: np.ndarray        # int16 (N,)
+    ts: np.ndarray        # float64 (N,), sorted
+    edges: np.ndarray     # float64 (R, H, W)
+    edge_ts: np.ndarray   # float64 (R,)
+    sensor_size: Tuple[int, int]
+    truth_theta: np.ndarray   # float64 (th, tw, 2) coarse truth flow (px / window)
+    hparams: Dict[str, float]
+
+    def args(self):
+        """Positional operands of loss_func after theta (reference src/eincm/losses.py:108-114)."""
+        return self.xs, self.ys, self.ts, self.edges, self.edge_ts
+
+
+def _bilinear_field(theta: np.ndarray, H: int, W: int) -> np.ndarray:
+    """Plain half-pixel bilinear upsample used only to synthesise the truth flow."""
+    h, w = theta.shape[:2]
+    fy = np.clip((np.arange(H) + 0.5) * h / H - 0.5, 0, h - 1)
+    fx = np.clip((np.arange(W) + 0.5) * w / W - 0.5, 0, w - 1)
+    y0 = np.floor(fy).astype(int); y1 = np.minimum(y0 + 1, h - 1); wy = (fy - y0)[:, None, None]
+    x0 = np.floor(fx).astype(int); x1 = np.minimum(x0 + 1, w - 1); wx = (fx - x0)[None, :, None]
+    top = theta[y0][:, x0] * (1 - wx) + theta[y0][:, x1] * wx
+    bot = theta[y1][:, x0] * (1 - wx) + theta[y1][:, x1] * wx
+    return top * (1 - wy) + bot * wy
+
+
+def _box_blur3(img: np.ndarray) -> np.ndarray:
+    p = np.pad(img, 1)
+    out = np.zeros_like(img)
+    for dy in range(3):
+        for dx in range(3):
+            out += p[dy:dy + img.shape[0], dx:dx + img.shape[1]]
+    return out / 9.0
+
+
+def make_window(H: int, W: int, N: int, edge_ts=(0.0, 0.5, 1.0), seed: int = 0, n_segments: int = 200,
+                flow_mag: float = 20.0, truth_tiles: Tuple[int, int] = (2, 2), noise_frac: float = 0.1,
+                hparams: Optional[Dict[str, float]] = None) -> Window:
+    rng = np.random.default_rng(seed)
+    edge_ts = np.asarray(edge_ts, dtype=np.float64)
+    R = len(edge_ts)
+    truth_theta = rng.uniform(-flow_mag, flow_mag, size=(truth_tiles[0], truth_tiles[1], 2))
+    flow = _bilinear_field(truth_theta, H, W)                      # (H, W, 2) px / window
+
+    # edge points: dense samples along random segments (sub-pixel positions at t = 0)
+    seg_len = rng.uniform(0.05, 0.4, size=n_segments) * min(H, W)
+    cx = rng.uniform(0, W, size=n_segments); cy = rng.uniform(0, H, size=n_segments)
+    ang = rng.uniform(0, np.pi, size=n_segments)
+    pts_per_seg = np.maximum(4, (seg_len * 2).astype(int))
+    seg_id = np.repeat(np.arange(n_segments), pts_per_seg)
+    u = rng.uniform(-0.5, 0.5, size=seg_id.size)
+    px = cx[seg_id] + u * seg_len[seg_id] * np.cos(ang[seg_id])
+    py = cy[seg_id] + u * seg_len[seg_id] * np.sin(ang[seg_id])
+    keep = (px >= 1) & (px < W - 1) & (py >= 1) & (py < H - 1)
+    px, py = px[keep], py[keep]
+    pf = flow[py.astype(int), px.astype(int)]                      # flow carried by each edge point
+
+    # edge maps at each reference time
+    edges = np.zeros((R, H, W), dtype=np.float64)
+    for r in range(R):
+        ex = np.clip(np.rint(px + pf[:, 0] * edge_ts[r]), 0, W - 1).astype(int)
+        ey = np.clip(np.rint(py + pf[:, 1] * edge_ts[r]), 0, H - 1).astype(int)
+        e = np.zeros((H, W)); e[ey, ex] = 1.0
+        e = _box_blur3(e)
+        edges[r] = (e - e.min()) / (e.max() - e.min() + np.finfo(np.float64).eps)
+
+    # events
+    n_noise = int(N * noise_frac)
+    n_sig = N - n_noise
+    which = rng.integers(0, px.size, size=n_sig)
+    t_sig = rng.uniform(0.0, 1.0, size=n_sig)
+    jitter = rng.normal(0.0, 0.35, size=(n_sig, 2))
+    ex = px[which] + pf[which, 0] * t_sig + jitter[:, 0]
+    ey = py[which] + pf[which, 1] * t_sig + jitter[:, 1]
+    xs = np.concatenate([np.rint(ex), rng.integers(0, W, size=n_noise).astype(np.float64)])
+    ys = np.concatenate([np.rint(ey), rng.integers(0, H, size=n_noise).astype(np.float64)])
+    ts = np.concatenate([t_sig, rng.uniform(0.0, 1.0, size=n_noise)])
+    xs = np.clip(xs, 0, W - 1).astype(np.int16)                    # loaders deliver in-sensor events
+    ys = np.clip(ys, 0, H - 1).astype(np.int16)
+    order = np.argsort(ts, kind='stable')                          # loaders deliver time-sorted events
+    return Window(xs=np.ascontiguousarray(xs[order]), ys=np.ascontiguousarray(ys[order]),
+                  ts=np.ascontiguousarray(ts[order]), edges=edges, edge_ts=edge_ts, sensor_size=(H, W),
+                  truth_theta=truth_theta, hparams=dict(hparams or {}))
+
+
+def make_workload(name: str, seed: int = 0, n_events: Optional[int] = None) -> Window:
+    cfg = dict(WORKLOADS[name])
+    N = n_events if n_events is not None else cfg['N']
+    hp = dict(alpha=cfg['alpha'], beta=cfg['beta'], gamma=cfg['gamma'], delta=0.0)
+    n_seg = max(20, int(200 * (cfg['H'] * cfg['W']) / (480 * 640)))
+    mag = 20.0 * min(1.0, cfg['W'] / 640 + 0.25)
+    return make_window(cfg['H'], cfg['W'], N, cfg['edge_ts'], seed=seed, n_segments=n_seg,
+                       flow_mag=mag, hparams=hp)
+
+
+def theta_test_points(win: Window, shape: Tuple[int, int], seed: int = 0) -> Dict[str, np.ndarray]:
+    """theta evaluation points of SURVEY.md §8d: zero, (resampled) truth, truth + N(0, 2^2)."""
+    rng = np.random.default_rng(seed + 1000)
+    H, W = win.sensor_size
+    h, w = shape
+    dense = _bilinear_field(win.truth_theta, H, W)
+    iy = np.minimum(((np.arange(h) + 0.5) * H / h).astype(int), H - 1)
+    ix = np.minimum(((np.arange(w) + 0.5) * W / w).astype(int), W - 1)
+    truth = np.ascontiguousarray(dense[iy][:, ix])
+    return {
+        'zero': np.zeros((h, w, 2)),
+        'truth': truth,
+        'perturbed': truth + rng.normal(0.0, 2.0, size=truth.shape),
+    }
