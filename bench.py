@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the EINCM objective+gradient hot path (BASELINE.json metric: warped-event objective+grad evals,
+Gevents/s/GPU at DSEC 640x480).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dsec] [--theta 16]
+
+A *step* is one objective+gradient evaluation (all R reference times, forward + analytic backward) of one synthetic
+DSEC-shaped event window.  Steps cycle round-robin over ``--windows`` distinct windows whose combined working set is
+larger than the 126 MB L2, so no step finds its inputs cached by the previous one.
+
+Own arm  : ``value``  = device-resident evaluation (theta, loss and gradient stay in HBM), timed with CUDA events on the
+           launching stream, max over ranks.  ``e2e`` = the same evaluations through the reference-facing host call
+           (``WindowObjective.value_and_grad`` -> ``eincm_value_and_grad_host``: theta from host memory, loss + gradient
+           read back to the host every step - exactly what jaxopt's ``scipy_fun`` does per line-search step).
+           ``e2e_stateless`` additionally re-stages the whole window (events + edge images) from pinned host memory every
+           step (``set_window`` + evaluation).
+Reference arm (``--impl reference``): the CPU restatement of the reference (``oracle/``; JAX is not installable in this
+           image) on the host cores, each step a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'objective+grad evaluation throughput (events x evals / s)'
+UNIT = 'Gevents/s'
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def algorithmic_bytes(N, R, H, W):
+    """SURVEY.md §8(d), reference dtypes: events (x:i16, y:i16, t:f64) read once per event pass (2 passes);
+    per reference image: IWE written + read, edge image read, dL/dIWE written + read (f64); dense theta field
+    written and dense gradient field read (f64 x 2 channels)."""
+    ev = 2 * N * 12
+    img = R * H * W * 8 * 5
+    fld = H * W * 2 * 8 * 2
+    return {'eval': ev + img + fld,
+            'k_splat': N * 12 + R * H * W * 8 + H * W * 16,
+            'k_backward_events': N * 12 + R * H * W * 8 + H * W * 16 + H * W * 16}
+
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index=0):
+        self.samples = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        rows = [s for s in self.samples if t0 - 0.05 <= s[0] <= t1 + 0.15] or self.samples[-3:]
+        for _, line in rows:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_windows(args, rank):
+    from eincm_b200 import synth
+    wins = []
+    for k in range(args.windows):
+        wins.append(synth.make_workload(args.workload, seed=1000 * rank + k, n_events=args.events))
+    return wins
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_eval_factory():
+    """Returns (fn(theta, win, hp, lvl) -> (loss, grad), kind, cores, label).  Prefers the multi-threaded C restatement
+    (oracle/_build) and falls back to the NumPy one; both are restatements ("port"), not the JAX reference itself."""
+    try:
+        from oracle import c_oracle
+        if c_oracle.available():
+            cores = c_oracle.num_threads()
+            return c_oracle.value_and_grad, 'port', cores, f'oracle/eincm_oracle_c.c (OpenMP, {cores} threads)'
+    except Exception:
+        pass
+    from oracle import eincm_oracle as O
+
+    def fn(theta, win, hp, lvl):
+        return O.value_and_grad(theta, *win.args(), hp['alpha'], hp['beta'], hp['gamma'], hp['delta'], lvl, 5, win.sensor_size)
+
+    return fn, 'port', 1, 'oracle/eincm_oracle.py (NumPy float64, 1 thread)'
+
+
+def cpu_sample_window(win, n_sample):
+    """A bounded sample of the workload: the first n_sample events of a random permutation (same sensor, same edges)."""
+    from eincm_b200.synth import Window
+    N = len(win.xs)
+    if n_sample >= N:
+        return win
+    idx = np.sort(np.random.default_rng(7).permutation(N)[:n_sample])
+    return Window(xs=np.ascontiguousarray(win.xs[idx]), ys=np.ascontiguousarray(win.ys[idx]), ts=np.ascontiguousarray(win.ts[idx]),
+                  edges=win.edges, edge_ts=win.edge_ts, sensor_size=win.sensor_size, truth_theta=win.truth_theta,
+                  hparams=win.hparams)
+
+
+def time_cpu(win, theta, steps, warmup, budget_s):
+    fn, kind, cores, label = cpu_eval_factory()
+    N = len(win.xs)
+    # probe on a small sample to size the per-step sample so that (steps + warmup) steps fit the budget
+    probe_n = min(N, 50_000)
+    pw = cpu_sample_window(win, probe_n)
+    t0 = time.perf_counter(); fn(theta, pw, win.hparams, 0); tp = time.perf_counter() - t0
+    t0 = time.perf_counter(); fn(theta, pw, win.hparams, 0); tp = min(tp, time.perf_counter() - t0)
+    per_event = max(tp, 1e-4) / probe_n          # upper bound: includes the image-space fixed cost
+    n_sample = int(min(N, max(probe_n, budget_s / max(1, steps + warmup) / per_event)))
+    sw = cpu_sample_window(win, n_sample)
+    for _ in range(warmup):
+        fn(theta, sw, win.hparams, 0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn(theta, sw, win.hparams, 0)
+    dt = time.perf_counter() - t0
+    return {'value': n_sample * steps / dt / 1e9, 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': f'{n_sample} of {N} events of one window, {steps} objective+grad evals, {label}',
+            'ms_per_step': dt / steps * 1e3, 'n_sample': n_sample}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from eincm_b200 import synth
+    win = synth.make_workload(args.workload, seed=0, n_events=args.events)
+    theta = synth.theta_test_points(win, (args.theta, args.theta))['perturbed']
+    r = time_cpu(win, theta, args.steps, args.warmup, budget_s=args.cpu_budget)
+    H, W = win.sensor_size
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: DSEC-shaped {W}x{H}, N={len(win.xs)} events/window, R={len(win.edge_ts)}, '
+                               f'theta {args.theta}x{args.theta}x2', 'sample_events': r['n_sample']},
+        'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+        'note': 'CPU restatement of the reference (JAX/jaxlib/jaxopt are not installable in this image: no network)',
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from eincm_b200 import plan as P, synth
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    wins = make_windows(args, rank)
+    H, W = wins[0].sensor_size
+    N = len(wins[0].xs)
+    R = len(wins[0].edge_ts)
+    hpd = wins[0].hparams
+    hp = P.make_hparams(hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], 0)
+    shape = (args.theta, args.theta)
+    plans, thetas_h, thetas_d, losses_d, grads_d = [], [], [], [], []
+    for w in wins:
+        p = P.Plan((H, W), max_events=N, max_refs=max(R, 3))
+        p.set_window(*w.args())
+        plans.append(p)
+        th = synth.theta_test_points(w, shape)['perturbed']
+        thetas_h.append(th)
+        thetas_d.append(torch.from_numpy(th).cuda())
+        losses_d.append(torch.zeros(1, dtype=torch.float64, device='cuda'))
+        grads_d.append(torch.zeros(shape + (2,), dtype=torch.float64, device='cuda'))
+    nw = len(plans)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dev_step(i):
+        k = i % nw
+        plans[k].value_and_grad_device(thetas_d[k], hp, losses_d[k], grads_d[k])
+
+    # ---- device-resident timing -------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        dev_step(i)
+    for p in plans:
+        p.set_timing(True)
+    launches0 = sum(p.launch_count() for p in plans)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    launches = sum(p.launch_count() for p in plans) - launches0
+    kt = {}
+    for p in plans:
+        for name, (ms, n) in p.get_timing().items():
+            a = kt.setdefault(name, [0.0, 0])
+            a[0] += ms; a[1] += n
+        p.set_timing(False)
+    ms_per_step = ms_total / args.steps
+    value = world * N * args.steps / (ms_total * 1e-3) / 1e9
+
+    # ---- end to end through the host-facing call --------------------------------------------------------------
+    def host_step(i):
+        k = i % nw
+        return plans[k].value_and_grad_host(thetas_h[k], hp)
+
+    for i in range(args.warmup):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss_h, grad_h = host_step(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * N * args.steps / e2e_s / 1e9
+    theta_bytes = int(np.prod(shape)) * 2 * 8
+
+    # ---- stateless: stage the whole window from pinned host memory every step ---------------------------------
+    pin = []
+    for w in wins:
+        pin.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (w.xs, w.ys, w.ts, w.edges)))
+    n_sl = max(2, min(args.steps, 8))
+
+    def stateless_step(i):
+        k = i % nw
+        xs, ys, ts, ed = (t.cuda(non_blocking=True) for t in pin[k])
+        plans[k].set_window(xs, ys, ts, ed, wins[k].edge_ts)
+        return plans[k].value_and_grad_host(thetas_h[k], hp)
+
+    stateless_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_sl):
+        stateless_step(i + 1)
+    torch.cuda.synchronize()
+    sl_s = max_over_ranks(time.perf_counter() - t0)
+    sl_value = world * N * n_sl / sl_s / 1e9
+    window_bytes = N * 12 + R * H * W * 8 + R * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    peak, peak_src = _peaks()
+    alg = algorithmic_bytes(N, R, H, W)
+    kern_ms = {k: v[0] / max(v[1], 1) for k, v in kt.items()}
+    span_total = sum(v[0] for v in kt.values())
+    dom = max(kt, key=lambda k: kt[k][0]) if kt else None
+    roofline = None
+    if dom is not None:
+        dom_bytes = alg.get(dom, alg['eval'])
+        achieved = dom_bytes / (kern_ms[dom] * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': None, 'algorithmic_bytes_per_launch': dom_bytes, 'kernel_ms': kern_ms[dom],
+                    'kernel_share_of_step': kt[dom][0] / span_total if span_total else None, 'peak_source': peak_src}
+    eval_achieved = alg['eval'] / (ms_per_step * 1e-3) / 1e9
+
+    # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_cpu(wins[0], thetas_h[0], steps=2, warmup=1, budget_s=args.cpu_budget)
+        cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: DSEC-shaped {W}x{H}, N={N} events/window, R={R} reference times, theta '
+                               f'{shape[0]}x{shape[1]}x2 (finest pyramid level), alpha={hpd["alpha"]}, beta={hpd["beta"]}',
+                   'l2': f'inputs larger than L2: {nw} distinct windows per GPU evaluated round-robin '
+                         f'(~{nw * (N * 16 + (3 * R + 6) * H * W * 8) / 1e6:.0f} MB working set)',
+                   'parallelism': f'windows sharded over {world} GPU(s), no data-path collective',
+                   'events_per_step_per_gpu': N},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': theta_bytes, 'd2h_bytes_per_step': theta_bytes + 8,
+                'call': 'WindowObjective/Plan.value_and_grad_host -> eincm_value_and_grad_host (theta from host, loss+grad to host; '
+                        'window operands staged once per window like the reference\'s jnp arrays)',
+                'ms_per_step': e2e_s / args.steps * 1e3},
+        'e2e_stateless': {'value': sl_value, 'unit': UNIT, 'h2d_bytes_per_step': window_bytes + theta_bytes,
+                          'd2h_bytes_per_step': theta_bytes + 8, 'steps': n_sl, 'ms_per_step': sl_s / n_sl * 1e3,
+                          'call': 'set_window from pinned host memory + value_and_grad_host every step'},
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+        'roofline_eval': {'bound': 'hbm', 'achieved': eval_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': eval_achieved / peak,
+                          'algorithmic_bytes_per_eval': alg['eval']},
+        'kernels_ms_per_launch': {k: round(v, 5) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
+        'cpu_baseline': cpu,
+        'check': {'loss': float(loss_h), 'grad_inf': float(np.abs(grad_h).max())},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--workload', default='dsec')
+    ap.add_argument('--events', type=int, default=None, help='override the number of events per window')
+    ap.add_argument('--theta', type=int, default=16, help='tile-flow resolution (theta is theta x theta x 2)')
+    ap.add_argument('--windows', type=int, default=4, help='distinct windows per GPU cycled round-robin')
+    ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU work for the CPU baseline / reference arm')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        args.cpu_budget = max(args.cpu_budget, 60.0)
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == '__main__':
+    main()

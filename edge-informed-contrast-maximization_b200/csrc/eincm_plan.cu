@@ -1,0 +1,690 @@
+// C-ABI of include/eincm.h: the plan object and the launch sequences of one window / one evaluation.
+// Host side only orchestrates; all arithmetic is in the k_*.cuh kernels (sm_100a).  No CPU fallback exists:
+// every compute entry point fails with EINCM_ECUDA when no CUDA device of compute capability 10.x is usable.
+#include "../../include/eincm.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "k_prep.cuh"
+#include "k_theta.cuh"
+#include "k_events.cuh"
+#include "k_image.cuh"
+
+using namespace eincm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct AxisTapsOwner {
+    int n_in = 0, n_out = 0;
+    void* blob = nullptr;   // one device allocation holding all six arrays
+    AxisTaps taps{};
+};
+
+}  // namespace
+
+struct eincm_plan {
+    int device = 0, H = 0, W = 0, max_refs = 0, sm_count = 148;
+    int64_t HW = 0, max_events = 0;
+    unsigned flags = 0;
+    bool wrap = true;
+    // window state
+    int64_t n_events = 0;
+    int R = 0;
+    bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
+    RefTimes tref{};
+    // last evaluation
+    int last_h = 0, last_w = 0;
+    const double* last_theta = nullptr;   // device pointers of the theta operands of the last forward
+    const double* last_prev = nullptr;
+    double last_a_ho = 0.0;
+    // device buffers
+    uint32_t* ev_xy = nullptr;
+    double* ev_t = nullptr;
+    uint32_t* perm = nullptr;
+    unsigned int *counts = nullptr, *cursor = nullptr, *block_sums = nullptr;
+    int n_keys = 0, tiles_x = 0, n_scan_blocks = 0;
+    uint8_t* mask = nullptr;
+    double2 *theta_full = nullptr, *Gtv = nullptr, *partial = nullptr;
+    double *G = nullptr, *iwe = nullptr, *zero_iwe = nullptr, *dldi = nullptr, *edges = nullptr;
+    double *sbar = nullptr, *gNdiv = nullptr;          // delta != 0 only, allocated on first use
+    double* part = nullptr;                            // per-CTA partials of the two-level reductions
+    int part_doubles = 0;
+    DevScalars* sc = nullptr;
+    double *theta_stage = nullptr, *prev_stage = nullptr, *grad_stage = nullptr, *grad_buf = nullptr, *out_stage = nullptr;
+    int16_t *xs_stage = nullptr, *ys_stage = nullptr;  // stateless host form only, allocated on first use
+    double* ts_stage = nullptr;
+    double* edges_stage = nullptr;
+    // pinned host staging
+    double* h_pinned = nullptr;     // [2*H*W + 1024]
+    int* h_flag = nullptr;
+    std::map<std::pair<int, int>, AxisTapsOwner> taps_cache;
+    std::string error;
+    // launch accounting / optional per-kernel timing
+    int64_t launch_count = 0;
+    bool timing = false;
+    struct Span { const char* name; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+int fail(eincm_plan* p, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (p) p->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(plan, e_ == cudaErrorMemoryAllocation ? EINCM_ENOMEM : EINCM_ECUDA, "%s: %s",   \
+                        #call, cudaGetErrorString(e_));                                                  \
+    } while (0)
+
+// One kernel launch on stream `st` of `plan`: counts it, checks the launch, and - when timing is enabled
+// (eincm_plan_set_timing) - brackets it with CUDA events on the same stream.
+#define LAUNCH(name, ...)                                                                                \
+    do {                                                                                                 \
+        const int span_ = span_begin(plan, name, st);                                                    \
+        __VA_ARGS__;                                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess) return fail(plan, EINCM_ECUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+        span_end(plan, span_, st);                                                                       \
+    } while (0)
+
+int span_begin(eincm_plan* p, const char* name, cudaStream_t st) {
+    ++p->launch_count;
+    if (!p->timing) return -1;
+    cudaEvent_t ev[2];
+    for (auto& e : ev) {
+        if (!p->event_pool.empty()) { e = p->event_pool.back(); p->event_pool.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    }
+    cudaEventRecord(ev[0], st);
+    p->spans.push_back({name, ev[0], ev[1]});
+    return (int)p->spans.size() - 1;
+}
+
+void span_end(eincm_plan* p, int idx, cudaStream_t st) {
+    if (idx >= 0) cudaEventRecord(p->spans[idx].b, st);
+}
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+// Per-axis resize taps of jax.image.scale_and_translate(method='bilinear', antialias=True) for n_in -> n_out
+// (n_out >= n_in), restating compute_weight_mat (reference src/utils/theta_utils.py:25-35).
+int build_axis_taps(eincm_plan* plan, int n_in, int n_out, AxisTaps* out) {
+    auto key = std::make_pair(n_in, n_out);
+    auto it = plan->taps_cache.find(key);
+    if (it != plan->taps_cache.end()) { *out = it->second.taps; return EINCM_OK; }
+    std::vector<int> i0(n_out), i1(n_out), lo(n_in, n_out), hi(n_in, 0);
+    std::vector<double> w0(n_out), w1(n_out);
+    const double scale = (double)n_out / (double)n_in;
+    const double inv = 1.0 / scale;
+    const double kscale = std::max(inv, 1.0);
+    for (int j = 0; j < n_out; ++j) {
+        const double f = ((double)j + 0.5) * inv - 0.0 * inv - 0.5;
+        int a = (int)std::floor(f), b = a + 1;
+        double wa = 0.0, wb = 0.0;
+        if (a >= 0 && a < n_in) wa = std::max(0.0, 1.0 - std::fabs(f - (double)a) / kscale);
+        if (b >= 0 && b < n_in) wb = std::max(0.0, 1.0 - std::fabs(f - (double)b) / kscale);
+        const double total = wa + wb;
+        if (std::fabs(total) > 1000.0 * 1.1920928955078125e-07) { wa /= total; wb /= total; } else { wa = wb = 0.0; }
+        if (!(f >= -0.5 && f <= (double)n_in - 0.5)) wa = wb = 0.0;
+        if (a < 0 || a >= n_in) { a = b; wa = wb; wb = 0.0; }          // single valid tap: keep it in slot 0
+        if (b < 0 || b >= n_in || wb == 0.0) { b = a; wb = 0.0; }
+        if (a < 0 || a >= n_in) { a = b = 0; wa = wb = 0.0; }
+        i0[j] = a; i1[j] = b; w0[j] = wa; w1[j] = wb;
+        if (wa != 0.0) { lo[a] = std::min(lo[a], j); hi[a] = std::max(hi[a], j + 1); }
+        if (wb != 0.0) { lo[b] = std::min(lo[b], j); hi[b] = std::max(hi[b], j + 1); }
+    }
+    for (int i = 0; i < n_in; ++i) if (hi[i] <= lo[i]) { lo[i] = 0; hi[i] = 0; }
+    AxisTapsOwner o;
+    o.n_in = n_in; o.n_out = n_out;
+    const size_t bytes = (size_t)n_out * (2 * sizeof(int) + 2 * sizeof(double)) + (size_t)n_in * 2 * sizeof(int);
+    CU(cudaMalloc(&o.blob, bytes));
+    char* base = (char*)o.blob;
+    double* d_w0 = (double*)base; double* d_w1 = d_w0 + n_out;
+    int* d_i0 = (int*)(d_w1 + n_out); int* d_i1 = d_i0 + n_out; int* d_lo = d_i1 + n_out; int* d_hi = d_lo + n_in;
+    // synchronous copies from pageable memory: happens once per (n_in, n_out) pair and plan
+    CU(cudaMemcpy(d_w0, w0.data(), n_out * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_w1, w1.data(), n_out * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_i0, i0.data(), n_out * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_i1, i1.data(), n_out * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_lo, lo.data(), n_in * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_hi, hi.data(), n_in * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());   // pageable H2D may still be in flight w.r.t. non-blocking streams
+    o.taps = AxisTaps{d_i0, d_i1, d_w0, d_w1, d_lo, d_hi};
+    plan->taps_cache[key] = o;
+    *out = o.taps;
+    return EINCM_OK;
+}
+
+__global__ void k_set_weights(DevScalars* sc, RefTimes w, int R) {
+    if (threadIdx.x < EINCM_MAX_REFS) sc->weights[threadIdx.x] = threadIdx.x < R ? w.t[threadIdx.x] : 0.0;
+}
+
+int event_grid(const eincm_plan* p, int64_t n, int threads) {
+    const int64_t want = (n + threads - 1) / threads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 8));
+}
+
+int img_tiles_x(const eincm_plan* p) { return (p->W + kImgTX - 1) / kImgTX; }
+int img_tiles_y(const eincm_plan* p) { return (p->H + kImgTY - 1) / kImgTY; }
+int img_nb_flat(const eincm_plan* p) { return (int)std::min<int64_t>((p->HW + kImgNT - 1) / kImgNT, (int64_t)p->sm_count * 4); }
+
+int check_hp(eincm_plan* plan, const eincm_hparams* hp) {
+    if (!hp) return fail(plan, EINCM_EINVAL, "hparams is NULL");
+    if (hp->method != EINCM_METHOD_BILINEAR)
+        return fail(plan, EINCM_EUNSUPPORTED, "scale_to_sensor_size_method %d unsupported (only bilinear, the shipped default)", hp->method);
+    return EINCM_OK;
+}
+
+int ensure_delta_buffers(eincm_plan* plan) {
+    if (plan->sbar) return EINCM_OK;
+    CU(dmalloc(&plan->sbar, (size_t)plan->max_refs * plan->HW));
+    CU(dmalloc(&plan->gNdiv, (size_t)plan->max_refs * plan->HW));
+    return EINCM_OK;
+}
+
+// zero-IWE statistics that depend on delta (computed on first use; losses.py:80)
+int ensure_zero_div(eincm_plan* plan, cudaStream_t st) {
+    if (plan->zero_div_valid) return EINCM_OK;
+    int rc = ensure_delta_buffers(plan);
+    if (rc) return rc;
+    const dim3 grid(img_tiles_x(plan), img_tiles_y(plan), 1), block(kImgTX, kImgTY);
+    LAUNCH("k_img_D1(zero)", k_img_D1<<<grid, block, 0, st>>>(plan->zero_iwe, 0, plan->H, plan->W, grid.x * grid.y, plan->sc->zero, 0, nullptr, nullptr,
+                                     plan->part, plan->sc->zero, &plan->sc->counters[2]));
+    plan->zero_div_valid = true;
+    return EINCM_OK;
+}
+
+int window_finalize_impl(eincm_plan* plan, cudaStream_t st) {
+    const dim3 block(kImgTX, kImgTY);
+    const dim3 gridA(img_tiles_x(plan), img_tiles_y(plan), 1);
+    LAUNCH("k_img_A(zero)", k_img_A<<<gridA, block, 0, st>>>(plan->zero_iwe, plan->H, plan->W, gridA.x * gridA.y, plan->part, plan->sc->zero,
+                                     &plan->sc->counters[0]));
+    const int nb = img_nb_flat(plan);
+    LAUNCH("k_img_B(zero)", k_img_B<<<dim3(nb, 1, plan->R), block, 0, st>>>(plan->zero_iwe, 0, plan->edges, nullptr, plan->HW, nb, plan->sc->zero, 0,
+                                                    nullptr, plan->part, plan->sc->zero, &plan->sc->counters[1]));
+    plan->window_final = true;
+    plan->zero_div_valid = false;
+    return EINCM_OK;
+}
+
+int forward_events_impl(eincm_plan* plan, const double* theta, const double* prev, double a_ho, int h, int w,
+                        const eincm_hparams* hp, cudaStream_t st) {
+    int rc = check_hp(plan, hp);
+    if (rc) return rc;
+    if (!plan->window_set) return fail(plan, EINCM_ESTATE, "value_and_grad before set_window");
+    if (!theta) return fail(plan, EINCM_EINVAL, "theta is NULL");
+    if (h < 1 || w < 1 || h > plan->H || w > plan->W)
+        return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) must be within (1,1)..(%d,%d): the resize only up-scales", h, w, plan->H, plan->W);
+    AxisTaps ty, tx;
+    if ((rc = build_axis_taps(plan, h, plan->H, &ty))) return rc;
+    if ((rc = build_axis_taps(plan, w, plan->W, &tx))) return rc;
+    {
+        const dim3 block(32, 8), grid((plan->W + 31) / 32, (plan->H + 7) / 8);
+        LAUNCH("k_upsample_theta", k_upsample_theta<<<grid, block, 0, st>>>(theta, prev, a_ho, h, w, plan->H, plan->W, ty, tx, plan->theta_full));
+    }
+    CU(cudaMemsetAsync(plan->iwe, 0, (size_t)plan->R * plan->HW * sizeof(double), st));
+    if (plan->n_events > 0) {
+        const int grid = event_grid(plan, plan->n_events, 256);
+        if (plan->wrap)
+            LAUNCH("k_splat", k_splat<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full, plan->H, plan->W,
+                                                                  plan->R, plan->tref, plan->iwe));
+        else
+            LAUNCH("k_splat", k_splat<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full, plan->H, plan->W,
+                                                                   plan->R, plan->tref, plan->iwe));
+    }
+    plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
+    plan->forward_done = true;
+    return EINCM_OK;
+}
+
+int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, double* dalpha_out, cudaStream_t st) {
+    int rc = check_hp(plan, hp);
+    if (rc) return rc;
+    if (!plan->forward_done) return fail(plan, EINCM_ESTATE, "eincm_backward before eincm_forward_events");
+    if (!plan->window_final) return fail(plan, EINCM_ESTATE, "eincm_backward before eincm_window_finalize");
+    const int R = plan->R, H = plan->H, W = plan->W, h = plan->last_h, w = plan->last_w;
+    const bool use_tv = hp->gamma != 0.0 && hp->cur_pyr_lvl <= 0;       // losses.py:171
+    const bool use_div = hp->delta != 0.0;
+    const bool want_grad = grad_out != nullptr || dalpha_out != nullptr;
+    const dim3 block(kImgTX, kImgTY);
+    const dim3 gridT(img_tiles_x(plan), img_tiles_y(plan), R);
+    const int nbT = gridT.x * gridT.y;
+    if (use_div) {
+        if ((rc = ensure_zero_div(plan, st))) return rc;
+    }
+    LAUNCH("k_img_A", k_img_A<<<gridT, block, 0, st>>>(plan->iwe, H, W, nbT, plan->part, plan->sc->ref, &plan->sc->counters[0]));
+    LAUNCH("k_scalars(0)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 0, nullptr));
+    const double* gNdiv = nullptr;
+    if (use_div) {
+        LAUNCH("k_img_D1", k_img_D1<<<gridT, block, 0, st>>>(plan->iwe, plan->HW, H, W, nbT, plan->sc->ref, 1, plan->sc->coefD, plan->sbar, plan->part,
+                                          plan->sc->ref, &plan->sc->counters[2]));
+        if (want_grad) {
+            LAUNCH("k_img_D2", k_img_D2<<<gridT, block, 0, st>>>(plan->sbar, H, W, plan->gNdiv));
+            gNdiv = plan->gNdiv;
+        }
+    }
+    const int nbF = img_nb_flat(plan);
+    LAUNCH("k_img_B", k_img_B<<<dim3(nbF, 1, R), block, 0, st>>>(plan->iwe, plan->HW, plan->edges, gNdiv, plan->HW, nbF, plan->sc->ref, 1,
+                                               plan->sc->coefB, plan->part, plan->sc->ref, &plan->sc->counters[1]));
+    if (use_tv) {
+        const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
+        LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
+    }
+    LAUNCH("k_scalars(1)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 1, loss_out));
+    if (!want_grad) return EINCM_OK;
+
+    LAUNCH("k_img_C", k_img_C<<<gridT, block, 0, st>>>(plan->iwe, plan->edges, gNdiv, H, W, plan->sc->ref, plan->sc->coefA, plan->sc->coefB, plan->dldi));
+    CU(cudaMemsetAsync(plan->G, 0, (size_t)plan->HW * 2 * sizeof(double), st));
+    if (plan->n_events > 0) {
+        const int grid = event_grid(plan, plan->n_events, 256);
+        if (plan->wrap)
+            LAUNCH("k_backward_events", k_backward_events<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full,
+                                                                                      H, W, R, plan->tref, plan->dldi, plan->G));
+        else
+            LAUNCH("k_backward_events", k_backward_events<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full,
+                                                                                       H, W, R, plan->tref, plan->dldi, plan->G));
+    }
+    AxisTaps ty, tx;
+    if ((rc = build_axis_taps(plan, h, H, &ty))) return rc;
+    if ((rc = build_axis_taps(plan, w, W, &tx))) return rc;
+    const double2* Gtv = use_tv ? plan->Gtv : nullptr;
+    const int n_el = h * w;
+    CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
+    const bool handover = plan->last_prev != nullptr;
+    double* gout = grad_out;
+    if (n_el <= kGatherMaxTiles) {
+        int S = std::max(1, (2 * plan->sm_count + n_el - 1) / n_el);
+        S = std::min(S, std::max(1, H / std::max(1, h)));
+        LAUNCH("k_theta_grad_gather", k_theta_grad_gather<<<n_el * S, 256, 0, st>>>((const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, S, ty, tx, plan->partial));
+        LAUNCH("k_grad_out", k_grad_out<<<std::min(plan->sm_count, (n_el + 255) / 256), 256, 0, st>>>(plan->partial, S, nullptr, n_el,
+                                                                               handover ? plan->last_prev : nullptr, plan->last_theta, gout, plan->sc));
+    } else {
+        CU(cudaMemsetAsync(plan->grad_buf, 0, (size_t)n_el * 2 * sizeof(double), st));
+        const dim3 b2(32, 8), g2((W + 31) / 32, (H + 7) / 8);
+        LAUNCH("k_theta_grad_scatter", k_theta_grad_scatter<<<g2, b2, 0, st>>>((const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, ty, tx, plan->grad_buf));
+        LAUNCH("k_grad_out", k_grad_out<<<std::min(plan->sm_count * 4, (n_el + 255) / 256), 256, 0, st>>>(nullptr, 0, plan->grad_buf, n_el,
+                                                                                   handover ? plan->last_prev : nullptr, plan->last_theta, gout, plan->sc));
+    }
+    if (dalpha_out) CU(cudaMemcpyAsync(dalpha_out, &plan->sc->dalpha, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return EINCM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eincm_abi_version(void) { return EINCM_ABI_VERSION; }
+
+const char* eincm_last_error(const eincm_plan* plan) { return plan ? plan->error.c_str() : g_create_error.c_str(); }
+
+int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_events, int max_refs, unsigned flags) {
+    eincm_plan* plan = nullptr;
+    if (!out) return fail(nullptr, EINCM_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (H < 3 || W < 3 || H > 32767 || W > 32767) return fail(nullptr, EINCM_EINVAL, "sensor size (%d,%d) out of range", H, W);
+    if (max_events < 0 || max_events > 0x7fffffffLL) return fail(nullptr, EINCM_EINVAL, "max_events out of range");
+    if (max_refs < 1 || max_refs > EINCM_MAX_REFS) return fail(nullptr, EINCM_EINVAL, "max_refs must be in 1..%d", EINCM_MAX_REFS);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, EINCM_ECUDA, "no CUDA device (%s): this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(nullptr, EINCM_EINVAL, "device %d out of range (%d devices)", device, n_dev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, EINCM_ECUDA, "%s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, EINCM_ECUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, EINCM_ECUDA, "%s", cudaGetErrorString(e));
+
+    plan = new (std::nothrow) eincm_plan();
+    if (!plan) return fail(nullptr, EINCM_ENOMEM, "host allocation failed");
+    plan->device = device; plan->H = H; plan->W = W; plan->HW = (int64_t)H * W; plan->max_events = max_events;
+    plan->max_refs = max_refs; plan->flags = flags; plan->wrap = !(flags & EINCM_FLAG_NO_WRAP_NEGATIVE);
+    plan->sm_count = prop.multiProcessorCount;
+    plan->tiles_x = (W + kSortTile - 1) / kSortTile;
+    plan->n_keys = plan->tiles_x * ((H + kSortTile - 1) / kSortTile) * kSortTile * kSortTile;
+    plan->n_scan_blocks = (plan->n_keys + kScanBlock - 1) / kScanBlock;
+    const size_t HW = (size_t)plan->HW, NE = (size_t)max_events, RR = (size_t)max_refs;
+    const int nbT = img_tiles_x(plan) * img_tiles_y(plan);
+    plan->part_doubles = 8 * max_refs * std::max(nbT, plan->sm_count * 4) + 64;
+    auto body = [&]() -> int {
+        CU(dmalloc(&plan->ev_xy, NE)); CU(dmalloc(&plan->ev_t, NE)); CU(dmalloc(&plan->perm, NE));
+        CU(dmalloc(&plan->counts, (size_t)plan->n_keys)); CU(dmalloc(&plan->cursor, (size_t)plan->n_keys));
+        CU(dmalloc(&plan->block_sums, (size_t)plan->n_scan_blocks));
+        CU(dmalloc(&plan->mask, HW));
+        CU(dmalloc(&plan->theta_full, HW)); CU(dmalloc(&plan->Gtv, HW));
+        CU(dmalloc(&plan->partial, (size_t)kGatherMaxTiles * 2 + (size_t)4 * plan->sm_count));
+        CU(dmalloc(&plan->G, HW * 2)); CU(dmalloc(&plan->iwe, RR * HW)); CU(dmalloc(&plan->zero_iwe, HW));
+        CU(dmalloc(&plan->dldi, RR * HW)); CU(dmalloc(&plan->edges, RR * HW));
+        CU(dmalloc(&plan->part, (size_t)plan->part_doubles));
+        CU(dmalloc(&plan->sc, 1));
+        CU(cudaMemset(plan->sc, 0, sizeof(DevScalars)));
+        CU(dmalloc(&plan->theta_stage, HW * 2)); CU(dmalloc(&plan->prev_stage, HW * 2));
+        CU(dmalloc(&plan->grad_stage, HW * 2)); CU(dmalloc(&plan->grad_buf, HW * 2));
+        CU(dmalloc(&plan->out_stage, 8));
+        CU(cudaMallocHost((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double)));
+        CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
+        return EINCM_OK;
+    };
+    const int rc = body();
+    if (rc != EINCM_OK) {
+        g_create_error = plan->error;
+        eincm_plan_destroy(plan);
+        return rc;
+    }
+    *out = plan;
+    return EINCM_OK;
+}
+
+void eincm_plan_destroy(eincm_plan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->device);
+    void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->counts, plan->cursor, plan->block_sums, plan->mask, plan->theta_full,
+                    plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
+                    plan->part, plan->sc, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
+                    plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (auto& kv : plan->taps_cache) if (kv.second.blob) cudaFree(kv.second.blob);
+    for (auto& sp : plan->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto& e : plan->event_pool) cudaEventDestroy(e);
+    if (plan->h_pinned) cudaFreeHost(plan->h_pinned);
+    if (plan->h_flag) cudaFreeHost(plan->h_flag);
+    delete plan;
+}
+
+int eincm_plan_info(const eincm_plan* plan, int* H, int* W, int64_t* n_events, int* n_refs, int* max_refs) {
+    if (!plan) return EINCM_EINVAL;
+    if (H) *H = plan->H;
+    if (W) *W = plan->W;
+    if (n_events) *n_events = plan->n_events;
+    if (n_refs) *n_refs = plan->R;
+    if (max_refs) *max_refs = plan->max_refs;
+    return EINCM_OK;
+}
+
+int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys, const double* ts, int64_t n, const double* edges,
+                          const double* edge_ts_host, int R, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (n < 0 || n > plan->max_events) return fail(plan, EINCM_EINVAL, "n_events %lld exceeds the plan's max_events %lld", (long long)n, (long long)plan->max_events);
+    if (R < 1 || R > plan->max_refs) return fail(plan, EINCM_EINVAL, "n_refs %d outside 1..max_refs=%d", R, plan->max_refs);
+    if ((n > 0 && (!xs || !ys || !ts)) || !edges || !edge_ts_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+    CU(cudaSetDevice(plan->device));
+    plan->window_set = false; plan->window_final = false; plan->forward_done = false; plan->zero_div_valid = false;
+    plan->n_events = n; plan->R = R;
+    for (int r = 0; r < EINCM_MAX_REFS; ++r) plan->tref.t[r] = r < R ? edge_ts_host[r] : 0.0;
+
+    // multi-reference weights (losses.py:39-46): stats.norm.pdf(linspace(-1.5, 1.5, R)) normalised
+    RefTimes wts{};
+    {
+        double sum = 0.0;
+        for (int r = 0; r < R; ++r) {
+            // np.linspace(-1.5, 1.5, R): start + r*step (last sample is exactly the stop value)
+            double x = R == 1 ? -1.5 : (r == R - 1 ? 1.5 : -1.5 + (double)r * (3.0 / (double)(R - 1)));
+            wts.t[r] = std::exp(-0.5 * x * x) / std::sqrt(2.0 * M_PI);
+            sum += wts.t[r];
+        }
+        for (int r = 0; r < R; ++r) wts.t[r] /= sum;
+    }
+    LAUNCH("k_set_weights", k_set_weights<<<1, 32, 0, st>>>(plan->sc, wts, R));
+
+    CU(cudaMemsetAsync(plan->counts, 0, (size_t)plan->n_keys * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(&plan->sc->error_flag, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(plan->sc->counters, 0, sizeof(plan->sc->counters), st));
+    if (n > 0) {
+        const int grid = event_grid(plan, n, 256);
+        LAUNCH("k_histogram", k_histogram<<<grid, 256, 0, st>>>(xs, ys, n, plan->H, plan->W, plan->tiles_x, plan->counts, &plan->sc->error_flag));
+    }
+    LAUNCH("k_scan_block_sums", k_scan_block_sums<<<plan->n_scan_blocks, kScanBlock, 0, st>>>(plan->counts, plan->n_keys, plan->block_sums));
+    LAUNCH("k_scan_of_block_sums", k_scan_of_block_sums<<<1, kScanBlock, 0, st>>>(plan->block_sums, plan->n_scan_blocks));
+    LAUNCH("k_scan_finish", k_scan_finish<<<plan->n_scan_blocks, kScanBlock, 0, st>>>(plan->counts, plan->n_keys, plan->block_sums, plan->cursor));
+    LAUNCH("k_event_mask", k_event_mask<<<(int)((plan->HW + 255) / 256), 256, 0, st>>>(plan->counts, plan->H, plan->W, plan->tiles_x, plan->mask));
+    if (n > 0) {
+        const int grid = event_grid(plan, n, 256);
+        LAUNCH("k_scatter_events", k_scatter_events<<<grid, 256, 0, st>>>(xs, ys, ts, n, plan->H, plan->W, plan->tiles_x, plan->cursor, plan->ev_xy, plan->ev_t, plan->perm));
+    }
+    CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // zero-warp IWE (losses.py:54): theta = 0 => x' = x for every reference time
+    CU(cudaMemsetAsync(plan->zero_iwe, 0, (size_t)plan->HW * sizeof(double), st));
+    if (n > 0) {
+        const int grid = event_grid(plan, n, 256);
+        RefTimes z{};
+        if (plan->wrap)
+            LAUNCH("k_splat(zero)", k_splat<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, nullptr, plan->H, plan->W, 1, z, plan->zero_iwe));
+        else
+            LAUNCH("k_splat(zero)", k_splat<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, nullptr, plan->H, plan->W, 1, z, plan->zero_iwe));
+    }
+    // validate (the reference's loaders guarantee in-sensor events; a violation would corrupt the gather at
+    // event_warpers.py:34-35, so it is an error here).  One 4-byte read back per window.
+    CU(cudaMemcpyAsync(plan->h_flag, &plan->sc->error_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (plan->h_flag[0] != 0) return fail(plan, EINCM_ERANGE, "an event lies outside the %dx%d sensor", plan->H, plan->W);
+    plan->window_set = true;
+    if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return window_finalize_impl(plan, st);
+    return EINCM_OK;
+}
+
+int eincm_window_finalize(eincm_plan* plan, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!plan->window_set) return fail(plan, EINCM_ESTATE, "eincm_window_finalize before set_window");
+    CU(cudaSetDevice(plan->device));
+    return window_finalize_impl(plan, (cudaStream_t)cuda_stream);
+}
+
+int eincm_forward_events(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    CU(cudaSetDevice(plan->device));
+    return forward_events_impl(plan, theta, nullptr, 0.0, h, w, hp, (cudaStream_t)cuda_stream);
+}
+
+int eincm_backward(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    CU(cudaSetDevice(plan->device));
+    return backward_impl(plan, hp, loss_out, grad_out, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int eincm_value_and_grad(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, double* loss_out,
+                         double* grad_out, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "event-split plans use the split-phase calls");
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = forward_events_impl(plan, theta, nullptr, 0.0, h, w, hp, st);
+    if (rc) return rc;
+    return backward_impl(plan, hp, loss_out, grad_out, nullptr, st);
+}
+
+int eincm_handover_value_and_grad(eincm_plan* plan, double alpha_handover, const double* prev_theta, const double* theta, int h, int w,
+                                  const eincm_hparams* hp, double* loss_out, double* dalpha_out, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "event-split plans use the split-phase calls");
+    if (!prev_theta) return fail(plan, EINCM_EINVAL, "prev_theta is NULL");
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = forward_events_impl(plan, theta, prev_theta, alpha_handover, h, w, hp, st);
+    if (rc) return rc;
+    return backward_impl(plan, hp, loss_out, nullptr, dalpha_out, st);
+}
+
+int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp, double* loss_out_host,
+                              double* grad_out_host, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!theta_host || !loss_out_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+    if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t nb = (size_t)h * w * 2 * sizeof(double);
+    std::memcpy(plan->h_pinned, theta_host, nb);
+    CU(cudaMemcpyAsync(plan->theta_stage, plan->h_pinned, nb, cudaMemcpyHostToDevice, st));
+    int rc = eincm_value_and_grad(plan, plan->theta_stage, h, w, hp, plan->out_stage, grad_out_host ? plan->grad_stage : nullptr, st);
+    if (rc) return rc;
+    double* h_out = plan->h_pinned + (size_t)plan->HW * 2;
+    CU(cudaMemcpyAsync(h_out, plan->out_stage, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grad_out_host) CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *loss_out_host = h_out[0];
+    if (grad_out_host) std::memcpy(grad_out_host, plan->h_pinned, nb);
+    return EINCM_OK;
+}
+
+int eincm_handover_value_and_grad_host(eincm_plan* plan, double alpha_handover, const double* prev_theta_host, const double* theta_host,
+                                       int h, int w, const eincm_hparams* hp, double* loss_out_host, double* dalpha_out_host,
+                                       void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!theta_host || !prev_theta_host || !loss_out_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+    if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t nb = (size_t)h * w * 2 * sizeof(double);
+    // both operands are staged through the one pinned buffer; the first copy must land before it is reused
+    std::memcpy(plan->h_pinned, theta_host, nb);
+    CU(cudaMemcpyAsync(plan->theta_stage, plan->h_pinned, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    std::memcpy(plan->h_pinned, prev_theta_host, nb);
+    CU(cudaMemcpyAsync(plan->prev_stage, plan->h_pinned, nb, cudaMemcpyHostToDevice, st));
+    int rc = eincm_handover_value_and_grad(plan, alpha_handover, plan->prev_stage, plan->theta_stage, h, w, hp, plan->out_stage,
+                                           dalpha_out_host ? plan->out_stage + 1 : nullptr, st);
+    if (rc) return rc;
+    double* h_out = plan->h_pinned + (size_t)plan->HW * 2;
+    CU(cudaMemcpyAsync(h_out, plan->out_stage, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *loss_out_host = h_out[0];
+    if (dalpha_out_host) *dalpha_out_host = h_out[1];
+    return EINCM_OK;
+}
+
+int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_host, int h, int w, const int16_t* xs_host,
+                                        const int16_t* ys_host, const double* ts_host, int64_t n, const double* edges_host,
+                                        const double* edge_ts_host, int R, const eincm_hparams* hp, double* loss_out_host,
+                                        double* grad_out_host, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (n < 0 || n > plan->max_events) return fail(plan, EINCM_EINVAL, "n_events exceeds the plan's max_events");
+    if (R < 1 || R > plan->max_refs) return fail(plan, EINCM_EINVAL, "n_refs %d outside 1..max_refs=%d", R, plan->max_refs);
+    if ((n > 0 && (!xs_host || !ys_host || !ts_host)) || !edges_host || !edge_ts_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (!plan->xs_stage) {
+        CU(dmalloc(&plan->xs_stage, (size_t)plan->max_events)); CU(dmalloc(&plan->ys_stage, (size_t)plan->max_events));
+        CU(dmalloc(&plan->ts_stage, (size_t)plan->max_events));
+        CU(dmalloc(&plan->edges_stage, (size_t)plan->max_refs * plan->HW));
+    }
+    // pageable sources: these copies are synchronous with respect to the host, which is the contract of a *_host call
+    CU(cudaMemcpyAsync(plan->xs_stage, xs_host, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(plan->ys_stage, ys_host, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(plan->ts_stage, ts_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(plan->edges_stage, edges_host, (size_t)R * plan->HW * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = eincm_plan_set_window(plan, plan->xs_stage, plan->ys_stage, plan->ts_stage, n, plan->edges_stage, edge_ts_host, R, st);
+    if (rc) return rc;
+    return eincm_value_and_grad_host(plan, theta_host, h, w, hp, loss_out_host, grad_out_host, st);
+}
+
+double* eincm_zero_iwe_ptr(eincm_plan* plan) { return plan ? plan->zero_iwe : nullptr; }
+double* eincm_iwe_ptr(eincm_plan* plan) { return plan ? plan->iwe : nullptr; }
+uint8_t* eincm_mask_ptr(eincm_plan* plan) { return plan ? plan->mask : nullptr; }
+double* eincm_dldi_ptr(eincm_plan* plan) { return plan ? plan->dldi : nullptr; }
+double* eincm_theta_full_ptr(eincm_plan* plan) { return plan ? (double*)plan->theta_full : nullptr; }
+
+int eincm_get_scalars(eincm_plan* plan, double* out_host, int n_doubles, void* cuda_stream) {
+    if (!plan || !out_host) return EINCM_EINVAL;
+    const int need = EINCM_S_HEADER + 5 * plan->max_refs;
+    if (n_doubles < need) return fail(plan, EINCM_EINVAL, "out_host needs %d doubles", need);
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DevScalars* hs = (DevScalars*)plan->h_pinned;
+    static_assert(sizeof(DevScalars) <= 1024 * sizeof(double), "scalar block fits the pinned staging area");
+    CU(cudaMemcpyAsync(hs, plan->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out_host[EINCM_S_FINAL_LOSS] = hs->loss;
+    out_host[EINCM_S_MEAN_REL_CORR] = hs->mean_rel_corr;
+    out_host[EINCM_S_MEAN_REL_CONTRAST] = hs->mean_rel_contrast;
+    out_host[EINCM_S_MEAN_REL_IWE_DIV] = hs->mean_rel_div;
+    out_host[EINCM_S_THETA_TV] = hs->tv;
+    out_host[EINCM_S_ZERO_CONTRAST] = hs->zero[0].contrast;
+    out_host[EINCM_S_ZERO_IWE_DIV] = plan->zero_div_valid ? hs->zero[0].div : 0.0;
+    out_host[EINCM_S_DALPHA_HANDOVER] = hs->dalpha;
+    const int M = plan->max_refs;
+    for (int r = 0; r < M; ++r) {
+        const bool live = r < plan->R;
+        out_host[EINCM_S_PER_REF + 0 * M + r] = live ? hs->ref[r].contrast : 0.0;
+        out_host[EINCM_S_PER_REF + 1 * M + r] = live ? -hs->ref[r].mse : 0.0;
+        out_host[EINCM_S_PER_REF + 2 * M + r] = live ? -hs->zero[r].mse : 0.0;
+        out_host[EINCM_S_PER_REF + 3 * M + r] = live ? hs->ref[r].div : 0.0;
+        out_host[EINCM_S_PER_REF + 4 * M + r] = live ? hs->weights[r] : 0.0;
+    }
+    return EINCM_OK;
+}
+
+int64_t eincm_plan_launch_count(const eincm_plan* plan) { return plan ? plan->launch_count : 0; }
+
+int eincm_plan_set_timing(eincm_plan* plan, int enabled) {
+    if (!plan) return EINCM_EINVAL;
+    plan->timing = enabled != 0;
+    return EINCM_OK;
+}
+
+int eincm_plan_get_timing(eincm_plan* plan, char* names_out, int names_cap, double* ms_out, int64_t* launches_out, int max_kernels,
+                          int* n_kernels_out) {
+    if (!plan || !n_kernels_out) return EINCM_EINVAL;
+    CU(cudaSetDevice(plan->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<int64_t> cnt;
+    for (auto& sp : plan->spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) != cudaSuccess) t = 0.f;
+        size_t k = 0;
+        for (; k < names.size(); ++k) if (names[k] == sp.name) break;
+        if (k == names.size()) { names.push_back(sp.name); ms.push_back(0.0); cnt.push_back(0); }
+        ms[k] += t; cnt[k] += 1;
+        plan->event_pool.push_back(sp.a); plan->event_pool.push_back(sp.b);
+    }
+    plan->spans.clear();
+    const int n = (int)std::min<size_t>(names.size(), (size_t)std::max(0, max_kernels));
+    std::string joined;
+    for (int k = 0; k < n; ++k) {
+        if (ms_out) ms_out[k] = ms[k];
+        if (launches_out) launches_out[k] = cnt[k];
+        joined += names[k]; joined += '\n';
+    }
+    if (names_out && names_cap > 0) { std::snprintf(names_out, (size_t)names_cap, "%s", joined.c_str()); }
+    *n_kernels_out = n;
+    return EINCM_OK;
+}
+
+int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int32_t* rows_out, void* cuda_stream) {
+    if (!plan || !cols_out || !rows_out) return EINCM_EINVAL;
+    if (!plan->forward_done) return fail(plan, EINCM_ESTATE, "no evaluation yet");
+    if (ref < 0 || ref >= plan->R) return fail(plan, EINCM_EINVAL, "ref %d outside 0..%d", ref, plan->R - 1);
+    CU(cudaSetDevice(plan->device));
+    if (plan->n_events == 0) return EINCM_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    LAUNCH("k_rounded_pixels", k_rounded_pixels<<<event_grid(plan, plan->n_events, 256), 256, 0, st>>>(
+        plan->ev_xy, plan->ev_t, plan->perm, plan->n_events, plan->theta_full, plan->W, plan->tref.t[ref], cols_out, rows_out));
+    return EINCM_OK;
+}
+
+}  // extern "C"

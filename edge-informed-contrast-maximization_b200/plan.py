@@ -1,0 +1,320 @@
+"""ctypes binding of the C-ABI in ``include/eincm.h`` (``lib/libeincm_b200.so``).
+
+PyTorch is used for plumbing only: device buffers (``torch.empty(..., device='cuda')``), the current CUDA
+stream, and ``torch.distributed`` in ``parallel.py``.  All arithmetic happens in the CUDA library; there is no
+CPU fallback - importing this module without the built library, or creating a plan without a B200, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, 'lib', 'libeincm_b200.so')
+
+EINCM_OK = 0
+EINCM_EINVAL, EINCM_ECUDA, EINCM_ENOMEM, EINCM_ESTATE, EINCM_ERANGE, EINCM_EUNSUPPORTED = -1, -2, -3, -4, -5, -6
+FLAG_NO_WRAP_NEGATIVE = 0x1
+FLAG_EVENT_SPLIT = 0x2
+METHOD_BILINEAR = 0
+S_HEADER = 8
+
+# every symbol include/eincm.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    'eincm_plan_create', 'eincm_plan_destroy', 'eincm_last_error', 'eincm_abi_version', 'eincm_plan_set_window',
+    'eincm_value_and_grad', 'eincm_handover_value_and_grad', 'eincm_value_and_grad_host',
+    'eincm_handover_value_and_grad_host', 'eincm_value_and_grad_stateless_host', 'eincm_window_finalize',
+    'eincm_forward_events', 'eincm_backward', 'eincm_zero_iwe_ptr', 'eincm_iwe_ptr', 'eincm_dldi_ptr',
+    'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
+    'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
+)
+
+
+class EincmError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f'eincm error {code}: {message}')
+        self.code = code
+
+
+class HParams(C.Structure):
+    """``eincm_hparams``: keyword-bound arguments of the loss partial (reference src/eincm/losses.py:115-122)."""
+    _fields_ = [('alpha', C.c_double), ('beta', C.c_double), ('gamma', C.c_double), ('delta', C.c_double),
+                ('cur_pyr_lvl', C.c_int32), ('n_pyr_lvls', C.c_int32), ('method', C.c_int32), ('reserved', C.c_int32)]
+
+
+def make_hparams(alpha, beta, gamma, delta, cur_pyr_lvl, n_pyr_lvls=5, scale_to_sensor_size_method='bilinear') -> HParams:
+    if scale_to_sensor_size_method not in ('bilinear', 'linear'):
+        raise EincmError(EINCM_EUNSUPPORTED, f'scale_to_sensor_size_method {scale_to_sensor_size_method!r}: only the '
+                                              f'shipped default (bilinear) is implemented')
+    return HParams(float(alpha), float(beta), float(gamma), float(delta), int(cur_pyr_lvl), int(n_pyr_lvls), METHOD_BILINEAR, 0)
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Loads the CUDA library.  Fails loudly when it has not been built (``python -c 'import __graft_entry__ as g;
+    g.build()'``): the product has no other code path."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(f'{path} is missing - build it with __graft_entry__.build(); there is no CPU fallback')
+    lib = C.CDLL(path)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    hp = C.POINTER(HParams)
+    sig = {
+        'eincm_plan_create': (i32, [C.POINTER(vp), i32, i32, i32, i64, i32, C.c_uint]),
+        'eincm_plan_destroy': (None, [vp]),
+        'eincm_last_error': (C.c_char_p, [vp]),
+        'eincm_abi_version': (i32, []),
+        'eincm_plan_set_window': (i32, [vp, vp, vp, vp, i64, vp, C.POINTER(dbl), i32, vp]),
+        'eincm_value_and_grad': (i32, [vp, vp, i32, i32, hp, vp, vp, vp]),
+        'eincm_handover_value_and_grad': (i32, [vp, dbl, vp, vp, i32, i32, hp, vp, vp, vp]),
+        'eincm_value_and_grad_host': (i32, [vp, vp, i32, i32, hp, C.POINTER(dbl), vp, vp]),
+        'eincm_handover_value_and_grad_host': (i32, [vp, dbl, vp, vp, i32, i32, hp, C.POINTER(dbl), C.POINTER(dbl), vp]),
+        'eincm_value_and_grad_stateless_host': (i32, [vp, vp, i32, i32, vp, vp, vp, i64, vp, vp, i32, hp, C.POINTER(dbl), vp, vp]),
+        'eincm_window_finalize': (i32, [vp, vp]),
+        'eincm_forward_events': (i32, [vp, vp, i32, i32, hp, vp]),
+        'eincm_backward': (i32, [vp, hp, vp, vp, vp]),
+        'eincm_zero_iwe_ptr': (vp, [vp]),
+        'eincm_iwe_ptr': (vp, [vp]),
+        'eincm_dldi_ptr': (vp, [vp]),
+        'eincm_theta_full_ptr': (vp, [vp]),
+        'eincm_mask_ptr': (vp, [vp]),
+        'eincm_get_scalars': (i32, [vp, C.POINTER(dbl), i32, vp]),
+        'eincm_debug_rounded_pixels': (i32, [vp, i32, vp, vp, vp]),
+        'eincm_plan_launch_count': (i64, [vp]),
+        'eincm_plan_set_timing': (i32, [vp, i32]),
+        'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
+        'eincm_plan_info': (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(stream=None) -> int:
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+class _DevView:
+    """Exposes a plan-owned device buffer through ``__cuda_array_interface__`` so that torch can alias it."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str, owner):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+        self._owner = owner
+
+
+class Plan:
+    """One ``eincm_plan``: all device state for windows of up to ``max_events`` events and ``max_refs`` reference
+    times on an ``H x W`` sensor.  Methods mirror the C entry points one to one."""
+
+    def __init__(self, sensor_size: Tuple[int, int], max_events: int, max_refs: int = 8, device: Optional[int] = None,
+                 flags: int = 0):
+        torch = _torch()
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise EincmError(EINCM_ECUDA, 'no CUDA device: the EINCM objective runs only on a B200 (no CPU fallback)')
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.H, self.W = int(sensor_size[0]), int(sensor_size[1])
+        self.max_events, self.max_refs, self.flags = int(max_events), int(max_refs), int(flags)
+        h = C.c_void_p()
+        rc = self.lib.eincm_plan_create(C.byref(h), self.device, self.H, self.W, self.max_events, self.max_refs, self.flags)
+        if rc != EINCM_OK:
+            raise EincmError(rc, (self.lib.eincm_last_error(None) or b'').decode())
+        self._h = h
+        self.n_events = 0
+        self.n_refs = 0
+        self._keep = []      # operand tensors of the last call (kept alive until the next one)
+        with torch.cuda.device(self.device):
+            self._out = torch.zeros(2, dtype=torch.float64, device='cuda')
+
+    # -- helpers ----------------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != EINCM_OK:
+            raise EincmError(rc, (self.lib.eincm_last_error(self._h) or b'').decode())
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.eincm_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, a, dtype):
+        """numpy / torch operand -> contiguous CUDA tensor of ``dtype`` on this plan's device."""
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+        return t.to(device=f'cuda:{self.device}', dtype=dtype).contiguous()
+
+    # -- window -----------------------------------------------------------------------------------------------
+    def set_window(self, xs, ys, ts, edges, edge_ts, stream=None):
+        """``eincm_plan_set_window`` (replaces ``MultipleLevelEINCMSolver.set_datasample``, reference
+        src/eincm/solver.py:185-194)."""
+        torch = _torch()
+        xs_d, ys_d = self._dev(xs, torch.int16), self._dev(ys, torch.int16)
+        ts_d, edges_d = self._dev(ts, torch.float64), self._dev(edges, torch.float64)
+        ets = np.ascontiguousarray(np.asarray(edge_ts.cpu() if isinstance(edge_ts, torch.Tensor) else edge_ts, dtype=np.float64))
+        n, R = int(xs_d.numel()), int(ets.shape[0])
+        if ys_d.numel() != n or ts_d.numel() != n:
+            raise EincmError(EINCM_EINVAL, 'xs, ys, ts must have the same length')
+        if tuple(edges_d.shape) != (R, self.H, self.W):
+            raise EincmError(EINCM_EINVAL, f'edges must have shape {(R, self.H, self.W)}, got {tuple(edges_d.shape)}')
+        self._check(self.lib.eincm_plan_set_window(self._h, xs_d.data_ptr(), ys_d.data_ptr(), ts_d.data_ptr(), n,
+                                                   edges_d.data_ptr(), ets.ctypes.data_as(C.POINTER(C.c_double)), R,
+                                                   _stream_ptr(stream)))
+        self.n_events, self.n_refs = n, R
+
+    def window_finalize(self, stream=None):
+        self._check(self.lib.eincm_window_finalize(self._h, _stream_ptr(stream)))
+
+    # -- evaluation, device operands (asynchronous) ---------------------------------------------------------------
+    def value_and_grad_device(self, theta_d, hp: HParams, loss_out_d, grad_out_d=None, stream=None):
+        h, w = int(theta_d.shape[0]), int(theta_d.shape[1])
+        self._keep = [theta_d, loss_out_d, grad_out_d]
+        self._check(self.lib.eincm_value_and_grad(self._h, theta_d.data_ptr(), h, w, C.byref(hp), loss_out_d.data_ptr(),
+                                                  grad_out_d.data_ptr() if grad_out_d is not None else None,
+                                                  _stream_ptr(stream)))
+
+    def handover_value_and_grad_device(self, alpha_handover: float, prev_d, theta_d, hp: HParams, loss_out_d, dalpha_out_d=None,
+                                       stream=None):
+        h, w = int(theta_d.shape[0]), int(theta_d.shape[1])
+        self._keep = [prev_d, theta_d, loss_out_d, dalpha_out_d]
+        self._check(self.lib.eincm_handover_value_and_grad(self._h, float(alpha_handover), prev_d.data_ptr(), theta_d.data_ptr(),
+                                                           h, w, C.byref(hp), loss_out_d.data_ptr(),
+                                                           dalpha_out_d.data_ptr() if dalpha_out_d is not None else None,
+                                                           _stream_ptr(stream)))
+
+    def forward_events(self, theta_d, hp: HParams, stream=None):
+        h, w = int(theta_d.shape[0]), int(theta_d.shape[1])
+        self._keep = [theta_d]
+        self._check(self.lib.eincm_forward_events(self._h, theta_d.data_ptr(), h, w, C.byref(hp), _stream_ptr(stream)))
+
+    def backward(self, hp: HParams, loss_out_d, grad_out_d=None, stream=None):
+        self._keep += [loss_out_d, grad_out_d]
+        self._check(self.lib.eincm_backward(self._h, C.byref(hp), loss_out_d.data_ptr(),
+                                            grad_out_d.data_ptr() if grad_out_d is not None else None, _stream_ptr(stream)))
+
+    # -- evaluation, host operands (synchronous: what jaxopt's scipy_fun does per line-search step) ------------------
+    def value_and_grad_host(self, theta: np.ndarray, hp: HParams, want_grad: bool = True, stream=None):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if theta.ndim != 3 or theta.shape[2] != 2:
+            raise EincmError(EINCM_EINVAL, f'theta must have shape (h, w, 2), got {theta.shape}')
+        h, w = theta.shape[:2]
+        loss = C.c_double()
+        grad = np.empty_like(theta) if want_grad else None
+        self._check(self.lib.eincm_value_and_grad_host(self._h, theta.ctypes.data, h, w, C.byref(hp), C.byref(loss),
+                                                       grad.ctypes.data if want_grad else None, _stream_ptr(stream)))
+        return loss.value, grad
+
+    def handover_value_and_grad_host(self, alpha_handover: float, prev_theta: np.ndarray, theta: np.ndarray, hp: HParams,
+                                     want_grad: bool = True, stream=None):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        prev_theta = np.ascontiguousarray(prev_theta, dtype=np.float64)
+        if theta.shape != prev_theta.shape or theta.ndim != 3 or theta.shape[2] != 2:
+            raise EincmError(EINCM_EINVAL, 'prev_theta and theta must both have shape (h, w, 2)')
+        h, w = theta.shape[:2]
+        loss, da = C.c_double(), C.c_double()
+        self._check(self.lib.eincm_handover_value_and_grad_host(self._h, float(alpha_handover), prev_theta.ctypes.data,
+                                                                theta.ctypes.data, h, w, C.byref(hp), C.byref(loss),
+                                                                C.byref(da) if want_grad else None, _stream_ptr(stream)))
+        return loss.value, (da.value if want_grad else None)
+
+    def value_and_grad_stateless_host(self, theta, xs, ys, ts, edges, edge_ts, hp: HParams, stream=None):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.int16); ys = np.ascontiguousarray(ys, dtype=np.int16)
+        ts = np.ascontiguousarray(ts, dtype=np.float64); edges = np.ascontiguousarray(edges, dtype=np.float64)
+        edge_ts = np.ascontiguousarray(edge_ts, dtype=np.float64)
+        h, w = theta.shape[:2]
+        loss = C.c_double()
+        grad = np.empty_like(theta)
+        self._check(self.lib.eincm_value_and_grad_stateless_host(
+            self._h, theta.ctypes.data, h, w, xs.ctypes.data, ys.ctypes.data, ts.ctypes.data, xs.shape[0], edges.ctypes.data,
+            edge_ts.ctypes.data, edge_ts.shape[0], C.byref(hp), C.byref(loss), grad.ctypes.data, _stream_ptr(stream)))
+        self.n_events, self.n_refs = int(xs.shape[0]), int(edge_ts.shape[0])
+        return loss.value, grad
+
+    # -- read-outs --------------------------------------------------------------------------------------------
+    def _view(self, ptr, shape, dtype_str):
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_DevView(ptr, shape, dtype_str, self), device=f'cuda:{self.device}')
+
+    def iwe(self):
+        """(R, H, W) float64 CUDA tensor aliasing the images of warped events of the last evaluation."""
+        return self._view(self.lib.eincm_iwe_ptr(self._h), (self.n_refs, self.H, self.W), '<f8')
+
+    def zero_iwe(self):
+        return self._view(self.lib.eincm_zero_iwe_ptr(self._h), (self.H, self.W), '<f8')
+
+    def dldi(self):
+        return self._view(self.lib.eincm_dldi_ptr(self._h), (self.n_refs, self.H, self.W), '<f8')
+
+    def theta_full(self):
+        """aux 'scaled_theta' (reference src/eincm/losses.py:197)."""
+        return self._view(self.lib.eincm_theta_full_ptr(self._h), (self.H, self.W, 2), '<f8')
+
+    def event_mask(self):
+        return self._view(self.lib.eincm_mask_ptr(self._h), (self.H, self.W), '|u1')
+
+    def scalars(self, stream=None) -> Dict[str, object]:
+        n = S_HEADER + 5 * self.max_refs
+        buf = (C.c_double * n)()
+        self._check(self.lib.eincm_get_scalars(self._h, buf, n, _stream_ptr(stream)))
+        a = np.frombuffer(buf, dtype=np.float64).copy()
+        M, R = self.max_refs, self.n_refs
+        per = a[S_HEADER:].reshape(5, M)[:, :R]
+        return {'final_loss': a[0], 'mean_rel_corr': a[1], 'mean_rel_contrast': a[2], 'mean_rel_iwe_divergence': a[3],
+                'theta_total_variation': a[4], 'zero_contrast': a[5], 'zero_iwe_divergence': a[6], 'dalpha_handover': a[7],
+                'contrasts': per[0].copy(), 'correlations': per[1].copy(), 'zero_correlations': per[2].copy(),
+                'iwe_divergences': per[3].copy(), 'multi_ref_weights': per[4].copy()}
+
+    def launch_count(self) -> int:
+        return int(self.lib.eincm_plan_launch_count(self._h))
+
+    def set_timing(self, enabled: bool):
+        self._check(self.lib.eincm_plan_set_timing(self._h, 1 if enabled else 0))
+
+    def get_timing(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel name: (total ms, launches)} of the spans recorded since the last call (synchronises)."""
+        cap = 64
+        names = C.create_string_buffer(4096)
+        ms = (C.c_double * cap)()
+        cnt = (C.c_int64 * cap)()
+        n = C.c_int()
+        self._check(self.lib.eincm_plan_get_timing(self._h, names, 4096, ms, cnt, cap, C.byref(n)))
+        ks = names.value.decode().split('\n')[:n.value]
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(ks)}
+
+    def rounded_pixels(self, ref: int, stream=None) -> Tuple[np.ndarray, np.ndarray]:
+        """Bit-exact event->pixel index stream (``Xs_rounded``, reference src/utils/event_utils.py:33) of reference
+        ``ref`` for the last evaluated theta, in the original event order."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            cols = torch.empty(self.n_events, dtype=torch.int32, device='cuda')
+            rows = torch.empty(self.n_events, dtype=torch.int32, device='cuda')
+        self._check(self.lib.eincm_debug_rounded_pixels(self._h, int(ref), cols.data_ptr(), rows.data_ptr(), _stream_ptr(stream)))
+        return cols.cpu().numpy(), rows.cpu().numpy()

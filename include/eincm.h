@@ -1,0 +1,167 @@
+/*
+ * eincm.h - C-ABI of the B200-native EINCM contrast-correlation objective (value + gradient).
+ *
+ * This is the drop-in boundary for ONE hot path of robotic-vision-lab/Edge-Informed-Contrast-Maximization:
+ * what `jit(value_and_grad(loss_func))` computes for the jaxopt ScipyMinimize / ScipyBoundedMinimize loops
+ * (reference src/eincm/solver.py:165-183, invoked :209-216, :227-234, :325-335).  Every entry point cites
+ * the reference interface it replaces.  The reference is pure Python on JAX; its "FFI" for this path is a
+ * JAX custom call (`jax.ffi.ffi_call`) whose handler forwards to the functions below - see INTEGRATION.md
+ * for the binding a maintainer would add on the reference side, and csrc/eincm_xla_ffi.cc for the handler.
+ *
+ * Conventions
+ *   - plain C, no torch / JAX / C++ types; `cuda_stream` is a `cudaStream_t` passed as `void*`.
+ *   - return 0 (EINCM_OK) on success, a negative EINCM_E* code otherwise; never throws, never aborts.
+ *     `eincm_last_error(plan)` gives the message of the last failing call on that plan (NULL plan: the
+ *     message of the last failing `eincm_plan_create` on this thread).
+ *   - pointers are DEVICE pointers owned by the caller and borrowed for the duration of the call unless the
+ *     parameter name ends in `_host`.  Outputs are caller-allocated.
+ *   - calls are asynchronous and stream-ordered on `cuda_stream` (the caller synchronises) unless the
+ *     function name ends in `_host` or the comment says "synchronous".
+ *   - one plan = one device and one call in flight (thread-compatible, not thread-safe).
+ *   - layouts are the reference's: theta / grad row-major [h][w][2] float64; edges [R][H][W] float64;
+ *     events as SoA xs,ys int16 and ts float64 (reference src/experiments/e00/exp_mgr.py:379-388).
+ *   - there is no CPU fallback: every compute entry point needs a CUDA device of compute capability 10.x.
+ */
+#ifndef EINCM_H_
+#define EINCM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EINCM_ABI_VERSION 1
+
+/* error codes */
+#define EINCM_OK              0
+#define EINCM_EINVAL        (-1)   /* bad argument (shape, NULL pointer, R > max_refs, theta larger than sensor ...) */
+#define EINCM_ECUDA         (-2)   /* a CUDA runtime call failed; message holds cudaGetErrorString */
+#define EINCM_ENOMEM        (-3)   /* allocation failed */
+#define EINCM_ESTATE        (-4)   /* call order violated (e.g. value_and_grad before set_window) */
+#define EINCM_ERANGE        (-5)   /* an event lies outside the sensor (the reference's loaders guarantee in-sensor events) */
+#define EINCM_EUNSUPPORTED  (-6)   /* e.g. scale method other than bilinear */
+
+/* plan flags (eincm_plan_create) */
+#define EINCM_FLAG_NO_WRAP_NEGATIVE  0x1u  /* drop votes with negative row/col instead of wrapping them (JAX wraps: default) */
+#define EINCM_FLAG_EVENT_SPLIT       0x2u  /* this plan holds 1/G of a window's events: split-phase calls below */
+
+/* theta -> sensor-size resize method (reference configs/main.yaml:27 `scale_theta_to_sensor_size_method`) */
+#define EINCM_METHOD_BILINEAR 0
+
+typedef struct eincm_plan eincm_plan;
+
+/* Keyword-bound hyper-parameters of the loss partial
+ * (reference src/eincm/losses.py:115-122, configs/theta_loss_func/default.yaml:1-9). */
+typedef struct eincm_hparams {
+    double alpha;          /* weight of the contrast objective      (losses.py:115) */
+    double beta;           /* weight of the correlation objective   (losses.py:116) */
+    double gamma;          /* weight of the TV regulariser, applied only when cur_pyr_lvl <= 0 (losses.py:117,171) */
+    double delta;          /* weight of the IWE-divergence objective (losses.py:118; shipped 0) */
+    int32_t cur_pyr_lvl;   /* losses.py:119 */
+    int32_t n_pyr_lvls;    /* losses.py:120 (carried for signature parity; unused by the arithmetic) */
+    int32_t method;        /* EINCM_METHOD_* (losses.py:122) */
+    int32_t reserved;
+} eincm_hparams;
+
+/* Layout of the float64 scalar block returned by eincm_get_scalars (indices into out_host). */
+enum {
+    EINCM_S_FINAL_LOSS = 0,             /* aux 'final_loss'                 (losses.py:196) */
+    EINCM_S_MEAN_REL_CORR = 1,          /* aux 'mean_rel_corr'              (losses.py:198) */
+    EINCM_S_MEAN_REL_CONTRAST = 2,      /* aux 'mean_rel_contrast'          (losses.py:199) */
+    EINCM_S_MEAN_REL_IWE_DIV = 3,       /* aux 'mean_rel_iwe_divergence'    (losses.py:200) */
+    EINCM_S_THETA_TV = 4,               /* aux 'theta_total_variation'      (losses.py:201; 0 when cur_pyr_lvl > 0) */
+    EINCM_S_ZERO_CONTRAST = 5,          /* 'zero_contrast'                  (losses.py:71) */
+    EINCM_S_ZERO_IWE_DIV = 6,           /* 'zero_iwe_divergence'            (losses.py:80; 0 unless delta != 0 was requested) */
+    EINCM_S_DALPHA_HANDOVER = 7,        /* d loss / d alpha_handover of the last handover call */
+    EINCM_S_PER_REF = 8,                /* then 5 blocks of max_refs doubles: contrasts, correlations (= -MSE),
+                                           zero_correlations, iwe_divergences, multi_ref_weights */
+    EINCM_S_HEADER = 8
+};
+
+/* ---- life cycle ---------------------------------------------------------------------------------------- */
+
+/* Allocates all device state for windows of up to `max_events` events and `max_refs` reference times on a
+ * sensor of H x W pixels (reference `sensor_size`, configs/dataset/dsec.yaml:1-5).  Synchronous. */
+int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_events, int max_refs, unsigned flags);
+void eincm_plan_destroy(eincm_plan* plan);
+const char* eincm_last_error(const eincm_plan* plan);
+int eincm_abi_version(void);
+
+/* ---- per window: replaces MultipleLevelEINCMSolver.set_datasample (reference src/eincm/solver.py:185-194)
+ * Stages one event window: validates and bins the events by source pixel, builds the event mask
+ * (theta_utils.py:66-71), the zero-warp IWE and its constants zero_contrast / zero_correlations
+ * (losses.py:54-55,66,71) - everything that does not depend on theta, which the reference recomputes inside
+ * every objective evaluation.  edge_ts_host: R float64 on the HOST (they become kernel constants). */
+int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys, const double* ts, int64_t n_events,
+                          const double* edges, const double* edge_ts_host, int n_refs, void* cuda_stream);
+
+/* ---- per evaluation: replaces jit(value_and_grad(partial(loss_func, cur_pyr_lvl=l)))(theta, xs, ys, ts, edges, edge_ts)
+ * (reference src/eincm/losses.py:108-205 differentiated w.r.t. argument 0; built by jaxopt from solver.py:165-173).
+ * theta: [h][w][2]; loss_out: 1 float64; grad_out: [h][w][2] float64 (may be NULL: value only). */
+int eincm_value_and_grad(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp,
+                         double* loss_out, double* grad_out, void* cuda_stream);
+
+/* replaces jit(value_and_grad(partial(handover_loss_func, cur_pyr_lvl=l)))(alpha_handover, prev_theta, theta, ...)
+ * (reference src/eincm/losses.py:208-276, differentiated w.r.t. the scalar argument 0; solver.py:175-183, :325-335).
+ * dalpha_out: 1 float64 (may be NULL). */
+int eincm_handover_value_and_grad(eincm_plan* plan, double alpha_handover, const double* prev_theta, const double* theta,
+                                  int h, int w, const eincm_hparams* hp, double* loss_out, double* dalpha_out,
+                                  void* cuda_stream);
+
+/* ---- host-buffer forms (synchronous; H2D / D2H copies inside the call) ---------------------------------- */
+
+/* What jaxopt's `scipy_fun(x_np) -> (value, grad)` does per line-search step (theta in, loss + grad out). */
+int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp,
+                              double* loss_out_host, double* grad_out_host, void* cuda_stream);
+int eincm_handover_value_and_grad_host(eincm_plan* plan, double alpha_handover, const double* prev_theta_host,
+                                       const double* theta_host, int h, int w, const eincm_hparams* hp,
+                                       double* loss_out_host, double* dalpha_out_host, void* cuda_stream);
+/* Stateless single shot with the exact operand list of loss_func (losses.py:108-114), every operand on the host:
+ * set_window + value_and_grad + copies. */
+int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_host, int h, int w,
+                                        const int16_t* xs_host, const int16_t* ys_host, const double* ts_host, int64_t n_events,
+                                        const double* edges_host, const double* edge_ts_host, int n_refs,
+                                        const eincm_hparams* hp, double* loss_out_host, double* grad_out_host,
+                                        void* cuda_stream);
+
+/* ---- split-phase form for one window whose events are split over G GPUs (EINCM_FLAG_EVENT_SPLIT) --------
+ * The splat is additive in events; everything after it needs the complete image.  Sequence per rank:
+ *   set_window (local events)      -> all-reduce(sum) eincm_zero_iwe_ptr  [H*W]   -> eincm_window_finalize
+ *                                     (+ all-reduce(max) eincm_mask_ptr [H*W] when gamma != 0)
+ *   eincm_forward_events (local)   -> all-reduce(sum) eincm_iwe_ptr       [R*H*W] -> eincm_backward
+ *   -> all-reduce(sum) of grad_out (and of the gamma-free loss is identical on all ranks already)
+ * The collective itself is the caller's (torch.distributed / NCCL over NVLink); these functions only expose
+ * the buffers.  Without the flag, set_window / value_and_grad run all phases back to back. */
+int eincm_window_finalize(eincm_plan* plan, void* cuda_stream);
+int eincm_forward_events(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, void* cuda_stream);
+int eincm_backward(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, void* cuda_stream);
+double* eincm_zero_iwe_ptr(eincm_plan* plan);   /* device, [H*W] float64 */
+double* eincm_iwe_ptr(eincm_plan* plan);        /* device, [R*H*W] float64, image of warped events of the last evaluation */
+/* device, [H*W] uint8: 1 where a pixel holds >= 1 (local) event (theta_utils.py:66-71); event-split plans that use
+ * gamma != 0 all-reduce(max) it together with the zero-IWE */
+uint8_t* eincm_mask_ptr(eincm_plan* plan);
+
+/* ---- read-outs (debug taps and the aux dict of loss_func) ------------------------------------------------ */
+double* eincm_dldi_ptr(eincm_plan* plan);        /* device, [R*H*W]: d loss / d IWE of the last evaluation */
+double* eincm_theta_full_ptr(eincm_plan* plan);  /* device, [H*W*2]: aux 'scaled_theta' (losses.py:197) */
+/* synchronous: copies EINCM_S_HEADER + 5*max_refs doubles (see enum above) to the host */
+int eincm_get_scalars(eincm_plan* plan, double* out_host, int n_doubles, void* cuda_stream);
+/* Bit-exact event->pixel index stream of reference r for the last evaluated theta, in the ORIGINAL event
+ * order: cols_out/rows_out [n_events] int32 = Xs_rounded of event_utils.py:33 (before the +dx,+dy taps). */
+int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int32_t* rows_out, void* cuda_stream);
+/* ---- measurement hooks (bench.py): launch accounting and optional per-kernel CUDA-event timing -------- */
+/* number of kernels this plan has launched since creation (memsets / copies not counted) */
+int64_t eincm_plan_launch_count(const eincm_plan* plan);
+/* enabled != 0: bracket every subsequent kernel launch with CUDA events on the launching stream */
+int eincm_plan_set_timing(eincm_plan* plan, int enabled);
+/* synchronous: sums the recorded spans per kernel name since the last call and clears them.
+ * names_out: '\n'-separated kernel names (names_cap bytes); ms_out / launches_out: [max_kernels]. */
+int eincm_plan_get_timing(eincm_plan* plan, char* names_out, int names_cap, double* ms_out, int64_t* launches_out, int max_kernels,
+                          int* n_kernels_out);
+int eincm_plan_info(const eincm_plan* plan, int* H, int* W, int64_t* n_events, int* n_refs, int* max_refs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EINCM_H_ */

@@ -1,0 +1,268 @@
+"""Parity of the CUDA path (through the C-ABI) against the float64 CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: objective <= 1e-5 relative, gradient <= 1e-4 relative (inf-norm / inf-norm), the
+event->pixel index stream bit-exact."""
+import functools
+
+import numpy as np
+import pytest
+
+import eincm_b200.synth as S
+from oracle import eincm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+OBJ_RTOL = 1e-5      # BASELINE.json north_star
+GRAD_RTOL = 1e-4     # BASELINE.json north_star
+
+
+def _kw(win, gamma=0.0, delta=0.0, lvl=1, alpha=20.0, beta=35.0):
+    return dict(alpha=alpha, beta=beta, gamma=gamma, delta=delta, cur_pyr_lvl=lvl, n_pyr_lvls=5,
+                sensor_size=win.sensor_size, scale_to_sensor_size_method='bilinear')
+
+
+def _rel_inf(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+@pytest.fixture(scope='module')
+def L():
+    from eincm_b200 import losses
+    yield losses
+    losses.clear_cache()
+
+
+@pytest.fixture(scope='module')
+def tiny():
+    return S.make_workload('tiny', seed=0)
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (2, 2), (4, 4), (16, 16), (48, 64)])
+@pytest.mark.parametrize('point', ['zero', 'truth', 'perturbed'])
+def test_value_and_grad_matches_oracle(L, tiny, shape, point):
+    th = S.theta_test_points(tiny, shape)[point]
+    kw = _kw(tiny)
+    (loss, aux), grad = L.value_and_grad(L.loss_func, has_aux=True)(th, *tiny.args(), **kw)
+    l_ref, g_ref = O.value_and_grad(th, *tiny.args(), **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+    assert grad.shape == th.shape and grad.dtype == np.float64
+    assert set(aux) == {'final_loss', 'scaled_theta', 'mean_rel_corr', 'mean_rel_contrast', 'mean_rel_iwe_divergence',
+                        'theta_total_variation', 'multi_ref_weights'}       # losses.py:195-203
+
+
+@pytest.mark.parametrize('gamma,delta,lvl', [(0.0025, 0.0, 0), (0.0, 0.3, 2), (0.0025, 0.3, 0), (0.0025, 0.0, 3)])
+@pytest.mark.parametrize('shape', [(2, 2), (16, 16), (48, 64)])
+def test_regulariser_and_divergence_terms(L, tiny, gamma, delta, lvl, shape):
+    th = S.theta_test_points(tiny, shape)['perturbed']
+    kw = _kw(tiny, gamma=gamma, delta=delta, lvl=lvl)
+    loss, grad = L.value_and_grad(L.loss_func)(th, *tiny.args(), **kw)
+    l_ref, g_ref = O.value_and_grad(th, *tiny.args(), **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize('R', [1, 2, 3, 5])
+def test_loss_at_zero_theta_known_answer(L, R):
+    # loss(theta=0) = -(alpha+beta)/R
+    w = S.make_window(48, 64, 3000, edge_ts=np.linspace(0, 1, R) if R > 1 else (0.0,), seed=3)
+    loss, _ = L.loss_func(np.zeros((4, 4, 2)), *w.args(), **_kw(w))
+    assert loss == pytest.approx(-(20.0 + 35.0) / R, rel=1e-9)
+
+
+def test_intermediates_and_bit_exact_pixel_indices(L, tiny):
+    from eincm_b200 import plan as P
+    th = S.theta_test_points(tiny, (4, 4))['perturbed']
+    kw = _kw(tiny)
+    l_ref, g_ref, inter = O.value_and_grad(th, *tiny.args(), **kw, return_intermediates=True)
+    p = P.Plan(tiny.sensor_size, max_events=len(tiny.xs), max_refs=3)
+    p.set_window(*tiny.args())
+    loss, grad = p.value_and_grad_host(th, P.make_hparams(20.0, 35.0, 0.0, 0.0, 1))
+    np.testing.assert_allclose(p.zero_iwe().cpu().numpy(), inter['zero_iwe'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(p.iwe().cpu().numpy(), inter['iwes'], rtol=1e-6, atol=1e-9)
+    assert _rel_inf(p.dldi().cpu().numpy(), inter['dLdI']) <= 1e-5
+    np.testing.assert_allclose(p.theta_full().cpu().numpy(), inter['aux']['scaled_theta'], rtol=1e-13, atol=1e-13)
+    np.testing.assert_array_equal(p.event_mask().cpu().numpy().astype(bool), O.make_event_mask(tiny.xs, tiny.ys, tiny.sensor_size))
+    obj = inter['objectives']
+    for r in range(3):
+        cols, rows = p.rounded_pixels(r)
+        xr, yr = O.rounded_event_pixels(obj['warped_xs'][r], obj['warped_ys'][r])
+        np.testing.assert_array_equal(cols, xr.astype(np.int32))      # bit-exact event->pixel indexing
+        np.testing.assert_array_equal(rows, yr.astype(np.int32))
+    s = p.scalars()
+    np.testing.assert_allclose(s['contrasts'], obj['contrasts'], rtol=1e-6)
+    np.testing.assert_allclose(s['correlations'], obj['correlations'], rtol=1e-6)
+    np.testing.assert_allclose(s['zero_correlations'], obj['zero_correlations'], rtol=1e-6)
+    np.testing.assert_allclose(s['zero_contrast'], obj['zero_contrast'], rtol=1e-6)
+    np.testing.assert_allclose(s['multi_ref_weights'], obj['multi_ref_weights'], rtol=1e-14)
+    p.close()
+
+
+def test_handover(L, tiny):
+    pts = S.theta_test_points(tiny, (4, 4))
+    prev, cur = pts['truth'], pts['perturbed']
+    kw = _kw(tiny)
+    a0 = 0.37
+    loss, da = L.value_and_grad(L.handover_loss_func)(a0, prev, cur, *tiny.args(), **kw)
+    l_ref, da_ref = O.handover_value_and_grad(a0, prev, cur, *tiny.args(), **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert abs(da - da_ref) <= GRAD_RTOL * abs(da_ref)
+    assert L.handover_loss_func(a0, prev, cur, *tiny.args(), **kw) == pytest.approx(loss, rel=1e-9)
+
+
+def test_partial_binding_like_hydra(L, tiny):
+    # configs/theta_loss_func/default.yaml builds partial(loss_func, alpha=..., ...); solver.py:165 adds cur_pyr_lvl
+    pf = functools.partial(L.loss_func, alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, n_pyr_lvls=5,
+                           sensor_size=tiny.sensor_size, scale_to_sensor_size_method='bilinear')
+    th = S.theta_test_points(tiny, (2, 2))['truth']
+    f = functools.partial(pf, cur_pyr_lvl=3)
+    (loss, _), grad = L.value_and_grad(f, has_aux=True)(th, *tiny.args())
+    l_ref, g_ref = O.value_and_grad(th, *tiny.args(), **_kw(tiny, lvl=3))
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
+def test_wrap_quirk_and_far_out_of_sensor_warps(tiny):
+    """Events warped past the left/top border wrap (JAX negative-index normalisation); far ones are dropped."""
+    from eincm_b200 import plan as P
+    th = np.zeros((1, 1, 2)); th[..., 0] = 80.0; th[..., 1] = 60.0
+    kw = _kw(tiny)
+    for flags, wrap in ((0, True), (P.FLAG_NO_WRAP_NEGATIVE, False)):
+        p = P.Plan(tiny.sensor_size, max_events=len(tiny.xs), max_refs=3, flags=flags)
+        p.set_window(*tiny.args())
+        loss, grad = p.value_and_grad_host(th, P.make_hparams(20.0, 35.0, 0.0, 0.0, 1))
+        l_ref, g_ref = O.value_and_grad(th, *tiny.args(), **kw, wrap_negative=wrap)
+        assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+        assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+        p.close()
+
+
+def test_error_behaviour(tiny):
+    from eincm_b200 import plan as P
+    p = P.Plan(tiny.sensor_size, max_events=1000, max_refs=3)
+    hp = P.make_hparams(20.0, 35.0, 0.0, 0.0, 1)
+    with pytest.raises(P.EincmError) as e:
+        p.value_and_grad_host(np.zeros((1, 1, 2)), hp)            # before set_window
+    assert e.value.code == P.EINCM_ESTATE
+    with pytest.raises(P.EincmError) as e:
+        p.set_window(*tiny.args())                                  # more events than the plan holds
+    assert e.value.code == P.EINCM_EINVAL
+    xs = tiny.xs[:100].copy(); xs[5] = tiny.sensor_size[1]          # outside the sensor
+    with pytest.raises(P.EincmError) as e:
+        p.set_window(xs, tiny.ys[:100], tiny.ts[:100], tiny.edges, tiny.edge_ts)
+    assert e.value.code == P.EINCM_ERANGE
+    p.set_window(tiny.xs[:100], tiny.ys[:100], tiny.ts[:100], tiny.edges, tiny.edge_ts)
+    with pytest.raises(P.EincmError) as e:
+        p.value_and_grad_host(np.zeros((100, 100, 2)), hp)          # theta larger than the sensor
+    assert e.value.code == P.EINCM_EINVAL
+    with pytest.raises(P.EincmError):
+        P.make_hparams(1, 1, 0, 0, 0, scale_to_sensor_size_method='lanczos3')
+    p.close()
+
+
+def test_empty_window_and_single_event(tiny):
+    from eincm_b200 import plan as P
+    p = P.Plan(tiny.sensor_size, max_events=16, max_refs=3)
+    hp = P.make_hparams(20.0, 35.0, 0.0, 0.0, 1)
+    e16 = np.zeros(0, dtype=np.int16)
+    p.set_window(e16, e16, np.zeros(0), tiny.edges, tiny.edge_ts)
+    loss, grad = p.value_and_grad_host(np.ones((2, 2, 2)), hp)
+    l_ref, g_ref = O.value_and_grad(np.ones((2, 2, 2)), e16, e16, np.zeros(0), tiny.edges, tiny.edge_ts, **_kw(tiny))
+    assert (np.isnan(loss) and np.isnan(l_ref)) or abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert (grad == 0).all() or np.isnan(grad).all()
+    xs = np.array([10], dtype=np.int16); ys = np.array([20], dtype=np.int16); ts = np.array([0.3])
+    p.set_window(xs, ys, ts, tiny.edges, tiny.edge_ts)
+    th = np.full((1, 1, 2), 3.3)
+    loss, grad = p.value_and_grad_host(th, hp)
+    l_ref, g_ref = O.value_and_grad(th, xs, ys, ts, tiny.edges, tiny.edge_ts, **_kw(tiny))
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+    p.close()
+
+
+def test_stateless_host_form(tiny):
+    from eincm_b200 import plan as P
+    p = P.Plan(tiny.sensor_size, max_events=len(tiny.xs), max_refs=3)
+    th = S.theta_test_points(tiny, (4, 4))['truth']
+    loss, grad = p.value_and_grad_stateless_host(th, *tiny.args(), P.make_hparams(20.0, 35.0, 0.0, 0.0, 1))
+    l_ref, g_ref = O.value_and_grad(th, *tiny.args(), **_kw(tiny))
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+    p.close()
+
+
+@pytest.mark.parametrize('name,shape', [('mvsec_dt4', (16, 16)), ('mvsec_dt1', (8, 8)), ('ecd', (4, 4)), ('mvsec_outdoor', (16, 16)),
+                                        ('mvsec_raw_dt4', (16, 16))])
+def test_mvsec_shaped_windows(L, name, shape):
+    """BASELINE.json configs[2] (MVSEC-shaped, R = 2 / 5) at the reference's own N (oracle runs in seconds)."""
+    w = S.make_workload(name, seed=1)
+    th = S.theta_test_points(w, shape)['perturbed']
+    kw = dict(w.hparams, cur_pyr_lvl=0, n_pyr_lvls=5, sensor_size=w.sensor_size, scale_to_sensor_size_method='bilinear')
+    loss, grad = L.value_and_grad(L.loss_func)(th, *w.args(), **kw)
+    l_ref, g_ref = O.value_and_grad(th, *w.args(), **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
+def test_dense_theta_mvsec(L):
+    """BASELINE.json configs[2]: dense per-pixel flow (theta of shape (H, W, 2): identity resize)."""
+    w = S.make_workload('mvsec_dt1', seed=2)
+    th = S.theta_test_points(w, w.sensor_size)['perturbed']
+    kw = dict(w.hparams, cur_pyr_lvl=0, n_pyr_lvls=5, sensor_size=w.sensor_size, scale_to_sensor_size_method='bilinear')
+    kw['gamma'] = 0.0025
+    loss, grad = L.value_and_grad(L.loss_func)(th, *w.args(), **kw)
+    l_ref, g_ref = O.value_and_grad(th, *w.args(), **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
+def test_dsec_shaped_window_reduced_events(L):
+    """BASELINE.json configs[0]/[1] shape (640x480, R=3) at an event count the NumPy oracle finishes in seconds."""
+    w = S.make_workload('dsec_shipped', seed=0, n_events=200_000)
+    kw = dict(w.hparams, cur_pyr_lvl=0, n_pyr_lvls=5, sensor_size=w.sensor_size, scale_to_sensor_size_method='bilinear')
+    for shape in [(1, 1), (16, 16)]:
+        th = S.theta_test_points(w, shape)['perturbed']
+        loss, grad = L.value_and_grad(L.loss_func)(th, *w.args(), **kw)
+        l_ref, g_ref = O.value_and_grad(th, *w.args(), **kw)
+        assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+        assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
+def test_full_size_properties_dsec(L):
+    """Size-independent properties at BASELINE's full DSEC size (N = 1.5 M, too slow for the NumPy oracle):
+    loss(theta=0) = -(alpha+beta)/R exactly; splat mass conservation; event-split additivity of the IWE; the handover
+    gradient equals <grad, prev - theta>; determinism of repeated evaluations within tolerance."""
+    from eincm_b200 import plan as P
+    w = S.make_workload('dsec_shipped', seed=0)
+    N = len(w.xs)
+    hp = P.make_hparams(w.hparams['alpha'], w.hparams['beta'], 0.0, 0.0, 0)
+    p = P.Plan(w.sensor_size, max_events=N, max_refs=3)
+    p.set_window(*w.args())
+    loss0, g0 = p.value_and_grad_host(np.zeros((16, 16, 2)), hp)
+    assert loss0 == pytest.approx(-(w.hparams['alpha'] + w.hparams['beta']) / 3, rel=1e-9)
+    # interior mass: each in-sensor, non-border event contributes 0.7794836797093877
+    z = p.zero_iwe().cpu().numpy()
+    interior = (w.xs >= 1) & (w.xs < w.sensor_size[1] - 1) & (w.ys >= 1) & (w.ys < w.sensor_size[0] - 1)
+    lo = 0.7794836797093877 * interior.sum()
+    assert lo <= z.sum() * (1 + 1e-9) and z.sum() <= 0.7794836797093877 * N * (1 + 1e-9) + 1e-6
+    th = S.theta_test_points(w, (16, 16))['perturbed']
+    loss, grad = p.value_and_grad_host(th, hp)
+    iwe_full = p.iwe().cpu().numpy().copy()
+    loss_b, grad_b = p.value_and_grad_host(th, hp)
+    assert abs(loss - loss_b) <= 1e-9 * abs(loss) and _rel_inf(grad_b, grad) <= 1e-7
+    # handover: d/d alpha = <grad(theta_ho), prev - theta>
+    prev = S.theta_test_points(w, (16, 16))['truth']
+    a0 = 0.25
+    th_ho = a0 * prev + (1 - a0) * th
+    l_ho, da = p.handover_value_and_grad_host(a0, prev, th, hp)
+    l_dir, g_dir = p.value_and_grad_host(th_ho, hp)
+    assert l_ho == pytest.approx(l_dir, rel=1e-9)
+    assert da == pytest.approx(float((g_dir * (prev - th)).sum()), rel=1e-6)
+    # additivity: IWE(A u B) = IWE(A) + IWE(B)
+    acc = np.zeros_like(iwe_full)
+    for sl in (slice(0, None, 2), slice(1, None, 2)):
+        p.set_window(w.xs[sl], w.ys[sl], w.ts[sl], w.edges, w.edge_ts)
+        p.value_and_grad_host(th, hp, want_grad=False)
+        acc += p.iwe().cpu().numpy()
+    np.testing.assert_allclose(acc, iwe_full, rtol=1e-9, atol=1e-9)
+    p.close()
