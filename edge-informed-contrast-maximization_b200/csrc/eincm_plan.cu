@@ -19,6 +19,7 @@
 #include "k_prep.cuh"
 #include "k_theta.cuh"
 #include "k_events.cuh"
+#include "k_events9.cuh"
 #include "k_image.cuh"
 
 using namespace eincm;
@@ -39,7 +40,7 @@ struct eincm_plan {
     int device = 0, H = 0, W = 0, max_refs = 0, sm_count = 148;
     int64_t HW = 0, max_events = 0;
     unsigned flags = 0;
-    bool wrap = true;
+    bool wrap = true, exact = false;
     // window state
     int64_t n_events = 0;
     int R = 0;
@@ -59,6 +60,7 @@ struct eincm_plan {
     uint8_t* mask = nullptr;
     double2 *theta_full = nullptr, *Gtv = nullptr, *partial = nullptr;
     double *G = nullptr, *iwe = nullptr, *zero_iwe = nullptr, *dldi = nullptr, *edges = nullptr;
+    float *C9 = nullptr, *dldi32 = nullptr;            // fast path: moment records [R][H*W][12], float copy of dL/dIWE
     double *sbar = nullptr, *gNdiv = nullptr;          // delta != 0 only, allocated on first use
     double* part = nullptr;                            // per-CTA partials of the two-level reductions
     int part_doubles = 0;
@@ -232,6 +234,32 @@ int window_finalize_impl(eincm_plan* plan, cudaStream_t st) {
     return EINCM_OK;
 }
 
+// Builds n_img images of warped events (one per reference time in `tref`) from the staged events: exact mode = nine
+// float64 scatter-adds per event and image; fast mode = moment splat + compose (k_events9.cuh).
+int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const RefTimes& tref, double* out, const char* tag,
+                 cudaStream_t st) {
+    const int64_t n = plan->n_events;
+    const int H = plan->H, W = plan->W;
+    if (plan->exact) {
+        CU(cudaMemsetAsync(out, 0, (size_t)n_img * plan->HW * sizeof(double), st));
+        if (n > 0) {
+            const int grid = event_grid(plan, n, 256);
+            if (plan->wrap) LAUNCH(tag, k_splat<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, out));
+            else LAUNCH(tag, k_splat<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, out));
+        }
+        return EINCM_OK;
+    }
+    CU(cudaMemsetAsync(plan->C9, 0, (size_t)n_img * plan->HW * kRec * sizeof(float), st));
+    if (n > 0) {
+        const int grid = event_grid(plan, n, 256);
+        if (plan->wrap) LAUNCH(tag, k_splat9<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, plan->C9));
+        else LAUNCH(tag, k_splat9<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, plan->C9));
+    }
+    const dim3 grid((W + kCmpTX - 1) / kCmpTX, (H + kCmpTY - 1) / kCmpTY, n_img), block(kCmpTX, kCmpTY);
+    LAUNCH("k_compose9", k_compose9<<<grid, block, 0, st>>>(plan->C9, H, W, out));
+    return EINCM_OK;
+}
+
 int forward_events_impl(eincm_plan* plan, const double* theta, const double* prev, double a_ho, int h, int w,
                         const eincm_hparams* hp, cudaStream_t st) {
     int rc = check_hp(plan, hp);
@@ -247,16 +275,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
         const dim3 block(32, 8), grid((plan->W + 31) / 32, (plan->H + 7) / 8);
         LAUNCH("k_upsample_theta", k_upsample_theta<<<grid, block, 0, st>>>(theta, prev, a_ho, h, w, plan->H, plan->W, ty, tx, plan->theta_full));
     }
-    CU(cudaMemsetAsync(plan->iwe, 0, (size_t)plan->R * plan->HW * sizeof(double), st));
-    if (plan->n_events > 0) {
-        const int grid = event_grid(plan, plan->n_events, 256);
-        if (plan->wrap)
-            LAUNCH("k_splat", k_splat<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full, plan->H, plan->W,
-                                                                  plan->R, plan->tref, plan->iwe));
-        else
-            LAUNCH("k_splat", k_splat<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full, plan->H, plan->W,
-                                                                   plan->R, plan->tref, plan->iwe));
-    }
+    if ((rc = splat_images(plan, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
     plan->forward_done = true;
     return EINCM_OK;
@@ -298,16 +317,27 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     LAUNCH("k_scalars(1)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 1, loss_out));
     if (!want_grad) return EINCM_OK;
 
-    LAUNCH("k_img_C", k_img_C<<<gridT, block, 0, st>>>(plan->iwe, plan->edges, gNdiv, H, W, plan->sc->ref, plan->sc->coefA, plan->sc->coefB, plan->dldi));
+    LAUNCH("k_img_C", k_img_C<<<gridT, block, 0, st>>>(plan->iwe, plan->edges, gNdiv, H, W, plan->sc->ref, plan->sc->coefA, plan->sc->coefB, plan->dldi,
+                                                           plan->exact ? nullptr : plan->dldi32));
     CU(cudaMemsetAsync(plan->G, 0, (size_t)plan->HW * 2 * sizeof(double), st));
     if (plan->n_events > 0) {
         const int grid = event_grid(plan, plan->n_events, 256);
-        if (plan->wrap)
-            LAUNCH("k_backward_events", k_backward_events<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full,
-                                                                                      H, W, R, plan->tref, plan->dldi, plan->G));
-        else
-            LAUNCH("k_backward_events", k_backward_events<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->n_events, plan->theta_full,
-                                                                                       H, W, R, plan->tref, plan->dldi, plan->G));
+        const int64_t n = plan->n_events;
+        if (plan->exact) {
+            if (plan->wrap)
+                LAUNCH("k_backward_events", k_backward_events<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R,
+                                                                                          plan->tref, plan->dldi, plan->G));
+            else
+                LAUNCH("k_backward_events", k_backward_events<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R,
+                                                                                           plan->tref, plan->dldi, plan->G));
+        } else {
+            if (plan->wrap)
+                LAUNCH("k_backward_events", k_backward9<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R, plan->tref,
+                                                                                    plan->dldi32, plan->dldi, plan->G));
+            else
+                LAUNCH("k_backward_events", k_backward9<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R, plan->tref,
+                                                                                     plan->dldi32, plan->dldi, plan->G));
+        }
     }
     AxisTaps ty, tx;
     if ((rc = build_axis_taps(plan, h, H, &ty))) return rc;
@@ -363,6 +393,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     if (!plan) return fail(nullptr, EINCM_ENOMEM, "host allocation failed");
     plan->device = device; plan->H = H; plan->W = W; plan->HW = (int64_t)H * W; plan->max_events = max_events;
     plan->max_refs = max_refs; plan->flags = flags; plan->wrap = !(flags & EINCM_FLAG_NO_WRAP_NEGATIVE);
+    plan->exact = (flags & EINCM_FLAG_EXACT_F64) != 0;
     plan->sm_count = prop.multiProcessorCount;
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
     plan->n_keys = plan->tiles_x * ((H + kSortTile - 1) / kSortTile) * kSortTile * kSortTile;
@@ -379,6 +410,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->partial, (size_t)kGatherMaxTiles * 2 + (size_t)4 * plan->sm_count));
         CU(dmalloc(&plan->G, HW * 2)); CU(dmalloc(&plan->iwe, RR * HW)); CU(dmalloc(&plan->zero_iwe, HW));
         CU(dmalloc(&plan->dldi, RR * HW)); CU(dmalloc(&plan->edges, RR * HW));
+        if (!plan->exact) { CU(dmalloc(&plan->C9, RR * HW * kRec)); CU(dmalloc(&plan->dldi32, RR * HW)); }
         CU(dmalloc(&plan->part, (size_t)plan->part_doubles));
         CU(dmalloc(&plan->sc, 1));
         CU(cudaMemset(plan->sc, 0, sizeof(DevScalars)));
@@ -404,7 +436,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     cudaSetDevice(plan->device);
     void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->counts, plan->cursor, plan->block_sums, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
-                    plan->part, plan->sc, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
+                    plan->part, plan->sc, plan->C9, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& kv : plan->taps_cache) if (kv.second.blob) cudaFree(kv.second.blob);
@@ -468,14 +500,10 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     }
     CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
     // zero-warp IWE (losses.py:54): theta = 0 => x' = x for every reference time
-    CU(cudaMemsetAsync(plan->zero_iwe, 0, (size_t)plan->HW * sizeof(double), st));
-    if (n > 0) {
-        const int grid = event_grid(plan, n, 256);
+    {
         RefTimes z{};
-        if (plan->wrap)
-            LAUNCH("k_splat(zero)", k_splat<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, nullptr, plan->H, plan->W, 1, z, plan->zero_iwe));
-        else
-            LAUNCH("k_splat(zero)", k_splat<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, nullptr, plan->H, plan->W, 1, z, plan->zero_iwe));
+        int rc = splat_images(plan, nullptr, 1, z, plan->zero_iwe, "k_splat(zero)", st);
+        if (rc) return rc;
     }
     // validate (the reference's loaders guarantee in-sensor events; a violation would corrupt the gather at
     // event_warpers.py:34-35, so it is an error here).  One 4-byte read back per window.

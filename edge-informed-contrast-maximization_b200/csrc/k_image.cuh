@@ -142,7 +142,7 @@ k_img_B(const double* __restrict__ imgs, int64_t img_stride, const double* __res
 __global__ void __launch_bounds__(kImgNT)
 k_img_C(const double* __restrict__ imgs, const double* __restrict__ edges, const double* __restrict__ gNdiv, int H, int W,
         const Stats* __restrict__ stats, const double* __restrict__ coefA, const double* __restrict__ coefB,
-        double* __restrict__ dldi) {
+        double* __restrict__ dldi, float* __restrict__ dldi32 /* optional: (float)(dldi / 2 pi) for the fast backward */) {
     __shared__ double tile[kImgTY + 4][kImgTX + 4];
     __shared__ double gxs[kImgTY + 2][kImgTX + 2], gys[kImgTY + 2][kImgTX + 2];
     const int r = blockIdx.z;
@@ -175,6 +175,7 @@ k_img_C(const double* __restrict__ imgs, const double* __restrict__ edges, const
     if (I == st.mn) out += g_m / st.cnt_min;
     if (I == st.mx) out += g_M / st.cnt_max;
     dldi[r * HW + p] = out;
+    if (dldi32 != nullptr) dldi32[r * HW + p] = (float)(out * kInv2Pi);
 }
 
 // ---- D1: S = divk(Gx(N)) + divk(Gy(N)); div = mean|S|; sbar = coefD[r] * sign(S) (coefD may be NULL: forward only)

@@ -40,11 +40,12 @@ class _WindowCache:
         self.plans: Dict[Tuple[int, int, int, int], _plan.Plan] = {}
         self.staged: Dict[Tuple[int, int, int, int], Tuple] = {}
 
-    def plan_for(self, xs, ys, ts, edges, edge_ts, sensor_size, flags=0) -> _plan.Plan:
+    def plan_for(self, xs, ys, ts, edges, edge_ts, sensor_size, flags=None) -> _plan.Plan:
         import torch
         if not torch.cuda.is_available():
             raise _plan.EincmError(_plan.EINCM_ECUDA, 'no CUDA device: the EINCM objective runs only on a B200 (no CPU fallback)')
         dev = torch.cuda.current_device()
+        flags = _default_flags if flags is None else flags
         H, W = int(sensor_size[0]), int(sensor_size[1])
         key = (dev, H, W, int(flags))
         n = int(np.shape(xs)[0]) if not hasattr(xs, 'numel') else int(xs.numel())
@@ -71,6 +72,19 @@ class _WindowCache:
 
 
 _cache = _WindowCache()
+_default_flags = 0
+
+
+def configure(exact_f64: Optional[bool] = None, wrap_negative: Optional[bool] = None) -> int:
+    """Plan flags used by the module-level callables: ``exact_f64`` selects the float64 nine-tap scatter
+    (EINCM_FLAG_EXACT_F64) instead of the default float32 moment splat; ``wrap_negative=False`` drops votes with negative
+    row / column instead of wrapping them as JAX does (EINCM_FLAG_NO_WRAP_NEGATIVE).  Returns the flag word."""
+    global _default_flags
+    if exact_f64 is not None:
+        _default_flags = (_default_flags | _plan.FLAG_EXACT_F64) if exact_f64 else (_default_flags & ~_plan.FLAG_EXACT_F64)
+    if wrap_negative is not None:
+        _default_flags = (_default_flags & ~_plan.FLAG_NO_WRAP_NEGATIVE) if wrap_negative else (_default_flags | _plan.FLAG_NO_WRAP_NEGATIVE)
+    return _default_flags
 
 
 def clear_cache():

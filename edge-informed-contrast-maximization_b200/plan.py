@@ -19,6 +19,7 @@ EINCM_OK = 0
 EINCM_EINVAL, EINCM_ECUDA, EINCM_ENOMEM, EINCM_ESTATE, EINCM_ERANGE, EINCM_EUNSUPPORTED = -1, -2, -3, -4, -5, -6
 FLAG_NO_WRAP_NEGATIVE = 0x1
 FLAG_EVENT_SPLIT = 0x2
+FLAG_EXACT_F64 = 0x4
 METHOD_BILINEAR = 0
 S_HEADER = 8
 

@@ -46,6 +46,10 @@ extern "C" {
 #define EINCM_FLAG_NO_WRAP_NEGATIVE  0x1u  /* drop votes with negative row/col instead of wrapping them (JAX wraps: default) */
 #define EINCM_FLAG_EVENT_SPLIT       0x2u  /* this plan holds 1/G of a window's events: split-phase calls below */
 
+#define EINCM_FLAG_EXACT_F64         0x4u  /* nine float64 scatter-adds per event and image, float64 tap values (slower; matches the
+                                              float64 reference to ~1e-13).  Default: float32 moment splat with float64 coordinates
+                                              (bit-exact pixel indices, objective within ~1e-7 relative) */
+
 /* theta -> sensor-size resize method (reference configs/main.yaml:27 `scale_theta_to_sensor_size_method`) */
 #define EINCM_METHOD_BILINEAR 0
 

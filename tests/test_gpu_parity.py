@@ -51,6 +51,22 @@ def test_value_and_grad_matches_oracle(L, tiny, shape, point):
                         'theta_total_variation', 'multi_ref_weights'}       # losses.py:195-203
 
 
+@pytest.mark.parametrize('shape', [(1, 1), (4, 4), (16, 16), (48, 64)])
+@pytest.mark.parametrize('gamma,delta,lvl', [(0.0, 0.0, 1), (0.0025, 0.3, 0)])
+def test_exact_f64_mode_is_tight(L, tiny, shape, gamma, delta, lvl):
+    """EINCM_FLAG_EXACT_F64: float64 taps and scatter-adds - agrees with the float64 oracle to rounding."""
+    th = S.theta_test_points(tiny, shape)['perturbed']
+    kw = _kw(tiny, gamma=gamma, delta=delta, lvl=lvl)
+    L.configure(exact_f64=True)
+    try:
+        loss, grad = L.value_and_grad(L.loss_func)(th, *tiny.args(), **kw)
+    finally:
+        L.configure(exact_f64=False)
+    l_ref, g_ref = O.value_and_grad(th, *tiny.args(), **kw)
+    assert abs(loss - l_ref) <= 1e-11 * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= 1e-9
+
+
 @pytest.mark.parametrize('gamma,delta,lvl', [(0.0025, 0.0, 0), (0.0, 0.3, 2), (0.0025, 0.3, 0), (0.0025, 0.0, 3)])
 @pytest.mark.parametrize('shape', [(2, 2), (16, 16), (48, 64)])
 def test_regulariser_and_divergence_terms(L, tiny, gamma, delta, lvl, shape):
@@ -67,6 +83,13 @@ def test_loss_at_zero_theta_known_answer(L, R):
     # loss(theta=0) = -(alpha+beta)/R
     w = S.make_window(48, 64, 3000, edge_ts=np.linspace(0, 1, R) if R > 1 else (0.0,), seed=3)
     loss, _ = L.loss_func(np.zeros((4, 4, 2)), *w.args(), **_kw(w))
+    # float32 moment splat: border events take scalar float32 reductions whose order differs between the zero-IWE and IWE_r
+    assert loss == pytest.approx(-(20.0 + 35.0) / R, rel=1e-6)
+    L.configure(exact_f64=True)
+    try:
+        loss, _ = L.loss_func(np.zeros((4, 4, 2)), *w.args(), **_kw(w))
+    finally:
+        L.configure(exact_f64=False)
     assert loss == pytest.approx(-(20.0 + 35.0) / R, rel=1e-9)
 
 
@@ -107,7 +130,7 @@ def test_handover(L, tiny):
     l_ref, da_ref = O.handover_value_and_grad(a0, prev, cur, *tiny.args(), **kw)
     assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
     assert abs(da - da_ref) <= GRAD_RTOL * abs(da_ref)
-    assert L.handover_loss_func(a0, prev, cur, *tiny.args(), **kw) == pytest.approx(loss, rel=1e-9)
+    assert L.handover_loss_func(a0, prev, cur, *tiny.args(), **kw) == pytest.approx(loss, rel=1e-6)
 
 
 def test_partial_binding_like_hydra(L, tiny):
@@ -127,7 +150,8 @@ def test_wrap_quirk_and_far_out_of_sensor_warps(tiny):
     from eincm_b200 import plan as P
     th = np.zeros((1, 1, 2)); th[..., 0] = 80.0; th[..., 1] = 60.0
     kw = _kw(tiny)
-    for flags, wrap in ((0, True), (P.FLAG_NO_WRAP_NEGATIVE, False)):
+    for flags, wrap in ((0, True), (P.FLAG_NO_WRAP_NEGATIVE, False), (P.FLAG_EXACT_F64, True),
+                        (P.FLAG_EXACT_F64 | P.FLAG_NO_WRAP_NEGATIVE, False)):
         p = P.Plan(tiny.sensor_size, max_events=len(tiny.xs), max_refs=3, flags=flags)
         p.set_window(*tiny.args())
         loss, grad = p.value_and_grad_host(th, P.make_hparams(20.0, 35.0, 0.0, 0.0, 1))
@@ -239,7 +263,7 @@ def test_full_size_properties_dsec(L):
     p = P.Plan(w.sensor_size, max_events=N, max_refs=3)
     p.set_window(*w.args())
     loss0, g0 = p.value_and_grad_host(np.zeros((16, 16, 2)), hp)
-    assert loss0 == pytest.approx(-(w.hparams['alpha'] + w.hparams['beta']) / 3, rel=1e-9)
+    assert loss0 == pytest.approx(-(w.hparams['alpha'] + w.hparams['beta']) / 3, rel=1e-6)
     # interior mass: each in-sensor, non-border event contributes 0.7794836797093877
     z = p.zero_iwe().cpu().numpy()
     interior = (w.xs >= 1) & (w.xs < w.sensor_size[1] - 1) & (w.ys >= 1) & (w.ys < w.sensor_size[0] - 1)
@@ -249,20 +273,20 @@ def test_full_size_properties_dsec(L):
     loss, grad = p.value_and_grad_host(th, hp)
     iwe_full = p.iwe().cpu().numpy().copy()
     loss_b, grad_b = p.value_and_grad_host(th, hp)
-    assert abs(loss - loss_b) <= 1e-9 * abs(loss) and _rel_inf(grad_b, grad) <= 1e-7
+    assert abs(loss - loss_b) <= 1e-6 * abs(loss) and _rel_inf(grad_b, grad) <= 1e-5     # float32 atomics: run-to-run noise
     # handover: d/d alpha = <grad(theta_ho), prev - theta>
     prev = S.theta_test_points(w, (16, 16))['truth']
     a0 = 0.25
     th_ho = a0 * prev + (1 - a0) * th
     l_ho, da = p.handover_value_and_grad_host(a0, prev, th, hp)
     l_dir, g_dir = p.value_and_grad_host(th_ho, hp)
-    assert l_ho == pytest.approx(l_dir, rel=1e-9)
-    assert da == pytest.approx(float((g_dir * (prev - th)).sum()), rel=1e-6)
+    assert l_ho == pytest.approx(l_dir, rel=1e-6)
+    assert da == pytest.approx(float((g_dir * (prev - th)).sum()), rel=1e-4)
     # additivity: IWE(A u B) = IWE(A) + IWE(B)
     acc = np.zeros_like(iwe_full)
     for sl in (slice(0, None, 2), slice(1, None, 2)):
         p.set_window(w.xs[sl], w.ys[sl], w.ts[sl], w.edges, w.edge_ts)
         p.value_and_grad_host(th, hp, want_grad=False)
         acc += p.iwe().cpu().numpy()
-    np.testing.assert_allclose(acc, iwe_full, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(acc, iwe_full, rtol=1e-5, atol=1e-6)
     p.close()
