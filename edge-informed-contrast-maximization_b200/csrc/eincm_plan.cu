@@ -41,6 +41,7 @@ struct eincm_plan {
     int64_t HW = 0, max_events = 0;
     unsigned flags = 0;
     bool wrap = true, exact = false;
+    int split_rank = 0, split_world = 1;   // event-split plans: rank 0 alone adds the (replicated) TV gradient
     // window state
     int64_t n_events = 0;
     int R = 0;
@@ -342,7 +343,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     AxisTaps ty, tx;
     if ((rc = build_axis_taps(plan, h, H, &ty))) return rc;
     if ((rc = build_axis_taps(plan, w, W, &tx))) return rc;
-    const double2* Gtv = use_tv ? plan->Gtv : nullptr;
+    const double2* Gtv = (use_tv && plan->split_rank == 0) ? plan->Gtv : nullptr;
     const int n_el = h * w;
     CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
     const bool handover = plan->last_prev != nullptr;
@@ -662,6 +663,14 @@ int eincm_get_scalars(eincm_plan* plan, double* out_host, int n_doubles, void* c
         out_host[EINCM_S_PER_REF + 3 * M + r] = live ? hs->ref[r].div : 0.0;
         out_host[EINCM_S_PER_REF + 4 * M + r] = live ? hs->weights[r] : 0.0;
     }
+    return EINCM_OK;
+}
+
+int eincm_plan_set_event_split(eincm_plan* plan, int rank, int world) {
+    if (!plan) return EINCM_EINVAL;
+    if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return fail(plan, EINCM_ESTATE, "plan was not created with EINCM_FLAG_EVENT_SPLIT");
+    if (world < 1 || rank < 0 || rank >= world) return fail(plan, EINCM_EINVAL, "rank %d outside 0..%d", rank, world - 1);
+    plan->split_rank = rank; plan->split_world = world;
     return EINCM_OK;
 }
 

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     'eincm_handover_value_and_grad_host', 'eincm_value_and_grad_stateless_host', 'eincm_window_finalize',
     'eincm_forward_events', 'eincm_backward', 'eincm_zero_iwe_ptr', 'eincm_iwe_ptr', 'eincm_dldi_ptr',
     'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
-    'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
+    'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
 )
 
 
@@ -89,6 +89,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_mask_ptr': (vp, [vp]),
         'eincm_get_scalars': (i32, [vp, C.POINTER(dbl), i32, vp]),
         'eincm_debug_rounded_pixels': (i32, [vp, i32, vp, vp, vp]),
+        'eincm_plan_set_event_split': (i32, [vp, i32, i32]),
         'eincm_plan_launch_count': (i64, [vp]),
         'eincm_plan_set_timing': (i32, [vp, i32]),
         'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
@@ -188,6 +189,9 @@ class Plan:
                                                    edges_d.data_ptr(), ets.ctypes.data_as(C.POINTER(C.c_double)), R,
                                                    _stream_ptr(stream)))
         self.n_events, self.n_refs = n, R
+
+    def set_event_split(self, rank: int, world: int):
+        self._check(self.lib.eincm_plan_set_event_split(self._h, int(rank), int(world)))
 
     def window_finalize(self, stream=None):
         self._check(self.lib.eincm_window_finalize(self._h, _stream_ptr(stream)))

@@ -138,6 +138,9 @@ int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_ho
  * The collective itself is the caller's (torch.distributed / NCCL over NVLink); these functions only expose
  * the buffers.  Without the flag, set_window / value_and_grad run all phases back to back. */
 int eincm_window_finalize(eincm_plan* plan, void* cuda_stream);
+/* Position of this plan in the split: the gradient of terms that are replicated on every rank (the TV regulariser, which
+ * depends on theta and the all-reduced mask only) is added by rank 0 alone, so that all-reduce(sum) of grad_out is exact. */
+int eincm_plan_set_event_split(eincm_plan* plan, int rank, int world);
 int eincm_forward_events(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, void* cuda_stream);
 int eincm_backward(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, void* cuda_stream);
 double* eincm_zero_iwe_ptr(eincm_plan* plan);   /* device, [H*W] float64 */

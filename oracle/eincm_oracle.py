@@ -480,3 +480,82 @@ def handover_value_and_grad(alpha_handover, prev_theta, theta, xs, ys, ts, edges
                              cur_pyr_lvl, n_pyr_lvls, sensor_size, scale_to_sensor_size_method,
                              wrap_negative=wrap_negative)
     return loss, float((g * (prev_theta - theta)).sum())
+
+
+# --------------------------------------------------------------------------- #
+# event-split restatement: the same arithmetic as value_and_grad, phrased over
+# COMPLETE images (sums over all ranks) and LOCAL events.  Used by the gloo tests of
+# eincm_b200.parallel.EventSplitObjective; tests pin it to value_and_grad.
+# --------------------------------------------------------------------------- #
+def partial_images(theta, xs, ys, ts, edge_ts, sensor_size, wrap_negative=True):
+    """Local contribution to the R images of warped events (additive over event subsets)."""
+    sensor_size = tuple(sensor_size)
+    theta_full = scale_theta_to_sensor_size(np.asarray(theta, dtype=np.float64), sensor_size)
+    out = []
+    for t_ref in np.asarray(edge_ts, dtype=np.float64):
+        xw, yw = per_pix_warp(theta_full, xs, ys, ts, t_ref, 1.0)
+        out.append(events_to_pdf_frame(xw, yw, sensor_size, wrap_negative=wrap_negative))
+    return np.stack(out)
+
+
+def split_value_and_grad(theta, iwes, zero_iwe, mask, xs, ys, ts, edges, edge_ts, alpha, beta, gamma, delta,
+                         cur_pyr_lvl, n_pyr_lvls, sensor_size, include_replicated_grad=True, wrap_negative=True):
+    """(loss, partial grad): loss from the complete images ``iwes`` / ``zero_iwe`` / ``mask``; gradient contribution of the
+    LOCAL events ``xs, ys, ts`` (plus, if ``include_replicated_grad``, the TV term that is identical on every rank)."""
+    theta = np.asarray(theta, dtype=np.float64)
+    sensor_size = tuple(sensor_size)
+    H, W = sensor_size
+    HW = float(H * W)
+    edges = np.asarray(edges, dtype=np.float64)
+    edge_ts = np.asarray(edge_ts, dtype=np.float64)
+    ts = np.asarray(ts, dtype=np.float64)
+    R = len(edge_ts)
+    theta_full = scale_theta_to_sensor_size(theta, sensor_size)
+    w = compute_weights_for_multi_reference(R)
+    nz0 = normalize_to_unit_range(zero_iwe)
+    C0 = compute_mean_gradient_magnitude(zero_iwe)
+    M0 = np.array([compute_mean_squared_error(edges[r], nz0) for r in range(R)])
+    D0 = iwe_divergence(nz0)
+    nrm = np.stack([normalize_to_unit_range(i) for i in iwes])
+    contrasts = np.array([compute_mean_gradient_magnitude(i) for i in iwes])
+    corrs = -np.array([compute_mean_squared_error(edges[r], nrm[r]) for r in range(R)])
+    divs = np.array([iwe_divergence(n) for n in nrm])
+    use_tv = cur_pyr_lvl <= 0
+    tv = 0.0
+    if use_tv:
+        flow = theta_full * mask[..., None]
+        a, b, c, d = _tv_fields(flow)
+        nzp = (np.abs(a) > 0) | (np.abs(b) > 0) | (np.abs(c) > 0) | (np.abs(d) > 0)
+        tv = float(np.sum((np.abs(a) * 0.25 + np.abs(b) * 0.25) + (np.abs(c) * 0.25 + np.abs(d) * 0.25)) / (nzp.sum() + EPSN))
+    mean_rel_corr = ((w * corrs) / (-M0 + EPSN)).mean()
+    mean_rel_contrast = ((w * contrasts) / (C0 + EPSN)).mean()
+    mean_rel_div = ((w * divs) / (D0 + EPSN)).mean()
+    loss = (alpha * (-mean_rel_contrast) + beta * (-mean_rel_corr)) + (gamma * tv + delta * mean_rel_div)
+
+    xi = np.rint(xs).astype(np.int64)
+    yi = np.rint(ys).astype(np.int64)
+    G_full = np.zeros((H, W, 2), dtype=np.float64)
+    for r in range(R):
+        a_r = -alpha * w[r] / ((C0 + EPSN) * R)
+        b_r = beta * w[r] / ((-M0[r] + EPSN) * R)
+        d_r = delta * w[r] / ((D0 + EPSN) * R)
+        I = iwes[r]
+        g = sobel_scharr_optimized_image_grads(I)
+        dI = a_r * (2.0 / HW) * _scharr_adjoint(g[..., 0], g[..., 1])
+        gN = b_r * (-2.0 / HW) * (edges[r] - nrm[r])
+        if delta != 0.0:
+            sbar = d_r * np.sign(_iwe_div_field(nrm[r])) / HW
+            kbar = _div_kern_adjoint(sbar)
+            gN = gN + _scharr_adjoint(kbar, kbar)
+        dI = dI + _minmax_normalize_backward(I, gN)
+        xw, yw = per_pix_warp(theta_full, xs, ys, ts, edge_ts[r], 1.0)
+        gx, gy = splat_backward(xw, yw, dI, wrap_negative)
+        dts = ts - edge_ts[r]
+        np.add.at(G_full[..., 0], (yi, xi), -dts * gx)
+        np.add.at(G_full[..., 1], (yi, xi), -dts * gy)
+    if gamma != 0.0 and use_tv and include_replicated_grad:
+        k = gamma * 0.25 / (nzp.sum() + EPSN)
+        G_full[..., 0] += k * _scharr_adjoint(np.sign(a), np.sign(b)) * mask
+        G_full[..., 1] += k * _scharr_adjoint(np.sign(c), np.sign(d)) * mask
+    Wy, Wx = resize_weights(theta.shape[:2], sensor_size)
+    return float(loss), np.einsum('yxc,iy,jx->ijc', G_full, Wy, Wx, optimize=True)

@@ -1,0 +1,100 @@
+"""Event-split evaluation of one window on real plans: (a) two plans on ONE GPU with the all-reduce done by hand,
+(b) two ranks on two GPUs over NCCL (skipped with fewer than 2 devices)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import eincm_b200.synth as S
+from oracle import eincm_oracle as O
+
+pytestmark = pytest.mark.gpu
+HP = dict(alpha=20.0, beta=35.0, gamma=0.0025, delta=0.0)
+
+
+def test_two_split_plans_on_one_gpu_match_oracle():
+    import torch
+    from eincm_b200 import parallel as PAR, plan as P
+    w = S.make_workload('tiny', seed=2)
+    th = S.theta_test_points(w, (4, 4))['perturbed']
+    hp = P.make_hparams(**HP, cur_pyr_lvl=0)
+    plans = []
+    for r in range(2):
+        p = P.Plan(w.sensor_size, max_events=len(w.xs), max_refs=3, flags=P.FLAG_EVENT_SPLIT)
+        p.set_event_split(r, 2)
+        p.set_window(*PAR.split_events(w.xs, w.ys, w.ts, 2, r), w.edges, w.edge_ts)
+        plans.append(p)
+    z = plans[0].zero_iwe() + plans[1].zero_iwe()
+    m = torch.maximum(plans[0].event_mask(), plans[1].event_mask())
+    for p in plans:
+        p.zero_iwe().copy_(z); p.event_mask().copy_(m); p.window_finalize()
+    th_d = torch.from_numpy(th).cuda()
+    for p in plans:
+        p.forward_events(th_d, hp)
+    iwe = plans[0].iwe() + plans[1].iwe()
+    losses, grads = [], []
+    for p in plans:
+        p.iwe().copy_(iwe)
+        lo = torch.zeros(1, dtype=torch.float64, device='cuda'); g = torch.zeros_like(th_d)
+        p.backward(hp, lo, g)
+        losses.append(lo); grads.append(g)
+    torch.cuda.synchronize()
+    l_ref, g_ref = O.value_and_grad(th, *w.args(), **HP, cur_pyr_lvl=0, n_pyr_lvls=5, sensor_size=w.sensor_size)
+    for lo in losses:
+        assert abs(float(lo[0]) - l_ref) <= 1e-5 * abs(l_ref)
+    g = (grads[0] + grads[1]).cpu().numpy()
+    assert np.abs(g - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
+    # a split plan refuses the fused single-GPU call
+    with pytest.raises(P.EincmError):
+        plans[0].value_and_grad_host(th, hp)
+    for p in plans:
+        p.close()
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from eincm_b200 import parallel as PAR, plan as P
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        w = S.make_workload('mvsec_dt4', seed=5)
+        th = S.theta_test_points(w, (16, 16))['perturbed']
+        xs, ys, ts = PAR.split_events(w.xs, w.ys, w.ts, world, rank)
+        p = P.Plan(w.sensor_size, max_events=len(w.xs), max_refs=5, flags=P.FLAG_EVENT_SPLIT)
+        obj = PAR.EventSplitObjective(p, lambda lvl: P.make_hparams(**HP, cur_pyr_lvl=lvl))
+        obj.set_datasample(xs, ys, ts, w.edges, w.edge_ts)
+        loss, grad = obj.value_and_grad(torch.from_numpy(th).cuda(), 0)
+        torch.cuda.synchronize()
+        q.put((rank, float(loss[0]), grad.cpu().numpy().copy()))
+        dist.barrier()
+        p.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_event_split_two_gpus_nccl():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    world = 2
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w = S.make_workload('mvsec_dt4', seed=5)
+    th = S.theta_test_points(w, (16, 16))['perturbed']
+    l_ref, g_ref = O.value_and_grad(th, *w.args(), **HP, cur_pyr_lvl=0, n_pyr_lvls=5, sensor_size=w.sensor_size)
+    for rank, loss, grad in res:
+        assert abs(loss - l_ref) <= 1e-5 * abs(l_ref)
+        assert np.abs(grad - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
