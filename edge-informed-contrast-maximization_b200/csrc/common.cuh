@@ -30,6 +30,7 @@ struct DevScalars {
     double coefA[EINCM_MAX_REFS]; // a_r * 2/HW   (contrast cotangent scale)
     double coefB[EINCM_MAX_REFS]; // b_r * -2/HW  (correlation cotangent scale)
     double coefD[EINCM_MAX_REFS]; // d_r / HW     (divergence cotangent scale)
+    double sumE[EINCM_MAX_REFS], sumE2[EINCM_MAX_REFS];   // per-window sums of edge_r and edge_r^2 (fused image pass)
     unsigned int counters[16];    // "last block done" tickets
     int error_flag;               // set by kernels on invalid input (event outside the sensor)
 };

@@ -21,6 +21,7 @@
 #include "k_events.cuh"
 #include "k_events9.cuh"
 #include "k_image.cuh"
+#include "k_image_fused.cuh"
 
 using namespace eincm;
 
@@ -46,6 +47,7 @@ struct eincm_plan {
     int64_t n_events = 0;
     int R = 0;
     bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
+    bool fused_pending = false;   // the last forward left the moment records un-composed for the fused image pass
     RefTimes tref{};
     // last evaluation
     int last_h = 0, last_w = 0;
@@ -235,10 +237,17 @@ int window_finalize_impl(eincm_plan* plan, cudaStream_t st) {
     return EINCM_OK;
 }
 
+int compose_images(eincm_plan* plan, int n_img, double* out, cudaStream_t st) {
+    const int H = plan->H, W = plan->W;
+    const dim3 grid((W + kCmpTX - 1) / kCmpTX, (H + kCmpTY - 1) / kCmpTY, n_img), block(kCmpTX, kCmpTY);
+    LAUNCH("k_compose9", k_compose9<<<grid, block, 0, st>>>(plan->C9, H, W, out));
+    return EINCM_OK;
+}
+
 // Builds n_img images of warped events (one per reference time in `tref`) from the staged events: exact mode = nine
 // float64 scatter-adds per event and image; fast mode = moment splat + compose (k_events9.cuh).
 int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const RefTimes& tref, double* out, const char* tag,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool compose = true) {
     const int64_t n = plan->n_events;
     const int H = plan->H, W = plan->W;
     if (plan->exact) {
@@ -256,9 +265,8 @@ int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const R
         if (plan->wrap) LAUNCH(tag, k_splat9<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, plan->C9));
         else LAUNCH(tag, k_splat9<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, plan->C9));
     }
-    const dim3 grid((W + kCmpTX - 1) / kCmpTX, (H + kCmpTY - 1) / kCmpTY, n_img), block(kCmpTX, kCmpTY);
-    LAUNCH("k_compose9", k_compose9<<<grid, block, 0, st>>>(plan->C9, H, W, out));
-    return EINCM_OK;
+    if (!compose) return EINCM_OK;
+    return compose_images(plan, n_img, out, st);
 }
 
 int forward_events_impl(eincm_plan* plan, const double* theta, const double* prev, double a_ho, int h, int w,
@@ -276,7 +284,9 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
         const dim3 block(32, 8), grid((plan->W + 31) / 32, (plan->H + 7) / 8);
         LAUNCH("k_upsample_theta", k_upsample_theta<<<grid, block, 0, st>>>(theta, prev, a_ho, h, w, plan->H, plan->W, ty, tx, plan->theta_full));
     }
-    if ((rc = splat_images(plan, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st))) return rc;
+    // default path (float32 moments, single GPU, delta == 0): the records are composed inside the fused image pass
+    plan->fused_pending = !plan->exact && !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && hp->delta == 0.0;
+    if ((rc = splat_images(plan, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
     plan->forward_done = true;
     return EINCM_OK;
@@ -294,32 +304,52 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     const dim3 block(kImgTX, kImgTY);
     const dim3 gridT(img_tiles_x(plan), img_tiles_y(plan), R);
     const int nbT = gridT.x * gridT.y;
-    if (use_div) {
-        if ((rc = ensure_zero_div(plan, st))) return rc;
+    if (plan->fused_pending && use_div) {        // hparams changed between the split-phase calls: fall back to the unfused pass
+        if ((rc = compose_images(plan, R, plan->iwe, st))) return rc;
+        plan->fused_pending = false;
     }
-    LAUNCH("k_img_A", k_img_A<<<gridT, block, 0, st>>>(plan->iwe, H, W, nbT, plan->part, plan->sc->ref, &plan->sc->counters[0]));
-    LAUNCH("k_scalars(0)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 0, nullptr));
-    const double* gNdiv = nullptr;
-    if (use_div) {
-        LAUNCH("k_img_D1", k_img_D1<<<gridT, block, 0, st>>>(plan->iwe, plan->HW, H, W, nbT, plan->sc->ref, 1, plan->sc->coefD, plan->sbar, plan->part,
-                                          plan->sc->ref, &plan->sc->counters[2]));
-        if (want_grad) {
-            LAUNCH("k_img_D2", k_img_D2<<<gridT, block, 0, st>>>(plan->sbar, H, W, plan->gNdiv));
-            gNdiv = plan->gNdiv;
+    if (plan->fused_pending) {
+        if (use_tv) {
+            const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
+            LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
         }
-    }
-    const int nbF = img_nb_flat(plan);
-    LAUNCH("k_img_B", k_img_B<<<dim3(nbF, 1, R), block, 0, st>>>(plan->iwe, plan->HW, plan->edges, gNdiv, plan->HW, nbF, plan->sc->ref, 1,
-                                               plan->sc->coefB, plan->part, plan->sc->ref, &plan->sc->counters[1]));
-    if (use_tv) {
-        const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
-        LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
-    }
-    LAUNCH("k_scalars(1)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 1, loss_out));
-    if (!want_grad) return EINCM_OK;
+        const dim3 gridF((W + kFTX - 1) / kFTX, (H + kFTY - 1) / kFTY, R), blockF(kFTX, 8);
+        const int nbF1 = gridF.x * gridF.y;
+        const int tvb = ((W + kTvTX - 1) / kTvTX) * ((H + kTvTY - 1) / kTvTY);
+        double* partF = plan->part + 2 * tvb;                    // k_tv's partials live at the start of `part`
+        LAUNCH("k_img_fused1", k_img_fused1<<<gridF, blockF, 0, st>>>(plan->C9, plan->edges, H, W, nbF1, plan->iwe, partF, plan->sc,
+                                                                      hp->alpha, hp->beta, hp->gamma, use_tv ? 1 : 0, loss_out));
+        plan->fused_pending = false;
+        if (!want_grad) return EINCM_OK;
+        LAUNCH("k_img_fused3", k_img_fused3<<<gridF, blockF, 0, st>>>(plan->iwe, plan->edges, H, W, plan->sc, plan->dldi, plan->dldi32));
+    } else {
+        if (use_div) {
+            if ((rc = ensure_zero_div(plan, st))) return rc;
+        }
+        LAUNCH("k_img_A", k_img_A<<<gridT, block, 0, st>>>(plan->iwe, H, W, nbT, plan->part, plan->sc->ref, &plan->sc->counters[0]));
+        LAUNCH("k_scalars(0)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 0, nullptr));
+        const double* gNdiv = nullptr;
+        if (use_div) {
+            LAUNCH("k_img_D1", k_img_D1<<<gridT, block, 0, st>>>(plan->iwe, plan->HW, H, W, nbT, plan->sc->ref, 1, plan->sc->coefD, plan->sbar, plan->part,
+                                              plan->sc->ref, &plan->sc->counters[2]));
+            if (want_grad) {
+                LAUNCH("k_img_D2", k_img_D2<<<gridT, block, 0, st>>>(plan->sbar, H, W, plan->gNdiv));
+                gNdiv = plan->gNdiv;
+            }
+        }
+        const int nbF = img_nb_flat(plan);
+        LAUNCH("k_img_B", k_img_B<<<dim3(nbF, 1, R), block, 0, st>>>(plan->iwe, plan->HW, plan->edges, gNdiv, plan->HW, nbF, plan->sc->ref, 1,
+                                                   plan->sc->coefB, plan->part, plan->sc->ref, &plan->sc->counters[1]));
+        if (use_tv) {
+            const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
+            LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
+        }
+        LAUNCH("k_scalars(1)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 1, loss_out));
+        if (!want_grad) return EINCM_OK;
 
-    LAUNCH("k_img_C", k_img_C<<<gridT, block, 0, st>>>(plan->iwe, plan->edges, gNdiv, H, W, plan->sc->ref, plan->sc->coefA, plan->sc->coefB, plan->dldi,
-                                                           plan->exact ? nullptr : plan->dldi32));
+        LAUNCH("k_img_C", k_img_C<<<gridT, block, 0, st>>>(plan->iwe, plan->edges, gNdiv, H, W, plan->sc->ref, plan->sc->coefA, plan->sc->coefB, plan->dldi,
+                                                               plan->exact ? nullptr : plan->dldi32));
+    }
     CU(cudaMemsetAsync(plan->G, 0, (size_t)plan->HW * 2 * sizeof(double), st));
     if (plan->n_events > 0) {
         const int grid = event_grid(plan, plan->n_events, 256);
@@ -401,7 +431,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     plan->n_scan_blocks = (plan->n_keys + kScanBlock - 1) / kScanBlock;
     const size_t HW = (size_t)plan->HW, NE = (size_t)max_events, RR = (size_t)max_refs;
     const int nbT = img_tiles_x(plan) * img_tiles_y(plan);
-    plan->part_doubles = 8 * max_refs * std::max(nbT, plan->sm_count * 4) + 64;
+    plan->part_doubles = 10 * max_refs * std::max(nbT, plan->sm_count * 4) + 4096;
     auto body = [&]() -> int {
         CU(dmalloc(&plan->ev_xy, NE)); CU(dmalloc(&plan->ev_t, NE)); CU(dmalloc(&plan->perm, NE));
         CU(dmalloc(&plan->counts, (size_t)plan->n_keys)); CU(dmalloc(&plan->cursor, (size_t)plan->n_keys));
@@ -467,6 +497,7 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     if ((n > 0 && (!xs || !ys || !ts)) || !edges || !edge_ts_host) return fail(plan, EINCM_EINVAL, "NULL operand");
     CU(cudaSetDevice(plan->device));
     plan->window_set = false; plan->window_final = false; plan->forward_done = false; plan->zero_div_valid = false;
+    plan->fused_pending = false;
     plan->n_events = n; plan->R = R;
     for (int r = 0; r < EINCM_MAX_REFS; ++r) plan->tref.t[r] = r < R ? edge_ts_host[r] : 0.0;
 
@@ -500,6 +531,7 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
         LAUNCH("k_scatter_events", k_scatter_events<<<grid, 256, 0, st>>>(xs, ys, ts, n, plan->H, plan->W, plan->tiles_x, plan->cursor, plan->ev_xy, plan->ev_t, plan->perm));
     }
     CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc));
     // zero-warp IWE (losses.py:54): theta = 0 => x' = x for every reference time
     {
         RefTimes z{};

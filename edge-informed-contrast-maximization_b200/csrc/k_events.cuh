@@ -15,8 +15,8 @@ struct Warped { double xw, yw; int rx, ry; bool ok; };
 // event_warpers.py:34-35 followed by event_utils.py:33 (jnp.round = half-to-even -> cvt.rni)
 __device__ __forceinline__ Warped warp_event(int x, int y, double thx, double thy, double dt) {
     Warped o;
-    o.xw = __dsub_rn((double)x, __dmul_rn(__dmul_rn(thx, dt), 1.0));
-    o.yw = __dsub_rn((double)y, __dmul_rn(__dmul_rn(thy, dt), 1.0));
+    o.xw = __dsub_rn((double)x, __dmul_rn(thx, dt));   // (theta*dt)*1.0 == theta*dt exactly (delta_time = 1.0)
+    o.yw = __dsub_rn((double)y, __dmul_rn(thy, dt));
     // NaN / inf / absurdly far warps: every tap is out of range under either index rule -> dropped
     o.ok = (fabs(o.xw) < 1.0e9) && (fabs(o.yw) < 1.0e9);
     o.rx = o.ok ? __double2int_rn(o.xw) : 0;

@@ -44,42 +44,61 @@ __device__ __forceinline__ void moments9(float fx, float fy, float m[9]) {
 // ---- forward: warp + moment splat ------------------------------------------------------------------------------
 // theta_full == nullptr: zero flow (the un-warped image of events, losses.py:54).
 template <bool WRAP>
-__global__ void __launch_bounds__(256)
-k_splat9(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, int64_t n,
-         const double2* __restrict__ theta_full, int H, int W, int R, RefTimes tref, float* __restrict__ C /* [R][H*W][kRec] */) {
-    const int64_t HW = (int64_t)H * W;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t xy = ev_xy[e];
-        const double t = ev_t[e];
-        const int x = xy & 0xffffu, y = xy >> 16;
-        const double2 th = theta_full != nullptr ? theta_full[y * W + x] : make_double2(0.0, 0.0);
-        for (int r = 0; r < R; ++r) {
-            const Warped wp = warp_event(x, y, th.x, th.y, t - tref.t[r]);
-            if (!wp.ok) continue;
-            const float fx = (float)(wp.xw - (double)wp.rx), fy = (float)(wp.yw - (double)wp.ry);
-            float* Cr = C + (int64_t)r * HW * kRec;
-            if (wp.rx >= 1 && wp.rx <= W - 2 && wp.ry >= 1 && wp.ry <= H - 2) {
-                float m[9];
-                moments9(fx, fy, m);
-                float* rec = Cr + ((int64_t)wp.ry * W + wp.rx) * kRec;
-                red_add_v4(rec, m[0], m[1], m[2], m[3]);
-                red_add_v4(rec + 4, m[4], m[5], m[6], m[7]);
-                red_add_f32(rec + 8, m[8]);
-            } else {
-                // slow path: the reference's per-tap index rule; value 2 pi v_ij goes to channel (0,0) of the destination
+__device__ __forceinline__ void splat9_event(int x, int y, double t, double2 th, int H, int W, int R, const RefTimes& tref,
+                                             float* __restrict__ C, int64_t HW) {
+    for (int r = 0; r < R; ++r) {
+        const Warped wp = warp_event(x, y, th.x, th.y, t - tref.t[r]);
+        if (!wp.ok) continue;
+        const float fx = (float)(wp.xw - (double)wp.rx), fy = (float)(wp.yw - (double)wp.ry);
+        float* Cr = C + (int64_t)r * HW * kRec;
+        if (wp.rx >= 1 && wp.rx <= W - 2 && wp.ry >= 1 && wp.ry <= H - 2) {
+            float m[9];
+            moments9(fx, fy, m);
+            float* rec = Cr + ((int64_t)wp.ry * W + wp.rx) * kRec;
+            red_add_v4(rec, m[0], m[1], m[2], m[3]);
+            red_add_v4(rec + 4, m[4], m[5], m[6], m[7]);
+            red_add_f32(rec + 8, m[8]);
+        } else {
+            // slow path: the reference's per-tap index rule; value 2 pi v_ij goes to channel (0,0) of the destination
 #pragma unroll
-                for (int i = -1; i <= 1; ++i) {
+            for (int i = -1; i <= 1; ++i) {
 #pragma unroll
-                    for (int j = -1; j <= 1; ++j) {
-                        int rr = wp.ry + j, cc = wp.rx + i;
-                        if (drop_index<WRAP>(rr, cc, H, W)) {
-                            const float qx = (float)i - fx, qy = (float)j - fy;
-                            red_add_f32(Cr + ((int64_t)rr * W + cc) * kRec + 4, __expf(-0.5f * (qx * qx + qy * qy)));
-                        }
+                for (int j = -1; j <= 1; ++j) {
+                    int rr = wp.ry + j, cc = wp.rx + i;
+                    if (drop_index<WRAP>(rr, cc, H, W)) {
+                        const float qx = (float)i - fx, qy = (float)j - fy;
+                        red_add_f32(Cr + ((int64_t)rr * W + cc) * kRec + 4, __expf(-0.5f * (qx * qx + qy * qy)));
                     }
                 }
             }
         }
+    }
+}
+
+// Two events per thread and iteration: both events' loads (packed coordinates, timestamp, then the dependent flow gather)
+// are issued before any arithmetic, doubling the memory-level parallelism of a loop that is otherwise latency bound.
+template <bool WRAP>
+__global__ void __launch_bounds__(256)
+k_splat9(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, int64_t n,
+         const double2* __restrict__ theta_full, int H, int W, int R, const __grid_constant__ RefTimes tref,
+         float* __restrict__ C /* [R][H*W][kRec] */) {
+    const int64_t HW = (int64_t)H * W;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e0 < n; e0 += 2 * stride) {
+        const int64_t e1 = e0 + stride;
+        const bool has1 = e1 < n;
+        const uint32_t xy0 = ev_xy[e0];
+        const uint32_t xy1 = has1 ? ev_xy[e1] : 0u;
+        const double t0 = ev_t[e0];
+        const double t1 = has1 ? ev_t[e1] : 0.0;
+        const int x0 = xy0 & 0xffffu, y0 = xy0 >> 16, x1 = xy1 & 0xffffu, y1 = xy1 >> 16;
+        double2 th0 = make_double2(0.0, 0.0), th1 = make_double2(0.0, 0.0);
+        if (theta_full != nullptr) {
+            th0 = theta_full[y0 * W + x0];
+            if (has1) th1 = theta_full[y1 * W + x1];
+        }
+        splat9_event<WRAP>(x0, y0, t0, th0, H, W, R, tref, C, HW);
+        if (has1) splat9_event<WRAP>(x1, y1, t1, th1, H, W, R, tref, C, HW);
     }
 }
 
@@ -129,11 +148,13 @@ k_compose9(const float* __restrict__ C, int H, int W, double* __restrict__ iwe /
 
 // ---- backward: gather d loss / d IWE (float32 copy) through the 3x3 taps --------------------------------------------
 // dL/dx' = sum_ij D[p + (i,j)] v_ij (i - fx),  v_ij = (1/2pi) G_i G_j A Bx^i By^j ;  same for y with (j - fy).
+// Separable evaluation: with wx_i = G_i Bx^i, wy_j = G_j By^j,
+//     s_j = sum_i D_ij wx_i,  sx_j = sum_i D_ij wx_i (i - fx)   =>   gx = A sum_j wy_j sx_j,  gy = A sum_j wy_j (j - fy) s_j.
 // Slow path (non-interior centre): float64 D with the wrap/drop rule, as in k_backward_events.
 template <bool WRAP>
 __global__ void __launch_bounds__(256)
 k_backward9(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, int64_t n,
-            const double2* __restrict__ theta_full, int H, int W, int R, RefTimes tref,
+            const double2* __restrict__ theta_full, int H, int W, int R, const __grid_constant__ RefTimes tref,
             const float* __restrict__ dldi32 /* [R][H][W], already scaled by 1/(2 pi) */, const double* __restrict__ dldi,
             double* __restrict__ G /* [H][W][2] */) {
     const int64_t HW = (int64_t)H * W;
@@ -154,21 +175,24 @@ k_backward9(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t,
                 const float fx = (float)(wp.xw - (double)wp.rx), fy = (float)(wp.yw - (double)wp.ry);
                 float gx = 0.f, gy = 0.f;
                 if (wp.rx >= 1 && wp.rx <= W - 2 && wp.ry >= 1 && wp.ry <= H - 2) {
-                    float m[9];
-                    moments9(fx, fy, m);
                     const float* Dp = dldi32 + (int64_t)r * HW + (int64_t)wp.ry * W + wp.rx;
-                    float sx = 0.f, sy = 0.f;
+                    float d[9];
 #pragma unroll
-                    for (int j = -1; j <= 1; ++j) {
+                    for (int j = -1; j <= 1; ++j)
 #pragma unroll
-                        for (int i = -1; i <= 1; ++i) {
-                            const float g = ((i != 0) ? kG1 : 1.f) * ((j != 0) ? kG1 : 1.f);
-                            const float d = __ldg(Dp + j * W + i) * (g * m[(j + 1) * 3 + (i + 1)]);
-                            sx = fmaf(d, (float)i - fx, sx);
-                            sy = fmaf(d, (float)j - fy, sy);
-                        }
+                        for (int i = -1; i <= 1; ++i) d[(j + 1) * 3 + (i + 1)] = __ldg(Dp + j * W + i);
+                    const float A = __expf(-0.5f * (fx * fx + fy * fy));
+                    const float wx0 = kG1 * __expf(-fx), wx2 = kG1 * __expf(fx);          // wx1 = 1
+                    const float wy0 = kG1 * __expf(-fy), wy2 = kG1 * __expf(fy);          // wy1 = 1
+                    const float ux0 = wx0 * (-1.f - fx), ux1 = -fx, ux2 = wx2 * (1.f - fx);  // wx_i (i - fx)
+                    float sj[3], sxj[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        sj[j] = fmaf(d[j * 3 + 0], wx0, fmaf(d[j * 3 + 2], wx2, d[j * 3 + 1]));
+                        sxj[j] = fmaf(d[j * 3 + 0], ux0, fmaf(d[j * 3 + 2], ux2, d[j * 3 + 1] * ux1));
                     }
-                    gx = sx; gy = sy;
+                    gx = A * fmaf(wy0, sxj[0], fmaf(wy2, sxj[2], sxj[1]));
+                    gy = A * fmaf(wy0 * (-1.f - fy), sj[0], fmaf(wy2 * (1.f - fy), sj[2], -fy * sj[1]));
                 } else {
                     const double* img = dldi + (int64_t)r * HW;
 #pragma unroll
@@ -190,21 +214,20 @@ k_backward9(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t,
                 gy_acc = fmaf(-dtf, gy, gy_acc);
             }
         }
-        // segmented (by source pixel) inclusive suffix sum inside the warp, in float64
-        double ax = (double)gx_acc, ay = (double)gy_acc;
+        // segmented (by source pixel) inclusive suffix sum inside the warp (float32: <= 32 terms), one float64 RED per run
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const double ox = __shfl_down_sync(0xffffffffu, ax, o);
-            const double oy = __shfl_down_sync(0xffffffffu, ay, o);
+            const float ox = __shfl_down_sync(0xffffffffu, gx_acc, o);
+            const float oy = __shfl_down_sync(0xffffffffu, gy_acc, o);
             const uint32_t oxy = __shfl_down_sync(0xffffffffu, xy, o);
-            if (lane + o < 32 && oxy == xy) { ax += ox; ay += oy; }
+            if (lane + o < 32 && oxy == xy) { gx_acc += ox; gy_acc += oy; }
         }
         const uint32_t prev = __shfl_up_sync(0xffffffffu, xy, 1);
         const bool head = (lane == 0) || (prev != xy);
         if (head && e < n) {
             const int x = xy & 0xffffu, y = xy >> 16;
-            atomicAdd(&G[(y * W + x) * 2 + 0], ax);
-            atomicAdd(&G[(y * W + x) * 2 + 1], ay);
+            atomicAdd(&G[(y * W + x) * 2 + 0], (double)gx_acc);
+            atomicAdd(&G[(y * W + x) * 2 + 1], (double)gy_acc);
         }
     }
 }

@@ -257,23 +257,26 @@ k_img_D2(const double* __restrict__ sbar, int H, int W, double* __restrict__ gNd
 // ---- scalar epilogue: K8 of SURVEY.md §2.1 (reference src/eincm/losses.py:171-193) ------------------------
 // Assembles the loss from the per-reference statistics; also derives the cotangent scales for the backward.
 // mode 0: compute coefA/B/D from the zero-IWE constants (called before B / C); mode 1: final loss.
-__global__ void k_scalars(DevScalars* __restrict__ sc, int R, double HW, double alpha, double beta, double gamma, double delta,
-                          int use_tv, int use_div, int mode, double* __restrict__ loss_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// coefA/B/D from the zero-IWE constants (needed by the image backward)
+__device__ __forceinline__ void scalars_coefs(DevScalars* sc, int R, double HW, double alpha, double beta, double delta, int use_div) {
     const double C0 = sc->zero[0].contrast;
     const double D0 = sc->zero[0].div;
-    if (mode == 0) {
-        for (int r = 0; r < R; ++r) {
-            const double w = sc->weights[r];
-            const double a_r = -alpha * w / ((C0 + kEps) * R);
-            const double b_r = beta * w / ((-sc->zero[r].mse + kEps) * R);
-            const double d_r = use_div ? delta * w / ((D0 + kEps) * R) : 0.0;
-            sc->coefA[r] = a_r * (2.0 / HW);
-            sc->coefB[r] = b_r * (-2.0 / HW);
-            sc->coefD[r] = d_r / HW;
-        }
-        return;
+    for (int r = 0; r < R; ++r) {
+        const double w = sc->weights[r];
+        const double a_r = -alpha * w / ((C0 + kEps) * R);
+        const double b_r = beta * w / ((-sc->zero[r].mse + kEps) * R);
+        const double d_r = use_div ? delta * w / ((D0 + kEps) * R) : 0.0;
+        sc->coefA[r] = a_r * (2.0 / HW);
+        sc->coefB[r] = b_r * (-2.0 / HW);
+        sc->coefD[r] = d_r / HW;
     }
+}
+
+// final loss (reference src/eincm/losses.py:171-193) from the per-reference statistics
+__device__ __forceinline__ void scalars_loss(DevScalars* sc, int R, double alpha, double beta, double gamma, double delta,
+                                             int use_tv, int use_div, double* loss_out) {
+    const double C0 = sc->zero[0].contrast;
+    const double D0 = sc->zero[0].div;
     double s_corr = 0.0, s_con = 0.0, s_div = 0.0;
     for (int r = 0; r < R; ++r) {
         const double w = sc->weights[r];
@@ -288,6 +291,14 @@ __global__ void k_scalars(DevScalars* __restrict__ sc, int R, double HW, double 
     sc->loss = loss; sc->mean_rel_corr = mean_rel_corr; sc->mean_rel_contrast = mean_rel_contrast;
     sc->mean_rel_div = mean_rel_div; sc->tv = tv;
     if (loss_out != nullptr) *loss_out = loss;
+}
+
+// mode 0: cotangent scales (called before B / C); mode 1: final loss.
+__global__ void k_scalars(DevScalars* __restrict__ sc, int R, double HW, double alpha, double beta, double gamma, double delta,
+                          int use_tv, int use_div, int mode, double* __restrict__ loss_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (mode == 0) scalars_coefs(sc, R, HW, alpha, beta, delta, use_div);
+    else scalars_loss(sc, R, alpha, beta, gamma, delta, use_tv, use_div, loss_out);
 }
 
 // ---- gradient epilogue: reduce the gather partials (or pass the scatter buffer through), write grad_out and

@@ -93,30 +93,34 @@ def test_loss_at_zero_theta_known_answer(L, R):
     assert loss == pytest.approx(-(20.0 + 35.0) / R, rel=1e-9)
 
 
-def test_intermediates_and_bit_exact_pixel_indices(L, tiny):
+@pytest.mark.parametrize('exact', [False, True])
+def test_intermediates_and_bit_exact_pixel_indices(L, tiny, exact):
     from eincm_b200 import plan as P
     th = S.theta_test_points(tiny, (4, 4))['perturbed']
     kw = _kw(tiny)
     l_ref, g_ref, inter = O.value_and_grad(th, *tiny.args(), **kw, return_intermediates=True)
-    p = P.Plan(tiny.sensor_size, max_events=len(tiny.xs), max_refs=3)
+    p = P.Plan(tiny.sensor_size, max_events=len(tiny.xs), max_refs=3, flags=P.FLAG_EXACT_F64 if exact else 0)
     p.set_window(*tiny.args())
     loss, grad = p.value_and_grad_host(th, P.make_hparams(20.0, 35.0, 0.0, 0.0, 1))
-    np.testing.assert_allclose(p.zero_iwe().cpu().numpy(), inter['zero_iwe'], rtol=1e-6, atol=1e-9)
-    np.testing.assert_allclose(p.iwe().cpu().numpy(), inter['iwes'], rtol=1e-6, atol=1e-9)
-    assert _rel_inf(p.dldi().cpu().numpy(), inter['dLdI']) <= 1e-5
+    # per-pixel image values: float32 moment sums (order-dependent rounding) in the default mode, float64 in EXACT_F64
+    rt, at, rd = (1e-12, 1e-14, 1e-9) if exact else (2e-5, 1e-7, 1e-4)
+    np.testing.assert_allclose(p.zero_iwe().cpu().numpy(), inter['zero_iwe'], rtol=rt, atol=at)
+    np.testing.assert_allclose(p.iwe().cpu().numpy(), inter['iwes'], rtol=rt, atol=at)
+    assert _rel_inf(p.dldi().cpu().numpy(), inter['dLdI']) <= rd
     np.testing.assert_allclose(p.theta_full().cpu().numpy(), inter['aux']['scaled_theta'], rtol=1e-13, atol=1e-13)
     np.testing.assert_array_equal(p.event_mask().cpu().numpy().astype(bool), O.make_event_mask(tiny.xs, tiny.ys, tiny.sensor_size))
     obj = inter['objectives']
     for r in range(3):
         cols, rows = p.rounded_pixels(r)
         xr, yr = O.rounded_event_pixels(obj['warped_xs'][r], obj['warped_ys'][r])
-        np.testing.assert_array_equal(cols, xr.astype(np.int32))      # bit-exact event->pixel indexing
+        np.testing.assert_array_equal(cols, xr.astype(np.int32))      # bit-exact event->pixel indexing (both modes)
         np.testing.assert_array_equal(rows, yr.astype(np.int32))
     s = p.scalars()
-    np.testing.assert_allclose(s['contrasts'], obj['contrasts'], rtol=1e-6)
-    np.testing.assert_allclose(s['correlations'], obj['correlations'], rtol=1e-6)
-    np.testing.assert_allclose(s['zero_correlations'], obj['zero_correlations'], rtol=1e-6)
-    np.testing.assert_allclose(s['zero_contrast'], obj['zero_contrast'], rtol=1e-6)
+    rs = 1e-11 if exact else 1e-6
+    np.testing.assert_allclose(s['contrasts'], obj['contrasts'], rtol=rs)
+    np.testing.assert_allclose(s['correlations'], obj['correlations'], rtol=rs)
+    np.testing.assert_allclose(s['zero_correlations'], obj['zero_correlations'], rtol=rs)
+    np.testing.assert_allclose(s['zero_contrast'], obj['zero_contrast'], rtol=rs)
     np.testing.assert_allclose(s['multi_ref_weights'], obj['multi_ref_weights'], rtol=1e-14)
     p.close()
 
