@@ -58,6 +58,8 @@ struct eincm_plan {
     uint32_t* ev_xy = nullptr;
     double* ev_t = nullptr;
     uint32_t* perm = nullptr;
+    double* ev_t2 = nullptr;      // ping-pong partners of ev_t / perm for the per-pixel time ordering
+    uint32_t* perm2 = nullptr;
     unsigned int *counts = nullptr, *cursor = nullptr, *block_sums = nullptr;
     int n_keys = 0, tiles_x = 0, n_scan_blocks = 0;
     uint8_t* mask = nullptr;
@@ -194,6 +196,12 @@ int event_grid(const eincm_plan* p, int64_t n, int threads) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 8));
 }
 
+// grid of the grouped event kernels: one thread per group of kEvK events, whole CTAs, capped (grid-stride beyond the cap)
+int group_grid(const eincm_plan* p, int64_t n_groups) {
+    const int64_t want = (n_groups + 255) / 256;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 32));
+}
+
 int img_tiles_x(const eincm_plan* p) { return (p->W + kImgTX - 1) / kImgTX; }
 int img_tiles_y(const eincm_plan* p) { return (p->H + kImgTY - 1) / kImgTY; }
 int img_nb_flat(const eincm_plan* p) { return (int)std::min<int64_t>((p->HW + kImgNT - 1) / kImgNT, (int64_t)p->sm_count * 4); }
@@ -261,9 +269,14 @@ int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const R
     }
     CU(cudaMemsetAsync(plan->C9, 0, (size_t)n_img * plan->HW * kRec * sizeof(float), st));
     if (n > 0) {
-        const int grid = event_grid(plan, n, 256);
-        if (plan->wrap) LAUNCH(tag, k_splat9<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, plan->C9));
-        else LAUNCH(tag, k_splat9<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, plan->C9));
+        const int64_t n_groups = (n + kEvK - 1) / kEvK;
+        const int grid = group_grid(plan, n_groups);
+#define SPLAT9(WR, RB) LAUNCH(tag, k_splat9<WR, RB><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n_groups, theta_full, H, W, n_img, tref, plan->C9))
+#define SPLAT9_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLAT9(WR, 1); break; case 2: SPLAT9(WR, 2); break; \
+                                                                 case 3: SPLAT9(WR, 3); break; default: SPLAT9(WR, 4); } } while (0)
+        if (plan->wrap) SPLAT9_RB(true); else SPLAT9_RB(false);
+#undef SPLAT9_RB
+#undef SPLAT9
     }
     if (!compose) return EINCM_OK;
     return compose_images(plan, n_img, out, st);
@@ -362,12 +375,15 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
                 LAUNCH("k_backward_events", k_backward_events<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R,
                                                                                            plan->tref, plan->dldi, plan->G));
         } else {
-            if (plan->wrap)
-                LAUNCH("k_backward_events", k_backward9<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R, plan->tref,
-                                                                                    plan->dldi32, plan->dldi, plan->G));
-            else
-                LAUNCH("k_backward_events", k_backward9<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R, plan->tref,
-                                                                                     plan->dldi32, plan->dldi, plan->G));
+            const int64_t n_groups = (n + kEvK - 1) / kEvK;
+            const int gg = group_grid(plan, n_groups);
+#define BWD9(WR, RB) LAUNCH("k_backward_events", k_backward9<WR, RB><<<gg, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n_groups, plan->theta_full, H, W, R, \
+                                                                                         plan->tref, plan->dldi32, plan->dldi, plan->G))
+#define BWD9_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BWD9(WR, 1); break; case 2: BWD9(WR, 2); break; \
+                                                           case 3: BWD9(WR, 3); break; default: BWD9(WR, 4); } } while (0)
+            if (plan->wrap) BWD9_RB(true); else BWD9_RB(false);
+#undef BWD9_RB
+#undef BWD9
         }
     }
     AxisTaps ty, tx;
@@ -433,7 +449,11 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     const int nbT = img_tiles_x(plan) * img_tiles_y(plan);
     plan->part_doubles = 10 * max_refs * std::max(nbT, plan->sm_count * 4) + 4096;
     auto body = [&]() -> int {
-        CU(dmalloc(&plan->ev_xy, NE)); CU(dmalloc(&plan->ev_t, NE)); CU(dmalloc(&plan->perm, NE));
+        // event stream padded to whole groups of kEvK (k_events9.cuh)
+        const size_t NP = (NE + kEvK - 1) / kEvK * kEvK + kEvK;
+        CU(dmalloc(&plan->ev_xy, NP)); CU(dmalloc(&plan->ev_t, NP)); CU(dmalloc(&plan->perm, NP));
+        CU(dmalloc(&plan->ev_t2, NP)); CU(dmalloc(&plan->perm2, NP));
+        CU(cudaMemset(plan->ev_t, 0, NP * sizeof(double))); CU(cudaMemset(plan->ev_t2, 0, NP * sizeof(double)));
         CU(dmalloc(&plan->counts, (size_t)plan->n_keys)); CU(dmalloc(&plan->cursor, (size_t)plan->n_keys));
         CU(dmalloc(&plan->block_sums, (size_t)plan->n_scan_blocks));
         CU(dmalloc(&plan->mask, HW));
@@ -465,7 +485,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
 void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
-    void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->counts, plan->cursor, plan->block_sums, plan->mask, plan->theta_full,
+    void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->block_sums, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->C9, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
@@ -529,6 +549,15 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     if (n > 0) {
         const int grid = event_grid(plan, n, 256);
         LAUNCH("k_scatter_events", k_scatter_events<<<grid, 256, 0, st>>>(xs, ys, ts, n, plan->H, plan->W, plan->tiles_x, plan->cursor, plan->ev_xy, plan->ev_t, plan->perm));
+        // stable order inside each pixel (by original index = by time), then the buffers swap roles
+        LAUNCH("k_rank_sort_segments", k_rank_sort_segments<<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->perm, n, plan->W, plan->tiles_x, plan->counts,
+                                                                                   plan->cursor, plan->ev_t2, plan->perm2));
+        std::swap(plan->ev_t, plan->ev_t2);
+        std::swap(plan->perm, plan->perm2);
+    }
+    {   // sentinel padding up to a whole group of kEvK events
+        const int64_t n_pad = (n + kEvK - 1) / kEvK * kEvK;
+        if (n_pad > n) CU(cudaMemsetAsync(plan->ev_xy + n, 0xff, (size_t)(n_pad - n) * sizeof(uint32_t), st));
     }
     CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
     LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc));
@@ -751,8 +780,12 @@ int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int
     CU(cudaSetDevice(plan->device));
     if (plan->n_events == 0) return EINCM_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    LAUNCH("k_rounded_pixels", k_rounded_pixels<<<event_grid(plan, plan->n_events, 256), 256, 0, st>>>(
-        plan->ev_xy, plan->ev_t, plan->perm, plan->n_events, plan->theta_full, plan->W, plan->tref.t[ref], cols_out, rows_out));
+    if (plan->exact)
+        LAUNCH("k_rounded_pixels", k_rounded_pixels<true><<<event_grid(plan, plan->n_events, 256), 256, 0, st>>>(
+            plan->ev_xy, plan->ev_t, plan->perm, plan->n_events, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));
+    else
+        LAUNCH("k_rounded_pixels", k_rounded_pixels<false><<<event_grid(plan, plan->n_events, 256), 256, 0, st>>>(
+            plan->ev_xy, plan->ev_t, plan->perm, plan->n_events, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));
     return EINCM_OK;
 }
 

@@ -128,19 +128,4 @@ k_backward_events(const uint32_t* __restrict__ ev_xy, const double* __restrict__
     }
 }
 
-// ---- debug tap: Xs_rounded (event_utils.py:33) of reference r, written back in the original event order ----
-__global__ void k_rounded_pixels(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const uint32_t* __restrict__ perm,
-                                 int64_t n, const double2* __restrict__ theta_full, int W, double t_ref,
-                                 int32_t* __restrict__ cols_out, int32_t* __restrict__ rows_out) {
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t xy = ev_xy[e];
-        const int x = xy & 0xffffu, y = xy >> 16;
-        const double2 th = theta_full[y * W + x];
-        const Warped wp = warp_event(x, y, th.x, th.y, ev_t[e] - t_ref);
-        const uint32_t o = perm[e];
-        cols_out[o] = wp.ok ? wp.rx : INT32_MAX;
-        rows_out[o] = wp.ok ? wp.ry : INT32_MAX;
-    }
-}
-
 }  // namespace eincm

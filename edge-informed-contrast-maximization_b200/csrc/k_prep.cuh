@@ -84,8 +84,7 @@ __global__ void k_scan_finish(const unsigned int* __restrict__ counts, int n_key
 }
 
 // Scatter events into pixel-sorted order.  ev_xy packs (x | y << 16); perm keeps the original index
-// (needed only by the debug index tap).  Order inside one pixel is arbitrary (sums are order-insensitive
-// up to float64 rounding).
+// (needed by the debug index tap and by k_rank_sort_segments).  Order inside one pixel is arbitrary here.
 __global__ void k_scatter_events(const int16_t* __restrict__ xs, const int16_t* __restrict__ ys, const double* __restrict__ ts,
                                  int64_t n, int H, int W, int tiles_x, unsigned int* __restrict__ cursor,
                                  uint32_t* __restrict__ ev_xy, double* __restrict__ ev_t, uint32_t* __restrict__ perm) {
@@ -96,6 +95,33 @@ __global__ void k_scatter_events(const int16_t* __restrict__ xs, const int16_t* 
         ev_xy[pos] = (uint32_t)x | ((uint32_t)y << 16);
         ev_t[pos] = ts[e];
         perm[pos] = (uint32_t)e;
+    }
+}
+
+// Orders the events of every pixel by their original index (= by time: the loaders deliver ts ascending,
+// reference src/dataloaders/dsec_loader.py:285-349), turning the unstable scatter above into a stable sort.  Consecutive
+// sorted events then differ little in (pixel, t), so their warped destinations coincide often and the event kernels can
+// merge them in registers before touching memory (k_events9.cuh).  Rank sort: one thread per event counts the events of
+// its own pixel segment with a smaller original index.  Segments longer than kMaxRankSeg (hot pixels) keep the scatter
+// order - the order only affects how many reductions are merged, never the result.
+constexpr unsigned int kMaxRankSeg = 4096;
+
+__global__ void k_rank_sort_segments(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const uint32_t* __restrict__ perm,
+                                     int64_t n, int W, int tiles_x, const unsigned int* __restrict__ counts,
+                                     const unsigned int* __restrict__ cursor_end, double* __restrict__ ev_t_out,
+                                     uint32_t* __restrict__ perm_out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t xy = ev_xy[e];
+        const int key = sort_key(xy & 0xffffu, xy >> 16, W, tiles_x);
+        const unsigned int cnt = counts[key], end = cursor_end[key], start = end - cnt;
+        const uint32_t p = perm[e];
+        unsigned int rank = (unsigned int)e - start;
+        if (cnt > 1u && cnt <= kMaxRankSeg) {
+            rank = 0;
+            for (unsigned int j = start; j < end; ++j) rank += perm[j] < p ? 1u : 0u;
+        }
+        ev_t_out[start + rank] = ev_t[e];
+        perm_out[start + rank] = p;
     }
 }
 
