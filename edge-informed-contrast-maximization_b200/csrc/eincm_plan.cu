@@ -20,6 +20,7 @@
 #include "k_theta.cuh"
 #include "k_events.cuh"
 #include "k_events9.cuh"
+#include "k_events_tile.cuh"
 #include "k_image.cuh"
 #include "k_image_fused.cuh"
 
@@ -41,10 +42,12 @@ struct eincm_plan {
     int device = 0, H = 0, W = 0, max_refs = 0, sm_count = 148;
     int64_t HW = 0, max_events = 0;
     unsigned flags = 0;
-    bool wrap = true, exact = false;
+    bool wrap = true, exact = false, moments = false;   // moments: legacy float32 moment splat (EINCM_FLAG_MOMENT_SPLAT)
     int split_rank = 0, split_world = 1;   // event-split plans: rank 0 alone adds the (replicated) TV gradient
     // window state
     int64_t n_events = 0;
+    int64_t n_stream = 0, stream_cap = 0;   // padded length of the sorted stream (k_prep.cuh) / its capacity
+    int n_chunks = 0, chunk_cap = 0, n_tiles = 0;
     int R = 0;
     bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
     bool fused_pending = false;   // the last forward left the moment records un-composed for the fused image pass
@@ -60,8 +63,11 @@ struct eincm_plan {
     uint32_t* perm = nullptr;
     double* ev_t2 = nullptr;      // ping-pong partners of ev_t / perm for the per-pixel time ordering
     uint32_t* perm2 = nullptr;
-    unsigned int *counts = nullptr, *cursor = nullptr, *block_sums = nullptr;
-    int n_keys = 0, tiles_x = 0, n_scan_blocks = 0;
+    unsigned int *counts = nullptr, *cursor = nullptr, *tile_cnt = nullptr, *tile_start = nullptr, *chunk_first = nullptr, *totals = nullptr;
+    Chunk* chunks = nullptr;
+    int4* chunk_win = nullptr;                         // [chunk_cap][max_refs] windows of the last forward pass
+    unsigned long long* iwe_fix = nullptr;             // [max_refs][H*W] fixed-point images of warped events
+    int n_keys = 0, tiles_x = 0;
     uint8_t* mask = nullptr;
     double2 *theta_full = nullptr, *Gtv = nullptr, *partial = nullptr;
     double *G = nullptr, *iwe = nullptr, *zero_iwe = nullptr, *dldi = nullptr, *edges = nullptr;
@@ -255,8 +261,8 @@ int compose_images(eincm_plan* plan, int n_img, double* out, cudaStream_t st) {
 // Builds n_img images of warped events (one per reference time in `tref`) from the staged events: exact mode = nine
 // float64 scatter-adds per event and image; fast mode = moment splat + compose (k_events9.cuh).
 int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const RefTimes& tref, double* out, const char* tag,
-                 cudaStream_t st, bool compose = true) {
-    const int64_t n = plan->n_events;
+                 cudaStream_t st, bool compose = true, bool record_windows = false) {
+    const int64_t n = plan->n_events > 0 ? plan->n_stream : 0;      // padded stream: sentinels are skipped by the kernels
     const int H = plan->H, W = plan->W;
     if (plan->exact) {
         CU(cudaMemsetAsync(out, 0, (size_t)n_img * plan->HW * sizeof(double), st));
@@ -265,6 +271,24 @@ int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const R
             if (plan->wrap) LAUNCH(tag, k_splat<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, out));
             else LAUNCH(tag, k_splat<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, theta_full, H, W, n_img, tref, out));
         }
+        return EINCM_OK;
+    }
+    if (!plan->moments) {
+        CU(cudaMemsetAsync(plan->iwe_fix, 0, (size_t)n_img * plan->HW * sizeof(unsigned long long), st));
+        if (n > 0) {
+            const int grid = std::max(1, plan->n_chunks);
+            int4* cw = record_windows ? plan->chunk_win : nullptr;
+#define SPLATT(WR, RB) LAUNCH(tag, k_splat_tile<WR, RB><<<grid, 256, RB * kWinCap * sizeof(uint32_t), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
+                                   plan->totals + 1, theta_full, H, W, n_img, tref, plan->iwe_fix, cw))
+#define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
+                                                                 case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
+            if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
+#undef SPLATT_RB
+#undef SPLATT
+        }
+        if (!compose) return EINCM_OK;
+        const int64_t cells = (int64_t)n_img * plan->HW;
+        LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, out));
         return EINCM_OK;
     }
     CU(cudaMemsetAsync(plan->C9, 0, (size_t)n_img * plan->HW * kRec * sizeof(float), st));
@@ -299,7 +323,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
     }
     // default path (float32 moments, single GPU, delta == 0): the records are composed inside the fused image pass
     plan->fused_pending = !plan->exact && !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && hp->delta == 0.0;
-    if ((rc = splat_images(plan, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending))) return rc;
+    if ((rc = splat_images(plan, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
     plan->forward_done = true;
     return EINCM_OK;
@@ -318,7 +342,12 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     const dim3 gridT(img_tiles_x(plan), img_tiles_y(plan), R);
     const int nbT = gridT.x * gridT.y;
     if (plan->fused_pending && use_div) {        // hparams changed between the split-phase calls: fall back to the unfused pass
-        if ((rc = compose_images(plan, R, plan->iwe, st))) return rc;
+        if (plan->moments) {
+            if ((rc = compose_images(plan, R, plan->iwe, st))) return rc;
+        } else {
+            const int64_t cells = (int64_t)R * plan->HW;
+            LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, plan->iwe));
+        }
         plan->fused_pending = false;
     }
     if (plan->fused_pending) {
@@ -330,8 +359,12 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         const int nbF1 = gridF.x * gridF.y;
         const int tvb = ((W + kTvTX - 1) / kTvTX) * ((H + kTvTY - 1) / kTvTY);
         double* partF = plan->part + 2 * tvb;                    // k_tv's partials live at the start of `part`
-        LAUNCH("k_img_fused1", k_img_fused1<<<gridF, blockF, 0, st>>>(plan->C9, plan->edges, H, W, nbF1, plan->iwe, partF, plan->sc,
-                                                                      hp->alpha, hp->beta, hp->gamma, use_tv ? 1 : 0, loss_out));
+        if (plan->moments)
+            LAUNCH("k_img_fused1", k_img_fused1<false><<<gridF, blockF, 0, st>>>(plan->C9, plan->edges, H, W, nbF1, plan->iwe, partF, plan->sc,
+                                                                                 hp->alpha, hp->beta, hp->gamma, use_tv ? 1 : 0, loss_out));
+        else
+            LAUNCH("k_img_fused1", k_img_fused1<true><<<gridF, blockF, 0, st>>>(plan->iwe_fix, plan->edges, H, W, nbF1, plan->iwe, partF, plan->sc,
+                                                                                hp->alpha, hp->beta, hp->gamma, use_tv ? 1 : 0, loss_out));
         plan->fused_pending = false;
         if (!want_grad) return EINCM_OK;
         LAUNCH("k_img_fused3", k_img_fused3<<<gridF, blockF, 0, st>>>(plan->iwe, plan->edges, H, W, plan->sc, plan->dldi, plan->dldi32));
@@ -365,8 +398,8 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     }
     CU(cudaMemsetAsync(plan->G, 0, (size_t)plan->HW * 2 * sizeof(double), st));
     if (plan->n_events > 0) {
-        const int grid = event_grid(plan, plan->n_events, 256);
-        const int64_t n = plan->n_events;
+        const int64_t n = plan->n_stream;
+        const int grid = event_grid(plan, n, 256);
         if (plan->exact) {
             if (plan->wrap)
                 LAUNCH("k_backward_events", k_backward_events<true><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R,
@@ -374,6 +407,15 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             else
                 LAUNCH("k_backward_events", k_backward_events<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R,
                                                                                            plan->tref, plan->dldi, plan->G));
+        } else if (!plan->moments) {
+            const int gridT2 = std::max(1, plan->n_chunks);
+#define BWDT(WR, RB) LAUNCH("k_backward_events", k_backward_tile<WR, RB><<<gridT2, 256, RB * kWinCap * sizeof(float), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
+                                   plan->totals + 1, plan->theta_full, H, W, R, plan->tref, plan->dldi32, plan->chunk_win, plan->G))
+#define BWDT_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BWDT(WR, 1); break; case 2: BWDT(WR, 2); break; \
+                                                           case 3: BWDT(WR, 3); break; default: BWDT(WR, 4); } } while (0)
+            if (plan->wrap) BWDT_RB(true); else BWDT_RB(false);
+#undef BWDT_RB
+#undef BWDT
         } else {
             const int64_t n_groups = (n + kEvK - 1) / kEvK;
             const int gg = group_grid(plan, n_groups);
@@ -436,32 +478,55 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     if (prop.major != 10) return fail(nullptr, EINCM_ECUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, EINCM_ECUDA, "%s", cudaGetErrorString(e));
 
+    {   // the tile kernels keep up to kMaxRB windows of kWinCap cells in dynamic shared memory (> 48 KB needs the opt-in)
+        cudaError_t ea = cudaSuccess;
+        auto opt_in = [&](const void* fn, int rb) {
+            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rb * kWinCap * (int)sizeof(uint32_t));
+        };
+#define OPT_IN_RB(RB) opt_in((const void*)k_splat_tile<true, RB>, RB); opt_in((const void*)k_splat_tile<false, RB>, RB); \
+                      opt_in((const void*)k_backward_tile<true, RB>, RB); opt_in((const void*)k_backward_tile<false, RB>, RB)
+        OPT_IN_RB(1); OPT_IN_RB(2); OPT_IN_RB(3); OPT_IN_RB(4);
+#undef OPT_IN_RB
+        if (ea != cudaSuccess) return fail(nullptr, EINCM_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
+    }
     plan = new (std::nothrow) eincm_plan();
     if (!plan) return fail(nullptr, EINCM_ENOMEM, "host allocation failed");
     plan->device = device; plan->H = H; plan->W = W; plan->HW = (int64_t)H * W; plan->max_events = max_events;
     plan->max_refs = max_refs; plan->flags = flags; plan->wrap = !(flags & EINCM_FLAG_NO_WRAP_NEGATIVE);
     plan->exact = (flags & EINCM_FLAG_EXACT_F64) != 0;
+    plan->moments = !plan->exact && (flags & EINCM_FLAG_MOMENT_SPLAT) != 0;
     plan->sm_count = prop.multiProcessorCount;
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
-    plan->n_keys = plan->tiles_x * ((H + kSortTile - 1) / kSortTile) * kSortTile * kSortTile;
-    plan->n_scan_blocks = (plan->n_keys + kScanBlock - 1) / kScanBlock;
+    plan->n_tiles = plan->tiles_x * ((H + kSortTile - 1) / kSortTile);
+    plan->n_keys = plan->n_tiles * kKeysPerTile;
+    plan->stream_cap = (max_events + kStreamAlign - 1) / kStreamAlign * kStreamAlign + (int64_t)kStreamAlign * plan->n_tiles + kStreamAlign;
+    plan->chunk_cap = (int)(max_events / kChunkEvents) + plan->n_tiles + 1;
     const size_t HW = (size_t)plan->HW, NE = (size_t)max_events, RR = (size_t)max_refs;
     const int nbT = img_tiles_x(plan) * img_tiles_y(plan);
     plan->part_doubles = 10 * max_refs * std::max(nbT, plan->sm_count * 4) + 4096;
     auto body = [&]() -> int {
-        // event stream padded to whole groups of kEvK (k_events9.cuh)
-        const size_t NP = (NE + kEvK - 1) / kEvK * kEvK + kEvK;
+        // sorted event stream: every tile segment padded to whole groups of kEvK events (k_prep.cuh)
+        const size_t NP = (size_t)plan->stream_cap;
+        (void)NE;
         CU(dmalloc(&plan->ev_xy, NP)); CU(dmalloc(&plan->ev_t, NP)); CU(dmalloc(&plan->perm, NP));
         CU(dmalloc(&plan->ev_t2, NP)); CU(dmalloc(&plan->perm2, NP));
         CU(cudaMemset(plan->ev_t, 0, NP * sizeof(double))); CU(cudaMemset(plan->ev_t2, 0, NP * sizeof(double)));
         CU(dmalloc(&plan->counts, (size_t)plan->n_keys)); CU(dmalloc(&plan->cursor, (size_t)plan->n_keys));
-        CU(dmalloc(&plan->block_sums, (size_t)plan->n_scan_blocks));
+        CU(dmalloc(&plan->tile_cnt, (size_t)plan->n_tiles + 1)); CU(dmalloc(&plan->tile_start, (size_t)plan->n_tiles + 1));
+        CU(dmalloc(&plan->chunk_first, (size_t)plan->n_tiles + 1)); CU(dmalloc(&plan->totals, 4));
+        CU(cudaMemset(plan->totals, 0, 4 * sizeof(unsigned int)));
+        CU(dmalloc(&plan->chunks, (size_t)plan->chunk_cap));
         CU(dmalloc(&plan->mask, HW));
         CU(dmalloc(&plan->theta_full, HW)); CU(dmalloc(&plan->Gtv, HW));
         CU(dmalloc(&plan->partial, (size_t)kGatherMaxTiles * 2 + (size_t)4 * plan->sm_count));
         CU(dmalloc(&plan->G, HW * 2)); CU(dmalloc(&plan->iwe, RR * HW)); CU(dmalloc(&plan->zero_iwe, HW));
         CU(dmalloc(&plan->dldi, RR * HW)); CU(dmalloc(&plan->edges, RR * HW));
-        if (!plan->exact) { CU(dmalloc(&plan->C9, RR * HW * kRec)); CU(dmalloc(&plan->dldi32, RR * HW)); }
+        if (plan->moments) CU(dmalloc(&plan->C9, RR * HW * kRec));
+        if (!plan->exact) CU(dmalloc(&plan->dldi32, RR * HW));
+        if (!plan->exact && !plan->moments) {
+            CU(dmalloc(&plan->iwe_fix, RR * HW));
+            CU(dmalloc(&plan->chunk_win, (size_t)plan->chunk_cap * RR));
+        }
         CU(dmalloc(&plan->part, (size_t)plan->part_doubles));
         CU(dmalloc(&plan->sc, 1));
         CU(cudaMemset(plan->sc, 0, sizeof(DevScalars)));
@@ -485,7 +550,8 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
 void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
-    void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->block_sums, plan->mask, plan->theta_full,
+    void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
+                    plan->chunk_first, plan->totals, plan->chunks, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->C9, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
@@ -542,22 +608,23 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
         const int grid = event_grid(plan, n, 256);
         LAUNCH("k_histogram", k_histogram<<<grid, 256, 0, st>>>(xs, ys, n, plan->H, plan->W, plan->tiles_x, plan->counts, &plan->sc->error_flag));
     }
-    LAUNCH("k_scan_block_sums", k_scan_block_sums<<<plan->n_scan_blocks, kScanBlock, 0, st>>>(plan->counts, plan->n_keys, plan->block_sums));
-    LAUNCH("k_scan_of_block_sums", k_scan_of_block_sums<<<1, kScanBlock, 0, st>>>(plan->block_sums, plan->n_scan_blocks));
-    LAUNCH("k_scan_finish", k_scan_finish<<<plan->n_scan_blocks, kScanBlock, 0, st>>>(plan->counts, plan->n_keys, plan->block_sums, plan->cursor));
+    LAUNCH("k_tile_counts", k_tile_counts<<<plan->n_tiles, kKeysPerTile, 0, st>>>(plan->counts, plan->tile_cnt));
+    LAUNCH("k_tile_layout", k_tile_layout<<<1, 1024, 0, st>>>(plan->tile_cnt, plan->n_tiles, plan->tile_start, plan->chunk_first, plan->totals));
+    LAUNCH("k_tile_finish", k_tile_finish<<<plan->n_tiles, kKeysPerTile, 0, st>>>(plan->counts, plan->tile_cnt, plan->tile_start, plan->chunk_first,
+                                                                                  plan->cursor, plan->chunks));
+    // until the totals are read back (end of this call) the host uses upper bounds; kernels skip sentinels / read the chunk count on device
+    plan->n_stream = std::min<int64_t>(plan->stream_cap, (n + kStreamAlign - 1) / kStreamAlign * kStreamAlign + (int64_t)kStreamAlign * plan->n_tiles);
+    plan->n_chunks = (int)std::min<int64_t>(plan->chunk_cap, n / kChunkEvents + plan->n_tiles + 1);
+    CU(cudaMemsetAsync(plan->ev_xy, 0xff, (size_t)plan->n_stream * sizeof(uint32_t), st));
     LAUNCH("k_event_mask", k_event_mask<<<(int)((plan->HW + 255) / 256), 256, 0, st>>>(plan->counts, plan->H, plan->W, plan->tiles_x, plan->mask));
     if (n > 0) {
         const int grid = event_grid(plan, n, 256);
         LAUNCH("k_scatter_events", k_scatter_events<<<grid, 256, 0, st>>>(xs, ys, ts, n, plan->H, plan->W, plan->tiles_x, plan->cursor, plan->ev_xy, plan->ev_t, plan->perm));
         // stable order inside each pixel (by original index = by time), then the buffers swap roles
-        LAUNCH("k_rank_sort_segments", k_rank_sort_segments<<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->perm, n, plan->W, plan->tiles_x, plan->counts,
-                                                                                   plan->cursor, plan->ev_t2, plan->perm2));
+        LAUNCH("k_rank_sort_segments", k_rank_sort_segments<<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->perm, plan->n_stream, plan->W, plan->tiles_x,
+                                                                                   plan->counts, plan->cursor, plan->ev_t2, plan->perm2));
         std::swap(plan->ev_t, plan->ev_t2);
         std::swap(plan->perm, plan->perm2);
-    }
-    {   // sentinel padding up to a whole group of kEvK events
-        const int64_t n_pad = (n + kEvK - 1) / kEvK * kEvK;
-        if (n_pad > n) CU(cudaMemsetAsync(plan->ev_xy + n, 0xff, (size_t)(n_pad - n) * sizeof(uint32_t), st));
     }
     CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
     LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc));
@@ -570,8 +637,11 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     // validate (the reference's loaders guarantee in-sensor events; a violation would corrupt the gather at
     // event_warpers.py:34-35, so it is an error here).  One 4-byte read back per window.
     CU(cudaMemcpyAsync(plan->h_flag, &plan->sc->error_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(plan->h_flag + 1, plan->totals, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (plan->h_flag[0] != 0) return fail(plan, EINCM_ERANGE, "an event lies outside the %dx%d sensor", plan->H, plan->W);
+    plan->n_stream = (int64_t)(unsigned int)plan->h_flag[1];
+    plan->n_chunks = (int)(unsigned int)plan->h_flag[2];
     plan->window_set = true;
     if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return window_finalize_impl(plan, st);
     return EINCM_OK;
@@ -781,11 +851,11 @@ int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int
     if (plan->n_events == 0) return EINCM_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (plan->exact)
-        LAUNCH("k_rounded_pixels", k_rounded_pixels<true><<<event_grid(plan, plan->n_events, 256), 256, 0, st>>>(
-            plan->ev_xy, plan->ev_t, plan->perm, plan->n_events, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));
+        LAUNCH("k_rounded_pixels", k_rounded_pixels<true><<<event_grid(plan, plan->n_stream, 256), 256, 0, st>>>(
+            plan->ev_xy, plan->ev_t, plan->perm, plan->n_stream, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));
     else
-        LAUNCH("k_rounded_pixels", k_rounded_pixels<false><<<event_grid(plan, plan->n_events, 256), 256, 0, st>>>(
-            plan->ev_xy, plan->ev_t, plan->perm, plan->n_events, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));
+        LAUNCH("k_rounded_pixels", k_rounded_pixels<false><<<event_grid(plan, plan->n_stream, 256), 256, 0, st>>>(
+            plan->ev_xy, plan->ev_t, plan->perm, plan->n_stream, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));
     return EINCM_OK;
 }
 

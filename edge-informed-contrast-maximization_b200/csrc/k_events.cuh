@@ -42,6 +42,7 @@ k_splat(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, int
     const int64_t HW = (int64_t)H * W;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t xy = ev_xy[e];
+        if (xy == 0xffffffffu) continue;                     // padding sentinel of the sorted stream (k_prep.cuh)
         const double t = ev_t[e];
         const int x = xy & 0xffffu, y = xy >> 16;
         const double2 th = theta_full != nullptr ? theta_full[y * W + x] : make_double2(0.0, 0.0);
@@ -79,8 +80,8 @@ k_backward_events(const uint32_t* __restrict__ ev_xy, const double* __restrict__
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_round; e += (int64_t)gridDim.x * blockDim.x) {
         double gx_acc = 0.0, gy_acc = 0.0;
         uint32_t xy = 0xffffffffu;
-        if (e < n) {
-            xy = ev_xy[e];
+        if (e < n) xy = ev_xy[e];
+        if (xy != 0xffffffffu) {
             const double t = ev_t[e];
             const int x = xy & 0xffffu, y = xy >> 16;
             const double2 th = theta_full[y * W + x];
@@ -120,7 +121,7 @@ k_backward_events(const uint32_t* __restrict__ ev_xy, const double* __restrict__
         }
         const uint32_t prev = __shfl_up_sync(0xffffffffu, xy, 1);
         const bool head = (lane == 0) || (prev != xy);
-        if (head && e < n) {
+        if (head && xy != 0xffffffffu) {
             const int x = xy & 0xffffu, y = xy >> 16;
             atomicAdd(&G[(y * W + x) * 2 + 0], gx_acc);
             atomicAdd(&G[(y * W + x) * 2 + 1], gy_acc);

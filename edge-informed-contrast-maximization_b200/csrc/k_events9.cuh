@@ -348,6 +348,7 @@ __global__ void k_rounded_pixels(const uint32_t* __restrict__ ev_xy, const doubl
                                  int32_t* __restrict__ cols_out, int32_t* __restrict__ rows_out) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t xy = ev_xy[e];
+        if (xy == kNoEvent) continue;
         const int x = xy & 0xffffu, y = xy >> 16;
         const double2 th = theta_full[y * W + x];
         const uint32_t o = perm[e];

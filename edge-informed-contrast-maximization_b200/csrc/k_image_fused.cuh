@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "k_events9.cuh"
+#include "k_events_tile.cuh"
 #include "k_image.cuh"
 
 namespace eincm {
@@ -68,22 +69,42 @@ __device__ __forceinline__ FusedAcc fused_block_reduce(FusedAcc a, double (*sh)[
     return a;
 }
 
-// grid (tiles_x, tiles_y, R), block (kFTX, 8): each thread owns 2 pixels of a 32x16 tile
+// grid (tiles_x, tiles_y, R), block (kFTX, 8): each thread owns 2 pixels of a 32x16 tile.
+// FIX: the source is the fixed-point image of the tile-privatised splat (k_events_tile.cuh), converted exactly to float64;
+// otherwise the float32 moment records of k_splat9, composed as in k_compose9.
+template <bool FIX>
 __global__ void __launch_bounds__(kFNT)
-k_img_fused1(const float* __restrict__ C, const double* __restrict__ edges, int H, int W, int nb /* tiles per image */,
+k_img_fused1(const void* __restrict__ src, const double* __restrict__ edges, int H, int W, int nb /* tiles per image */,
              double* __restrict__ iwe, double* __restrict__ part /* [R][nb][kFPart] */, DevScalars* sc,
              double alpha, double beta, double gamma, int use_tv, double* __restrict__ loss_out) {
     constexpr int RW = kFTX + 4, RH = kFTY + 4;     // record cells (halo 2)
-    constexpr int IW = kFTX + 2, IH = kFTY + 2;     // composed image cells (halo 1)
-    __shared__ float rec[RH][RW][9];
+    constexpr int IW = kFTX + 2, IH = kFTY + 2;     // image cells (halo 1)
+    __shared__ float rec[FIX ? 1 : RH][FIX ? 1 : RW][9];
     __shared__ double img[IH][IW];
     __shared__ double red[kFNT / 32][kFPart];
     __shared__ bool last;
     const int r = blockIdx.z, R = gridDim.z;
     const int64_t HW = (int64_t)H * W;
-    const float* Cr = C + (int64_t)r * HW * kRec;
     const int x0 = blockIdx.x * kFTX, y0 = blockIdx.y * kFTY;
     const int tid = linear_tid();
+    if (FIX) {
+        const unsigned long long* Fr = reinterpret_cast<const unsigned long long*>(src) + (int64_t)r * HW;
+        constexpr int NIT = (IW * IH + kFNT - 1) / kFNT;
+        unsigned long long v[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k = tid + it * kFNT;
+            const int cy = k / IW, cx = k % IW;
+            const int X = x0 + cx - 1, Y = y0 + cy - 1;
+            v[it] = (k < IW * IH && X >= 0 && X < W && Y >= 0 && Y < H) ? __ldcg(Fr + (int64_t)Y * W + X) : 0ull;
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k = tid + it * kFNT;
+            if (k < IW * IH) (&img[0][0])[k] = (double)(long long)v[it] * kFixToIwe;
+        }
+    } else {
+    const float* Cr = reinterpret_cast<const float*>(src) + (int64_t)r * HW * kRec;
     {
         // all global loads first (independent, in flight together), then the shared-memory stores
         constexpr int NIT = (RW * RH * 3 + kFNT - 1) / kFNT;
@@ -131,6 +152,7 @@ k_img_fused1(const float* __restrict__ C, const double* __restrict__ edges, int 
             v = (centre + g1 * edg + g2 * corners) * kInv2Pi;
         }
         img[cy][cx] = v;
+    }
     }
     __syncthreads();
     FusedAcc acc;

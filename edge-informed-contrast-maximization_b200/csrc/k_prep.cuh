@@ -25,62 +25,99 @@ __global__ void k_histogram(const int16_t* __restrict__ xs, const int16_t* __res
     }
 }
 
-// Exclusive scan of `counts` (n_keys entries) in three launches: block sums, scan of block sums, add-back.
-constexpr int kScanBlock = 1024;
+// ---- layout of the sorted stream ---------------------------------------------------------------------------------
+// Every 16x16 source tile owns one contiguous segment of the sorted stream, padded with kNoEvent sentinels to a multiple of
+// kStreamAlign events (so that a thread's vector load of 4 events never straddles two tiles), and is cut into chunks of
+// <= kChunkEvents events - the work items of the tile-privatised event kernels (k_events_tile.cuh).
+constexpr int kKeysPerTile = kSortTile * kSortTile;     // 256 sort keys (pixels) per tile
+constexpr unsigned int kStreamAlign = 4;
+constexpr unsigned int kChunkEvents = 1024;
 
-__global__ void k_scan_block_sums(const unsigned int* __restrict__ counts, int n_keys, unsigned int* __restrict__ block_sums) {
-    __shared__ unsigned int sh[32];
-    const int i = blockIdx.x * kScanBlock + threadIdx.x;
-    unsigned int v = (i < n_keys) ? counts[i] : 0u;
+struct Chunk { uint32_t start, count; };   // count is a multiple of kStreamAlign, <= kChunkEvents
+
+// tile_cnt[t] = number of events of tile t
+__global__ void __launch_bounds__(kKeysPerTile)
+k_tile_counts(const unsigned int* __restrict__ counts, unsigned int* __restrict__ tile_cnt) {
+    __shared__ unsigned int sh[kKeysPerTile / 32];
+    unsigned int v = counts[blockIdx.x * kKeysPerTile + threadIdx.x];
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        v = sh[threadIdx.x];
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
+    if (threadIdx.x == 0) {
+        unsigned int s = 0;
+        for (int k = 0; k < kKeysPerTile / 32; ++k) s += sh[k];
+        tile_cnt[blockIdx.x] = s;
     }
 }
 
-// single block: exclusive scan of up to 1024*1024/kScanBlock block sums, serially chunked
-__global__ void k_scan_of_block_sums(unsigned int* __restrict__ block_sums, int n_blocks) {
-    __shared__ unsigned int sh[kScanBlock];
-    __shared__ unsigned int carry;
-    if (threadIdx.x == 0) carry = 0;
+// single CTA of 1024 threads: exclusive scans over the tiles of (padded event count, chunk count), 1024 tiles per round.
+// totals[0] = padded stream length, totals[1] = number of chunks.
+__global__ void __launch_bounds__(1024)
+k_tile_layout(const unsigned int* __restrict__ tile_cnt, int n_tiles, unsigned int* __restrict__ tile_start,
+              unsigned int* __restrict__ chunk_first, unsigned int* __restrict__ totals) {
+    __shared__ unsigned int sh_a[32], sh_b[32];
+    __shared__ unsigned int carry_a, carry_b;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; }
     __syncthreads();
-    for (int base = 0; base < n_blocks; base += kScanBlock) {
-        const int i = base + threadIdx.x;
-        const unsigned int v = (i < n_blocks) ? block_sums[i] : 0u;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < kScanBlock; o <<= 1) {       // Hillis-Steele inclusive scan
-            unsigned int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0u;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const unsigned int cnt = t < n_tiles ? tile_cnt[t] : 0u;
+        const unsigned int a = (cnt + kStreamAlign - 1) / kStreamAlign * kStreamAlign;
+        const unsigned int b = (cnt + kChunkEvents - 1) / kChunkEvents;
+        unsigned int ia = a, ib = b;                         // inclusive warp scans
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ua; ib += ub; }
         }
-        if (i < n_blocks) block_sums[i] = carry + sh[threadIdx.x] - v;
+        if (lane == 31) { sh_a[wid] = ia; sh_b[wid] = ib; }
         __syncthreads();
-        if (threadIdx.x == 0) carry += sh[kScanBlock - 1];
+        if (wid == 0) {
+            unsigned int wa = sh_a[lane], wb = sh_b[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int ua = __shfl_up_sync(0xffffffffu, wa, o), ub = __shfl_up_sync(0xffffffffu, wb, o);
+                if (lane >= o) { wa += ua; wb += ub; }
+            }
+            sh_a[lane] = wa; sh_b[lane] = wb;                // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned int off_a = carry_a + (wid ? sh_a[wid - 1] : 0u) + ia - a;
+        const unsigned int off_b = carry_b + (wid ? sh_b[wid - 1] : 0u) + ib - b;
+        if (t < n_tiles) { tile_start[t] = off_a; chunk_first[t] = off_b; }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry_a += sh_a[31]; carry_b += sh_b[31]; }
         __syncthreads();
     }
+    if (threadIdx.x == 0) { tile_start[n_tiles] = carry_a; chunk_first[n_tiles] = carry_b; totals[0] = carry_a; totals[1] = carry_b; }
 }
 
-// offsets[i] = exclusive prefix of counts; cursor[i] = offsets[i] (scatter cursor); mask[pixel] = count > 0
-__global__ void k_scan_finish(const unsigned int* __restrict__ counts, int n_keys, const unsigned int* __restrict__ block_sums,
-                              unsigned int* __restrict__ cursor) {
-    __shared__ unsigned int sh[kScanBlock];
-    const int i = blockIdx.x * kScanBlock + threadIdx.x;
-    const unsigned int v = (i < n_keys) ? counts[i] : 0u;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < kScanBlock; o <<= 1) {
-        unsigned int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0u;
-        __syncthreads();
-        sh[threadIdx.x] += t;
-        __syncthreads();
+// one CTA per tile: cursor[key] = tile_start + exclusive prefix of the tile's key counts; chunk records of the tile
+__global__ void __launch_bounds__(kKeysPerTile)
+k_tile_finish(const unsigned int* __restrict__ counts, const unsigned int* __restrict__ tile_cnt, const unsigned int* __restrict__ tile_start,
+              const unsigned int* __restrict__ chunk_first, unsigned int* __restrict__ cursor, Chunk* __restrict__ chunks) {
+    __shared__ unsigned int sh[kKeysPerTile / 32];
+    const int t = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int v = counts[t * kKeysPerTile + threadIdx.x];
+    unsigned int iv = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, iv, o);
+        if (lane >= o) iv += u;
     }
-    if (i < n_keys) cursor[i] = block_sums[blockIdx.x] + sh[threadIdx.x] - v;
+    if (lane == 31) sh[wid] = iv;
+    __syncthreads();
+    unsigned int before = 0;
+    for (int k = 0; k < wid; ++k) before += sh[k];
+    const unsigned int start = tile_start[t];
+    cursor[t * kKeysPerTile + threadIdx.x] = start + before + iv - v;
+    const unsigned int cnt = tile_cnt[t];
+    const unsigned int padded = (cnt + kStreamAlign - 1) / kStreamAlign * kStreamAlign;
+    const unsigned int nch = (cnt + kChunkEvents - 1) / kChunkEvents, first = chunk_first[t];
+    for (unsigned int j = threadIdx.x; j < nch; j += kKeysPerTile) {
+        Chunk c;
+        c.start = start + j * kChunkEvents;
+        c.count = min(kChunkEvents, padded - j * kChunkEvents);
+        chunks[first + j] = c;
+    }
 }
 
 // Scatter events into pixel-sorted order.  ev_xy packs (x | y << 16); perm keeps the original index
@@ -112,6 +149,7 @@ __global__ void k_rank_sort_segments(const uint32_t* __restrict__ ev_xy, const d
                                      uint32_t* __restrict__ perm_out) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t xy = ev_xy[e];
+        if (xy == 0xffffffffu) continue;                    // padding sentinel (n = capacity of the padded stream)
         const int key = sort_key(xy & 0xffffu, xy >> 16, W, tiles_x);
         const unsigned int cnt = counts[key], end = cursor_end[key], start = end - cnt;
         const uint32_t p = perm[e];

@@ -50,6 +50,9 @@ extern "C" {
                                               float64 reference to ~1e-13).  Default: float32 moment splat with float64 coordinates
                                               (bit-exact pixel indices, objective within ~1e-7 relative) */
 
+#define EINCM_FLAG_MOMENT_SPLAT      0x8u  /* legacy float32 "moment" splat through L2 vector reductions instead of the shared-memory
+                                              tile windows (kept for A/B measurements; results agree to ~1e-7) */
+
 /* theta -> sensor-size resize method (reference configs/main.yaml:27 `scale_theta_to_sensor_size_method`) */
 #define EINCM_METHOD_BILINEAR 0
 
