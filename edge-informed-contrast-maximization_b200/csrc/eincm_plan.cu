@@ -19,7 +19,6 @@
 #include "k_prep.cuh"
 #include "k_theta.cuh"
 #include "k_events.cuh"
-#include "k_events9.cuh"
 #include "k_events_tile.cuh"
 #include "k_image.cuh"
 #include "k_image_fused.cuh"
@@ -42,7 +41,7 @@ struct eincm_plan {
     int device = 0, H = 0, W = 0, max_refs = 0, sm_count = 148;
     int64_t HW = 0, max_events = 0;
     unsigned flags = 0;
-    bool wrap = true, exact = false, moments = false;   // moments: legacy float32 moment splat (EINCM_FLAG_MOMENT_SPLAT)
+    bool wrap = true, exact = false;
     int split_rank = 0, split_world = 1;   // event-split plans: rank 0 alone adds the (replicated) TV gradient
     // window state
     int64_t n_events = 0;
@@ -50,7 +49,9 @@ struct eincm_plan {
     int n_chunks = 0, chunk_cap = 0, n_tiles = 0;
     int R = 0;
     bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
-    bool fused_pending = false;   // the last forward left the moment records un-composed for the fused image pass
+    bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
+    int coop_ctas = 0;            // co-resident CTAs of k_image_pass
+    bool fused_pending = false;   // the last forward left the fixed-point images for the fused image pass (no float64 copy yet)
     RefTimes tref{};
     // last evaluation
     int last_h = 0, last_w = 0;
@@ -71,7 +72,7 @@ struct eincm_plan {
     uint8_t* mask = nullptr;
     double2 *theta_full = nullptr, *Gtv = nullptr, *partial = nullptr;
     double *G = nullptr, *iwe = nullptr, *zero_iwe = nullptr, *dldi = nullptr, *edges = nullptr;
-    float *C9 = nullptr, *dldi32 = nullptr;            // fast path: moment records [R][H*W][12], float copy of dL/dIWE
+    float* dldi32 = nullptr;                           // default path: float32 copy of dL/dIWE, scaled by 1/(2 pi)
     double *sbar = nullptr, *gNdiv = nullptr;          // delta != 0 only, allocated on first use
     double* part = nullptr;                            // per-CTA partials of the two-level reductions
     int part_doubles = 0;
@@ -202,12 +203,6 @@ int event_grid(const eincm_plan* p, int64_t n, int threads) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 8));
 }
 
-// grid of the grouped event kernels: one thread per group of kEvK events, whole CTAs, capped (grid-stride beyond the cap)
-int group_grid(const eincm_plan* p, int64_t n_groups) {
-    const int64_t want = (n_groups + 255) / 256;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 32));
-}
-
 int img_tiles_x(const eincm_plan* p) { return (p->W + kImgTX - 1) / kImgTX; }
 int img_tiles_y(const eincm_plan* p) { return (p->H + kImgTY - 1) / kImgTY; }
 int img_nb_flat(const eincm_plan* p) { return (int)std::min<int64_t>((p->HW + kImgNT - 1) / kImgNT, (int64_t)p->sm_count * 4); }
@@ -251,17 +246,11 @@ int window_finalize_impl(eincm_plan* plan, cudaStream_t st) {
     return EINCM_OK;
 }
 
-int compose_images(eincm_plan* plan, int n_img, double* out, cudaStream_t st) {
-    const int H = plan->H, W = plan->W;
-    const dim3 grid((W + kCmpTX - 1) / kCmpTX, (H + kCmpTY - 1) / kCmpTY, n_img), block(kCmpTX, kCmpTY);
-    LAUNCH("k_compose9", k_compose9<<<grid, block, 0, st>>>(plan->C9, H, W, out));
-    return EINCM_OK;
-}
-
 // Builds n_img images of warped events (one per reference time in `tref`) from the staged events: exact mode = nine
-// float64 scatter-adds per event and image; fast mode = moment splat + compose (k_events9.cuh).
+// float64 scatter-adds per event and image; default = tile-privatised fixed-point splat (k_events_tile.cuh), optionally
+// converted to a float64 image.
 int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const RefTimes& tref, double* out, const char* tag,
-                 cudaStream_t st, bool compose = true, bool record_windows = false) {
+                 cudaStream_t st, bool to_f64 = true, bool record_windows = false) {
     const int64_t n = plan->n_events > 0 ? plan->n_stream : 0;      // padded stream: sentinels are skipped by the kernels
     const int H = plan->H, W = plan->W;
     if (plan->exact) {
@@ -273,37 +262,23 @@ int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const R
         }
         return EINCM_OK;
     }
-    if (!plan->moments) {
-        CU(cudaMemsetAsync(plan->iwe_fix, 0, (size_t)n_img * plan->HW * sizeof(unsigned long long), st));
-        if (n > 0) {
-            const int grid = std::max(1, plan->n_chunks);
-            int4* cw = record_windows ? plan->chunk_win : nullptr;
+    if (!plan->fix_clean) CU(cudaMemsetAsync(plan->iwe_fix, 0, (size_t)plan->max_refs * plan->HW * sizeof(unsigned long long), st));
+    plan->fix_clean = false;
+    if (n > 0) {
+        const int grid = std::max(1, plan->n_chunks);
+        int4* cw = record_windows ? plan->chunk_win : nullptr;
 #define SPLATT(WR, RB) LAUNCH(tag, k_splat_tile<WR, RB><<<grid, 256, RB * kWinCap * sizeof(uint32_t), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
-                                   plan->totals + 1, theta_full, H, W, n_img, tref, plan->iwe_fix, cw))
+                               plan->totals + 1, theta_full, H, W, n_img, tref, plan->iwe_fix, cw))
 #define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
-                                                                 case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
-            if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
+                                                             case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
+        if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
 #undef SPLATT_RB
 #undef SPLATT
-        }
-        if (!compose) return EINCM_OK;
-        const int64_t cells = (int64_t)n_img * plan->HW;
-        LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, out));
-        return EINCM_OK;
     }
-    CU(cudaMemsetAsync(plan->C9, 0, (size_t)n_img * plan->HW * kRec * sizeof(float), st));
-    if (n > 0) {
-        const int64_t n_groups = (n + kEvK - 1) / kEvK;
-        const int grid = group_grid(plan, n_groups);
-#define SPLAT9(WR, RB) LAUNCH(tag, k_splat9<WR, RB><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n_groups, theta_full, H, W, n_img, tref, plan->C9))
-#define SPLAT9_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLAT9(WR, 1); break; case 2: SPLAT9(WR, 2); break; \
-                                                                 case 3: SPLAT9(WR, 3); break; default: SPLAT9(WR, 4); } } while (0)
-        if (plan->wrap) SPLAT9_RB(true); else SPLAT9_RB(false);
-#undef SPLAT9_RB
-#undef SPLAT9
-    }
-    if (!compose) return EINCM_OK;
-    return compose_images(plan, n_img, out, st);
+    if (!to_f64) return EINCM_OK;
+    const int64_t cells = (int64_t)n_img * plan->HW;
+    LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, out));
+    return EINCM_OK;
 }
 
 int forward_events_impl(eincm_plan* plan, const double* theta, const double* prev, double a_ho, int h, int w,
@@ -321,7 +296,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
         const dim3 block(32, 8), grid((plan->W + 31) / 32, (plan->H + 7) / 8);
         LAUNCH("k_upsample_theta", k_upsample_theta<<<grid, block, 0, st>>>(theta, prev, a_ho, h, w, plan->H, plan->W, ty, tx, plan->theta_full));
     }
-    // default path (float32 moments, single GPU, delta == 0): the records are composed inside the fused image pass
+    // default path (single GPU, delta == 0): the fixed-point images are consumed by the fused image pass directly
     plan->fused_pending = !plan->exact && !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && hp->delta == 0.0;
     if ((rc = splat_images(plan, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
@@ -342,12 +317,8 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     const dim3 gridT(img_tiles_x(plan), img_tiles_y(plan), R);
     const int nbT = gridT.x * gridT.y;
     if (plan->fused_pending && use_div) {        // hparams changed between the split-phase calls: fall back to the unfused pass
-        if (plan->moments) {
-            if ((rc = compose_images(plan, R, plan->iwe, st))) return rc;
-        } else {
-            const int64_t cells = (int64_t)R * plan->HW;
-            LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, plan->iwe));
-        }
+        const int64_t cells = (int64_t)R * plan->HW;
+        LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, plan->iwe));
         plan->fused_pending = false;
     }
     if (plan->fused_pending) {
@@ -355,19 +326,20 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
             LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
         }
-        const dim3 gridF((W + kFTX - 1) / kFTX, (H + kFTY - 1) / kFTY, R), blockF(kFTX, 8);
-        const int nbF1 = gridF.x * gridF.y;
         const int tvb = ((W + kTvTX - 1) / kTvTX) * ((H + kTvTY - 1) / kTvTY);
-        double* partF = plan->part + 2 * tvb;                    // k_tv's partials live at the start of `part`
-        if (plan->moments)
-            LAUNCH("k_img_fused1", k_img_fused1<false><<<gridF, blockF, 0, st>>>(plan->C9, plan->edges, H, W, nbF1, plan->iwe, partF, plan->sc,
-                                                                                 hp->alpha, hp->beta, hp->gamma, use_tv ? 1 : 0, loss_out));
-        else
-            LAUNCH("k_img_fused1", k_img_fused1<true><<<gridF, blockF, 0, st>>>(plan->iwe_fix, plan->edges, H, W, nbF1, plan->iwe, partF, plan->sc,
-                                                                                hp->alpha, hp->beta, hp->gamma, use_tv ? 1 : 0, loss_out));
+        ImagePassArgs ia{};
+        ia.fix = plan->iwe_fix; ia.edges = plan->edges; ia.iwe = plan->iwe;
+        ia.part = plan->part + 2 * tvb;                          // k_tv's partials live at the start of `part`
+        ia.sc = plan->sc; ia.dldi = plan->dldi; ia.dldi32 = plan->dldi32; ia.loss_out = loss_out;
+        ia.zero_buf = nullptr; ia.n_zero = 0;
+        ia.H = H; ia.W = W; ia.R = R; ia.tiles_x = (W + kFTX - 1) / kFTX; ia.tiles_y = (H + kFTY - 1) / kFTY;
+        ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0; ia.want_grad = want_grad ? 1 : 0;
+        const int gridI = std::max(1, std::min(plan->coop_ctas, ia.tiles_x * ia.tiles_y * R));
+        void* kargs[] = {(void*)&ia};
+        LAUNCH("k_image_pass", cudaLaunchCooperativeKernel((const void*)k_image_pass, dim3(gridI), dim3(kFTX, 8), kargs, sizeof(ImagePassSmem), st));
         plan->fused_pending = false;
+        plan->fix_clean = true;                                  // the pass clears the cells it has read
         if (!want_grad) return EINCM_OK;
-        LAUNCH("k_img_fused3", k_img_fused3<<<gridF, blockF, 0, st>>>(plan->iwe, plan->edges, H, W, plan->sc, plan->dldi, plan->dldi32));
     } else {
         if (use_div) {
             if ((rc = ensure_zero_div(plan, st))) return rc;
@@ -407,7 +379,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             else
                 LAUNCH("k_backward_events", k_backward_events<false><<<grid, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n, plan->theta_full, H, W, R,
                                                                                            plan->tref, plan->dldi, plan->G));
-        } else if (!plan->moments) {
+        } else {
             const int gridT2 = std::max(1, plan->n_chunks);
 #define BWDT(WR, RB) LAUNCH("k_backward_events", k_backward_tile<WR, RB><<<gridT2, 256, RB * kWinCap * sizeof(float), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
                                    plan->totals + 1, plan->theta_full, H, W, R, plan->tref, plan->dldi32, plan->chunk_win, plan->G))
@@ -416,16 +388,6 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             if (plan->wrap) BWDT_RB(true); else BWDT_RB(false);
 #undef BWDT_RB
 #undef BWDT
-        } else {
-            const int64_t n_groups = (n + kEvK - 1) / kEvK;
-            const int gg = group_grid(plan, n_groups);
-#define BWD9(WR, RB) LAUNCH("k_backward_events", k_backward9<WR, RB><<<gg, 256, 0, st>>>(plan->ev_xy, plan->ev_t, n_groups, plan->theta_full, H, W, R, \
-                                                                                         plan->tref, plan->dldi32, plan->dldi, plan->G))
-#define BWD9_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BWD9(WR, 1); break; case 2: BWD9(WR, 2); break; \
-                                                           case 3: BWD9(WR, 3); break; default: BWD9(WR, 4); } } while (0)
-            if (plan->wrap) BWD9_RB(true); else BWD9_RB(false);
-#undef BWD9_RB
-#undef BWD9
         }
     }
     AxisTaps ty, tx;
@@ -494,8 +456,16 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     plan->device = device; plan->H = H; plan->W = W; plan->HW = (int64_t)H * W; plan->max_events = max_events;
     plan->max_refs = max_refs; plan->flags = flags; plan->wrap = !(flags & EINCM_FLAG_NO_WRAP_NEGATIVE);
     plan->exact = (flags & EINCM_FLAG_EXACT_F64) != 0;
-    plan->moments = !plan->exact && (flags & EINCM_FLAG_MOMENT_SPLAT) != 0;
     plan->sm_count = prop.multiProcessorCount;
+    {
+        int per_sm = 0;
+        if ((e = cudaFuncSetAttribute((const void*)k_image_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImagePassSmem))) != cudaSuccess ||
+            (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_image_pass, kFNT, sizeof(ImagePassSmem))) != cudaSuccess || per_sm < 1) {
+            delete plan;
+            return fail(nullptr, EINCM_ECUDA, "occupancy query of the cooperative image pass failed (%s)", cudaGetErrorString(e));
+        }
+        plan->coop_ctas = plan->sm_count * std::min(per_sm, 3);
+    }
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
     plan->n_tiles = plan->tiles_x * ((H + kSortTile - 1) / kSortTile);
     plan->n_keys = plan->n_tiles * kKeysPerTile;
@@ -521,9 +491,8 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->partial, (size_t)kGatherMaxTiles * 2 + (size_t)4 * plan->sm_count));
         CU(dmalloc(&plan->G, HW * 2)); CU(dmalloc(&plan->iwe, RR * HW)); CU(dmalloc(&plan->zero_iwe, HW));
         CU(dmalloc(&plan->dldi, RR * HW)); CU(dmalloc(&plan->edges, RR * HW));
-        if (plan->moments) CU(dmalloc(&plan->C9, RR * HW * kRec));
-        if (!plan->exact) CU(dmalloc(&plan->dldi32, RR * HW));
-        if (!plan->exact && !plan->moments) {
+        if (!plan->exact) {
+            CU(dmalloc(&plan->dldi32, RR * HW));
             CU(dmalloc(&plan->iwe_fix, RR * HW));
             CU(dmalloc(&plan->chunk_win, (size_t)plan->chunk_cap * RR));
         }
@@ -553,7 +522,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
                     plan->chunk_first, plan->totals, plan->chunks, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
-                    plan->part, plan->sc, plan->C9, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
+                    plan->part, plan->sc, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& kv : plan->taps_cache) if (kv.second.blob) cudaFree(kv.second.blob);

@@ -22,10 +22,57 @@
 
 #include "common.cuh"
 #include "k_events.cuh"
-#include "k_events9.cuh"
 #include "k_prep.cuh"
 
 namespace eincm {
+
+constexpr int kEvK = 4;                    // events per thread (one 128-bit load of packed coordinates, two of timestamps)
+constexpr uint32_t kNoEvent = 0xffffffffu; // padding sentinel of the sorted stream
+constexpr int kMaxRB = 4;                  // reference times processed per pass over a chunk
+
+// Warp of one event to one reference time on the default path.  Same float64 arithmetic, in the same order, as warp_event
+// (event_warpers.py:34-35: x' = x - (theta * dt) * 1.0), but rint() and the int conversion use the 2^52 magic constant
+// (two DADDs instead of F2I + I2F on the slow conversion pipe): for |x'| < 2^31, (x' + M) - M == rint(x') under
+// round-half-to-even and the low word of (x' + M) is that integer.  `cls`: 0 = dropped (non-finite / absurdly far),
+// 1 = centre is an interior pixel (fast record path), 2 = border / outside (per-tap index rule).
+struct Hit { int rx, ry; float fx, fy; int cls; };
+
+__device__ __forceinline__ Hit warp_hit(double xd, double yd, double thx, double thy, double dt, int H, int W) {
+    constexpr double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+    const double xw = __dsub_rn(xd, __dmul_rn(thx, dt));
+    const double yw = __dsub_rn(yd, __dmul_rn(thy, dt));
+    const bool ok = (fabs(xw) < 1.0e9) && (fabs(yw) < 1.0e9);      // false for NaN
+    const double sx = __dadd_rn(xw, kMagic), sy = __dadd_rn(yw, kMagic);
+    Hit h;
+    h.rx = __double2loint(sx);
+    h.ry = __double2loint(sy);
+    h.fx = (float)__dsub_rn(xw, __dsub_rn(sx, kMagic));
+    h.fy = (float)__dsub_rn(yw, __dsub_rn(sy, kMagic));
+    const bool interior = ((unsigned)(h.rx - 1) < (unsigned)(W - 2)) && ((unsigned)(h.ry - 1) < (unsigned)(H - 2));
+    h.cls = ok ? (interior ? 1 : 2) : 0;
+    return h;
+}
+
+struct EventGroup {
+    uint32_t xy[kEvK];
+    double t[kEvK];
+};
+
+__device__ __forceinline__ void load_group(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, int64_t g, EventGroup& G) {
+    static_assert(kEvK == 4, "one uint4 of packed coordinates per thread");
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(ev_xy) + g);
+    const double2 ta = __ldg(reinterpret_cast<const double2*>(ev_t) + 2 * g);
+    const double2 tb = __ldg(reinterpret_cast<const double2*>(ev_t) + 2 * g + 1);
+    G.xy[0] = q.x; G.xy[1] = q.y; G.xy[2] = q.z; G.xy[3] = q.w;
+    G.t[0] = ta.x; G.t[1] = ta.y; G.t[2] = tb.x; G.t[3] = tb.y;
+}
+
+__device__ __forceinline__ void red_G(double* __restrict__ G, int W, uint32_t xy, float sx, float sy) {
+    double* g = G + ((int64_t)(xy >> 16) * W + (xy & 0xffffu)) * 2;
+    atomicAdd(g, (double)sx);
+    atomicAdd(g + 1, (double)sy);
+}
+
 
 constexpr int kChunk = (int)kChunkEvents;   // events per chunk = kEvK events per thread x 256 threads
 static_assert(kChunk == kEvK * 256 && kStreamAlign == kEvK, "one chunk = one CTA pass of kEvK events per thread");
@@ -358,6 +405,31 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
         const uint32_t prev = __shfl_up_sync(0xffffffffu, run_xy, 1);
         const bool head = (lane == 0) || (prev != run_xy);
         if (head && run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
+    }
+}
+
+// ---- debug tap: Xs_rounded (event_utils.py:33) of reference r, written back in the original event order ----
+// EXACT selects the conversion used by the float64 nine-tap kernels (cvt.rni), otherwise the magic-constant rint of the tile
+// kernels: the tap reports the indices the active kernels really use.
+template <bool EXACT>
+__global__ void k_rounded_pixels(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const uint32_t* __restrict__ perm,
+                                 int64_t n, const double2* __restrict__ theta_full, int H, int W, double t_ref,
+                                 int32_t* __restrict__ cols_out, int32_t* __restrict__ rows_out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t xy = ev_xy[e];
+        if (xy == kNoEvent) continue;
+        const int x = xy & 0xffffu, y = xy >> 16;
+        const double2 th = theta_full[y * W + x];
+        const uint32_t o = perm[e];
+        if (EXACT) {
+            const Warped wp = warp_event(x, y, th.x, th.y, ev_t[e] - t_ref);
+            cols_out[o] = wp.ok ? wp.rx : INT32_MAX;
+            rows_out[o] = wp.ok ? wp.ry : INT32_MAX;
+        } else {
+            const Hit h = warp_hit((double)x, (double)y, th.x, th.y, ev_t[e] - t_ref, H, W);
+            cols_out[o] = h.cls ? h.rx : INT32_MAX;
+            rows_out[o] = h.cls ? h.ry : INT32_MAX;
+        }
     }
 }
 

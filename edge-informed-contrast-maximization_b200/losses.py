@@ -77,7 +77,7 @@ _default_flags = 0
 
 def configure(exact_f64: Optional[bool] = None, wrap_negative: Optional[bool] = None) -> int:
     """Plan flags used by the module-level callables: ``exact_f64`` selects the float64 nine-tap scatter
-    (EINCM_FLAG_EXACT_F64) instead of the default float32 moment splat; ``wrap_negative=False`` drops votes with negative
+    (EINCM_FLAG_EXACT_F64) instead of the default fixed-point tile splat; ``wrap_negative=False`` drops votes with negative
     row / column instead of wrapping them as JAX does (EINCM_FLAG_NO_WRAP_NEGATIVE).  Returns the flag word."""
     global _default_flags
     if exact_f64 is not None:

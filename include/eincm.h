@@ -47,11 +47,9 @@ extern "C" {
 #define EINCM_FLAG_EVENT_SPLIT       0x2u  /* this plan holds 1/G of a window's events: split-phase calls below */
 
 #define EINCM_FLAG_EXACT_F64         0x4u  /* nine float64 scatter-adds per event and image, float64 tap values (slower; matches the
-                                              float64 reference to ~1e-13).  Default: float32 moment splat with float64 coordinates
-                                              (bit-exact pixel indices, objective within ~1e-7 relative) */
-
-#define EINCM_FLAG_MOMENT_SPLAT      0x8u  /* legacy float32 "moment" splat through L2 vector reductions instead of the shared-memory
-                                              tile windows (kept for A/B measurements; results agree to ~1e-7) */
+                                              float64 reference to ~1e-13).  Default: fixed-point votes (2^-21 of the centre tap) into shared-
+                                              memory windows, float64 coordinates (bit-exact pixel indices, order-independent image sums,
+                                              objective within ~1e-7 relative) */
 
 /* theta -> sensor-size resize method (reference configs/main.yaml:27 `scale_theta_to_sensor_size_method`) */
 #define EINCM_METHOD_BILINEAR 0

@@ -83,8 +83,8 @@ def test_loss_at_zero_theta_known_answer(L, R):
     # loss(theta=0) = -(alpha+beta)/R
     w = S.make_window(48, 64, 3000, edge_ts=np.linspace(0, 1, R) if R > 1 else (0.0,), seed=3)
     loss, _ = L.loss_func(np.zeros((4, 4, 2)), *w.args(), **_kw(w))
-    # float32 moment splat: border events take scalar float32 reductions whose order differs between the zero-IWE and IWE_r
-    assert loss == pytest.approx(-(20.0 + 35.0) / R, rel=1e-6)
+    # fixed-point votes are order-independent: IWE_r == zero-IWE exactly at theta = 0
+    assert loss == pytest.approx(-(20.0 + 35.0) / R, rel=1e-12)
     L.configure(exact_f64=True)
     try:
         loss, _ = L.loss_func(np.zeros((4, 4, 2)), *w.args(), **_kw(w))
@@ -102,7 +102,7 @@ def test_intermediates_and_bit_exact_pixel_indices(L, tiny, exact):
     p = P.Plan(tiny.sensor_size, max_events=len(tiny.xs), max_refs=3, flags=P.FLAG_EXACT_F64 if exact else 0)
     p.set_window(*tiny.args())
     loss, grad = p.value_and_grad_host(th, P.make_hparams(20.0, 35.0, 0.0, 0.0, 1))
-    # per-pixel image values: float32 moment sums (order-dependent rounding) in the default mode, float64 in EXACT_F64
+    # per-pixel image values: votes quantised to 2^-21 of the centre tap in the default mode, float64 in EXACT_F64
     rt, at, rd = (1e-12, 1e-14, 1e-9) if exact else (2e-5, 1e-7, 1e-4)
     np.testing.assert_allclose(p.zero_iwe().cpu().numpy(), inter['zero_iwe'], rtol=rt, atol=at)
     np.testing.assert_allclose(p.iwe().cpu().numpy(), inter['iwes'], rtol=rt, atol=at)
