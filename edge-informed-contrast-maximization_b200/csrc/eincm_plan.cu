@@ -49,6 +49,8 @@ struct eincm_plan {
     int n_chunks = 0, chunk_cap = 0, n_tiles = 0;
     int R = 0;
     bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
+    ThetaSrc tsrc{};              // flow operand of the last forward pass
+    bool theta_full_valid = false;
     bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
     int coop_ctas = 0;            // co-resident CTAs of k_image_pass
     bool fused_pending = false;   // the last forward left the fixed-point images for the fused image pass (no float64 copy yet)
@@ -249,7 +251,7 @@ int window_finalize_impl(eincm_plan* plan, cudaStream_t st) {
 // Builds n_img images of warped events (one per reference time in `tref`) from the staged events: exact mode = nine
 // float64 scatter-adds per event and image; default = tile-privatised fixed-point splat (k_events_tile.cuh), optionally
 // converted to a float64 image.
-int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const RefTimes& tref, double* out, const char* tag,
+int splat_images(eincm_plan* plan, const ThetaSrc& T, const double2* theta_full, int n_img, const RefTimes& tref, double* out, const char* tag,
                  cudaStream_t st, bool to_f64 = true, bool record_windows = false) {
     const int64_t n = plan->n_events > 0 ? plan->n_stream : 0;      // padded stream: sentinels are skipped by the kernels
     const int H = plan->H, W = plan->W;
@@ -268,7 +270,7 @@ int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const R
         const int grid = std::max(1, plan->n_chunks);
         int4* cw = record_windows ? plan->chunk_win : nullptr;
 #define SPLATT(WR, RB) LAUNCH(tag, k_splat_tile<WR, RB><<<grid, 256, RB * kWinCap * sizeof(uint32_t), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
-                               plan->totals + 1, theta_full, H, W, n_img, tref, plan->iwe_fix, cw))
+                               plan->totals + 1, T, H, W, n_img, tref, plan->iwe_fix, cw))
 #define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
                                                              case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
         if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
@@ -278,6 +280,15 @@ int splat_images(eincm_plan* plan, const double2* theta_full, int n_img, const R
     if (!to_f64) return EINCM_OK;
     const int64_t cells = (int64_t)n_img * plan->HW;
     LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, out));
+    return EINCM_OK;
+}
+
+// dense flow field of the last forward pass (k_upsample_theta), computed at most once per evaluation
+int ensure_theta_full(eincm_plan* plan, cudaStream_t st) {
+    if (plan->theta_full_valid) return EINCM_OK;
+    const dim3 block(32, 8), grid((plan->W + 31) / 32, (plan->H + 7) / 8);
+    LAUNCH("k_upsample_theta", k_upsample_theta<<<grid, block, 0, st>>>(plan->tsrc, plan->H, plan->W, plan->theta_full));
+    plan->theta_full_valid = true;
     return EINCM_OK;
 }
 
@@ -292,13 +303,16 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
     AxisTaps ty, tx;
     if ((rc = build_axis_taps(plan, h, plan->H, &ty))) return rc;
     if ((rc = build_axis_taps(plan, w, plan->W, &tx))) return rc;
-    {
-        const dim3 block(32, 8), grid((plan->W + 31) / 32, (plan->H + 7) / 8);
-        LAUNCH("k_upsample_theta", k_upsample_theta<<<grid, block, 0, st>>>(theta, prev, a_ho, h, w, plan->H, plan->W, ty, tx, plan->theta_full));
+    plan->tsrc = ThetaSrc{theta, prev, a_ho, h, w, ty, tx};
+    plan->theta_full_valid = false;
+    // the dense field is only materialised for the float64 nine-tap kernels and the TV regulariser (and, on demand, the debug tap);
+    // the default event kernels evaluate theta per source tile
+    if (plan->exact || (hp->gamma != 0.0 && hp->cur_pyr_lvl <= 0)) {
+        if ((rc = ensure_theta_full(plan, st))) return rc;
     }
     // default path (single GPU, delta == 0): the fixed-point images are consumed by the fused image pass directly
     plan->fused_pending = !plan->exact && !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && hp->delta == 0.0;
-    if ((rc = splat_images(plan, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
+    if ((rc = splat_images(plan, plan->tsrc, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
     plan->forward_done = true;
     return EINCM_OK;
@@ -313,6 +327,8 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     const bool use_tv = hp->gamma != 0.0 && hp->cur_pyr_lvl <= 0;       // losses.py:171
     const bool use_div = hp->delta != 0.0;
     const bool want_grad = grad_out != nullptr || dalpha_out != nullptr;
+    bool g_zeroed = false;               // the cooperative image pass also clears G
+    bool g_zeroed_grad = false;          // ... and the theta-gradient accumulator of k_theta_grad
     const dim3 block(kImgTX, kImgTY);
     const dim3 gridT(img_tiles_x(plan), img_tiles_y(plan), R);
     const int nbT = gridT.x * gridT.y;
@@ -324,6 +340,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     if (plan->fused_pending) {
         if (use_tv) {
             const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
+            if ((rc = ensure_theta_full(plan, st))) return rc;
             LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
         }
         const int tvb = ((W + kTvTX - 1) / kTvTX) * ((H + kTvTY - 1) / kTvTY);
@@ -331,7 +348,12 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         ia.fix = plan->iwe_fix; ia.edges = plan->edges; ia.iwe = plan->iwe;
         ia.part = plan->part + 2 * tvb;                          // k_tv's partials live at the start of `part`
         ia.sc = plan->sc; ia.dldi = plan->dldi; ia.dldi32 = plan->dldi32; ia.loss_out = loss_out;
-        ia.zero_buf = nullptr; ia.n_zero = 0;
+        ia.zero_buf = want_grad ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
+        g_zeroed = want_grad;
+        if (want_grad && h * w <= kGatherMaxTiles) {
+            ia.zero_buf2 = grad_out ? grad_out : plan->grad_buf; ia.n_zero2 = h * w * 2;
+            g_zeroed_grad = true;
+        }
         ia.H = H; ia.W = W; ia.R = R; ia.tiles_x = (W + kFTX - 1) / kFTX; ia.tiles_y = (H + kFTY - 1) / kFTY;
         ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0; ia.want_grad = want_grad ? 1 : 0;
         const int gridI = std::max(1, std::min(plan->coop_ctas, ia.tiles_x * ia.tiles_y * R));
@@ -360,6 +382,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
                                                    plan->sc->coefB, plan->part, plan->sc->ref, &plan->sc->counters[1]));
         if (use_tv) {
             const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
+            if ((rc = ensure_theta_full(plan, st))) return rc;
             LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
         }
         LAUNCH("k_scalars(1)", k_scalars<<<1, 32, 0, st>>>(plan->sc, R, (double)plan->HW, hp->alpha, hp->beta, hp->gamma, hp->delta, use_tv, use_div, 1, loss_out));
@@ -368,7 +391,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         LAUNCH("k_img_C", k_img_C<<<gridT, block, 0, st>>>(plan->iwe, plan->edges, gNdiv, H, W, plan->sc->ref, plan->sc->coefA, plan->sc->coefB, plan->dldi,
                                                                plan->exact ? nullptr : plan->dldi32));
     }
-    CU(cudaMemsetAsync(plan->G, 0, (size_t)plan->HW * 2 * sizeof(double), st));
+    if (!g_zeroed) CU(cudaMemsetAsync(plan->G, 0, (size_t)plan->HW * 2 * sizeof(double), st));
     if (plan->n_events > 0) {
         const int64_t n = plan->n_stream;
         const int grid = event_grid(plan, n, 256);
@@ -382,7 +405,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         } else {
             const int gridT2 = std::max(1, plan->n_chunks);
 #define BWDT(WR, RB) LAUNCH("k_backward_events", k_backward_tile<WR, RB><<<gridT2, 256, RB * kWinCap * sizeof(float), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
-                                   plan->totals + 1, plan->theta_full, H, W, R, plan->tref, plan->dldi32, plan->chunk_win, plan->G))
+                                   plan->totals + 1, plan->tsrc, H, W, R, plan->tref, plan->dldi32, plan->chunk_win, plan->G))
 #define BWDT_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BWDT(WR, 1); break; case 2: BWDT(WR, 2); break; \
                                                            case 3: BWDT(WR, 3); break; default: BWDT(WR, 4); } } while (0)
             if (plan->wrap) BWDT_RB(true); else BWDT_RB(false);
@@ -395,21 +418,32 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
     if ((rc = build_axis_taps(plan, w, W, &tx))) return rc;
     const double2* Gtv = (use_tv && plan->split_rank == 0) ? plan->Gtv : nullptr;
     const int n_el = h * w;
-    CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
     const bool handover = plan->last_prev != nullptr;
-    double* gout = grad_out;
     if (n_el <= kGatherMaxTiles) {
-        int S = std::max(1, (2 * plan->sm_count + n_el - 1) / n_el);
-        S = std::min(S, std::max(1, H / std::max(1, h)));
-        LAUNCH("k_theta_grad_gather", k_theta_grad_gather<<<n_el * S, 256, 0, st>>>((const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, S, ty, tx, plan->partial));
-        LAUNCH("k_grad_out", k_grad_out<<<std::min(plan->sm_count, (n_el + 255) / 256), 256, 0, st>>>(plan->partial, S, nullptr, n_el,
-                                                                               handover ? plan->last_prev : nullptr, plan->last_theta, gout, plan->sc));
+        // accumulate straight into the caller's gradient (an internal buffer when only d/d alpha is wanted)
+        double* gout = grad_out ? grad_out : plan->grad_buf;
+        if (!g_zeroed_grad) CU(cudaMemsetAsync(gout, 0, (size_t)n_el * 2 * sizeof(double), st));
+        // support of one theta element: <= 2 cells of the resize (+ rounding) per axis
+        const int max_ny = std::min(H, 2 * ((H + h - 1) / h) + 2), max_nx = std::min(W, 2 * ((W + w - 1) / w) + 2);
+        const int SX = (max_nx + kTgCols - 1) / kTgCols;
+        const int SY = (max_ny + kTgRows - 1) / kTgRows;
+        const int n_items = n_el * SY * SX;
+        const int gridG = (n_items + kTgWarps - 1) / kTgWarps;
+        if (Gtv != nullptr)
+            LAUNCH("k_theta_grad", k_theta_grad<true><<<gridG, kTgWarps * 32, 0, st>>>(
+                (const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout));
+        else
+            LAUNCH("k_theta_grad", k_theta_grad<false><<<gridG, kTgWarps * 32, 0, st>>>(
+                (const double2*)plan->G, nullptr, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout));
     } else {
+        CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
         CU(cudaMemsetAsync(plan->grad_buf, 0, (size_t)n_el * 2 * sizeof(double), st));
         const dim3 b2(32, 8), g2((W + 31) / 32, (H + 7) / 8);
         LAUNCH("k_theta_grad_scatter", k_theta_grad_scatter<<<g2, b2, 0, st>>>((const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, ty, tx, plan->grad_buf));
         LAUNCH("k_grad_out", k_grad_out<<<std::min(plan->sm_count * 4, (n_el + 255) / 256), 256, 0, st>>>(nullptr, 0, plan->grad_buf, n_el,
-                                                                                   handover ? plan->last_prev : nullptr, plan->last_theta, gout, plan->sc));
+                                                                                   handover ? plan->last_prev : nullptr, plan->last_theta, grad_out, plan->sc));
     }
     if (dalpha_out) CU(cudaMemcpyAsync(dalpha_out, &plan->sc->dalpha, sizeof(double), cudaMemcpyDeviceToDevice, st));
     return EINCM_OK;
@@ -580,7 +614,7 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     LAUNCH("k_tile_counts", k_tile_counts<<<plan->n_tiles, kKeysPerTile, 0, st>>>(plan->counts, plan->tile_cnt));
     LAUNCH("k_tile_layout", k_tile_layout<<<1, 1024, 0, st>>>(plan->tile_cnt, plan->n_tiles, plan->tile_start, plan->chunk_first, plan->totals));
     LAUNCH("k_tile_finish", k_tile_finish<<<plan->n_tiles, kKeysPerTile, 0, st>>>(plan->counts, plan->tile_cnt, plan->tile_start, plan->chunk_first,
-                                                                                  plan->cursor, plan->chunks));
+                                                                                  plan->tiles_x, plan->cursor, plan->chunks));
     // until the totals are read back (end of this call) the host uses upper bounds; kernels skip sentinels / read the chunk count on device
     plan->n_stream = std::min<int64_t>(plan->stream_cap, (n + kStreamAlign - 1) / kStreamAlign * kStreamAlign + (int64_t)kStreamAlign * plan->n_tiles);
     plan->n_chunks = (int)std::min<int64_t>(plan->chunk_cap, n / kChunkEvents + plan->n_tiles + 1);
@@ -600,7 +634,7 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     // zero-warp IWE (losses.py:54): theta = 0 => x' = x for every reference time
     {
         RefTimes z{};
-        int rc = splat_images(plan, nullptr, 1, z, plan->zero_iwe, "k_splat(zero)", st);
+        int rc = splat_images(plan, ThetaSrc{}, nullptr, 1, z, plan->zero_iwe, "k_splat(zero)", st);
         if (rc) return rc;
     }
     // validate (the reference's loaders guarantee in-sensor events; a violation would corrupt the gather at
@@ -734,7 +768,17 @@ double* eincm_zero_iwe_ptr(eincm_plan* plan) { return plan ? plan->zero_iwe : nu
 double* eincm_iwe_ptr(eincm_plan* plan) { return plan ? plan->iwe : nullptr; }
 uint8_t* eincm_mask_ptr(eincm_plan* plan) { return plan ? plan->mask : nullptr; }
 double* eincm_dldi_ptr(eincm_plan* plan) { return plan ? plan->dldi : nullptr; }
-double* eincm_theta_full_ptr(eincm_plan* plan) { return plan ? (double*)plan->theta_full : nullptr; }
+double* eincm_theta_full_ptr(eincm_plan* plan) {
+    if (!plan) return nullptr;
+    // debug tap: the default path does not materialise the dense field - do it now (synchronous, legacy default stream)
+    if (plan->forward_done && !plan->theta_full_valid) {
+        cudaSetDevice(plan->device);
+        cudaDeviceSynchronize();
+        if (ensure_theta_full(plan, (cudaStream_t)0) != EINCM_OK) return nullptr;
+        cudaDeviceSynchronize();
+    }
+    return (double*)plan->theta_full;
+}
 
 int eincm_get_scalars(eincm_plan* plan, double* out_host, int n_doubles, void* cuda_stream) {
     if (!plan || !out_host) return EINCM_EINVAL;
@@ -819,6 +863,10 @@ int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int
     CU(cudaSetDevice(plan->device));
     if (plan->n_events == 0) return EINCM_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    {
+        const int rc = ensure_theta_full(plan, st);
+        if (rc) return rc;
+    }
     if (plan->exact)
         LAUNCH("k_rounded_pixels", k_rounded_pixels<true><<<event_grid(plan, plan->n_stream, 256), 256, 0, st>>>(
             plan->ev_xy, plan->ev_t, plan->perm, plan->n_stream, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));

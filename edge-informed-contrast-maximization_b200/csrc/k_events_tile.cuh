@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "k_events.cuh"
 #include "k_prep.cuh"
+#include "k_theta.cuh"
 
 namespace eincm {
 
@@ -33,23 +34,21 @@ constexpr int kMaxRB = 4;                  // reference times processed per pass
 // Warp of one event to one reference time on the default path.  Same float64 arithmetic, in the same order, as warp_event
 // (event_warpers.py:34-35: x' = x - (theta * dt) * 1.0), but rint() and the int conversion use the 2^52 magic constant
 // (two DADDs instead of F2I + I2F on the slow conversion pipe): for |x'| < 2^31, (x' + M) - M == rint(x') under
-// round-half-to-even and the low word of (x' + M) is that integer.  `cls`: 0 = dropped (non-finite / absurdly far),
-// 1 = centre is an interior pixel (fast record path), 2 = border / outside (per-tap index rule).
-struct Hit { int rx, ry; float fx, fy; int cls; };
+// round-half-to-even and the low word of (x' + M) is that integer.  `ok` is false for non-finite / absurdly far warps
+// (every tap is out of range under either index rule: dropped).
+struct Hit { int rx, ry; float fx, fy; bool ok; };
 
-__device__ __forceinline__ Hit warp_hit(double xd, double yd, double thx, double thy, double dt, int H, int W) {
+__device__ __forceinline__ Hit warp_hit(double xd, double yd, double thx, double thy, double dt) {
     constexpr double kMagic = 6755399441055744.0;   // 1.5 * 2^52
     const double xw = __dsub_rn(xd, __dmul_rn(thx, dt));
     const double yw = __dsub_rn(yd, __dmul_rn(thy, dt));
-    const bool ok = (fabs(xw) < 1.0e9) && (fabs(yw) < 1.0e9);      // false for NaN
     const double sx = __dadd_rn(xw, kMagic), sy = __dadd_rn(yw, kMagic);
     Hit h;
+    h.ok = (fabs(xw) < 1.0e9) && (fabs(yw) < 1.0e9);      // false for NaN
     h.rx = __double2loint(sx);
     h.ry = __double2loint(sy);
     h.fx = (float)__dsub_rn(xw, __dsub_rn(sx, kMagic));
     h.fy = (float)__dsub_rn(yw, __dsub_rn(sy, kMagic));
-    const bool interior = ((unsigned)(h.rx - 1) < (unsigned)(W - 2)) && ((unsigned)(h.ry - 1) < (unsigned)(H - 2));
-    h.cls = ok ? (interior ? 1 : 2) : 0;
     return h;
 }
 
@@ -148,16 +147,45 @@ __device__ __forceinline__ bool in_window(const Window& w, int rx, int ry) {
     return ((unsigned)(rx - w.ox - 1) < (unsigned)(w.pw - 2)) & ((unsigned)(ry - w.oy - 1) < (unsigned)(w.ph - 2));
 }
 
-// float32 copies of one event for the bounding-rectangle pre-pass
-struct EventF { float x, y, t, thx, thy; };
+// Adds the nine pending tap sums to the 3x3 cells around the shared-memory cell `mid` (rows `pitch4` bytes apart): nine
+// `red.shared.add.u32` (ATOMS.ADD without return value) with immediate column offsets.  Callers branch around the whole
+// block: ptxas turns a predicated shared-memory atomic into its own branch, which costs four instructions per vote.
+__device__ __forceinline__ void emit9(uint32_t mid, uint32_t pitch4, const int (&a)[9]) {
+    const uint32_t up = mid - pitch4, dn = mid + pitch4;
+    asm volatile(
+        "red.shared.add.u32 [%0 + -4], %3;\n\tred.shared.add.u32 [%0], %4;\n\tred.shared.add.u32 [%0 + 4], %5;\n\t"
+        "red.shared.add.u32 [%1 + -4], %6;\n\tred.shared.add.u32 [%1], %7;\n\tred.shared.add.u32 [%1 + 4], %8;\n\t"
+        "red.shared.add.u32 [%2 + -4], %9;\n\tred.shared.add.u32 [%2], %10;\n\tred.shared.add.u32 [%2 + 4], %11;"
+        ::"r"(up), "r"(mid), "r"(dn), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8])
+        : "memory");
+}
+
+// theta of the 16x16 source tile at `origin` -> shared memory (zero flow when T.theta is null)
+__device__ __forceinline__ void tile_theta(const ThetaSrc& T, uint32_t origin, int H, int W, double2* __restrict__ th_s) {
+    const int p = threadIdx.x;                       // 256 threads <-> 256 pixels
+    const int x = (int)(origin & 0xffffu) + (p & 15), y = (int)(origin >> 16) + (p >> 4);
+    double2 v = make_double2(0.0, 0.0);
+    if (T.theta != nullptr && x < W && y < H) v = theta_at(T, x, y);
+    th_s[p] = v;
+}
+
+__device__ __forceinline__ double2 event_theta(const double2* __restrict__ th_s, uint32_t xy) {
+    return th_s[((xy >> 12) & 0xf0u) | (xy & 0xfu)];         // (y & 15) * 16 + (x & 15)
+}
 
 // ---- forward -----------------------------------------------------------------------------------------------------
+// One CTA per chunk (grid-stride), RB reference times per pass with one window each.  Per pass: zero the windows, measure
+// the bounding rectangles (float32 pre-pass), vote, flush.  A thread walks its kEvK consecutive events per reference time and
+// merges a vote into the next one when both have the same centre cell (events of one source pixel are time-sorted, so this is
+// common): the nine pending tap sums stay in registers and are only sent to shared memory when the centre changes.  The merge
+// is branch-free (predicated adds / predicated reductions), so diverging lanes cost nothing extra.
 template <bool WRAP, int RB>
 __global__ void __launch_bounds__(256, 3)
 k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
-             const double2* __restrict__ theta_full, int H, int W, int R, const __grid_constant__ RefTimes tref,
+             const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
              unsigned long long* __restrict__ iwe_fix /* [R][H*W] */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
     extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
+    __shared__ double2 th_s[kKeysPerTile];
     __shared__ int sbox[8][RB][4];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
@@ -167,30 +195,29 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
         const Chunk ch = chunks[c];
         EventGroup ev;
         load_chunk_events(ev_xy, ev_t, ch, ev);
-        double2 th[kEvK];
-#pragma unroll
-        for (int k = 0; k < kEvK; ++k) {
-            th[k] = make_double2(0.0, 0.0);
-            if (theta_full != nullptr && ev.xy[k] != kNoEvent)
-                th[k] = __ldg(theta_full + (int)(ev.xy[k] >> 16) * W + (int)(ev.xy[k] & 0xffffu));
-        }
+        tile_theta(T, ch.origin, H, W, th_s);
         for (int r0 = 0; r0 < R; r0 += RB) {
             // zero the windows (whole capacity: a handful of 128-bit stores per thread)
             for (int i = tid; i < RB * kWinCap / 4; i += 256) reinterpret_cast<uint4*>(win)[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();                         // th_s ready (first pass); previous flush done
             // pre-pass: bounding rectangle of the rounded warped pixels per reference time.  float32 arithmetic (error far
             // below the 0.01 px margin for any flow a window can hold); an event the rectangle misses takes the fallback.
             {
-                float lox[RB], loy[RB], hix[RB], hiy[RB];
+                float lox[RB], loy[RB], hix[RB], hiy[RB], trf[RB];
 #pragma unroll
-                for (int r = 0; r < RB; ++r) { lox[r] = 3.0e9f; loy[r] = 3.0e9f; hix[r] = -3.0e9f; hiy[r] = -3.0e9f; }
+                for (int r = 0; r < RB; ++r) {
+                    lox[r] = 3.0e9f; loy[r] = 3.0e9f; hix[r] = -3.0e9f; hiy[r] = -3.0e9f;
+                    trf[r] = (float)tref.t[min(r0 + r, EINCM_MAX_REFS - 1)];
+                }
 #pragma unroll
                 for (int k = 0; k < kEvK; ++k) {
                     if (ev.xy[k] == kNoEvent) continue;
+                    const double2 th = event_theta(th_s, ev.xy[k]);
                     const float xf = (float)(ev.xy[k] & 0xffffu), yf = (float)(ev.xy[k] >> 16), tf = (float)ev.t[k];
-                    const float thx = (float)th[k].x, thy = (float)th[k].y;
+                    const float thx = (float)th.x, thy = (float)th.y;
 #pragma unroll
                     for (int r = 0; r < RB; ++r) {
-                        const float dt = tf - (float)tref.t[min(r0 + r, EINCM_MAX_REFS - 1)];
+                        const float dt = tf - trf[r];
                         const float xw = fmaf(-thx, dt, xf), yw = fmaf(-thy, dt, yf);
                         lox[r] = fminf(lox[r], xw); hix[r] = fmaxf(hix[r], xw);
                         loy[r] = fminf(loy[r], yw); hiy[r] = fmaxf(hiy[r], yw);
@@ -219,26 +246,35 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                 if (chunk_win != nullptr && r0 + tid < R) chunk_win[(int64_t)c * R + r0 + tid] = make_int4(wn.ox, wn.oy, wn.pw, wn.ph);
             }
             __syncthreads();
-            // main pass: nine shared-memory integer atomics per event and reference time
+            // main pass
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 if (r0 + r >= R) continue;
                 const Window wn = swin[r];
-                uint32_t* wr = win + r * kWinCap;
+                const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win + r * kWinCap);
+                const uint32_t pitch4 = (uint32_t)wn.pw * 4u;
                 const double tr = tref.t[r0 + r];
+                int acc[9];
+                uint32_t acc_addr = 0u;               // shared address of the pending centre cell; 0 = nothing pending
+#pragma unroll
+                for (int q = 0; q < 9; ++q) acc[q] = 0;
 #pragma unroll
                 for (int k = 0; k < kEvK; ++k) {
                     if (ev.xy[k] == kNoEvent) continue;
+                    const double2 th = event_theta(th_s, ev.xy[k]);
                     const double xd = (double)(ev.xy[k] & 0xffffu), yd = (double)(ev.xy[k] >> 16);
-                    const Hit h = warp_hit(xd, yd, th[k].x, th[k].y, ev.t[k] - tr, H, W);
-                    if (!h.cls) continue;
+                    const Hit h = warp_hit(xd, yd, th.x, th.y, ev.t[k] - tr);
+                    if (!h.ok) continue;
                     const TapsFix t = taps_fix(h.fx, h.fy);
                     if (in_window(wn, h.rx, h.ry)) {
-                        uint32_t* p = wr + (h.ry - wn.oy) * wn.pw + (h.rx - wn.ox);
+                        const uint32_t addr = wbase + (uint32_t)((h.ry - wn.oy) * wn.pw + (h.rx - wn.ox)) * 4u;
+                        const bool same = addr == acc_addr;
+                        const bool emit = !same && acc_addr != 0u;
+                        // send the pending sums (other centre), then fold them into the new taps when the centre is the same
+                        if (emit) emit9(acc_addr, pitch4, acc);
 #pragma unroll
-                        for (int j = 0; j < 3; ++j)
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) atomicAdd(p + (j - 1) * wn.pw + (i - 1), (uint32_t)t.n[j * 3 + i]);
+                        for (int q = 0; q < 9; ++q) acc[q] = t.n[q] + (same ? acc[q] : 0);
+                        acc_addr = addr;
                     } else {
                         // outside the window: per-tap global reductions with the reference's index rule
                         unsigned long long* img = iwe_fix + (int64_t)(r0 + r) * HW;
@@ -251,9 +287,10 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                             }
                     }
                 }
+                if (acc_addr != 0u) emit9(acc_addr, pitch4, acc);
             }
             __syncthreads();
-            // flush: non-zero window cells -> global fixed-point image (index rule applied here)
+            // flush: non-zero window cells -> global fixed-point image (index rule applied here unless the window is interior)
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 if (r0 + r >= R) continue;
@@ -261,13 +298,14 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                 const uint32_t* wr = win + r * kWinCap;
                 unsigned long long* img = iwe_fix + (int64_t)(r0 + r) * HW;
                 const int cells = wn.pw * wn.ph;
+                const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
                 for (int i = tid; i < cells; i += 256) {
                     const uint32_t v = wr[i];
                     if (v != 0u) {
                         int row, col;
                         cell_to_rc(wn, i, row, col);
                         int rr = wn.oy + row, cc = wn.ox + col;
-                        if (drop_index<WRAP>(rr, cc, H, W)) atomicAdd(img + (int64_t)rr * W + cc, (unsigned long long)v);
+                        if (interior || drop_index<WRAP>(rr, cc, H, W)) atomicAdd(img + (rr * W + cc), (unsigned long long)v);
                     }
                 }
             }
@@ -288,10 +326,11 @@ __global__ void k_fix_to_f64(const unsigned long long* __restrict__ fix, int64_t
 template <bool WRAP, int RB>
 __global__ void __launch_bounds__(256, 3)
 k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
-                const double2* __restrict__ theta_full, int H, int W, int R, const __grid_constant__ RefTimes tref,
+                const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
                 const float* __restrict__ dldi32 /* [R][H][W], scaled by 1/(2 pi) */, const int4* __restrict__ chunk_win,
                 double* __restrict__ G /* [H][W][2] */) {
     extern __shared__ __align__(16) float dwin[];            // [RB][kWinCap]
+    __shared__ double2 th_s[kKeysPerTile];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -300,14 +339,10 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
         const Chunk ch = chunks[c];
         EventGroup ev;
         load_chunk_events(ev_xy, ev_t, ch, ev);
-        double2 th[kEvK];
+        tile_theta(T, ch.origin, H, W, th_s);
         float ax[kEvK], ay[kEvK];
 #pragma unroll
-        for (int k = 0; k < kEvK; ++k) {
-            ax[k] = 0.f; ay[k] = 0.f;
-            th[k] = make_double2(0.0, 0.0);
-            if (ev.xy[k] != kNoEvent) th[k] = __ldg(theta_full + (int)(ev.xy[k] >> 16) * W + (int)(ev.xy[k] & 0xffffu));
-        }
+        for (int k = 0; k < kEvK; ++k) { ax[k] = 0.f; ay[k] = 0.f; }
         for (int r0 = 0; r0 < R; r0 += RB) {
             if (tid < RB && r0 + tid < R) {
                 const int4 q = chunk_win[(int64_t)c * R + r0 + tid];
@@ -323,11 +358,12 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
                 const float* img = dldi32 + (int64_t)(r0 + r) * HW;
                 float* wr = dwin + r * kWinCap;
                 const int cells = wn.pw * wn.ph;
+                const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
                 for (int i = tid; i < cells; i += 256) {
                     int row, col;
                     cell_to_rc(wn, i, row, col);
                     int rr = wn.oy + row, cc = wn.ox + col;
-                    wr[i] = drop_index<WRAP>(rr, cc, H, W) ? __ldg(img + (int64_t)rr * W + cc) : 0.f;
+                    wr[i] = (interior || drop_index<WRAP>(rr, cc, H, W)) ? __ldg(img + (rr * W + cc)) : 0.f;
                 }
             }
             __syncthreads();
@@ -341,9 +377,10 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
 #pragma unroll
                 for (int k = 0; k < kEvK; ++k) {
                     if (ev.xy[k] == kNoEvent) continue;
+                    const double2 th = event_theta(th_s, ev.xy[k]);
                     const double xd = (double)(ev.xy[k] & 0xffffu), yd = (double)(ev.xy[k] >> 16);
-                    const Hit h = warp_hit(xd, yd, th[k].x, th[k].y, ev.t[k] - tr, H, W);
-                    if (!h.cls) continue;
+                    const Hit h = warp_hit(xd, yd, th.x, th.y, ev.t[k] - tr);
+                    if (!h.ok) continue;
                     float d[9];
                     if (in_window(wn, h.rx, h.ry)) {
                         const float* p = wr + (h.ry - wn.oy) * wn.pw + (h.rx - wn.ox);
@@ -426,9 +463,9 @@ __global__ void k_rounded_pixels(const uint32_t* __restrict__ ev_xy, const doubl
             cols_out[o] = wp.ok ? wp.rx : INT32_MAX;
             rows_out[o] = wp.ok ? wp.ry : INT32_MAX;
         } else {
-            const Hit h = warp_hit((double)x, (double)y, th.x, th.y, ev_t[e] - t_ref, H, W);
-            cols_out[o] = h.cls ? h.rx : INT32_MAX;
-            rows_out[o] = h.cls ? h.ry : INT32_MAX;
+            const Hit h = warp_hit((double)x, (double)y, th.x, th.y, ev_t[e] - t_ref);
+            cols_out[o] = h.ok ? h.rx : INT32_MAX;
+            rows_out[o] = h.ok ? h.ry : INT32_MAX;
         }
     }
 }

@@ -90,8 +90,9 @@ struct ImagePassArgs {
     double* dldi;                 // [R][H*W] float64 d loss / d IWE (debug tap) or null
     float* dldi32;                // [R][H*W] float32 d loss / d IWE / (2 pi)
     double* loss_out;
-    double* zero_buf;             // small buffer cleared for the event backward pass (theta gradient accumulators) or null
-    int n_zero;
+    double* zero_buf;             // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
+    double* zero_buf2;
+    int n_zero, n_zero2;
     int H, W, R, tiles_x, tiles_y;
     double alpha, beta, gamma;
     int use_tv, want_grad;
@@ -185,6 +186,8 @@ k_image_pass(const ImagePassArgs A) {
     }
     if (A.zero_buf != nullptr)
         for (int k = b * kFNT + tid; k < A.n_zero; k += G * kFNT) A.zero_buf[k] = 0.0;
+    if (A.zero_buf2 != nullptr)
+        for (int k = b * kFNT + tid; k < A.n_zero2; k += G * kFNT) A.zero_buf2[k] = 0.0;
 
     // ---- phase 1: statistics ----------------------------------------------------------------------------------------------
     FusedAcc acc;

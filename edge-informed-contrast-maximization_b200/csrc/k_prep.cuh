@@ -33,7 +33,7 @@ constexpr int kKeysPerTile = kSortTile * kSortTile;     // 256 sort keys (pixels
 constexpr unsigned int kStreamAlign = 4;
 constexpr unsigned int kChunkEvents = 1024;
 
-struct Chunk { uint32_t start, count; };   // count is a multiple of kStreamAlign, <= kChunkEvents
+struct Chunk { uint32_t start, count, origin, pad; };   // count: multiple of kStreamAlign, <= kChunkEvents; origin: tile corner x | y << 16
 
 // tile_cnt[t] = number of events of tile t
 __global__ void __launch_bounds__(kKeysPerTile)
@@ -94,7 +94,7 @@ k_tile_layout(const unsigned int* __restrict__ tile_cnt, int n_tiles, unsigned i
 // one CTA per tile: cursor[key] = tile_start + exclusive prefix of the tile's key counts; chunk records of the tile
 __global__ void __launch_bounds__(kKeysPerTile)
 k_tile_finish(const unsigned int* __restrict__ counts, const unsigned int* __restrict__ tile_cnt, const unsigned int* __restrict__ tile_start,
-              const unsigned int* __restrict__ chunk_first, unsigned int* __restrict__ cursor, Chunk* __restrict__ chunks) {
+              const unsigned int* __restrict__ chunk_first, int tiles_x, unsigned int* __restrict__ cursor, Chunk* __restrict__ chunks) {
     __shared__ unsigned int sh[kKeysPerTile / 32];
     const int t = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned int v = counts[t * kKeysPerTile + threadIdx.x];
@@ -116,6 +116,8 @@ k_tile_finish(const unsigned int* __restrict__ counts, const unsigned int* __res
         Chunk c;
         c.start = start + j * kChunkEvents;
         c.count = min(kChunkEvents, padded - j * kChunkEvents);
+        c.origin = (uint32_t)((t % tiles_x) * kSortTile) | ((uint32_t)((t / tiles_x) * kSortTile) << 16);
+        c.pad = 0u;
         chunks[first + j] = c;
     }
 }

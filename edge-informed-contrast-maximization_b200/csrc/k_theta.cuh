@@ -20,64 +20,136 @@ struct AxisTaps {
     const int* hi;      // [n_in]  one past the last
 };
 
-// theta_full[y][x][c] = sum_ij Wy[i][y] Wx[j][x] theta[i][j][c]; optional handover blend
-// theta_ho = a*prev + (1-a)*theta (reference src/eincm/losses.py:269) applied to the taps on the fly.
-__global__ void k_upsample_theta(const double* __restrict__ theta, const double* __restrict__ prev, double a_ho,
-                                 int h, int w, int H, int W, AxisTaps ty, AxisTaps tx, double2* __restrict__ theta_full) {
+// The flow operand of one evaluation: tile field theta [h][w][2] (null = zero flow), optional handover blend
+// theta_ho = a*prev + (1-a)*theta (reference src/eincm/losses.py:269), and the per-axis resize taps to the sensor size.
+struct ThetaSrc {
+    const double* theta;
+    const double* prev;
+    double a_ho;
+    int h, w;
+    AxisTaps ty, tx;
+};
+
+// theta_full[y][x][c] = sum_ij Wy[i][y] Wx[j][x] theta[i][j][c] (reference src/utils/theta_utils.py:25-35).  The one
+// definition used by k_upsample_theta (dense field for the TV regulariser and the debug tap) and by the event kernels,
+// which evaluate it per source tile instead of reading a dense field: identical arithmetic, identical bits.
+__device__ __forceinline__ double2 theta_at(const ThetaSrc& T, int x, int y) {
+    const int i0 = __ldg(T.ty.i0 + y), i1 = __ldg(T.ty.i1 + y), j0 = __ldg(T.tx.i0 + x), j1 = __ldg(T.tx.i1 + x);
+    const double wy0 = __ldg(T.ty.w0 + y), wy1 = __ldg(T.ty.w1 + y), wx0 = __ldg(T.tx.w0 + x), wx1 = __ldg(T.tx.w1 + x);
+    const int w = T.w;
+    // scalar loads: the C-ABI only promises 8-byte alignment of theta / prev
+    auto ld2 = [](const double* p, int e) { return make_double2(__ldg(p + 2 * e), __ldg(p + 2 * e + 1)); };
+    double2 t00 = ld2(T.theta, i0 * w + j0), t01 = ld2(T.theta, i0 * w + j1), t10 = ld2(T.theta, i1 * w + j0), t11 = ld2(T.theta, i1 * w + j1);
+    if (T.prev != nullptr) {
+        const double a = T.a_ho, b = 1.0 - T.a_ho;
+        const double2 p00 = ld2(T.prev, i0 * w + j0), p01 = ld2(T.prev, i0 * w + j1), p10 = ld2(T.prev, i1 * w + j0), p11 = ld2(T.prev, i1 * w + j1);
+        t00.x = a * p00.x + b * t00.x; t00.y = a * p00.y + b * t00.y;
+        t01.x = a * p01.x + b * t01.x; t01.y = a * p01.y + b * t01.y;
+        t10.x = a * p10.x + b * t10.x; t10.y = a * p10.y + b * t10.y;
+        t11.x = a * p11.x + b * t11.x; t11.y = a * p11.y + b * t11.y;
+    }
+    double2 out;
+    out.x = wy0 * (wx0 * t00.x + wx1 * t01.x) + wy1 * (wx0 * t10.x + wx1 * t11.x);
+    out.y = wy0 * (wx0 * t00.y + wx1 * t01.y) + wy1 * (wx0 * t10.y + wx1 * t11.y);
+    return out;
+}
+
+__global__ void k_upsample_theta(const ThetaSrc T, int H, int W, double2* __restrict__ theta_full) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
-    const int i0 = ty.i0[y], i1 = ty.i1[y], j0 = tx.i0[x], j1 = tx.i1[x];
-    const double wy0 = ty.w0[y], wy1 = ty.w1[y], wx0 = tx.w0[x], wx1 = tx.w1[x];
-    double out[2];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        double t00 = theta[(i0 * w + j0) * 2 + c], t01 = theta[(i0 * w + j1) * 2 + c];
-        double t10 = theta[(i1 * w + j0) * 2 + c], t11 = theta[(i1 * w + j1) * 2 + c];
-        if (prev != nullptr) {
-            const double b = 1.0 - a_ho;
-            t00 = a_ho * prev[(i0 * w + j0) * 2 + c] + b * t00;
-            t01 = a_ho * prev[(i0 * w + j1) * 2 + c] + b * t01;
-            t10 = a_ho * prev[(i1 * w + j0) * 2 + c] + b * t10;
-            t11 = a_ho * prev[(i1 * w + j1) * 2 + c] + b * t11;
-        }
-        out[c] = wy0 * (wx0 * t00 + wx1 * t01) + wy1 * (wx0 * t10 + wx1 * t11);
-    }
-    theta_full[y * W + x] = make_double2(out[0], out[1]);
+    theta_full[y * W + x] = theta_at(T, x, y);
 }
 
-// ---- backward of the resize, gather form (small theta: h*w <= kGatherMaxTiles) --------------------------
-// One CTA per (theta element, split s): sums Wy[i][y] Wx[j][x] (G[y][x] + tv_coef * Gtv[y][x]) over its share
-// of the element's support rectangle; partial[(i*w+j)*S + s] = (sum_c0, sum_c1).  Deterministic.
+// ---- backward of the resize, gather form (tile theta: h*w <= kGatherMaxTiles) ------------------------------------------
+// d theta[i][j] = sum_{y,x} Wy[i][y] Wx[j][x] (G[y][x] + tv_coef * Gtv[y][x]).  One WARP per work item (theta element, row
+// split sy, column split sx): <= 32 rows (one row weight per lane, broadcast by shuffle) x <= 96 columns (three per lane), no
+// block-level synchronisation; the partial goes to grad[i][j] (pre-zeroed) with two float64 reductions.  The last warp to
+// finish evaluates d loss / d alpha_handover = <grad, prev - theta> (reference src/eincm/losses.py:269) from the complete
+// gradient, so the whole theta backward is one launch.
 constexpr int kGatherMaxTiles = 4096;
+constexpr int kTgWarps = 4;              // warps (work items) per CTA
+constexpr int kTgRows = 4, kTgCols = 96;  // rows x columns per work item: 12 independent 16-byte loads in flight per lane
 
-__global__ void __launch_bounds__(256)
-k_theta_grad_gather(const double2* __restrict__ G, const double2* __restrict__ Gtv, const DevScalars* __restrict__ sc,
-                    double gamma, int h, int w, int H, int W, int S, AxisTaps ty, AxisTaps tx, double2* __restrict__ partial) {
-    __shared__ double sh[8];
-    const int ij = blockIdx.x / S, s = blockIdx.x % S;
-    const int i = ij / w, j = ij % w;
-    const int ylo = ty.lo[i], yhi = ty.hi[i], xlo = tx.lo[j], xhi = tx.hi[j];
-    const int ny = yhi - ylo;
-    const int y_begin = ylo + (int)(((long long)ny * s) / S), y_end = ylo + (int)(((long long)ny * (s + 1)) / S);
-    const int nx = xhi - xlo;
-    double tvc = 0.0;
-    if (Gtv != nullptr) tvc = gamma * 0.25 / (sc->tv_cnt + kEps);
+__device__ __forceinline__ double axis_weight(const AxisTaps& t, int o, int i) {
+    const int i0 = __ldg(t.i0 + o), i1 = __ldg(t.i1 + o);
+    const double w0 = __ldg(t.w0 + o), w1 = __ldg(t.w1 + o);
+    return (i0 == i ? w0 : 0.0) + ((i1 == i && i1 != i0) ? w1 : 0.0);
+}
+
+template <bool HAS_TV>
+__global__ void __launch_bounds__(kTgWarps * 32)
+k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
+             double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, AxisTaps ty, AxisTaps tx,
+             const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */) {
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kTgWarps + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int ij = item / (SY * SX), rem = item - ij * (SY * SX);
+    const int sy = rem / SX, sx = rem - sy * SX;
+    const int i = ij / w, j = ij - i * w;
+    const int ylo = __ldg(ty.lo + i), yhi = __ldg(ty.hi + i), xlo = __ldg(tx.lo + j), xhi = __ldg(tx.hi + j);
+    const int ny = yhi - ylo, nx = xhi - xlo;
+    const int y_begin = ylo + (ny * sy) / SY, y_end = ylo + (ny * (sy + 1)) / SY;
+    const int x_begin = xlo + (nx * sx) / SX, x_end = xlo + (nx * (sx + 1)) / SX;
+    const double tvc = HAS_TV ? gamma * 0.25 / (sc->tv_cnt + kEps) : 0.0;
     double a0 = 0.0, a1 = 0.0;
-    const int total = (y_end - y_begin) * nx;
-    for (int k = threadIdx.x; k < total; k += blockDim.x) {
-        const int y = y_begin + k / nx, x = xlo + k % nx;
-        const double wy = (ty.i0[y] == i ? ty.w0[y] : 0.0) + ((ty.i1[y] == i && ty.i1[y] != ty.i0[y]) ? ty.w1[y] : 0.0);
-        const double wx = (tx.i0[x] == j ? tx.w0[x] : 0.0) + ((tx.i1[x] == j && tx.i1[x] != tx.i0[x]) ? tx.w1[x] : 0.0);
-        double2 g = G[y * W + x];
-        if (Gtv != nullptr) { const double2 t = Gtv[y * W + x]; g.x += tvc * t.x; g.y += tvc * t.y; }
-        const double ww = wy * wx;
-        a0 += ww * g.x;
-        a1 += ww * g.y;
+    for (int yb = y_begin; yb < y_end; yb += kTgRows) {                 // one trip by construction (host sizes SY); general anyway
+        for (int xb = x_begin; xb < x_end; xb += kTgCols) {
+            // all loads first: kTgRows x 3 cells per lane (out-of-range cells read an in-range address with weight 0)
+            double2 g[kTgRows][3], t[kTgRows][3];
+            int xc[3];
+            bool okc[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { xc[c] = xb + lane + 32 * c; okc[c] = xc[c] < x_end; if (!okc[c]) xc[c] = x_begin; }
+#pragma unroll
+            for (int r = 0; r < kTgRows; ++r) {
+                const int y = min(yb + r, y_end - 1);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    g[r][c] = __ldcg(G + (int64_t)y * W + xc[c]);
+                    if (HAS_TV) t[r][c] = __ldcg(Gtv + (int64_t)y * W + xc[c]);
+                }
+            }
+            double wy[kTgRows], wx[3];
+#pragma unroll
+            for (int r = 0; r < kTgRows; ++r) wy[r] = (yb + r < y_end) ? axis_weight(ty, yb + r, i) : 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) wx[c] = okc[c] ? axis_weight(tx, xc[c], j) : 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < kTgRows; ++r) {
+                    double gx = g[r][c].x, gy = g[r][c].y;
+                    if (HAS_TV) { gx += tvc * t[r][c].x; gy += tvc * t[r][c].y; }
+                    c0 += wy[r] * gx;
+                    c1 += wy[r] * gy;
+                }
+                a0 += wx[c] * c0;
+                a1 += wx[c] * c1;
+            }
+        }
     }
-    a0 = block_reduce<256>(a0, OpSum(), sh);
-    a1 = block_reduce<256>(a1, OpSum(), sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(a0, a1);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+    unsigned int ticket = 0u;
+    if (lane == 0) {
+        atomicAdd(grad + 2 * ij, a0);
+        atomicAdd(grad + 2 * ij + 1, a1);
+        __threadfence();
+        ticket = atomicAdd(&sc->counters[5], 1u);
+    }
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != (unsigned int)n_items - 1u) return;
+    double da = 0.0;
+    if (prev != nullptr) {
+        const int n = h * w * 2;
+        for (int e = lane; e < n; e += 32) da += __ldcg(grad + e) * (prev[e] - theta[e]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+    if (lane == 0) { sc->dalpha = da; sc->counters[5] = 0u; }
 }
 
 // ---- backward of the resize, scatter form (large / dense theta) -----------------------------------------
