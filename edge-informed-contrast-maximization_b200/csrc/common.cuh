@@ -64,23 +64,31 @@ struct OpMax { __device__ __forceinline__ double operator()(double a, double b) 
 //   Gx = (3*(I[i+1,j+1]-I[i+1,j-1]) + 10*(I[i,j+1]-I[i,j-1])) + 3*(I[i-1,j+1]-I[i-1,j-1])
 //   Gy = (3*(I[i+1,j+1]-I[i-1,j+1]) + 10*(I[i+1,j]-I[i-1,j])) + 3*(I[i+1,j-1]-I[i-1,j-1])
 // p points at I[i][j] inside a shared-memory tile with row pitch `pitch` (reference src/utils/img_utils.py:414-425).
-__device__ __forceinline__ void scharr_at(const double* p, int pitch, double& gx, double& gy) {
-    const double a = p[pitch + 1], b = p[pitch - 1], c = p[1], d = p[-1], e = p[-pitch + 1], f = p[-pitch - 1];
-    const double u = p[pitch], v = p[-pitch];
+// a..f, u, v = I[i+1,j+1], I[i+1,j-1], I[i,j+1], I[i,j-1], I[i-1,j+1], I[i-1,j-1], I[i+1,j], I[i-1,j]
+__device__ __forceinline__ void scharr_vals(double a, double b, double c, double d, double e, double f, double u, double v,
+                                            double& gx, double& gy) {
     gx = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(a, b)), __dmul_rn(10.0, __dsub_rn(c, d))), __dmul_rn(3.0, __dsub_rn(e, f)));
     gy = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(a, e)), __dmul_rn(10.0, __dsub_rn(u, v))), __dmul_rn(3.0, __dsub_rn(b, f)));
 }
 
+__device__ __forceinline__ void scharr_at(const double* p, int pitch, double& gx, double& gy) {
+    scharr_vals(p[pitch + 1], p[pitch - 1], p[1], p[-1], p[-pitch + 1], p[-pitch - 1], p[pitch], p[-pitch], gx, gy);
+}
+
 // Adjoint of the Scharr pair ('same' correlation with the same kernels), canonical order of oracle._scharr_adjoint.
+// xu/xm/xd point at the cotangent of Gx at column j of rows i-1 / i / i+1 (yu/ym/yd likewise for Gy).
+__device__ __forceinline__ double scharr_adjoint_rows(const double* xu, const double* xm, const double* xd,
+                                                      const double* yu, const double* yd) {
+    const double ax = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(xu[-1], xu[1])), __dmul_rn(10.0, __dsub_rn(xm[-1], xm[1]))),
+                                __dmul_rn(3.0, __dsub_rn(xd[-1], xd[1])));
+    const double ay = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(yu[-1], yd[-1])), __dmul_rn(10.0, __dsub_rn(yu[0], yd[0]))),
+                                __dmul_rn(3.0, __dsub_rn(yu[1], yd[1])));
+    return __dadd_rn(ax, ay);
+}
+
 // px / py point at the cotangents of Gx / Gy at [i][j] in shared-memory tiles with row pitch `pitch`.
 __device__ __forceinline__ double scharr_adjoint_at(const double* px, const double* py, int pitch) {
-    const double ax = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(px[-pitch - 1], px[-pitch + 1])),
-                                          __dmul_rn(10.0, __dsub_rn(px[-1], px[1]))),
-                                __dmul_rn(3.0, __dsub_rn(px[pitch - 1], px[pitch + 1])));
-    const double ay = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(py[-pitch - 1], py[pitch - 1])),
-                                          __dmul_rn(10.0, __dsub_rn(py[-pitch], py[pitch]))),
-                                __dmul_rn(3.0, __dsub_rn(py[-pitch + 1], py[pitch + 1])));
-    return __dadd_rn(ax, ay);
+    return scharr_adjoint_rows(px - pitch, px, px + pitch, py - pitch, py + pitch);
 }
 
 // convolve(a, DIV_KERN, 'same') in the canonical order of oracle.div_kern_conv (event_collapse_objectives.py:14-16)

@@ -53,6 +53,7 @@ struct eincm_plan {
     bool theta_full_valid = false;
     bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
     int coop_ctas = 0;            // co-resident CTAs of k_image_pass
+    bool coop_ok = false;         // the sensor is narrow enough for the row-band cooperative image pass
     bool fused_pending = false;   // the last forward left the fixed-point images for the fused image pass (no float64 copy yet)
     RefTimes tref{};
     // last evaluation
@@ -200,6 +201,18 @@ __global__ void k_set_weights(DevScalars* sc, RefTimes w, int R) {
     if (threadIdx.x < EINCM_MAX_REFS) sc->weights[threadIdx.x] = threadIdx.x < R ? w.t[threadIdx.x] : 0.0;
 }
 
+// instantiation of the cooperative image pass for a sensor width (columns per thread is a template parameter)
+const void* image_pass_kernel(int W) {
+    switch ((W + kBandNT - 1) / kBandNT) {
+        case 1: return (const void*)k_image_pass<1>;
+        case 2: return (const void*)k_image_pass<2>;
+        case 3: return (const void*)k_image_pass<3>;
+        case 4: return (const void*)k_image_pass<4>;
+        case 5: return (const void*)k_image_pass<5>;
+        default: return (const void*)k_image_pass<6>;
+    }
+}
+
 int event_grid(const eincm_plan* p, int64_t n, int threads) {
     const int64_t want = (n + threads - 1) / threads;
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 8));
@@ -311,7 +324,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
         if ((rc = ensure_theta_full(plan, st))) return rc;
     }
     // default path (single GPU, delta == 0): the fixed-point images are consumed by the fused image pass directly
-    plan->fused_pending = !plan->exact && !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && hp->delta == 0.0;
+    plan->fused_pending = !plan->exact && plan->coop_ok && !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && hp->delta == 0.0;
     if ((rc = splat_images(plan, plan->tsrc, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
     plan->forward_done = true;
@@ -354,11 +367,11 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             ia.zero_buf2 = grad_out ? grad_out : plan->grad_buf; ia.n_zero2 = h * w * 2;
             g_zeroed_grad = true;
         }
-        ia.H = H; ia.W = W; ia.R = R; ia.tiles_x = (W + kFTX - 1) / kFTX; ia.tiles_y = (H + kFTY - 1) / kFTY;
+        ia.H = H; ia.W = W; ia.R = R;
         ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0; ia.want_grad = want_grad ? 1 : 0;
-        const int gridI = std::max(1, std::min(plan->coop_ctas, ia.tiles_x * ia.tiles_y * R));
+        const int gridI = std::max(1, std::min(plan->coop_ctas, (R * H + 3) / 4));       // >= 4 rows per CTA
         void* kargs[] = {(void*)&ia};
-        LAUNCH("k_image_pass", cudaLaunchCooperativeKernel((const void*)k_image_pass, dim3(gridI), dim3(kFTX, 8), kargs, sizeof(ImagePassSmem), st));
+        LAUNCH("k_image_pass", cudaLaunchCooperativeKernel(image_pass_kernel(W), dim3(gridI), dim3(kBandNT), kargs, image_pass_smem_bytes(W), st));
         plan->fused_pending = false;
         plan->fix_clean = true;                                  // the pass clears the cells it has read
         if (!want_grad) return EINCM_OK;
@@ -493,12 +506,17 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     plan->sm_count = prop.multiProcessorCount;
     {
         int per_sm = 0;
-        if ((e = cudaFuncSetAttribute((const void*)k_image_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImagePassSmem))) != cudaSuccess ||
-            (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_image_pass, kFNT, sizeof(ImagePassSmem))) != cudaSuccess || per_sm < 1) {
-            delete plan;
-            return fail(nullptr, EINCM_ECUDA, "occupancy query of the cooperative image pass failed (%s)", cudaGetErrorString(e));
+        // the cooperative image pass keeps whole rows in shared memory; very wide sensors use the unfused image kernels
+        const size_t smem_img = image_pass_smem_bytes(W);
+        plan->coop_ok = W <= kMaxCPT * kBandNT && smem_img <= (size_t)prop.sharedMemPerBlockOptin;
+        if (plan->coop_ok) {
+            if ((e = cudaFuncSetAttribute(image_pass_kernel(W), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess ||
+                (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_pass_kernel(W), kBandNT, smem_img)) != cudaSuccess || per_sm < 1) {
+                delete plan;
+                return fail(nullptr, EINCM_ECUDA, "occupancy query of the cooperative image pass failed (%s)", cudaGetErrorString(e));
+            }
+            plan->coop_ctas = plan->sm_count * std::min(per_sm, 3);
         }
-        plan->coop_ctas = plan->sm_count * std::min(per_sm, 3);
     }
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
     plan->n_tiles = plan->tiles_x * ((H + kSortTile - 1) / kSortTile);

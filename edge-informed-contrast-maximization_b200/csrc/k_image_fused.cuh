@@ -93,7 +93,7 @@ struct ImagePassArgs {
     double* zero_buf;             // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
     double* zero_buf2;
     int n_zero, n_zero2;
-    int H, W, R, tiles_x, tiles_y;
+    int H, W, R;
     double alpha, beta, gamma;
     int use_tv, want_grad;
 };
@@ -113,157 +113,130 @@ __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double
     return st;
 }
 
-// 8-byte asynchronous global -> shared copy; `valid == false` zero-fills (image border)
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Row-band formulation: a CTA owns a contiguous run of complete image rows (R*H rows laid end to end are split evenly over the
+// grid) and walks them top to bottom.  A thread owns the same <= kMaxCPT columns (tid, tid + 256, ...) in every row; rows live
+// in 4-slot shared-memory rings with a zero column on either side, so the 3x3 stencils need no index arithmetic beyond the
+// slot of a row, global loads / stores are perfectly coalesced row segments, the next row is prefetched into registers while
+// the current one is computed, and every thread accumulates its statistics over all its pixels before the single block
+// reduction per (CTA, reference image).
+constexpr int kBandNT = 256;
+constexpr int kMaxCPT = 6;                          // columns per thread (template parameter 1..6): sensors up to 1536 px wide
+constexpr int kRing = 4;
 
-constexpr int kStages = 3;                          // tiles in flight per CTA (cp.async ring)
-
-struct ImagePassSmem {
-    // phase 1: raw fixed-point tile (halo 1), converted in place to float64; phase 3: float64 tile (halo 2)
-    double img[kStages][(kFTY + 4) * (kFTX + 4)];
-    double edg[kStages][kFTY * kFTX];
-    double gxs[(kFTY + 2) * (kFTX + 2)], gys[(kFTY + 2) * (kFTX + 2)];
-    double red[kFNT / 32][kFPart];
+struct BandSmemTail {
+    double red[kBandNT / 32][kFPart];
     Stats st[kCoopMaxRefs];
     double coefA[kCoopMaxRefs], coefB[kCoopMaxRefs];
 };
 
-// issue the asynchronous loads of one tile: HALO cells around the kFTX x kFTY interior of image `src` (8-byte cells), and
-// the tile's edge-image cells
-template <int HALO>
-__device__ __forceinline__ void issue_tile(const void* __restrict__ src, const double* __restrict__ edges, int H, int W, int x0, int y0,
-                                           double* __restrict__ img_dst, double* __restrict__ edg_dst) {
-    constexpr int TW = kFTX + 2 * HALO, TH = kFTY + 2 * HALO;
-    const int tid = linear_tid();
-    const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(src);
-    for (int k = tid; k < TW * TH; k += kFNT) {
-        const int cy = k / TW, cx = k - cy * TW;
-        const int X = x0 + cx - HALO, Y = y0 + cy - HALO;
-        const bool ok = (X >= 0) & (X < W) & (Y >= 0) & (Y < H);
-        cp_async8(img_dst + k, ok ? (const void*)(s8 + (int64_t)Y * W + X) : (const void*)s8, ok);
-    }
-    for (int k = tid; k < kFTX * kFTY; k += kFNT) {
-        const int cy = k / kFTX, cx = k - cy * kFTX;
-        const int X = x0 + cx, Y = y0 + cy;
-        const bool ok = (X < W) & (Y < H);
-        cp_async8(edg_dst + k, ok ? (const void*)(edges + (int64_t)Y * W + X) : (const void*)edges, ok);
-    }
+__host__ __device__ inline size_t image_pass_smem_bytes(int W) {
+    return (size_t)3 * kRing * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
 }
 
-__global__ void __launch_bounds__(kFNT)
+template <int CPT>
+__global__ void __launch_bounds__(kBandNT)
 k_image_pass(const ImagePassArgs A) {
-    constexpr int IW = kFTX + 2;                    // row pitch of a halo-1 tile (phase 1)
-    constexpr int PW = kFTX + 4;                    // row pitch of a halo-2 tile (phase 3)
-    constexpr int GW = kFTX + 2, GH = kFTY + 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ImagePassSmem& S = *reinterpret_cast<ImagePassSmem*>(smem_raw);
-    const int H = A.H, W = A.W, R = A.R;
-    const int64_t HW = (int64_t)H * W;
-    const int tid = linear_tid();
-    const int tpi = A.tiles_x * A.tiles_y;          // tiles per image
-    const int T = tpi * R;
+    const int H = A.H, W = A.W, R = A.R, Wp = W + 2;
+    double* ringI = reinterpret_cast<double*>(smem_raw);             // [kRing][Wp]
+    double* ringX = ringI + kRing * Wp;                              // Scharr x of rows, phase 3
+    double* ringY = ringX + kRing * Wp;
+    BandSmemTail& S = *reinterpret_cast<BandSmemTail*>(ringY + kRing * Wp);
+    const int HW = H * W;
+    const int tid = threadIdx.x;
     const int G = gridDim.x, b = blockIdx.x;
-    const int t_begin = (int)(((long long)T * b) / G), t_end = (int)(((long long)T * (b + 1)) / G);
-    const int r_first = t_begin < t_end ? t_begin / tpi : 0, r_last = t_begin < t_end ? (t_end - 1) / tpi : -1;
-    auto tile_origin = [&](int t, int& r, int& x0, int& y0) {
-        r = t / tpi;
-        const int tt = t - r * tpi;
-        const int ty = tt / A.tiles_x;
-        x0 = (tt - ty * A.tiles_x) * kFTX; y0 = ty * kFTY;
-    };
+    const int RH = R * H;
+    const int row_begin = (int)(((long long)RH * b) / G), row_end = (int)(((long long)RH * (b + 1)) / G);
+    const int r_first = row_begin < row_end ? row_begin / H : 0, r_last = row_begin < row_end ? (row_end - 1) / H : -1;
 
-    // identity partials for every reference image (a CTA usually touches one or two)
-    for (int k = tid; k < R * kFPart; k += kFNT) {
+    // zero columns of the rings (never written afterwards), identity partials, accumulators of the event backward pass
+    for (int k = tid; k < 3 * kRing; k += kBandNT) { ringI[k * Wp] = 0.0; ringI[k * Wp + W + 1] = 0.0; }
+    for (int k = tid; k < R * kFPart; k += kBandNT) {
         const int q = k / kFPart, f = k % kFPart;
-        A.part[((int64_t)q * G + b) * kFPart + f] = (f == 4) ? INFINITY : ((f == 6) ? -INFINITY : 0.0);
+        A.part[(q * G + b) * kFPart + f] = (f == 4) ? INFINITY : ((f == 6) ? -INFINITY : 0.0);
     }
     if (A.zero_buf != nullptr)
-        for (int k = b * kFNT + tid; k < A.n_zero; k += G * kFNT) A.zero_buf[k] = 0.0;
+        for (int k = b * kBandNT + tid; k < A.n_zero; k += G * kBandNT) A.zero_buf[k] = 0.0;
     if (A.zero_buf2 != nullptr)
-        for (int k = b * kFNT + tid; k < A.n_zero2; k += G * kFNT) A.zero_buf2[k] = 0.0;
+        for (int k = b * kBandNT + tid; k < A.n_zero2; k += G * kBandNT) A.zero_buf2[k] = 0.0;
 
-    // ---- phase 1: statistics ----------------------------------------------------------------------------------------------
-    FusedAcc acc;
-    acc.init();
+    // ---- phase 1: float64 image + statistics --------------------------------------------------------------------------
+    for (int r = r_first; r <= r_last; ++r) {
+        const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
+        const unsigned long long* Fr = A.fix + r * HW;
+        const double* Er = A.edges + r * HW;
+        double* Ir = A.iwe + r * HW;
+        auto load_fix_row = [&](int y, unsigned long long (&v)[CPT]) {
 #pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) {
-        if (t_begin + s < t_end) {
-            int r, x0, y0;
-            tile_origin(t_begin + s, r, x0, y0);
-            issue_tile<1>(A.fix + (int64_t)r * HW, A.edges + (int64_t)r * HW, H, W, x0, y0, S.img[s], S.edg[s]);
-        }
-        cp_async_commit();
-    }
-    for (int t = t_begin; t < t_end; ++t) {
-        const int stage = (t - t_begin) % kStages;
-        {
-            const int tn = t + kStages - 1;          // refill the stage consumed in the previous iteration
-            if (tn < t_end) {
-                int r, x0, y0;
-                tile_origin(tn, r, x0, y0);
-                const int sn = (tn - t_begin) % kStages;
-                issue_tile<1>(A.fix + (int64_t)r * HW, A.edges + (int64_t)r * HW, H, W, x0, y0, S.img[sn], S.edg[sn]);
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                v[c] = (x < W && y >= 0 && y < H) ? __ldcg(Fr + y * W + x) : 0ull;
             }
-            cp_async_commit();
-        }
-        cp_async_wait<kStages - 1>();
-        __syncthreads();
-        int r, x0, y0;
-        tile_origin(t, r, x0, y0);
-        double* img = S.img[stage];
-        for (int k = tid; k < IW * (kFTY + 2); k += kFNT)
-            img[k] = (double)(long long)reinterpret_cast<const unsigned long long*>(img)[k] * kFixToIwe;
-        __syncthreads();
+        };
+        auto store_row = [&](int y, const unsigned long long (&v)[CPT]) {
+            double* dst = ringI + (y & (kRing - 1)) * Wp + 1;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ty = threadIdx.y + 8 * h;
-            const int x = x0 + threadIdx.x, y = y0 + ty;
-            if (x < W && y < H) {
-                const double* p = img + (ty + 1) * IW + threadIdx.x + 1;
-                double gx, gy;
-                scharr_at(p, IW, gx, gy);
-                const double I = *p;
-                const double E = S.edg[stage][ty * kFTX + threadIdx.x];
-                A.iwe[(int64_t)r * HW + (int64_t)y * W + x] = I;
-                FusedAcc o;
-                o.sq = gx * gx + gy * gy; o.sI = I; o.sI2 = I * I; o.sEI = E * I; o.mn = I; o.cmn = 1.0; o.mx = I; o.cmx = 1.0;
-                acc.merge(o);
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                if (x < W) dst[x] = (double)(long long)v[c] * kFixToIwe;
+            }
+        };
+        unsigned long long pre[CPT];
+        double epre[CPT];
+        __syncthreads();                               // ring reuse across reference images
+        load_fix_row(ya - 1, pre); store_row(ya - 1 + kRing, pre);     // (+kRing keeps the slot index non-negative)
+        load_fix_row(ya, pre); store_row(ya, pre);
+        load_fix_row(ya + 1, pre);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int x = tid + c * kBandNT;
+            epre[c] = (x < W) ? __ldg(Er + ya * W + x) : 0.0;
+        }
+        FusedAcc acc;
+        acc.init();
+        int cnt_mn = 0, cnt_mx = 0;                   // tie counts of the running min / max (integers: branch-free update)
+        for (int y = ya; y < yb; ++y) {
+            store_row(y + 1, pre);
+            double e[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) e[c] = epre[c];
+            if (y + 1 < yb) {                          // prefetch the next iteration's operands
+                load_fix_row(y + 2, pre);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    epre[c] = (x < W) ? __ldg(Er + (y + 1) * W + x) : 0.0;
+                }
+            }
+            __syncthreads();
+            const double* up = ringI + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
+            const double* mid = ringI + (y & (kRing - 1)) * Wp + 1;
+            const double* dn = ringI + ((y + 1) & (kRing - 1)) * Wp + 1;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                if (x < W) {
+                    double gx, gy;
+                    scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
+                    const double I = mid[x];
+                    Ir[y * W + x] = I;
+                    acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += e[c] * I;
+                    cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
+                    cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
+                    acc.mn = fmin(acc.mn, I);
+                    acc.mx = fmax(acc.mx, I);
+                }
             }
         }
-        const bool flush = (t + 1 == t_end) || ((t + 1) / tpi != r);
-        if (flush) {
-            const FusedAcc a = fused_block_reduce(acc, S.red);
-            if (tid == 0) {
-                double* d = A.part + ((int64_t)r * G + b) * kFPart;
-                d[0] = a.sq; d[1] = a.sI; d[2] = a.sI2; d[3] = a.sEI; d[4] = a.mn; d[5] = a.cmn; d[6] = a.mx; d[7] = a.cmx;
-            }
-            acc.init();
+        acc.cmn = (double)cnt_mn; acc.cmx = (double)cnt_mx;
+        const FusedAcc a = fused_block_reduce(acc, S.red);
+        if (tid == 0) {
+            double* d = A.part + (r * G + b) * kFPart;
+            d[0] = a.sq; d[1] = a.sI; d[2] = a.sI2; d[3] = a.sEI; d[4] = a.mn; d[5] = a.cmn; d[6] = a.mx; d[7] = a.cmx;
         }
-        __syncthreads();                             // stage may be refilled by the next iteration
     }
-    cp_async_wait<0>();
     __threadfence();
     cooperative_groups::this_grid().sync();
-
-    // phase 3 prologue first (its loads fly while phase 2 reduces): the float64 images are complete after the barrier
-    if (A.want_grad) {
-#pragma unroll
-        for (int s = 0; s < kStages - 1; ++s) {
-            if (t_begin + s < t_end) {
-                int r, x0, y0;
-                tile_origin(t_begin + s, r, x0, y0);
-                issue_tile<2>(A.iwe + (int64_t)r * HW, A.edges + (int64_t)r * HW, H, W, x0, y0, S.img[s], S.edg[s]);
-            }
-            cp_async_commit();
-        }
-    }
 
     // ---- phase 2: global statistics of the reference images this CTA owns (CTA 0: all, plus the loss) ----------------------
     {
@@ -279,8 +252,8 @@ k_image_pass(const ImagePassArgs A) {
         for (int q = q_lo; q <= q_hi; ++q) {
             FusedAcc a;
             a.init();
-            for (int k = tid; k < G; k += kFNT) {
-                const double* d = A.part + ((int64_t)q * G + k) * kFPart;
+            for (int k = tid; k < G; k += kBandNT) {
+                const double* d = A.part + (q * G + k) * kFPart;
                 FusedAcc o;
                 o.sq = __ldcg(d + 0); o.sI = __ldcg(d + 1); o.sI2 = __ldcg(d + 2); o.sEI = __ldcg(d + 3);
                 o.mn = __ldcg(d + 4); o.cmn = __ldcg(d + 5); o.mx = __ldcg(d + 6); o.cmx = __ldcg(d + 7);
@@ -296,62 +269,107 @@ k_image_pass(const ImagePassArgs A) {
         }
     }
 
-    // ---- phase 3: clear the fixed-point cells; d loss / d IWE ----------------------------------------------------------------
-    for (int t = t_begin; t < t_end; ++t) {
-        int r, x0, y0;
-        tile_origin(t, r, x0, y0);
-        unsigned long long* Fr = A.fix + (int64_t)r * HW;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int x = x0 + threadIdx.x, y = y0 + threadIdx.y + 8 * h;
-            if (x < W && y < H) Fr[(int64_t)y * W + x] = 0ull;
-        }
+    // ---- phase 3: clear the fixed-point rows; d loss / d IWE ---------------------------------------------------------------
+    for (int r = r_first; r <= r_last; ++r) {
+        const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
+        unsigned long long* Fr = A.fix + r * HW;
+        for (int k = ya * W + tid; k < yb * W; k += kBandNT) Fr[k] = 0ull;
         if (!A.want_grad) continue;
-        const int stage = (t - t_begin) % kStages;
-        {
-            const int tn = t + kStages - 1;
-            if (tn < t_end) {
-                int rn, xn, yn;
-                tile_origin(tn, rn, xn, yn);
-                const int sn = (tn - t_begin) % kStages;
-                issue_tile<2>(A.iwe + (int64_t)rn * HW, A.edges + (int64_t)rn * HW, H, W, xn, yn, S.img[sn], S.edg[sn]);
+        const double* Er = A.edges + r * HW;
+        const double* Ir = A.iwe + r * HW;
+        auto load_row = [&](int y, double (&v)[CPT]) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                v[c] = (x < W && y >= 0 && y < H) ? __ldcg(Ir + y * W + x) : 0.0;
             }
-            cp_async_commit();
-        }
-        cp_async_wait<kStages - 1>();
-        __syncthreads();
-        const double* tile = S.img[stage];
-        for (int k = tid; k < GW * GH; k += kFNT) {
-            const int ly = k / GW, lx = k - ly * GW;
-            const int y = y0 + ly - 1, x = x0 + lx - 1;
-            double gx = 0.0, gy = 0.0;
-            if (x >= 0 && x < W && y >= 0 && y < H) scharr_at(tile + (ly + 1) * PW + lx + 1, PW, gx, gy);
-            S.gxs[k] = gx; S.gys[k] = gy;
-        }
-        __syncthreads();
+        };
+        auto store_row = [&](int y, const double (&v)[CPT]) {
+            double* dst = ringI + ((y + kRing) & (kRing - 1)) * Wp + 1;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                if (x < W) dst[x] = v[c];
+            }
+        };
+        // Scharr pair of row q from the ring rows q-1, q, q+1 (zero outside the image: 'same' output only exists inside)
+        auto grad_row = [&](int q) {
+            const double* up = ringI + ((q - 1 + kRing) & (kRing - 1)) * Wp + 1;
+            const double* mid = ringI + ((q + kRing) & (kRing - 1)) * Wp + 1;
+            const double* dn = ringI + ((q + 1 + kRing) & (kRing - 1)) * Wp + 1;
+            double* gxr = ringX + ((q + kRing) & (kRing - 1)) * Wp + 1;
+            double* gyr = ringY + ((q + kRing) & (kRing - 1)) * Wp + 1;
+            const bool inside = q >= 0 && q < H;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                if (x < W) {
+                    double gx = 0.0, gy = 0.0;
+                    if (inside) scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
+                    gxr[x] = gx; gyr[x] = gy;
+                }
+            }
+        };
         const Stats st = S.st[r];
         const double cA = S.coefA[r], cB = S.coefB[r];
         const double g_M = -st.s2 / (st.D * st.D);
         const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
+        double pre[CPT], epre[CPT];
+        __syncthreads();                               // ring reuse across reference images
+        load_row(ya - 2, pre); store_row(ya - 2, pre);
+        load_row(ya - 1, pre); store_row(ya - 1, pre);
+        load_row(ya, pre); store_row(ya, pre);
+        __syncthreads();
+        grad_row(ya - 1);                              // needs rows ya-2 .. ya
+        load_row(ya + 1, pre); store_row(ya + 1, pre); // slot of row ya-3: free
+        __syncthreads();
+        grad_row(ya);                                  // needs rows ya-1 .. ya+1
+        load_row(ya + 2, pre);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ty = threadIdx.y + 8 * h;
-            const int x = x0 + threadIdx.x, y = y0 + ty;
-            if (x >= W || y >= H) continue;
-            const double I = tile[(ty + 2) * PW + threadIdx.x + 2];
-            const int64_t p = (int64_t)y * W + x;
-            const double adj = scharr_adjoint_at(S.gxs + (ty + 1) * GW + threadIdx.x + 1, S.gys + (ty + 1) * GW + threadIdx.x + 1, GW);
-            const double c = I - st.mn;
-            const double gN = cB * (S.edg[stage][ty * kFTX + threadIdx.x] - c / st.D);
-            double out = cA * adj + gN / st.D;
-            if (I == st.mn) out += g_m / st.cnt_min;
-            if (I == st.mx) out += g_M / st.cnt_max;
-            if (A.dldi != nullptr) A.dldi[r * HW + p] = out;
-            A.dldi32[r * HW + p] = (float)(out * kInv2Pi);
+        for (int c = 0; c < CPT; ++c) {
+            const int x = tid + c * kBandNT;
+            epre[c] = (x < W) ? __ldg(Er + ya * W + x) : 0.0;
         }
-        __syncthreads();                             // stage / gxs / gys may be rewritten by the next iteration
+        for (int y = ya; y < yb; ++y) {
+            store_row(y + 2, pre);                     // into the slot of row y-2, last read two iterations ago
+            double e[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) e[c] = epre[c];
+            if (y + 1 < yb) {
+                load_row(y + 3, pre);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    epre[c] = (x < W) ? __ldg(Er + (y + 1) * W + x) : 0.0;
+                }
+            }
+            __syncthreads();
+            grad_row(y + 1);                           // rows y .. y+2
+            __syncthreads();
+            const double* xu = ringX + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
+            const double* xm = ringX + (y & (kRing - 1)) * Wp + 1;
+            const double* xd = ringX + ((y + 1) & (kRing - 1)) * Wp + 1;
+            const double* yu = ringY + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
+            const double* yd = ringY + ((y + 1) & (kRing - 1)) * Wp + 1;
+            const double* mid = ringI + (y & (kRing - 1)) * Wp + 1;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                if (x < W) {
+                    const double I = mid[x];
+                    const double adj = scharr_adjoint_rows(xu + x, xm + x, xd + x, yu + x, yd + x);
+                    const double cI = I - st.mn;
+                    const double gN = cB * (e[c] - cI / st.D);
+                    double out = cA * adj + gN / st.D;
+                    if (I == st.mn) out += g_m / st.cnt_min;
+                    if (I == st.mx) out += g_M / st.cnt_max;
+                    const int p = y * W + x;
+                    if (A.dldi != nullptr) A.dldi[r * HW + p] = out;
+                    A.dldi32[r * HW + p] = (float)(out * kInv2Pi);
+                }
+            }
+        }
     }
-    cp_async_wait<0>();
 }
 
 // per-window: sum E_r and sum E_r^2 (deterministic single-CTA-per-reference reduction; once per window)
