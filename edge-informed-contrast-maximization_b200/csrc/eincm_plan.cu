@@ -552,7 +552,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->sc, 1));
         CU(cudaMemset(plan->sc, 0, sizeof(DevScalars)));
         CU(dmalloc(&plan->theta_stage, HW * 2)); CU(dmalloc(&plan->prev_stage, HW * 2));
-        CU(dmalloc(&plan->grad_stage, HW * 2)); CU(dmalloc(&plan->grad_buf, HW * 2));
+        CU(dmalloc(&plan->grad_stage, HW * 2 + 8)); CU(dmalloc(&plan->grad_buf, HW * 2));     // + 8: loss slot right behind a staged gradient
         CU(dmalloc(&plan->out_stage, 8));
         CU(cudaMallocHost((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double)));
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
@@ -720,13 +720,14 @@ int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h,
     const size_t nb = (size_t)h * w * 2 * sizeof(double);
     std::memcpy(plan->h_pinned, theta_host, nb);
     CU(cudaMemcpyAsync(plan->theta_stage, plan->h_pinned, nb, cudaMemcpyHostToDevice, st));
-    int rc = eincm_value_and_grad(plan, plan->theta_stage, h, w, hp, plan->out_stage, grad_out_host ? plan->grad_stage : nullptr, st);
+    // loss lands right behind the gradient in the staging buffer: one device -> host copy for both
+    const size_t n_g = grad_out_host ? (size_t)h * w * 2 : 0;
+    double* loss_dev = plan->grad_stage + n_g;
+    int rc = eincm_value_and_grad(plan, plan->theta_stage, h, w, hp, loss_dev, grad_out_host ? plan->grad_stage : nullptr, st);
     if (rc) return rc;
-    double* h_out = plan->h_pinned + (size_t)plan->HW * 2;
-    CU(cudaMemcpyAsync(h_out, plan->out_stage, sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (grad_out_host) CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, (n_g + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    *loss_out_host = h_out[0];
+    *loss_out_host = plan->h_pinned[n_g];
     if (grad_out_host) std::memcpy(grad_out_host, plan->h_pinned, nb);
     return EINCM_OK;
 }

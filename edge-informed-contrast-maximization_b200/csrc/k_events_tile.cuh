@@ -180,7 +180,7 @@ __device__ __forceinline__ double2 event_theta(const double2* __restrict__ th_s,
 // common): the nine pending tap sums stay in registers and are only sent to shared memory when the centre changes.  The merge
 // is branch-free (predicated adds / predicated reductions), so diverging lanes cost nothing extra.
 template <bool WRAP, int RB>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
              const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
              unsigned long long* __restrict__ iwe_fix /* [R][H*W] */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
@@ -324,7 +324,7 @@ __global__ void k_fix_to_f64(const unsigned long long* __restrict__ fix, int64_t
 // Same chunks and windows as the forward pass of the same theta (chunk_win).  dwin holds d loss / d IWE / (2 pi) (float32)
 // of the window cells, zero where the index rule drops the cell.
 template <bool WRAP, int RB>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
                 const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
                 const float* __restrict__ dldi32 /* [R][H][W], scaled by 1/(2 pi) */, const int4* __restrict__ chunk_win,
