@@ -51,6 +51,8 @@ struct eincm_plan {
     bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
     ThetaSrc tsrc{};              // flow operand of the last forward pass
     bool theta_full_valid = false;
+    bool host_delivered = false;  // the last backward pass wrote its results into the mapped host buffer itself
+    double* h_mapped_dev = nullptr;   // device alias of h_pinned (cudaHostAllocMapped)
     bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
     int coop_ctas = 0;            // co-resident CTAs of k_image_pass
     bool coop_ok = false;         // the sensor is narrow enough for the row-band cooperative image pass
@@ -331,7 +333,11 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
     return EINCM_OK;
 }
 
-int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, double* dalpha_out, cudaStream_t st) {
+// host_out: device alias of mapped pinned memory; when the tile-theta gradient kernel runs it delivers [grad | loss | dalpha]
+// there itself (plan->host_delivered), otherwise the caller copies the results back.
+int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, double* dalpha_out, cudaStream_t st,
+                  double* host_out = nullptr) {
+    plan->host_delivered = false;
     int rc = check_hp(plan, hp);
     if (rc) return rc;
     if (!plan->forward_done) return fail(plan, EINCM_ESTATE, "eincm_backward before eincm_forward_events");
@@ -445,11 +451,12 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         if (Gtv != nullptr)
             LAUNCH("k_theta_grad", k_theta_grad<true><<<gridG, kTgWarps * 32, 0, st>>>(
                 (const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                handover ? plan->last_prev : nullptr, plan->last_theta, gout));
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0));
         else
             LAUNCH("k_theta_grad", k_theta_grad<false><<<gridG, kTgWarps * 32, 0, st>>>(
                 (const double2*)plan->G, nullptr, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                handover ? plan->last_prev : nullptr, plan->last_theta, gout));
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0));
+        plan->host_delivered = host_out != nullptr;
     } else {
         CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
         CU(cudaMemsetAsync(plan->grad_buf, 0, (size_t)n_el * 2 * sizeof(double), st));
@@ -554,7 +561,8 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->theta_stage, HW * 2)); CU(dmalloc(&plan->prev_stage, HW * 2));
         CU(dmalloc(&plan->grad_stage, HW * 2 + 8)); CU(dmalloc(&plan->grad_buf, HW * 2));     // + 8: loss slot right behind a staged gradient
         CU(dmalloc(&plan->out_stage, 8));
-        CU(cudaMallocHost((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double)));
+        CU(cudaHostAlloc((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double), cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void**)&plan->h_mapped_dev, plan->h_pinned, 0));
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
         return EINCM_OK;
     };
@@ -715,16 +723,29 @@ int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h,
     if (!plan) return EINCM_EINVAL;
     if (!theta_host || !loss_out_host) return fail(plan, EINCM_EINVAL, "NULL operand");
     if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "event-split plans use the split-phase calls");
     CU(cudaSetDevice(plan->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t nb = (size_t)h * w * 2 * sizeof(double);
     std::memcpy(plan->h_pinned, theta_host, nb);
     CU(cudaMemcpyAsync(plan->theta_stage, plan->h_pinned, nb, cudaMemcpyHostToDevice, st));
-    // loss lands right behind the gradient in the staging buffer: one device -> host copy for both
+    // results come back through mapped pinned memory written by the last kernel; the staged copy is the fallback for the
+    // paths that end in other kernels (dense theta, loss only)
     const size_t n_g = grad_out_host ? (size_t)h * w * 2 : 0;
     double* loss_dev = plan->grad_stage + n_g;
-    int rc = eincm_value_and_grad(plan, plan->theta_stage, h, w, hp, loss_dev, grad_out_host ? plan->grad_stage : nullptr, st);
+    double* h_res = plan->h_pinned + (size_t)plan->HW * 2 + 16;       // [grad | loss | dalpha]; theta staging lives in front
+    int rc = forward_events_impl(plan, plan->theta_stage, nullptr, 0.0, h, w, hp, st);
     if (rc) return rc;
+    const bool small = n_g + 2 <= 1000;                                // fits behind the theta staging area
+    rc = backward_impl(plan, hp, loss_dev, grad_out_host ? plan->grad_stage : nullptr, nullptr, st,
+                       small ? plan->h_mapped_dev + (size_t)plan->HW * 2 + 16 : nullptr);
+    if (rc) return rc;
+    if (plan->host_delivered) {
+        CU(cudaStreamSynchronize(st));
+        *loss_out_host = h_res[n_g];
+        if (grad_out_host) std::memcpy(grad_out_host, h_res, nb);
+        return EINCM_OK;
+    }
     CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, (n_g + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *loss_out_host = plan->h_pinned[n_g];

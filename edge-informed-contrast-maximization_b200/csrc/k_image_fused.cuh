@@ -114,14 +114,25 @@ __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double
 }
 
 // Row-band formulation: a CTA owns a contiguous run of complete image rows (R*H rows laid end to end are split evenly over the
-// grid) and walks them top to bottom.  A thread owns the same <= kMaxCPT columns (tid, tid + 256, ...) in every row; rows live
-// in 4-slot shared-memory rings with a zero column on either side, so the 3x3 stencils need no index arithmetic beyond the
-// slot of a row, global loads / stores are perfectly coalesced row segments, the next row is prefetched into registers while
-// the current one is computed, and every thread accumulates its statistics over all its pixels before the single block
-// reduction per (CTA, reference image).
+// grid) and handles it in sub-bands of <= kBandRows rows.  A sub-band (plus two halo rows on either side and a zero column on
+// either side) is brought into shared memory with one burst of asynchronous copies - all loads of the CTA in flight at once -
+// and then processed without further global reads: a thread owns the same CPT columns (tid, tid + 256, ...) in every row, so
+// the 3x3 stencils need no index arithmetic, global traffic is perfectly coalesced row segments, and every thread accumulates
+// its statistics over all its pixels before the single block reduction per (CTA, reference image).
 constexpr int kBandNT = 256;
 constexpr int kMaxCPT = 6;                          // columns per thread (template parameter 1..6): sensors up to 1536 px wide
-constexpr int kRing = 4;
+constexpr int kBandRows = 8;                        // rows of a sub-band
+constexpr int kRing = 4;                            // rows of the rolling Scharr rings (phase 3)
+
+// 8-byte asynchronous global -> shared copy; `valid == false` zero-fills (rows outside the image)
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 struct BandSmemTail {
     double red[kBandNT / 32][kFPart];
@@ -130,7 +141,7 @@ struct BandSmemTail {
 };
 
 __host__ __device__ inline size_t image_pass_smem_bytes(int W) {
-    return (size_t)3 * kRing * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
+    return (size_t)(kBandRows + 4 + 2 * kRing) * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
 }
 
 template <int CPT>
@@ -138,10 +149,11 @@ __global__ void __launch_bounds__(kBandNT)
 k_image_pass(const ImagePassArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = A.H, W = A.W, R = A.R, Wp = W + 2;
-    double* ringI = reinterpret_cast<double*>(smem_raw);             // [kRing][Wp]
-    double* ringX = ringI + kRing * Wp;                              // Scharr x of rows, phase 3
-    double* ringY = ringX + kRing * Wp;
+    double* bandI = reinterpret_cast<double*>(smem_raw);             // [kBandRows + 4][Wp]: image rows sa-2 .. sa+kBandRows+1
+    double* ringX = bandI + (kBandRows + 4) * Wp;                    // [kRing][Wp]   phase 1: edge rows of the sub-band
+    double* ringY = ringX + kRing * Wp;                              // [kRing][Wp]   (2 * kRing == kBandRows rows in total)
     BandSmemTail& S = *reinterpret_cast<BandSmemTail*>(ringY + kRing * Wp);
+    static_assert(2 * kRing == kBandRows, "the edge rows of a sub-band live in the two Scharr rings during phase 1");
     const int HW = H * W;
     const int tid = threadIdx.x;
     const int G = gridDim.x, b = blockIdx.x;
@@ -149,8 +161,8 @@ k_image_pass(const ImagePassArgs A) {
     const int row_begin = (int)(((long long)RH * b) / G), row_end = (int)(((long long)RH * (b + 1)) / G);
     const int r_first = row_begin < row_end ? row_begin / H : 0, r_last = row_begin < row_end ? (row_end - 1) / H : -1;
 
-    // zero columns of the rings (never written afterwards), identity partials, accumulators of the event backward pass
-    for (int k = tid; k < 3 * kRing; k += kBandNT) { ringI[k * Wp] = 0.0; ringI[k * Wp + W + 1] = 0.0; }
+    // zero columns (never written afterwards), identity partials, accumulators of the event backward pass
+    for (int k = tid; k < kBandRows + 4 + 2 * kRing; k += kBandNT) { bandI[k * Wp] = 0.0; bandI[k * Wp + W + 1] = 0.0; }
     for (int k = tid; k < R * kFPart; k += kBandNT) {
         const int q = k / kFPart, f = k % kFPart;
         A.part[(q * G + b) * kFPart + f] = (f == 4) ? INFINITY : ((f == 6) ? -INFINITY : 0.0);
@@ -160,71 +172,70 @@ k_image_pass(const ImagePassArgs A) {
     if (A.zero_buf2 != nullptr)
         for (int k = b * kBandNT + tid; k < A.n_zero2; k += G * kBandNT) A.zero_buf2[k] = 0.0;
 
+    // asynchronous copy of image rows [y0, y1) of `src` (8-byte cells) into bandI, row y at slot y - slot0
+    auto copy_rows = [&](const void* src, int y0, int y1, int slot0) {
+        const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(src);
+        for (int y = y0; y < y1; ++y) {
+            double* dst = bandI + (y - slot0) * Wp + 1;
+            const bool in = y >= 0 && y < H;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                if (x < W) cp_async8(dst + x, in ? (const void*)(s8 + y * W + x) : (const void*)s8, in);
+            }
+        }
+    };
+
     // ---- phase 1: float64 image + statistics --------------------------------------------------------------------------
     for (int r = r_first; r <= r_last; ++r) {
         const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
         const unsigned long long* Fr = A.fix + r * HW;
         const double* Er = A.edges + r * HW;
         double* Ir = A.iwe + r * HW;
-        auto load_fix_row = [&](int y, unsigned long long (&v)[CPT]) {
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                v[c] = (x < W && y >= 0 && y < H) ? __ldcg(Fr + y * W + x) : 0ull;
-            }
-        };
-        auto store_row = [&](int y, const unsigned long long (&v)[CPT]) {
-            double* dst = ringI + (y & (kRing - 1)) * Wp + 1;
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                if (x < W) dst[x] = (double)(long long)v[c] * kFixToIwe;
-            }
-        };
-        unsigned long long pre[CPT];
-        double epre[CPT];
-        __syncthreads();                               // ring reuse across reference images
-        load_fix_row(ya - 1, pre); store_row(ya - 1 + kRing, pre);     // (+kRing keeps the slot index non-negative)
-        load_fix_row(ya, pre); store_row(ya, pre);
-        load_fix_row(ya + 1, pre);
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const int x = tid + c * kBandNT;
-            epre[c] = (x < W) ? __ldg(Er + ya * W + x) : 0.0;
-        }
         FusedAcc acc;
         acc.init();
         int cnt_mn = 0, cnt_mx = 0;                   // tie counts of the running min / max (integers: branch-free update)
-        for (int y = ya; y < yb; ++y) {
-            store_row(y + 1, pre);
-            double e[CPT];
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) e[c] = epre[c];
-            if (y + 1 < yb) {                          // prefetch the next iteration's operands
-                load_fix_row(y + 2, pre);
+        for (int sa = ya; sa < yb; sa += kBandRows) {
+            const int sb = min(sa + kBandRows, yb);
+            __syncthreads();                           // previous readers of the band are done
+            copy_rows(Fr, sa - 1, sb + 1, sa - 2);
+            for (int y = sa; y < sb; ++y) {            // edge rows -> ring area, row y at slot y - sa
+                double* dst = ringX + (y - sa) * Wp + 1;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
-                    epre[c] = (x < W) ? __ldg(Er + (y + 1) * W + x) : 0.0;
+                    if (x < W) cp_async8(dst + x, Er + y * W + x, true);
+                }
+            }
+            cp_async_commit_wait_all();
+            for (int y = sa - 1; y < sb + 1; ++y) {    // fixed point -> float64, each thread the cells it copied
+                double* row = bandI + (y - sa + 2) * Wp + 1;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    if (x < W) row[x] = (double)(long long)reinterpret_cast<const unsigned long long*>(row)[x] * kFixToIwe;
                 }
             }
             __syncthreads();
-            const double* up = ringI + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
-            const double* mid = ringI + (y & (kRing - 1)) * Wp + 1;
-            const double* dn = ringI + ((y + 1) & (kRing - 1)) * Wp + 1;
+            for (int y = sa; y < sb; ++y) {
+                const double* mid = bandI + (y - sa + 2) * Wp + 1;
+                const double* up = mid - Wp;
+                const double* dn = mid + Wp;
+                const double* er = ringX + (y - sa) * Wp + 1;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                if (x < W) {
-                    double gx, gy;
-                    scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
-                    const double I = mid[x];
-                    Ir[y * W + x] = I;
-                    acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += e[c] * I;
-                    cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
-                    cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
-                    acc.mn = fmin(acc.mn, I);
-                    acc.mx = fmax(acc.mx, I);
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    if (x < W) {
+                        double gx, gy;
+                        scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
+                        const double I = mid[x];
+                        Ir[y * W + x] = I;
+                        acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += er[x] * I;
+                        cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
+                        cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
+                        acc.mn = fmin(acc.mn, I);
+                        acc.mx = fmax(acc.mx, I);
+                    }
                 }
             }
         }
@@ -277,26 +288,11 @@ k_image_pass(const ImagePassArgs A) {
         if (!A.want_grad) continue;
         const double* Er = A.edges + r * HW;
         const double* Ir = A.iwe + r * HW;
-        auto load_row = [&](int y, double (&v)[CPT]) {
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                v[c] = (x < W && y >= 0 && y < H) ? __ldcg(Ir + y * W + x) : 0.0;
-            }
-        };
-        auto store_row = [&](int y, const double (&v)[CPT]) {
-            double* dst = ringI + ((y + kRing) & (kRing - 1)) * Wp + 1;
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                if (x < W) dst[x] = v[c];
-            }
-        };
-        // Scharr pair of row q from the ring rows q-1, q, q+1 (zero outside the image: 'same' output only exists inside)
-        auto grad_row = [&](int q) {
-            const double* up = ringI + ((q - 1 + kRing) & (kRing - 1)) * Wp + 1;
-            const double* mid = ringI + ((q + kRing) & (kRing - 1)) * Wp + 1;
-            const double* dn = ringI + ((q + 1 + kRing) & (kRing - 1)) * Wp + 1;
+        // Scharr pair of row q from the band rows q-1, q, q+1 (zero outside the image: 'same' output only exists inside)
+        auto grad_row = [&](int q, int sa) {
+            const double* mid = bandI + (q - sa + 2) * Wp + 1;
+            const double* up = mid - Wp;
+            const double* dn = mid + Wp;
             double* gxr = ringX + ((q + kRing) & (kRing - 1)) * Wp + 1;
             double* gyr = ringY + ((q + kRing) & (kRing - 1)) * Wp + 1;
             const bool inside = q >= 0 && q < H;
@@ -314,58 +310,54 @@ k_image_pass(const ImagePassArgs A) {
         const double cA = S.coefA[r], cB = S.coefB[r];
         const double g_M = -st.s2 / (st.D * st.D);
         const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
-        double pre[CPT], epre[CPT];
-        __syncthreads();                               // ring reuse across reference images
-        load_row(ya - 2, pre); store_row(ya - 2, pre);
-        load_row(ya - 1, pre); store_row(ya - 1, pre);
-        load_row(ya, pre); store_row(ya, pre);
-        __syncthreads();
-        grad_row(ya - 1);                              // needs rows ya-2 .. ya
-        load_row(ya + 1, pre); store_row(ya + 1, pre); // slot of row ya-3: free
-        __syncthreads();
-        grad_row(ya);                                  // needs rows ya-1 .. ya+1
-        load_row(ya + 2, pre);
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const int x = tid + c * kBandNT;
-            epre[c] = (x < W) ? __ldg(Er + ya * W + x) : 0.0;
-        }
-        for (int y = ya; y < yb; ++y) {
-            store_row(y + 2, pre);                     // into the slot of row y-2, last read two iterations ago
-            double e[CPT];
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) e[c] = epre[c];
-            if (y + 1 < yb) {
-                load_row(y + 3, pre);
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    epre[c] = (x < W) ? __ldg(Er + (y + 1) * W + x) : 0.0;
-                }
-            }
-            __syncthreads();
-            grad_row(y + 1);                           // rows y .. y+2
-            __syncthreads();
-            const double* xu = ringX + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
-            const double* xm = ringX + (y & (kRing - 1)) * Wp + 1;
-            const double* xd = ringX + ((y + 1) & (kRing - 1)) * Wp + 1;
-            const double* yu = ringY + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
-            const double* yd = ringY + ((y + 1) & (kRing - 1)) * Wp + 1;
-            const double* mid = ringI + (y & (kRing - 1)) * Wp + 1;
+        for (int sa = ya; sa < yb; sa += kBandRows) {
+            const int sb = min(sa + kBandRows, yb);
+            __syncthreads();                           // previous readers of the band / rings are done
+            copy_rows(Ir, sa - 2, sb + 2, sa - 2);
+            double epre[CPT];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
                 const int x = tid + c * kBandNT;
-                if (x < W) {
-                    const double I = mid[x];
-                    const double adj = scharr_adjoint_rows(xu + x, xm + x, xd + x, yu + x, yd + x);
-                    const double cI = I - st.mn;
-                    const double gN = cB * (e[c] - cI / st.D);
-                    double out = cA * adj + gN / st.D;
-                    if (I == st.mn) out += g_m / st.cnt_min;
-                    if (I == st.mx) out += g_M / st.cnt_max;
-                    const int p = y * W + x;
-                    if (A.dldi != nullptr) A.dldi[r * HW + p] = out;
-                    A.dldi32[r * HW + p] = (float)(out * kInv2Pi);
+                epre[c] = (x < W) ? __ldg(Er + sa * W + x) : 0.0;
+            }
+            cp_async_commit_wait_all();
+            __syncthreads();
+            grad_row(sa - 1, sa);
+            grad_row(sa, sa);
+            for (int y = sa; y < sb; ++y) {
+                grad_row(y + 1, sa);                   // ring slot of row y-3: last read by the adjoint of row y-2
+                double e[CPT];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) e[c] = epre[c];
+                if (y + 1 < sb) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        const int x = tid + c * kBandNT;
+                        epre[c] = (x < W) ? __ldg(Er + (y + 1) * W + x) : 0.0;
+                    }
+                }
+                __syncthreads();
+                const double* xu = ringX + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
+                const double* xm = ringX + (y & (kRing - 1)) * Wp + 1;
+                const double* xd = ringX + ((y + 1) & (kRing - 1)) * Wp + 1;
+                const double* yu = ringY + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
+                const double* yd = ringY + ((y + 1) & (kRing - 1)) * Wp + 1;
+                const double* mid = bandI + (y - sa + 2) * Wp + 1;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    if (x < W) {
+                        const double I = mid[x];
+                        const double adj = scharr_adjoint_rows(xu + x, xm + x, xd + x, yu + x, yd + x);
+                        const double cI = I - st.mn;
+                        const double gN = cB * (e[c] - cI / st.D);
+                        double out = cA * adj + gN / st.D;
+                        if (I == st.mn) out += g_m / st.cnt_min;
+                        if (I == st.mx) out += g_M / st.cnt_max;
+                        const int p = y * W + x;
+                        if (A.dldi != nullptr) A.dldi[r * HW + p] = out;
+                        A.dldi32[r * HW + p] = (float)(out * kInv2Pi);
+                    }
                 }
             }
         }

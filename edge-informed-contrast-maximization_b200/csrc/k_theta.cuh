@@ -81,7 +81,8 @@ template <bool HAS_TV>
 __global__ void __launch_bounds__(kTgWarps * 32)
 k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
              double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, AxisTaps ty, AxisTaps tx,
-             const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */) {
+             const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */,
+             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kTgWarps + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -150,6 +151,14 @@ k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, Dev
 #pragma unroll
     for (int o = 16; o; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
     if (lane == 0) { sc->dalpha = da; sc->counters[5] = 0u; }
+    // synchronous host entry points: the last warp delivers [gradient | loss | d/d alpha] straight into mapped pinned host
+    // memory (no device -> host copy operation after the kernel)
+    if (host_out != nullptr) {
+        const int n = host_grad ? h * w * 2 : 0;
+        for (int e = lane; e < n; e += 32) host_out[e] = __ldcg(grad + e);
+        if (lane == 0) { host_out[n] = __ldcg(loss_dev); host_out[n + 1] = da; }
+        __threadfence_system();
+    }
 }
 
 // ---- backward of the resize, scatter form (large / dense theta) -----------------------------------------
