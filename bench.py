@@ -4,14 +4,14 @@ Gevents/s/GPU at DSEC 640x480).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dsec] [--theta 16]
 
-A *step* is one objective+gradient evaluation (all R reference times, forward + analytic backward) of one synthetic
-DSEC-shaped event window.  Steps cycle round-robin over ``--windows`` distinct windows whose combined working set is
-larger than the 126 MB L2, so no step finds its inputs cached by the previous one.
+A *step* is one objective+gradient evaluation (all R reference times, forward + analytic backward) of EACH of ``--windows``
+independent synthetic DSEC-shaped event windows resident on the GPU (a batch of windows; one plan and one stream per window).
+Their combined working set is larger than the 126 MB L2.  ``single_window`` reports the same evaluations one at a time.
 
 Own arm  : ``value``  = device-resident evaluation (theta, loss and gradient stay in HBM), timed with CUDA events on the
            launching stream, max over ranks.  ``e2e`` = the same evaluations through the reference-facing host call
-           (``WindowObjective.value_and_grad`` -> ``eincm_value_and_grad_host``: theta from host memory, loss + gradient
-           read back to the host every step - exactly what jaxopt's ``scipy_fun`` does per line-search step).
+           (``eincm_value_and_grad_host_batch``: theta of every window from host memory, loss + gradient of every window
+           read back to the host every step; per window this is what jaxopt's ``scipy_fun`` does per line-search step).
            ``e2e_stateless`` additionally re-stages the whole window (events + edge images) from pinned host memory every
            step (``set_window`` + evaluation).
 Reference arm (``--impl reference``): the CPU restatement of the reference (``oracle/``; JAX is not installable in this
@@ -232,13 +232,32 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def dev_step(i):
-        k = i % nw
+    # A step = one objective+gradient evaluation of EACH of the nw independent windows resident on this GPU (a batch of
+    # windows, BASELINE.json configs[2]/[3]); every window has its own plan and stream, so kernels of different windows overlap.
+    streams = [torch.cuda.Stream() for _ in plans]
+    main = torch.cuda.current_stream()
+
+    def dev_eval(k):
         plans[k].value_and_grad_device(thetas_d[k], hp, losses_d[k], grads_d[k])
 
+    def dev_step():
+        for k in range(nw):
+            with torch.cuda.stream(streams[k]):
+                dev_eval(k)
+
+    def fork():
+        for st in streams:
+            st.wait_stream(main)
+
+    def join():
+        for st in streams:
+            main.wait_stream(st)
+
     # ---- device-resident timing -------------------------------------------------------------------------------
+    fork()
     for i in range(args.warmup):
-        dev_step(i)
+        dev_step()
+    join()
     launches0 = sum(p.launch_count() for p in plans)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -248,8 +267,10 @@ def run_own(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
+    fork()
     for i in range(args.steps):
-        dev_step(args.warmup + i)
+        dev_step()
+    join()
     ev1.record()
     barrier()
     t_wall1 = time.time()
@@ -257,14 +278,26 @@ def run_own(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     launches = sum(p.launch_count() for p in plans) - launches0
     ms_per_step = ms_total / args.steps
-    value = world * N * args.steps / (ms_total * 1e-3) / 1e9
+    value = world * nw * N * args.steps / (ms_total * 1e-3) / 1e9
 
-    # per-kernel durations for the roofline: a second pass over the same steps with CUDA events around every launch
-    # (eincm_plan_set_timing, events on the launching stream); kept out of the timed region above
+    # the same evaluations one window at a time on one stream (no overlap between windows)
+    for i in range(args.warmup):
+        dev_eval(i % nw)
+    barrier()
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record()
+    for i in range(args.steps * nw):
+        dev_eval(i % nw)
+    es1.record()
+    barrier()
+    ms_single = max_over_ranks(es0.elapsed_time(es1)) / (args.steps * nw)
+
+    # per-kernel durations for the roofline: a third pass (one stream) with CUDA events around every launch
+    # (eincm_plan_set_timing, events on the launching stream); kept out of the timed regions above
     for p in plans:
         p.set_timing(True)
-    for i in range(args.steps):
-        dev_step(args.warmup + i)
+    for i in range(args.steps * nw):
+        dev_eval(i % nw)
     torch.cuda.synchronize()
     kt = {}
     for p in plans:
@@ -274,20 +307,32 @@ def run_own(args):
         p.set_timing(False)
 
     # ---- end to end through the host-facing call --------------------------------------------------------------
-    def host_step(i):
-        k = i % nw
-        return plans[k].value_and_grad_host(thetas_h[k], hp)
+    # per step: theta of every window from host memory in, loss + gradient of every window out (one synchronous batched call)
+    def host_step():
+        return P.value_and_grad_host_batch(plans, thetas_h, hp)
 
     for i in range(args.warmup):
-        host_step(i)
+        host_step()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        loss_h, grad_h = host_step(args.warmup + i)
+        losses_h, grads_h = host_step()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * N * args.steps / e2e_s / 1e9
+    e2e_value = world * nw * N * args.steps / e2e_s / 1e9
+    loss_h, grad_h = float(losses_h[-1]), grads_h[-1]
     theta_bytes = int(np.prod(shape)) * 2 * 8
+
+    # the reference's own calling pattern: one window per synchronous host call (jaxopt's scipy_fun per line-search step)
+    for i in range(args.warmup):
+        plans[i % nw].value_and_grad_host(thetas_h[i % nw], hp)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps * nw):
+        plans[i % nw].value_and_grad_host(thetas_h[i % nw], hp)
+    torch.cuda.synchronize()
+    e2e1_s = max_over_ranks(time.perf_counter() - t0)
+    e2e1_value = world * N * args.steps * nw / e2e1_s / 1e9
 
     # ---- stateless: stage the whole window from pinned host memory every step ---------------------------------
     pin = []
@@ -329,7 +374,7 @@ def run_own(args):
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                     'traffic': None, 'algorithmic_bytes_per_launch': dom_bytes, 'kernel_ms': kern_ms[dom],
                     'kernel_share_of_step': kt[dom][0] / span_total if span_total else None, 'peak_source': peak_src}
-    eval_achieved = alg['eval'] / (ms_per_step * 1e-3) / 1e9
+    eval_achieved = nw * alg['eval'] / (ms_per_step * 1e-3) / 1e9
 
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----------------------------------------------------
     cpu = None
@@ -343,15 +388,22 @@ def run_own(args):
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'{args.workload}: DSEC-shaped {W}x{H}, N={N} events/window, R={R} reference times, theta '
                                f'{shape[0]}x{shape[1]}x2 (finest pyramid level), alpha={hpd["alpha"]}, beta={hpd["beta"]}',
-                   'l2': f'inputs larger than L2: {nw} distinct windows per GPU evaluated round-robin '
+                   'step': f'one objective+gradient evaluation of each of {nw} independent windows per GPU (one plan and one '
+                           f'stream per window: kernels of different windows overlap)',
+                   'l2': f'inputs larger than L2: {nw} distinct windows per GPU '
                          f'(~{nw * (N * 16 + (3 * R + 6) * H * W * 8) / 1e6:.0f} MB working set)',
                    'parallelism': f'windows sharded over {world} GPU(s), no data-path collective',
-                   'events_per_step_per_gpu': N},
+                   'windows_per_step_per_gpu': nw, 'events_per_step_per_gpu': nw * N},
         'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': theta_bytes, 'd2h_bytes_per_step': theta_bytes + 8,
-                'call': 'WindowObjective/Plan.value_and_grad_host -> eincm_value_and_grad_host (theta from host, loss+grad to host; '
-                        'window operands staged once per window like the reference\'s jnp arrays)',
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nw * theta_bytes, 'd2h_bytes_per_step': nw * (theta_bytes + 8),
+                'call': 'plan.value_and_grad_host_batch -> eincm_value_and_grad_host_batch: one synchronous call per step, theta of '
+                        'every window from host memory in, loss + gradient of every window out (window operands are staged once '
+                        'per window like the reference\'s jnp arrays)',
                 'ms_per_step': e2e_s / args.steps * 1e3},
+        'single_window': {'value': world * N / (ms_single * 1e-3) / 1e9, 'ms_per_eval': ms_single,
+                          'e2e_value': e2e1_value, 'e2e_ms_per_eval': e2e1_s / (args.steps * nw) * 1e3, 'unit': UNIT,
+                          'note': 'one window at a time on one stream; e2e = eincm_value_and_grad_host per evaluation (what '
+                                  'jaxopt\'s scipy_fun does per line-search step)'},
         'e2e_stateless': {'value': sl_value, 'unit': UNIT, 'h2d_bytes_per_step': window_bytes + theta_bytes,
                           'd2h_bytes_per_step': theta_bytes + 8, 'steps': n_sl, 'ms_per_step': sl_s / n_sl * 1e3,
                           'call': 'set_window from pinned host memory + value_and_grad_host every step'},

@@ -51,6 +51,8 @@ struct eincm_plan {
     bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
     ThetaSrc tsrc{};              // flow operand of the last forward pass
     bool theta_full_valid = false;
+    cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
+    size_t host_ng = 0;                  // gradient doubles of the host evaluation in flight (host_enqueue -> host_collect)
     bool host_delivered = false;  // the last backward pass wrote its results into the mapped host buffer itself
     double* h_mapped_dev = nullptr;   // device alias of h_pinned (cudaHostAllocMapped)
     bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
@@ -563,6 +565,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->out_stage, 8));
         CU(cudaHostAlloc((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double), cudaHostAllocMapped));
         CU(cudaHostGetDevicePointer((void**)&plan->h_mapped_dev, plan->h_pinned, 0));
+        CU(cudaStreamCreateWithFlags(&plan->own_stream, cudaStreamNonBlocking));
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
         return EINCM_OK;
     };
@@ -588,6 +591,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     for (auto& kv : plan->taps_cache) if (kv.second.blob) cudaFree(kv.second.blob);
     for (auto& sp : plan->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& e : plan->event_pool) cudaEventDestroy(e);
+    if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     if (plan->h_pinned) cudaFreeHost(plan->h_pinned);
     if (plan->h_flag) cudaFreeHost(plan->h_flag);
     delete plan;
@@ -718,39 +722,83 @@ int eincm_handover_value_and_grad(eincm_plan* plan, double alpha_handover, const
     return backward_impl(plan, hp, loss_out, nullptr, dalpha_out, st);
 }
 
-int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp, double* loss_out_host,
-                              double* grad_out_host, void* cuda_stream) {
-    if (!plan) return EINCM_EINVAL;
-    if (!theta_host || !loss_out_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+}  // extern "C"
+
+namespace {
+
+// Enqueues one host-operand evaluation on `st`: theta through the pinned staging area, the four kernels, and - when the
+// results do not come back through mapped memory - the device -> host copy.  host_collect waits and hands the results over.
+int host_enqueue(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp, bool want_grad, cudaStream_t st) {
+    if (!theta_host) return fail(plan, EINCM_EINVAL, "NULL operand");
     if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
     if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "event-split plans use the split-phase calls");
     CU(cudaSetDevice(plan->device));
-    cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t nb = (size_t)h * w * 2 * sizeof(double);
     std::memcpy(plan->h_pinned, theta_host, nb);
     CU(cudaMemcpyAsync(plan->theta_stage, plan->h_pinned, nb, cudaMemcpyHostToDevice, st));
     // results come back through mapped pinned memory written by the last kernel; the staged copy is the fallback for the
     // paths that end in other kernels (dense theta, loss only)
-    const size_t n_g = grad_out_host ? (size_t)h * w * 2 : 0;
+    const size_t n_g = want_grad ? (size_t)h * w * 2 : 0;
+    plan->host_ng = n_g;
     double* loss_dev = plan->grad_stage + n_g;
-    double* h_res = plan->h_pinned + (size_t)plan->HW * 2 + 16;       // [grad | loss | dalpha]; theta staging lives in front
     int rc = forward_events_impl(plan, plan->theta_stage, nullptr, 0.0, h, w, hp, st);
     if (rc) return rc;
     const bool small = n_g + 2 <= 1000;                                // fits behind the theta staging area
-    rc = backward_impl(plan, hp, loss_dev, grad_out_host ? plan->grad_stage : nullptr, nullptr, st,
+    rc = backward_impl(plan, hp, loss_dev, want_grad ? plan->grad_stage : nullptr, nullptr, st,
                        small ? plan->h_mapped_dev + (size_t)plan->HW * 2 + 16 : nullptr);
     if (rc) return rc;
-    if (plan->host_delivered) {
-        CU(cudaStreamSynchronize(st));
-        *loss_out_host = h_res[n_g];
-        if (grad_out_host) std::memcpy(grad_out_host, h_res, nb);
-        return EINCM_OK;
-    }
-    CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, (n_g + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    *loss_out_host = plan->h_pinned[n_g];
-    if (grad_out_host) std::memcpy(grad_out_host, plan->h_pinned, nb);
+    if (!plan->host_delivered)
+        CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, (n_g + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
     return EINCM_OK;
+}
+
+int host_collect(eincm_plan* plan, double* loss_out_host, double* grad_out_host, cudaStream_t st) {
+    CU(cudaStreamSynchronize(st));
+    const double* h_res = plan->host_delivered ? plan->h_pinned + (size_t)plan->HW * 2 + 16 : plan->h_pinned;   // [grad | loss]
+    *loss_out_host = h_res[plan->host_ng];
+    if (grad_out_host) std::memcpy(grad_out_host, h_res, plan->host_ng * sizeof(double));
+    return EINCM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp, double* loss_out_host,
+                              double* grad_out_host, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!loss_out_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int rc = host_enqueue(plan, theta_host, h, w, hp, grad_out_host != nullptr, st);
+    if (rc) return rc;
+    return host_collect(plan, loss_out_host, grad_out_host, st);
+}
+
+int eincm_value_and_grad_host_batch(eincm_plan* const* plans, int n_plans, const double* const* thetas_host, int h, int w,
+                                    const eincm_hparams* hp, double* losses_out_host, double* const* grads_out_host) {
+    if (!plans || n_plans < 1 || !plans[0]) return EINCM_EINVAL;
+    eincm_plan* plan = plans[0];                                       // errors of the batch are reported on the first plan
+    if (!thetas_host || !losses_out_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+    for (int k = 0; k < n_plans; ++k) {
+        if (!plans[k] || !thetas_host[k]) return fail(plan, EINCM_EINVAL, "plan / theta %d is NULL", k);
+        if (plans[k]->device != plan->device) return fail(plan, EINCM_EINVAL, "all plans of a batch must live on one device");
+        for (int q = 0; q < k; ++q) if (plans[q] == plans[k]) return fail(plan, EINCM_EINVAL, "plan %d appears twice in the batch", k);
+    }
+    for (int k = 0; k < n_plans; ++k) {
+        const bool want_grad = grads_out_host != nullptr && grads_out_host[k] != nullptr;
+        const int rc = host_enqueue(plans[k], thetas_host[k], h, w, hp, want_grad, plans[k]->own_stream);
+        if (rc) {
+            if (plans[k] != plan) plan->error = plans[k]->error;
+            for (int q = 0; q < k; ++q) cudaStreamSynchronize(plans[q]->own_stream);
+            return rc;
+        }
+    }
+    int rc_all = EINCM_OK;
+    for (int k = 0; k < n_plans; ++k) {
+        const int rc = host_collect(plans[k], losses_out_host + k, grads_out_host ? grads_out_host[k] : nullptr, plans[k]->own_stream);
+        if (rc && !rc_all) { rc_all = rc; if (plans[k] != plan) plan->error = plans[k]->error; }
+    }
+    return rc_all;
 }
 
 int eincm_handover_value_and_grad_host(eincm_plan* plan, double alpha_handover, const double* prev_theta_host, const double* theta_host,

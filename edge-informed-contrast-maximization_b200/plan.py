@@ -27,7 +27,8 @@ S_HEADER = 8
 EXPORTED_SYMBOLS = (
     'eincm_plan_create', 'eincm_plan_destroy', 'eincm_last_error', 'eincm_abi_version', 'eincm_plan_set_window',
     'eincm_value_and_grad', 'eincm_handover_value_and_grad', 'eincm_value_and_grad_host',
-    'eincm_handover_value_and_grad_host', 'eincm_value_and_grad_stateless_host', 'eincm_window_finalize',
+    'eincm_handover_value_and_grad_host', 'eincm_value_and_grad_stateless_host', 'eincm_value_and_grad_host_batch',
+    'eincm_window_finalize',
     'eincm_forward_events', 'eincm_backward', 'eincm_zero_iwe_ptr', 'eincm_iwe_ptr', 'eincm_dldi_ptr',
     'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
@@ -79,6 +80,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_value_and_grad_host': (i32, [vp, vp, i32, i32, hp, C.POINTER(dbl), vp, vp]),
         'eincm_handover_value_and_grad_host': (i32, [vp, dbl, vp, vp, i32, i32, hp, C.POINTER(dbl), C.POINTER(dbl), vp]),
         'eincm_value_and_grad_stateless_host': (i32, [vp, vp, i32, i32, vp, vp, vp, i64, vp, vp, i32, hp, C.POINTER(dbl), vp, vp]),
+        'eincm_value_and_grad_host_batch': (i32, [C.POINTER(vp), i32, C.POINTER(vp), i32, i32, hp, C.POINTER(dbl), C.POINTER(vp)]),
         'eincm_window_finalize': (i32, [vp, vp]),
         'eincm_forward_events': (i32, [vp, vp, i32, i32, hp, vp]),
         'eincm_backward': (i32, [vp, hp, vp, vp, vp]),
@@ -113,6 +115,28 @@ def _stream_ptr(stream=None) -> int:
     torch = _torch()
     s = stream if stream is not None else torch.cuda.current_stream()
     return int(s.cuda_stream)
+
+
+def value_and_grad_host_batch(plans: Sequence['Plan'], thetas: Sequence[np.ndarray], hp: HParams, want_grad: bool = True):
+    """``eincm_value_and_grad_host_batch``: one synchronous call evaluating independent windows (one plan each) concurrently.
+    Returns ``(losses float64[n], grads list of (h, w, 2) arrays or None)``."""
+    n = len(plans)
+    if n == 0 or len(thetas) != n:
+        raise EincmError(EINCM_EINVAL, 'plans and thetas must be non-empty and of equal length')
+    ths = [np.ascontiguousarray(t, dtype=np.float64) for t in thetas]
+    shape = ths[0].shape
+    if len(shape) != 3 or shape[2] != 2 or any(t.shape != shape for t in ths):
+        raise EincmError(EINCM_EINVAL, 'every theta of a batch must have the same shape (h, w, 2)')
+    lib = plans[0].lib
+    hs = (C.c_void_p * n)(*[p._h.value for p in plans])
+    tp = (C.c_void_p * n)(*[t.ctypes.data for t in ths])
+    losses = np.empty(n, dtype=np.float64)
+    grads = [np.empty_like(t) for t in ths] if want_grad else None
+    gp = (C.c_void_p * n)(*[g.ctypes.data for g in grads]) if want_grad else None
+    rc = lib.eincm_value_and_grad_host_batch(hs, n, tp, shape[0], shape[1], C.byref(hp), losses.ctypes.data_as(C.POINTER(C.c_double)), gp)
+    if rc != EINCM_OK:
+        raise EincmError(rc, (lib.eincm_last_error(plans[0]._h) or b'').decode())
+    return losses, grads
 
 
 class _DevView:

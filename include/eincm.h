@@ -122,6 +122,13 @@ int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h,
 int eincm_handover_value_and_grad_host(eincm_plan* plan, double alpha_handover, const double* prev_theta_host,
                                        const double* theta_host, int h, int w, const eincm_hparams* hp,
                                        double* loss_out_host, double* dalpha_out_host, void* cuda_stream);
+/* Batch of independent windows (BASELINE.json configs[2], [3]: "batch of windows on 1xB200", windows sharded): evaluates
+ * plans[k] at thetas_host[k] ([h][w][2] each), every plan on its own internal stream, and returns when all are done.  The fixed
+ * launch / synchronisation latency of a host call is paid once per batch and kernels of different windows overlap.  All plans on
+ * one device; grads_out_host (or single entries of it) may be NULL: value only.  The reference evaluates windows one at a time
+ * (src/eincm/solver.py:209-216); independent sequences / windows without handover may be evaluated together. */
+int eincm_value_and_grad_host_batch(eincm_plan* const* plans, int n_plans, const double* const* thetas_host, int h, int w,
+                                    const eincm_hparams* hp, double* losses_out_host, double* const* grads_out_host);
 /* Stateless single shot with the exact operand list of loss_func (losses.py:108-114), every operand on the host:
  * set_window + value_and_grad + copies. */
 int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_host, int h, int w,

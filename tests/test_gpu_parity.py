@@ -331,3 +331,31 @@ def test_hot_pixel_and_ragged_tiles(L):
     l_ref, g_ref = O.value_and_grad(th, xs, ys, ts, base.edges, base.edge_ts, **kw)
     assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
     assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
+def test_batched_host_call_matches_single_calls(tiny):
+    """eincm_value_and_grad_host_batch: independent windows evaluated concurrently, each on its own stream, give the results
+    of one-at-a-time calls (objective bit-identical: it does not depend on scheduling)."""
+    from eincm_b200 import plan as P
+    hp = P.make_hparams(20.0, 35.0, 0.0, 0.0, 1)
+    wins = [tiny, S.make_workload('tiny', seed=7), S.make_workload('tiny', seed=8)]
+    plans, thetas = [], []
+    for k, w in enumerate(wins):
+        p = P.Plan(w.sensor_size, max_events=len(w.xs), max_refs=3)
+        p.set_window(*w.args())
+        plans.append(p)
+        thetas.append(S.theta_test_points(w, (4, 4), seed=k)['perturbed'])
+    losses, grads = P.value_and_grad_host_batch(plans, thetas, hp)
+    for k, w in enumerate(wins):
+        l1, g1 = plans[k].value_and_grad_host(thetas[k], hp)
+        assert losses[k] == l1
+        assert _rel_inf(grads[k], g1) <= 1e-11
+        l_ref, g_ref = O.value_and_grad(thetas[k], *w.args(), **_kw(w))
+        assert abs(losses[k] - l_ref) <= OBJ_RTOL * abs(l_ref)
+        assert _rel_inf(grads[k], g_ref) <= GRAD_RTOL
+    losses_v, none = P.value_and_grad_host_batch(plans, thetas, hp, want_grad=False)
+    assert none is None and (losses_v == losses).all()
+    with pytest.raises(P.EincmError):
+        P.value_and_grad_host_batch([plans[0], plans[0]], thetas[:2], hp)      # the same plan twice
+    for p in plans:
+        p.close()
