@@ -334,6 +334,33 @@ def run_own(args):
     e2e1_s = max_over_ranks(time.perf_counter() - t0)
     e2e1_value = world * N * args.steps * nw / e2e1_s / 1e9
 
+    # ---- windows/s: complete multi-level solves (BASELINE.json metric, second half) -------------------------------
+    # The reference's run loop (exp_mgr.py:615-659): per window the 5-level coarse-to-fine solve of solver.py with the
+    # main.yaml defaults (BFGS 40/28/19/11/8 iterations, retries at levels 0/1, handover solved by L-BFGS-B at levels 1/0),
+    # consecutive windows of a rank chained through the handover prior.  scipy drives, every evaluation is a host call.
+    solve = None
+    if args.solve_windows > 0:
+        from eincm_b200 import losses, solver as SV
+        obj = losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3))
+        sol = SV.MultipleLevelEINCMSolver(obj)
+        sol.set_datasample(*wins[0].args())
+        sol.solve()                                    # warm-up solve (first sample: no handover)
+        barrier()
+        n0 = obj.n_evals
+        t0 = time.perf_counter()
+        for k in range(args.solve_windows):
+            sol.set_datasample(*wins[(k + 1) % nw].args())
+            res = sol.solve()
+        solve_s = max_over_ranks(time.perf_counter() - t0)
+        n_ev = obj.n_evals - n0
+        solve = {'value': world * args.solve_windows / solve_s, 'unit': 'windows/s', 'windows_per_gpu': args.solve_windows,
+                 'ms_per_window': solve_s / args.solve_windows * 1e3, 'evals_per_window': n_ev / args.solve_windows,
+                 'final_loss': res['theta_opt_state_pyr']['pyr_lvl_0'].fun_val,
+                 'note': 'eincm_b200.solver.MultipleLevelEINCMSolver (mirror of reference src/eincm/solver.py, main.yaml defaults), '
+                         'scipy BFGS / L-BFGS-B on the host, set_datasample (staging) inside the timed region, windows of a rank '
+                         'chained by handover'}
+        obj.close()
+
     # ---- stateless: stage the whole window from pinned host memory every step ---------------------------------
     pin = []
     for w in wins:
@@ -407,6 +434,7 @@ def run_own(args):
         'e2e_stateless': {'value': sl_value, 'unit': UNIT, 'h2d_bytes_per_step': window_bytes + theta_bytes,
                           'd2h_bytes_per_step': theta_bytes + 8, 'steps': n_sl, 'ms_per_step': sl_s / n_sl * 1e3,
                           'call': 'set_window from pinned host memory + value_and_grad_host every step'},
+        'windows_per_s': solve,
         'gpu_launches': int(launches),
         'roofline': roofline,
         'roofline_eval': {'bound': 'hbm', 'achieved': eval_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': eval_achieved / peak,
@@ -432,6 +460,7 @@ def main():
     ap.add_argument('--windows', type=int, default=4, help='distinct windows per GPU cycled round-robin')
     ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU work for the CPU baseline / reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--solve-windows', type=int, default=2, help='complete multi-level solves per GPU for the windows/s figure (0: skip)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':

@@ -359,3 +359,32 @@ def test_batched_host_call_matches_single_calls(tiny):
         P.value_and_grad_host_batch([plans[0], plans[0]], thetas[:2], hp)      # the same plan twice
     for p in plans:
         p.close()
+
+
+def test_multi_level_solve_on_the_cuda_objective():
+    """The solver mirror (reference src/eincm/solver.py) driven by the CUDA objective: level schedule, BFGS, handover.  BFGS
+    trajectories are chaotic in the last digits of the objective, so instead of comparing two solves the oracle is evaluated AT
+    the iterates the CUDA-driven solve produced ('theta test points: ... BFGS iterates'): the value the solver saw
+    at every level is the oracle's value there, and no level ends above where it started."""
+    from eincm_b200 import losses, solver as SV
+    w0 = S.make_window(32, 48, 1500, seed=21, n_segments=12, flow_mag=4.0)
+    w1 = S.make_window(32, 48, 1500, seed=22, n_segments=12, flow_mag=4.0)
+    kwargs = dict(n_pyr_lvls=3, theta_opt_maxiters={'pyr_lvl_0': 8, 'pyr_lvl_1': 6, 'pyr_lvl_2': 5},
+                  handover_opt_maxiters={'pyr_lvl_0': 4, 'pyr_lvl_1': 3, 'pyr_lvl_2': 2})
+    gpu = losses.WindowObjective((32, 48), 20.0, 35.0, max_events=4096, max_refs=3)
+    res = SV.solve_sequence(gpu, [w0, w1], kwargs)
+    kw = dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, n_pyr_lvls=5, sensor_size=(32, 48), scale_to_sensor_size_method='bilinear')
+    for w, r in zip((w0, w1), res):
+        for k in range(3):
+            key = f'pyr_lvl_{k}'
+            l_end = O.loss_func(r['pre_handover_theta_pyr'][key], *w.args(), cur_pyr_lvl=k, **kw)[0]
+            l_start = O.loss_func(r['pre_opt_theta_pyr'][key], *w.args(), cur_pyr_lvl=k, **kw)[0]
+            assert r['theta_opt_state_pyr'][key].fun_val == pytest.approx(l_end, rel=OBJ_RTOL)
+            assert l_end <= l_start + 1e-9 * abs(l_start)
+    assert res[0]['ho_opt_state_pyr'] == {} and set(res[1]['ho_opt_state_pyr']) == {'pyr_lvl_1', 'pyr_lvl_0'}
+    for k in (1, 0):                                   # the solved handover weight is what the blend used (solver.py:344-345)
+        key = f'pyr_lvl_{k}'
+        a = res[1]['final_handover_weight_pyr'][key]
+        blend = a * res[1]['prior_theta_pyr'][key] + (1 - a) * res[1]['pre_handover_theta_pyr'][key]
+        np.testing.assert_allclose(res[1]['final_theta_pyr'][key], blend, rtol=1e-12, atol=1e-12)
+    gpu.close()
