@@ -43,6 +43,16 @@ def _peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic():
+    """DRAM bytes per launch from the committed ncu capture of this command (profiles/r1_traffic.json)."""
+    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    try:
+        with open(p) as f:
+            return json.load(f)['dram_bytes_per_launch']
+    except Exception:
+        return {}
+
+
 def algorithmic_bytes(N, R, H, W):
     """SURVEY.md §8(d), reference dtypes: events (x:i16, y:i16, t:f64) read once per event pass (2 passes);
     per reference image: IWE written + read, edge image read, dL/dIWE written + read (f64); dense theta field
@@ -399,7 +409,7 @@ def run_own(args):
         dom_bytes = alg.get(dom, alg['eval'])
         achieved = dom_bytes / (kern_ms[dom] * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': None, 'algorithmic_bytes_per_launch': dom_bytes, 'kernel_ms': kern_ms[dom],
+                    'traffic': measured_traffic().get(dom) if args.workload == 'dsec' and args.events is None else None, 'algorithmic_bytes_per_launch': dom_bytes, 'kernel_ms': kern_ms[dom],
                     'kernel_share_of_step': kt[dom][0] / span_total if span_total else None, 'peak_source': peak_src}
     eval_achieved = nw * alg['eval'] / (ms_per_step * 1e-3) / 1e9
 
