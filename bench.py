@@ -126,6 +126,9 @@ def cpu_eval_factory():
     try:
         from oracle import c_oracle
         if c_oracle.available():
+            # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: override it for the CPU arm)
+            n_cpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+            c_oracle.set_num_threads(n_cpu)
             cores = c_oracle.num_threads()
             return c_oracle.value_and_grad, 'port', cores, f'oracle/eincm_oracle_c.c (OpenMP, {cores} threads)'
     except Exception:
@@ -208,7 +211,18 @@ def run_own(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # NCCL prints its version banner on stdout at the first collective: keep stdout for the ONE JSON line
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            t = torch.zeros(1, device='cuda')
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     wins = make_windows(args, rank)
     H, W = wins[0].sensor_size
