@@ -51,6 +51,9 @@ struct eincm_plan {
     bool window_set = false, window_final = false, zero_div_valid = false, forward_done = false;
     ThetaSrc tsrc{};              // flow operand of the last forward pass
     bool theta_full_valid = false;
+    unsigned long long* peer_fix[kMaxPeers] = {};   // event split with peer access: fixed-point images of all ranks (own included)
+    void* peer_opened[kMaxPeers] = {};              // pointers obtained from cudaIpcOpenMemHandle (closed on destroy)
+    int n_peers = 0;                                // 0: no peer access (the caller all-reduces the float64 images)
     cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
     size_t host_ng = 0;                  // gradient doubles of the host evaluation in flight (host_enqueue -> host_collect)
     bool host_delivered = false;  // the last backward pass wrote its results into the mapped host buffer itself
@@ -281,13 +284,21 @@ int splat_images(eincm_plan* plan, const ThetaSrc& T, const double2* theta_full,
         }
         return EINCM_OK;
     }
-    if (!plan->fix_clean) CU(cudaMemsetAsync(plan->iwe_fix, 0, (size_t)plan->max_refs * plan->HW * sizeof(unsigned long long), st));
+    if (plan->n_peers > 0) {
+        // peers add into this rank's image: it must be clean BEFORE the cross-rank barrier that precedes the splat
+        if (!plan->fix_clean) return fail(plan, EINCM_ESTATE, "event split with peer access: call eincm_split_prepare (+ barrier) before the splat");
+    } else if (!plan->fix_clean) {
+        CU(cudaMemsetAsync(plan->iwe_fix, 0, (size_t)plan->max_refs * plan->HW * sizeof(unsigned long long), st));
+    }
     plan->fix_clean = false;
     if (n > 0) {
         const int grid = std::max(1, plan->n_chunks);
         int4* cw = record_windows ? plan->chunk_win : nullptr;
+        FixDst dst{};
+        if (plan->n_peers > 0) { dst.n = plan->n_peers; for (int q = 0; q < dst.n; ++q) dst.p[q] = plan->peer_fix[q]; }
+        else { dst.n = 1; dst.p[0] = plan->iwe_fix; }
 #define SPLATT(WR, RB) LAUNCH(tag, k_splat_tile<WR, RB><<<grid, 256, RB * kWinCap * sizeof(uint32_t), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
-                               plan->totals + 1, T, H, W, n_img, tref, plan->iwe_fix, cw))
+                               plan->totals + 1, T, H, W, n_img, tref, dst, cw))
 #define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
                                                              case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
         if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
@@ -328,7 +339,8 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
         if ((rc = ensure_theta_full(plan, st))) return rc;
     }
     // default path (single GPU, delta == 0): the fixed-point images are consumed by the fused image pass directly
-    plan->fused_pending = !plan->exact && plan->coop_ok && !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && hp->delta == 0.0;
+    // single GPU, or event split with peer access (every rank then holds the complete fixed-point images after the barrier)
+    plan->fused_pending = !plan->exact && plan->coop_ok && (!(plan->flags & EINCM_FLAG_EVENT_SPLIT) || plan->n_peers > 0) && hp->delta == 0.0;
     if ((rc = splat_images(plan, plan->tsrc, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
     plan->forward_done = true;
@@ -591,6 +603,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     for (auto& kv : plan->taps_cache) if (kv.second.blob) cudaFree(kv.second.blob);
     for (auto& sp : plan->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& e : plan->event_pool) cudaEventDestroy(e);
+    for (void* q : plan->peer_opened) if (q) cudaIpcCloseMemHandle(q);
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     if (plan->h_pinned) cudaFreeHost(plan->h_pinned);
     if (plan->h_flag) cudaFreeHost(plan->h_flag);
@@ -664,7 +677,9 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     // zero-warp IWE (losses.py:54): theta = 0 => x' = x for every reference time
     {
         RefTimes z{};
-        int rc = splat_images(plan, ThetaSrc{}, nullptr, 1, z, plan->zero_iwe, "k_splat(zero)", st);
+        // event split with peer access: every rank votes into every rank's image; the float64 copy is taken after the
+        // cross-rank barrier (eincm_split_window_images)
+        int rc = splat_images(plan, ThetaSrc{}, nullptr, 1, z, plan->zero_iwe, "k_splat(zero)", st, plan->n_peers == 0);
         if (rc) return rc;
     }
     // validate (the reference's loaders guarantee in-sensor events; a violation would corrupt the gather at
@@ -903,6 +918,76 @@ int eincm_plan_set_event_split(eincm_plan* plan, int rank, int world) {
     if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return fail(plan, EINCM_ESTATE, "plan was not created with EINCM_FLAG_EVENT_SPLIT");
     if (world < 1 || rank < 0 || rank >= world) return fail(plan, EINCM_EINVAL, "rank %d outside 0..%d", rank, world - 1);
     plan->split_rank = rank; plan->split_world = world;
+    return EINCM_OK;
+}
+
+int eincm_plan_ipc_handle(eincm_plan* plan, void* handle_out, int handle_bytes) {
+    if (!plan || !handle_out) return EINCM_EINVAL;
+    if (plan->exact || !plan->iwe_fix) return fail(plan, EINCM_ESTATE, "peer access needs the default (fixed-point) path");
+    if (handle_bytes < (int)sizeof(cudaIpcMemHandle_t)) return fail(plan, EINCM_EINVAL, "handle_out needs %d bytes", (int)sizeof(cudaIpcMemHandle_t));
+    CU(cudaSetDevice(plan->device));
+    cudaIpcMemHandle_t hnd;
+    CU(cudaIpcGetMemHandle(&hnd, plan->iwe_fix));
+    std::memcpy(handle_out, &hnd, sizeof hnd);
+    return EINCM_OK;
+}
+
+namespace {
+int check_split_peers(eincm_plan* plan, int n) {
+    if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return fail(plan, EINCM_ESTATE, "plan was not created with EINCM_FLAG_EVENT_SPLIT");
+    if (plan->exact || !plan->iwe_fix) return fail(plan, EINCM_ESTATE, "peer access needs the default (fixed-point) path");
+    if (n != plan->split_world || n < 1 || n > kMaxPeers)
+        return fail(plan, EINCM_EINVAL, "expected one entry per rank of the split (%d, at most %d), got %d", plan->split_world, kMaxPeers, n);
+    return EINCM_OK;
+}
+}  // namespace
+
+int eincm_plan_set_peers(eincm_plan* plan, const void* handles, int n_handles) {
+    if (!plan || !handles) return EINCM_EINVAL;
+    int rc = check_split_peers(plan, n_handles);
+    if (rc) return rc;
+    CU(cudaSetDevice(plan->device));
+    for (int q = 0; q < n_handles; ++q) {
+        if (q == plan->split_rank) { plan->peer_fix[q] = plan->iwe_fix; continue; }
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, (const char*)handles + (size_t)q * sizeof hnd, sizeof hnd);
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+        plan->peer_opened[q] = ptr;
+        plan->peer_fix[q] = (unsigned long long*)ptr;
+    }
+    plan->n_peers = n_handles;
+    return EINCM_OK;
+}
+
+int eincm_plan_set_peer_pointers(eincm_plan* plan, void* const* fix_ptrs, int n_ptrs) {
+    if (!plan || !fix_ptrs) return EINCM_EINVAL;
+    int rc = check_split_peers(plan, n_ptrs);
+    if (rc) return rc;
+    for (int q = 0; q < n_ptrs; ++q) plan->peer_fix[q] = (q == plan->split_rank) ? plan->iwe_fix : (unsigned long long*)fix_ptrs[q];
+    plan->n_peers = n_ptrs;
+    return EINCM_OK;
+}
+
+void* eincm_iwe_fix_ptr(eincm_plan* plan) { return plan ? (void*)plan->iwe_fix : nullptr; }
+
+int eincm_split_prepare(eincm_plan* plan, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (plan->n_peers == 0 || plan->fix_clean) return EINCM_OK;
+    CU(cudaSetDevice(plan->device));
+    CU(cudaMemsetAsync(plan->iwe_fix, 0, (size_t)plan->max_refs * plan->HW * sizeof(unsigned long long), (cudaStream_t)cuda_stream));
+    plan->fix_clean = true;
+    return EINCM_OK;
+}
+
+int eincm_split_window_images(eincm_plan* plan, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!plan->window_set) return fail(plan, EINCM_ESTATE, "eincm_split_window_images before set_window");
+    if (plan->n_peers == 0) return EINCM_OK;
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // after the barrier: this rank's fixed-point image 0 holds the complete zero-warp image of the window
+    LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((plan->HW + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, plan->HW, plan->zero_iwe));
     return EINCM_OK;
 }
 

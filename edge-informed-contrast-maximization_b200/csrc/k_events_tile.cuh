@@ -173,6 +173,13 @@ __device__ __forceinline__ double2 event_theta(const double2* __restrict__ th_s,
     return th_s[((xy >> 12) & 0xf0u) | (xy & 0xfu)];         // (y & 15) * 16 + (x & 15)
 }
 
+// Destination images of the flush.  Single GPU: the plan's own fixed-point image.  Event split with peer access: the images
+// of ALL ranks of the split (own + peers' device pointers opened through CUDA IPC) - every rank adds its non-zero window
+// cells to every rank's image with 64-bit integer reductions over NVLink, so the "all-reduce of the partial images" is fused
+// into the splat: integer sums are order-independent, every rank ends up with the identical complete image.
+constexpr int kMaxPeers = 8;
+struct FixDst { unsigned long long* p[kMaxPeers]; int n; };
+
 // ---- forward -----------------------------------------------------------------------------------------------------
 // One CTA per chunk (grid-stride), RB reference times per pass with one window each.  Per pass: zero the windows, measure
 // the bounding rectangles (float32 pre-pass), vote, flush.  A thread walks its kEvK consecutive events per reference time and
@@ -183,7 +190,7 @@ template <bool WRAP, int RB>
 __global__ void __launch_bounds__(256, 4)
 k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
              const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
-             unsigned long long* __restrict__ iwe_fix /* [R][H*W] */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
+             const __grid_constant__ FixDst dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
     extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ int sbox[8][RB][4];
@@ -277,13 +284,15 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                         acc_addr = addr;
                     } else {
                         // outside the window: per-tap global reductions with the reference's index rule
-                        unsigned long long* img = iwe_fix + (int64_t)(r0 + r) * HW;
 #pragma unroll
                         for (int j = 0; j < 3; ++j)
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
                                 int rr = h.ry + j - 1, cc = h.rx + i - 1;
-                                if (drop_index<WRAP>(rr, cc, H, W)) atomicAdd(img + (int64_t)rr * W + cc, (unsigned long long)t.n[j * 3 + i]);
+                                if (drop_index<WRAP>(rr, cc, H, W)) {
+                                    const int64_t off = (int64_t)(r0 + r) * HW + (int64_t)rr * W + cc;
+                                    for (int q = 0; q < dst.n; ++q) atomicAdd(dst.p[q] + off, (unsigned long long)t.n[j * 3 + i]);
+                                }
                             }
                     }
                 }
@@ -296,7 +305,7 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                 if (r0 + r >= R) continue;
                 const Window wn = swin[r];
                 const uint32_t* wr = win + r * kWinCap;
-                unsigned long long* img = iwe_fix + (int64_t)(r0 + r) * HW;
+                const int64_t img_off = (int64_t)(r0 + r) * HW;
                 const int cells = wn.pw * wn.ph;
                 const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
                 for (int i = tid; i < cells; i += 256) {
@@ -305,7 +314,10 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                         int row, col;
                         cell_to_rc(wn, i, row, col);
                         int rr = wn.oy + row, cc = wn.ox + col;
-                        if (interior || drop_index<WRAP>(rr, cc, H, W)) atomicAdd(img + (rr * W + cc), (unsigned long long)v);
+                        if (interior || drop_index<WRAP>(rr, cc, H, W)) {
+                            const int64_t off = img_off + (rr * W + cc);
+                            for (int q = 0; q < dst.n; ++q) atomicAdd(dst.p[q] + off, (unsigned long long)v);
+                        }
                     }
                 }
             }

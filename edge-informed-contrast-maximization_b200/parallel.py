@@ -55,9 +55,15 @@ class EventSplitObjective:
 
     ``plan`` is an ``eincm_b200.plan.Plan`` created with ``FLAG_EVENT_SPLIT`` (or any object with the same split-phase
     methods - the CPU tests drive this class with an oracle-backed stand-in over gloo).  Every rank passes ITS events to
-    ``set_datasample``; ``value_and_grad`` returns the same ``(loss, grad)`` on every rank."""
+    ``set_datasample``; ``value_and_grad`` returns the same ``(loss, grad)`` on every rank.
 
-    def __init__(self, plan, make_hparams: Callable, group=None, rank: Optional[int] = None, world: Optional[int] = None):
+    ``p2p=True`` (GPUs of one NVLink domain, NCCL group): the ranks exchange the CUDA IPC handles of their fixed-point image
+    buffers once, and from then on every splat adds its votes to the images of ALL ranks over NVLink - the all-reduce of the
+    ``R*H*W`` images is fused into the splat kernel (``include/eincm.h``); the only collectives left per evaluation are two
+    one-element barriers and the all-reduce of the small flow gradient."""
+
+    def __init__(self, plan, make_hparams: Callable, group=None, rank: Optional[int] = None, world: Optional[int] = None,
+                 p2p: bool = False):
         import torch.distributed as dist
         self.dist = dist
         self.plan = plan
@@ -68,6 +74,12 @@ class EventSplitObjective:
         plan.set_event_split(self.rank, self.world)
         self.n_collectives = 0
         self.collective_bytes = 0
+        self.p2p = bool(p2p)
+        self._token = None
+        if self.p2p:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, plan.ipc_handle(), group=group)
+            plan.set_peers(handles)
 
     def _allreduce(self, t, op=None):
         op = self.dist.ReduceOp.SUM if op is None else op
@@ -76,9 +88,23 @@ class EventSplitObjective:
         self.n_collectives += 1
         self.collective_bytes += t.numel() * t.element_size()
 
+    def _barrier(self):
+        """Stream-ordered cross-rank barrier: a one-element all-reduce on the current stream."""
+        import torch
+        if self._token is None:
+            self._token = torch.zeros(1, dtype=torch.float32, device=f'cuda:{self.plan.device}')
+        self._allreduce(self._token)
+
     def set_datasample(self, xs_local, ys_local, ts_local, edges, edge_ts, need_mask: bool = True):
-        self.plan.set_window(xs_local, ys_local, ts_local, edges, edge_ts)
-        self._allreduce(self.plan.zero_iwe())                            # sum of the partial un-warped images
+        if self.p2p:
+            self.plan.split_prepare()
+            self._barrier()                                              # every rank's image buffer is clean
+            self.plan.set_window(xs_local, ys_local, ts_local, edges, edge_ts)   # votes of the zero-warp image go to all ranks
+            self._barrier()                                              # all votes have landed
+            self.plan.split_window_images()
+        else:
+            self.plan.set_window(xs_local, ys_local, ts_local, edges, edge_ts)
+            self._allreduce(self.plan.zero_iwe())                        # sum of the partial un-warped images
         if need_mask:
             self._allreduce(self.plan.event_mask(), self.dist.ReduceOp.MAX)   # union of the per-rank event masks (TV only)
         self.plan.window_finalize()
@@ -91,8 +117,14 @@ class EventSplitObjective:
             loss_out = torch.zeros(1, dtype=torch.float64, device=theta.device)
         if grad_out is None:
             grad_out = torch.zeros_like(theta)
-        self.plan.forward_events(theta, hp)
-        self._allreduce(self.plan.iwe())                                 # C1: partial images of warped events
+        if self.p2p:
+            self.plan.split_prepare()
+            self._barrier()                                              # nobody still reads / clears the image buffers
+            self.plan.forward_events(theta, hp)                          # splat fused with the all-reduce (NVLink reductions)
+            self._barrier()                                              # all votes have landed: images complete everywhere
+        else:
+            self.plan.forward_events(theta, hp)
+            self._allreduce(self.plan.iwe())                             # C1: partial images of warped events
         self.plan.backward(hp, loss_out, grad_out)
         self._allreduce(grad_out)                                        # C2: partial flow-parameter gradients
         return loss_out, grad_out

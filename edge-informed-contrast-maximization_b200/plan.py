@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     'eincm_forward_events', 'eincm_backward', 'eincm_zero_iwe_ptr', 'eincm_iwe_ptr', 'eincm_dldi_ptr',
     'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
+    'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
+    'eincm_split_window_images',
 )
 
 
@@ -92,6 +94,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_get_scalars': (i32, [vp, C.POINTER(dbl), i32, vp]),
         'eincm_debug_rounded_pixels': (i32, [vp, i32, vp, vp, vp]),
         'eincm_plan_set_event_split': (i32, [vp, i32, i32]),
+        'eincm_plan_ipc_handle': (i32, [vp, vp, i32]),
+        'eincm_plan_set_peers': (i32, [vp, vp, i32]),
+        'eincm_plan_set_peer_pointers': (i32, [vp, C.POINTER(vp), i32]),
+        'eincm_iwe_fix_ptr': (vp, [vp]),
+        'eincm_split_prepare': (i32, [vp, vp]),
+        'eincm_split_window_images': (i32, [vp, vp]),
         'eincm_plan_launch_count': (i64, [vp]),
         'eincm_plan_set_timing': (i32, [vp, i32]),
         'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
@@ -216,6 +224,30 @@ class Plan:
 
     def set_event_split(self, rank: int, world: int):
         self._check(self.lib.eincm_plan_set_event_split(self._h, int(rank), int(world)))
+
+    # -- event split with peer access (fused splat + all-reduce over NVLink) ---------------------------------------
+    IPC_HANDLE_BYTES = 64
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        self._check(self.lib.eincm_plan_ipc_handle(self._h, buf, self.IPC_HANDLE_BYTES))
+        return buf.raw
+
+    def set_peers(self, handles: Sequence[bytes]):
+        """``handles``: the ``ipc_handle()`` of every rank of the split, in rank order (this rank's own entry is ignored)."""
+        blob = b''.join(handles)
+        self._check(self.lib.eincm_plan_set_peers(self._h, blob, len(handles)))
+
+    def set_peer_pointers(self, plans: Sequence['Plan']):
+        """In-process form: the plans of all ranks of the split live in this process (same device or peer-accessible)."""
+        ptrs = (C.c_void_p * len(plans))(*[p.lib.eincm_iwe_fix_ptr(p._h) for p in plans])
+        self._check(self.lib.eincm_plan_set_peer_pointers(self._h, ptrs, len(plans)))
+
+    def split_prepare(self, stream=None):
+        self._check(self.lib.eincm_split_prepare(self._h, _stream_ptr(stream)))
+
+    def split_window_images(self, stream=None):
+        self._check(self.lib.eincm_split_window_images(self._h, _stream_ptr(stream)))
 
     def window_finalize(self, stream=None):
         self._check(self.lib.eincm_window_finalize(self._h, _stream_ptr(stream)))

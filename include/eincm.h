@@ -151,6 +151,24 @@ int eincm_window_finalize(eincm_plan* plan, void* cuda_stream);
 int eincm_plan_set_event_split(eincm_plan* plan, int rank, int world);
 int eincm_forward_events(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, void* cuda_stream);
 int eincm_backward(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, void* cuda_stream);
+/* ---- event split with peer access: the all-reduce of the partial images fused into the splat --------------------
+ * One process per GPU of one NVLink / NVSwitch domain.  Every rank publishes the CUDA IPC handle of its fixed-point image
+ * buffer (eincm_plan_ipc_handle, 64 bytes), the caller exchanges the handles (torch.distributed all-gather) and hands all of
+ * them, in rank order, to eincm_plan_set_peers (after eincm_plan_set_event_split).  From then on the splat adds the non-zero
+ * cells of its shared-memory windows to the image of EVERY rank with 64-bit integer reductions over NVLink: integer sums are
+ * order-independent, so after a cross-rank barrier every rank holds the identical complete images and runs the (fused) image
+ * pass on them - no all-reduce of the R*H*W images, and the objective is bit-identical on all ranks.  Sequence per rank:
+ *   eincm_split_prepare  -> barrier -> set_window (local events) -> barrier -> eincm_split_window_images -> eincm_window_finalize
+ *   eincm_split_prepare  -> barrier -> eincm_forward_events      -> barrier -> eincm_backward -> all-reduce(sum) of grad_out
+ * (eincm_split_prepare clears this rank's image buffer when it is not clean already; the barrier before the splat guarantees
+ * that no rank adds into a buffer that is still being read or cleared - the gradient all-reduce of the previous evaluation can
+ * serve as that barrier.)  eincm_plan_set_peer_pointers is the in-process form (plans of one process, e.g. tests). */
+int eincm_plan_ipc_handle(eincm_plan* plan, void* handle_out, int handle_bytes);
+int eincm_plan_set_peers(eincm_plan* plan, const void* handles /* [world][64] */, int n_handles);
+int eincm_plan_set_peer_pointers(eincm_plan* plan, void* const* fix_ptrs /* [world], eincm_iwe_fix_ptr of every rank */, int n_ptrs);
+void* eincm_iwe_fix_ptr(eincm_plan* plan);       /* device, [max_refs*H*W] uint64 fixed-point images (2^21 * 2 pi * value) */
+int eincm_split_prepare(eincm_plan* plan, void* cuda_stream);
+int eincm_split_window_images(eincm_plan* plan, void* cuda_stream);
 double* eincm_zero_iwe_ptr(eincm_plan* plan);   /* device, [H*W] float64 */
 double* eincm_iwe_ptr(eincm_plan* plan);        /* device, [R*H*W] float64, image of warped events of the last evaluation */
 /* device, [H*W] uint8: 1 where a pixel holds >= 1 (local) event (theta_utils.py:66-71); event-split plans that use
