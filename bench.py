@@ -472,7 +472,69 @@ def run_own(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------------------
+# event split of ONE large window over the GPUs (BASELINE.json configs[4]); not the driver's default line
+# --------------------------------------------------------------------------------------------------------------
+def run_event_split(args):
+    import torch
+    import torch.distributed as dist
+    from eincm_b200 import parallel as PAR, plan as P, synth
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if world > 1:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        else:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29533')
+            dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', local_rank))
+        t = torch.zeros(1, device='cuda'); dist.all_reduce(t); torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    win = synth.make_workload(args.workload, seed=0, n_events=args.events)      # the same window on every rank
+    H, W = win.sensor_size
+    N, R = len(win.xs), len(win.edge_ts)
+    xs, ys, ts = PAR.split_events(win.xs, win.ys, win.ts, world, rank)
+    hpd = win.hparams
+    shape = (args.theta, args.theta)
+    theta = torch.from_numpy(synth.theta_test_points(win, shape)['perturbed']).cuda()
+    res = {}
+    for mode, p2p in (('nccl_allreduce_of_images', False), ('peer_fused_splat', True)):
+        plan = P.Plan((H, W), max_events=len(xs), max_refs=max(R, 3), flags=P.FLAG_EVENT_SPLIT)
+        obj = PAR.EventSplitObjective(plan, lambda lvl: P.make_hparams(hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], lvl), p2p=p2p)
+        obj.set_datasample(xs, ys, ts, win.edges, win.edge_ts, need_mask=False)
+        loss = torch.zeros(1, dtype=torch.float64, device='cuda'); grad = torch.zeros_like(theta)
+        for _ in range(args.warmup):
+            obj.value_and_grad(theta, 0, loss, grad)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = obj.collective_bytes
+        e0.record()
+        for _ in range(args.steps):
+            obj.value_and_grad(theta, 0, loss, grad)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item()) / args.steps
+        res[mode] = {'value': N / (ms * 1e-3) / 1e9, 'unit': UNIT, 'ms_per_eval': ms,
+                     'collective_bytes_per_eval_per_rank': (obj.collective_bytes - c0) // args.steps, 'loss': float(loss.item())}
+        plan.close()
+    if rank == 0:
+        print(json.dumps({'mode': 'event_split', 'metric': METRIC, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                          'config': {'workload': f'{args.workload}: ONE window of {W}x{H}, N={N} events split over {world} GPU(s), R={R}, '
+                                                 f'theta {shape[0]}x{shape[1]}x2'}, 'scaling': 'strong', **res}))
+    dist.destroy_process_group()
+
+
 def main():
+    # NCCL's version banner goes to (buffered) stdout; rank 0 must print ONE JSON line
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=40)
@@ -485,8 +547,12 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU work for the CPU baseline / reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--solve-windows', type=int, default=2, help='complete multi-level solves per GPU for the windows/s figure (0: skip)')
+    ap.add_argument('--event-split', action='store_true', help='ONE window split over the GPUs (configs[4]) instead of windows sharded')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.event_split:
+        run_event_split(args)
+        return
     if args.impl == 'reference':
         args.cpu_budget = max(args.cpu_budget, 60.0)
         run_reference(args)
