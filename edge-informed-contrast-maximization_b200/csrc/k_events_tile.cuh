@@ -133,7 +133,7 @@ __device__ __forceinline__ Window make_window(int mnx, int mny, int mxx, int mxy
         if (bw > kWinCap / bh) bw = kWinCap / bh;
     }
     w.ox = mnx - 1; w.oy = mny - 1; w.pw = (int)bw; w.ph = (int)bh;
-    w.inv_pw = (uint32_t)((0x100000000ull + (unsigned long long)bw - 1ull) / (unsigned long long)bw);
+    w.inv_pw = 0xffffffffu / (uint32_t)bw + 1u;              // ceil(2^32 / pw): exact cell -> row for cells < 2^16
     return w;
 }
 
@@ -179,6 +179,30 @@ __device__ __forceinline__ double2 event_theta(const double2* __restrict__ th_s,
 // into the splat: integer sums are order-independent, every rank ends up with the identical complete image.
 constexpr int kMaxPeers = 8;
 struct FixDst { unsigned long long* p[kMaxPeers]; int n; };
+
+// cold path of the splat: an event whose patch leaves its window adds its taps to the global images one by one, with the
+// reference's index rule (out of line: keeps the hot loop small - the kernel was instruction-cache bound with it inlined)
+template <bool WRAP>
+__device__ __noinline__ void splat_fallback(const FixDst& dst, int64_t img_off, int rx, int ry, const TapsFix& t, int H, int W) {
+    for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) {
+            int rr = ry + j - 1, cc = rx + i - 1;
+            if (drop_index<WRAP>(rr, cc, H, W)) {
+                const int64_t off = img_off + (int64_t)rr * W + cc;
+#pragma unroll 1
+                for (int q = 0; q < dst.n; ++q) atomicAdd(dst.p[q] + off, (unsigned long long)t.n[j * 3 + i]);
+            }
+        }
+}
+
+template <bool WRAP>
+__device__ __noinline__ void gather_fallback(const float* __restrict__ img, int rx, int ry, int H, int W, float (&d)[9]) {
+    for (int j = -1; j <= 1; ++j)
+        for (int i = -1; i <= 1; ++i) {
+            int rr = ry + j, cc = rx + i;
+            d[(j + 1) * 3 + (i + 1)] = drop_index<WRAP>(rr, cc, H, W) ? __ldg(img + (int64_t)rr * W + cc) : 0.f;
+        }
+}
 
 // ---- forward -----------------------------------------------------------------------------------------------------
 // One CTA per chunk (grid-stride), RB reference times per pass with one window each.  Per pass: zero the windows, measure
@@ -283,17 +307,7 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                         for (int q = 0; q < 9; ++q) acc[q] = t.n[q] + (same ? acc[q] : 0);
                         acc_addr = addr;
                     } else {
-                        // outside the window: per-tap global reductions with the reference's index rule
-#pragma unroll
-                        for (int j = 0; j < 3; ++j)
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                int rr = h.ry + j - 1, cc = h.rx + i - 1;
-                                if (drop_index<WRAP>(rr, cc, H, W)) {
-                                    const int64_t off = (int64_t)(r0 + r) * HW + (int64_t)rr * W + cc;
-                                    for (int q = 0; q < dst.n; ++q) atomicAdd(dst.p[q] + off, (unsigned long long)t.n[j * 3 + i]);
-                                }
-                            }
+                        splat_fallback<WRAP>(dst, (int64_t)(r0 + r) * HW, h.rx, h.ry, t, H, W);
                     }
                 }
                 if (acc_addr != 0u) emit9(acc_addr, pitch4, acc);
@@ -316,6 +330,7 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                         int rr = wn.oy + row, cc = wn.ox + col;
                         if (interior || drop_index<WRAP>(rr, cc, H, W)) {
                             const int64_t off = img_off + (rr * W + cc);
+#pragma unroll 1
                             for (int q = 0; q < dst.n; ++q) atomicAdd(dst.p[q] + off, (unsigned long long)v);
                         }
                     }
@@ -359,7 +374,7 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
             if (tid < RB && r0 + tid < R) {
                 const int4 q = chunk_win[(int64_t)c * R + r0 + tid];
                 Window wn{q.x, q.y, q.z, q.w, 0u};
-                if (q.z > 0) wn.inv_pw = (uint32_t)((0x100000000ull + (unsigned long long)q.z - 1ull) / (unsigned long long)q.z);
+                if (q.z > 0) wn.inv_pw = 0xffffffffu / (uint32_t)q.z + 1u;
                 swin[tid] = wn;
             }
             __syncthreads();
@@ -371,11 +386,21 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
                 float* wr = dwin + r * kWinCap;
                 const int cells = wn.pw * wn.ph;
                 const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
-                for (int i = tid; i < cells; i += 256) {
-                    int row, col;
-                    cell_to_rc(wn, i, row, col);
-                    int rr = wn.oy + row, cc = wn.ox + col;
-                    wr[i] = (interior || drop_index<WRAP>(rr, cc, H, W)) ? __ldg(img + (rr * W + cc)) : 0.f;
+                for (int i0 = tid; i0 < cells; i0 += 4 * 256) {       // all global loads of a round first, then the stores
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * 256;
+                        int row, col;
+                        cell_to_rc(wn, min(i, cells - 1), row, col);
+                        int rr = wn.oy + row, cc = wn.ox + col;
+                        v[u] = (i < cells && (interior || drop_index<WRAP>(rr, cc, H, W))) ? __ldg(img + (rr * W + cc)) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * 256;
+                        if (i < cells) wr[i] = v[u];
+                    }
                 }
             }
             __syncthreads();
@@ -401,14 +426,7 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
 #pragma unroll
                             for (int i = -1; i <= 1; ++i) d[(j + 1) * 3 + (i + 1)] = p[j * wn.pw + i];
                     } else {
-                        const float* img = dldi32 + (int64_t)(r0 + r) * HW;
-#pragma unroll
-                        for (int j = -1; j <= 1; ++j)
-#pragma unroll
-                            for (int i = -1; i <= 1; ++i) {
-                                int rr = h.ry + j, cc = h.rx + i;
-                                d[(j + 1) * 3 + (i + 1)] = drop_index<WRAP>(rr, cc, H, W) ? __ldg(img + (int64_t)rr * W + cc) : 0.f;
-                            }
+                        gather_fallback<WRAP>(dldi32 + (int64_t)(r0 + r) * HW, h.rx, h.ry, H, W, d);
                     }
                     // separable evaluation: wx_i = exp(-0.5 (i - fx)^2), s_j = sum_i D_ij wx_i, sx_j = sum_i D_ij wx_i (i - fx)
                     //   dL/dx' = sum_j wy_j sx_j,   dL/dy' = sum_j wy_j (j - fy) s_j        (D already carries 1/(2 pi))
