@@ -365,25 +365,51 @@ def run_own(args):
     solve = None
     if args.solve_windows > 0:
         from eincm_b200 import losses, solver as SV
-        obj = losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3))
-        sol = SV.MultipleLevelEINCMSolver(obj)
-        sol.set_datasample(*wins[0].args())
-        sol.solve()                                    # warm-up solve (first sample: no handover)
-        barrier()
-        n0 = obj.n_evals
-        t0 = time.perf_counter()
-        for k in range(args.solve_windows):
-            sol.set_datasample(*wins[(k + 1) % nw].args())
-            res = sol.solve()
-        solve_s = max_over_ranks(time.perf_counter() - t0)
-        n_ev = obj.n_evals - n0
-        solve = {'value': world * args.solve_windows / solve_s, 'unit': 'windows/s', 'windows_per_gpu': args.solve_windows,
-                 'ms_per_window': solve_s / args.solve_windows * 1e3, 'evals_per_window': n_ev / args.solve_windows,
-                 'final_loss': res['theta_opt_state_pyr']['pyr_lvl_0'].fun_val,
-                 'note': 'eincm_b200.solver.MultipleLevelEINCMSolver (mirror of reference src/eincm/solver.py, main.yaml defaults), '
-                         'scipy BFGS / L-BFGS-B on the host, set_datasample (staging) inside the timed region, windows of a rank '
-                         'chained by handover'}
-        obj.close()
+
+        def run_solves(backend, n_threads):
+            """n_threads independent sequences per GPU, each: warm-up solve, then args.solve_windows chained windows."""
+            objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3))
+                    for _ in range(n_threads)]
+            sols = [SV.MultipleLevelEINCMSolver(o, backend=backend, own_stream=(backend == 'native')) for o in objs]
+            for t, sol in enumerate(sols):
+                sol.set_datasample(*wins[t % nw].args())
+                sol.solve()                            # warm-up solve (first sample: no handover)
+            finals = [None] * n_threads
+
+            def work(t):
+                torch.cuda.set_device(local_rank)
+                for k in range(args.solve_windows):
+                    sols[t].set_datasample(*wins[(t + k + 1) % nw].args())
+                    finals[t] = sols[t].solve()
+
+            barrier()
+            n0 = sum(o.n_evals for o in objs)
+            t0 = time.perf_counter()
+            if n_threads == 1:
+                work(0)
+            else:
+                ths = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+                for th in ths:
+                    th.start()
+                for th in ths:
+                    th.join()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            n_win = n_threads * args.solve_windows
+            n_ev = sum(o.n_evals for o in objs) - n0
+            res = {'value': world * n_win / dt, 'unit': 'windows/s', 'sequences_per_gpu': n_threads, 'windows_per_sequence': args.solve_windows,
+                   'ms_per_window': dt / args.solve_windows * 1e3, 'evals_per_window': n_ev / n_win,
+                   'final_loss': finals[0]['theta_opt_state_pyr']['pyr_lvl_0'].fun_val}
+            for o in objs:
+                o.close()
+            return res
+
+        solve = run_solves('native', min(4, nw))
+        solve['note'] = ('eincm_b200.solver.MultipleLevelEINCMSolver (mirror of reference src/eincm/solver.py, main.yaml defaults: 5 levels, '
+                         'BFGS 40/28/19/11/8 iterations, retries, handover solved at levels 1/0); optimizers native '
+                         '(eincm_minimize_bfgs_host / eincm_minimize_handover_host), one host thread and one CUDA stream per '
+                         'sequence, windows of a sequence chained by handover, set_datasample (staging) inside the timed region')
+        solve['scipy_single_sequence'] = run_solves('scipy', 1)
 
     # ---- stateless: stage the whole window from pinned host memory every step ---------------------------------
     pin = []

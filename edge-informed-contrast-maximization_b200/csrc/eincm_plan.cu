@@ -22,6 +22,7 @@
 #include "k_events_tile.cuh"
 #include "k_image.cuh"
 #include "k_image_fused.cuh"
+#include "eincm_opt.h"
 
 using namespace eincm;
 
@@ -787,6 +788,57 @@ int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h,
     const int rc = host_enqueue(plan, theta_host, h, w, hp, grad_out_host != nullptr, st);
     if (rc) return rc;
     return host_collect(plan, loss_out_host, grad_out_host, st);
+}
+
+int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
+                             eincm_opt_result* result_out, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!theta_inout_host || !result_out) return fail(plan, EINCM_EINVAL, "NULL operand");
+    if (maxiter < 0) return fail(plan, EINCM_EINVAL, "maxiter must be >= 0");
+    cudaStream_t st = cuda_stream == (void*)(intptr_t)-1 ? plan->own_stream : (cudaStream_t)cuda_stream;
+    const int n = h * w * 2;
+    eincm_opt::Objective fun = [&](const double* x, double* f, double* g) -> int {
+        const int rc = host_enqueue(plan, x, h, w, hp, true, st);
+        if (rc) return rc;
+        return host_collect(plan, f, g, st);
+    };
+    int err = 0;
+    const eincm_opt::Result r = eincm_opt::bfgs(fun, n, theta_inout_host, maxiter, gtol, &err);
+    if (err) return err;
+    result_out->fun = r.fun; result_out->nit = r.nit; result_out->nfev = r.nfev; result_out->status = r.status; result_out->reserved = 0;
+    return EINCM_OK;
+}
+
+int eincm_minimize_handover_host(eincm_plan* plan, double* alpha_inout_host, double lo, double hi, const double* prev_theta_host,
+                                 const double* theta_host, int h, int w, const eincm_hparams* hp, int maxiter, double pgtol,
+                                 eincm_opt_result* result_out, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!alpha_inout_host || !prev_theta_host || !theta_host || !result_out) return fail(plan, EINCM_EINVAL, "NULL operand");
+    if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    if (!(lo <= hi)) return fail(plan, EINCM_EINVAL, "empty interval [%g, %g]", lo, hi);
+    if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "event-split plans use the split-phase calls");
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = cuda_stream == (void*)(intptr_t)-1 ? plan->own_stream : (cudaStream_t)cuda_stream;
+    const size_t nb = (size_t)h * w * 2 * sizeof(double);
+    // the two flow fields are constant during the solve: stage them once (pageable sources: the copies are synchronous)
+    CU(cudaMemcpyAsync(plan->theta_stage, theta_host, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(plan->prev_stage, prev_theta_host, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    double* h_out = plan->h_pinned + (size_t)plan->HW * 2;
+    eincm_opt::Objective fun = [&](const double* a, double* f, double* g) -> int {
+        const int rc = eincm_handover_value_and_grad(plan, *a, plan->prev_stage, plan->theta_stage, h, w, hp, plan->out_stage, plan->out_stage + 1, st);
+        if (rc) return rc;
+        if (cudaMemcpyAsync(h_out, plan->out_stage, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            return fail(plan, EINCM_ECUDA, "copy of the handover result failed");
+        *f = h_out[0]; *g = h_out[1];
+        return EINCM_OK;
+    };
+    int err = 0;
+    const eincm_opt::Result r = eincm_opt::bounded_scalar(fun, alpha_inout_host, lo, hi, maxiter, pgtol, 1e7, &err);
+    if (err) return err;
+    result_out->fun = r.fun; result_out->nit = r.nit; result_out->nfev = r.nfev; result_out->status = r.status; result_out->reserved = 0;
+    return EINCM_OK;
 }
 
 int eincm_value_and_grad_host_batch(eincm_plan* const* plans, int n_plans, const double* const* thetas_host, int h, int w,

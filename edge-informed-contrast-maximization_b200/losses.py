@@ -238,5 +238,17 @@ class WindowObjective:
 
         return fun
 
+    # native optimizers (eincm_minimize_*_host): the BFGS / bounded loops run inside the library
+    def minimize_bfgs(self, theta0, cur_pyr_lvl: int, maxiter: int, gtol: float, own_stream: bool = False):
+        theta, res = self.plan.minimize_bfgs_host(_as_theta(theta0), self.hparams(cur_pyr_lvl), maxiter, gtol, own_stream=own_stream)
+        self.n_evals += int(res.nfev)
+        return theta, res
+
+    def minimize_handover(self, alpha0, bounds, prev_theta, theta, cur_pyr_lvl: int, maxiter: int, pgtol: float, own_stream: bool = False):
+        a, res = self.plan.minimize_handover_host(alpha0, bounds, _as_theta(prev_theta), _as_theta(theta), self.hparams(cur_pyr_lvl),
+                                                  maxiter, pgtol, own_stream=own_stream)
+        self.n_evals += int(res.nfev)
+        return a, res
+
     def close(self):
         self.plan.close()

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = (
     'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
     'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
-    'eincm_split_window_images',
+    'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host',
 )
 
 
@@ -41,6 +41,14 @@ class EincmError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f'eincm error {code}: {message}')
         self.code = code
+
+
+class OptResult(C.Structure):
+    """``eincm_opt_result``: what ``jaxopt`` reports as ``state.fun_val / iter_num / status`` (reference src/eincm/solver.py:379-384)."""
+    _fields_ = [('fun', C.c_double), ('nit', C.c_int32), ('nfev', C.c_int32), ('status', C.c_int32), ('reserved', C.c_int32)]
+
+
+OWN_STREAM = C.c_void_p(-1)     # stream argument selecting the plan's own stream
 
 
 class HParams(C.Structure):
@@ -100,6 +108,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_iwe_fix_ptr': (vp, [vp]),
         'eincm_split_prepare': (i32, [vp, vp]),
         'eincm_split_window_images': (i32, [vp, vp]),
+        'eincm_minimize_bfgs_host': (i32, [vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
+        'eincm_minimize_handover_host': (i32, [vp, C.POINTER(dbl), dbl, dbl, vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
         'eincm_plan_launch_count': (i64, [vp]),
         'eincm_plan_set_timing': (i32, [vp, i32]),
         'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
@@ -303,6 +313,33 @@ class Plan:
                                                                 theta.ctypes.data, h, w, C.byref(hp), C.byref(loss),
                                                                 C.byref(da) if want_grad else None, _stream_ptr(stream)))
         return loss.value, (da.value if want_grad else None)
+
+    # -- native optimizers (no Python between evaluations; ctypes releases the GIL for the whole solve) ---------------
+    def minimize_bfgs_host(self, theta0: np.ndarray, hp: HParams, maxiter: int, gtol: float, own_stream: bool = False, stream=None):
+        """``ScipyMinimize(method='BFGS').run`` on this plan's objective: returns ``(theta, OptResult)``."""
+        theta = np.array(theta0, dtype=np.float64, order='C', copy=True)
+        if theta.ndim != 3 or theta.shape[2] != 2:
+            raise EincmError(EINCM_EINVAL, f'theta must have shape (h, w, 2), got {theta.shape}')
+        res = OptResult()
+        st = OWN_STREAM if own_stream else _stream_ptr(stream)
+        self._check(self.lib.eincm_minimize_bfgs_host(self._h, theta.ctypes.data, theta.shape[0], theta.shape[1], C.byref(hp),
+                                                      int(maxiter), float(gtol), C.byref(res), st))
+        return theta, res
+
+    def minimize_handover_host(self, alpha0: float, bounds, prev_theta: np.ndarray, theta: np.ndarray, hp: HParams, maxiter: int,
+                               pgtol: float, own_stream: bool = False, stream=None):
+        """``ScipyBoundedMinimize(method='L-BFGS-B').run`` on the scalar handover weight: returns ``(alpha, OptResult)``."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        prev_theta = np.ascontiguousarray(prev_theta, dtype=np.float64)
+        if theta.shape != prev_theta.shape or theta.ndim != 3 or theta.shape[2] != 2:
+            raise EincmError(EINCM_EINVAL, 'prev_theta and theta must both have shape (h, w, 2)')
+        a = C.c_double(float(alpha0))
+        res = OptResult()
+        st = OWN_STREAM if own_stream else _stream_ptr(stream)
+        self._check(self.lib.eincm_minimize_handover_host(self._h, C.byref(a), float(bounds[0]), float(bounds[1]), prev_theta.ctypes.data,
+                                                          theta.ctypes.data, theta.shape[0], theta.shape[1], C.byref(hp), int(maxiter),
+                                                          float(pgtol), C.byref(res), st))
+        return a.value, res
 
     def value_and_grad_stateless_host(self, theta, xs, ys, ts, edges, edge_ts, hp: HParams, stream=None):
         theta = np.ascontiguousarray(theta, dtype=np.float64)

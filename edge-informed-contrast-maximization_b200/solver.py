@@ -123,7 +123,13 @@ class MultipleLevelEINCMSolver:
                  handover_opt_solver_params: Optional[dict] = None, handover_settings: Optional[dict] = None,
                  pyramid_downscale_method: str = 'lanczos3', pyramid_upscale_method: str = 'repeat',
                  pyramid_bases: Optional[Sequence[int]] = None, theta_solver_callback=None, handover_solver_callback=None,
-                 maxiters_grow_order: float = 1.413):
+                 maxiters_grow_order: float = 1.413, backend: str = 'scipy', own_stream: bool = False):
+        """``backend='scipy'``: the scipy calls jaxopt makes, every evaluation a host call; ``backend='native'``: the same two
+        optimizers inside the library (``eincm_minimize_bfgs_host`` / ``eincm_minimize_handover_host``), one host call per
+        level - per-iteration callbacks are not invoked.  ``own_stream``: run on the plan's own CUDA stream (several solvers
+        driven from several host threads overlap on the GPU; the native calls release the GIL)."""
+        assert backend in ('scipy', 'native')
+        self.backend, self.own_stream = backend, own_stream
         self.objective = objective
         self.n_pyr_lvls = n_pyr_lvls
         self.theta_opt_solver_params = theta_opt_solver_params or DEFAULT_THETA_OPT
@@ -181,8 +187,12 @@ class MultipleLevelEINCMSolver:
     # -- the two scipy calls jaxopt makes -------------------------------------------------------------------------
     def _run_theta_solver(self, pyr_lvl: int, theta0: np.ndarray):
         """ScipyMinimize.run (solver.py:165-173, :209-216): BFGS on the raveled theta, jac=True."""
-        import scipy.optimize
         key = f'pyr_lvl_{pyr_lvl}'
+        if self.backend == 'native':
+            theta, r = self.objective.minimize_bfgs(theta0, pyr_lvl, self.theta_opt_maxiters[key],
+                                                    self.theta_opt_solver_params['options']['gtol'], own_stream=self.own_stream)
+            return theta, OptState(float(r.fun), r.status == 0, int(r.status), int(r.nit), int(r.nfev))
+        import scipy.optimize
         shape = theta0.shape
         n0 = self.objective.n_evals
         res = scipy.optimize.minimize(self.objective.scipy_fun(shape, pyr_lvl), np.asarray(theta0, dtype=np.float64).ravel(),
@@ -194,8 +204,12 @@ class MultipleLevelEINCMSolver:
 
     def _run_handover_solver(self, pyr_lvl: int, alpha0: float, bounds, prior_theta, theta):
         """ScipyBoundedMinimize.run (solver.py:175-183, :325-335): L-BFGS-B on the scalar handover weight."""
-        import scipy.optimize
         key = f'pyr_lvl_{pyr_lvl}'
+        if self.backend == 'native':
+            a, r = self.objective.minimize_handover(alpha0, bounds, prior_theta, theta, pyr_lvl, self.handover_opt_maxiters[key],
+                                                    self.handover_opt_solver_params['options']['gtol'], own_stream=self.own_stream)
+            return a, OptState(float(r.fun), r.status == 0, int(r.status), int(r.nit), int(r.nfev))
+        import scipy.optimize
         n0 = self.objective.n_evals
 
         def fun(a):

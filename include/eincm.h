@@ -129,6 +129,17 @@ int eincm_handover_value_and_grad_host(eincm_plan* plan, double alpha_handover, 
  * (src/eincm/solver.py:209-216); independent sequences / windows without handover may be evaluated together. */
 int eincm_value_and_grad_host_batch(eincm_plan* const* plans, int n_plans, const double* const* thetas_host, int h, int w,
                                     const eincm_hparams* hp, double* losses_out_host, double* const* grads_out_host);
+/* ---- native optimizers: what jaxopt's ScipyMinimize(method='BFGS').run / ScipyBoundedMinimize(method='L-BFGS-B').run do with
+ * the objective (reference src/eincm/solver.py:165-183, :209-216, :325-335), without returning to Python between evaluations.
+ * Same algorithms and default parameters as scipy.optimize.minimize (csrc/eincm_opt.h); status: 0 converged (max|grad| <= gtol),
+ * 1 maxiter reached, 2 line search failed ("precision loss"), 3 non-finite objective - the codes solver.py:218-239 reacts to.
+ * cuda_stream == (void*)-1 selects the plan's own stream (several plans solved concurrently from several host threads). */
+typedef struct eincm_opt_result { double fun; int32_t nit, nfev, status, reserved; } eincm_opt_result;
+int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host /* [h][w][2] */, int h, int w, const eincm_hparams* hp,
+                             int maxiter, double gtol, eincm_opt_result* result_out, void* cuda_stream);
+int eincm_minimize_handover_host(eincm_plan* plan, double* alpha_inout_host, double lo, double hi, const double* prev_theta_host,
+                                 const double* theta_host, int h, int w, const eincm_hparams* hp, int maxiter, double pgtol,
+                                 eincm_opt_result* result_out, void* cuda_stream);
 /* Stateless single shot with the exact operand list of loss_func (losses.py:108-114), every operand on the host:
  * set_window + value_and_grad + copies. */
 int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_host, int h, int w,

@@ -1,0 +1,85 @@
+"""The native optimizers of csrc/eincm_opt.h (host-only C++) against scipy.optimize.minimize on classic test functions:
+same minima, scipy's status codes (0 converged, 1 maxiter).  No GPU needed."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.optimize
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'native', 'opt_harness.cpp')
+SO = os.path.join(HERE, 'native', '_opt_harness.so')
+
+
+class Out(C.Structure):
+    _fields_ = [('fun', C.c_double), ('nit', C.c_int), ('nfev', C.c_int), ('status', C.c_int), ('pad', C.c_int)]
+
+
+@pytest.fixture(scope='module')
+def lib():
+    hdr = os.path.join(HERE, '..', 'edge-informed-contrast-maximization_b200', 'csrc', 'eincm_opt.h')
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, SRC], check=True)
+    return C.CDLL(SO)
+
+
+def _rosen(x):
+    return scipy.optimize.rosen(x), scipy.optimize.rosen_der(x)
+
+
+@pytest.mark.parametrize('n', [2, 8, 32])
+def test_bfgs_rosenbrock_matches_scipy(lib, n):
+    x0 = np.linspace(-1.2, 1.0, n)
+    ref = scipy.optimize.minimize(_rosen, x0, jac=True, method='BFGS', options={'gtol': 1e-7, 'maxiter': 2000})
+    x = x0.copy()
+    out = Out()
+    assert lib.bfgs_rosenbrock(n, x.ctypes.data_as(C.POINTER(C.c_double)), 2000, C.c_double(1e-7), C.byref(out)) == 0
+    assert out.status == 0 and ref.status == 0
+    assert out.fun <= 1e-12 and np.abs(x - 1.0).max() <= 1e-5
+    assert np.abs(x - ref.x).max() <= 1e-5
+    assert out.nfev <= 2 * ref.nfev + 20                       # comparable work, not the same iterates
+
+
+def test_bfgs_status_codes(lib):
+    x = np.linspace(-1.2, 1.0, 8)
+    out = Out()
+    lib.bfgs_rosenbrock(8, x.ctypes.data_as(C.POINTER(C.c_double)), 5, C.c_double(1e-7), C.byref(out))
+    assert out.status == 1 and out.nit == 5                    # maxiter, as scipy reports it
+    f0 = scipy.optimize.rosen(np.linspace(-1.2, 1.0, 8))
+    assert out.fun < f0
+    x = np.ones(8)
+    lib.bfgs_rosenbrock(8, x.ctypes.data_as(C.POINTER(C.c_double)), 5, C.c_double(1e-7), C.byref(out))
+    assert out.status == 0 and out.nit == 0 and out.nfev == 1  # already converged
+
+
+def test_bfgs_quartic_matches_scipy(lib):
+    n = 16
+
+    def f(v):
+        c = 1.0 + 10.0 * np.arange(n); d = v - 0.1 * np.arange(n)
+        return float((0.5 * c * d * d + 0.25 * d ** 4).sum()), c * d + d ** 3
+
+    x0 = np.full(n, 3.0)
+    ref = scipy.optimize.minimize(f, x0, jac=True, method='BFGS', options={'gtol': 1e-7, 'maxiter': 500})
+    x = x0.copy()
+    out = Out()
+    assert lib.bfgs_quartic(n, x.ctypes.data_as(C.POINTER(C.c_double)), 500, C.c_double(1e-7), C.byref(out)) == 0
+    assert out.status == 0
+    np.testing.assert_allclose(x, 0.1 * np.arange(n), atol=1e-6)
+    np.testing.assert_allclose(x, ref.x, atol=1e-6)
+
+
+@pytest.mark.parametrize('m,lo,hi,a0', [(0.3, 0.0, 1.0, 0.5), (1.7, 0.0, 1.0, 0.5), (-0.4, 0.0, 1.0, 0.5), (0.6, 0.0, 1.0, 0.0)])
+def test_bounded_scalar_matches_lbfgsb(lib, m, lo, hi, a0):
+    def f(a):
+        return float((a[0] - m) ** 2 + 0.3 * np.sin(5 * a[0])), np.array([2 * (a[0] - m) + 1.5 * np.cos(5 * a[0])])
+
+    ref = scipy.optimize.minimize(f, np.array([a0]), jac=True, method='L-BFGS-B', bounds=[(lo, hi)], options={'gtol': 1e-6, 'maxiter': 20})
+    a = C.c_double(a0)
+    out = Out()
+    assert lib.bounded_scalar_wavy(C.c_double(m), C.byref(a), C.c_double(lo), C.c_double(hi), 20, C.c_double(1e-6), C.byref(out)) == 0
+    assert lo <= a.value <= hi
+    assert out.fun <= ref.fun + 1e-7                            # at least as good a point as L-BFGS-B finds
+    assert abs(a.value - ref.x[0]) <= 1e-3 or out.fun < ref.fun - 1e-9
