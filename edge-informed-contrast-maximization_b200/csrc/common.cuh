@@ -77,12 +77,14 @@ __device__ __forceinline__ void scharr_at(const double* p, int pitch, double& gx
 
 // Adjoint of the Scharr pair ('same' correlation with the same kernels), canonical order of oracle._scharr_adjoint.
 // xu/xm/xd point at the cotangent of Gx at column j of rows i-1 / i / i+1 (yu/ym/yd likewise for Gy).
-__device__ __forceinline__ double scharr_adjoint_rows(const double* xu, const double* xm, const double* xd,
-                                                      const double* yu, const double* yd) {
-    const double ax = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(xu[-1], xu[1])), __dmul_rn(10.0, __dsub_rn(xm[-1], xm[1]))),
-                                __dmul_rn(3.0, __dsub_rn(xd[-1], xd[1])));
-    const double ay = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(yu[-1], yd[-1])), __dmul_rn(10.0, __dsub_rn(yu[0], yd[0]))),
-                                __dmul_rn(3.0, __dsub_rn(yu[1], yd[1])));
+template <typename T>
+__device__ __forceinline__ double scharr_adjoint_rows(const T* xu, const T* xm, const T* xd, const T* yu, const T* yd) {
+    const double ax = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn((double)xu[-1], (double)xu[1])),
+                                          __dmul_rn(10.0, __dsub_rn((double)xm[-1], (double)xm[1]))),
+                                __dmul_rn(3.0, __dsub_rn((double)xd[-1], (double)xd[1])));
+    const double ay = __dadd_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn((double)yu[-1], (double)yd[-1])),
+                                          __dmul_rn(10.0, __dsub_rn((double)yu[0], (double)yd[0]))),
+                                __dmul_rn(3.0, __dsub_rn((double)yu[1], (double)yd[1])));
     return __dadd_rn(ax, ay);
 }
 

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -57,10 +58,12 @@ struct eincm_plan {
     int n_peers = 0;                                // 0: no peer access (the caller all-reduces the float64 images)
     cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
     size_t host_ng = 0;                  // gradient doubles of the host evaluation in flight (host_enqueue -> host_collect)
+    unsigned long long* img_dbg = nullptr;   // EINCM_IMAGE_PASS_STAMPS=1: phase time stamps of the image pass (profiling aid)
     bool host_delivered = false;  // the last backward pass wrote its results into the mapped host buffer itself
     double* h_mapped_dev = nullptr;   // device alias of h_pinned (cudaHostAllocMapped)
     bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
-    int coop_ctas = 0;            // co-resident CTAs of k_image_pass
+    struct CoopCfg { int ctas = 0, band_rows = 0; };
+    CoopCfg coop_cfg[EINCM_MAX_REFS + 1];   // grid / sub-band height of k_image_pass per number of reference images (lazy)
     bool coop_ok = false;         // the sensor is narrow enough for the row-band cooperative image pass
     bool fused_pending = false;   // the last forward left the fixed-point images for the fused image pass (no float64 copy yet)
     RefTimes tref{};
@@ -389,10 +392,28 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             g_zeroed_grad = true;
         }
         ia.H = H; ia.W = W; ia.R = R;
+        ia.dbg = plan->img_dbg;
         ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0; ia.want_grad = want_grad ? 1 : 0;
-        const int gridI = std::max(1, std::min(plan->coop_ctas, (R * H + 3) / 4));       // >= 4 rows per CTA
+        // grid and sub-band height: as many co-resident CTAs as fit (at most 2 per SM), each ideally holding its whole row
+        // band in shared memory (one sub-band)
+        eincm_plan::CoopCfg& cc = plan->coop_cfg[R];
+        if (cc.ctas == 0) {
+            const int target = std::max(1, std::min(plan->sm_count * 2, (R * H + 3) / 4));          // >= 4 rows per CTA
+            int B = std::min(kBandRowsMax, std::max(2, (R * H + target - 1) / target));
+            int per_sm = 0;
+            for (;; --B) {
+                cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_pass_kernel(W), kBandNT, image_pass_smem_bytes(W, B));
+                if (eo != cudaSuccess) return fail(plan, EINCM_ECUDA, "occupancy query of the image pass: %s", cudaGetErrorString(eo));
+                if (per_sm >= 2 || B <= 2) break;
+            }
+            if (per_sm < 1) return fail(plan, EINCM_ECUDA, "the cooperative image pass does not fit this device for W = %d", W);
+            cc.band_rows = B;
+            cc.ctas = std::max(1, std::min(target, per_sm * plan->sm_count));
+        }
+        ia.band_rows = cc.band_rows;
         void* kargs[] = {(void*)&ia};
-        LAUNCH("k_image_pass", cudaLaunchCooperativeKernel(image_pass_kernel(W), dim3(gridI), dim3(kBandNT), kargs, image_pass_smem_bytes(W), st));
+        LAUNCH("k_image_pass", cudaLaunchCooperativeKernel(image_pass_kernel(W), dim3(cc.ctas), dim3(kBandNT), kargs,
+                                                           image_pass_smem_bytes(W, cc.band_rows), st));
         plan->fused_pending = false;
         plan->fix_clean = true;                                  // the pass clears the cells it has read
         if (!want_grad) return EINCM_OK;
@@ -529,16 +550,15 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     {
         int per_sm = 0;
         // the cooperative image pass keeps whole rows in shared memory; very wide sensors use the unfused image kernels
-        const size_t smem_img = image_pass_smem_bytes(W);
+        const size_t smem_img = image_pass_smem_bytes(W, 2);
         plan->coop_ok = W <= kMaxCPT * kBandNT && smem_img <= (size_t)prop.sharedMemPerBlockOptin;
         if (plan->coop_ok) {
-            if ((e = cudaFuncSetAttribute(image_pass_kernel(W), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess ||
-                (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_pass_kernel(W), kBandNT, smem_img)) != cudaSuccess || per_sm < 1) {
+            if ((e = cudaFuncSetAttribute(image_pass_kernel(W), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess) {
                 delete plan;
-                return fail(nullptr, EINCM_ECUDA, "occupancy query of the cooperative image pass failed (%s)", cudaGetErrorString(e));
+                return fail(nullptr, EINCM_ECUDA, "shared-memory opt-in of the cooperative image pass failed (%s)", cudaGetErrorString(e));
             }
-            plan->coop_ctas = plan->sm_count * std::min(per_sm, 3);
         }
+        (void)per_sm;
     }
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
     plan->n_tiles = plan->tiles_x * ((H + kSortTile - 1) / kSortTile);
@@ -579,6 +599,9 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(cudaHostAlloc((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double), cudaHostAllocMapped));
         CU(cudaHostGetDevicePointer((void**)&plan->h_mapped_dev, plan->h_pinned, 0));
         CU(cudaStreamCreateWithFlags(&plan->own_stream, cudaStreamNonBlocking));
+        if (const char* e = std::getenv("EINCM_IMAGE_PASS_STAMPS")) {
+            if (e[0] == '1') { CU(dmalloc(&plan->img_dbg, 16)); CU(cudaMemset(plan->img_dbg, 0, 16 * sizeof(unsigned long long))); }
+        }
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
         return EINCM_OK;
     };
@@ -596,7 +619,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
     void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
-                    plan->chunk_first, plan->totals, plan->chunks, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
+                    plan->chunk_first, plan->totals, plan->img_dbg, plan->chunks, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
@@ -1040,6 +1063,15 @@ int eincm_split_window_images(eincm_plan* plan, void* cuda_stream) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // after the barrier: this rank's fixed-point image 0 holds the complete zero-warp image of the window
     LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((plan->HW + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, plan->HW, plan->zero_iwe));
+    return EINCM_OK;
+}
+
+int eincm_debug_image_pass_stamps(eincm_plan* plan, unsigned long long* out_host /* [6] */) {
+    if (!plan || !out_host) return EINCM_EINVAL;
+    if (!plan->img_dbg) return fail(plan, EINCM_ESTATE, "set EINCM_IMAGE_PASS_STAMPS=1 before creating the plan");
+    CU(cudaSetDevice(plan->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out_host, plan->img_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return EINCM_OK;
 }
 

@@ -96,7 +96,17 @@ struct ImagePassArgs {
     int H, W, R;
     double alpha, beta, gamma;
     int use_tv, want_grad;
+    int band_rows;                // rows of a sub-band held in shared memory (<= kBandRowsMax; shared memory is sized for it)
+    unsigned long long* dbg;      // optional: %globaltimer stamps of CTA 0 at the phase boundaries (profiling aid) or null
 };
+
+__device__ __forceinline__ void stamp(const ImagePassArgs& A, int slot) {
+    if (A.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        A.dbg[slot] = t;
+    }
+}
 
 __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double sE, double sE2, double cb) {
     Stats st;
@@ -121,8 +131,7 @@ __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double
 // its statistics over all its pixels before the single block reduction per (CTA, reference image).
 constexpr int kBandNT = 256;
 constexpr int kMaxCPT = 6;                          // columns per thread (template parameter 1..6): sensors up to 1536 px wide
-constexpr int kBandRows = 8;                        // rows of a sub-band
-constexpr int kRing = 4;                            // rows of the rolling Scharr rings (phase 3)
+constexpr int kBandRowsMax = 8;                     // rows of a sub-band (chosen by the host: ImagePassArgs::band_rows)
 
 // 8-byte asynchronous global -> shared copy; `valid == false` zero-fills (rows outside the image)
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
@@ -138,10 +147,12 @@ struct BandSmemTail {
     double red[kBandNT / 32][kFPart];
     Stats st[kCoopMaxRefs];
     double coefA[kCoopMaxRefs], coefB[kCoopMaxRefs];
+    double wts[kCoopMaxRefs], zero_mse[kCoopMaxRefs], sumE[kCoopMaxRefs], sumE2[kCoopMaxRefs], zero_contrast;
 };
 
-__host__ __device__ inline size_t image_pass_smem_bytes(int W) {
-    return (size_t)(kBandRows + 4 + 2 * kRing) * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
+// image rows (halo 2) + Scharr pair of rows (halo 1, float32) + edge rows of a sub-band of B rows
+__host__ __device__ inline size_t image_pass_smem_bytes(int W, int B) {
+    return (size_t)((B + 4) + (B + 2) + B) * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
 }
 
 template <int CPT>
@@ -149,11 +160,12 @@ __global__ void __launch_bounds__(kBandNT)
 k_image_pass(const ImagePassArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = A.H, W = A.W, R = A.R, Wp = W + 2;
-    double* bandI = reinterpret_cast<double*>(smem_raw);             // [kBandRows + 4][Wp]: image rows sa-2 .. sa+kBandRows+1
-    double* ringX = bandI + (kBandRows + 4) * Wp;                    // [kRing][Wp]   phase 1: edge rows of the sub-band
-    double* ringY = ringX + kRing * Wp;                              // [kRing][Wp]   (2 * kRing == kBandRows rows in total)
-    BandSmemTail& S = *reinterpret_cast<BandSmemTail*>(ringY + kRing * Wp);
-    static_assert(2 * kRing == kBandRows, "the edge rows of a sub-band live in the two Scharr rings during phase 1");
+    const int B = A.band_rows;
+    double* bandI = reinterpret_cast<double*>(smem_raw);             // [B + 4][Wp]: image rows sa-2 .. sa+B+1
+    float* gxs = reinterpret_cast<float*>(bandI + (B + 4) * Wp);     // [B + 2][Wp] Scharr x of rows sa-1 .. sa+B (phase 3)
+    float* gys = gxs + (B + 2) * Wp;                                 // [B + 2][Wp] Scharr y
+    double* bandE = reinterpret_cast<double*>(gys + (B + 2) * Wp);   // [B][Wp] edge rows of the sub-band
+    BandSmemTail& S = *reinterpret_cast<BandSmemTail*>(bandE + B * Wp);
     const int HW = H * W;
     const int tid = threadIdx.x;
     const int G = gridDim.x, b = blockIdx.x;
@@ -161,8 +173,10 @@ k_image_pass(const ImagePassArgs A) {
     const int row_begin = (int)(((long long)RH * b) / G), row_end = (int)(((long long)RH * (b + 1)) / G);
     const int r_first = row_begin < row_end ? row_begin / H : 0, r_last = row_begin < row_end ? (row_end - 1) / H : -1;
 
+    stamp(A, 0);
     // zero columns (never written afterwards), identity partials, accumulators of the event backward pass
-    for (int k = tid; k < kBandRows + 4 + 2 * kRing; k += kBandNT) { bandI[k * Wp] = 0.0; bandI[k * Wp + W + 1] = 0.0; }
+    for (int k = tid; k < B + 4; k += kBandNT) { bandI[k * Wp] = 0.0; bandI[k * Wp + W + 1] = 0.0; }
+    for (int k = tid; k < 2 * (B + 2); k += kBandNT) { gxs[k * Wp] = 0.f; gxs[k * Wp + W + 1] = 0.f; }
     for (int k = tid; k < R * kFPart; k += kBandNT) {
         const int q = k / kFPart, f = k % kFPart;
         A.part[(q * G + b) * kFPart + f] = (f == 4) ? INFINITY : ((f == 6) ? -INFINITY : 0.0);
@@ -171,6 +185,17 @@ k_image_pass(const ImagePassArgs A) {
         for (int k = b * kBandNT + tid; k < A.n_zero; k += G * kBandNT) A.zero_buf[k] = 0.0;
     if (A.zero_buf2 != nullptr)
         for (int k = b * kBandNT + tid; k < A.n_zero2; k += G * kBandNT) A.zero_buf2[k] = 0.0;
+    // per-window constants of phase 2 (cotangent scales from the zero-warp image, losses.py:176-177): fetched now, their
+    // latency hides behind phase 1
+    if (tid < R) {
+        const double w = A.sc->weights[tid], zc = A.sc->zero[0].contrast, zm = A.sc->zero[tid].mse;
+        const double a_r = -A.alpha * w / ((zc + kEps) * R);
+        const double b_r = A.beta * w / ((-zm + kEps) * R);
+        S.coefA[tid] = a_r * (2.0 / (double)HW);
+        S.coefB[tid] = b_r * (-2.0 / (double)HW);
+        S.wts[tid] = w; S.zero_mse[tid] = zm; S.sumE[tid] = A.sc->sumE[tid]; S.sumE2[tid] = A.sc->sumE2[tid];
+        if (tid == 0) S.zero_contrast = zc;
+    }
 
     // asynchronous copy of image rows [y0, y1) of `src` (8-byte cells) into bandI, row y at slot y - slot0
     auto copy_rows = [&](const void* src, int y0, int y1, int slot0) {
@@ -186,6 +211,7 @@ k_image_pass(const ImagePassArgs A) {
         }
     };
 
+    stamp(A, 1);
     // ---- phase 1: float64 image + statistics --------------------------------------------------------------------------
     for (int r = r_first; r <= r_last; ++r) {
         const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
@@ -195,12 +221,12 @@ k_image_pass(const ImagePassArgs A) {
         FusedAcc acc;
         acc.init();
         int cnt_mn = 0, cnt_mx = 0;                   // tie counts of the running min / max (integers: branch-free update)
-        for (int sa = ya; sa < yb; sa += kBandRows) {
-            const int sb = min(sa + kBandRows, yb);
+        for (int sa = ya; sa < yb; sa += B) {
+            const int sb = min(sa + B, yb);
             __syncthreads();                           // previous readers of the band are done
             copy_rows(Fr, sa - 1, sb + 1, sa - 2);
-            for (int y = sa; y < sb; ++y) {            // edge rows -> ring area, row y at slot y - sa
-                double* dst = ringX + (y - sa) * Wp + 1;
+            for (int y = sa; y < sb; ++y) {            // edge rows, row y at slot y - sa
+                double* dst = bandE + (y - sa) * Wp + 1;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
@@ -221,7 +247,7 @@ k_image_pass(const ImagePassArgs A) {
                 const double* mid = bandI + (y - sa + 2) * Wp + 1;
                 const double* up = mid - Wp;
                 const double* dn = mid + Wp;
-                const double* er = ringX + (y - sa) * Wp + 1;
+                const double* er = bandE + (y - sa) * Wp + 1;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
@@ -246,40 +272,68 @@ k_image_pass(const ImagePassArgs A) {
             d[0] = a.sq; d[1] = a.sI; d[2] = a.sI2; d[3] = a.sEI; d[4] = a.mn; d[5] = a.cmn; d[6] = a.mx; d[7] = a.cmx;
         }
     }
+    stamp(A, 2);
     __threadfence();
     cooperative_groups::this_grid().sync();
+    stamp(A, 3);
 
-    // ---- phase 2: global statistics of the reference images this CTA owns (CTA 0: all, plus the loss) ----------------------
+    // ---- phase 2: global statistics of every reference image, one WARP per image (no block-level synchronisation inside), the
+    // same fixed order in every CTA: identical, deterministic results everywhere; CTA 0 also evaluates the loss --------------
     {
-        if (tid < R) {                               // cotangent scales from the zero-warp constants (losses.py:176-177)
-            const double w = A.sc->weights[tid];
-            const double a_r = -A.alpha * w / ((A.sc->zero[0].contrast + kEps) * R);
-            const double b_r = A.beta * w / ((-A.sc->zero[tid].mse + kEps) * R);
-            S.coefA[tid] = a_r * (2.0 / (double)HW);
-            S.coefB[tid] = b_r * (-2.0 / (double)HW);
-        }
-        __syncthreads();
-        const int q_lo = (b == 0) ? 0 : r_first, q_hi = (b == 0) ? R - 1 : r_last;
-        for (int q = q_lo; q <= q_hi; ++q) {
+        const int lane = tid & 31;
+        for (int q = tid >> 5; q < R; q += kBandNT / 32) {
+            // only the CTAs whose rows intersect image q hold a non-identity partial: a contiguous range of CTAs.  Four records
+            // per lane and round, all loads of a round issued before the first merge (one L2 round trip per round)
+            const int k_lo = (int)(((long long)q * H * G) / RH);
+            const int k_hi = min(G, (int)((((long long)(q + 1) * H * G) + RH - 1) / RH) + 1);
             FusedAcc a;
             a.init();
-            for (int k = tid; k < G; k += kBandNT) {
-                const double* d = A.part + (q * G + k) * kFPart;
-                FusedAcc o;
-                o.sq = __ldcg(d + 0); o.sI = __ldcg(d + 1); o.sI2 = __ldcg(d + 2); o.sEI = __ldcg(d + 3);
-                o.mn = __ldcg(d + 4); o.cmn = __ldcg(d + 5); o.mx = __ldcg(d + 6); o.cmx = __ldcg(d + 7);
-                a.merge(o);
+            for (int k0 = k_lo + lane; k0 < k_hi; k0 += 4 * 32) {
+                double v[4][kFPart];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = min(k0 + 32 * u, k_hi - 1);
+                    const double* d = A.part + (q * G + k) * kFPart;
+#pragma unroll
+                    for (int f = 0; f < kFPart; ++f) v[u][f] = __ldcg(d + f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + 32 * u < k_hi) {
+                        FusedAcc o;
+                        o.sq = v[u][0]; o.sI = v[u][1]; o.sI2 = v[u][2]; o.sEI = v[u][3];
+                        o.mn = v[u][4]; o.cmn = v[u][5]; o.mx = v[u][6]; o.cmx = v[u][7];
+                        a.merge(o);
+                    }
+                }
             }
-            a = fused_block_reduce(a, S.red);
-            if (tid == 0) S.st[q] = fused_stats(a, (double)HW, A.sc->sumE[q], A.sc->sumE2[q], S.coefB[q]);
+            if (q == 0) stamp(A, 6);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) a.merge(a.shfl_xor(o));
+            if (q == 0) stamp(A, 7);
+            if (lane == 0) S.st[q] = fused_stats(a, (double)HW, S.sumE[q], S.sumE2[q], S.coefB[q]);
+            if (q == 0) stamp(A, 8);
         }
         __syncthreads();
+        stamp(A, 9);
         if (b == 0 && tid == 0) {
             for (int q = 0; q < R; ++q) { A.sc->ref[q] = S.st[q]; A.sc->coefA[q] = S.coefA[q]; A.sc->coefB[q] = S.coefB[q]; A.sc->coefD[q] = 0.0; }
-            scalars_loss(A.sc, R, A.alpha, A.beta, A.gamma, 0.0, A.use_tv, 0, A.loss_out);
+            // final loss (reference src/eincm/losses.py:171-193) from operands prefetched before the barrier
+            double s_corr = 0.0, s_con = 0.0;
+            for (int q = 0; q < R; ++q) {
+                s_corr += (S.wts[q] * (-S.st[q].mse)) / ((-S.zero_mse[q]) + kEps);          // losses.py:176
+                s_con += (S.wts[q] * S.st[q].contrast) / (S.zero_contrast + kEps);          // losses.py:177
+            }
+            const double mean_rel_corr = s_corr / R, mean_rel_contrast = s_con / R;
+            const double tv = A.use_tv ? A.sc->tv_sum / (A.sc->tv_cnt + kEps) : 0.0;        // regularizers.py:31-36, losses.py:171
+            const double loss = (A.alpha * (mean_rel_contrast * (-1.0)) + A.beta * (mean_rel_corr * (-1.0))) + (A.gamma * tv + 0.0);
+            A.sc->loss = loss; A.sc->mean_rel_corr = mean_rel_corr; A.sc->mean_rel_contrast = mean_rel_contrast;
+            A.sc->mean_rel_div = 0.0; A.sc->tv = tv;
+            if (A.loss_out != nullptr) *A.loss_out = loss;
         }
     }
 
+    stamp(A, 4);
     // ---- phase 3: clear the fixed-point rows; d loss / d IWE ---------------------------------------------------------------
     for (int r = r_first; r <= r_last; ++r) {
         const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
@@ -288,69 +342,57 @@ k_image_pass(const ImagePassArgs A) {
         if (!A.want_grad) continue;
         const double* Er = A.edges + r * HW;
         const double* Ir = A.iwe + r * HW;
-        // Scharr pair of row q from the band rows q-1, q, q+1 (zero outside the image: 'same' output only exists inside)
-        auto grad_row = [&](int q, int sa) {
-            const double* mid = bandI + (q - sa + 2) * Wp + 1;
-            const double* up = mid - Wp;
-            const double* dn = mid + Wp;
-            double* gxr = ringX + ((q + kRing) & (kRing - 1)) * Wp + 1;
-            double* gyr = ringY + ((q + kRing) & (kRing - 1)) * Wp + 1;
-            const bool inside = q >= 0 && q < H;
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                if (x < W) {
-                    double gx = 0.0, gy = 0.0;
-                    if (inside) scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
-                    gxr[x] = gx; gyr[x] = gy;
-                }
-            }
-        };
         const Stats st = S.st[r];
         const double cA = S.coefA[r], cB = S.coefB[r];
         const double g_M = -st.s2 / (st.D * st.D);
         const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
-        for (int sa = ya; sa < yb; sa += kBandRows) {
-            const int sb = min(sa + kBandRows, yb);
-            __syncthreads();                           // previous readers of the band / rings are done
+        for (int sa = ya; sa < yb; sa += B) {
+            const int sb = min(sa + B, yb);
+            __syncthreads();                           // previous readers of the band are done
             copy_rows(Ir, sa - 2, sb + 2, sa - 2);
-            double epre[CPT];
+            for (int y = sa; y < sb; ++y) {
+                double* dst = bandE + (y - sa) * Wp + 1;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                epre[c] = (x < W) ? __ldg(Er + sa * W + x) : 0.0;
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    if (x < W) cp_async8(dst + x, Er + y * W + x, true);
+                }
             }
             cp_async_commit_wait_all();
             __syncthreads();
-            grad_row(sa - 1, sa);
-            grad_row(sa, sa);
-            for (int y = sa; y < sb; ++y) {
-                grad_row(y + 1, sa);                   // ring slot of row y-3: last read by the adjoint of row y-2
-                double e[CPT];
+            // Scharr pair of rows sa-1 .. sb from the band rows (zero outside the image: 'same' output only exists inside);
+            // all rows and columns of a thread are independent
+            for (int q = sa - 1; q <= sb; ++q) {
+                const double* mid = bandI + (q - sa + 2) * Wp + 1;
+                const double* up = mid - Wp;
+                const double* dn = mid + Wp;
+                float* gxr = gxs + (q - sa + 1) * Wp + 1;
+                float* gyr = gys + (q - sa + 1) * Wp + 1;
+                const bool inside = q >= 0 && q < H;
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) e[c] = epre[c];
-                if (y + 1 < sb) {
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        const int x = tid + c * kBandNT;
-                        epre[c] = (x < W) ? __ldg(Er + (y + 1) * W + x) : 0.0;
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    if (x < W) {
+                        double gx = 0.0, gy = 0.0;
+                        if (inside) scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
+                        gxr[x] = (float)gx; gyr[x] = (float)gy;
                     }
                 }
-                __syncthreads();
-                const double* xu = ringX + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
-                const double* xm = ringX + (y & (kRing - 1)) * Wp + 1;
-                const double* xd = ringX + ((y + 1) & (kRing - 1)) * Wp + 1;
-                const double* yu = ringY + ((y - 1 + kRing) & (kRing - 1)) * Wp + 1;
-                const double* yd = ringY + ((y + 1) & (kRing - 1)) * Wp + 1;
+            }
+            __syncthreads();
+            for (int y = sa; y < sb; ++y) {
+                const float* xm = gxs + (y - sa + 1) * Wp + 1;
+                const float* ym = gys + (y - sa + 1) * Wp + 1;
                 const double* mid = bandI + (y - sa + 2) * Wp + 1;
+                const double* er = bandE + (y - sa) * Wp + 1;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
                     if (x < W) {
                         const double I = mid[x];
-                        const double adj = scharr_adjoint_rows(xu + x, xm + x, xd + x, yu + x, yd + x);
+                        const double adj = scharr_adjoint_rows(xm - Wp + x, xm + x, xm + Wp + x, ym - Wp + x, ym + Wp + x);
                         const double cI = I - st.mn;
-                        const double gN = cB * (e[c] - cI / st.D);
+                        const double gN = cB * (er[x] - cI / st.D);
                         double out = cA * adj + gN / st.D;
                         if (I == st.mn) out += g_m / st.cnt_min;
                         if (I == st.mx) out += g_M / st.cnt_max;
@@ -362,6 +404,7 @@ k_image_pass(const ImagePassArgs A) {
             }
         }
     }
+    stamp(A, 5);
 }
 
 // per-window: sum E_r and sum E_r^2 (deterministic single-CTA-per-reference reduction; once per window)
