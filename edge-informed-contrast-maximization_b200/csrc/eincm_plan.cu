@@ -81,6 +81,7 @@ struct eincm_plan {
     unsigned int *counts = nullptr, *cursor = nullptr, *tile_cnt = nullptr, *tile_start = nullptr, *chunk_first = nullptr, *totals = nullptr;
     Chunk* chunks = nullptr;
     int4* chunk_win = nullptr;                         // [chunk_cap][max_refs] windows of the last forward pass
+    float2* chunk_tr = nullptr;                        // [chunk_cap] t range of the events of every chunk (per window)
     unsigned long long* iwe_fix = nullptr;             // [max_refs][H*W] fixed-point images of warped events
     int n_keys = 0, tiles_x = 0;
     uint8_t* mask = nullptr;
@@ -302,7 +303,7 @@ int splat_images(eincm_plan* plan, const ThetaSrc& T, const double2* theta_full,
         if (plan->n_peers > 0) { dst.n = plan->n_peers; for (int q = 0; q < dst.n; ++q) dst.p[q] = plan->peer_fix[q]; }
         else { dst.n = 1; dst.p[0] = plan->iwe_fix; }
 #define SPLATT(WR, RB) LAUNCH(tag, k_splat_tile<WR, RB><<<grid, 256, RB * kWinCap * sizeof(uint32_t), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
-                               plan->totals + 1, T, H, W, n_img, tref, dst, cw))
+                               plan->chunk_tr, plan->totals + 1, T, H, W, n_img, tref, dst, cw))
 #define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
                                                              case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
         if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
@@ -580,6 +581,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->chunk_first, (size_t)plan->n_tiles + 1)); CU(dmalloc(&plan->totals, 4));
         CU(cudaMemset(plan->totals, 0, 4 * sizeof(unsigned int)));
         CU(dmalloc(&plan->chunks, (size_t)plan->chunk_cap));
+        CU(dmalloc(&plan->chunk_tr, (size_t)plan->chunk_cap));
         CU(dmalloc(&plan->mask, HW));
         CU(dmalloc(&plan->theta_full, HW)); CU(dmalloc(&plan->Gtv, HW));
         CU(dmalloc(&plan->partial, (size_t)kGatherMaxTiles * 2 + (size_t)4 * plan->sm_count));
@@ -619,7 +621,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
     void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
-                    plan->chunk_first, plan->totals, plan->img_dbg, plan->chunks, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
+                    plan->chunk_first, plan->totals, plan->img_dbg, plan->chunks, plan->chunk_tr, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
@@ -695,6 +697,8 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
                                                                                    plan->counts, plan->cursor, plan->ev_t2, plan->perm2));
         std::swap(plan->ev_t, plan->ev_t2);
         std::swap(plan->perm, plan->perm2);
+        LAUNCH("k_chunk_trange", k_chunk_trange<<<std::max(1, std::min(plan->n_chunks, plan->sm_count * 8)), 256, 0, st>>>(plan->ev_xy, plan->ev_t, plan->chunks,
+                                                                                                          plan->totals + 1, plan->chunk_tr));
     }
     CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
     LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc));

@@ -78,12 +78,11 @@ static_assert(kChunk == kEvK * 256 && kStreamAlign == kEvK, "one chunk = one CTA
 constexpr int kWinCap = 4096;         // window cells per reference time (16 KB of uint32 / float)
 constexpr int kWinMaxH = 64;          // rows kept when the bounding rectangle exceeds kWinCap
 constexpr int kFixShift = 21;
-constexpr float kFixScale = 2097152.0f;                  // 2^21
 constexpr double kFixToIwe = kInv2Pi / 2097152.0;        // fixed-point sum -> image value
-constexpr float kRoundMagic = 12582912.0f;               // 1.5 * 2^23: float -> int by mantissa alignment
-constexpr int kRoundMagicBits = 0x4B400000;
-
-struct TapsFix { int n[9]; };                            // index (j+1)*3 + (i+1): column offset i, row offset j
+// float -> fixed point by mantissa alignment: for 0 <= p <= 1, the float 6 + p lies in [4, 8) where one ulp is 2^-21, so
+// bits(fma(ex, ey, 6.0f)) - bits(6.0f) == round(2^21 * ex * ey) (round to nearest even), no scaling multiply
+constexpr float kRoundMagic = 6.0f;
+constexpr int kRoundMagicBits = 0x40C00000;
 
 // exp(-0.5 (d - f)^2) for d = -1, 0, 1:  u = s f, q_d = s d - u, value = 2^(-q_d^2) with s = sqrt(0.5 log2 e)
 __device__ __forceinline__ void axis_exp3(float f, float e[3]) {
@@ -95,13 +94,13 @@ __device__ __forceinline__ void axis_exp3(float f, float e[3]) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[2]) : "f"(-q2 * q2));
 }
 
+struct TapsFix { int n[9]; };                            // index (j+1)*3 + (i+1): column offset i, row offset j
+
 // nine fixed-point tap values of one warped event: round(2^21 * exp(-0.5 ((i - fx)^2 + (j - fy)^2)))
 __device__ __forceinline__ TapsFix taps_fix(float fx, float fy) {
     float ex[3], ey[3];
     axis_exp3(fx, ex);
     axis_exp3(fy, ey);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) ey[d] *= kFixScale;
     TapsFix t;
 #pragma unroll
     for (int j = 0; j < 3; ++j)
@@ -110,46 +109,114 @@ __device__ __forceinline__ TapsFix taps_fix(float fx, float fy) {
     return t;
 }
 
+// Thread -> event group (kEvK consecutive events of the sorted stream).  The backward pass gives consecutive groups to consecutive
+// lanes (neighbouring lanes hold the same or neighbouring source pixels: its per-pixel segmented sums run over lanes, and equal
+// shared-memory addresses are broadcasts for loads).  The splat spreads the lanes of a warp over the chunk - with nw = warps
+// needed for the chunk's groups, lane l of warp w < nw takes group nw * l + w: consecutive events land on the same or
+// neighbouring destination cells, and equal addresses inside one shared-memory ATOMIC instruction are serialised.
+template <bool SPREAD>
 __device__ __forceinline__ void load_chunk_events(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk ch,
                                                   EventGroup& ev) {
-    if (4u * threadIdx.x < ch.count) {
-        load_group(ev_xy, ev_t, (int64_t)(ch.start >> 2) + threadIdx.x, ev);
+    uint32_t g = threadIdx.x;
+    if (SPREAD) {
+        const uint32_t nw = (ch.count + 127u) >> 7, w = threadIdx.x >> 5;       // 128 events per full warp
+        g = w < nw ? nw * (threadIdx.x & 31u) + w : 0xffffu;
+    }
+    if (4u * g < ch.count) {
+        load_group(ev_xy, ev_t, (int64_t)(ch.start >> 2) + g, ev);
     } else {
 #pragma unroll
         for (int k = 0; k < kEvK; ++k) { ev.xy[k] = kNoEvent; ev.t[k] = 0.0; }
     }
 }
 
-// Window of one reference time inside the destination image: origin (ox, oy), pw x ph cells, row pitch pw, and the
-// multiplier of the exact division i / pw for i < 2^16 (cell index -> row, column without an integer division).
-struct Window { int ox, oy, pw, ph; uint32_t inv_pw; };
+// Window of one reference time inside the destination image: origin (ox, oy), pw x ph cells, row pitch pw.  A warped event
+// votes into the window when its rounded centre lies in [ox + 1, ox + pw - 2] x [oy + 1, oy + ph - 2]; the kernels test that on
+// the float64 warped coordinate itself, |x' - cx| < hx (strict: a coordinate exactly on the rounding boundary takes the
+// fallback), which also rejects NaN / infinite / absurdly far warps in the same two comparisons.
+struct Window { int ox, oy, pw, ph; double cx, hx, cy, hy; };
 
-__device__ __forceinline__ Window make_window(int mnx, int mny, int mxx, int mxy) {
-    Window w{0, 0, 0, 0, 0u};
-    if (mnx > mxx || mny > mxy) return w;                    // no valid event
+__device__ __forceinline__ Window make_window(int ox, int oy, int pw, int ph) {
+    Window w;
+    w.ox = ox; w.oy = oy; w.pw = pw; w.ph = ph;
+    w.cx = (double)ox + 0.5 * (double)(pw - 1); w.hx = 0.5 * (double)(pw - 2);
+    w.cy = (double)oy + 0.5 * (double)(ph - 1); w.hy = 0.5 * (double)(ph - 2);
+    if (pw < 3 || ph < 3) { w.hx = -1.0; w.hy = -1.0; }
+    return w;
+}
+
+// window that holds the centres [mnx, mxx] x [mny, mxy] (cropped to kWinCap cells: the events outside take the fallback)
+__device__ __forceinline__ Window bound_window(int mnx, int mny, int mxx, int mxy) {
     long long bw = (long long)mxx - mnx + 3, bh = (long long)mxy - mny + 3;
     if (bw * bh > kWinCap) {
         if (bh > kWinMaxH) bh = kWinMaxH;
         if (bw > kWinCap / bh) bw = kWinCap / bh;
     }
-    w.ox = mnx - 1; w.oy = mny - 1; w.pw = (int)bw; w.ph = (int)bh;
-    w.inv_pw = 0xffffffffu / (uint32_t)bw + 1u;              // ceil(2^32 / pw): exact cell -> row for cells < 2^16
-    return w;
+    return make_window(mnx - 1, mny - 1, (int)bw, (int)bh);
 }
 
-__device__ __forceinline__ void cell_to_rc(const Window& w, int i, int& row, int& col) {
-    row = (int)__umulhi((uint32_t)i, w.inv_pw);
-    col = i - row * w.pw;
+// float <-> int32 with the same ordering (for REDUX.MIN / REDUX.MAX); NaN maps beyond +-inf and survives the round trip
+__device__ __forceinline__ int ordered_int(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// Conservative window of one chunk and one reference time: every event of the chunk starts inside the 16x16 source tile at
+// (x0, y0), has theta inside [thx_lo, thx_hi] x [thy_lo, thy_hi] (range over the tile) and t inside [t_lo, t_hi] (range over
+// the chunk, k_chunk_trange), so x' = x - theta_x (t - t_ref) lies inside an interval known without touching the events.
+// float32 interval arithmetic with explicit slack; rint(x') of every event is inside [floor(lo + 0.49), ceil(hi - 0.49)].
+__device__ __forceinline__ Window chunk_window(int x0, int y0, int x1, int y1, float thx_lo, float thx_hi, float thy_lo, float thy_hi,
+                                               float t_lo, float t_hi, double t_ref) {
+    const float trf = (float)t_ref;
+    const float es = 1.0e-6f * (1.f + fabsf(trf) + fmaxf(fabsf(t_lo), fabsf(t_hi)));
+    const float d_lo = (t_lo - trf) - es, d_hi = (t_hi - trf) + es;
+    const float px_lo = fminf(fminf(thx_lo * d_lo, thx_lo * d_hi), fminf(thx_hi * d_lo, thx_hi * d_hi));
+    const float px_hi = fmaxf(fmaxf(thx_lo * d_lo, thx_lo * d_hi), fmaxf(thx_hi * d_lo, thx_hi * d_hi));
+    const float py_lo = fminf(fminf(thy_lo * d_lo, thy_lo * d_hi), fminf(thy_hi * d_lo, thy_hi * d_hi));
+    const float py_hi = fmaxf(fmaxf(thy_lo * d_lo, thy_lo * d_hi), fmaxf(thy_hi * d_lo, thy_hi * d_hi));
+    const float lox = (float)x0 - px_hi, hix = (float)x1 - px_lo, loy = (float)y0 - py_hi, hiy = (float)y1 - py_lo;
+    const float mx = 1.0e-5f * (fabsf(lox) + fabsf(hix)) + 1.0e-3f, my = 1.0e-5f * (fabsf(loy) + fabsf(hiy)) + 1.0e-3f;
+    // the comparison is false for NaN (theta or t not finite): no window, every event of the chunk takes the fallback
+    const bool finite = (lox > -1.0e9f) && (hix < 1.0e9f) && (loy > -1.0e9f) && (hiy < 1.0e9f) &&
+                        (fabsf(thx_lo) + fabsf(thx_hi) + fabsf(thy_lo) + fabsf(thy_hi) < 3.0e38f) && (d_hi - d_lo < 3.0e38f);
+    if (!finite) return make_window(0, 0, 0, 0);
+    return bound_window(__float2int_rd(lox + 0.49f - mx), __float2int_rd(loy + 0.49f - my),
+                        __float2int_ru(hix - 0.49f + mx), __float2int_ru(hiy - 0.49f + my));
 }
 
-// the patch of a warped event with rounded centre (rx, ry) lies inside the window
-__device__ __forceinline__ bool in_window(const Window& w, int rx, int ry) {
-    return ((unsigned)(rx - w.ox - 1) < (unsigned)(w.pw - 2)) & ((unsigned)(ry - w.oy - 1) < (unsigned)(w.ph - 2));
+// per window: t range of every chunk (float32, rounded outwards; +inf / -inf for a chunk without events)
+__global__ void __launch_bounds__(256)
+k_chunk_trange(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks,
+               const unsigned int* __restrict__ n_chunks_dev, float2* __restrict__ chunk_tr) {
+    __shared__ int sh[8][2];
+    const int n_chunks = (int)__ldg(n_chunks_dev);
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const Chunk ch = chunks[c];
+        EventGroup ev;
+        load_chunk_events<false>(ev_xy, ev_t, ch, ev);
+        float lo = INFINITY, hi = -INFINITY;
+        bool nan = false;                       // fminf / fmaxf drop NaN operands: a NaN timestamp must poison the range instead
+#pragma unroll
+        for (int k = 0; k < kEvK; ++k)
+            if (ev.xy[k] != kNoEvent) {
+                nan |= ev.t[k] != ev.t[k];
+                lo = fminf(lo, __double2float_rd(ev.t[k]));
+                hi = fmaxf(hi, __double2float_ru(ev.t[k]));
+            }
+        const float qnan = __int_as_float(0x7fc00000);
+        const int rl = __reduce_min_sync(0xffffffffu, ordered_int(nan ? -qnan : lo));     // -NaN orders below -inf
+        const int rh = __reduce_max_sync(0xffffffffu, ordered_int(nan ? qnan : hi));      // +NaN orders above +inf
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = rl; sh[threadIdx.x >> 5][1] = rh; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int a = sh[0][0], b = sh[0][1];
+            for (int w8 = 1; w8 < 8; ++w8) { a = min(a, sh[w8][0]); b = max(b, sh[w8][1]); }
+            chunk_tr[c] = make_float2(ordered_float(a), ordered_float(b));
+        }
+    }
 }
 
-// Adds the nine pending tap sums to the 3x3 cells around the shared-memory cell `mid` (rows `pitch4` bytes apart): nine
-// `red.shared.add.u32` (ATOMS.ADD without return value) with immediate column offsets.  Callers branch around the whole
-// block: ptxas turns a predicated shared-memory atomic into its own branch, which costs four instructions per vote.
+// Adds nine tap values to the 3x3 cells around the shared-memory cell `mid` (rows `pitch4` bytes apart): nine
+// `red.shared.add.u32` (ATOMS.ADD without return value) with immediate column offsets.
 __device__ __forceinline__ void emit9(uint32_t mid, uint32_t pitch4, const int (&a)[9]) {
     const uint32_t up = mid - pitch4, dn = mid + pitch4;
     asm volatile(
@@ -160,17 +227,37 @@ __device__ __forceinline__ void emit9(uint32_t mid, uint32_t pitch4, const int (
         : "memory");
 }
 
-// theta of the 16x16 source tile at `origin` -> shared memory (zero flow when T.theta is null)
-__device__ __forceinline__ void tile_theta(const ThetaSrc& T, uint32_t origin, int H, int W, double2* __restrict__ th_s) {
+// theta of the 16x16 source tile at `origin` -> shared memory (zero flow when T.theta is null); returns the thread's value
+__device__ __forceinline__ double2 tile_theta(const ThetaSrc& T, uint32_t origin, int H, int W, double2* __restrict__ th_s) {
     const int p = threadIdx.x;                       // 256 threads <-> 256 pixels
     const int x = (int)(origin & 0xffffu) + (p & 15), y = (int)(origin >> 16) + (p >> 4);
     double2 v = make_double2(0.0, 0.0);
     if (T.theta != nullptr && x < W && y < H) v = theta_at(T, x, y);
     th_s[p] = v;
+    return v;
 }
 
-__device__ __forceinline__ double2 event_theta(const double2* __restrict__ th_s, uint32_t xy) {
-    return th_s[((xy >> 12) & 0xf0u) | (xy & 0xfu)];         // (y & 15) * 16 + (x & 15)
+// range of theta over the tile: per-warp REDUX of the order-preserving integer images of (float) theta -> sbox[warp][0..3]
+__device__ __forceinline__ void tile_theta_range(const double2 v, int (*sbox)[4]) {
+    const int ax = __reduce_min_sync(0xffffffffu, ordered_int(__double2float_rd(v.x)));
+    const int bx = __reduce_max_sync(0xffffffffu, ordered_int(__double2float_ru(v.x)));
+    const int ay = __reduce_min_sync(0xffffffffu, ordered_int(__double2float_rd(v.y)));
+    const int by = __reduce_max_sync(0xffffffffu, ordered_int(__double2float_ru(v.y)));
+    if ((threadIdx.x & 31) == 0) { int* s = sbox[threadIdx.x >> 5]; s[0] = ax; s[1] = bx; s[2] = ay; s[3] = by; }
+}
+
+// shared-memory address that the compiler cannot rematerialise (it would rebuild it from %cluster_ctarank at every use)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
+
+__device__ __forceinline__ double2 lds_theta(uint32_t th_base, uint32_t xy) {
+    double2 v;                                              // ((y & 15) * 16 + (x & 15)) * 16 bytes
+    const uint32_t a = th_base + ((((xy >> 12) & 0xf0u) | (xy & 0xfu)) << 4);
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
 }
 
 // Destination images of the flush.  Single GPU: the plan's own fixed-point image.  Event split with peer access: the images
@@ -180,13 +267,35 @@ __device__ __forceinline__ double2 event_theta(const double2* __restrict__ th_s,
 constexpr int kMaxPeers = 8;
 struct FixDst { unsigned long long* p[kMaxPeers]; int n; };
 
-// cold path of the splat: an event whose patch leaves its window adds its taps to the global images one by one, with the
-// reference's index rule (out of line: keeps the hot loop small - the kernel was instruction-cache bound with it inlined)
+// float64 warp of one event, shared by the hot loops and the cold paths (event_warpers.py:34-35: x' = x - (theta * dt) * 1.0).
+// rint() and the int conversion use the 2^52 magic constant (two DADDs instead of F2I + I2F on the slow conversion pipe): for
+// |x'| < 2^31, (x' + M) - M == rint(x') under round-half-to-even and the low word of (x' + M) is that integer.
+struct Hit2 { double xw, yw; int rx, ry; float fx, fy; };
+
+__device__ __forceinline__ Hit2 warp_hit2(uint32_t xy, double2 th, double dt) {
+    constexpr double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+    Hit2 h;
+    h.xw = __dsub_rn((double)(xy & 0xffffu), __dmul_rn(th.x, dt));
+    h.yw = __dsub_rn((double)(xy >> 16), __dmul_rn(th.y, dt));
+    const double sx = __dadd_rn(h.xw, kMagic), sy = __dadd_rn(h.yw, kMagic);
+    h.rx = __double2loint(sx);
+    h.ry = __double2loint(sy);
+    h.fx = (float)__dsub_rn(h.xw, __dsub_rn(sx, kMagic));
+    h.fy = (float)__dsub_rn(h.yw, __dsub_rn(sy, kMagic));
+    return h;
+}
+
+// cold path of the splat: an event whose patch leaves its window (or whose warp is not finite) adds its taps to the global
+// images one by one, with the reference's index rule; non-finite / absurdly far warps are dropped (every tap is out of range
+// under either index rule).  Out of line and self-contained: the hot loop keeps no state alive for it.
 template <bool WRAP>
-__device__ __noinline__ void splat_fallback(const FixDst& dst, int64_t img_off, int rx, int ry, const TapsFix& t, int H, int W) {
+__device__ __noinline__ void splat_fallback(const FixDst& dst, int64_t img_off, uint32_t xy, double2 th, double dt, int H, int W) {
+    const Hit2 h = warp_hit2(xy, th, dt);
+    if (!((fabs(h.xw) < 1.0e9) && (fabs(h.yw) < 1.0e9))) return;
+    const TapsFix t = taps_fix(h.fx, h.fy);
     for (int j = 0; j < 3; ++j)
         for (int i = 0; i < 3; ++i) {
-            int rr = ry + j - 1, cc = rx + i - 1;
+            int rr = h.ry + j - 1, cc = h.rx + i - 1;
             if (drop_index<WRAP>(rr, cc, H, W)) {
                 const int64_t off = img_off + (int64_t)rr * W + cc;
 #pragma unroll 1
@@ -195,149 +304,160 @@ __device__ __noinline__ void splat_fallback(const FixDst& dst, int64_t img_off, 
         }
 }
 
+// d loss / d x', d loss / d y' of one warped event from the nine cotangent cells d[] (already scaled by 1 / 2 pi):
+// separable evaluation  wx_i = exp(-0.5 (i - fx)^2), s_j = sum_i D_ij wx_i, sx_j = sum_i D_ij wx_i (i - fx)
+//   dL/dx' = sum_j wy_j sx_j,   dL/dy' = sum_j wy_j (j - fy) s_j
+__device__ __forceinline__ void tap_gradient(const float (&d)[9], float fx, float fy, float& gx, float& gy) {
+    float wx[3], wy[3];
+    axis_exp3(fx, wx);
+    axis_exp3(fy, wy);
+    const float ux0 = wx[0] * (-1.f - fx), ux1 = -fx * wx[1], ux2 = wx[2] * (1.f - fx);
+    float sj[3], sxj[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        sj[j] = fmaf(d[j * 3 + 0], wx[0], fmaf(d[j * 3 + 2], wx[2], d[j * 3 + 1] * wx[1]));
+        sxj[j] = fmaf(d[j * 3 + 0], ux0, fmaf(d[j * 3 + 2], ux2, d[j * 3 + 1] * ux1));
+    }
+    gx = fmaf(wy[0], sxj[0], fmaf(wy[2], sxj[2], wy[1] * sxj[1]));
+    gy = fmaf(wy[0] * (-1.f - fy), sj[0], fmaf(wy[2] * (1.f - fy), sj[2], -fy * wy[1] * sj[1]));
+}
+
+// cold path of the backward pass: gathers the nine cotangent cells from the global image with the reference's index rule
 template <bool WRAP>
-__device__ __noinline__ void gather_fallback(const float* __restrict__ img, int rx, int ry, int H, int W, float (&d)[9]) {
+__device__ __noinline__ float2 gather_fallback(const float* __restrict__ img, uint32_t xy, double2 th, double dt, int H, int W) {
+    const Hit2 h = warp_hit2(xy, th, dt);
+    if (!((fabs(h.xw) < 1.0e9) && (fabs(h.yw) < 1.0e9))) return make_float2(0.f, 0.f);
+    float d[9];
     for (int j = -1; j <= 1; ++j)
         for (int i = -1; i <= 1; ++i) {
-            int rr = ry + j, cc = rx + i;
+            int rr = h.ry + j, cc = h.rx + i;
             d[(j + 1) * 3 + (i + 1)] = drop_index<WRAP>(rr, cc, H, W) ? __ldg(img + (int64_t)rr * W + cc) : 0.f;
         }
+    float gx, gy;
+    tap_gradient(d, h.fx, h.fy, gx, gy);
+    return make_float2(gx, gy);
 }
 
 // ---- forward -----------------------------------------------------------------------------------------------------
-// One CTA per chunk (grid-stride), RB reference times per pass with one window each.  Per pass: zero the windows, measure
-// the bounding rectangles (float32 pre-pass), vote, flush.  A thread walks its kEvK consecutive events per reference time and
-// merges a vote into the next one when both have the same centre cell (events of one source pixel are time-sorted, so this is
-// common): the nine pending tap sums stay in registers and are only sent to shared memory when the centre changes.  The merge
-// is branch-free (predicated adds / predicated reductions), so diverging lanes cost nothing extra.
+// One CTA per chunk (grid-stride), RB reference times per pass with one window each.  Per pass: the windows follow from the
+// theta range of the tile and the t range of the chunk (no pass over the events), are zeroed, voted into, and flushed.  The
+// vote loop is branch-free: an event that misses its window (or a padding sentinel) votes zeros into a fixed cell of the
+// window and is remembered in a bit mask; the rare misses are replayed through the out-of-line fallback afterwards.  Without
+// branches the compiler interleaves the independent (event, reference time) pairs of a thread.
 template <bool WRAP, int RB>
 __global__ void __launch_bounds__(256, 4)
-k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
+k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks,
+             const float2* __restrict__ chunk_tr, const unsigned int* __restrict__ n_chunks_dev,
              const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
              const __grid_constant__ FixDst dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
     extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
     __shared__ double2 th_s[kKeysPerTile];
-    __shared__ int sbox[8][RB][4];
+    __shared__ int sbox[8][4];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_chunks = (int)__ldg(n_chunks_dev);
+    const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(win);
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
         EventGroup ev;
-        load_chunk_events(ev_xy, ev_t, ch, ev);
-        tile_theta(T, ch.origin, H, W, th_s);
+        load_chunk_events<true>(ev_xy, ev_t, ch, ev);
+        tile_theta_range(tile_theta(T, ch.origin, H, W, th_s), sbox);
+        const bool active = (ev.xy[0] != kNoEvent);      // groups are padded at their end only
         for (int r0 = 0; r0 < R; r0 += RB) {
-            // zero the windows (whole capacity: a handful of 128-bit stores per thread)
-            for (int i = tid; i < RB * kWinCap / 4; i += 256) reinterpret_cast<uint4*>(win)[i] = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();                         // th_s ready (first pass); previous flush done
-            // pre-pass: bounding rectangle of the rounded warped pixels per reference time.  float32 arithmetic (error far
-            // below the 0.01 px margin for any flow a window can hold); an event the rectangle misses takes the fallback.
-            {
-                float lox[RB], loy[RB], hix[RB], hiy[RB], trf[RB];
-#pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    lox[r] = 3.0e9f; loy[r] = 3.0e9f; hix[r] = -3.0e9f; hiy[r] = -3.0e9f;
-                    trf[r] = (float)tref.t[min(r0 + r, EINCM_MAX_REFS - 1)];
-                }
-#pragma unroll
-                for (int k = 0; k < kEvK; ++k) {
-                    if (ev.xy[k] == kNoEvent) continue;
-                    const double2 th = event_theta(th_s, ev.xy[k]);
-                    const float xf = (float)(ev.xy[k] & 0xffffu), yf = (float)(ev.xy[k] >> 16), tf = (float)ev.t[k];
-                    const float thx = (float)th.x, thy = (float)th.y;
-#pragma unroll
-                    for (int r = 0; r < RB; ++r) {
-                        const float dt = tf - trf[r];
-                        const float xw = fmaf(-thx, dt, xf), yw = fmaf(-thy, dt, yf);
-                        lox[r] = fminf(lox[r], xw); hix[r] = fmaxf(hix[r], xw);
-                        loy[r] = fminf(loy[r], yw); hiy[r] = fmaxf(hiy[r], yw);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    // clamp (huge / non-finite flows end up in the fallback path anyway), widen by the rounding margin
-                    const int a = __float2int_rd(fmaxf(lox[r], -1.0e9f) - 0.51f), b = __float2int_rd(fmaxf(loy[r], -1.0e9f) - 0.51f);
-                    const int cx = __float2int_ru(fminf(hix[r], 1.0e9f) + 0.51f), d = __float2int_ru(fminf(hiy[r], 1.0e9f) + 0.51f);
-                    const int ra = __reduce_min_sync(0xffffffffu, a), rb = __reduce_min_sync(0xffffffffu, b);
-                    const int rc = __reduce_max_sync(0xffffffffu, cx), rd = __reduce_max_sync(0xffffffffu, d);
-                    if (lane == 0) { sbox[wid][r][0] = ra; sbox[wid][r][1] = rb; sbox[wid][r][2] = rc; sbox[wid][r][3] = rd; }
-                }
-            }
-            __syncthreads();
+            __syncthreads();                         // th_s / sbox ready (first pass); previous flush done
             if (tid < RB) {
-                int a = INT_MAX, b = INT_MAX, cmx = INT_MIN, d = INT_MIN;
+                Window wn = make_window(0, 0, 0, 0);
+                if (r0 + tid < R) {
+                    int ax = sbox[0][0], bx = sbox[0][1], ay = sbox[0][2], by = sbox[0][3];
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) {
-                    a = min(a, sbox[w8][tid][0]); b = min(b, sbox[w8][tid][1]);
-                    cmx = max(cmx, sbox[w8][tid][2]); d = max(d, sbox[w8][tid][3]);
+                    for (int w8 = 1; w8 < 8; ++w8) {
+                        ax = min(ax, sbox[w8][0]); bx = max(bx, sbox[w8][1]); ay = min(ay, sbox[w8][2]); by = max(by, sbox[w8][3]);
+                    }
+                    const float2 tr = __ldg(chunk_tr + c);
+                    const int x0 = (int)(ch.origin & 0xffffu), y0 = (int)(ch.origin >> 16);
+                    wn = chunk_window(x0, y0, min(x0 + kSortTile, W) - 1, min(y0 + kSortTile, H) - 1, ordered_float(ax), ordered_float(bx),
+                                      ordered_float(ay), ordered_float(by), tr.x, tr.y, tref.t[r0 + tid]);
+                    if (chunk_win != nullptr) chunk_win[(int64_t)c * R + r0 + tid] = make_int4(wn.ox, wn.oy, wn.pw, wn.ph);
                 }
-                const Window wn = make_window(a, b, cmx, d);
                 swin[tid] = wn;
-                if (chunk_win != nullptr && r0 + tid < R) chunk_win[(int64_t)c * R + r0 + tid] = make_int4(wn.ox, wn.oy, wn.pw, wn.ph);
             }
             __syncthreads();
-            // main pass
+            // zero the cells in use
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
-                if (r0 + r >= R) continue;
-                const Window wn = swin[r];
-                const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win + r * kWinCap);
-                const uint32_t pitch4 = (uint32_t)wn.pw * 4u;
-                const double tr = tref.t[r0 + r];
-                int acc[9];
-                uint32_t acc_addr = 0u;               // shared address of the pending centre cell; 0 = nothing pending
+                const int n4 = (swin[r].pw * swin[r].ph + 3) >> 2;
+                for (int i = tid; i < n4; i += 256) reinterpret_cast<uint4*>(win + r * kWinCap)[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncthreads();
+            // votes
+            uint32_t missed = 0u;                    // bit r * kEvK + k: event k missed the window of reference time r0 + r
+            if (active) {
 #pragma unroll
-                for (int q = 0; q < 9; ++q) acc[q] = 0;
+                for (int r = 0; r < RB; ++r) {
+                    if (r0 + r >= R) continue;
+                    const Window wn = swin[r];
+                    const uint32_t pitch4 = (uint32_t)wn.pw * 4u;
+                    const uint32_t wb = win_base + (uint32_t)(r * kWinCap - (wn.oy * wn.pw + wn.ox)) * 4u;   // address of cell (0, 0) of the image
+                    const uint32_t safe = win_base + (uint32_t)(r * kWinCap) * 4u + pitch4 + 4u;
+                    const double tr = tref.t[r0 + r];
 #pragma unroll
-                for (int k = 0; k < kEvK; ++k) {
-                    if (ev.xy[k] == kNoEvent) continue;
-                    const double2 th = event_theta(th_s, ev.xy[k]);
-                    const double xd = (double)(ev.xy[k] & 0xffffu), yd = (double)(ev.xy[k] >> 16);
-                    const Hit h = warp_hit(xd, yd, th.x, th.y, ev.t[k] - tr);
-                    if (!h.ok) continue;
-                    const TapsFix t = taps_fix(h.fx, h.fy);
-                    if (in_window(wn, h.rx, h.ry)) {
-                        const uint32_t addr = wbase + (uint32_t)((h.ry - wn.oy) * wn.pw + (h.rx - wn.ox)) * 4u;
-                        const bool same = addr == acc_addr;
-                        const bool emit = !same && acc_addr != 0u;
-                        // send the pending sums (other centre), then fold them into the new taps when the centre is the same
-                        if (emit) emit9(acc_addr, pitch4, acc);
-#pragma unroll
-                        for (int q = 0; q < 9; ++q) acc[q] = t.n[q] + (same ? acc[q] : 0);
-                        acc_addr = addr;
-                    } else {
-                        splat_fallback<WRAP>(dst, (int64_t)(r0 + r) * HW, h.rx, h.ry, t, H, W);
+                    for (int k = 0; k < kEvK; ++k) {
+                        const uint32_t xy = ev.xy[k];
+                        const Hit2 h = warp_hit2(xy, lds_theta(th_base, xy), ev.t[k] - tr);
+                        const bool valid = xy != kNoEvent;
+                        const bool hit = valid & (fabs(h.xw - wn.cx) < wn.hx) & (fabs(h.yw - wn.cy) < wn.hy);
+                        // a miss votes zeros: exp2(-(s * 1e4)^2) underflows to 0 for all three column factors
+                        const TapsFix t = taps_fix(hit ? h.fx : 1.0e4f, hit ? h.fy : 0.f);
+                        const uint32_t mid = hit ? wb + (uint32_t)(h.ry * wn.pw + h.rx) * 4u : safe;
+                        emit9(mid, pitch4, t.n);
+                        missed |= (valid & !hit) ? (1u << (r * kEvK + k)) : 0u;
                     }
                 }
-                if (acc_addr != 0u) emit9(acc_addr, pitch4, acc);
+            }
+            if (missed != 0u) {
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) {
+#pragma unroll 1
+                    for (int r = 0; r < RB; ++r)
+                        if ((missed >> (r * kEvK + k)) & 1u)
+                            splat_fallback<WRAP>(dst, (int64_t)(r0 + r) * HW, ev.xy[k], lds_theta(th_base, ev.xy[k]), ev.t[k] - tref.t[r0 + r], H, W);
+                }
             }
             __syncthreads();
-            // flush: non-zero window cells -> global fixed-point image (index rule applied here unless the window is interior)
+            // flush: non-zero window cells -> global fixed-point image (index rule applied here unless the window is interior).
+            // Four cells per thread and round (one 128-bit load); most cells of a window are zero.
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 if (r0 + r >= R) continue;
                 const Window wn = swin[r];
-                const uint32_t* wr = win + r * kWinCap;
+                const uint4* wr4 = reinterpret_cast<const uint4*>(win + r * kWinCap);
                 const int64_t img_off = (int64_t)(r0 + r) * HW;
                 const int cells = wn.pw * wn.ph;
                 const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
-                for (int i = tid; i < cells; i += 256) {
-                    const uint32_t v = wr[i];
-                    if (v != 0u) {
-                        int row, col;
-                        cell_to_rc(wn, i, row, col);
-                        int rr = wn.oy + row, cc = wn.ox + col;
-                        if (interior || drop_index<WRAP>(rr, cc, H, W)) {
-                            const int64_t off = img_off + (rr * W + cc);
+                const uint32_t inv_pw = wn.pw > 0 ? 0xffffffffu / (uint32_t)wn.pw + 1u : 0u;    // ceil(2^32 / pw): exact i / pw for i < 2^16
+                for (int i4 = tid; 4 * i4 < cells; i4 += 256) {
+                    const uint4 q = wr4[i4];
+                    if ((q.x | q.y | q.z | q.w) == 0u) continue;
+                    const uint32_t v4[4] = {q.x, q.y, q.z, q.w};
+                    int row = (int)__umulhi((uint32_t)(4 * i4), inv_pw);
+                    int col = 4 * i4 - row * wn.pw;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (v4[u] != 0u && 4 * i4 + u < cells) {
+                            int rr = wn.oy + row, cc = wn.ox + col;
+                            if (interior || drop_index<WRAP>(rr, cc, H, W)) {
+                                const int64_t off = img_off + (rr * W + cc);
 #pragma unroll 1
-                            for (int q = 0; q < dst.n; ++q) atomicAdd(dst.p[q] + off, (unsigned long long)v);
+                                for (int p = 0; p < dst.n; ++p) atomicAdd(dst.p[p] + off, (unsigned long long)v4[u]);
+                            }
                         }
+                        if (++col == wn.pw) { col = 0; ++row; }
                     }
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();                             // th_s / sbox / swin are rewritten for the next chunk
     }
 }
 
@@ -349,7 +469,8 @@ __global__ void k_fix_to_f64(const unsigned long long* __restrict__ fix, int64_t
 
 // ---- backward ----------------------------------------------------------------------------------------------------
 // Same chunks and windows as the forward pass of the same theta (chunk_win).  dwin holds d loss / d IWE / (2 pi) (float32)
-// of the window cells, zero where the index rule drops the cell.
+// of the window cells, zero where the index rule drops the cell.  Same branch-free structure as the forward pass: a miss
+// reads a fixed cell and contributes zero, the rare misses are replayed through the out-of-line gather afterwards.
 template <bool WRAP, int RB>
 __global__ void __launch_bounds__(256, 4)
 k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
@@ -360,24 +481,27 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_chunks = (int)__ldg(n_chunks_dev);
+    const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(dwin);
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
         EventGroup ev;
-        load_chunk_events(ev_xy, ev_t, ch, ev);
+        load_chunk_events<false>(ev_xy, ev_t, ch, ev);
         tile_theta(T, ch.origin, H, W, th_s);
+        const bool active = 4u * (unsigned)tid < ch.count;
         float ax[kEvK], ay[kEvK];
 #pragma unroll
         for (int k = 0; k < kEvK; ++k) { ax[k] = 0.f; ay[k] = 0.f; }
         for (int r0 = 0; r0 < R; r0 += RB) {
-            if (tid < RB && r0 + tid < R) {
-                const int4 q = chunk_win[(int64_t)c * R + r0 + tid];
-                Window wn{q.x, q.y, q.z, q.w, 0u};
-                if (q.z > 0) wn.inv_pw = 0xffffffffu / (uint32_t)q.z + 1u;
-                swin[tid] = wn;
+            if (r0 > 0) __syncthreads();             // previous readers of swin / dwin are done
+            if (tid < RB) {
+                int4 q = make_int4(0, 0, 0, 0);
+                if (r0 + tid < R) q = chunk_win[(int64_t)c * R + r0 + tid];
+                swin[tid] = make_window(q.x, q.y, q.z, q.w);
             }
             __syncthreads();
+            // window cells <- d loss / d IWE: all global loads of a round (four cells per thread) are issued before the stores
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 if (r0 + r >= R) continue;
@@ -386,13 +510,13 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
                 float* wr = dwin + r * kWinCap;
                 const int cells = wn.pw * wn.ph;
                 const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
-                for (int i0 = tid; i0 < cells; i0 += 4 * 256) {       // all global loads of a round first, then the stores
+                const uint32_t inv_pw = wn.pw > 0 ? 0xffffffffu / (uint32_t)wn.pw + 1u : 0u;
+                for (int i0 = tid; i0 < cells; i0 += 4 * 256) {
                     float v[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int i = i0 + u * 256;
-                        int row, col;
-                        cell_to_rc(wn, min(i, cells - 1), row, col);
+                        const int row = (int)__umulhi((uint32_t)min(i, cells - 1), inv_pw), col = min(i, cells - 1) - row * wn.pw;
                         int rr = wn.oy + row, cc = wn.ox + col;
                         v[u] = (i < cells && (interior || drop_index<WRAP>(rr, cc, H, W))) ? __ldg(img + (rr * W + cc)) : 0.f;
                     }
@@ -404,51 +528,54 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
                 }
             }
             __syncthreads();
+            uint32_t missed = 0u;
+            if (active) {
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                if (r0 + r >= R) continue;
-                const Window wn = swin[r];
-                const float* wr = dwin + r * kWinCap;
-                const double tr = tref.t[r0 + r];
-                const float trf = (float)tr;
+                for (int r = 0; r < RB; ++r) {
+                    if (r0 + r >= R) continue;
+                    const Window wn = swin[r];
+                    const uint32_t pitch4 = (uint32_t)wn.pw * 4u;
+                    const uint32_t wb = win_base + (uint32_t)(r * kWinCap - (wn.oy * wn.pw + wn.ox)) * 4u;
+                    const uint32_t safe = win_base + (uint32_t)(r * kWinCap) * 4u + pitch4 + 4u;
+                    const double tr = tref.t[r0 + r];
 #pragma unroll
-                for (int k = 0; k < kEvK; ++k) {
-                    if (ev.xy[k] == kNoEvent) continue;
-                    const double2 th = event_theta(th_s, ev.xy[k]);
-                    const double xd = (double)(ev.xy[k] & 0xffffu), yd = (double)(ev.xy[k] >> 16);
-                    const Hit h = warp_hit(xd, yd, th.x, th.y, ev.t[k] - tr);
-                    if (!h.ok) continue;
-                    float d[9];
-                    if (in_window(wn, h.rx, h.ry)) {
-                        const float* p = wr + (h.ry - wn.oy) * wn.pw + (h.rx - wn.ox);
-#pragma unroll
-                        for (int j = -1; j <= 1; ++j)
-#pragma unroll
-                            for (int i = -1; i <= 1; ++i) d[(j + 1) * 3 + (i + 1)] = p[j * wn.pw + i];
-                    } else {
-                        gather_fallback<WRAP>(dldi32 + (int64_t)(r0 + r) * HW, h.rx, h.ry, H, W, d);
+                    for (int k = 0; k < kEvK; ++k) {
+                        const uint32_t xy = ev.xy[k];
+                        const double dt = ev.t[k] - tr;
+                        const Hit2 h = warp_hit2(xy, lds_theta(th_base, xy), dt);
+                        const bool valid = xy != kNoEvent;
+                        const bool hit = valid & (fabs(h.xw - wn.cx) < wn.hx) & (fabs(h.yw - wn.cy) < wn.hy);
+                        const uint32_t mid = hit ? wb + (uint32_t)(h.ry * wn.pw + h.rx) * 4u : safe;
+                        const uint32_t up = mid - pitch4, dn = mid + pitch4;
+                        float d[9];
+                        asm volatile("ld.shared.f32 %0, [%9 + -4];\n\tld.shared.f32 %1, [%9];\n\tld.shared.f32 %2, [%9 + 4];\n\t"
+                                     "ld.shared.f32 %3, [%10 + -4];\n\tld.shared.f32 %4, [%10];\n\tld.shared.f32 %5, [%10 + 4];\n\t"
+                                     "ld.shared.f32 %6, [%11 + -4];\n\tld.shared.f32 %7, [%11];\n\tld.shared.f32 %8, [%11 + 4];"
+                                     : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]), "=f"(d[8])
+                                     : "r"(up), "r"(mid), "r"(dn));
+                        float gx, gy;
+                        tap_gradient(d, hit ? h.fx : 0.f, hit ? h.fy : 0.f, gx, gy);
+                        const float ndt = -(float)dt;
+                        // a miss may have read anything (and a padding sentinel has no timestamp): select, do not multiply by zero
+                        ax[k] = hit ? fmaf(ndt, gx, ax[k]) : ax[k];
+                        ay[k] = hit ? fmaf(ndt, gy, ay[k]) : ay[k];
+                        missed |= (valid & !hit) ? (1u << (r * kEvK + k)) : 0u;
                     }
-                    // separable evaluation: wx_i = exp(-0.5 (i - fx)^2), s_j = sum_i D_ij wx_i, sx_j = sum_i D_ij wx_i (i - fx)
-                    //   dL/dx' = sum_j wy_j sx_j,   dL/dy' = sum_j wy_j (j - fy) s_j        (D already carries 1/(2 pi))
-                    const float fx = h.fx, fy = h.fy;
-                    float wx[3], wy[3];
-                    axis_exp3(fx, wx);
-                    axis_exp3(fy, wy);
-                    const float ux0 = wx[0] * (-1.f - fx), ux1 = -fx * wx[1], ux2 = wx[2] * (1.f - fx);
-                    float sj[3], sxj[3];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        sj[j] = fmaf(d[j * 3 + 0], wx[0], fmaf(d[j * 3 + 2], wx[2], d[j * 3 + 1] * wx[1]));
-                        sxj[j] = fmaf(d[j * 3 + 0], ux0, fmaf(d[j * 3 + 2], ux2, d[j * 3 + 1] * ux1));
-                    }
-                    const float gx = fmaf(wy[0], sxj[0], fmaf(wy[2], sxj[2], wy[1] * sxj[1]));
-                    const float gy = fmaf(wy[0] * (-1.f - fy), sj[0], fmaf(wy[2] * (1.f - fy), sj[2], -fy * wy[1] * sj[1]));
-                    const float dtf = (float)ev.t[k] - trf;
-                    ax[k] = fmaf(-dtf, gx, ax[k]);
-                    ay[k] = fmaf(-dtf, gy, ay[k]);
                 }
             }
-            __syncthreads();
+            if (missed != 0u) {
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) {
+#pragma unroll 1
+                    for (int r = 0; r < RB; ++r)
+                        if ((missed >> (r * kEvK + k)) & 1u) {
+                            const double dt = ev.t[k] - tref.t[r0 + r];
+                            const float2 g = gather_fallback<WRAP>(dldi32 + (int64_t)(r0 + r) * HW, ev.xy[k], lds_theta(th_base, ev.xy[k]), dt, H, W);
+                            ax[k] = fmaf(-(float)dt, g.x, ax[k]);
+                            ay[k] = fmaf(-(float)dt, g.y, ay[k]);
+                        }
+                }
+            }
         }
         // per-thread runs of equal source pixel: all but the last run go straight to G
         uint32_t run_xy = ev.xy[0];
@@ -472,6 +599,7 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
         const uint32_t prev = __shfl_up_sync(0xffffffffu, run_xy, 1);
         const bool head = (lane == 0) || (prev != run_xy);
         if (head && run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
+        __syncthreads();                             // th_s / swin / dwin are rewritten for the next chunk
     }
 }
 

@@ -52,9 +52,11 @@ def main(path, kernel, top=40):
         total_samp += samp
     print(f'# {first_kernel}\n# total warp instructions {total_inst}, stall samples {total_samp}')
     print(f'{"file:line":34s} {"inst":>10s} {"inst%":>6s} {"samples%":>8s}  source')
-    for (f, ln), (inst, samp, src) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    by = 1 if '--by-samples' in sys.argv else 0
+    for (f, ln), (inst, samp, src) in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
         print(f'{f + ":" + str(ln):34s} {inst:10d} {100.0 * inst / max(total_inst, 1):6.2f} {100.0 * samp / max(total_samp, 1):8.2f}  {src[:110]}')
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    main(args[0], args[1], int(args[2]) if len(args) > 2 else 40)
