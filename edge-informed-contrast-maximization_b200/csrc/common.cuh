@@ -104,6 +104,15 @@ __device__ __forceinline__ double sign_of(double v) { return (v > 0.0) ? 1.0 : (
 
 // Index rule of `frame.at[r, c].add(v, mode='drop')` (reference src/utils/event_utils.py:59):
 // negative indices in [-N, -1] wrap (NumPy-style normalisation), anything still outside [0, N) is dropped.
+// float32 form for cotangents that only exist in float32 (k_image_stats): same order of operations
+__device__ __forceinline__ float scharr_adjoint_rows_f32(const float* xu, const float* xm, const float* xd, const float* yu, const float* yd) {
+    const float ax = __fadd_rn(__fadd_rn(__fmul_rn(3.f, __fsub_rn(xu[-1], xu[1])), __fmul_rn(10.f, __fsub_rn(xm[-1], xm[1]))),
+                               __fmul_rn(3.f, __fsub_rn(xd[-1], xd[1])));
+    const float ay = __fadd_rn(__fadd_rn(__fmul_rn(3.f, __fsub_rn(yu[-1], yd[-1])), __fmul_rn(10.f, __fsub_rn(yu[0], yd[0]))),
+                               __fmul_rn(3.f, __fsub_rn(yu[1], yd[1])));
+    return __fadd_rn(ax, ay);
+}
+
 template <bool WRAP>
 __device__ __forceinline__ bool drop_index(int& r, int& c, int H, int W) {
     if (WRAP) {

@@ -58,12 +58,12 @@ struct eincm_plan {
     int n_peers = 0;                                // 0: no peer access (the caller all-reduces the float64 images)
     cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
     size_t host_ng = 0;                  // gradient doubles of the host evaluation in flight (host_enqueue -> host_collect)
-    unsigned long long* img_dbg = nullptr;   // EINCM_IMAGE_PASS_STAMPS=1: phase time stamps of the image pass (profiling aid)
     bool host_delivered = false;  // the last backward pass wrote its results into the mapped host buffer itself
     double* h_mapped_dev = nullptr;   // device alias of h_pinned (cudaHostAllocMapped)
+    bool dldi_stale = false;      // plan->dldi does not hold the last evaluation's d loss / d IWE yet (fused path: built on demand)
     bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
     struct CoopCfg { int ctas = 0, band_rows = 0; };
-    CoopCfg coop_cfg[EINCM_MAX_REFS + 1];   // grid / sub-band height of k_image_pass per number of reference images (lazy)
+    CoopCfg coop_cfg[EINCM_MAX_REFS + 1];   // grid / sub-band height of k_image_stats per number of reference images (lazy)
     bool coop_ok = false;         // the sensor is narrow enough for the row-band cooperative image pass
     bool fused_pending = false;   // the last forward left the fixed-point images for the fused image pass (no float64 copy yet)
     RefTimes tref{};
@@ -81,6 +81,7 @@ struct eincm_plan {
     unsigned int *counts = nullptr, *cursor = nullptr, *tile_cnt = nullptr, *tile_start = nullptr, *chunk_first = nullptr, *totals = nullptr;
     Chunk* chunks = nullptr;
     int4* chunk_win = nullptr;                         // [chunk_cap][max_refs] windows of the last forward pass
+    float* adj32 = nullptr;                            // [max_refs][H*W] adjoint of the Scharr pair applied to (Gx, Gy) (k_image_stats -> k_image_grad)
     float2* chunk_tr = nullptr;                        // [chunk_cap] t range of the events of every chunk (per window)
     unsigned long long* iwe_fix = nullptr;             // [max_refs][H*W] fixed-point images of warped events
     int n_keys = 0, tiles_x = 0;
@@ -213,15 +214,15 @@ __global__ void k_set_weights(DevScalars* sc, RefTimes w, int R) {
     if (threadIdx.x < EINCM_MAX_REFS) sc->weights[threadIdx.x] = threadIdx.x < R ? w.t[threadIdx.x] : 0.0;
 }
 
-// instantiation of the cooperative image pass for a sensor width (columns per thread is a template parameter)
+// instantiation of the row-band image statistics kernel for a sensor width (columns per thread is a template parameter)
 const void* image_pass_kernel(int W) {
     switch ((W + kBandNT - 1) / kBandNT) {
-        case 1: return (const void*)k_image_pass<1>;
-        case 2: return (const void*)k_image_pass<2>;
-        case 3: return (const void*)k_image_pass<3>;
-        case 4: return (const void*)k_image_pass<4>;
-        case 5: return (const void*)k_image_pass<5>;
-        default: return (const void*)k_image_pass<6>;
+        case 1: return (const void*)k_image_stats<1>;
+        case 2: return (const void*)k_image_stats<2>;
+        case 3: return (const void*)k_image_stats<3>;
+        case 4: return (const void*)k_image_stats<4>;
+        case 5: return (const void*)k_image_stats<5>;
+        default: return (const void*)k_image_stats<6>;
     }
 }
 
@@ -357,6 +358,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
 int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, double* dalpha_out, cudaStream_t st,
                   double* host_out = nullptr) {
     plan->host_delivered = false;
+    plan->dldi_stale = false;
     int rc = check_hp(plan, hp);
     if (rc) return rc;
     if (!plan->forward_done) return fail(plan, EINCM_ESTATE, "eincm_backward before eincm_forward_events");
@@ -382,10 +384,10 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             LAUNCH("k_tv", k_tv<<<gridV, blockV, 0, st>>>(plan->theta_full, plan->mask, H, W, gridV.x * gridV.y, plan->Gtv, plan->part, plan->sc));
         }
         const int tvb = ((W + kTvTX - 1) / kTvTX) * ((H + kTvTY - 1) / kTvTY);
-        ImagePassArgs ia{};
-        ia.fix = plan->iwe_fix; ia.edges = plan->edges; ia.iwe = plan->iwe;
+        ImageStatsArgs ia{};
+        ia.fix = plan->iwe_fix; ia.edges = plan->edges; ia.iwe = plan->iwe; ia.adj32 = plan->adj32;
         ia.part = plan->part + 2 * tvb;                          // k_tv's partials live at the start of `part`
-        ia.sc = plan->sc; ia.dldi = plan->dldi; ia.dldi32 = plan->dldi32; ia.loss_out = loss_out;
+        ia.sc = plan->sc; ia.loss_out = loss_out;
         ia.zero_buf = want_grad ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
         g_zeroed = want_grad;
         if (want_grad && h * w <= kGatherMaxTiles) {
@@ -393,28 +395,34 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             g_zeroed_grad = true;
         }
         ia.H = H; ia.W = W; ia.R = R;
-        ia.dbg = plan->img_dbg;
-        ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0; ia.want_grad = want_grad ? 1 : 0;
-        // grid and sub-band height: as many co-resident CTAs as fit (at most 2 per SM), each ideally holding its whole row
-        // band in shared memory (one sub-band)
+        ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0;
+        // grid and sub-band height: two CTAs per SM, each ideally holding its whole row band in shared memory (one sub-band)
         eincm_plan::CoopCfg& cc = plan->coop_cfg[R];
         if (cc.ctas == 0) {
-            const int target = std::max(1, std::min(plan->sm_count * 2, (R * H + 3) / 4));          // >= 4 rows per CTA
+            const int k_per_sm = 2;
+            const int target = std::max(1, std::min(plan->sm_count * k_per_sm, (R * H + 1) / 2));          // >= 2 rows per CTA
             int B = std::min(kBandRowsMax, std::max(2, (R * H + target - 1) / target));
             int per_sm = 0;
             for (;; --B) {
                 cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_pass_kernel(W), kBandNT, image_pass_smem_bytes(W, B));
                 if (eo != cudaSuccess) return fail(plan, EINCM_ECUDA, "occupancy query of the image pass: %s", cudaGetErrorString(eo));
-                if (per_sm >= 2 || B <= 2) break;
+                if (per_sm >= k_per_sm || B <= 2) break;
             }
-            if (per_sm < 1) return fail(plan, EINCM_ECUDA, "the cooperative image pass does not fit this device for W = %d", W);
+            if (per_sm < 1) return fail(plan, EINCM_ECUDA, "the image statistics kernel does not fit this device for W = %d", W);
             cc.band_rows = B;
-            cc.ctas = std::max(1, std::min(target, per_sm * plan->sm_count));
+            cc.ctas = target;
         }
         ia.band_rows = cc.band_rows;
-        void* kargs[] = {(void*)&ia};
-        LAUNCH("k_image_pass", cudaLaunchCooperativeKernel(image_pass_kernel(W), dim3(cc.ctas), dim3(kBandNT), kargs,
-                                                           image_pass_smem_bytes(W, cc.band_rows), st));
+        {
+            typedef void (*stats_fn)(const ImageStatsArgs);
+            stats_fn fn = (stats_fn)image_pass_kernel(W);
+            LAUNCH("k_image_stats", fn<<<cc.ctas, kBandNT, image_pass_smem_bytes(W, cc.band_rows), st>>>(ia));
+        }
+        ImageGradArgs ga{};
+        ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
+        ga.dldi = nullptr; ga.dldi32 = plan->dldi32; ga.HW = (int)plan->HW; ga.R = R; ga.want_grad = want_grad ? 1 : 0;
+        plan->dldi_stale = want_grad;                            // the float64 copy (debug tap) is produced on demand: eincm_dldi_ptr
+        LAUNCH("k_image_grad", k_image_grad<<<std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8)), 256, 0, st>>>(ga));
         plan->fused_pending = false;
         plan->fix_clean = true;                                  // the pass clears the cells it has read
         if (!want_grad) return EINCM_OK;
@@ -549,17 +557,15 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     plan->exact = (flags & EINCM_FLAG_EXACT_F64) != 0;
     plan->sm_count = prop.multiProcessorCount;
     {
-        int per_sm = 0;
-        // the cooperative image pass keeps whole rows in shared memory; very wide sensors use the unfused image kernels
+        // the row-band image kernel keeps whole rows in shared memory; very wide sensors use the unfused image kernels
         const size_t smem_img = image_pass_smem_bytes(W, 2);
         plan->coop_ok = W <= kMaxCPT * kBandNT && smem_img <= (size_t)prop.sharedMemPerBlockOptin;
         if (plan->coop_ok) {
             if ((e = cudaFuncSetAttribute(image_pass_kernel(W), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess) {
                 delete plan;
-                return fail(nullptr, EINCM_ECUDA, "shared-memory opt-in of the cooperative image pass failed (%s)", cudaGetErrorString(e));
+                return fail(nullptr, EINCM_ECUDA, "shared-memory opt-in of the image statistics kernel failed (%s)", cudaGetErrorString(e));
             }
         }
-        (void)per_sm;
     }
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
     plan->n_tiles = plan->tiles_x * ((H + kSortTile - 1) / kSortTile);
@@ -589,6 +595,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->dldi, RR * HW)); CU(dmalloc(&plan->edges, RR * HW));
         if (!plan->exact) {
             CU(dmalloc(&plan->dldi32, RR * HW));
+            CU(dmalloc(&plan->adj32, RR * HW));
             CU(dmalloc(&plan->iwe_fix, RR * HW));
             CU(dmalloc(&plan->chunk_win, (size_t)plan->chunk_cap * RR));
         }
@@ -601,9 +608,6 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(cudaHostAlloc((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double), cudaHostAllocMapped));
         CU(cudaHostGetDevicePointer((void**)&plan->h_mapped_dev, plan->h_pinned, 0));
         CU(cudaStreamCreateWithFlags(&plan->own_stream, cudaStreamNonBlocking));
-        if (const char* e = std::getenv("EINCM_IMAGE_PASS_STAMPS")) {
-            if (e[0] == '1') { CU(dmalloc(&plan->img_dbg, 16)); CU(cudaMemset(plan->img_dbg, 0, 16 * sizeof(unsigned long long))); }
-        }
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
         return EINCM_OK;
     };
@@ -621,7 +625,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
     void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
-                    plan->chunk_first, plan->totals, plan->img_dbg, plan->chunks, plan->chunk_tr, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
+                    plan->chunk_first, plan->totals, plan->adj32, plan->chunks, plan->chunk_tr, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
@@ -949,7 +953,21 @@ int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_ho
 double* eincm_zero_iwe_ptr(eincm_plan* plan) { return plan ? plan->zero_iwe : nullptr; }
 double* eincm_iwe_ptr(eincm_plan* plan) { return plan ? plan->iwe : nullptr; }
 uint8_t* eincm_mask_ptr(eincm_plan* plan) { return plan ? plan->mask : nullptr; }
-double* eincm_dldi_ptr(eincm_plan* plan) { return plan ? plan->dldi : nullptr; }
+double* eincm_dldi_ptr(eincm_plan* plan) {
+    if (!plan) return nullptr;
+    if (plan->dldi_stale) {
+        // the fused image pass only writes the float32 copy the event kernels read: rebuild the float64 image of the last evaluation
+        // from the same operands (debug tap: synchronous)
+        if (cudaSetDevice(plan->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+        ImageGradArgs ga{};
+        ga.fix = nullptr; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
+        ga.dldi = plan->dldi; ga.dldi32 = nullptr; ga.HW = (int)plan->HW; ga.R = plan->R; ga.want_grad = 1;
+        k_image_grad<<<std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8)), 256>>>(ga);
+        if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+        plan->dldi_stale = false;
+    }
+    return plan->dldi;
+}
 double* eincm_theta_full_ptr(eincm_plan* plan) {
     if (!plan) return nullptr;
     // debug tap: the default path does not materialise the dense field - do it now (synchronous, legacy default stream)
@@ -1067,15 +1085,6 @@ int eincm_split_window_images(eincm_plan* plan, void* cuda_stream) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // after the barrier: this rank's fixed-point image 0 holds the complete zero-warp image of the window
     LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((plan->HW + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, plan->HW, plan->zero_iwe));
-    return EINCM_OK;
-}
-
-int eincm_debug_image_pass_stamps(eincm_plan* plan, unsigned long long* out_host /* [6] */) {
-    if (!plan || !out_host) return EINCM_EINVAL;
-    if (!plan->img_dbg) return fail(plan, EINCM_ESTATE, "set EINCM_IMAGE_PASS_STAMPS=1 before creating the plan");
-    CU(cudaSetDevice(plan->device));
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out_host, plan->img_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return EINCM_OK;
 }
 

@@ -355,7 +355,7 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
     __shared__ int sbox[8][4];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     const int n_chunks = (int)__ldg(n_chunks_dev);
     const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(win);
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
@@ -481,7 +481,7 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int n_chunks = (int)__ldg(n_chunks_dev);
     const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(dwin);
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {

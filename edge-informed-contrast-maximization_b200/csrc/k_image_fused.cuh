@@ -1,7 +1,7 @@
-// Fused image-space pass of the default (tile-privatised splat, delta == 0, single GPU) path: two kernels per evaluation
+// Fused image-space pass of the default (tile-privatised splat, delta == 0) path: two kernels per evaluation
 // instead of compose + A + scalars + B + scalars + C.
 //
-//   k_image_pass: fixed-point image -> float64 image of warped events, Scharr contrast, min / max with
+//   k_image_stats: fixed-point image -> float64 image of warped events, Scharr contrast, min / max with
 //                 tie counts, and the moments  sum I, sum I^2, sum E*I  from which the min-max-normalised MSE and the sums of
 //                 its backward follow algebraically once the GLOBAL min / max are known:
 //                     N = (I - m)/D,  D = max - m + eps
@@ -10,9 +10,11 @@
 //                     s2 = sum gN(I-m)= cb ((sum EI - m sum E) - Q/D)
 //                 so no second pass over the images is needed for the statistics (reference: src/utils/img_utils.py:24-25,
 //                 src/eincm/objectives/correlation_objectives.py:25-26, contrast_objectives.py:22-25, src/eincm/losses.py:171-193);
-//                 then d loss / d IWE (float64 + float32/2pi copies), as k_img_C.
+//                 It also applies the adjoint of the Scharr pair to (Gx, Gy) - the part of d loss / d IWE that does not depend on
+//                 the global statistics - and its last CTA reduces the per-CTA partials and evaluates the loss.
+//   k_image_grad:  pointwise  d loss / d IWE = cA * adjoint + gN / D + min/max tie terms  (float64 + float32/2pi copies, as
+//                 k_img_C), and clears the fixed-point images for the next evaluation.
 #pragma once
-#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "k_events_tile.cuh"
@@ -69,44 +71,38 @@ __device__ __forceinline__ FusedAcc fused_block_reduce(FusedAcc a, double (*sh)[
     return a;
 }
 
-// ---- the cooperative image pass -------------------------------------------------------------------------------------------
-// One persistent cooperative kernel (grid = min(2 x SMs, tiles), all CTAs co-resident) does the whole image-space part of an
-// evaluation:
-//   phase 1  every CTA walks its contiguous share of the R x tiles work list: fixed-point image -> float64 image (written out
-//            for phase 3 and for the debug taps), the fixed-point cells are cleared for the next evaluation (no memset launch),
-//            per-thread statistics are accumulated over all its pixels and reduced ONCE per (CTA, reference image);
-//   barrier  grid-wide;
-//   phase 2  every CTA reduces the per-CTA partials of the reference images it owns in the same fixed order (identical,
-//            deterministic results everywhere - no serial "last CTA" tail); CTA 0 also evaluates the loss;
-//   phase 3  d loss / d IWE of the CTA's tiles.
+// ---- k_image_stats ---------------------------------------------------------------------------------------------------------
+// Row-band formulation: a CTA owns a contiguous run of complete image rows (R*H rows laid end to end are split evenly over the
+// grid) and handles it in sub-bands of <= band_rows rows.  A sub-band (plus two halo rows on either side and a zero column on
+// either side) is brought into shared memory with one burst of asynchronous copies - all loads of the CTA in flight at once -
+// and then processed without further global reads: a thread owns the same CPT columns (tid, tid + 256, ...) in every row, so
+// the 3x3 stencils need no index arithmetic, global traffic is perfectly coalesced row segments, and every thread accumulates
+// its statistics over all its pixels before the single block reduction per (CTA, reference image).  The last CTA to finish
+// (ticket) reduces the per-CTA partials of every reference image in a fixed order (deterministic) and evaluates the loss;
+// the kernel boundary before k_image_grad replaces the grid-wide barrier of a cooperative formulation (measured: launch of a
+// cooperative kernel + barrier + redundant second-level reduction cost more than the second launch).
 constexpr int kCoopMaxRefs = EINCM_MAX_REFS;
+constexpr int kBandNT = 256;
+constexpr int kMaxCPT = 6;                          // columns per thread (template parameter 1..6): sensors up to 1536 px wide
+constexpr int kBandRowsMax = 8;                     // rows of a sub-band (chosen by the host: ImageStatsArgs::band_rows)
+constexpr int kStatsTicket = 6;                     // DevScalars::counters slot of the "last CTA" ticket
 
-struct ImagePassArgs {
-    unsigned long long* fix;      // [R][H*W] fixed-point images of warped events (read, then cleared)
-    const double* edges;          // [R][H*W]
-    double* iwe;                  // [R][H*W] float64 images (written in phase 1, read in phase 3)
-    double* part;                 // [R][grid][kFPart]
+struct ImageStatsArgs {
+    const unsigned long long* fix;  // [R][H*W] fixed-point images of warped events
+    const double* edges;            // [R][H*W]
+    double* iwe;                    // [R][H*W] float64 images (out)
+    float* adj32;                   // [R][H*W] adjoint of the Scharr pair applied to (Gx, Gy) (out; d contrast / d IWE up to cA)
+    double* part;                   // [R][grid][kFPart]
     DevScalars* sc;
-    double* dldi;                 // [R][H*W] float64 d loss / d IWE (debug tap) or null
-    float* dldi32;                // [R][H*W] float32 d loss / d IWE / (2 pi)
     double* loss_out;
-    double* zero_buf;             // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
+    double* zero_buf;               // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
     double* zero_buf2;
     int n_zero, n_zero2;
     int H, W, R;
     double alpha, beta, gamma;
-    int use_tv, want_grad;
-    int band_rows;                // rows of a sub-band held in shared memory (<= kBandRowsMax; shared memory is sized for it)
-    unsigned long long* dbg;      // optional: %globaltimer stamps of CTA 0 at the phase boundaries (profiling aid) or null
+    int use_tv;
+    int band_rows;                  // rows of a sub-band held in shared memory (<= kBandRowsMax; shared memory is sized for it)
 };
-
-__device__ __forceinline__ void stamp(const ImagePassArgs& A, int slot) {
-    if (A.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        A.dbg[slot] = t;
-    }
-}
 
 __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double sE, double sE2, double cb) {
     Stats st;
@@ -123,16 +119,6 @@ __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double
     return st;
 }
 
-// Row-band formulation: a CTA owns a contiguous run of complete image rows (R*H rows laid end to end are split evenly over the
-// grid) and handles it in sub-bands of <= kBandRows rows.  A sub-band (plus two halo rows on either side and a zero column on
-// either side) is brought into shared memory with one burst of asynchronous copies - all loads of the CTA in flight at once -
-// and then processed without further global reads: a thread owns the same CPT columns (tid, tid + 256, ...) in every row, so
-// the 3x3 stencils need no index arithmetic, global traffic is perfectly coalesced row segments, and every thread accumulates
-// its statistics over all its pixels before the single block reduction per (CTA, reference image).
-constexpr int kBandNT = 256;
-constexpr int kMaxCPT = 6;                          // columns per thread (template parameter 1..6): sensors up to 1536 px wide
-constexpr int kBandRowsMax = 8;                     // rows of a sub-band (chosen by the host: ImagePassArgs::band_rows)
-
 // 8-byte asynchronous global -> shared copy; `valid == false` zero-fills (rows outside the image)
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -148,24 +134,24 @@ struct BandSmemTail {
     Stats st[kCoopMaxRefs];
     double coefA[kCoopMaxRefs], coefB[kCoopMaxRefs];
     double wts[kCoopMaxRefs], zero_mse[kCoopMaxRefs], sumE[kCoopMaxRefs], sumE2[kCoopMaxRefs], zero_contrast;
+    int is_last;
 };
 
-// image rows (halo 2) + Scharr pair of rows (halo 1, float32) + edge rows of a sub-band of B rows
+// image rows (halo 2) + Scharr pair of rows (halo 1, float32) of a sub-band of B rows
 __host__ __device__ inline size_t image_pass_smem_bytes(int W, int B) {
-    return (size_t)((B + 4) + (B + 2) + B) * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
+    return (size_t)((B + 4) + (B + 2)) * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
 }
 
 template <int CPT>
-__global__ void __launch_bounds__(kBandNT)
-k_image_pass(const ImagePassArgs A) {
+__global__ void __launch_bounds__(kBandNT, 2)
+k_image_stats(const ImageStatsArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = A.H, W = A.W, R = A.R, Wp = W + 2;
     const int B = A.band_rows;
     double* bandI = reinterpret_cast<double*>(smem_raw);             // [B + 4][Wp]: image rows sa-2 .. sa+B+1
-    float* gxs = reinterpret_cast<float*>(bandI + (B + 4) * Wp);     // [B + 2][Wp] Scharr x of rows sa-1 .. sa+B (phase 3)
+    float* gxs = reinterpret_cast<float*>(bandI + (B + 4) * Wp);     // [B + 2][Wp] Scharr x of rows sa-1 .. sa+B
     float* gys = gxs + (B + 2) * Wp;                                 // [B + 2][Wp] Scharr y
-    double* bandE = reinterpret_cast<double*>(gys + (B + 2) * Wp);   // [B][Wp] edge rows of the sub-band
-    BandSmemTail& S = *reinterpret_cast<BandSmemTail*>(bandE + B * Wp);
+    BandSmemTail& S = *reinterpret_cast<BandSmemTail*>(gys + (B + 2) * Wp);
     const int HW = H * W;
     const int tid = threadIdx.x;
     const int G = gridDim.x, b = blockIdx.x;
@@ -173,7 +159,6 @@ k_image_pass(const ImagePassArgs A) {
     const int row_begin = (int)(((long long)RH * b) / G), row_end = (int)(((long long)RH * (b + 1)) / G);
     const int r_first = row_begin < row_end ? row_begin / H : 0, r_last = row_begin < row_end ? (row_end - 1) / H : -1;
 
-    stamp(A, 0);
     // zero columns (never written afterwards), identity partials, accumulators of the event backward pass
     for (int k = tid; k < B + 4; k += kBandNT) { bandI[k * Wp] = 0.0; bandI[k * Wp + W + 1] = 0.0; }
     for (int k = tid; k < 2 * (B + 2); k += kBandNT) { gxs[k * Wp] = 0.f; gxs[k * Wp + W + 1] = 0.f; }
@@ -185,8 +170,8 @@ k_image_pass(const ImagePassArgs A) {
         for (int k = b * kBandNT + tid; k < A.n_zero; k += G * kBandNT) A.zero_buf[k] = 0.0;
     if (A.zero_buf2 != nullptr)
         for (int k = b * kBandNT + tid; k < A.n_zero2; k += G * kBandNT) A.zero_buf2[k] = 0.0;
-    // per-window constants of phase 2 (cotangent scales from the zero-warp image, losses.py:176-177): fetched now, their
-    // latency hides behind phase 1
+    // per-window constants of the tail (cotangent scales from the zero-warp image, losses.py:176-177): fetched now, their
+    // latency hides behind the band loop
     if (tid < R) {
         const double w = A.sc->weights[tid], zc = A.sc->zero[0].contrast, zm = A.sc->zero[tid].mse;
         const double a_r = -A.alpha * w / ((zc + kEps) * R);
@@ -197,71 +182,90 @@ k_image_pass(const ImagePassArgs A) {
         if (tid == 0) S.zero_contrast = zc;
     }
 
-    // asynchronous copy of image rows [y0, y1) of `src` (8-byte cells) into bandI, row y at slot y - slot0
-    auto copy_rows = [&](const void* src, int y0, int y1, int slot0) {
-        const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(src);
-        for (int y = y0; y < y1; ++y) {
-            double* dst = bandI + (y - slot0) * Wp + 1;
-            const bool in = y >= 0 && y < H;
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                if (x < W) cp_async8(dst + x, in ? (const void*)(s8 + y * W + x) : (const void*)s8, in);
-            }
-        }
-    };
-
-    stamp(A, 1);
-    // ---- phase 1: float64 image + statistics --------------------------------------------------------------------------
     for (int r = r_first; r <= r_last; ++r) {
         const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
         const unsigned long long* Fr = A.fix + r * HW;
         const double* Er = A.edges + r * HW;
         double* Ir = A.iwe + r * HW;
+        float* Ar = A.adj32 + r * HW;
         FusedAcc acc;
         acc.init();
         int cnt_mn = 0, cnt_mx = 0;                   // tie counts of the running min / max (integers: branch-free update)
         for (int sa = ya; sa < yb; sa += B) {
             const int sb = min(sa + B, yb);
             __syncthreads();                           // previous readers of the band are done
-            copy_rows(Fr, sa - 1, sb + 1, sa - 2);
-            for (int y = sa; y < sb; ++y) {            // edge rows, row y at slot y - sa
-                double* dst = bandE + (y - sa) * Wp + 1;
+            for (int y = sa - 2; y < sb + 2; ++y) {    // fixed-point rows sa-2 .. sb+1 -> bandI, row y at slot y - sa + 2
+                double* dst = bandI + (y - sa + 2) * Wp + 1;
+                const bool in = y >= 0 && y < H;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
-                    if (x < W) cp_async8(dst + x, Er + y * W + x, true);
+                    if (x < W) cp_async8(dst + x, in ? (const void*)(Fr + y * W + x) : (const void*)Fr, in);
                 }
             }
+            double e_next[CPT];                        // edge row of the next own row: register prefetch, one row ahead
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int x = tid + c * kBandNT;
+                e_next[c] = (x < W) ? __ldg(Er + sa * W + x) : 0.0;
+            }
             cp_async_commit_wait_all();
-            for (int y = sa - 1; y < sb + 1; ++y) {    // fixed point -> float64, each thread the cells it copied
+            for (int y = sa - 2; y < sb + 2; ++y) {    // fixed point -> float64, each thread the cells it copied
                 double* row = bandI + (y - sa + 2) * Wp + 1;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
-                    if (x < W) row[x] = (double)(long long)reinterpret_cast<const unsigned long long*>(row)[x] * kFixToIwe;
+                    // sums are far below 2^52: (2^52 | v) reinterpreted as float64 is exactly 2^52 + v
+                    if (x < W) row[x] = __dsub_rn(__longlong_as_double(0x4330000000000000ll | reinterpret_cast<const long long*>(row)[x]), 4503599627370496.0) * kFixToIwe;
                 }
             }
             __syncthreads();
-            for (int y = sa; y < sb; ++y) {
-                const double* mid = bandI + (y - sa + 2) * Wp + 1;
+            // Scharr pair of rows sa-1 .. sb (zero outside the image: the 'same' output only exists inside); statistics of the
+            // rows this CTA owns; float32 copies for the adjoint
+            for (int q = sa - 1; q <= sb; ++q) {
+                const double* mid = bandI + (q - sa + 2) * Wp + 1;
                 const double* up = mid - Wp;
                 const double* dn = mid + Wp;
-                const double* er = bandE + (y - sa) * Wp + 1;
+                float* gxr = gxs + (q - sa + 1) * Wp + 1;
+                float* gyr = gys + (q - sa + 1) * Wp + 1;
+                const bool inside = q >= 0 && q < H, own = q >= sa && q < sb;
+                double er[CPT];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) er[c] = e_next[c];
+                if (own && q + 1 < sb) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        const int x = tid + c * kBandNT;
+                        e_next[c] = (x < W) ? __ldg(Er + (q + 1) * W + x) : 0.0;
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
                     if (x < W) {
-                        double gx, gy;
-                        scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
-                        const double I = mid[x];
-                        Ir[y * W + x] = I;
-                        acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += er[x] * I;
-                        cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
-                        cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
-                        acc.mn = fmin(acc.mn, I);
-                        acc.mx = fmax(acc.mx, I);
+                        double gx = 0.0, gy = 0.0;
+                        if (inside) scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
+                        gxr[x] = (float)gx; gyr[x] = (float)gy;
+                        if (own) {
+                            const double I = mid[x];
+                            Ir[q * W + x] = I;
+                            acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += er[c] * I;
+                            cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
+                            cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
+                            acc.mn = fmin(acc.mn, I);
+                            acc.mx = fmax(acc.mx, I);
+                        }
                     }
+                }
+            }
+            __syncthreads();
+            for (int y = sa; y < sb; ++y) {
+                const float* xm = gxs + (y - sa + 1) * Wp + 1;
+                const float* ym = gys + (y - sa + 1) * Wp + 1;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int x = tid + c * kBandNT;
+                    if (x < W) Ar[y * W + x] = scharr_adjoint_rows_f32(xm - Wp + x, xm + x, xm + Wp + x, ym - Wp + x, ym + Wp + x);
                 }
             }
         }
@@ -272,13 +276,14 @@ k_image_pass(const ImagePassArgs A) {
             d[0] = a.sq; d[1] = a.sI; d[2] = a.sI2; d[3] = a.sEI; d[4] = a.mn; d[5] = a.cmn; d[6] = a.mx; d[7] = a.cmx;
         }
     }
-    stamp(A, 2);
-    __threadfence();
-    cooperative_groups::this_grid().sync();
-    stamp(A, 3);
 
-    // ---- phase 2: global statistics of every reference image, one WARP per image (no block-level synchronisation inside), the
-    // same fixed order in every CTA: identical, deterministic results everywhere; CTA 0 also evaluates the loss --------------
+    // ---- tail: the last CTA reduces the partials of every reference image (one WARP per image, fixed order) -----------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) S.is_last = atomicAdd(&A.sc->counters[kStatsTicket], 1u) == (unsigned)(G - 1);
+    __syncthreads();
+    if (!S.is_last) return;
+    __threadfence();
     {
         const int lane = tid & 31;
         for (int q = tid >> 5; q < R; q += kBandNT / 32) {
@@ -307,18 +312,14 @@ k_image_pass(const ImagePassArgs A) {
                     }
                 }
             }
-            if (q == 0) stamp(A, 6);
 #pragma unroll
             for (int o = 16; o; o >>= 1) a.merge(a.shfl_xor(o));
-            if (q == 0) stamp(A, 7);
             if (lane == 0) S.st[q] = fused_stats(a, (double)HW, S.sumE[q], S.sumE2[q], S.coefB[q]);
-            if (q == 0) stamp(A, 8);
         }
         __syncthreads();
-        stamp(A, 9);
-        if (b == 0 && tid == 0) {
+        if (tid == 0) {
             for (int q = 0; q < R; ++q) { A.sc->ref[q] = S.st[q]; A.sc->coefA[q] = S.coefA[q]; A.sc->coefB[q] = S.coefB[q]; A.sc->coefD[q] = 0.0; }
-            // final loss (reference src/eincm/losses.py:171-193) from operands prefetched before the barrier
+            // final loss (reference src/eincm/losses.py:171-193)
             double s_corr = 0.0, s_con = 0.0;
             for (int q = 0; q < R; ++q) {
                 s_corr += (S.wts[q] * (-S.st[q].mse)) / ((-S.zero_mse[q]) + kEps);          // losses.py:176
@@ -330,81 +331,72 @@ k_image_pass(const ImagePassArgs A) {
             A.sc->loss = loss; A.sc->mean_rel_corr = mean_rel_corr; A.sc->mean_rel_contrast = mean_rel_contrast;
             A.sc->mean_rel_div = 0.0; A.sc->tv = tv;
             if (A.loss_out != nullptr) *A.loss_out = loss;
+            A.sc->counters[kStatsTicket] = 0u;
         }
     }
+}
 
-    stamp(A, 4);
-    // ---- phase 3: clear the fixed-point rows; d loss / d IWE ---------------------------------------------------------------
-    for (int r = r_first; r <= r_last; ++r) {
-        const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
-        unsigned long long* Fr = A.fix + r * HW;
-        for (int k = ya * W + tid; k < yb * W; k += kBandNT) Fr[k] = 0ull;
-        if (!A.want_grad) continue;
-        const double* Er = A.edges + r * HW;
-        const double* Ir = A.iwe + r * HW;
-        const Stats st = S.st[r];
-        const double cA = S.coefA[r], cB = S.coefB[r];
+// ---- k_image_grad ----------------------------------------------------------------------------------------------------------
+// d loss / d IWE_r = cA_r * adjoint(Gx, Gy) + gN / D + (tie-split cotangents of min and max)   with   gN = cB_r (E - (I - m) / D)
+// (reverse mode of contrast_objectives.py:22-25, img_utils.py:24-25, correlation_objectives.py:25-26; min / max cotangents
+// split evenly among ties like jnp.min / jnp.max).  Pointwise: four cells per thread and round, loads batched.  Also clears the
+// fixed-point images (every reader has finished: kernel boundary).
+struct ImageGradArgs {
+    unsigned long long* fix;        // [R][H*W] cleared (null: left alone)
+    const double* edges;
+    const double* iwe;
+    const float* adj32;
+    const DevScalars* sc;
+    double* dldi;                   // [R][H*W] float64 d loss / d IWE (debug tap) or null
+    float* dldi32;                  // [R][H*W] float32 d loss / d IWE / (2 pi) or null
+    int HW, R;
+    int want_grad;                  // 0: only clear the fixed-point images
+};
+
+__global__ void __launch_bounds__(256)
+k_image_grad(const ImageGradArgs A) {
+    __shared__ double s_mn[kCoopMaxRefs], s_mx[kCoopMaxRefs], s_iD[kCoopMaxRefs], s_cA[kCoopMaxRefs], s_cB[kCoopMaxRefs], s_tm[kCoopMaxRefs], s_tM[kCoopMaxRefs];
+    if (threadIdx.x < A.R && A.want_grad) {
+        const Stats st = A.sc->ref[threadIdx.x];
+        s_mn[threadIdx.x] = st.mn; s_mx[threadIdx.x] = st.mx; s_iD[threadIdx.x] = 1.0 / st.D;
+        s_cA[threadIdx.x] = A.sc->coefA[threadIdx.x]; s_cB[threadIdx.x] = A.sc->coefB[threadIdx.x];
         const double g_M = -st.s2 / (st.D * st.D);
         const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
-        for (int sa = ya; sa < yb; sa += B) {
-            const int sb = min(sa + B, yb);
-            __syncthreads();                           // previous readers of the band are done
-            copy_rows(Ir, sa - 2, sb + 2, sa - 2);
-            for (int y = sa; y < sb; ++y) {
-                double* dst = bandE + (y - sa) * Wp + 1;
+        s_tm[threadIdx.x] = g_m / st.cnt_min; s_tM[threadIdx.x] = g_M / st.cnt_max;
+    }
+    __syncthreads();
+    const int T = gridDim.x * blockDim.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int r = 0; r < A.R; ++r) {
+        // 1 / D is a per-image constant: the two divisions of the reference formula become multiplications (one rounding more)
+        const double mn = s_mn[r], mx = s_mx[r], iD = s_iD[r], cA = s_cA[r], cBD = s_cB[r] * s_iD[r], tm = s_tm[r], tM = s_tM[r];
+        const double* Er = A.edges + (size_t)r * A.HW;
+        const double* Ir = A.iwe + (size_t)r * A.HW;
+        const float* Ar = A.adj32 + (size_t)r * A.HW;
+        for (int base = gt; base < A.HW; base += 4 * T) {
+            double I[4], E[4];
+            float a[4];
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    if (x < W) cp_async8(dst + x, Er + y * W + x, true);
-                }
+            for (int u = 0; u < 4; ++u) {
+                const int p = min(base + u * T, A.HW - 1);
+                if (A.want_grad) { I[u] = __ldcg(Ir + p); E[u] = __ldg(Er + p); a[u] = __ldcg(Ar + p); }
             }
-            cp_async_commit_wait_all();
-            __syncthreads();
-            // Scharr pair of rows sa-1 .. sb from the band rows (zero outside the image: 'same' output only exists inside);
-            // all rows and columns of a thread are independent
-            for (int q = sa - 1; q <= sb; ++q) {
-                const double* mid = bandI + (q - sa + 2) * Wp + 1;
-                const double* up = mid - Wp;
-                const double* dn = mid + Wp;
-                float* gxr = gxs + (q - sa + 1) * Wp + 1;
-                float* gyr = gys + (q - sa + 1) * Wp + 1;
-                const bool inside = q >= 0 && q < H;
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    if (x < W) {
-                        double gx = 0.0, gy = 0.0;
-                        if (inside) scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
-                        gxr[x] = (float)gx; gyr[x] = (float)gy;
-                    }
-                }
-            }
-            __syncthreads();
-            for (int y = sa; y < sb; ++y) {
-                const float* xm = gxs + (y - sa + 1) * Wp + 1;
-                const float* ym = gys + (y - sa + 1) * Wp + 1;
-                const double* mid = bandI + (y - sa + 2) * Wp + 1;
-                const double* er = bandE + (y - sa) * Wp + 1;
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    if (x < W) {
-                        const double I = mid[x];
-                        const double adj = scharr_adjoint_rows(xm - Wp + x, xm + x, xm + Wp + x, ym - Wp + x, ym + Wp + x);
-                        const double cI = I - st.mn;
-                        const double gN = cB * (er[x] - cI / st.D);
-                        double out = cA * adj + gN / st.D;
-                        if (I == st.mn) out += g_m / st.cnt_min;
-                        if (I == st.mx) out += g_M / st.cnt_max;
-                        const int p = y * W + x;
-                        if (A.dldi != nullptr) A.dldi[r * HW + p] = out;
-                        A.dldi32[r * HW + p] = (float)(out * kInv2Pi);
+            for (int u = 0; u < 4; ++u) {
+                const int p = base + u * T;
+                if (p < A.HW) {
+                    if (A.fix != nullptr) A.fix[(size_t)r * A.HW + p] = 0ull;
+                    if (A.want_grad) {
+                        double out = cA * (double)a[u] + cBD * (E[u] - (I[u] - mn) * iD);
+                        if (I[u] == mn) out += tm;
+                        if (I[u] == mx) out += tM;
+                        if (A.dldi != nullptr) A.dldi[(size_t)r * A.HW + p] = out;
+                        if (A.dldi32 != nullptr) A.dldi32[(size_t)r * A.HW + p] = (float)(out * kInv2Pi);
                     }
                 }
             }
         }
     }
-    stamp(A, 5);
 }
 
 // per-window: sum E_r and sum E_r^2 (deterministic single-CTA-per-reference reduction; once per window)

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = (
     'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
     'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
-    'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host', 'eincm_debug_image_pass_stamps',
+    'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host',
 )
 
 
@@ -108,7 +108,6 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_iwe_fix_ptr': (vp, [vp]),
         'eincm_split_prepare': (i32, [vp, vp]),
         'eincm_split_window_images': (i32, [vp, vp]),
-        'eincm_debug_image_pass_stamps': (i32, [vp, C.POINTER(C.c_uint64)]),
         'eincm_minimize_bfgs_host': (i32, [vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
         'eincm_minimize_handover_host': (i32, [vp, C.POINTER(dbl), dbl, dbl, vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
         'eincm_plan_launch_count': (i64, [vp]),

@@ -194,9 +194,6 @@ int eincm_get_scalars(eincm_plan* plan, double* out_host, int n_doubles, void* c
 /* Bit-exact event->pixel index stream of reference r for the last evaluated theta, in the ORIGINAL event
  * order: cols_out/rows_out [n_events] int32 = Xs_rounded of event_utils.py:33 (before the +dx,+dy taps). */
 int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int32_t* rows_out, void* cuda_stream);
-/* profiling aid: %globaltimer (ns) of CTA 0 at the phase boundaries of the cooperative image pass of the last evaluation
- * (start, phase 1, barrier reached, barrier passed, phase 3, end); plans created with EINCM_IMAGE_PASS_STAMPS=1 in the environment */
-int eincm_debug_image_pass_stamps(eincm_plan* plan, unsigned long long* out_host);
 /* ---- measurement hooks (bench.py): launch accounting and optional per-kernel CUDA-event timing -------- */
 /* number of kernels this plan has launched since creation (memsets / copies not counted) */
 int64_t eincm_plan_launch_count(const eincm_plan* plan);
