@@ -134,7 +134,7 @@ __device__ __forceinline__ void load_chunk_events(const uint32_t* __restrict__ e
 // votes into the window when its rounded centre lies in [ox + 1, ox + pw - 2] x [oy + 1, oy + ph - 2]; the kernels test that on
 // the float64 warped coordinate itself, |x' - cx| < hx (strict: a coordinate exactly on the rounding boundary takes the
 // fallback), which also rejects NaN / infinite / absurdly far warps in the same two comparisons.
-struct Window { int ox, oy, pw, ph; double cx, hx, cy, hy; };
+struct Window { int ox, oy, pw, ph; double cx, hx, cy, hy; uint32_t inv_pw, interior; };   // inv_pw = ceil(2^32 / pw): exact i / pw for i < 2^16
 
 __device__ __forceinline__ Window make_window(int ox, int oy, int pw, int ph) {
     Window w;
@@ -142,7 +142,14 @@ __device__ __forceinline__ Window make_window(int ox, int oy, int pw, int ph) {
     w.cx = (double)ox + 0.5 * (double)(pw - 1); w.hx = 0.5 * (double)(pw - 2);
     w.cy = (double)oy + 0.5 * (double)(ph - 1); w.hy = 0.5 * (double)(ph - 2);
     if (pw < 3 || ph < 3) { w.hx = -1.0; w.hy = -1.0; }
+    w.inv_pw = pw > 0 ? 0xffffffffu / (uint32_t)pw + 1u : 0u;
+    w.interior = 0u;
     return w;
+}
+
+// every cell of the window lies inside the H x W image: the index rule of the reference (wrap / drop) has nothing to do
+__device__ __forceinline__ void set_interior(Window& w, int H, int W) {
+    w.interior = (w.ox >= 0 && w.oy >= 0 && w.ox + w.pw <= W && w.oy + w.ph <= H) ? 1u : 0u;
 }
 
 // window that holds the centres [mnx, mxx] x [mny, mxy] (cropped to kWinCap cells: the events outside take the fallback)
@@ -380,6 +387,7 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                                       ordered_float(ay), ordered_float(by), tr.x, tr.y, tref.t[r0 + tid]);
                     if (chunk_win != nullptr) chunk_win[(int64_t)c * R + r0 + tid] = make_int4(wn.ox, wn.oy, wn.pw, wn.ph);
                 }
+                set_interior(wn, H, W);
                 swin[tid] = wn;
             }
             __syncthreads();
@@ -391,8 +399,12 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
             }
             __syncthreads();
             // votes
-            uint32_t missed = 0u;                    // bit r * kEvK + k: event k missed the window of reference time r0 + r
+            // misses are rare: the hot loop only counts hits; a thread whose count falls short repeats the window tests below
+            int n_hit = 0, n_valid = 0;
             if (active) {
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) n_valid += ev.xy[k] != kNoEvent ? 1 : 0;
+                n_valid *= min(RB, R - r0);
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     if (r0 + r >= R) continue;
@@ -411,17 +423,23 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                         const TapsFix t = taps_fix(hit ? h.fx : 1.0e4f, hit ? h.fy : 0.f);
                         const uint32_t mid = hit ? wb + (uint32_t)(h.ry * wn.pw + h.rx) * 4u : safe;
                         emit9(mid, pitch4, t.n);
-                        missed |= (valid & !hit) ? (1u << (r * kEvK + k)) : 0u;
+                        n_hit += hit ? 1 : 0;
                     }
                 }
             }
-            if (missed != 0u) {
+            if (n_hit != n_valid) {
 #pragma unroll
                 for (int k = 0; k < kEvK; ++k) {
+                    if (ev.xy[k] == kNoEvent) continue;
+                    const double2 th = lds_theta(th_base, ev.xy[k]);
 #pragma unroll 1
-                    for (int r = 0; r < RB; ++r)
-                        if ((missed >> (r * kEvK + k)) & 1u)
-                            splat_fallback<WRAP>(dst, (int64_t)(r0 + r) * HW, ev.xy[k], lds_theta(th_base, ev.xy[k]), ev.t[k] - tref.t[r0 + r], H, W);
+                    for (int r = 0; r < RB && r0 + r < R; ++r) {
+                        const double dt = ev.t[k] - tref.t[r0 + r];
+                        const Hit2 h = warp_hit2(ev.xy[k], th, dt);
+                        const Window& wn = swin[r];
+                        if (!((fabs(h.xw - wn.cx) < wn.hx) & (fabs(h.yw - wn.cy) < wn.hy)))
+                            splat_fallback<WRAP>(dst, (int64_t)(r0 + r) * HW, ev.xy[k], th, dt, H, W);
+                    }
                 }
             }
             __syncthreads();
@@ -434,8 +452,9 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                 const uint4* wr4 = reinterpret_cast<const uint4*>(win + r * kWinCap);
                 const int64_t img_off = (int64_t)(r0 + r) * HW;
                 const int cells = wn.pw * wn.ph;
-                const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
-                const uint32_t inv_pw = wn.pw > 0 ? 0xffffffffu / (uint32_t)wn.pw + 1u : 0u;    // ceil(2^32 / pw): exact i / pw for i < 2^16
+                const bool interior = wn.interior != 0u;
+                const uint32_t inv_pw = wn.inv_pw;
+                unsigned long long* const img0 = dst.p[0] + img_off;
                 for (int i4 = tid; 4 * i4 < cells; i4 += 256) {
                     const uint4 q = wr4[i4];
                     if ((q.x | q.y | q.z | q.w) == 0u) continue;
@@ -447,9 +466,9 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                         if (v4[u] != 0u && 4 * i4 + u < cells) {
                             int rr = wn.oy + row, cc = wn.ox + col;
                             if (interior || drop_index<WRAP>(rr, cc, H, W)) {
-                                const int64_t off = img_off + (rr * W + cc);
+                                atomicAdd(img0 + (rr * W + cc), (unsigned long long)v4[u]);
 #pragma unroll 1
-                                for (int p = 0; p < dst.n; ++p) atomicAdd(dst.p[p] + off, (unsigned long long)v4[u]);
+                                for (int p = 1; p < dst.n; ++p) atomicAdd(dst.p[p] + img_off + (rr * W + cc), (unsigned long long)v4[u]);
                             }
                         }
                         if (++col == wn.pw) { col = 0; ++row; }
@@ -498,7 +517,9 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
             if (tid < RB) {
                 int4 q = make_int4(0, 0, 0, 0);
                 if (r0 + tid < R) q = chunk_win[(int64_t)c * R + r0 + tid];
-                swin[tid] = make_window(q.x, q.y, q.z, q.w);
+                Window wn = make_window(q.x, q.y, q.z, q.w);
+                set_interior(wn, H, W);
+                swin[tid] = wn;
             }
             __syncthreads();
             // window cells <- d loss / d IWE: all global loads of a round (four cells per thread) are issued before the stores
@@ -509,8 +530,8 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
                 const float* img = dldi32 + (int64_t)(r0 + r) * HW;
                 float* wr = dwin + r * kWinCap;
                 const int cells = wn.pw * wn.ph;
-                const bool interior = wn.ox >= 0 && wn.oy >= 0 && wn.ox + wn.pw <= W && wn.oy + wn.ph <= H;
-                const uint32_t inv_pw = wn.pw > 0 ? 0xffffffffu / (uint32_t)wn.pw + 1u : 0u;
+                const bool interior = wn.interior != 0u;
+                const uint32_t inv_pw = wn.inv_pw;
                 for (int i0 = tid; i0 < cells; i0 += 4 * 256) {
                     float v[4];
 #pragma unroll
@@ -528,8 +549,11 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
                 }
             }
             __syncthreads();
-            uint32_t missed = 0u;
+            int n_hit = 0, n_valid = 0;
             if (active) {
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) n_valid += ev.xy[k] != kNoEvent ? 1 : 0;
+                n_valid *= min(RB, R - r0);
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     if (r0 + r >= R) continue;
@@ -559,21 +583,26 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
                         // a miss may have read anything (and a padding sentinel has no timestamp): select, do not multiply by zero
                         ax[k] = hit ? fmaf(ndt, gx, ax[k]) : ax[k];
                         ay[k] = hit ? fmaf(ndt, gy, ay[k]) : ay[k];
-                        missed |= (valid & !hit) ? (1u << (r * kEvK + k)) : 0u;
+                        n_hit += hit ? 1 : 0;
                     }
                 }
             }
-            if (missed != 0u) {
+            if (n_hit != n_valid) {
 #pragma unroll
                 for (int k = 0; k < kEvK; ++k) {
+                    if (ev.xy[k] == kNoEvent) continue;
+                    const double2 th = lds_theta(th_base, ev.xy[k]);
 #pragma unroll 1
-                    for (int r = 0; r < RB; ++r)
-                        if ((missed >> (r * kEvK + k)) & 1u) {
-                            const double dt = ev.t[k] - tref.t[r0 + r];
-                            const float2 g = gather_fallback<WRAP>(dldi32 + (int64_t)(r0 + r) * HW, ev.xy[k], lds_theta(th_base, ev.xy[k]), dt, H, W);
+                    for (int r = 0; r < RB && r0 + r < R; ++r) {
+                        const double dt = ev.t[k] - tref.t[r0 + r];
+                        const Hit2 h = warp_hit2(ev.xy[k], th, dt);
+                        const Window& wn = swin[r];
+                        if (!((fabs(h.xw - wn.cx) < wn.hx) & (fabs(h.yw - wn.cy) < wn.hy))) {
+                            const float2 g = gather_fallback<WRAP>(dldi32 + (int64_t)(r0 + r) * HW, ev.xy[k], th, dt, H, W);
                             ax[k] = fmaf(-(float)dt, g.x, ax[k]);
                             ay[k] = fmaf(-(float)dt, g.y, ay[k]);
                         }
+                    }
                 }
             }
         }
