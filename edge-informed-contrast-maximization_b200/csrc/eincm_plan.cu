@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -56,7 +57,9 @@ struct eincm_plan {
     unsigned long long* peer_fix[kMaxPeers] = {};   // event split with peer access: fixed-point images of all ranks (own included)
     void* peer_opened[kMaxPeers] = {};              // pointers obtained from cudaIpcOpenMemHandle (closed on destroy)
     int n_peers = 0;                                // 0: no peer access (the caller all-reduces the float64 images)
+    cudaEvent_t wait_ev = nullptr;       // EINCM_FLAG_BLOCKING_SYNC: blocking-sync event the host entry points sleep on
     cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
+    double host_seq = 0.0;               // sequence number of the last host evaluation (written back by its last kernel)
     size_t host_ng = 0;                  // gradient doubles of the host evaluation in flight (host_enqueue -> host_collect)
     bool host_delivered = false;  // the last backward pass wrote its results into the mapped host buffer itself
     double* h_mapped_dev = nullptr;   // device alias of h_pinned (cudaHostAllocMapped)
@@ -356,7 +359,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
 // host_out: device alias of mapped pinned memory; when the tile-theta gradient kernel runs it delivers [grad | loss | dalpha]
 // there itself (plan->host_delivered), otherwise the caller copies the results back.
 int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, double* dalpha_out, cudaStream_t st,
-                  double* host_out = nullptr) {
+                  double* host_out = nullptr, double host_seq = 0.0) {
     plan->host_delivered = false;
     plan->dldi_stale = false;
     int rc = check_hp(plan, hp);
@@ -496,11 +499,11 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         if (Gtv != nullptr)
             LAUNCH("k_theta_grad", k_theta_grad<true><<<gridG, kTgWarps * 32, 0, st>>>(
                 (const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0));
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0, host_seq));
         else
             LAUNCH("k_theta_grad", k_theta_grad<false><<<gridG, kTgWarps * 32, 0, st>>>(
                 (const double2*)plan->G, nullptr, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0));
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0, host_seq));
         plan->host_delivered = host_out != nullptr;
     } else {
         CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
@@ -541,13 +544,25 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
 
     {   // the tile kernels keep up to kMaxRB windows of kWinCap cells in dynamic shared memory (> 48 KB needs the opt-in)
         cudaError_t ea = cudaSuccess;
+        // every kernel of an evaluation asks for the same shared-memory carve-out (the maximum): the L1 / shared-memory split of an
+        // SM can only change while the SM is idle, so kernels of concurrent windows (one stream each) that prefer different splits
+        // cannot share an SM and serialise
+        auto max_carveout = [&](const void* fn) {
+            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        };
         auto opt_in = [&](const void* fn, int rb) {
             if (ea == cudaSuccess) ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rb * kWinCap * (int)sizeof(uint32_t));
+            max_carveout(fn);
         };
 #define OPT_IN_RB(RB) opt_in((const void*)k_splat_tile<true, RB>, RB); opt_in((const void*)k_splat_tile<false, RB>, RB); \
                       opt_in((const void*)k_backward_tile<true, RB>, RB); opt_in((const void*)k_backward_tile<false, RB>, RB)
         OPT_IN_RB(1); OPT_IN_RB(2); OPT_IN_RB(3); OPT_IN_RB(4);
 #undef OPT_IN_RB
+        max_carveout((const void*)k_image_grad);
+        max_carveout((const void*)k_theta_grad<false>); max_carveout((const void*)k_theta_grad<true>);
+        max_carveout((const void*)k_theta_grad_scatter); max_carveout((const void*)k_tv); max_carveout((const void*)k_upsample_theta);
+        max_carveout((const void*)k_image_stats<1>); max_carveout((const void*)k_image_stats<2>); max_carveout((const void*)k_image_stats<3>);
+        max_carveout((const void*)k_image_stats<4>); max_carveout((const void*)k_image_stats<5>); max_carveout((const void*)k_image_stats<6>);
         if (ea != cudaSuccess) return fail(nullptr, EINCM_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
     }
     plan = new (std::nothrow) eincm_plan();
@@ -608,6 +623,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(cudaHostAlloc((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double), cudaHostAllocMapped));
         CU(cudaHostGetDevicePointer((void**)&plan->h_mapped_dev, plan->h_pinned, 0));
         CU(cudaStreamCreateWithFlags(&plan->own_stream, cudaStreamNonBlocking));
+        if (flags & EINCM_FLAG_BLOCKING_SYNC) CU(cudaEventCreateWithFlags(&plan->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
         return EINCM_OK;
     };
@@ -637,6 +653,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     if (plan->h_pinned) cudaFreeHost(plan->h_pinned);
     if (plan->h_flag) cudaFreeHost(plan->h_flag);
+    if (plan->wait_ev) cudaEventDestroy(plan->wait_ev);
     delete plan;
 }
 
@@ -790,18 +807,47 @@ int host_enqueue(eincm_plan* plan, const double* theta_host, int h, int w, const
     double* loss_dev = plan->grad_stage + n_g;
     int rc = forward_events_impl(plan, plan->theta_stage, nullptr, 0.0, h, w, hp, st);
     if (rc) return rc;
-    const bool small = n_g + 2 <= 1000;                                // fits behind the theta staging area
+    const bool small = n_g + 3 <= 1000;                                // fits behind the theta staging area
+    plan->host_seq += 1.0;
+    if (small) plan->h_pinned[(size_t)plan->HW * 2 + 16 + n_g + 2] = -1.0;     // sequence slot of this evaluation: not yet written
     rc = backward_impl(plan, hp, loss_dev, want_grad ? plan->grad_stage : nullptr, nullptr, st,
-                       small ? plan->h_mapped_dev + (size_t)plan->HW * 2 + 16 : nullptr);
+                       small ? plan->h_mapped_dev + (size_t)plan->HW * 2 + 16 : nullptr, plan->host_seq);
     if (rc) return rc;
     if (!plan->host_delivered)
         CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, (n_g + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
     return EINCM_OK;
 }
 
+// waits for the work enqueued on `st`: spinning (lowest latency) or, with EINCM_FLAG_BLOCKING_SYNC, asleep on an event
+int host_wait(eincm_plan* plan, cudaStream_t st) {
+    if (plan->wait_ev != nullptr) {
+        CU(cudaEventRecord(plan->wait_ev, st));
+        CU(cudaEventSynchronize(plan->wait_ev));
+    } else {
+        CU(cudaStreamSynchronize(st));
+    }
+    return EINCM_OK;
+}
+
 int host_collect(eincm_plan* plan, double* loss_out_host, double* grad_out_host, cudaStream_t st) {
-    CU(cudaStreamSynchronize(st));
     const double* h_res = plan->host_delivered ? plan->h_pinned + (size_t)plan->HW * 2 + 16 : plan->h_pinned;   // [grad | loss]
+    bool arrived = false;
+    if (plan->host_delivered && plan->wait_ev == nullptr) {
+        // the last kernel wrote [grad | loss | d alpha | sequence number] into mapped pinned memory: poll the sequence number
+        // there (bounded; an error or a very long evaluation ends in the stream synchronisation below)
+        const volatile double* seq = h_res + plan->host_ng + 2;
+        for (long spin = 0; spin < 20000000L; ++spin) {
+            if (*seq == plan->host_seq) { arrived = true; break; }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!arrived) {
+        const int rcw = host_wait(plan, st);
+        if (rcw) return rcw;
+    }
     *loss_out_host = h_res[plan->host_ng];
     if (grad_out_host) std::memcpy(grad_out_host, h_res, plan->host_ng * sizeof(double));
     return EINCM_OK;

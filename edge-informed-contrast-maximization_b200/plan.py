@@ -20,6 +20,7 @@ EINCM_EINVAL, EINCM_ECUDA, EINCM_ENOMEM, EINCM_ESTATE, EINCM_ERANGE, EINCM_EUNSU
 FLAG_NO_WRAP_NEGATIVE = 0x1
 FLAG_EVENT_SPLIT = 0x2
 FLAG_EXACT_F64 = 0x4
+FLAG_BLOCKING_SYNC = 0x8
 METHOD_BILINEAR = 0
 S_HEADER = 8
 

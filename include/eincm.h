@@ -51,6 +51,10 @@ extern "C" {
                                               memory windows, float64 coordinates (bit-exact pixel indices, order-independent image sums,
                                               objective within ~1e-7 relative) */
 
+#define EINCM_FLAG_BLOCKING_SYNC     0x8u  /* the synchronous host entry points sleep on a blocking CUDA event instead of spinning in
+                                              cudaStreamSynchronize: for hosts with fewer cores than driving threads (one thread per
+                                              sequence, several sequences per GPU); costs some wake-up latency per call */
+
 /* theta -> sensor-size resize method (reference configs/main.yaml:27 `scale_theta_to_sensor_size_method`) */
 #define EINCM_METHOD_BILINEAR 0
 
