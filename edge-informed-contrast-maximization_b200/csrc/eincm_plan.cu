@@ -23,6 +23,7 @@
 #include "k_events.cuh"
 #include "k_events_tile.cuh"
 #include "k_image.cuh"
+#include "k_eval.cuh"
 #include "k_image_fused.cuh"
 #include "eincm_opt.h"
 
@@ -1131,6 +1132,116 @@ int eincm_split_window_images(eincm_plan* plan, void* cuda_stream) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // after the barrier: this rank's fixed-point image 0 holds the complete zero-warp image of the window
     LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((plan->HW + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, plan->HW, plan->zero_iwe));
+    return EINCM_OK;
+}
+
+namespace {
+static_assert(EINCM_EVAL_MAX_REFS == EINCM_MAX_REFS, "eincm_eval_metrics holds one slot per reference time");
+
+// launches the flow-error reduction; the kFlowErrCols sums end up in dev_out (device)
+int flow_error_launch(const double* pred_flow, const uint8_t* pred_mult, const double* gt_flow, const uint8_t* event_mask, int64_t n,
+                      int grid, double* part, double* dev_out, cudaStream_t st) {
+    k_flow_error<<<grid, 256, 0, st>>>((const double2*)pred_flow, pred_mult, (const double2*)gt_flow, event_mask, n, part);
+    k_sum_rows<<<1, 32, 0, st>>>(part, grid, kFlowErrCols, dev_out);
+    return cudaGetLastError() == cudaSuccess ? EINCM_OK : EINCM_ECUDA;
+}
+
+void flow_errors_from_sums(const double* s, eincm_flow_errors* out) {
+    out->n_pred = (int64_t)s[0]; out->n_gt = (int64_t)s[1]; out->n_ee = (int64_t)s[2];
+    out->AEE = s[2] > 0.0 ? s[3] / s[2] : std::nan("");                     // mean of an empty array
+    out->AREE = s[2] > 0.0 ? s[4] / s[2] : std::nan("");
+    for (int k = 0; k < 6; ++k) out->ANPE[k] = s[5 + k] * 100.0 / (s[2] + kEps);   // flow_eval.py:73-74
+}
+}  // namespace
+
+int eincm_sparse_flow_error(int device, int H, int W, const double* pred_flow, const double* gt_flow, const uint8_t* event_mask,
+                            eincm_flow_errors* out_host, void* cuda_stream) {
+    if (!pred_flow || !gt_flow || !out_host || H < 1 || W < 1) return EINCM_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return EINCM_ECUDA;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int64_t n = (int64_t)H * W;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 1024));
+    double* scratch = nullptr;
+    if (cudaMalloc((void**)&scratch, ((size_t)grid + 1) * kFlowErrCols * sizeof(double)) != cudaSuccess) return EINCM_ENOMEM;
+    double sums[kFlowErrCols];
+    int rc = flow_error_launch(pred_flow, nullptr, gt_flow, event_mask, n, grid, scratch + kFlowErrCols, scratch, st);
+    if (rc == EINCM_OK && (cudaMemcpyAsync(sums, scratch, sizeof(sums), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                           cudaStreamSynchronize(st) != cudaSuccess))
+        rc = EINCM_ECUDA;
+    cudaFree(scratch);
+    if (rc) return rc;
+    flow_errors_from_sums(sums, out_host);
+    return EINCM_OK;
+}
+
+int eincm_evaluate_theta(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, const double* gt_flow,
+                         const uint8_t* err_eval_event_mask, eincm_eval_metrics* out_host, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!theta || !out_host) return fail(plan, EINCM_EINVAL, "NULL operand");
+    if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "evaluation metrics are not available on event-split plans");
+    if (!plan->window_set) return fail(plan, EINCM_ESTATE, "eincm_evaluate_theta before set_window");
+    int rc = check_hp(plan, hp);
+    if (rc) return rc;
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // every term is evaluated (theta_eval.py:21-42 does not gate them): force the TV and divergence paths, level 0
+    eincm_hparams hpe = *hp;
+    if (hpe.gamma == 0.0) hpe.gamma = 1.0;
+    if (hpe.delta == 0.0) hpe.delta = 1.0;
+    hpe.cur_pyr_lvl = 0;
+    if ((rc = forward_events_impl(plan, theta, nullptr, 0.0, h, w, &hpe, st))) return rc;
+    if ((rc = backward_impl(plan, &hpe, plan->out_stage, nullptr, nullptr, st))) return rc;
+    if ((rc = ensure_theta_full(plan, st))) return rc;
+    const int R = plan->R, H = plan->H, W = plan->W;
+    // scratch layout inside `part`: [var of R images | var of the zero image | theta_div | flow sums | partials ...]
+    double* res = plan->part;
+    double* scratch = plan->part + 64;
+    LAUNCH("k_image_var", k_image_var<<<R, 1024, 0, st>>>(plan->iwe, plan->HW, res, nullptr));
+    LAUNCH("k_image_var(zero)", k_image_var<<<1, 1024, 0, st>>>(plan->zero_iwe, plan->HW, res + EINCM_MAX_REFS, nullptr));
+    const dim3 gridD((W + kEvTX - 1) / kEvTX, (H + kEvTY - 1) / kEvTY), blockD(kEvTX, kEvTY);
+    const int nD = gridD.x * gridD.y;
+    if (64 + (int64_t)nD + 1 > plan->part_doubles) return fail(plan, EINCM_ENOMEM, "scratch too small for the theta divergence");
+    LAUNCH("k_theta_divergence", k_theta_divergence<<<gridD, blockD, 0, st>>>((const double2*)plan->theta_full, H, W, scratch));
+    LAUNCH("k_sum_rows", k_sum_rows<<<1, 32, 0, st>>>(scratch, nD, 1, res + EINCM_MAX_REFS + 1));
+    if (gt_flow != nullptr) {
+        const int grid = std::max(1, std::min((int)((plan->HW + 255) / 256), plan->sm_count * 4));
+        if (64 + (int64_t)nD + (int64_t)grid * kFlowErrCols > plan->part_doubles) return fail(plan, EINCM_ENOMEM, "scratch too small for the flow errors");
+        // pred_flow = theta_full * [pixel holds an event] (theta_eval.py:47, theta_utils.py:40-73)
+        if ((rc = flow_error_launch((const double*)plan->theta_full, plan->mask, gt_flow, err_eval_event_mask, plan->HW, grid, scratch + nD,
+                                    res + EINCM_MAX_REFS + 2, st)))
+            return fail(plan, rc, "flow error kernels failed to launch");
+        plan->launch_count += 2;
+    }
+    double hres[64];
+    DevScalars* hs = (DevScalars*)plan->h_pinned;
+    CU(cudaMemcpyAsync(hs, plan->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(plan->h_pinned + 1024, res, 64 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::memcpy(hres, plan->h_pinned + 1024, sizeof(hres));
+    eincm_eval_metrics m;
+    std::memset(&m, 0, sizeof(m));
+    m.n_refs = R;
+    double s_con = 0.0, s_cor = 0.0, s_div = 0.0;
+    for (int r = 0; r < R; ++r) {
+        m.rel_contrasts[r] = hs->ref[r].contrast / (hs->zero[0].contrast + kEps);                  // losses.py:72
+        m.rel_correlations[r] = (-hs->ref[r].mse) / ((-hs->zero[r].mse) + kEps);                   // losses.py:67
+        m.rel_iwe_divergences[r] = hs->ref[r].div / (hs->zero[0].div + kEps);                      // losses.py:81
+        m.flow_warp_losses[r] = hres[r] / hres[EINCM_MAX_REFS];                                    // losses.py:84
+        m.multi_ref_weights[r] = hs->weights[r];
+        s_con += m.rel_contrasts[r]; s_cor += m.rel_correlations[r]; s_div += m.rel_iwe_divergences[r];
+    }
+    m.mean_rel_contrast = s_con / R; m.mean_rel_corr = s_cor / R; m.mean_rel_iwe_div = s_div / R;  // theta_eval.py:27-29
+    m.theta_tot_var = hs->tv_sum / (hs->tv_cnt + kEps);                                            // regularizers.py:31-36
+    m.theta_div = hres[EINCM_MAX_REFS + 1] / (double)plan->HW;                                     // regularizers.py:58
+    m.fwl = m.flow_warp_losses[0];                                                                 // theta_eval.py:32
+    m.iwe_var = hres[0];                                                                           // theta_eval.py:36,82
+    m.loss = hp->alpha * (-m.mean_rel_contrast) + hp->beta * (-m.mean_rel_corr) + hp->gamma * m.theta_tot_var + hp->delta * m.mean_rel_iwe_div;
+    if (gt_flow != nullptr) {
+        m.has_flow = 1;
+        m.n_pixels = plan->HW;
+        flow_errors_from_sums(hres + EINCM_MAX_REFS + 2, &m.flow);
+    }
+    *out_host = m;
     return EINCM_OK;
 }
 

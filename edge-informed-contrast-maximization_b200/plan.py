@@ -34,7 +34,8 @@ EXPORTED_SYMBOLS = (
     'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
     'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
-    'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host',
+    'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host', 'eincm_sparse_flow_error',
+    'eincm_evaluate_theta',
 )
 
 
@@ -50,6 +51,29 @@ class OptResult(C.Structure):
 
 
 OWN_STREAM = C.c_void_p(-1)     # stream argument selecting the plan's own stream
+EVAL_MAX_REFS = 8
+
+
+class FlowErrors(C.Structure):
+    """``eincm_flow_errors`` (reference src/evaluations/flow_eval.py:14-75)."""
+    _fields_ = [('AEE', C.c_double), ('AREE', C.c_double), ('ANPE', C.c_double * 6), ('n_ee', C.c_int64), ('n_pred', C.c_int64),
+                ('n_gt', C.c_int64)]
+
+    def as_dict(self):
+        errs = {'AEE': self.AEE, 'AREE': self.AREE}
+        for k, n in enumerate((1, 2, 3, 5, 10, 20)):
+            errs[f'A{n}PE'] = self.ANPE[k]
+        return {'errors': errs, 'counts': {'n_ee': int(self.n_ee), 'n_pred': int(self.n_pred), 'n_gt': int(self.n_gt)}}
+
+
+class EvalMetrics(C.Structure):
+    """``eincm_eval_metrics`` (reference src/evaluations/theta_eval.py:80-94)."""
+    _fields_ = [('loss', C.c_double), ('iwe_var', C.c_double), ('mean_rel_contrast', C.c_double), ('mean_rel_corr', C.c_double),
+                ('mean_rel_iwe_div', C.c_double), ('theta_tot_var', C.c_double), ('theta_div', C.c_double), ('fwl', C.c_double),
+                ('rel_contrasts', C.c_double * EVAL_MAX_REFS), ('rel_correlations', C.c_double * EVAL_MAX_REFS),
+                ('rel_iwe_divergences', C.c_double * EVAL_MAX_REFS), ('flow_warp_losses', C.c_double * EVAL_MAX_REFS),
+                ('multi_ref_weights', C.c_double * EVAL_MAX_REFS), ('n_refs', C.c_int32), ('has_flow', C.c_int32),
+                ('n_pixels', C.c_int64), ('flow', FlowErrors)]
 
 
 class HParams(C.Structure):
@@ -111,6 +135,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_split_window_images': (i32, [vp, vp]),
         'eincm_minimize_bfgs_host': (i32, [vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
         'eincm_minimize_handover_host': (i32, [vp, C.POINTER(dbl), dbl, dbl, vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
+        'eincm_sparse_flow_error': (i32, [i32, i32, i32, vp, vp, vp, C.POINTER(FlowErrors), vp]),
+        'eincm_evaluate_theta': (i32, [vp, vp, i32, i32, hp, vp, vp, C.POINTER(EvalMetrics), vp]),
         'eincm_plan_launch_count': (i64, [vp]),
         'eincm_plan_set_timing': (i32, [vp, i32]),
         'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
@@ -357,6 +383,21 @@ class Plan:
         return loss.value, grad
 
     # -- read-outs --------------------------------------------------------------------------------------------
+    # -- evaluation metrics of a solved window (reference src/evaluations/theta_eval.py) ----------------------------
+    def evaluate_theta(self, theta, hp: HParams, gt_flow=None, err_eval_event_mask=None, stream=None) -> EvalMetrics:
+        torch = _torch()
+        th = self._dev(theta, torch.float64)
+        gt = self._dev(gt_flow, torch.float64) if gt_flow is not None else None
+        em = self._dev(np.asarray(err_eval_event_mask.cpu() if isinstance(err_eval_event_mask, torch.Tensor) else err_eval_event_mask).astype(np.uint8),
+                       torch.uint8) if err_eval_event_mask is not None else None
+        if gt is not None and tuple(gt.shape) != (self.H, self.W, 2):
+            raise EincmError(EINCM_EINVAL, f'gt_flow must have shape {(self.H, self.W, 2)}')
+        out = EvalMetrics()
+        self._check(self.lib.eincm_evaluate_theta(self._h, th.data_ptr(), int(th.shape[0]), int(th.shape[1]), C.byref(hp),
+                                                  gt.data_ptr() if gt is not None else None, em.data_ptr() if em is not None else None,
+                                                  C.byref(out), _stream_ptr(stream)))
+        return out
+
     def _view(self, ptr, shape, dtype_str):
         torch = _torch()
         with torch.cuda.device(self.device):

@@ -198,6 +198,39 @@ int eincm_get_scalars(eincm_plan* plan, double* out_host, int n_doubles, void* c
 /* Bit-exact event->pixel index stream of reference r for the last evaluated theta, in the ORIGINAL event
  * order: cols_out/rows_out [n_events] int32 = Xs_rounded of event_utils.py:33 (before the +dx,+dy taps). */
 int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int32_t* rows_out, void* cuda_stream);
+/* ---- evaluation metrics of a solved window (reference src/evaluations/theta_eval.py:14-95, flow_eval.py:14-75) ----------
+ * Computed on the device from the images the evaluation leaves there; one call per solved window (not the optimisation hot path). */
+#define EINCM_EVAL_MAX_REFS 8
+typedef struct {
+    double AEE, AREE;            /* mean end-point error / relative end-point error over the valid pixels (NaN when n_ee == 0) */
+    double ANPE[6];              /* percentage of valid pixels with end-point error > 1, 2, 3, 5, 10, 20 px (flow_eval.py:72-74) */
+    int64_t n_ee, n_pred, n_gt;  /* counts of flow_eval.py:65-67 */
+} eincm_flow_errors;
+
+typedef struct {
+    double loss;                 /* alpha (-mean_rel_contrast) + beta (-mean_rel_corr) + gamma tot_var + delta mean_rel_iwe_div (theta_eval.py:37-42) */
+    double iwe_var;              /* var of the image of warped events at the first reference time (theta_eval.py:36,82) */
+    double mean_rel_contrast, mean_rel_corr, mean_rel_iwe_div;   /* UN-weighted means over the reference times (theta_eval.py:27-29) */
+    double theta_tot_var, theta_div;                             /* regularizers.py:14-38 / :41-58 */
+    double fwl;                  /* flow warp loss at the first reference time: var(IWE_0) / var(zero-IWE) (contrast_metrics.py:6-17) */
+    double rel_contrasts[EINCM_EVAL_MAX_REFS], rel_correlations[EINCM_EVAL_MAX_REFS], rel_iwe_divergences[EINCM_EVAL_MAX_REFS];
+    double flow_warp_losses[EINCM_EVAL_MAX_REFS], multi_ref_weights[EINCM_EVAL_MAX_REFS];
+    int32_t n_refs, has_flow;    /* has_flow != 0: `flow` and n_pixels are valid (a ground-truth flow was given) */
+    int64_t n_pixels;
+    eincm_flow_errors flow;
+} eincm_eval_metrics;
+
+/* sparse_flow_error(pred_flow, gt_flow, event_mask) of flow_eval.py:14-75.  pred_flow / gt_flow: DEVICE [H*W*2] float64 (row-major
+ * [H][W][2]); event_mask: DEVICE [H*W] uint8 or NULL.  Synchronous; result in host memory. */
+int eincm_sparse_flow_error(int device, int H, int W, const double* pred_flow, const double* gt_flow, const uint8_t* event_mask,
+                            eincm_flow_errors* out_host, void* cuda_stream);
+/* evaluate_theta_array of theta_eval.py:14-95 on the staged window.  theta: DEVICE [h][w][2] (up-scaled to the sensor size like
+ * loss_func does; pass h = H, w = W for a dense field).  gt_flow: DEVICE [H][W][2] or NULL; err_eval_event_mask: DEVICE [H*W] uint8
+ * or NULL.  The total-variation and divergence terms are always evaluated (the reference's evaluation does not gate them on
+ * cur_pyr_lvl, gamma or delta); hp supplies alpha, beta, gamma, delta.  Synchronous.  Not for event-split plans. */
+int eincm_evaluate_theta(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, const double* gt_flow,
+                         const uint8_t* err_eval_event_mask, eincm_eval_metrics* out_host, void* cuda_stream);
+
 /* ---- measurement hooks (bench.py): launch accounting and optional per-kernel CUDA-event timing -------- */
 /* number of kernels this plan has launched since creation (memsets / copies not counted) */
 int64_t eincm_plan_launch_count(const eincm_plan* plan);

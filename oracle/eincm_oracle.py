@@ -338,6 +338,64 @@ def loss_func(theta, xs, ys, ts, edges, edge_ts, alpha, beta, gamma, delta,
     return float(final_loss), aux
 
 
+# --------------------------------------------------------------------------- #
+# evaluation metrics: src/evaluations/flow_eval.py:14-75, src/evaluations/theta_eval.py:14-95
+# --------------------------------------------------------------------------- #
+N_PE_THRESHOLDS = (1, 2, 3, 5, 10, 20)                                    # flow_eval.py:72
+
+
+def sparse_flow_error(pred_flow, gt_flow, event_mask=None) -> Dict:
+    """src/evaluations/flow_eval.py:14-75: end-point errors over the pixels where both flows are valid."""
+    pred_flow = np.asarray(pred_flow, dtype=np.float64)
+    gt_flow = np.asarray(gt_flow, dtype=np.float64)
+    mask_pred = (~np.isinf(pred_flow[..., 0]) & ~np.isinf(pred_flow[..., 1])) & (np.linalg.norm(pred_flow, axis=-1) > 0)   # :32-36
+    if event_mask is not None:
+        mask_pred = mask_pred & np.asarray(event_mask, dtype=bool)                                                    # :38-39
+    mask_gt = (~np.isinf(gt_flow[..., 0]) & ~np.isinf(gt_flow[..., 1])) & (np.linalg.norm(gt_flow, axis=-1) > 0)       # :42-46
+    inter = mask_pred & mask_gt                                                                                        # :49
+    pm, gm = pred_flow[inter], gt_flow[inter]                                                                          # :52-53
+    ee = np.linalg.norm(pm - gm, axis=-1)                                                                              # :56
+    ree = ee / (np.linalg.norm(gm, axis=-1) + EPSN)                                                                    # :59
+    cnts = {'n_ee': int(ee.shape[0]), 'n_pred': int(mask_pred.sum()), 'n_gt': int(mask_gt.sum())}                      # :65-67
+    with np.errstate(invalid='ignore'), __import__('warnings').catch_warnings():
+        __import__('warnings').simplefilter('ignore')
+        errs = {'AEE': float(ee.mean()) if ee.size else float('nan'),                                                  # :70 (mean of empty = nan)
+                'AREE': float(ree.mean()) if ree.size else float('nan')}                                               # :71
+    for n in N_PE_THRESHOLDS:
+        errs[f'A{n}PE'] = float((ee > n).sum() * 100 / (cnts['n_ee'] + EPSN))                                          # :73-74
+    return {'errors': errs, 'counts': cnts}
+
+
+def evaluate_theta_array(theta_array, xs, ys, ts, edges, edge_ts, gt_flow, alpha, beta, gamma, delta, sensor_size,
+                         err_eval_event_mask=None, wrap_negative=True) -> Dict:
+    """src/evaluations/theta_eval.py:14-95 (the numbers; the reference also formats a log line).  theta_array is the
+    sensor-size field (H, W, 2).  Note the un-weighted means (:27-29) and that TV / divergence enter regardless of the
+    pyramid level (:37-42), unlike loss_func."""
+    sensor_size = tuple(sensor_size)
+    theta_array = np.asarray(theta_array, dtype=np.float64)
+    lo = compute_loss_objectives(theta_array, xs, ys, ts, edges, edge_ts, sensor_size, wrap_negative=wrap_negative)   # :21-24
+    mean_rel_contrast = float(lo['rel_contrasts'].mean())                                                             # :27
+    mean_rel_corr = float(lo['rel_correlations'].mean())                                                              # :28
+    mean_rel_iwe_div = float(lo['rel_iwe_divergences'].mean())                                                        # :29
+    tot_var = float(lo['theta_total_variation'])                                                                      # :30
+    theta_div = float(lo['theta_divergence'])                                                                         # :31
+    fwl = float(lo['flow_warp_losses'][0])                                                                            # :32
+    l_iwe = events_to_pdf_frame(lo['warped_xs'][0], lo['warped_ys'][0], sensor_size, wrap_negative=wrap_negative)     # :36
+    loss = alpha * (-mean_rel_contrast) + beta * (-mean_rel_corr) + gamma * tot_var + delta * mean_rel_iwe_div        # :37-42
+    evals = {}
+    if gt_flow is not None:
+        pred_flow = per_pix_theta_to_flow(theta_array, xs, ys, ts)                                                    # :47
+        fe = sparse_flow_error(pred_flow, gt_flow, err_eval_event_mask)                                               # :48
+        evals.update(fe['errors']); evals.update(fe['counts'])                                                        # :61-62
+        evals['n_pixels'] = sensor_size[0] * sensor_size[1]                                                           # :59,63
+    evals.update({'loss': float(loss), 'iwe_var': float(np.var(l_iwe)), 'mean_rel_contrast': mean_rel_contrast,      # :80-94
+                  'mean_rel_corr': mean_rel_corr, 'theta_tot_var': tot_var, 'theta_div': theta_div, 'fwl': fwl,
+                  'mean_rel_iwe_div': mean_rel_iwe_div, 'rel_iwe_divergences': lo['rel_iwe_divergences'],
+                  'rel_contrasts': lo['rel_contrasts'], 'rel_correlations': lo['rel_correlations'],
+                  'flow_warp_losses': lo['flow_warp_losses'], 'multi_ref_weights': lo['multi_ref_weights']})
+    return evals
+
+
 def handover_loss_func(alpha_handover, prev_theta, theta, xs, ys, ts, edges, edge_ts,
                        alpha, beta, gamma, delta, cur_pyr_lvl, n_pyr_lvls, sensor_size,
                        scale_to_sensor_size_method='bilinear', wrap_negative=True) -> float:
