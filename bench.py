@@ -368,12 +368,15 @@ def run_own(args):
 
         def run_solves(backend, n_threads):
             """n_threads independent sequences per GPU, each: warm-up solve, then args.solve_windows chained windows."""
-            # more driving threads than host cores (e.g. 8 GPUs x 4 sequences on 16 cores): sleep on a blocking event instead
-            # of spinning in cudaStreamSynchronize
-            blocking = world * n_threads > max(1, len(os.sched_getaffinity(0)) - 2)
-            objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3),
-                                           flags=P.FLAG_BLOCKING_SYNC if blocking else 0)
+            # fewer host cores than driving threads (e.g. 8 GPUs x 4 sequences on 16 cores): the sequences of a GPU join an evaluation
+            # group - one thread launches the evaluations of all of them in a burst, the others sleep (include/eincm.h)
+            grouped = backend == 'native' and n_threads > 1 and len(os.sched_getaffinity(0)) // world < n_threads + 1
+            objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3))
                     for _ in range(n_threads)]
+            group = P.Group() if grouped else None
+            for o in objs:
+                if group is not None:
+                    o.plan.set_group(group)
             sols = [SV.MultipleLevelEINCMSolver(o, backend=backend, own_stream=(backend == 'native')) for o in objs]
             for t, sol in enumerate(sols):
                 sol.set_datasample(*wins[t % nw].args())
@@ -403,9 +406,11 @@ def run_own(args):
             n_ev = sum(o.n_evals for o in objs) - n0
             res = {'value': world * n_win / dt, 'unit': 'windows/s', 'sequences_per_gpu': n_threads, 'windows_per_sequence': args.solve_windows,
                    'ms_per_window': dt / args.solve_windows * 1e3, 'evals_per_window': n_ev / n_win,
-                   'final_loss': finals[0]['theta_opt_state_pyr']['pyr_lvl_0'].fun_val, 'host_wait': 'blocking event' if blocking else 'spin'}
+                   'final_loss': finals[0]['theta_opt_state_pyr']['pyr_lvl_0'].fun_val, 'host_threads': 'evaluation group (one launching thread per GPU)' if grouped else 'independent (one spinning thread per sequence)'}
             for o in objs:
                 o.close()
+            if group is not None:
+                group.close()
             return res
 
         solve = run_solves('native', min(4, nw))

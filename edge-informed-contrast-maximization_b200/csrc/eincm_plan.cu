@@ -12,9 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
 #include <utility>
+#include <vector>
 #include <vector>
 
 #include "common.cuh"
@@ -58,6 +61,7 @@ struct eincm_plan {
     unsigned long long* peer_fix[kMaxPeers] = {};   // event split with peer access: fixed-point images of all ranks (own included)
     void* peer_opened[kMaxPeers] = {};              // pointers obtained from cudaIpcOpenMemHandle (closed on destroy)
     int n_peers = 0;                                // 0: no peer access (the caller all-reduces the float64 images)
+    eincm_group* group = nullptr;        // evaluation group this plan rendezvous with inside eincm_minimize_bfgs_host (or null)
     cudaEvent_t wait_ev = nullptr;       // EINCM_FLAG_BLOCKING_SYNC: blocking-sync event the host entry points sleep on
     cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
     double host_seq = 0.0;               // sequence number of the last host evaluation (written back by its last kernel)
@@ -868,6 +872,84 @@ int eincm_value_and_grad_host(eincm_plan* plan, const double* theta_host, int h,
     return host_collect(plan, loss_out_host, grad_out_host, st);
 }
 
+}  // extern "C"
+
+// Rendezvous of the objective evaluations of concurrently running minimisations (see include/eincm.h).
+struct eincm_group {
+    struct Request {
+        eincm_plan* plan; const double* x; int h, w; const eincm_hparams* hp; double* f; double* g;
+        int rc = 0; bool done = false;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    int active = 0;                       // members currently inside a minimisation
+    bool in_flight = false;               // a burst is being launched / collected
+    std::vector<Request*> posted;         // evaluations waiting for the next burst
+    int device = -1;
+    int burst_percent = 100;              // share of the active members that must have posted before a burst is launched
+
+    void enter() { std::lock_guard<std::mutex> lk(mu); ++active; }
+    void leave() {
+        { std::lock_guard<std::mutex> lk(mu); --active; }
+        cv.notify_all();                  // the remaining members may now be complete: one of the waiters becomes the leader
+    }
+    // posts one evaluation and returns when it is done (launched by this thread or by another member)
+    int evaluate(Request& rq) {
+        std::unique_lock<std::mutex> lk(mu);
+        posted.push_back(&rq);
+        for (;;) {
+            if (rq.done) return rq.rc;
+            if (!in_flight && !posted.empty() && (int)posted.size() * 100 >= active * burst_percent) {
+                // every active member is waiting: this thread launches the burst
+                std::vector<Request*> burst;
+                burst.swap(posted);
+                in_flight = true;
+                lk.unlock();
+                for (Request* q : burst)
+                    q->rc = host_enqueue(q->plan, q->x, q->h, q->w, q->hp, true, q->plan->own_stream);
+                for (Request* q : burst) {
+                    if (q->rc == EINCM_OK) q->rc = host_collect(q->plan, q->f, q->g, q->plan->own_stream);
+                    else cudaStreamSynchronize(q->plan->own_stream);
+                }
+                lk.lock();
+                for (Request* q : burst) q->done = true;
+                in_flight = false;
+                cv.notify_all();
+                continue;                 // rq is part of the burst: returns at the top of the loop
+            }
+            cv.wait(lk);
+        }
+    }
+};
+
+extern "C" {
+
+int eincm_group_create(eincm_group** out) {
+    if (!out) return EINCM_EINVAL;
+    *out = new (std::nothrow) eincm_group();
+    return *out ? EINCM_OK : EINCM_ENOMEM;
+}
+
+void eincm_group_destroy(eincm_group* group) { delete group; }
+
+int eincm_group_set_burst_percent(eincm_group* group, int percent) {
+    if (!group || percent < 1 || percent > 100) return EINCM_EINVAL;
+    std::lock_guard<std::mutex> lk(group->mu);
+    group->burst_percent = percent;
+    return EINCM_OK;
+}
+
+int eincm_plan_set_group(eincm_plan* plan, eincm_group* group) {
+    if (!plan) return EINCM_EINVAL;
+    if (group) {
+        std::lock_guard<std::mutex> lk(group->mu);
+        if (group->device >= 0 && group->device != plan->device) return fail(plan, EINCM_EINVAL, "all plans of a group must live on one device");
+        group->device = plan->device;
+    }
+    plan->group = group;
+    return EINCM_OK;
+}
+
 int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
                              eincm_opt_result* result_out, void* cuda_stream) {
     if (!plan) return EINCM_EINVAL;
@@ -875,13 +957,20 @@ int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host, int h, 
     if (maxiter < 0) return fail(plan, EINCM_EINVAL, "maxiter must be >= 0");
     cudaStream_t st = cuda_stream == (void*)(intptr_t)-1 ? plan->own_stream : (cudaStream_t)cuda_stream;
     const int n = h * w * 2;
+    eincm_group* grp = plan->group;
     eincm_opt::Objective fun = [&](const double* x, double* f, double* g) -> int {
+        if (grp != nullptr) {             // rendezvous with the other sequences of the group: launched in a burst by one thread
+            eincm_group::Request rq{plan, x, h, w, hp, f, g};
+            return grp->evaluate(rq);
+        }
         const int rc = host_enqueue(plan, x, h, w, hp, true, st);
         if (rc) return rc;
         return host_collect(plan, f, g, st);
     };
     int err = 0;
+    if (grp != nullptr) grp->enter();
     const eincm_opt::Result r = eincm_opt::bfgs(fun, n, theta_inout_host, maxiter, gtol, &err);
+    if (grp != nullptr) grp->leave();
     if (err) return err;
     result_out->fun = r.fun; result_out->nit = r.nit; result_out->nfev = r.nfev; result_out->status = r.status; result_out->reserved = 0;
     return EINCM_OK;

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
     'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
     'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host', 'eincm_sparse_flow_error',
-    'eincm_evaluate_theta',
+    'eincm_evaluate_theta', 'eincm_group_create', 'eincm_group_destroy', 'eincm_plan_set_group', 'eincm_group_set_burst_percent',
 )
 
 
@@ -137,6 +137,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_minimize_handover_host': (i32, [vp, C.POINTER(dbl), dbl, dbl, vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
         'eincm_sparse_flow_error': (i32, [i32, i32, i32, vp, vp, vp, C.POINTER(FlowErrors), vp]),
         'eincm_evaluate_theta': (i32, [vp, vp, i32, i32, hp, vp, vp, C.POINTER(EvalMetrics), vp]),
+        'eincm_group_create': (i32, [C.POINTER(vp)]),
+        'eincm_group_destroy': (None, [vp]),
+        'eincm_plan_set_group': (i32, [vp, vp]),
+        'eincm_group_set_burst_percent': (i32, [vp, i32]),
         'eincm_plan_launch_count': (i64, [vp]),
         'eincm_plan_set_timing': (i32, [vp, i32]),
         'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
@@ -182,6 +186,33 @@ def value_and_grad_host_batch(plans: Sequence['Plan'], thetas: Sequence[np.ndarr
     if rc != EINCM_OK:
         raise EincmError(rc, (lib.eincm_last_error(plans[0]._h) or b'').decode())
     return losses, grads
+
+
+class Group:
+    """``eincm_group``: plans that joined the same group rendezvous their objective evaluations inside ``minimize_bfgs_host`` - one
+    thread launches the evaluations of all concurrently running minimisations in a burst, the others sleep (include/eincm.h)."""
+
+    def __init__(self, burst_percent: int = 100):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.eincm_group_create(C.byref(h))
+        if rc != 0:
+            raise EincmError(rc, 'eincm_group_create failed')
+        self._h = h
+        rc = self.lib.eincm_group_set_burst_percent(self._h, int(burst_percent))
+        if rc != 0:
+            raise EincmError(rc, 'burst_percent must be in 1..100')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.eincm_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _DevView:
@@ -383,6 +414,11 @@ class Plan:
         return loss.value, grad
 
     # -- read-outs --------------------------------------------------------------------------------------------
+    def set_group(self, group: Optional['Group']):
+        """Joins (or, with ``None``, leaves) an evaluation group: see ``Group``."""
+        self._check(self.lib.eincm_plan_set_group(self._h, group._h if group is not None else None))
+        self._group = group               # keeps the group alive as long as the plan refers to it
+
     # -- evaluation metrics of a solved window (reference src/evaluations/theta_eval.py) ----------------------------
     def evaluate_theta(self, theta, hp: HParams, gt_flow=None, err_eval_event_mask=None, stream=None) -> EvalMetrics:
         torch = _torch()

@@ -198,6 +198,25 @@ int eincm_get_scalars(eincm_plan* plan, double* out_host, int n_doubles, void* c
 /* Bit-exact event->pixel index stream of reference r for the last evaluated theta, in the ORIGINAL event
  * order: cols_out/rows_out [n_events] int32 = Xs_rounded of event_utils.py:33 (before the +dx,+dy taps). */
 int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int32_t* rows_out, void* cuda_stream);
+/* ---- evaluation groups: several sequences solved concurrently on one GPU, launched by one thread ---------------------------
+ * The reference solves one window at a time; on a B200 several independent sequences (one plan, one host thread each) are solved
+ * concurrently so that kernels of different windows overlap.  Plans that joined the same group rendezvous inside
+ * eincm_minimize_bfgs_host: a thread that needs an objective evaluation posts it and sleeps; when every member that is currently
+ * inside a minimisation has posted, one of them launches all the posted evaluations back to back (each on its plan's own stream),
+ * collects them and wakes the others.  Launches then come in bursts from ONE thread (the evaluations of a burst overlap on the GPU
+ * like eincm_value_and_grad_host_batch) and the waiting threads do not spin - the form to use when there are fewer host cores
+ * than sequences.  Results are identical to the ungrouped calls (each optimizer sees exactly its own evaluations). */
+typedef struct eincm_group eincm_group;
+int eincm_group_create(eincm_group** out);
+void eincm_group_destroy(eincm_group* group);
+/* A burst is launched as soon as `percent` % of the members that are inside a minimisation have posted (default 100: lock step).
+ * With 50 and twice as many sequences, one half evaluates on the GPU while the optimizers of the other half do their host-side
+ * work (line search, BFGS update). */
+int eincm_group_set_burst_percent(eincm_group* group, int percent);
+/* group == NULL leaves the group.  All plans of a group must live on one device.  Not thread-safe against a running minimisation
+ * of the same plan. */
+int eincm_plan_set_group(eincm_plan* plan, eincm_group* group);
+
 /* ---- evaluation metrics of a solved window (reference src/evaluations/theta_eval.py:14-95, flow_eval.py:14-75) ----------
  * Computed on the device from the images the evaluation leaves there; one call per solved window (not the optimisation hot path). */
 #define EINCM_EVAL_MAX_REFS 8

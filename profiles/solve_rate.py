@@ -17,6 +17,8 @@ ap.add_argument('--threads', type=int, default=4)
 ap.add_argument('--windows', type=int, default=2)
 ap.add_argument('--repeat', type=int, default=3)
 ap.add_argument('--blocking', action='store_true')
+ap.add_argument('--group', action='store_true', help='rendezvous the evaluations of the sequences (eincm_group)')
+ap.add_argument('--burst', type=int, default=100)
 a = ap.parse_args()
 dev = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(dev)
@@ -26,6 +28,10 @@ hpd = wins[0].hparams
 N, R = len(wins[0].xs), len(wins[0].edge_ts)
 objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3),
                                flags=P.FLAG_BLOCKING_SYNC if a.blocking else 0) for _ in range(a.threads)]
+grp = P.Group(a.burst) if a.group else None
+if grp is not None:
+    for o in objs:
+        o.plan.set_group(grp)
 sols = [SV.MultipleLevelEINCMSolver(o, backend='native', own_stream=True) for o in objs]
 for t, sol in enumerate(sols):
     sol.set_datasample(*wins[t % 4].args())
@@ -70,7 +76,7 @@ for rep in range(a.repeat):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     n_ev = sum(o.n_evals for o in objs) - n0
-    print(f'rank {os.environ.get("RANK", "-")} OMP={os.environ.get("OMP_NUM_THREADS", "-")} threads {a.threads} blocking {a.blocking}: '
+    print(f'rank {os.environ.get("RANK", "-")} OMP={os.environ.get("OMP_NUM_THREADS", "-")} threads {a.threads} blocking {a.blocking} group {a.group} burst {a.burst}: '
           f'{a.threads * a.windows / dt:.2f} windows/s, {n_ev / (a.threads * a.windows):.0f} evals/window, {dt / n_ev * 1e6:.0f} us wall per eval, '
           f'per-thread s {[round(x, 2) for x in per_thread]}', flush=True)
     g, c = probes()

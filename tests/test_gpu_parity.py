@@ -423,3 +423,58 @@ def test_native_solver_backend_matches_scipy_backend():
     f_n = out['native'][0]['theta_opt_state_pyr']['pyr_lvl_2'].fun_val
     f_s = out['scipy'][0]['theta_opt_state_pyr']['pyr_lvl_2'].fun_val
     assert f_n == pytest.approx(f_s, rel=1e-3)
+
+
+@pytest.mark.parametrize('burst', [100, 50])
+def test_evaluation_group_solves_match_independent_solves(burst):
+    """Sequences solved concurrently through an evaluation group (eincm_group: one thread launches the evaluations of all running
+    minimisations in a burst) reach what the same sequences reach when solved one after the other: every optimizer sees exactly its
+    own evaluations, so each level's end point is confirmed by the oracle and the coarsest level (one BFGS run from theta = 0)
+    agrees with the ungrouped run."""
+    import threading
+    from eincm_b200 import losses, plan as P, solver as SV
+    wins = [S.make_window(32, 48, 1500, seed=31 + k, n_segments=12, flow_mag=4.0) for k in range(3)]
+    base = dict(n_pyr_lvls=3, theta_opt_maxiters={'pyr_lvl_0': 8, 'pyr_lvl_1': 6, 'pyr_lvl_2': 5},
+                handover_opt_maxiters={'pyr_lvl_0': 4, 'pyr_lvl_1': 3, 'pyr_lvl_2': 2}, backend='native', own_stream=True)
+    kw = dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, n_pyr_lvls=5, sensor_size=(32, 48), scale_to_sensor_size_method='bilinear')
+
+    def run(grouped):
+        objs = [losses.WindowObjective((32, 48), 20.0, 35.0, max_events=4096, max_refs=3) for _ in wins]
+        grp = P.Group(burst) if grouped else None
+        res = [None] * len(wins)
+
+        def work(t):
+            import torch
+            torch.cuda.set_device(0)
+            res[t] = SV.solve_sequence(objs[t], [wins[t], wins[(t + 1) % 3]], dict(base))
+
+        if grouped:
+            for o in objs:
+                o.plan.set_group(grp)
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(len(wins))]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join(timeout=120)
+            assert not any(th.is_alive() for th in ths), 'evaluation group deadlocked'
+        else:
+            for t in range(len(wins)):
+                work(t)
+        for o in objs:
+            o.plan.set_group(None)
+            o.close()
+        if grp is not None:
+            grp.close()
+        return res
+
+    solo, grouped = run(False), run(True)
+    for t in range(3):
+        for wi, (w, r) in enumerate(zip((wins[t], wins[(t + 1) % 3]), grouped[t])):
+            for k in range(3):
+                key = f'pyr_lvl_{k}'
+                st = r['theta_opt_state_pyr'][key]
+                l_end = O.loss_func(r['pre_handover_theta_pyr'][key], *w.args(), cur_pyr_lvl=k, **kw)[0]
+                assert st.fun_val == pytest.approx(l_end, rel=OBJ_RTOL)
+        f_g = grouped[t][0]['theta_opt_state_pyr']['pyr_lvl_2'].fun_val
+        f_s = solo[t][0]['theta_opt_state_pyr']['pyr_lvl_2'].fun_val
+        assert f_g == pytest.approx(f_s, rel=1e-6)
