@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 #include <vector>
@@ -64,6 +66,8 @@ struct eincm_plan {
     eincm_group* group = nullptr;        // evaluation group this plan rendezvous with inside eincm_minimize_bfgs_host (or null)
     cudaEvent_t wait_ev = nullptr;       // EINCM_FLAG_BLOCKING_SYNC: blocking-sync event the host entry points sleep on
     cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
+    double host_enqueue_s = 0.0, host_wait_s = 0.0;   // wall time spent launching / waiting in the synchronous host entry points
+    int64_t host_evals = 0;
     double host_seq = 0.0;               // sequence number of the last host evaluation (written back by its last kernel)
     size_t host_ng = 0;                  // gradient doubles of the host evaluation in flight (host_enqueue -> host_collect)
     bool host_delivered = false;  // the last backward pass wrote its results into the mapped host buffer itself
@@ -795,9 +799,11 @@ int eincm_handover_value_and_grad(eincm_plan* plan, double alpha_handover, const
 
 namespace {
 
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // Enqueues one host-operand evaluation on `st`: theta through the pinned staging area, the four kernels, and - when the
 // results do not come back through mapped memory - the device -> host copy.  host_collect waits and hands the results over.
-int host_enqueue(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp, bool want_grad, cudaStream_t st) {
+int host_enqueue_impl(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp, bool want_grad, cudaStream_t st) {
     if (!theta_host) return fail(plan, EINCM_EINVAL, "NULL operand");
     if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
     if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "event-split plans use the split-phase calls");
@@ -834,18 +840,26 @@ int host_wait(eincm_plan* plan, cudaStream_t st) {
     return EINCM_OK;
 }
 
-int host_collect(eincm_plan* plan, double* loss_out_host, double* grad_out_host, cudaStream_t st) {
+int host_collect_impl(eincm_plan* plan, double* loss_out_host, double* grad_out_host, cudaStream_t st) {
     const double* h_res = plan->host_delivered ? plan->h_pinned + (size_t)plan->HW * 2 + 16 : plan->h_pinned;   // [grad | loss]
     bool arrived = false;
     if (plan->host_delivered && plan->wait_ev == nullptr) {
         // the last kernel wrote [grad | loss | d alpha | sequence number] into mapped pinned memory: poll the sequence number
         // there (bounded; an error or a very long evaluation ends in the stream synchronisation below)
         const volatile double* seq = h_res + plan->host_ng + 2;
-        for (long spin = 0; spin < 20000000L; ++spin) {
+        // a short pure spin (lowest latency), then yield between polls: on a host with fewer cores than driving threads the
+        // optimizers of the other sequences get the core while this thread waits; with idle cores the yield returns at once
+        const double t_end = now_s() + 2.0;
+        for (long spin = 0;; ++spin) {
             if (*seq == plan->host_seq) { arrived = true; break; }
+            if (spin < 4000) {
 #if defined(__x86_64__) || defined(__i386__)
-            __builtin_ia32_pause();
+                __builtin_ia32_pause();
 #endif
+            } else {
+                std::this_thread::yield();
+                if ((spin & 1023) == 0 && now_s() > t_end) break;
+            }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
     }
@@ -856,6 +870,21 @@ int host_collect(eincm_plan* plan, double* loss_out_host, double* grad_out_host,
     *loss_out_host = h_res[plan->host_ng];
     if (grad_out_host) std::memcpy(grad_out_host, h_res, plan->host_ng * sizeof(double));
     return EINCM_OK;
+}
+
+int host_enqueue(eincm_plan* plan, const double* theta_host, int h, int w, const eincm_hparams* hp, bool want_grad, cudaStream_t st) {
+    const double t0 = now_s();
+    const int rc = host_enqueue_impl(plan, theta_host, h, w, hp, want_grad, st);
+    plan->host_enqueue_s += now_s() - t0;
+    return rc;
+}
+
+int host_collect(eincm_plan* plan, double* loss_out_host, double* grad_out_host, cudaStream_t st) {
+    const double t0 = now_s();
+    const int rc = host_collect_impl(plan, loss_out_host, grad_out_host, st);
+    plan->host_wait_s += now_s() - t0;
+    plan->host_evals += 1;
+    return rc;
 }
 
 }  // namespace
@@ -1331,6 +1360,15 @@ int eincm_evaluate_theta(eincm_plan* plan, const double* theta, int h, int w, co
         flow_errors_from_sums(hres + EINCM_MAX_REFS + 2, &m.flow);
     }
     *out_host = m;
+    return EINCM_OK;
+}
+
+int eincm_plan_host_times(eincm_plan* plan, double* enqueue_s, double* wait_s, int64_t* n_evals, int reset) {
+    if (!plan) return EINCM_EINVAL;
+    if (enqueue_s) *enqueue_s = plan->host_enqueue_s;
+    if (wait_s) *wait_s = plan->host_wait_s;
+    if (n_evals) *n_evals = plan->host_evals;
+    if (reset) { plan->host_enqueue_s = plan->host_wait_s = 0.0; plan->host_evals = 0; }
     return EINCM_OK;
 }
 

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
     'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
     'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host', 'eincm_sparse_flow_error',
-    'eincm_evaluate_theta', 'eincm_group_create', 'eincm_group_destroy', 'eincm_plan_set_group', 'eincm_group_set_burst_percent',
+    'eincm_evaluate_theta', 'eincm_group_create', 'eincm_group_destroy', 'eincm_plan_set_group', 'eincm_group_set_burst_percent', 'eincm_plan_host_times',
 )
 
 
@@ -141,6 +141,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_group_destroy': (None, [vp]),
         'eincm_plan_set_group': (i32, [vp, vp]),
         'eincm_group_set_burst_percent': (i32, [vp, i32]),
+        'eincm_plan_host_times': (i32, [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), i32]),
         'eincm_plan_launch_count': (i64, [vp]),
         'eincm_plan_set_timing': (i32, [vp, i32]),
         'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
@@ -467,6 +468,12 @@ class Plan:
                 'theta_total_variation': a[4], 'zero_contrast': a[5], 'zero_iwe_divergence': a[6], 'dalpha_handover': a[7],
                 'contrasts': per[0].copy(), 'correlations': per[1].copy(), 'zero_correlations': per[2].copy(),
                 'iwe_divergences': per[3].copy(), 'multi_ref_weights': per[4].copy()}
+
+    def host_times(self, reset: bool = False):
+        """(seconds launching, seconds waiting, evaluations) of the synchronous host entry points since the last reset."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self.lib.eincm_plan_host_times(self._h, C.byref(a), C.byref(b), C.byref(n), int(reset)))
+        return a.value, b.value, n.value
 
     def launch_count(self) -> int:
         return int(self.lib.eincm_plan_launch_count(self._h))

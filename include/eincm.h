@@ -251,6 +251,9 @@ int eincm_evaluate_theta(eincm_plan* plan, const double* theta, int h, int w, co
                          const uint8_t* err_eval_event_mask, eincm_eval_metrics* out_host, void* cuda_stream);
 
 /* ---- measurement hooks (bench.py): launch accounting and optional per-kernel CUDA-event timing -------- */
+/* wall time the synchronous host entry points of this plan spent launching (enqueue_s) and waiting for results (wait_s) over
+ * n_evals evaluations since the last reset: shows whether a solve loop is bound by the host or by the GPU */
+int eincm_plan_host_times(eincm_plan* plan, double* enqueue_s, double* wait_s, int64_t* n_evals, int reset);
 /* number of kernels this plan has launched since creation (memsets / copies not counted) */
 int64_t eincm_plan_launch_count(const eincm_plan* plan);
 /* enabled != 0: bracket every subsequent kernel launch with CUDA events on the launching stream */

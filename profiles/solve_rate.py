@@ -79,5 +79,7 @@ for rep in range(a.repeat):
     print(f'rank {os.environ.get("RANK", "-")} OMP={os.environ.get("OMP_NUM_THREADS", "-")} threads {a.threads} blocking {a.blocking} group {a.group} burst {a.burst}: '
           f'{a.threads * a.windows / dt:.2f} windows/s, {n_ev / (a.threads * a.windows):.0f} evals/window, {dt / n_ev * 1e6:.0f} us wall per eval, '
           f'per-thread s {[round(x, 2) for x in per_thread]}', flush=True)
+    ht = [o.plan.host_times(reset=True) for o in objs]
+    print('   host per eval (us): launch ' + ' '.join(f'{x[0] / max(x[2], 1) * 1e6:.0f}' for x in ht) + ' | wait ' + ' '.join(f'{x[1] / max(x[2], 1) * 1e6:.0f}' for x in ht), flush=True)
     g, c = probes()
     print(f'   probes: GPU {g:.0f} us per device-resident eval, CPU loop {c:.1f} ms', flush=True)
