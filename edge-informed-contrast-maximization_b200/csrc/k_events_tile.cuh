@@ -4,21 +4,25 @@
 // (k_prep.cuh); every tile's segment is padded to a multiple of kEvK events and cut into chunks of <= kChunk events.
 // One CTA owns one chunk.  Because all events of a chunk start inside one 16x16 tile, their warped 3x3 patches
 // (reference src/utils/event_utils.py:41-59) fall into a small rectangle of the destination image per reference time:
-// the CTA measures that rectangle (pre-pass: warp + rint only), keeps it as a window in shared memory, votes into it
+// the CTA bounds that rectangle (interval arithmetic on the tile's theta range and the chunk's t range), keeps it as a window in shared memory, votes into it
 // with native 32-bit shared-memory integer atomics (ATOMS.ADD), and finally adds the non-zero window cells to the
 // global image with one 64-bit integer reduction each.  Votes are fixed point, 2^kFixShift * (2 pi v):
 //   * shared-memory float atomics are CAS loops on sm_100a, integer adds are native (see profiles/microbench);
 //   * integer sums do not depend on the order of the votes, so the image of warped events - and therefore the
 //     objective - is bit-reproducible from run to run, which matters to BFGS with gtol = 1e-7 (main.yaml:34).
 // A vote is quantised to 2^-21 of the centre-tap value (4.8e-7, about 4 float32 ulps of the largest tap); coordinates,
-// the warp and rint() stay float64, so pixel indices are bit-exact.  Events whose patch leaves the window (bounding
-// rectangle larger than kWinCap cells: very large flow) fall back to per-tap global reductions.  The reference's index
-// rule (negative indices wrap, out of range drops: SURVEY.md A.4) is applied once per window cell at flush time.
+// the warp and rint() stay float64, so pixel indices are bit-exact.  A rectangle larger than kWinCap cells (flows beyond
+// ~45 px per window) is processed in row SLICES, one more pass over the chunk per RB slices; events outside a rectangle
+// cropped at kMaxSlices slices / kWinMaxW columns, or exactly on a rounding boundary between slices, fall back to per-tap
+// global reductions.  The reference's index rule (negative indices wrap, out of range drops: SURVEY.md A.4) is applied
+// once per window cell at flush time.
 //
-// Backward: the same windows (recorded by the forward pass) are filled with d loss / d IWE and the nine taps of every
-// event are read from shared memory instead of global memory.
+// Backward: the same rectangles (recorded by the forward pass) are filled with d loss / d IWE and the nine taps of every
+// event are read from shared memory instead of global memory; of a sliced rectangle the backward pass keeps the first
+// slice and gathers the rest from the global image (it only reads: measured cheaper than further passes).
 #pragma once
 #include <climits>
+#include <type_traits>
 
 #include "common.cuh"
 #include "k_events.cuh"
@@ -76,7 +80,6 @@ __device__ __forceinline__ void red_G(double* __restrict__ G, int W, uint32_t xy
 constexpr int kChunk = (int)kChunkEvents;   // events per chunk = kEvK events per thread x 256 threads
 static_assert(kChunk == kEvK * 256 && kStreamAlign == kEvK, "one chunk = one CTA pass of kEvK events per thread");
 constexpr int kWinCap = 4096;         // window cells per reference time (16 KB of uint32 / float)
-constexpr int kWinMaxH = 64;          // rows kept when the bounding rectangle exceeds kWinCap
 constexpr int kFixShift = 21;
 constexpr double kFixToIwe = kInv2Pi / 2097152.0;        // fixed-point sum -> image value
 // float -> fixed point by mantissa alignment: for 0 <= p <= 1, the float 6 + p lies in [4, 8) where one ulp is 2^-21, so
@@ -134,7 +137,10 @@ __device__ __forceinline__ void load_chunk_events(const uint32_t* __restrict__ e
 // votes into the window when its rounded centre lies in [ox + 1, ox + pw - 2] x [oy + 1, oy + ph - 2]; the kernels test that on
 // the float64 warped coordinate itself, |x' - cx| < hx (strict: a coordinate exactly on the rounding boundary takes the
 // fallback), which also rejects NaN / infinite / absurdly far warps in the same two comparisons.
-struct Window { int ox, oy, pw, ph; double cx, hx, cy, hy; uint32_t inv_pw, interior; };   // inv_pw = ceil(2^32 / pw): exact i / pw for i < 2^16
+struct Window {
+    int ox, oy, pw, ph; double cx, hx, cy, hy; uint32_t inv_pw, interior;   // inv_pw = ceil(2^32 / pw): exact i / pw for i < 2^16
+    double tr; int img, pad;                                                // reference time and image the window belongs to
+};
 
 __device__ __forceinline__ Window make_window(int ox, int oy, int pw, int ph) {
     Window w;
@@ -144,6 +150,7 @@ __device__ __forceinline__ Window make_window(int ox, int oy, int pw, int ph) {
     if (pw < 3 || ph < 3) { w.hx = -1.0; w.hy = -1.0; }
     w.inv_pw = pw > 0 ? 0xffffffffu / (uint32_t)pw + 1u : 0u;
     w.interior = 0u;
+    w.tr = 0.0; w.img = 0; w.pad = 0;
     return w;
 }
 
@@ -152,25 +159,98 @@ __device__ __forceinline__ void set_interior(Window& w, int H, int W) {
     w.interior = (w.ox >= 0 && w.oy >= 0 && w.ox + w.pw <= W && w.oy + w.ph <= H) ? 1u : 0u;
 }
 
-// window that holds the centres [mnx, mxx] x [mny, mxy] (cropped to kWinCap cells: the events outside take the fallback)
-__device__ __forceinline__ Window bound_window(int mnx, int mny, int mxx, int mxy) {
+// Destination rectangle of one (chunk, reference time) as (ox, oy, pw, ph): holds the centres [mnx, mxx] x [mny, mxy] plus a halo
+// of one cell.  A rectangle larger than a shared-memory window (kWinCap cells: large flows) is processed in SLICES of complete
+// rows, one pass over the chunk's events per slice, each slice being an ordinary window (centre rows partitioned, halo rows
+// shared); only rectangles wider than kWinMaxW cells or taller than kMaxSlices slices are cropped - the events outside take
+// the per-tap global fallback.
+constexpr int kWinMaxW = kWinCap / 3;   // a window needs at least three rows
+constexpr int kMaxSlices = 16;
+constexpr int kMissThreadsPerPass = 2;    // more threads (of 256) than this with left-over events justify one more pass over the chunk
+
+__device__ __forceinline__ int slice_rows(int pw) { return kWinCap / pw - 2; }       // centre rows per slice of a pw-wide rectangle
+
+__device__ __forceinline__ int4 bound_rect(int mnx, int mny, int mxx, int mxy) {
     long long bw = (long long)mxx - mnx + 3, bh = (long long)mxy - mny + 3;
+    if (bw > kWinMaxW) bw = kWinMaxW;
     if (bw * bh > kWinCap) {
-        if (bh > kWinMaxH) bh = kWinMaxH;
-        if (bw > kWinCap / bh) bw = kWinCap / bh;
+        const long long max_h = (long long)slice_rows((int)bw) * kMaxSlices + 2;
+        if (bh > max_h) bh = max_h;
     }
-    return make_window(mnx - 1, mny - 1, (int)bw, (int)bh);
+    return make_int4(mnx - 1, mny - 1, (int)bw, (int)bh);
+}
+
+__device__ __forceinline__ int n_slices(const int4 rect) {
+    if (rect.z < 3 || rect.w < 3) return 0;
+    if (rect.z * rect.w <= kWinCap) return 1;
+    const int hs = slice_rows(rect.z);
+    return (rect.w - 2 + hs - 1) / hs;
+}
+
+// window of slice s of a rectangle (an empty window when the rectangle has fewer slices)
+__device__ __forceinline__ Window slice_window(const int4 rect, int s) {
+    if (s >= n_slices(rect)) return make_window(0, 0, 0, 0);
+    if (rect.z * rect.w <= kWinCap) return make_window(rect.x, rect.y, rect.z, rect.w);
+    const int hs = slice_rows(rect.z);
+    const int first = rect.y + 1 + s * hs;                                  // first centre row of the slice
+    const int n = min(hs, rect.y + rect.w - 1 - first);                     // centre rows: up to rect.y + ph - 2
+    return make_window(rect.x, first - 1, rect.z, n + 2);
+}
+
+// A pass of the event kernels holds RB windows.  The windows of a chunk are its (reference time, slice) PAIRS: pair j < R is the first
+// slice of reference time j (pairs R .. Rpad - 1 are empty, Rpad = R rounded up to a multiple of RB), the further slices of sliced
+// rectangles follow in reference-major order from pair Rpad: off[r] = index of the pair of slice 1 of reference r, off[R] = number
+// of pairs (= Rpad unless a rectangle is sliced).  Window of pair j (an empty window where there is none).
+__device__ __forceinline__ Window pair_window(const int4* rects, const int* off, int R, int Rpad, int j, const RefTimes& tref, int H, int W) {
+    Window wn = make_window(0, 0, 0, 0);
+    if (j < R) {
+        wn = slice_window(rects[j], 0);
+        wn.tr = tref.t[j];
+        wn.img = j;
+    } else if (j >= Rpad && j < off[R]) {
+        int r = 0;
+        while (off[r + 1] <= j) ++r;
+        wn = slice_window(rects[r], j - off[r] + 1);
+        wn.tr = tref.t[r];
+        wn.img = r;
+    }
+    set_interior(wn, H, W);
+    return wn;
+}
+
+// slice counts of the lanes' rectangles -> off[] (warp-wide, lanes >= R pass ns = 0)
+__device__ __forceinline__ void pair_offsets(int ns, int R, int Rpad, int* off) {
+    const int lane = threadIdx.x & 31;
+    int incl = max(ns - 1, 0);
+#pragma unroll
+    for (int o = 1; o < EINCM_MAX_REFS; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane < R) off[lane + 1] = Rpad + incl;
+    if (lane == 0) off[0] = Rpad;
+}
+
+// true when the warped coordinate votes into one of the slices of the rectangle (the hit test of the hot loops, replayed
+// out of line: a coordinate exactly on the rounding boundary between two slices belongs to neither and takes the fallback)
+__device__ __noinline__ bool hits_rect(const int4 rect, double xw, double yw, int max_slices) {
+    const int ns = min(n_slices(rect), max_slices);
+    for (int s = 0; s < ns; ++s) {
+        const Window w = slice_window(rect, s);
+        if ((fabs(xw - w.cx) < w.hx) & (fabs(yw - w.cy) < w.hy)) return true;
+    }
+    return false;
 }
 
 // float <-> int32 with the same ordering (for REDUX.MIN / REDUX.MAX); NaN maps beyond +-inf and survives the round trip
 __device__ __forceinline__ int ordered_int(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-// Conservative window of one chunk and one reference time: every event of the chunk starts inside the 16x16 source tile at
+// Conservative destination rectangle of one chunk and one reference time: every event of the chunk starts inside the 16x16 source tile at
 // (x0, y0), has theta inside [thx_lo, thx_hi] x [thy_lo, thy_hi] (range over the tile) and t inside [t_lo, t_hi] (range over
 // the chunk, k_chunk_trange), so x' = x - theta_x (t - t_ref) lies inside an interval known without touching the events.
 // float32 interval arithmetic with explicit slack; rint(x') of every event is inside [floor(lo + 0.49), ceil(hi - 0.49)].
-__device__ __forceinline__ Window chunk_window(int x0, int y0, int x1, int y1, float thx_lo, float thx_hi, float thy_lo, float thy_hi,
+__device__ __forceinline__ int4 chunk_rect(int x0, int y0, int x1, int y1, float thx_lo, float thx_hi, float thy_lo, float thy_hi,
                                                float t_lo, float t_hi, double t_ref) {
     const float trf = (float)t_ref;
     const float es = 1.0e-6f * (1.f + fabsf(trf) + fmaxf(fabsf(t_lo), fabsf(t_hi)));
@@ -184,8 +264,8 @@ __device__ __forceinline__ Window chunk_window(int x0, int y0, int x1, int y1, f
     // the comparison is false for NaN (theta or t not finite): no window, every event of the chunk takes the fallback
     const bool finite = (lox > -1.0e9f) && (hix < 1.0e9f) && (loy > -1.0e9f) && (hiy < 1.0e9f) &&
                         (fabsf(thx_lo) + fabsf(thx_hi) + fabsf(thy_lo) + fabsf(thy_hi) < 3.0e38f) && (d_hi - d_lo < 3.0e38f);
-    if (!finite) return make_window(0, 0, 0, 0);
-    return bound_window(__float2int_rd(lox + 0.49f - mx), __float2int_rd(loy + 0.49f - my),
+    if (!finite) return make_int4(0, 0, 0, 0);
+    return bound_rect(__float2int_rd(lox + 0.49f - mx), __float2int_rd(loy + 0.49f - my),
                         __float2int_ru(hix - 0.49f + mx), __float2int_ru(hiy - 0.49f + my));
 }
 
@@ -361,36 +441,28 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ int sbox[8][4];
     __shared__ Window swin[RB];
+    __shared__ int4 srect[EINCM_MAX_REFS];
+    __shared__ int s_off[EINCM_MAX_REFS + 1];
+    __shared__ int s_sliced;
     const int64_t HW = (int64_t)H * W;
     const int tid = threadIdx.x;
     const int n_chunks = (int)__ldg(n_chunks_dev);
     const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(win);
+    const int Rpad = (R + RB - 1) / RB * RB;
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
         EventGroup ev;
         load_chunk_events<true>(ev_xy, ev_t, ch, ev);
         tile_theta_range(tile_theta(T, ch.origin, H, W, th_s), sbox);
         const bool active = (ev.xy[0] != kNoEvent);      // groups are padded at their end only
-        for (int r0 = 0; r0 < R; r0 += RB) {
-            __syncthreads();                         // th_s / sbox ready (first pass); previous flush done
-            if (tid < RB) {
-                Window wn = make_window(0, 0, 0, 0);
-                if (r0 + tid < R) {
-                    int ax = sbox[0][0], bx = sbox[0][1], ay = sbox[0][2], by = sbox[0][3];
-#pragma unroll
-                    for (int w8 = 1; w8 < 8; ++w8) {
-                        ax = min(ax, sbox[w8][0]); bx = max(bx, sbox[w8][1]); ay = min(ay, sbox[w8][2]); by = max(by, sbox[w8][3]);
-                    }
-                    const float2 tr = __ldg(chunk_tr + c);
-                    const int x0 = (int)(ch.origin & 0xffffu), y0 = (int)(ch.origin >> 16);
-                    wn = chunk_window(x0, y0, min(x0 + kSortTile, W) - 1, min(y0 + kSortTile, H) - 1, ordered_float(ax), ordered_float(bx),
-                                      ordered_float(ay), ordered_float(by), tr.x, tr.y, tref.t[r0 + tid]);
-                    if (chunk_win != nullptr) chunk_win[(int64_t)c * R + r0 + tid] = make_int4(wn.ox, wn.oy, wn.pw, wn.ph);
-                }
-                set_interior(wn, H, W);
-                swin[tid] = wn;
-            }
-            __syncthreads();
+        if (tid == 0) s_sliced = 0;
+        int n_pairs = 0;                             // only used by the passes over further slices
+        // misses are rare: the hot loop only counts hits; a thread whose count falls short repeats the window tests below
+        int n_hit = 0;
+        // One pass over the chunk for the windows of pairs p0 .. p0 + RB - 1.  PLAIN: pair j is reference time j (p0 < Rpad).
+        auto pass = [&](auto plain_tag, const int p0) {
+            constexpr bool PLAIN = decltype(plain_tag)::value;
+            const int p_end = PLAIN ? R : n_pairs;
             // zero the cells in use
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
@@ -399,19 +471,14 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
             }
             __syncthreads();
             // votes
-            // misses are rare: the hot loop only counts hits; a thread whose count falls short repeats the window tests below
-            int n_hit = 0, n_valid = 0;
             if (active) {
 #pragma unroll
-                for (int k = 0; k < kEvK; ++k) n_valid += ev.xy[k] != kNoEvent ? 1 : 0;
-                n_valid *= min(RB, R - r0);
-#pragma unroll
                 for (int r = 0; r < RB; ++r) {
-                    if (r0 + r >= R) continue;
+                    if (p0 + r >= p_end) continue;
                     const Window wn = swin[r];
                     const uint32_t pitch4 = (uint32_t)wn.pw * 4u;
                     const uint32_t wb = win_base + (uint32_t)(r * kWinCap - (wn.oy * wn.pw + wn.ox)) * 4u;   // address of cell (0, 0) of the image
-                    const double tr = tref.t[r0 + r];
+                    const double tr = PLAIN ? tref.t[p0 + r] : wn.tr;
                     // A thread's events are consecutive in the sorted stream (same source pixel, ascending time), so consecutive
                     // votes often share their centre cell: the nine tap sums stay pending in registers and go to shared memory
                     // only when the centre changes.  The shared-memory atomic pipe is the limiter of this kernel (ncu: l1tex ~73 %,
@@ -441,30 +508,15 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                     if (acc_addr != kNone) emit9(acc_addr, pitch4, acc);
                 }
             }
-            if (n_hit != n_valid) {
-#pragma unroll
-                for (int k = 0; k < kEvK; ++k) {
-                    if (ev.xy[k] == kNoEvent) continue;
-                    const double2 th = lds_theta(th_base, ev.xy[k]);
-#pragma unroll 1
-                    for (int r = 0; r < RB && r0 + r < R; ++r) {
-                        const double dt = ev.t[k] - tref.t[r0 + r];
-                        const Hit2 h = warp_hit2(ev.xy[k], th, dt);
-                        const Window& wn = swin[r];
-                        if (!((fabs(h.xw - wn.cx) < wn.hx) & (fabs(h.yw - wn.cy) < wn.hy)))
-                            splat_fallback<WRAP>(dst, (int64_t)(r0 + r) * HW, ev.xy[k], th, dt, H, W);
-                    }
-                }
-            }
             __syncthreads();
             // flush: non-zero window cells -> global fixed-point image (index rule applied here unless the window is interior).
             // Four cells per thread and round (one 128-bit load); most cells of a window are zero.
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
-                if (r0 + r >= R) continue;
+                if (p0 + r >= p_end) continue;
                 const Window wn = swin[r];
                 const uint4* wr4 = reinterpret_cast<const uint4*>(win + r * kWinCap);
-                const int64_t img_off = (int64_t)(r0 + r) * HW;
+                const int64_t img_off = (int64_t)(PLAIN ? p0 + r : wn.img) * HW;
                 const int cells = wn.pw * wn.ph;
                 const bool interior = wn.interior != 0u;
                 const uint32_t inv_pw = wn.inv_pw;
@@ -489,8 +541,75 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
                     }
                 }
             }
+        };
+        auto count_valid = [&]() {                   // event-reference pairs of the thread
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < kEvK; ++k) n += ev.xy[k] != kNoEvent ? 1 : 0;
+            return active ? n * R : 0;
+        };
+        // first slice of every reference time, RB reference times per pass (no rectangle is sliced in the common case)
+        for (int r0 = 0; r0 < R; r0 += RB) {
+            __syncthreads();                         // th_s / sbox ready (first pass); previous flush done
+            if (tid < RB) {
+                int4 rect = make_int4(0, 0, 0, 0);
+                if (r0 + tid < R) {
+                    int ax = sbox[0][0], bx = sbox[0][1], ay = sbox[0][2], by = sbox[0][3];
+#pragma unroll
+                    for (int w8 = 1; w8 < 8; ++w8) {
+                        ax = min(ax, sbox[w8][0]); bx = max(bx, sbox[w8][1]); ay = min(ay, sbox[w8][2]); by = max(by, sbox[w8][3]);
+                    }
+                    const float2 tr = __ldg(chunk_tr + c);
+                    const int x0 = (int)(ch.origin & 0xffffu), y0 = (int)(ch.origin >> 16);
+                    rect = chunk_rect(x0, y0, min(x0 + kSortTile, W) - 1, min(y0 + kSortTile, H) - 1, ordered_float(ax), ordered_float(bx),
+                                      ordered_float(ay), ordered_float(by), tr.x, tr.y, tref.t[r0 + tid]);
+                    if (chunk_win != nullptr) chunk_win[(int64_t)c * R + r0 + tid] = rect;
+                    srect[r0 + tid] = rect;
+                    if (n_slices(rect) > 1) s_sliced = 1;
+                }
+                Window wn = slice_window(rect, 0);
+                set_interior(wn, H, W);
+                swin[tid] = wn;
+            }
+            __syncthreads();
+            pass(std::true_type{}, r0);
         }
-        __syncthreads();                             // th_s / sbox / swin are rewritten for the next chunk
+        // Further slices of sliced rectangles (large flows).  The rectangles are conservative bounds: when (almost) no event is
+        // left over after the first slices, the out-of-line fallback is cheaper than more passes over the whole chunk.  The
+        // threshold is low because the fallback of a thread is serial while the rest of the CTA waits (measured: 16 threads per
+        // pass made 50 .. 120 px flows 15 - 50 % slower than always slicing, profiles/r1_large_flow.txt).
+        int slices_done = kMaxSlices;
+        if (s_sliced != 0) {
+            const int n_thr = __syncthreads_count(n_hit != count_valid());      // also: flush done
+            if (tid < 32) pair_offsets(tid < R ? n_slices(srect[tid]) : 0, R, Rpad, s_off);
+            __syncthreads();
+            n_pairs = s_off[R];
+            if (n_thr > kMissThreadsPerPass * ((n_pairs - Rpad + RB - 1) / RB)) {
+                for (int p0 = Rpad; p0 < n_pairs; p0 += RB) {
+                    if (p0 > Rpad) __syncthreads();  // flush done
+                    if (tid < RB) swin[tid] = pair_window(srect, s_off, R, Rpad, p0 + tid, tref, H, W);
+                    __syncthreads();
+                    pass(std::false_type{}, p0);
+                }
+            } else {
+                slices_done = 1;
+            }
+        }
+        if (n_hit != count_valid()) {                // events outside the (possibly cropped) rectangles, non-finite warps
+#pragma unroll
+            for (int k = 0; k < kEvK; ++k) {
+                if (ev.xy[k] == kNoEvent) continue;
+                const double2 th = lds_theta(th_base, ev.xy[k]);
+#pragma unroll 1
+                for (int r = 0; r < R; ++r) {
+                    const double dt = ev.t[k] - tref.t[r];
+                    const Hit2 h = warp_hit2(ev.xy[k], th, dt);
+                    if (!hits_rect(srect[r], h.xw, h.yw, slices_done))
+                        splat_fallback<WRAP>(dst, (int64_t)r * HW, ev.xy[k], th, dt, H, W);
+                }
+            }
+        }
+        __syncthreads();                             // th_s / sbox / swin / srect are rewritten for the next chunk
     }
 }
 
@@ -531,7 +650,7 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
             if (tid < RB) {
                 int4 q = make_int4(0, 0, 0, 0);
                 if (r0 + tid < R) q = chunk_win[(int64_t)c * R + r0 + tid];
-                Window wn = make_window(q.x, q.y, q.z, q.w);
+                Window wn = slice_window(q, 0);      // a sliced rectangle (large flow): first slice here, the rest gathers from the global image
                 set_interior(wn, H, W);
                 swin[tid] = wn;
             }

@@ -298,16 +298,33 @@ def test_full_size_properties_dsec(L):
     p.close()
 
 
-@pytest.mark.parametrize('flow', [(300.0, -250.0), (-45.0, 70.0), (0.0, 1500.0)])
+@pytest.mark.parametrize('flow', [(300.0, -250.0), (-45.0, 70.0), (0.0, 1500.0), (60.0, -55.0), (110.0, 15.0), (-20.0, 190.0)])
 def test_large_flow_takes_the_window_fallback(L, flow):
-    """Flows far larger than a shared-memory window can hold: the bounding rectangle is clipped and most votes take the
-    per-tap global reductions (forward) / global gathers (backward); many warps leave the sensor (wrap / drop rule)."""
+    """Flows larger than one shared-memory window can hold: the destination rectangle of a chunk is processed in row slices
+    (60 .. 190 px), and beyond 16 slices / 1365 columns it is cropped and the remaining votes take the per-tap global
+    reductions (forward) / global gathers (backward); many warps leave the sensor (wrap / drop rule)."""
     w = S.make_workload('dsec_shipped', seed=4, n_events=60_000)
     kw = dict(w.hparams, cur_pyr_lvl=1, n_pyr_lvls=5, sensor_size=w.sensor_size, scale_to_sensor_size_method='bilinear')
     th = np.zeros((2, 2, 2)); th[..., 0] = flow[0]; th[..., 1] = flow[1]
     th += np.random.default_rng(5).normal(0.0, 3.0, size=th.shape)
     loss, grad = L.value_and_grad(L.loss_func)(th, *w.args(), **kw)
     l_ref, g_ref = O.value_and_grad(th, *w.args(), **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize('c', [64.0, 96.0])
+def test_sliced_windows_with_coordinates_on_rounding_boundaries(L, c):
+    """Dyadic timestamps and a dyadic constant flow put thousands of warped coordinates exactly on k + 0.5 (round half to even,
+    event_utils.py:33), some of them on the row that separates two slices of a sliced destination rectangle: those belong to
+    neither slice and must take the fallback exactly once."""
+    w = S.make_workload('dsec_shipped', seed=9, n_events=40_000)
+    ts = np.sort(np.round(w.ts * 128.0) / 128.0)
+    kw = dict(w.hparams, cur_pyr_lvl=4, n_pyr_lvls=5, sensor_size=w.sensor_size, scale_to_sensor_size_method='bilinear')
+    th = np.zeros((1, 1, 2)); th[..., 0] = c; th[..., 1] = -c
+    p = L.value_and_grad(L.loss_func)
+    loss, grad = p(th, w.xs, w.ys, ts, w.edges, w.edge_ts, **kw)
+    l_ref, g_ref = O.value_and_grad(th, w.xs, w.ys, ts, w.edges, w.edge_ts, **kw)
     assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
     assert _rel_inf(grad, g_ref) <= GRAD_RTOL
 
