@@ -175,6 +175,62 @@ def time_cpu(win, theta, steps, warmup, budget_s):
             'ms_per_step': dt / steps * 1e3, 'n_sample': n_sample}
 
 
+def time_edge_maps(H, W, R, cpu=True, reps=20):
+    """Edge-image stage of one window: R uint8 frames (pinned host memory) -> Canny -> Gaussian -> normalise, result on the device
+    (eincm_b200.img_utils.edge_maps -> eincm_edge_maps).  CPU side: OpenCV itself (the reference's implementation of this stage,
+    exp_mgr.py:343-350) when cv2 is importable on the box, else the NumPy restatement."""
+    import torch
+    from eincm_b200 import img_utils, synth
+    frames = synth.make_frames(H, W, R, seed=0)
+    pinned = torch.from_numpy(frames).pin_memory()
+    for _ in range(3):
+        img_utils.edge_maps(pinned.cuda(non_blocking=True), 30, 80)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = img_utils.edge_maps(pinned.cuda(non_blocking=True), 30, 80)
+    torch.cuda.synchronize()
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    d_frames = pinned.cuda()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        img_utils.edge_maps(d_frames, 30, 80)
+    b.record()
+    torch.cuda.synchronize()
+    res = {'ms_per_window_e2e': gpu_ms, 'ms_per_window_device': a.elapsed_time(b) / reps, 'frames': f'{R} x {W}x{H} uint8',
+           'h2d_bytes': int(frames.nbytes), 'stages': 'Canny (3x3 Sobel, L2, 30/80) + Gaussian sigma 1 (9 taps) + normalise',
+           'edge_pixels': int((out > 0.5).sum().item())}
+    if cpu:
+        try:
+            import cv2 as cv
+            eps = np.finfo(np.float64).eps
+
+            def ref():
+                es = []
+                for f in frames:
+                    s_ = cv.GaussianBlur(cv.Canny(f, 30, 80, None, 3, True).astype(np.float64), None, 1, 1, 0)
+                    es.append((s_ - s_.min()) / (s_.max() - s_.min() + eps))
+                return np.stack(es)
+            kind = f'reference (OpenCV {cv.__version__}, {cv.getNumThreads()} threads)'
+        except ImportError:
+            from oracle import edge_oracle as EO
+
+            def ref():
+                return np.stack([EO.edge_map(f, 30, 80) for f in frames])
+            kind = 'port (oracle/edge_oracle.py, NumPy)'
+        ref()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 5 or (time.perf_counter() - t0 < 1.0 and n < 200):
+            e_ref = ref()
+            n += 1
+        res['cpu_ms_per_window'] = (time.perf_counter() - t0) / n * 1e3
+        res['cpu_kind'] = kind
+        res['max_abs_diff_vs_cpu'] = float(np.abs(out.cpu().numpy() - e_ref).max())
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -468,6 +524,11 @@ def run_own(args):
         r = time_cpu(wins[0], thetas_h[0], steps=2, warmup=1, budget_s=args.cpu_budget)
         cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
 
+    # ---- edge images of a window: uint8 frames in host memory -> float64 edge images on the device ----
+    edge = None
+    if world == 1:
+        edge = time_edge_maps(H, W, R, cpu=not args.no_cpu_baseline)
+
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -494,6 +555,7 @@ def run_own(args):
                           'd2h_bytes_per_step': theta_bytes + 8, 'steps': n_sl, 'ms_per_step': sl_s / n_sl * 1e3,
                           'call': 'set_window from pinned host memory + value_and_grad_host every step'},
         'windows_per_s': solve,
+        'edge_maps': edge,
         'gpu_launches': int(launches),
         'roofline': roofline,
         'roofline_eval': {'bound': 'hbm', 'achieved': eval_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': eval_achieved / peak,

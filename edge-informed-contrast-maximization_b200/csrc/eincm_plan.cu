@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "k_edges.cuh"
 #include "k_prep.cuh"
 #include "k_theta.cuh"
 #include "k_events.cuh"
@@ -1429,5 +1430,7 @@ int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int
             plan->ev_xy, plan->ev_t, plan->perm, plan->n_stream, plan->theta_full, plan->H, plan->W, plan->tref.t[ref], cols_out, rows_out));
     return EINCM_OK;
 }
+
+#include "eincm_edges.inl"
 
 }  // extern "C"

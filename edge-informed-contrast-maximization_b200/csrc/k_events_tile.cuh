@@ -166,7 +166,7 @@ __device__ __forceinline__ void set_interior(Window& w, int H, int W) {
 // the per-tap global fallback.
 constexpr int kWinMaxW = kWinCap / 3;   // a window needs at least three rows
 constexpr int kMaxSlices = 16;
-constexpr int kMissThreadsPerPass = 2;    // more threads (of 256) than this with left-over events justify one more pass over the chunk
+constexpr int kMissThreadsPerPass = 0;    // more threads (of 256) than this with left-over events justify one more pass over the chunk
 
 __device__ __forceinline__ int slice_rows(int pw) { return kWinCap / pw - 2; }       // centre rows per slice of a pw-wide rectangle
 
@@ -574,10 +574,10 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
             __syncthreads();
             pass(std::true_type{}, r0);
         }
-        // Further slices of sliced rectangles (large flows).  The rectangles are conservative bounds: when (almost) no event is
-        // left over after the first slices, the out-of-line fallback is cheaper than more passes over the whole chunk.  The
-        // threshold is low because the fallback of a thread is serial while the rest of the CTA waits (measured: 16 threads per
-        // pass made 50 .. 120 px flows 15 - 50 % slower than always slicing, profiles/r1_large_flow.txt).
+        // Further slices of sliced rectangles (large flows).  The rectangles are conservative bounds: when no event is left over
+        // after the first slices, the further passes are skipped.  Any left-over event justifies them: the out-of-line fallback
+        // of a thread is serial while the rest of the CTA waits (measured: tolerating 16 / 2 threads with left-over events per
+        // pass made 50 .. 120 px flows 15 - 50 % / 10 - 20 % slower than always slicing, profiles/r1_large_flow.txt).
         int slices_done = kMaxSlices;
         if (s_sliced != 0) {
             const int n_thr = __syncthreads_count(n_hit != count_valid());      // also: flush done

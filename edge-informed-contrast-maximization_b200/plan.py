@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
     'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host', 'eincm_sparse_flow_error',
     'eincm_evaluate_theta', 'eincm_group_create', 'eincm_group_destroy', 'eincm_plan_set_group', 'eincm_group_set_burst_percent', 'eincm_plan_host_times',
+    'eincm_edge_workspace_bytes', 'eincm_edge_maps', 'eincm_edge_maps_host',
 )
 
 
@@ -92,6 +93,16 @@ def make_hparams(alpha, beta, gamma, delta, cur_pyr_lvl, n_pyr_lvls=5, scale_to_
 _lib = None
 
 
+class EdgeParams(C.Structure):
+    """``eincm_edge_params`` of include/eincm.h."""
+    _fields_ = [('canny_th1', C.c_double), ('canny_th2', C.c_double), ('smoothen', C.c_int32), ('stages', C.c_int32),
+                ('gauss_sigma', C.c_double), ('iedt_alpha', C.c_double)]
+
+
+EINCM_SMOOTHEN_GAUSSIAN, EINCM_SMOOTHEN_IEDT = 0, 1
+EINCM_EDGE_STAGE_CANNY, EINCM_EDGE_STAGE_SMOOTHEN, EINCM_EDGE_STAGE_NORMALIZE = 1, 2, 4
+
+
 def load_library(path: Optional[str] = None) -> C.CDLL:
     """Loads the CUDA library.  Fails loudly when it has not been built (``python -c 'import __graft_entry__ as g;
     g.build()'``): the product has no other code path."""
@@ -146,6 +157,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_plan_set_timing': (i32, [vp, i32]),
         'eincm_plan_get_timing': (i32, [vp, C.c_char_p, i32, C.POINTER(dbl), C.POINTER(i64), i32, C.POINTER(i32)]),
         'eincm_plan_info': (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+        'eincm_edge_workspace_bytes': (C.c_size_t, [i32, i32, i32]),
+        'eincm_edge_maps': (i32, [i32, vp, i32, i32, i32, C.POINTER(EdgeParams), vp, vp, vp, C.c_size_t, vp]),
+        'eincm_edge_maps_host': (i32, [i32, vp, i32, i32, i32, C.POINTER(EdgeParams), vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -147,3 +147,36 @@ def theta_test_points(win: Window, shape: Tuple[int, int], seed: int = 0) -> Dic
         'truth': truth,
         'perturbed': truth + rng.normal(0.0, 2.0, size=truth.shape),
     }
+
+
+def make_frames(H: int, W: int, R: int = 3, seed: int = 0, n_shapes: int = 40, noise_sigma: float = 3.0) -> np.ndarray:
+    """Synthetic grayscale frames ``uint8 (R, H, W)`` for the edge-image stage (what ``cv.Canny`` receives in
+    exp_mgr.py:345-347): random bars, discs and half-planes of different brightness, shifted a little from frame to frame,
+    3x3-blurred, with Gaussian sensor noise."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    kind = rng.integers(0, 3, size=n_shapes)
+    cx, cy = rng.uniform(0, W, n_shapes), rng.uniform(0, H, n_shapes)
+    ang = rng.uniform(0, np.pi, n_shapes)
+    size = rng.uniform(0.03, 0.25, n_shapes) * min(H, W)
+    level = rng.uniform(20, 235, n_shapes)
+    vel = rng.uniform(-6, 6, size=(n_shapes, 2))
+    frames = np.empty((R, H, W), np.uint8)
+    for r in range(R):
+        t = r / max(R - 1, 1)
+        img = np.full((H, W), 90.0)
+        for k in range(n_shapes):
+            x0, y0 = cx[k] + vel[k, 0] * t, cy[k] + vel[k, 1] * t
+            u = (xx - x0) * np.cos(ang[k]) + (yy - y0) * np.sin(ang[k])
+            v = -(xx - x0) * np.sin(ang[k]) + (yy - y0) * np.cos(ang[k])
+            if kind[k] == 0:
+                m = (np.abs(u) < size[k] * 2.5) & (np.abs(v) < size[k] * 0.25)      # bar
+            elif kind[k] == 1:
+                m = u * u + v * v < size[k] * size[k]                              # disc
+            else:
+                m = (u > 0) & (np.abs(v) < size[k]) & (u < size[k] * 1.5)          # box
+            img[m] = level[k]
+        img = _box_blur3(np.pad(img, 1, mode='edge'))[1:-1, 1:-1]
+        img = img + rng.normal(0.0, noise_sigma, size=img.shape)
+        frames[r] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return frames

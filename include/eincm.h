@@ -25,6 +25,7 @@
 #ifndef EINCM_H_
 #define EINCM_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -249,6 +250,41 @@ int eincm_sparse_flow_error(int device, int H, int W, const double* pred_flow, c
  * cur_pyr_lvl, gamma or delta); hp supplies alpha, beta, gamma, delta.  Synchronous.  Not for event-split plans. */
 int eincm_evaluate_theta(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, const double* gt_flow,
                          const uint8_t* err_eval_event_mask, eincm_eval_metrics* out_host, void* cuda_stream);
+
+/* ---- edge images of a window from its grayscale frames (the step before set_window) --------
+ * Replaces, per reference time, `normalize_to_unit_range(smoothen_edges(image_to_edge(jnp_to_ocv_n255(image))))` of
+ * src/experiments/e00/exp_mgr.py:343-350:
+ *   image_to_edge                = cv.Canny(img, th1, th2, None, 3, L2gradient=True)            src/utils/img_utils.py:194-211
+ *   smoothen_edges               = cv.GaussianBlur(float64 edge image, None, k_size, sigma, 0)  src/utils/img_utils.py:213-222
+ *                                  (OpenCV reads k_size as sigmaX and derives the kernel size from it; `sigma` is ignored)
+ *   eincm_inv_exp_dist_transform = 1 - normalize(1 - exp(-EDT(~edge) / alpha))                  src/utils/img_utils.py:231-235
+ * The Canny stage is bit-exact with OpenCV (integer arithmetic); the smoothing stages are float64 (1e-12).  The image
+ * pre-processing before Canny (non-local-means denoise, CLAHE, sharpen, bilateral filter: preprocess_image, img_utils.py:131-191)
+ * stays with OpenCV: `images` are the uint8 frames that cv.Canny receives. */
+#define EINCM_SMOOTHEN_GAUSSIAN 0      /* configs/edge_extraction/smoothen/gaussian.yaml */
+#define EINCM_SMOOTHEN_IEDT     1      /* configs/edge_extraction/smoothen/iedt.yaml */
+#define EINCM_EDGE_STAGE_CANNY      1
+#define EINCM_EDGE_STAGE_SMOOTHEN   2  /* always performed */
+#define EINCM_EDGE_STAGE_NORMALIZE  4
+typedef struct eincm_edge_params {
+    double canny_th1, canny_th2;       /* edge_extraction.canny.threshold_1 / threshold_2 (run.sh: 30 / 80 DSEC, 100 / 200 MVSEC) */
+    int32_t smoothen;                  /* EINCM_SMOOTHEN_* */
+    int32_t stages;                    /* 0 = all; else a mask of EINCM_EDGE_STAGE_*: without CANNY `images` are taken as edge images
+                                          (the stand-alone smoothen_edges / eincm_inv_exp_dist_transform), without NORMALIZE the
+                                          smoothing function's own result is returned */
+    double gauss_sigma;                /* smoothen_edges' k_size (= sigmaX as OpenCV reads the call); gaussian.yaml: 1 */
+    double iedt_alpha;                 /* eincm_inv_exp_dist_transform's alpha; iedt.yaml: 6 / 5.541 */
+} eincm_edge_params;
+/* bytes of device scratch eincm_edge_maps needs for n_images frames of H x W (0 for invalid sizes) */
+size_t eincm_edge_workspace_bytes(int H, int W, int n_images);
+/* images: DEVICE [n_images][H][W] uint8; edges_out: DEVICE [n_images][H][W] float64 (the `edges` operand of
+ * eincm_plan_set_window); canny_out: DEVICE [n_images][H][W] uint8 or NULL (cv.Canny's 0 / 255 image, debug tap);
+ * workspace: DEVICE, eincm_edge_workspace_bytes.  Asynchronous on cuda_stream. */
+int eincm_edge_maps(int device, const uint8_t* images, int n_images, int H, int W, const eincm_edge_params* p, double* edges_out,
+                    uint8_t* canny_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+/* the same with HOST buffers (allocates, copies, synchronises): what a loader thread calls once per window */
+int eincm_edge_maps_host(int device, const uint8_t* images_host, int n_images, int H, int W, const eincm_edge_params* p,
+                         double* edges_out_host, uint8_t* canny_out_host);
 
 /* ---- measurement hooks (bench.py): launch accounting and optional per-kernel CUDA-event timing -------- */
 /* wall time the synchronous host entry points of this plan spent launching (enqueue_s) and waiting for results (wait_s) over

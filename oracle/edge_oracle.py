@@ -1,0 +1,156 @@
+"""CPU restatement of the reference's edge-map production - TEST INFRASTRUCTURE, not product.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this module.
+
+The reference builds the edge images of a window with OpenCV and SciPy (reference src/experiments/e00/exp_mgr.py:343-350):
+
+    edges_r = normalize_to_unit_range(smoothen_edges(image_to_edge(u8 image)))
+
+* ``image_to_edge``  = ``cv.Canny(img, th1, th2, None, 3, L2gradient=True)``            (src/utils/img_utils.py:194-211)
+* ``smoothen_edges`` = ``cv.GaussianBlur(edge.astype(f64), None, k_size, sigma, 0)``      (src/utils/img_utils.py:213-222);
+  the positional arguments land on (src, ksize=None, sigmaX=k_size, dst=sigma, sigmaY=0): the kernel size is derived from
+  sigmaX = k_size (9 taps for k_size = 1 at float64 depth), ``sigma`` is ignored.  Restated as OpenCV behaves, not as named.
+* alternative smoothing ``eincm_inv_exp_dist_transform`` (src/utils/img_utils.py:231-235):
+  ``1 - normalize(1 - exp(-EDT(~edge) / alpha))`` with ``scipy.ndimage.distance_transform_edt``
+* ``normalize_to_unit_range`` (src/utils/img_utils.py:24-25)
+
+The arithmetic lives in third-party libraries that are not under /root/reference: OpenCV (unpinned, ``pip install
+opencv-python``; 4.13.0 is importable in this image) and SciPy.  OpenCV's published Canny algorithm (modules/imgproc/src/canny.cpp)
+is restated here in NumPy; the restatement is PINNED against ``cv2`` itself in tests/test_edge_oracle.py (run wherever cv2 is
+importable) and against golden fixtures generated with cv2 4.13.0 (tests/golden/edges_*.npz, tests/golden/make_golden_edges.py).
+"""
+import numpy as np
+
+EPS = np.finfo(np.float64).eps          # jnp.finfo(jnp.float64).eps, img_utils.py:25
+CANNY_SHIFT = 15
+TG22 = int(0.4142135623730950488016887242097 * (1 << CANNY_SHIFT) + 0.5)     # 13573
+
+
+def normalize_to_unit_range(a):
+    """src/utils/img_utils.py:24-25"""
+    a = np.asarray(a, dtype=np.float64)
+    return (a - a.min()) / (a.max() - a.min() + EPS)
+
+
+def sobel3_replicate(img_u8):
+    """cv.Sobel(src, CV_16S, 1|0, 0|1, ksize=3, borderType=BORDER_REPLICATE) as cv.Canny calls it: (dx, dy) int16."""
+    p = np.pad(np.asarray(img_u8).astype(np.int32), 1, mode='edge')
+    dx = (p[:-2, 2:] - p[:-2, :-2]) + 2 * (p[1:-1, 2:] - p[1:-1, :-2]) + (p[2:, 2:] - p[2:, :-2])
+    dy = (p[2:, :-2] - p[:-2, :-2]) + 2 * (p[2:, 1:-1] - p[:-2, 1:-1]) + (p[2:, 2:] - p[:-2, 2:])
+    return dx.astype(np.int16), dy.astype(np.int16)
+
+
+def canny_thresholds(th1, th2):
+    """cv.Canny with L2gradient: thresholds are clamped to 32767, squared and floored; th1 > th2 are swapped."""
+    lo, hi = (th2, th1) if th1 > th2 else (th1, th2)
+    lo, hi = min(32767.0, float(lo)), min(32767.0, float(hi))
+    if lo > 0:
+        lo *= lo
+    if hi > 0:
+        hi *= hi
+    return int(np.floor(lo)), int(np.floor(hi))
+
+
+def canny_candidates(img_u8, th1, th2):
+    """Non-maximum suppression of cv.Canny (L2 gradient, aperture 3).  Returns the map of OpenCV's first stage without its push
+    shortcuts: 0 = local maximum above the low threshold (edge if connected to a strong one), 1 = not an edge, 2 = local maximum
+    above the high threshold."""
+    dx, dy = sobel3_replicate(img_u8)
+    H, W = dx.shape
+    xs, ys = dx.astype(np.int64), dy.astype(np.int64)
+    mag = xs * xs + ys * ys
+    lo, hi = canny_thresholds(th1, th2)
+    mp = np.pad(mag, 1)                                        # zero border of the magnitude buffer
+    c = mp[1:-1, 1:-1]
+    left, right = mp[1:-1, :-2], mp[1:-1, 2:]
+    up, down = mp[:-2, 1:-1], mp[2:, 1:-1]
+    x, y = np.abs(xs), np.abs(ys) << CANNY_SHIFT
+    tg22x = x * TG22
+    tg67x = tg22x + (x << (CANNY_SHIFT + 1))
+    horiz = y < tg22x
+    vert = (~horiz) & (y > tg67x)
+    diag = ~(horiz | vert)
+    s_neg = (xs ^ ys) < 0                                       # s = -1: compare (row-1, col+1) and (row+1, col-1)
+    up_l, up_r = mp[:-2, :-2], mp[:-2, 2:]
+    dn_l, dn_r = mp[2:, :-2], mp[2:, 2:]
+    d_prev = np.where(s_neg, up_r, up_l)                        # _mag_p[j - s]
+    d_next = np.where(s_neg, dn_l, dn_r)                        # _mag_n[j + s]
+    is_max = (horiz & (c > left) & (c >= right)) | (vert & (c > up) & (c >= down)) | (diag & (c > d_prev) & (c > d_next))
+    cand = (c > lo) & is_max
+    out = np.ones((H, W), np.uint8)
+    out[cand] = 0
+    out[cand & (c > hi)] = 2
+    return out
+
+
+def canny(img_u8, th1, th2):
+    """cv.Canny(img, th1, th2, None, 3, True): 255 on candidates 8-connected to a strong candidate (src/utils/img_utils.py:194-211)."""
+    m = canny_candidates(img_u8, th1, th2)
+    H, W = m.shape
+    edge = (m == 2)
+    stack = list(zip(*np.nonzero(edge)))
+    while stack:                                                # hysteresis: flood fill from the strong pixels
+        r, c = stack.pop()
+        for rr in range(max(r - 1, 0), min(r + 2, H)):
+            for cc in range(max(c - 1, 0), min(c + 2, W)):
+                if m[rr, cc] == 0 and not edge[rr, cc]:
+                    edge[rr, cc] = True
+                    stack.append((rr, cc))
+    return np.where(edge, 255, 0).astype(np.uint8)
+
+
+def gaussian_kernel_f64(sigma):
+    """cv.getGaussianKernel(ksize, sigma, CV_64F) with ksize derived from sigma for a float64 image: round(sigma * 8 + 1) | 1."""
+    k = int(round(sigma * 8 + 1)) | 1
+    x = np.arange(k, dtype=np.float64) - (k - 1) * 0.5
+    w = np.exp(-0.5 / (sigma * sigma) * x * x)
+    return w / w.sum()
+
+
+def smoothen_edges(edge_img, k_size=1, sigma=1):
+    """src/utils/img_utils.py:213-222 as OpenCV executes it: separable Gaussian with sigmaX = sigmaY = k_size, BORDER_REFLECT_101."""
+    del sigma                                                   # lands on the dst parameter of cv.GaussianBlur
+    a = np.asarray(edge_img, dtype=np.float64)
+    w = gaussian_kernel_f64(float(k_size))
+    h = len(w) // 2
+    p = np.pad(a, ((0, 0), (h, h)), mode='reflect')
+    rowf = sum(w[i] * p[:, i:i + a.shape[1]] for i in range(len(w)))
+    p = np.pad(rowf, ((h, h), (0, 0)), mode='reflect')
+    return sum(w[i] * p[i:i + a.shape[0], :] for i in range(len(w)))
+
+
+def distance_transform_edt(mask):
+    """scipy.ndimage.distance_transform_edt(mask): exact Euclidean distance of every non-zero pixel to the nearest zero pixel."""
+    mask = np.asarray(mask, dtype=bool)
+    H, W = mask.shape
+    INF = np.int64(1) << 40
+    g = np.full((H, W), INF, np.int64)                          # vertical distance to the nearest zero pixel of the column
+    run = np.full(W, INF, np.int64)
+    for r in range(H):
+        run = np.where(mask[r], np.minimum(run + 1, INF), 0)
+        g[r] = run
+    run = np.full(W, INF, np.int64)
+    for r in range(H - 1, -1, -1):
+        run = np.where(mask[r], np.minimum(run + 1, INF), 0)
+        g[r] = np.minimum(g[r], run)
+    g2 = np.where(g >= INF, INF, g * g)
+    cols = np.arange(W, dtype=np.int64)
+    dx2 = (cols[:, None] - cols[None, :]) ** 2                   # [x, x']
+    d2 = np.empty((H, W), np.int64)
+    for r in range(H):
+        d2[r] = np.min(dx2 + g2[r][None, :], axis=1)
+    return np.sqrt(d2.astype(np.float64))
+
+
+def eincm_inv_exp_dist_transform(edge_img, alpha=6):
+    """src/utils/img_utils.py:231-235"""
+    d = distance_transform_edt(~(np.asarray(edge_img).astype(bool)))
+    e = 1.0 - np.exp(-d / alpha)
+    return 1.0 - normalize_to_unit_range(e)
+
+
+def edge_map(img_u8, th1=30, th2=80, smoothen='gaussian', k_size=1, alpha=6 / 5.541):
+    """One edge image of a window as exp_mgr.py:343-350 stages it (the u8 image is the pre-processed grayscale frame)."""
+    e = canny(img_u8, th1, th2)
+    s = smoothen_edges(e, k_size) if smoothen == 'gaussian' else eincm_inv_exp_dist_transform(e, alpha)
+    return normalize_to_unit_range(s)
