@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "k_edges.cuh"
+#include "k_ingest.cuh"
 #include "k_prep.cuh"
 #include "k_theta.cuh"
 #include "k_events.cuh"
@@ -1432,5 +1433,6 @@ int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int
 }
 
 #include "eincm_edges.inl"
+#include "eincm_ingest.inl"
 
 }  // extern "C"

@@ -286,6 +286,27 @@ int eincm_edge_maps(int device, const uint8_t* images, int n_images, int H, int 
 int eincm_edge_maps_host(int device, const uint8_t* images_host, int n_images, int H, int W, const eincm_edge_params* p,
                          double* edges_out_host, uint8_t* canny_out_host);
 
+/* ---- event ingest before staging --------
+ * What the reference's DSEC loader / experiment manager do in NumPy between the h5 event stream and loss_func's operands.
+ * All pointers DEVICE unless suffixed _host. */
+/* rectify_events, src/dataloaders/dsec_loader.py:145-170: (x, y) <- round-half-even(rectify_map[y, x]) as int16; events whose
+ * rectified pixel leaves the H x W sensor are dropped, the order of the others is kept.  rectify_map: float32 [H][W][2] (x, y).
+ * t / t_out (int64 microseconds) and p / p_out (uint8 polarity) may be NULL together.  Outputs hold up to n_events entries.
+ * Synchronous (the surviving count is returned in host memory). */
+size_t eincm_rectify_workspace_bytes(int64_t n_events);
+int eincm_rectify_events(int device, const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p, int64_t n_events,
+                         const float* rectify_map, int H, int W, int16_t* x_out, int16_t* y_out, int64_t* t_out, uint8_t* p_out,
+                         int64_t* n_out_host, void* workspace, size_t workspace_bytes, void* cuda_stream);
+/* stage_datasample, src/experiments/e00/exp_mgr.py:313-321: ts = (t - start) / (end - start + eps) in float64 (the `ts` operand
+ * of loss_func / eincm_plan_set_window).  Asynchronous. */
+int eincm_normalize_times(int device, const int64_t* t_us, int64_t n_events, int64_t start_us, int64_t end_us, double* ts_out,
+                          void* cuda_stream);
+/* fixed-N window rule of DSECDataLoader.get_sample, dsec_loader.py:293-311 (host arithmetic): the event index range
+ * [idx_start, idx_end) of a window is widened symmetrically (ceil / floor of half the deficiency, clamped to the stream) or cut to
+ * des_n_events (keeping the latest or the earliest events).  des_n_events <= 0: unchanged. */
+int eincm_window_event_range(int64_t idx_start, int64_t idx_end, int64_t n_total, int64_t des_n_events, int prefer_latest_events,
+                             int64_t* start_out, int64_t* end_out, int64_t* deficiency_out);
+
 /* ---- measurement hooks (bench.py): launch accounting and optional per-kernel CUDA-event timing -------- */
 /* wall time the synchronous host entry points of this plan spent launching (enqueue_s) and waiting for results (wait_s) over
  * n_evals evaluations since the last reset: shows whether a solve loop is bound by the host or by the GPU */
