@@ -313,6 +313,21 @@ def test_large_flow_takes_the_window_fallback(L, flow):
     assert _rel_inf(grad, g_ref) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize('name,flow,shape', [('mvsec_dt4', (70.0, -90.0), (2, 2)), ('mvsec_dt1', (-120.0, 60.0), (1, 1)),
+                                             ('mvsec_raw_dt4', (55.0, 140.0), (4, 4)), ('e00_single', (80.0, 80.0), (2, 2))])
+def test_sliced_windows_with_other_reference_counts(L, name, flow, shape):
+    """Sliced rectangles when the reference times do not fill whole passes: R = 5 (two passes of first slices, RB = 4), R = 2, R = 1,
+    with different numbers of slices per reference time (the rectangle grows with |t - t_ref|)."""
+    w = S.make_workload(name, seed=21, n_events=20_000)
+    kw = dict(w.hparams, cur_pyr_lvl=1, n_pyr_lvls=5, sensor_size=w.sensor_size, scale_to_sensor_size_method='bilinear')
+    th = np.zeros(shape + (2,)); th[..., 0] = flow[0]; th[..., 1] = flow[1]
+    th += np.random.default_rng(22).normal(0.0, 2.0, size=th.shape)
+    loss, grad = L.value_and_grad(L.loss_func)(th, *w.args(), **kw)
+    l_ref, g_ref = O.value_and_grad(th, *w.args(), **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+
+
 @pytest.mark.parametrize('c', [64.0, 96.0])
 def test_sliced_windows_with_coordinates_on_rounding_boundaries(L, c):
     """Dyadic timestamps and a dyadic constant flow put thousands of warped coordinates exactly on k + 0.5 (round half to even,
