@@ -94,6 +94,7 @@ struct eincm_plan {
     uint32_t* perm2 = nullptr;
     unsigned int *counts = nullptr, *cursor = nullptr, *tile_cnt = nullptr, *tile_start = nullptr, *chunk_first = nullptr, *totals = nullptr;
     Chunk* chunks = nullptr;
+    Chunk* chunks2 = nullptr;                          // second table: k_chunk_order writes the size-ordered table here, then the two swap
     int4* chunk_win = nullptr;                         // [chunk_cap][max_refs] windows of the last forward pass
     float* adj32 = nullptr;                            // [max_refs][H*W] adjoint of the Scharr pair applied to (Gx, Gy) (k_image_stats -> k_image_grad)
     float2* chunk_tr = nullptr;                        // [chunk_cap] t range of the events of every chunk (per window)
@@ -613,6 +614,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->chunk_first, (size_t)plan->n_tiles + 1)); CU(dmalloc(&plan->totals, 4));
         CU(cudaMemset(plan->totals, 0, 4 * sizeof(unsigned int)));
         CU(dmalloc(&plan->chunks, (size_t)plan->chunk_cap));
+        CU(dmalloc(&plan->chunks2, (size_t)plan->chunk_cap));
         CU(dmalloc(&plan->chunk_tr, (size_t)plan->chunk_cap));
         CU(dmalloc(&plan->mask, HW));
         CU(dmalloc(&plan->theta_full, HW)); CU(dmalloc(&plan->Gtv, HW));
@@ -652,7 +654,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
     void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
-                    plan->chunk_first, plan->totals, plan->adj32, plan->chunks, plan->chunk_tr, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
+                    plan->chunk_first, plan->totals, plan->adj32, plan->chunks, plan->chunks2, plan->chunk_tr, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
                     plan->xs_stage, plan->ys_stage, plan->ts_stage, plan->edges_stage};
@@ -719,6 +721,10 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     // until the totals are read back (end of this call) the host uses upper bounds; kernels skip sentinels / read the chunk count on device
     plan->n_stream = std::min<int64_t>(plan->stream_cap, (n + kStreamAlign - 1) / kStreamAlign * kStreamAlign + (int64_t)kStreamAlign * plan->n_tiles);
     plan->n_chunks = (int)std::min<int64_t>(plan->chunk_cap, n / kChunkEvents + plan->n_tiles + 1);
+    if (n > 0 && plan->n_chunks <= kMaxOrderedChunks) {          // largest chunks first (see k_chunk_order)
+        LAUNCH("k_chunk_order", k_chunk_order<<<(plan->n_chunks + 255) / 256, 256, 0, st>>>(plan->chunks, plan->totals + 1, plan->chunks2));
+        std::swap(plan->chunks, plan->chunks2);
+    }
     CU(cudaMemsetAsync(plan->ev_xy, 0xff, (size_t)plan->n_stream * sizeof(uint32_t), st));
     LAUNCH("k_event_mask", k_event_mask<<<(int)((plan->HW + 255) / 256), 256, 0, st>>>(plan->counts, plan->H, plan->W, plan->tiles_x, plan->mask));
     if (n > 0) {

@@ -122,6 +122,26 @@ k_tile_finish(const unsigned int* __restrict__ counts, const unsigned int* __res
     }
 }
 
+// Chunk table in descending order of event count (ties by table position: deterministic).  The event kernels run one CTA per chunk and
+// the hardware hands CTAs out in index order, so this is longest-processing-time-first list scheduling: the tail of the grid is
+// filled with the small chunks instead of whatever tiles happen to be last in the image.  One thread per chunk counts the chunks
+// that precede it (n^2 / 2 comparisons on L1-resident data; once per window; the host skips tables beyond kMaxOrderedChunks).
+constexpr int kMaxOrderedChunks = 16384;
+
+__global__ void __launch_bounds__(256)
+k_chunk_order(const Chunk* __restrict__ in, const unsigned int* __restrict__ n_chunks_dev, Chunk* __restrict__ out) {
+    const int n = (int)__ldg(n_chunks_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Chunk me = in[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+        const unsigned int cj = __ldg(&in[j].count);
+        rank += (cj > me.count || (cj == me.count && j < i)) ? 1 : 0;
+    }
+    out[rank] = me;
+}
+
 // Scatter events into pixel-sorted order.  ev_xy packs (x | y << 16); perm keeps the original index
 // (needed by the debug index tap and by k_rank_sort_segments).  Order inside one pixel is arbitrary here.
 __global__ void k_scatter_events(const int16_t* __restrict__ xs, const int16_t* __restrict__ ys, const double* __restrict__ ts,
