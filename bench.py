@@ -462,7 +462,8 @@ def run_own(args):
                 torch.cuda.synchronize()
                 runs.append((max_over_ranks(time.perf_counter() - t0), sum(o.n_evals for o in objs) - n0))
             dt, n_ev = sorted(runs)[len(runs) // 2]
-            res = {'value': world * n_win / dt, 'unit': 'windows/s', 'repeats_windows_per_s': [round(world * n_win / r[0], 2) for r in runs], 'sequences_per_gpu': n_threads, 'windows_per_sequence': args.solve_windows,
+            res = {'value': world * n_win / dt, 'unit': 'windows/s', 'repeats_windows_per_s': [round(world * n_win / r[0], 2) for r in runs],
+                   'repeats_evals_per_window': [round(r[1] / n_win, 1) for r in runs], 'sequences_per_gpu': n_threads, 'windows_per_sequence': args.solve_windows,
                    'ms_per_window': dt / args.solve_windows * 1e3, 'evals_per_window': n_ev / n_win,
                    'final_loss': finals[0]['theta_opt_state_pyr']['pyr_lvl_0'].fun_val, 'host_threads': 'evaluation group (one launching thread per GPU)' if grouped else 'independent (one spinning thread per sequence)'}
             for o in objs:
