@@ -426,7 +426,9 @@ def run_own(args):
             """n_threads independent sequences per GPU, each: warm-up solve, then args.solve_windows chained windows."""
             # fewer host cores than driving threads (e.g. 8 GPUs x 4 sequences on 16 cores): the sequences of a GPU join an evaluation
             # group - one thread launches the evaluations of all of them in a burst, the others sleep (include/eincm.h)
-            grouped = backend == 'native' and n_threads > 1 and len(os.sched_getaffinity(0)) // world < n_threads + 1
+            # (with cores to spare the group does not pay inside this bench: 10.6 - 11.8 windows/s grouped against 12.9 - 18.7 independent
+            # on one B200 with 4 sequences; --group-sequences forces it)
+            grouped = backend == 'native' and n_threads > 1 and (args.group_sequences or len(os.sched_getaffinity(0)) // world < n_threads + 1)
             objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3))
                     for _ in range(n_threads)]
             group = P.Group() if grouped else None
@@ -646,6 +648,7 @@ def main():
     ap.add_argument('--windows', type=int, default=4, help='distinct windows per GPU cycled round-robin')
     ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU work for the CPU baseline / reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--group-sequences', action='store_true', help='windows/s with the sequences of a GPU in one evaluation group even when host cores are plentiful')
     ap.add_argument('--solve-windows', type=int, default=2, help='complete multi-level solves per GPU for the windows/s figure (0: skip)')
     ap.add_argument('--event-split', action='store_true', help='ONE window split over the GPUs (configs[4]) instead of windows sharded')
     args = ap.parse_args()
