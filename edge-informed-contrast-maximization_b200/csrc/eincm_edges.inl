@@ -60,6 +60,7 @@ int eincm_edge_maps(int device, const uint8_t* images, int n_images, int H, int 
     GaussTaps taps{};
     if (p->smoothen == EINCM_SMOOTHEN_GAUSSIAN && !gauss_taps(p->gauss_sigma, &taps)) return EINCM_EINVAL;
     if (p->smoothen == EINCM_SMOOTHEN_IEDT && !(p->iedt_alpha > 0.0)) return EINCM_EINVAL;
+    if (p->smoothen == EINCM_SMOOTHEN_IEDT && (size_t)W * sizeof(long long) > 48u * 1024u) return EINCM_EUNSUPPORTED;   // one image row in shared memory
     ECU(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const EdgeWorkspace ws = edge_ws_carve(workspace, H, W, n_images);
