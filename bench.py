@@ -198,6 +198,15 @@ def time_edge_maps(H, W, R, cpu=True, reps=20):
         img_utils.edge_maps(d_frames, 30, 80)
     b.record()
     torch.cuda.synchronize()
+    for _ in range(2):
+        den = img_utils.fast_nl_means_denoising(d_frames, 4, 3, 11)
+    a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a2.record()
+    for _ in range(reps):
+        den = img_utils.fast_nl_means_denoising(d_frames, 4, 3, 11)
+    b2.record()
+    torch.cuda.synchronize()
+    nlm = {'ms_per_window_device': a2.elapsed_time(b2) / reps, 'params': 'h 4, template 3, search 11 (denoise/default.yaml)'}
     res = {'ms_per_window_e2e': gpu_ms, 'ms_per_window_device': a.elapsed_time(b) / reps, 'frames': f'{R} x {W}x{H} uint8',
            'h2d_bytes': int(frames.nbytes), 'stages': 'Canny (3x3 Sobel, L2, 30/80) + Gaussian sigma 1 (9 taps) + normalise',
            'edge_pixels': int((out > 0.5).sum().item())}
@@ -228,6 +237,16 @@ def time_edge_maps(H, W, R, cpu=True, reps=20):
         res['cpu_ms_per_window'] = (time.perf_counter() - t0) / n * 1e3
         res['cpu_kind'] = kind
         res['max_abs_diff_vs_cpu'] = float(np.abs(out.cpu().numpy() - e_ref).max())
+        try:
+            import cv2 as cv
+            t0 = time.perf_counter()
+            ref_den = np.stack([cv.fastNlMeansDenoising(f, None, 4, 3, 11) for f in frames])
+            nlm['cpu_ms_per_window'] = (time.perf_counter() - t0) * 1e3
+            nlm['cpu_kind'] = f'reference (OpenCV {cv.__version__}, {cv.getNumThreads()} threads)'
+            nlm['identical_to_cpu'] = bool(np.array_equal(den.cpu().numpy(), ref_den))
+        except ImportError:
+            pass
+    res['nlm_denoise'] = nlm
     return res
 
 

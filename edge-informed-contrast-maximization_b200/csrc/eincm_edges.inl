@@ -123,5 +123,72 @@ int eincm_edge_maps_host(int device, const uint8_t* images_host, int n_images, i
     return rc;
 }
 
+// ---- non-local-means denoise (cv.fastNlMeansDenoising, uint8, one channel) ----
+namespace {
+struct NlmTable { int shift = 0; std::vector<int> w; };
+// OpenCV's FastNlMeansDenoisingInvoker constructor (fast_nlmeans_denoising_invoker.hpp) for <uchar, int, unsigned, DistSquared, int>
+NlmTable nlm_table(float h, int tw, int sw) {
+    NlmTable t;
+    const long long max_estimate_sum_value = (long long)sw * sw * 255;
+    const int fixed_point_mult = (int)std::min<long long>(2147483647LL / max_estimate_sum_value, 2147483647LL);
+    const int tsq = tw * tw;
+    while ((1 << t.shift) < tsq) ++t.shift;                       // getNearestPowerOf2
+    const double mult = (double)(1 << t.shift) / tsq;             // almost_dist2actual_dist_multiplier
+    const int max_dist = 255 * 255;                               // DistSquared::maxDist<uchar>
+    const int almost_max_dist = (int)(max_dist / mult + 1);
+    t.w.resize((size_t)almost_max_dist);
+    for (int a = 0; a < almost_max_dist; ++a) {
+        const double dist = a * mult;
+        double w = std::exp(-dist / (h * h * 1));                 // float h * h like OpenCV (h[0] * h[0] * channels)
+        if (w != w) w = 1.0;
+        int weight = (int)std::nearbyint(fixed_point_mult * w);   // cvRound
+        if (weight < 0.001 * fixed_point_mult) weight = 0;        // WEIGHT_THRESHOLD
+        t.w[(size_t)a] = weight;
+    }
+    return t;
+}
+bool nlm_sizes_ok(int tw, int sw) { return tw >= 1 && sw >= 1 && tw <= 15 && sw <= 41; }
+}  // namespace
+
+size_t eincm_nlm_workspace_bytes(int template_window_size, int search_window_size) {
+    const int tw = template_window_size / 2 * 2 + 1, sw = search_window_size / 2 * 2 + 1;
+    if (!nlm_sizes_ok(tw, sw)) return 0;
+    const int tsq = tw * tw;
+    int shift = 0;
+    while ((1 << shift) < tsq) ++shift;
+    return 256 + ((size_t)(255 * 255 / ((double)(1 << shift) / tsq) + 1) + 1) * sizeof(int);
+}
+
+int eincm_nlm_denoise(int device, const uint8_t* images, int n_images, int H, int W, float h, int template_window_size,
+                      int search_window_size, uint8_t* out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    using namespace eincm;
+    if (!images || !out || !workspace || n_images < 1 || n_images > 65535 || H < 1 || W < 1 || !(h == h)) return EINCM_EINVAL;
+    const int th = template_window_size / 2, sh = search_window_size / 2;      // OpenCV: sizes are made odd this way
+    const int tw = 2 * th + 1, sw = 2 * sh + 1;
+    if (!nlm_sizes_ok(tw, sw)) return EINCM_EUNSUPPORTED;
+    if (workspace_bytes < eincm_nlm_workspace_bytes(tw, sw)) return EINCM_EINVAL;
+    ECU(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // weight tables are cached per (h, template, search): the host copy outlives the asynchronous upload
+    static std::mutex mu;
+    static std::map<std::tuple<uint32_t, int, int>, NlmTable> cache;
+    const NlmTable* tab;
+    {
+        uint32_t hb; std::memcpy(&hb, &h, sizeof(hb));
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_tuple(hb, tw, sw);
+        auto it = cache.find(key);
+        if (it == cache.end()) it = cache.emplace(key, nlm_table(h, tw, sw)).first;
+        tab = &it->second;
+    }
+    int* d_tab = (int*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    ECU(cudaMemcpyAsync(d_tab, tab->w.data(), tab->w.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int b = th + sh;
+    const size_t smem = (size_t)(kNlmTX + 2 * b) * (kNlmTY + 2 * b);
+    const dim3 tiles((W + kNlmTX - 1) / kNlmTX, (H + kNlmTY - 1) / kNlmTY, n_images);
+    ELAUNCH(k_nlm_denoise<<<tiles, dim3(kNlmTX, kNlmTY), smem, st>>>(images, H, W, th, sh, tab->shift, d_tab, out));
+    return EINCM_OK;
+}
+
 #undef ECU
 #undef ELAUNCH

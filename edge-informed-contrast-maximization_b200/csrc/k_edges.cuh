@@ -273,4 +273,50 @@ __global__ void k_edge_normalize(double* __restrict__ img_all, int64_t HW, const
     }
 }
 
+
+// ---- non-local-means denoise of the frames before Canny (preprocess_image, src/utils/img_utils.py:147-157:
+// cv.fastNlMeansDenoising(img, None, h, template_win_size, search_win_size), uint8, one channel) -----------------------------
+// OpenCV's algorithm (modules/photo/src/fast_nlmeans_denoising_invoker.hpp) is integer and table-driven, restated bit-exactly:
+// for every pixel and every offset of the search window, dist = sum over the template window of squared differences between the
+// patch around the candidate and the patch around the pixel (BORDER_REFLECT_101); weight = table[dist >> shift] (fixed point,
+// table built on the host exactly like OpenCV builds it); output = (sum weight * candidate + sum weight / 2) / sum weight.
+// One thread per pixel, the frame tile with its halo (search / 2 + template / 2) in shared memory.
+constexpr int kNlmTX = 32, kNlmTY = 8;
+
+__global__ void __launch_bounds__(kNlmTX* kNlmTY)
+k_nlm_denoise(const uint8_t* __restrict__ img, int H, int W, int th /* template half */, int sh /* search half */, int shift,
+              const int* __restrict__ weight_table, uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = th + sh, SW = kNlmTX + 2 * b, SH = kNlmTY + 2 * b;
+    uint8_t* tile = smem_raw;                                                // [SH][SW]
+    const int64_t off = (int64_t)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * kNlmTX, y0 = blockIdx.y * kNlmTY;
+    const int tid = threadIdx.y * kNlmTX + threadIdx.x;
+    for (int i = tid; i < SW * SH; i += kNlmTX * kNlmTY) {
+        const int sy = i / SW, sx = i - sy * SW;
+        tile[i] = img[off + (int64_t)reflect101(y0 + sy - b, H) * W + reflect101(x0 + sx - b, W)];
+    }
+    __syncthreads();
+    const int gx = x0 + threadIdx.x, gy = y0 + threadIdx.y;
+    if (gx >= W || gy >= H) return;
+    const uint8_t* me = tile + (threadIdx.y + b) * SW + threadIdx.x + b;    // the pixel inside the tile
+    unsigned int est = 0u, wsum = 0u;                                        // OpenCV sizes the fixed point so that both fit 31 bits
+    for (int y = -sh; y <= sh; ++y) {
+        for (int x = -sh; x <= sh; ++x) {
+            const uint8_t* cand = me + y * SW + x;
+            int dist = 0;
+            for (int ty = -th; ty <= th; ++ty)
+                for (int tx = -th; tx <= th; ++tx) {
+                    const int d = (int)cand[ty * SW + tx] - (int)me[ty * SW + tx];
+                    dist += d * d;
+                }
+            const unsigned int wgt = (unsigned int)__ldg(weight_table + (dist >> shift));
+            est += wgt * (unsigned int)cand[0];
+            wsum += wgt;
+        }
+    }
+    const unsigned int v = (est + wsum / 2u) / wsum;                          // the pixel itself always has the full weight: wsum > 0
+    out[off + (int64_t)gy * W + gx] = (uint8_t)min(v, 255u);
+}
+
 }  // namespace eincm

@@ -286,6 +286,16 @@ int eincm_edge_maps(int device, const uint8_t* images, int n_images, int H, int 
 int eincm_edge_maps_host(int device, const uint8_t* images_host, int n_images, int H, int W, const eincm_edge_params* p,
                          double* edges_out_host, uint8_t* canny_out_host);
 
+/* Non-local-means denoise of the frames, the first and by far the slowest step of preprocess_image (src/utils/img_utils.py:147-157:
+ * cv.fastNlMeansDenoising(img, None, h, template_win_size, search_win_size); denoise/default.yaml: h 4, template 3, search 11 -
+ * ~110 ms per 640x480 frame with OpenCV on 8 host threads).  uint8, one channel, bit-exact with OpenCV (integer patch distances,
+ * OpenCV's fixed-point weight table, BORDER_REFLECT_101).  images / out: DEVICE [n_images][H][W] uint8 (must not alias);
+ * workspace: DEVICE, eincm_nlm_workspace_bytes (weight table).  Window sizes are made odd like OpenCV does (size / 2 * 2 + 1);
+ * template <= 15, search <= 41.  Asynchronous on cuda_stream. */
+size_t eincm_nlm_workspace_bytes(int template_window_size, int search_window_size);
+int eincm_nlm_denoise(int device, const uint8_t* images, int n_images, int H, int W, float h, int template_window_size,
+                      int search_window_size, uint8_t* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* ---- event ingest before staging --------
  * What the reference's DSEC loader / experiment manager do in NumPy between the h5 event stream and loss_func's operands.
  * All pointers DEVICE unless suffixed _host. */

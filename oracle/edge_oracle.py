@@ -154,3 +154,62 @@ def edge_map(img_u8, th1=30, th2=80, smoothen='gaussian', k_size=1, alpha=6 / 5.
     e = canny(img_u8, th1, th2)
     s = smoothen_edges(e, k_size) if smoothen == 'gaussian' else eincm_inv_exp_dist_transform(e, alpha)
     return normalize_to_unit_range(s)
+
+
+def fast_nl_means_denoising(src, h=4, template_win_size=3, search_win_size=11):
+    """cv.fastNlMeansDenoising(src, None, h, template_win_size, search_win_size) for a uint8 single-channel image, as
+    preprocess_image calls it (src/utils/img_utils.py:147-157).  Restates OpenCV's FastNlMeansDenoisingInvoker<uchar, int, unsigned,
+    DistSquared, int> (modules/photo/src/fast_nlmeans_denoising_invoker.hpp): reflect-101 border of search / 2 + template / 2 pixels,
+    integer patch distances, the fixed-point weight table indexed by dist >> log2ceil(template^2), rounded integer average.
+    Pinned bit-exactly against cv2 (tests/test_edge_oracle.py, tests/golden/edges)."""
+    import math
+    src = np.asarray(src, np.uint8)
+    th, sh = int(template_win_size) // 2, int(search_win_size) // 2
+    tw, sw = 2 * th + 1, 2 * sh + 1
+    b = th + sh
+    H, W = src.shape
+    idx_r = np.arange(-b, H + b); idx_c = np.arange(-b, W + b)
+
+    def refl(i, n):                                             # cv::borderInterpolate, BORDER_REFLECT_101
+        if n == 1:
+            return np.zeros_like(i)
+        i = i.copy()
+        while True:
+            bad = (i < 0) | (i >= n)
+            if not bad.any():
+                return i
+            i = np.where(i < 0, -i, i)
+            i = np.where(i >= n, 2 * (n - 1) - i, i)
+
+    ext = src.astype(np.int64)[refl(idx_r, H)][:, refl(idx_c, W)]
+    fixed_point_mult = min((2 ** 31 - 1) // (sw * sw * 255), 2 ** 31 - 1)
+    tsq = tw * tw
+    shift = 0
+    while (1 << shift) < tsq:
+        shift += 1
+    mult = float(1 << shift) / tsq
+    almost_max = int(255 * 255 / mult + 1)
+    hh = float(np.float32(h) * np.float32(h))
+    wt = np.empty(almost_max, np.int64)
+    for a in range(almost_max):
+        w = math.exp(-(a * mult) / hh)
+        v = int(round(fixed_point_mult * w))                    # cvRound: half to even, like Python's round
+        wt[a] = 0 if v < 0.001 * fixed_point_mult else v
+    est = np.zeros((H, W), np.int64)
+    wsum = np.zeros((H, W), np.int64)
+
+    def at(dy, dx):
+        return ext[b + dy: b + dy + H, b + dx: b + dx + W]
+
+    own = [[at(ty, tx) for tx in range(-th, th + 1)] for ty in range(-th, th + 1)]
+    for y in range(-sh, sh + 1):
+        for x in range(-sh, sh + 1):
+            d = np.zeros((H, W), np.int64)
+            for ty in range(-th, th + 1):
+                for tx in range(-th, th + 1):
+                    diff = at(y + ty, x + tx) - own[ty + th][tx + th]
+                    d += diff * diff
+            wgt = wt[d >> shift]
+            est += wgt * at(y, x)
+            wsum += wgt
+    return np.clip((est + wsum // 2) // wsum, 0, 255).astype(np.uint8)

@@ -9,6 +9,7 @@ src/experiments/e00/exp_mgr.py:343-350):
     canny  = cv.Canny(img, th1, th2, None, 3, True)
     gauss  = normalize_to_unit_range(cv.GaussianBlur(canny.astype(float64), None, 1, 1, 0))
     iedt   = normalize_to_unit_range(eincm_inv_exp_dist_transform(canny, alpha))
+    nlm    = cv.fastNlMeansDenoising(img, None, 4, 3, 11)              (first step of preprocess_image, img_utils.py:147-157)
 
 They pin the NumPy restatement (oracle/edge_oracle.py, tests/test_edge_oracle.py) and the CUDA path (tests/test_gpu_edges.py).
 """
@@ -56,7 +57,8 @@ def main():
         canny = np.stack([cv.Canny(f, th1, th2, None, 3, True) for f in frames])
         gauss = np.stack([normalize_to_unit_range(cv.GaussianBlur(c.astype(np.float64), None, 1, 1, 0)) for c in canny])
         iedt = np.stack([normalize_to_unit_range(ref_iedt(c, ALPHA)) for c in canny])
-        np.savez_compressed(os.path.join(out_dir, name + '.npz'), frames=frames, canny=canny, gauss=gauss, iedt=iedt,
+        nlm = np.stack([cv.fastNlMeansDenoising(f, None, 4, 3, 11) for f in frames])     # denoise/default.yaml: h 4, template 3, search 11
+        np.savez_compressed(os.path.join(out_dir, name + '.npz'), frames=frames, canny=canny, gauss=gauss, iedt=iedt, nlm=nlm,
                             th=np.array([th1, th2], np.float64), alpha=np.float64(ALPHA), cv_version=np.array(cv.__version__))
         print(name, frames.shape, 'edge pixels', int((canny > 0).sum()))
 

@@ -29,6 +29,13 @@ def test_oracle_matches_opencv_fixtures(path):
         np.testing.assert_allclose(E.edge_map(f, th1, th2, 'iedt', alpha=float(z['alpha'])), iedt, rtol=0, atol=FTOL)
 
 
+@pytest.mark.parametrize('path', GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_nlm_oracle_matches_opencv_fixtures(path):
+    z = np.load(path)
+    for f, ref in zip(z['frames'], z['nlm']):
+        assert np.array_equal(E.fast_nl_means_denoising(f, 4, 3, 11), ref)    # bit-exact
+
+
 def test_threshold_rule():
     assert E.canny_thresholds(30, 80) == (900, 6400)
     assert E.canny_thresholds(200, 100) == (10000, 40000)                     # swapped like cv.Canny does
@@ -71,3 +78,12 @@ def test_oracle_matches_live_opencv(seed, H, W, th):
     rng = np.random.default_rng(seed)
     f = (rng.integers(0, 5, size=(H, W)) * 60).astype(np.uint8)                # many exact ties in the magnitudes
     assert np.array_equal(E.canny(f, *th), cv.Canny(f, th[0], th[1], None, 3, True))
+
+
+@pytest.mark.parametrize('shape,h,t,sw', [((40, 56), 4, 3, 11), ((5, 7), 4, 3, 11), ((3, 40), 4, 3, 11), ((30, 31), 7.5, 5, 9),
+                                          ((30, 31), 4, 4, 10), ((24, 24), 10, 7, 21)])
+def test_nlm_oracle_matches_live_opencv(shape, h, t, sw):
+    f = np.random.default_rng(shape[0] * 7 + shape[1]).integers(0, 256, size=shape).astype(np.uint8)
+    assert np.array_equal(E.fast_nl_means_denoising(f, h, t, sw), cv.fastNlMeansDenoising(f, None, h, t, sw))
+    g = S.make_frames(max(shape[0], 8), max(shape[1], 8), 1, seed=3, noise_sigma=5.0)[0]
+    assert np.array_equal(E.fast_nl_means_denoising(g, h, t, sw), cv.fastNlMeansDenoising(g, None, h, t, sw))

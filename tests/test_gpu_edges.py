@@ -118,3 +118,29 @@ def test_error_behaviour(I):
     assert lib.eincm_edge_workspace_bytes(0, 4, 1) == 0
     p = plan.EdgeParams(30.0, 80.0, 0, 0, 1.0, 1.0)
     assert lib.eincm_edge_maps(0, None, 1, 4, 4, C.byref(p), None, None, None, 0, None) == plan.EINCM_EINVAL
+
+
+@pytest.mark.parametrize('path', GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_nlm_denoise_matches_opencv_fixtures(I, path):
+    z = np.load(path)
+    got = I.fast_nl_means_denoising(z['frames'], 4, 3, 11)
+    assert np.array_equal(got.cpu().numpy(), z['nlm'])                        # bit-exact with cv.fastNlMeansDenoising
+
+
+@pytest.mark.parametrize('shape,h,t,sw', [((480, 640), 4, 3, 11), ((5, 7), 4, 3, 11), ((3, 40), 4, 3, 11), ((61, 83), 7.5, 5, 9),
+                                          ((33, 65), 4, 4, 10), ((40, 40), 10, 7, 21), ((1, 1), 4, 3, 11)])
+def test_nlm_denoise_matches_oracle(I, shape, h, t, sw):
+    if shape == (480, 640):
+        f = S.make_frames(480, 640, 1, seed=12, noise_sigma=4.0)[0]
+    else:
+        f = np.random.default_rng(shape[0] * 7 + shape[1]).integers(0, 256, size=shape).astype(np.uint8)
+    got = I.fast_nl_means_denoising(f, h, t, sw).cpu().numpy()
+    assert np.array_equal(got, E.fast_nl_means_denoising(f, h, t, sw))
+
+
+def test_nlm_error_behaviour(I):
+    from eincm_b200 import plan
+    with pytest.raises(plan.EincmError):
+        I.fast_nl_means_denoising(np.zeros((4, 4), np.float32))
+    with pytest.raises(plan.EincmError):
+        I.fast_nl_means_denoising(np.zeros((4, 4), np.uint8), 4, 3, 99)        # search window beyond the supported size
