@@ -11,7 +11,7 @@ import numpy as np
 
 from . import plan as _plan
 
-__all__ = ['rectify_events', 'window_event_range', 'normalize_times', 'stage_window_events']
+__all__ = ['rectify_events', 'crop_events', 'window_event_range', 'normalize_times', 'stage_window_events']
 
 
 def _dev(a, dtype, device=None):
@@ -50,6 +50,24 @@ def rectify_events(x, y, t, p, rectify_map, height, width):
         raise _plan.EincmError(rc, 'eincm_rectify_events failed')
     k = int(n_out.value)
     return ox[:k], oy[:k], ot[:k], op[:k].bool()
+
+
+def crop_events(xs, ys, ts, ps, x_offset=5, y_offset=2, height=256, width=336, in_height=260, in_width=346):
+    """The event crop of the reference's MVSEC loader (src/dataloaders/mvsec_loader.py:113-129): ``xs - 5, ys - 2``, events outside the
+    ``width x height`` window dropped, order kept.  Runs through ``eincm_rectify_events`` with a shift map whose out-of-window pixels
+    point outside the sensor.  ``ts`` may be float64 (MVSEC) or int64; returned with the dtype it came with."""
+    import torch
+    dev = f'cuda:{torch.cuda.current_device()}'
+    xx = torch.arange(in_width, device=dev, dtype=torch.float32) - float(x_offset)
+    yy = torch.arange(in_height, device=dev, dtype=torch.float32) - float(y_offset)
+    xx = torch.where((xx >= 0) & (xx < width), xx, torch.full_like(xx, -1.0))
+    yy = torch.where((yy >= 0) & (yy < height), yy, torch.full_like(yy, -1.0))
+    rmap = torch.stack([xx[None, :].expand(in_height, in_width), yy[:, None].expand(in_height, in_width)], dim=-1).contiguous()
+    t = ts if isinstance(ts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(ts)))
+    is_float = t.dtype == torch.float64
+    t_bits = t.contiguous().view(torch.int64) if is_float else t.to(torch.int64)
+    x, y, tt, p = rectify_events(xs, ys, t_bits, ps, rmap, in_height, in_width)
+    return x, y, (tt.view(torch.float64) if is_float else tt), p
 
 
 def window_event_range(idx_evt_start, idx_evt_end, n_total, des_n_events=None, prefer_latest_events=False):

@@ -49,3 +49,11 @@ def normalize_times(ts_us, start_time, end_time):
     uint64 with int64 to float64)."""
     ts = np.asarray(ts_us).astype(np.uint64)
     return (ts - np.int64(start_time)) / (np.int64(end_time) - np.int64(start_time) + sys.float_info.epsilon)
+
+
+def crop_events(xs, ys, ts, ps, x_offset=5, y_offset=2, height=256, width=336):
+    """src/dataloaders/mvsec_loader.py:113-129"""
+    xs = xs - x_offset
+    ys = ys - y_offset
+    m = (xs >= 0) & (xs < width) & (ys >= 0) & (ys < height)
+    return xs[m].astype('int16'), ys[m].astype('int16'), ts[m].astype('float64'), ps[m].astype('bool')

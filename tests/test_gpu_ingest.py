@@ -73,3 +73,17 @@ def test_stage_window_feeds_set_window():
     edges = torch.rand((3, H, W), dtype=torch.float64, device='cuda')
     pl.set_window(xs, ys, ts, edges, np.array([0.0, 0.5, 1.0]))
     pl.close()
+
+
+def test_mvsec_crop_matches_loader_code():
+    from eincm_b200 import dataloaders as D
+    rng = np.random.default_rng(9)
+    n = 50_000
+    xs = rng.integers(0, 346, n).astype(np.int16); ys = rng.integers(0, 260, n).astype(np.int16)
+    ts = np.sort(rng.uniform(1.5e9, 1.5e9 + 30.0, n)); ps = rng.integers(0, 2, n).astype(bool)
+    x, y, t, p = D.crop_events(xs, ys, ts, ps)
+    ex, ey, et, ep = G.crop_events(xs, ys, ts, ps)
+    assert 0 < len(ex) < n
+    assert np.array_equal(x.cpu().numpy(), ex) and np.array_equal(y.cpu().numpy(), ey)
+    assert np.array_equal(t.cpu().numpy(), et) and np.array_equal(p.cpu().numpy(), ep)       # float64 timestamps pass through bit for bit
+    assert int(x.max()) <= 335 and int(y.max()) <= 255

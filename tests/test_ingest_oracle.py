@@ -39,3 +39,11 @@ def test_normalize_times_known_answer():
     out = G.normalize_times(ts, 1_000_000, 1_100_000)
     assert out.dtype == np.float64
     np.testing.assert_array_equal(out, np.array([0.0, 50000.0, 100000.0]) / (100000.0 + 2.220446049250313e-16))
+
+
+def test_mvsec_crop_known_answer():
+    xs = np.array([4, 5, 340, 341, 100], np.int64); ys = np.array([10, 1, 2, 257, 258], np.int64)
+    ts = np.arange(5, dtype=np.float64); ps = np.array([1, 1, 0, 0, 1])
+    x, y, t, p = G.crop_events(xs, ys, ts, ps)
+    # x - 5 in [0, 336) and y - 2 in [0, 256): only (340, 2) -> (335, 0) and (341, 257) -> x = 336 is out; (100, 258) -> y = 256 is out
+    assert x.tolist() == [335] and y.tolist() == [0] and t.tolist() == [2.0] and p.tolist() == [False]
