@@ -213,3 +213,103 @@ def fast_nl_means_denoising(src, h=4, template_win_size=3, search_win_size=11):
             est += wgt * at(y, x)
             wsum += wgt
     return np.clip((est + wsum // 2) // wsum, 0, 255).astype(np.uint8)
+
+
+# ---- the steps of preprocess_image between the denoise and the bilateral filter (src/utils/img_utils.py:159-181) ---------------
+# Restated and pinned against cv2 as preparation for moving them to the device; no CUDA counterpart yet.
+# The bilateral filter that follows them (img_utils.py:183-189) is NOT restated: with OpenCV 4.13.0 from the opencv-python wheel its
+# interior comes from Intel IPP (truncating) and its left / right border columns from OpenCV's own code (rounding), so its output is a
+# property of the build, not of an algorithm one can cite.
+
+def clahe_apply(src, clip_limit=5.0, tile_grid_size=(10, 10)):
+    """cv.createCLAHE(clipLimit, tileGridSize).apply(src) for a uint8 image (modules/imgproc/src/clahe.cpp): per-tile histogram,
+    clip + redistribution (batch + residual with stride), LUT = round(cdf * 255 / tile area) in float32, bilinear blend of the four
+    neighbouring tile LUTs in float32, round half to even."""
+    src = np.asarray(src, np.uint8)
+    H, W = src.shape
+    tx, ty = int(tile_grid_size[0]), int(tile_grid_size[1])
+    if W % tx == 0 and H % ty == 0:
+        ext = src
+    else:                                                       # BORDER_REFLECT_101 padding on the right / bottom
+        ext = np.pad(src, ((0, ty - (H % ty)), (0, tx - (W % tx))), mode='reflect')
+    tw, th = ext.shape[1] // tx, ext.shape[0] // ty
+    area = tw * th
+    lut_scale = np.float32(255) / np.float32(area)
+    clip = max(int(clip_limit * area / 256), 1) if clip_limit > 0.0 else 0
+    luts = np.zeros((ty, tx, 256), np.uint8)
+    for j in range(ty):
+        for i in range(tx):
+            hist = np.bincount(ext[j * th:(j + 1) * th, i * tw:(i + 1) * tw].ravel(), minlength=256).astype(np.int64)
+            if clip > 0:
+                clipped = int(np.maximum(hist - clip, 0).sum())
+                hist = np.minimum(hist, clip)
+                batch = clipped // 256
+                residual = clipped - batch * 256
+                hist += batch
+                if residual != 0:
+                    step = max(256 // residual, 1)
+                    k = 0
+                    while k < 256 and residual > 0:
+                        hist[k] += 1
+                        k += step
+                        residual -= 1
+            luts[j, i] = np.clip(np.rint(np.cumsum(hist).astype(np.float32) * lut_scale), 0, 255).astype(np.uint8)
+    inv_tw, inv_th = np.float32(1.0) / np.float32(tw), np.float32(1.0) / np.float32(th)
+    txf = np.arange(W).astype(np.float32) * inv_tw - np.float32(0.5)
+    tx1 = np.floor(txf).astype(np.int64)
+    xa = (txf - tx1.astype(np.float32)).astype(np.float32)
+    xa1 = (np.float32(1.0) - xa).astype(np.float32)
+    tx2 = np.minimum(tx1 + 1, tx - 1)
+    tx1 = np.maximum(tx1, 0)
+    out = np.zeros((H, W), np.uint8)
+    for y in range(H):
+        tyf = np.float32(y) * inv_th - np.float32(0.5)
+        ty1 = int(np.floor(tyf))
+        ya = np.float32(tyf - np.float32(ty1))
+        ya1 = np.float32(1.0) - ya
+        ty2 = min(ty1 + 1, ty - 1)
+        ty1 = max(ty1, 0)
+        v = src[y]
+        res = ((luts[ty1, tx1, v].astype(np.float32) * xa1 + luts[ty1, tx2, v].astype(np.float32) * xa) * ya1
+               + (luts[ty2, tx1, v].astype(np.float32) * xa1 + luts[ty2, tx2, v].astype(np.float32) * xa) * ya)
+        out[y] = np.clip(np.rint(res.astype(np.float32)), 0, 255).astype(np.uint8)
+    return out
+
+
+def gaussian_kernel_u8_fixed_point(sigma):
+    """The 8-bit fixed-point kernel cv.GaussianBlur uses for uint8 images (getGaussianKernelFixedPoint_ED): size round(sigma * 6 + 1) | 1,
+    taps rounded to 1/256 with error diffusion from the ends inwards, centre tap = 256 - the rest."""
+    k = int(round(sigma * 3 * 2 + 1)) | 1
+    x = np.arange(k, dtype=np.float64) - (k - 1) * 0.5
+    w = np.exp(-0.5 / (sigma * sigma) * x * x)
+    w /= w.sum()
+    taps = np.zeros(k, np.int64)
+    err, total = 0.0, 0
+    for i in range(k // 2):
+        adj = w[i] * 256.0 + err
+        v = int(round(adj))
+        err = adj - v
+        taps[i] = taps[k - 1 - i] = v
+        total += v
+    taps[k // 2] = 256 - 2 * total
+    return taps
+
+
+def gaussian_blur_u8(src, sigma):
+    """cv.GaussianBlur(uint8 image, None, sigma, ...) - preprocess_image's sharpening blur (img_utils.py:165-169; as OpenCV reads that
+    call, sigmaX = sharpen_kernel_size = 3, 19 taps): separable integer filter with the 8-bit kernel, BORDER_REFLECT_101,
+    (sum + 2^15) >> 16."""
+    taps = gaussian_kernel_u8_fixed_point(float(sigma))
+    h = len(taps) // 2
+    a = np.asarray(src).astype(np.int64)
+    p = np.pad(a, ((0, 0), (h, h)), mode='reflect')
+    row = sum(taps[i] * p[:, i:i + a.shape[1]] for i in range(len(taps)))
+    p = np.pad(row, ((h, h), (0, 0)), mode='reflect')
+    col = sum(taps[i] * p[i:i + a.shape[0], :] for i in range(len(taps)))
+    return np.clip((col + (1 << 15)) >> 16, 0, 255).astype(np.uint8)
+
+
+def add_weighted_u8(a, alpha, b, beta, gamma=0.0):
+    """cv.addWeighted for uint8 images (img_utils.py:171-178): float32 arithmetic, round half to even, saturate."""
+    r = np.asarray(a).astype(np.float32) * np.float32(alpha) + np.asarray(b).astype(np.float32) * np.float32(beta) + np.float32(gamma)
+    return np.clip(np.rint(r), 0, 255).astype(np.uint8)

@@ -93,3 +93,17 @@ def test_nlm_oracle_matches_live_opencv(shape, h, t, sw):
     assert np.array_equal(E.fast_nl_means_denoising(f, h, t, sw), cv.fastNlMeansDenoising(f, None, h, t, sw))
     g = S.make_frames(max(shape[0], 8), max(shape[1], 8), 1, seed=3, noise_sigma=5.0)[0]
     assert np.array_equal(E.fast_nl_means_denoising(g, h, t, sw), cv.fastNlMeansDenoising(g, None, h, t, sw))
+
+
+@needs_cv
+@pytest.mark.parametrize('H,W,seed', [(480, 640, 0), (96, 128, 1), (61, 83, 2), (100, 100, 3)])
+def test_clahe_sharpen_restatements_match_live_opencv(H, W, seed):
+    """The steps of preprocess_image between the denoise and the bilateral filter (img_utils.py:159-181), called as the reference calls
+    them.  Restated for the next build step (no CUDA counterpart yet): bit-exact."""
+    f = S.make_frames(H, W, 1, seed=seed, noise_sigma=4.0)[0]
+    clahe = cv.createCLAHE(clipLimit=5, tileGridSize=(10, 10)).apply(f)
+    assert np.array_equal(E.clahe_apply(f, 5, (10, 10)), clahe)
+    blur = cv.GaussianBlur(clahe, None, 3, 2, 0)                              # positional like img_utils.py:165-169: sigmaX = 3
+    assert np.array_equal(E.gaussian_blur_u8(clahe, 3.0), blur)
+    assert np.array_equal(E.add_weighted_u8(clahe, 1.5, blur, -0.5), cv.addWeighted(clahe, 1.5, blur, -0.5, 0))
+    assert int(E.gaussian_kernel_u8_fixed_point(3.0).sum()) == 256 and len(E.gaussian_kernel_u8_fixed_point(3.0)) == 19
