@@ -493,7 +493,12 @@ def run_own(args):
                 group.close()
             return res
 
-        solve = run_solves('native', min(4, nw))
+        # Sequences per GPU: four when every driving thread can have a core of its own (each spins on its evaluation), fewer on hosts
+        # with fewer cores per rank - one sequence alone already keeps a B200 > 90 % busy (profiles/solve_breakdown.py: 15 windows/s),
+        # while 4 sequences per GPU squeezed onto 2 cores per rank measured 4.5 windows/s per GPU on 8 GPUs (profiles/r1_bench_8gpu.json).
+        cores_per_rank = max(1, len(os.sched_getaffinity(0)) // world)
+        n_seq = max(1, min(4, nw, cores_per_rank - 1)) if not args.group_sequences else min(4, nw)
+        solve = run_solves('native', n_seq)
         solve['note'] = ('eincm_b200.solver.MultipleLevelEINCMSolver (mirror of reference src/eincm/solver.py, main.yaml defaults: 5 levels, '
                          'BFGS 40/28/19/11/8 iterations, retries, handover solved at levels 1/0); optimizers native '
                          '(eincm_minimize_bfgs_host / eincm_minimize_handover_host), one host thread and one CUDA stream per '
