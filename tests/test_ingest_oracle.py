@@ -47,3 +47,20 @@ def test_mvsec_crop_known_answer():
     x, y, t, p = G.crop_events(xs, ys, ts, ps)
     # x - 5 in [0, 336) and y - 2 in [0, 256): only (340, 2) -> (335, 0) and (341, 257) -> x = 336 is out; (100, 258) -> y = 256 is out
     assert x.tolist() == [335] and y.tolist() == [0] and t.tolist() == [2.0] and p.tolist() == [False]
+
+
+def test_window_event_range_randomised_against_library():
+    """eincm_window_event_range is host arithmetic (no device): compared with the loader's lines on random index ranges."""
+    from hypothesis import given, settings, strategies as st
+    from eincm_b200 import dataloaders
+
+    @settings(max_examples=300, deadline=None, derandomize=True)
+    @given(n=st.integers(0, 5_000_000), data=st.data())
+    def check(n, data):
+        a = data.draw(st.integers(0, n))
+        b = data.draw(st.integers(a, n))
+        des = data.draw(st.one_of(st.none(), st.integers(1, 6_000_000)))
+        latest = data.draw(st.booleans())
+        assert dataloaders.window_event_range(a, b, n, des, latest) == G.window_event_range(a, b, n, des, latest)
+
+    check()
