@@ -33,6 +33,7 @@
 #include "k_image.cuh"
 #include "k_eval.cuh"
 #include "k_image_fused.cuh"
+#include "k_backward_fold.cuh"
 #include "eincm_opt.h"
 
 using namespace eincm;
@@ -105,6 +106,16 @@ struct eincm_plan {
     double2 *theta_full = nullptr, *Gtv = nullptr, *partial = nullptr;
     double *G = nullptr, *iwe = nullptr, *zero_iwe = nullptr, *dldi = nullptr, *edges = nullptr;
     float* dldi32 = nullptr;                           // default path: float32 copy of dL/dIWE, scaled by 1/(2 pi)
+    bool fused_fill = true;                            // EINCM_FUSED_FILL=0: d loss / d IWE by k_image_grad instead of inside the backward window fill
+    bool no_fold = true;                               // the fused backward is opt-in (EINCM_FLAG_FOLD_BACKWARD or EINCM_FOLD=1)
+    CellRec* rec = nullptr;                            // [max_refs][H*W] cell records of the image pass (fused backward fill)
+    bool rec_pending = false;                          // the last evaluation left its images in `rec`: iwe / adj32 are unpacked on demand
+    float* e32 = nullptr;                              // [max_refs][H*W] float32 copy of the edge images (fused backward fill)
+    cudaEvent_t window_ev = nullptr;                   // recorded behind the last kernel of set_window / window_finalize
+    cudaStream_t window_stream = nullptr;              // ... on this stream; evaluations on another stream wait for it once
+    bool window_ev_valid = false;
+    cudaStream_t window_waited = nullptr;              // stream that has already waited for window_ev of the current window
+    bool window_waited_valid = false;
     double *sbar = nullptr, *gNdiv = nullptr;          // delta != 0 only, allocated on first use
     double* part = nullptr;                            // per-CTA partials of the two-level reductions
     int part_doubles = 0;
@@ -156,6 +167,19 @@ int fail(eincm_plan* p, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(plan, EINCM_ECUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
         span_end(plan, span_, st);                                                                       \
     } while (0)
+
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while the previous kernel of the stream drains;
+// it calls griddepcontrol.wait before it touches anything the previous kernel produces.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 int span_begin(eincm_plan* p, const char* name, cudaStream_t st) {
     ++p->launch_count;
@@ -242,6 +266,9 @@ const void* image_pass_kernel(int W) {
     }
 }
 
+// dynamic shared memory of k_backward_fold: RB windows, reused as the [18][256] float reduction buffer of the theta fold
+size_t fold_smem_bytes(int rb) { return std::max<size_t>((size_t)rb * kWinCap * sizeof(float), (size_t)2 * kFoldTaps * kFoldTaps * 256 * sizeof(float)); }
+
 int event_grid(const eincm_plan* p, int64_t n, int threads) {
     const int64_t want = (n + threads - 1) / threads;
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 8));
@@ -287,6 +314,10 @@ int window_finalize_impl(eincm_plan* plan, cudaStream_t st) {
                                                     nullptr, plan->part, plan->sc->zero, &plan->sc->counters[1]));
     plan->window_final = true;
     plan->zero_div_valid = false;
+    // split-phase use (eincm_window_finalize is asynchronous): evaluations enqueued on ANOTHER stream must not overtake these
+    // kernels - they wait for this event once (forward_events_impl)
+    if (cudaEventRecord(plan->window_ev, st) != cudaSuccess) return fail(plan, EINCM_ECUDA, "cudaEventRecord failed");
+    plan->window_ev_valid = true; plan->window_stream = st; plan->window_waited_valid = false;
     return EINCM_OK;
 }
 
@@ -319,8 +350,8 @@ int splat_images(eincm_plan* plan, const ThetaSrc& T, const double2* theta_full,
         FixDst dst{};
         if (plan->n_peers > 0) { dst.n = plan->n_peers; for (int q = 0; q < dst.n; ++q) dst.p[q] = plan->peer_fix[q]; }
         else { dst.n = 1; dst.p[0] = plan->iwe_fix; }
-#define SPLATT(WR, RB) LAUNCH(tag, k_splat_tile<WR, RB><<<grid, 256, RB * kWinCap * sizeof(uint32_t), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
-                               plan->chunk_tr, plan->totals + 1, T, H, W, n_img, tref, dst, cw))
+#define SPLATT(WR, RB) LAUNCH(tag, launch_pdl(k_splat_tile<WR, RB>, dim3(grid), dim3(256), RB * kWinCap * sizeof(uint32_t), st, (const uint32_t*)plan->ev_xy, \
+                               (const double*)plan->ev_t, (const Chunk*)plan->chunks, (const float2*)plan->chunk_tr, (const unsigned int*)(plan->totals + 1), T, H, W, n_img, tref, dst, cw))
 #define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
                                                              case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
         if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
@@ -353,6 +384,10 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
     AxisTaps ty, tx;
     if ((rc = build_axis_taps(plan, h, plan->H, &ty))) return rc;
     if ((rc = build_axis_taps(plan, w, plan->W, &tx))) return rc;
+    if (plan->window_ev_valid && st != plan->window_stream && !(plan->window_waited_valid && plan->window_waited == st)) {
+        CU(cudaStreamWaitEvent(st, plan->window_ev, 0));
+        plan->window_waited = st; plan->window_waited_valid = true;
+    }
     plan->tsrc = ThetaSrc{theta, prev, a_ho, h, w, ty, tx};
     plan->theta_full_valid = false;
     // the dense field is only materialised for the float64 nine-tap kernels and the TV regulariser (and, on demand, the debug tap);
@@ -362,6 +397,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
     }
     // default path (single GPU, delta == 0): the fixed-point images are consumed by the fused image pass directly
     // single GPU, or event split with peer access (every rank then holds the complete fixed-point images after the barrier)
+    plan->rec_pending = false;
     plan->fused_pending = !plan->exact && plan->coop_ok && (!(plan->flags & EINCM_FLAG_EVENT_SPLIT) || plan->n_peers > 0) && hp->delta == 0.0;
     if ((rc = splat_images(plan, plan->tsrc, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
@@ -372,7 +408,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
 // host_out: device alias of mapped pinned memory; when the tile-theta gradient kernel runs it delivers [grad | loss | dalpha]
 // there itself (plan->host_delivered), otherwise the caller copies the results back.
 int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, double* dalpha_out, cudaStream_t st,
-                  double* host_out = nullptr, double host_seq = 0.0) {
+                  double* host_out = nullptr) {
     plan->host_delivered = false;
     plan->dldi_stale = false;
     int rc = check_hp(plan, hp);
@@ -393,6 +429,11 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, plan->iwe));
         plan->fused_pending = false;
     }
+    // Tile flow whose cells are at least one source tile wide (every pyramid level of the shipped recipes): the backward pass folds
+    // the per-event sums into the <= 3 x 3 theta elements of the source tile and evaluates d loss / d IWE inside its window fill -
+    // three launches per evaluation (k_backward_fold.cuh).  Otherwise: k_image_grad + k_backward_tile + k_theta_grad(_scatter).
+    const bool fold = plan->fused_pending && !use_div && !use_tv && want_grad && h * w <= kGatherMaxTiles && H >= kSortTile * h && W >= kSortTile * w &&
+                      !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && plan->n_events > 0 && !plan->no_fold;
     if (plan->fused_pending) {
         if (use_tv) {
             const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
@@ -402,9 +443,11 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         const int tvb = ((W + kTvTX - 1) / kTvTX) * ((H + kTvTY - 1) / kTvTY);
         ImageStatsArgs ia{};
         ia.fix = plan->iwe_fix; ia.edges = plan->edges; ia.iwe = plan->iwe; ia.adj32 = plan->adj32;
+        ia.rec = (fold && plan->fused_fill) ? plan->rec : nullptr; ia.e32 = plan->e32;
+        plan->rec_pending = ia.rec != nullptr;
         ia.part = plan->part + 2 * tvb;                          // k_tv's partials live at the start of `part`
         ia.sc = plan->sc; ia.loss_out = loss_out;
-        ia.zero_buf = want_grad ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
+        ia.zero_buf = (want_grad && !fold) ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
         g_zeroed = want_grad;
         if (want_grad && h * w <= kGatherMaxTiles) {
             ia.zero_buf2 = grad_out ? grad_out : plan->grad_buf; ia.n_zero2 = h * w * 2;
@@ -432,13 +475,44 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         {
             typedef void (*stats_fn)(const ImageStatsArgs);
             stats_fn fn = (stats_fn)image_pass_kernel(W);
-            LAUNCH("k_image_stats", fn<<<cc.ctas, kBandNT, image_pass_smem_bytes(W, cc.band_rows), st>>>(ia));
+            LAUNCH("k_image_stats", launch_pdl(fn, dim3(cc.ctas), dim3(kBandNT), image_pass_smem_bytes(W, cc.band_rows), st, ia));
+        }
+        if (fold && !plan->fused_fill) {
+            // d loss / d IWE materialised by its own (pointwise) kernel, which also clears the fixed-point images
+            ImageGradArgs ga{};
+            ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
+            ga.dldi = nullptr; ga.dldi32 = plan->dldi32; ga.HW = (int)plan->HW; ga.R = R; ga.want_grad = 1;
+            LAUNCH("k_image_grad", launch_pdl(k_image_grad, dim3(std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8))), dim3(256), 0, st, ga));
+        }
+        if (fold) {
+            BackwardFoldArgs ba{};
+            ba.dldi32 = plan->fused_fill ? nullptr : plan->dldi32;
+            ba.ev_xy = plan->ev_xy; ba.ev_t = plan->ev_t; ba.chunks = plan->chunks; ba.n_chunks_dev = plan->totals + 1;
+            ba.T = plan->tsrc; ba.H = H; ba.W = W; ba.R = R; ba.tref = plan->tref;
+            ba.rec = plan->rec; ba.chunk_win = plan->chunk_win; ba.sc = plan->sc;
+            ba.grad = grad_out ? grad_out : plan->grad_buf;
+            ba.loss_dev = loss_out ? loss_out : &plan->sc->loss; ba.host_out = host_out; ba.host_grad = grad_out != nullptr ? 1 : 0;
+            ba.fix_clear = plan->fused_fill ? plan->iwe_fix : nullptr; ba.n_fix = (int64_t)R * plan->HW;
+            const int gridF = std::max(1, plan->n_chunks);
+#define BFOLD(WR, RB) LAUNCH("k_backward_fold", launch_pdl(k_backward_fold<WR, RB>, dim3(gridF), dim3(256), fold_smem_bytes(RB), st, ba))
+#define BFOLD_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BFOLD(WR, 1); break; case 2: BFOLD(WR, 2); break; \
+                                                           case 3: BFOLD(WR, 3); break; default: BFOLD(WR, 4); } } while (0)
+            if (plan->wrap) BFOLD_RB(true); else BFOLD_RB(false);
+#undef BFOLD_RB
+#undef BFOLD
+            plan->dldi_stale = true;                                 // the float64 d loss / d IWE (debug tap) is built on demand
+            plan->fused_pending = false;
+            // cells of images R .. max_refs - 1 were never written: the whole buffer is clean again
+            plan->fix_clean = true;
+            plan->host_delivered = host_out != nullptr;
+            if (dalpha_out) CU(cudaMemcpyAsync(dalpha_out, &plan->sc->dalpha, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            return EINCM_OK;
         }
         ImageGradArgs ga{};
         ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
         ga.dldi = nullptr; ga.dldi32 = plan->dldi32; ga.HW = (int)plan->HW; ga.R = R; ga.want_grad = want_grad ? 1 : 0;
         plan->dldi_stale = want_grad;                            // the float64 copy (debug tap) is produced on demand: eincm_dldi_ptr
-        LAUNCH("k_image_grad", k_image_grad<<<std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8)), 256, 0, st>>>(ga));
+        LAUNCH("k_image_grad", launch_pdl(k_image_grad, dim3(std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8))), dim3(256), 0, st, ga));
         plan->fused_pending = false;
         plan->fix_clean = true;                                  // the pass clears the cells it has read
         if (!want_grad) return EINCM_OK;
@@ -484,8 +558,9 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
                                                                                            plan->tref, plan->dldi, plan->G));
         } else {
             const int gridT2 = std::max(1, plan->n_chunks);
-#define BWDT(WR, RB) LAUNCH("k_backward_events", k_backward_tile<WR, RB><<<gridT2, 256, RB * kWinCap * sizeof(float), st>>>(plan->ev_xy, plan->ev_t, plan->chunks, \
-                                   plan->totals + 1, plan->tsrc, H, W, R, plan->tref, plan->dldi32, plan->chunk_win, plan->G))
+#define BWDT(WR, RB) LAUNCH("k_backward_events", launch_pdl(k_backward_tile<WR, RB>, dim3(gridT2), dim3(256), RB * kWinCap * sizeof(float), st, (const uint32_t*)plan->ev_xy, \
+                                   (const double*)plan->ev_t, (const Chunk*)plan->chunks, (const unsigned int*)(plan->totals + 1), plan->tsrc, H, W, R, plan->tref, \
+                                   (const float*)plan->dldi32, (const int4*)plan->chunk_win, plan->G))
 #define BWDT_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BWDT(WR, 1); break; case 2: BWDT(WR, 2); break; \
                                                            case 3: BWDT(WR, 3); break; default: BWDT(WR, 4); } } while (0)
             if (plan->wrap) BWDT_RB(true); else BWDT_RB(false);
@@ -512,11 +587,11 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         if (Gtv != nullptr)
             LAUNCH("k_theta_grad", k_theta_grad<true><<<gridG, kTgWarps * 32, 0, st>>>(
                 (const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0, host_seq));
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0));
         else
-            LAUNCH("k_theta_grad", k_theta_grad<false><<<gridG, kTgWarps * 32, 0, st>>>(
-                (const double2*)plan->G, nullptr, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0, host_seq));
+            LAUNCH("k_theta_grad", launch_pdl(k_theta_grad<false>, dim3(gridG), dim3(kTgWarps * 32), 0, st,
+                (const double2*)plan->G, (const double2*)nullptr, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
+                (const double*)(handover ? plan->last_prev : nullptr), plan->last_theta, gout, (const double*)loss_out, host_out, grad_out != nullptr ? 1 : 0));
         plan->host_delivered = host_out != nullptr;
     } else {
         CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
@@ -571,6 +646,13 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
                       opt_in((const void*)k_backward_tile<true, RB>, RB); opt_in((const void*)k_backward_tile<false, RB>, RB)
         OPT_IN_RB(1); OPT_IN_RB(2); OPT_IN_RB(3); OPT_IN_RB(4);
 #undef OPT_IN_RB
+        auto opt_in_fold = [&](const void* fn, int rb) {
+            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fold_smem_bytes(rb));
+            max_carveout(fn);
+        };
+#define OPT_IN_FOLD(RB) opt_in_fold((const void*)k_backward_fold<true, RB>, RB); opt_in_fold((const void*)k_backward_fold<false, RB>, RB)
+        OPT_IN_FOLD(1); OPT_IN_FOLD(2); OPT_IN_FOLD(3); OPT_IN_FOLD(4);
+#undef OPT_IN_FOLD
         max_carveout((const void*)k_image_grad);
         max_carveout((const void*)k_theta_grad<false>); max_carveout((const void*)k_theta_grad<true>);
         max_carveout((const void*)k_theta_grad_scatter); max_carveout((const void*)k_tv); max_carveout((const void*)k_upsample_theta);
@@ -625,6 +707,8 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         if (!plan->exact) {
             CU(dmalloc(&plan->dldi32, RR * HW));
             CU(dmalloc(&plan->adj32, RR * HW));
+            CU(dmalloc(&plan->e32, RR * HW));
+            CU(dmalloc(&plan->rec, RR * HW));
             CU(dmalloc(&plan->iwe_fix, RR * HW));
             CU(dmalloc(&plan->chunk_win, (size_t)plan->chunk_cap * RR));
         }
@@ -635,8 +719,15 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(dmalloc(&plan->grad_stage, HW * 2 + 8)); CU(dmalloc(&plan->grad_buf, HW * 2));     // + 8: loss slot right behind a staged gradient
         CU(dmalloc(&plan->out_stage, 8));
         CU(cudaHostAlloc((void**)&plan->h_pinned, (HW * 2 + 1024) * sizeof(double), cudaHostAllocMapped));
+        // the sequence slot the host entry points poll must not hold a stale number of an earlier plan (freed pinned memory is reused)
+        std::memset(plan->h_pinned, 0, (HW * 2 + 1024) * sizeof(double));
         CU(cudaHostGetDevicePointer((void**)&plan->h_mapped_dev, plan->h_pinned, 0));
         CU(cudaStreamCreateWithFlags(&plan->own_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&plan->window_ev, cudaEventDisableTiming));
+        // the fused backward (k_backward_fold.cuh) is opt-in: measured on a B200 it is no faster than the unfused kernels, whose small
+        // launches overlap with the event kernels of concurrently evaluated windows (profiles/r2_fold_ab.txt)
+        { const char* nf = std::getenv("EINCM_FOLD"); plan->no_fold = !((flags & EINCM_FLAG_FOLD_BACKWARD) || (nf != nullptr && nf[0] == '1')); }
+        { const char* ff = std::getenv("EINCM_FUSED_FILL"); plan->fused_fill = !(ff != nullptr && ff[0] == '0'); }
         if (flags & EINCM_FLAG_BLOCKING_SYNC) CU(cudaEventCreateWithFlags(&plan->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
         return EINCM_OK;
@@ -654,7 +745,8 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
 void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
-    void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
+    if (plan->window_ev) cudaEventDestroy(plan->window_ev);
+    void* bufs[] = {plan->rec, plan->e32, plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
                     plan->chunk_first, plan->totals, plan->adj32, plan->chunks, plan->chunks2, plan->chunk_tr, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
@@ -740,7 +832,7 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
                                                                                                           plan->totals + 1, plan->chunk_tr));
     }
     CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc));
+    LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc, plan->e32));
     // zero-warp IWE (losses.py:54): theta = 0 => x' = x for every reference time
     {
         RefTimes z{};
@@ -751,14 +843,21 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     }
     // validate (the reference's loaders guarantee in-sensor events; a violation would corrupt the gather at
     // event_warpers.py:34-35, so it is an error here).  One 4-byte read back per window.
+    // The zero-warp statistics are launched BEFORE the read-back and its synchronisation: when this call returns, no kernel of the
+    // staging is still in flight on `st` (an evaluation on another stream - the plan's own stream - may follow at once).
+    if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) {
+        const int rcf = window_finalize_impl(plan, st);
+        if (rcf) return rcf;
+    }
     CU(cudaMemcpyAsync(plan->h_flag, &plan->sc->error_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(plan->h_flag + 1, plan->totals, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (plan->h_flag[0] != 0) return fail(plan, EINCM_ERANGE, "an event lies outside the %dx%d sensor", plan->H, plan->W);
+    if (plan->h_flag[0] != 0) { plan->window_final = false; return fail(plan, EINCM_ERANGE, "an event lies outside the %dx%d sensor", plan->H, plan->W); }
     plan->n_stream = (int64_t)(unsigned int)plan->h_flag[1];
     plan->n_chunks = (int)(unsigned int)plan->h_flag[2];
     plan->window_set = true;
-    if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return window_finalize_impl(plan, st);
+    plan->window_ev_valid = false;           // everything is complete (synchronised above): nothing to wait for
+    plan->window_waited_valid = false;
     return EINCM_OK;
 }
 
@@ -827,12 +926,12 @@ int host_enqueue_impl(eincm_plan* plan, const double* theta_host, int h, int w, 
     double* loss_dev = plan->grad_stage + n_g;
     int rc = forward_events_impl(plan, plan->theta_stage, nullptr, 0.0, h, w, hp, st);
     if (rc) return rc;
-    const bool small = n_g + 3 <= 1000;                                // fits behind the theta staging area
-    plan->host_seq += 1.0;
-    if (small) plan->h_pinned[(size_t)plan->HW * 2 + 16 + n_g + 2] = -1.0;     // sequence slot of this evaluation: not yet written
+    // results come back as [sequence | loss | d alpha | gradient] in the mapped area behind the theta staging area when they fit
+    const bool small = n_g + 3 <= 1000;
     rc = backward_impl(plan, hp, loss_dev, want_grad ? plan->grad_stage : nullptr, nullptr, st,
-                       small ? plan->h_mapped_dev + (size_t)plan->HW * 2 + 16 : nullptr, plan->host_seq);
+                       small ? plan->h_mapped_dev + (size_t)plan->HW * 2 + 16 : nullptr);
     if (rc) return rc;
+    if (plan->host_delivered) plan->host_seq += 1.0;                   // the delivering kernel counts the same way (DevScalars::eval_seq)
     if (!plan->host_delivered)
         CU(cudaMemcpyAsync(plan->h_pinned, plan->grad_stage, (n_g + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
     return EINCM_OK;
@@ -850,12 +949,12 @@ int host_wait(eincm_plan* plan, cudaStream_t st) {
 }
 
 int host_collect_impl(eincm_plan* plan, double* loss_out_host, double* grad_out_host, cudaStream_t st) {
-    const double* h_res = plan->host_delivered ? plan->h_pinned + (size_t)plan->HW * 2 + 16 : plan->h_pinned;   // [grad | loss]
+    const double* h_map = plan->h_pinned + (size_t)plan->HW * 2 + 16;   // [sequence | loss | d alpha | gradient] (delivered by the last kernel)
     bool arrived = false;
     if (plan->host_delivered && plan->wait_ev == nullptr) {
-        // the last kernel wrote [grad | loss | d alpha | sequence number] into mapped pinned memory: poll the sequence number
-        // there (bounded; an error or a very long evaluation ends in the stream synchronisation below)
-        const volatile double* seq = h_res + plan->host_ng + 2;
+        // poll the sequence number in mapped pinned memory (bounded; an error or a very long evaluation ends in the stream
+        // synchronisation below)
+        const volatile double* seq = h_map;
         // a short pure spin (lowest latency), then yield between polls: on a host with fewer cores than driving threads the
         // optimizers of the other sequences get the core while this thread waits; with idle cores the yield returns at once
         const double t_end = now_s() + 2.0;
@@ -876,8 +975,13 @@ int host_collect_impl(eincm_plan* plan, double* loss_out_host, double* grad_out_
         const int rcw = host_wait(plan, st);
         if (rcw) return rcw;
     }
-    *loss_out_host = h_res[plan->host_ng];
-    if (grad_out_host) std::memcpy(grad_out_host, h_res, plan->host_ng * sizeof(double));
+    if (plan->host_delivered) {
+        *loss_out_host = h_map[1];
+        if (grad_out_host) std::memcpy(grad_out_host, h_map + 3, plan->host_ng * sizeof(double));
+    } else {                                                            // staged copy: [gradient | loss]
+        *loss_out_host = plan->h_pinned[plan->host_ng];
+        if (grad_out_host) std::memcpy(grad_out_host, plan->h_pinned, plan->host_ng * sizeof(double));
+    }
     return EINCM_OK;
 }
 
@@ -1125,11 +1229,27 @@ int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_ho
 }
 
 double* eincm_zero_iwe_ptr(eincm_plan* plan) { return plan ? plan->zero_iwe : nullptr; }
-double* eincm_iwe_ptr(eincm_plan* plan) { return plan ? plan->iwe : nullptr; }
+
+// debug taps: the fused path keeps the images of the last evaluation as cell records - unpack them (synchronous)
+static bool unpack_records(eincm_plan* plan) {
+    if (!plan->rec_pending) return true;
+    if (cudaSetDevice(plan->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return false;
+    const int64_t n = (int64_t)plan->R * plan->HW;
+    k_unpack_records<<<(int)std::min<int64_t>((n + 255) / 256, plan->sm_count * 8), 256>>>(plan->rec, n, plan->iwe, plan->adj32);
+    if (cudaDeviceSynchronize() != cudaSuccess) return false;
+    plan->rec_pending = false;
+    return true;
+}
+
+double* eincm_iwe_ptr(eincm_plan* plan) {
+    if (!plan || !unpack_records(plan)) return nullptr;
+    return plan->iwe;
+}
 uint8_t* eincm_mask_ptr(eincm_plan* plan) { return plan ? plan->mask : nullptr; }
 double* eincm_dldi_ptr(eincm_plan* plan) {
     if (!plan) return nullptr;
     if (plan->dldi_stale) {
+        if (!unpack_records(plan)) return nullptr;
         // the fused image pass only writes the float32 copy the event kernels read: rebuild the float64 image of the last evaluation
         // from the same operands (debug tap: synchronous)
         if (cudaSetDevice(plan->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return nullptr;

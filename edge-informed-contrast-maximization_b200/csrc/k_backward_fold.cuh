@@ -1,0 +1,370 @@
+// Fused backward pass of the default path for tile flow fields (every source tile of 16x16 pixels touches <= 3 x 3 theta elements):
+// ONE kernel does what k_image_grad + k_backward_tile + k_theta_grad (+ the clear of the dense gradient field G) did.
+//
+//   * window fill: d loss / d IWE of the window cells is evaluated on the fly from the cell records k_image_stats left behind (image
+//     value, Scharr adjoint, edge value: one 16-byte load per cell) and the per-reference coefficients of its last CTA
+//     (DevScalars::cot) - no dense d loss / d IWE image is written or read (reverse mode of contrast_objectives.py:22-25,
+//     img_utils.py:24-25, correlation_objectives.py:25-26; the min / max cotangents are split evenly among ties like jnp.min / max).
+//     One warp per window row, lanes along the row;
+//   * event gather: as k_backward_tile (nine shared-memory loads per event and reference time, separable tap derivative);
+//   * reverse of the warp and of the resize (event_warpers.py:34-35, theta_utils.py:25-35): the per-event sums -(t - t_ref) dL/dx'
+//     are folded straight into the <= 3 x 3 theta elements whose bilinear support covers the source tile (weights per tile row /
+//     column in shared memory), reduced over the warp with a shuffle reduce-scatter and added to the gradient with <= 18 float64
+//     reductions per warp - the dense field G[H][W][2], its clear, its per-pixel reductions and the W^T G W kernel are gone
+//     (SURVEY.md K11 / K12);
+//   * the last CTA evaluates d loss / d alpha_handover (losses.py:269) and delivers [sequence | loss | d alpha | gradient] into
+//     mapped pinned host memory for the synchronous host entry points;
+//   * every CTA clears its slice of the fixed-point images for the next evaluation (all readers finished: kernel boundary).
+//
+// Launched with programmatic stream serialization behind k_image_stats: everything before griddepcontrol.wait (chunk record, event
+// loads, theta of the tile, resize weights) only reads per-window constants and the flow operand and overlaps the tail of the
+// image pass.
+#pragma once
+#include "k_events_tile.cuh"
+#include "k_image_fused.cuh"
+
+namespace eincm {
+
+constexpr int kFoldTicket = 7;            // DevScalars::counters slot of the "last CTA" ticket
+constexpr int kFoldTaps = 3;              // theta elements per axis whose support can cover one 16-pixel tile edge
+constexpr int kFoldSums = 2 * kFoldTaps * kFoldTaps;
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+struct BackwardFoldArgs {
+    const uint32_t* ev_xy; const double* ev_t; const Chunk* chunks; const unsigned int* n_chunks_dev;
+    ThetaSrc T;
+    int H, W, R;
+    RefTimes tref;
+    const CellRec* rec;          // [R][H*W] cell records of the image pass: image value, Scharr adjoint, edge value (k_image_stats)
+    const float* dldi32;         // non-null: d loss / d IWE / (2 pi) was materialised by k_image_grad - the fill copies it instead
+    const int4* chunk_win;       // [n_chunks][R] destination rectangles recorded by the forward pass
+    DevScalars* sc;
+    double* grad;                // [h][w][2] pre-zeroed accumulator (the caller's gradient, or an internal buffer for handover calls)
+    const double* loss_dev;      // loss of this evaluation (k_image_stats)
+    double* host_out;            // mapped pinned host memory [seq | loss | dalpha | grad...] or null
+    int host_grad;               // copy the gradient to host_out
+    unsigned long long* fix_clear;   // fixed-point images to clear for the next evaluation (or null)
+    int64_t n_fix;               // cells of fix_clear (< 2^32)
+};
+
+// float32 form of the per-reference coefficients held in shared memory by the fill (min / max stay float64: the tie tests are exact)
+struct CotCoefF { float cA, a1, a2, a3, tm, tM; double mn, mx; };
+
+__device__ __forceinline__ CotCoefF cot_to_float(const CotCoef& c) {
+    CotCoefF f;
+    f.cA = (float)c.cA; f.a1 = (float)c.a1; f.a2 = (float)c.a2; f.a3 = (float)c.a3; f.tm = (float)c.tm; f.tM = (float)c.tM;
+    f.mn = c.mn; f.mx = c.mx;
+    return f;
+}
+
+// d loss / d IWE / (2 pi) of one cell from its image value, edge value and Scharr adjoint (the value k_image_grad stores as dldi32;
+// evaluated in float32 here - the result is a float32 either way)
+__device__ __forceinline__ float cotangent_value(const CotCoefF& c, double I, float E, float A) {
+    float out = fmaf(c.cA, A, fmaf(c.a1, E, fmaf(-c.a2, (float)I, c.a3)));
+    out += (I == c.mn) ? c.tm : 0.f;
+    out += (I == c.mx) ? c.tM : 0.f;
+    return out;
+}
+
+__device__ __forceinline__ CellRec ld_rec(const CellRec* p) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    CellRec c;
+    c.I = v.x;
+    c.adj = __int_as_float(__double2loint(v.y)); c.e = __int_as_float(__double2hiint(v.y));
+    return c;
+}
+
+__device__ __forceinline__ float cotangent_cell(const CotCoefF& c, const CellRec* __restrict__ rec, int idx) {
+    const CellRec v = ld_rec(rec + idx);
+    return cotangent_value(c, v.I, v.e, v.adj);
+}
+
+// cold path: nine cotangent cells straight from the global records with the reference's index rule (sliced rectangles, misses)
+template <bool WRAP>
+__device__ __noinline__ float2 gather_fallback_fused(const CotCoefF& c, const CellRec* __restrict__ rec, uint32_t xy, double2 th, double dt, int H, int W) {
+    const Hit2 h = warp_hit2(xy, th, dt);
+    if (!((fabs(h.xw) < 1.0e9) && (fabs(h.yw) < 1.0e9))) return make_float2(0.f, 0.f);
+    float d[9];
+    for (int j = -1; j <= 1; ++j)
+        for (int i = -1; i <= 1; ++i) {
+            int rr = h.ry + j, cc = h.rx + i;
+            d[(j + 1) * 3 + (i + 1)] = drop_index<WRAP>(rr, cc, H, W) ? cotangent_cell(c, rec, rr * W + cc) : 0.f;
+        }
+    float gx, gy;
+    tap_gradient(d, h.fx, h.fy, gx, gy);
+    return make_float2(gx, gy);
+}
+
+// One halving step of the warp-wide "reduce-scatter" of the theta fold: every lane holds N_IN partial sums; after the step it holds
+// N_OUT = ceil(N_IN / 2) sums over itself and its partner (lane ^ OFFSET) - the lane whose OFFSET bit is clear keeps the values
+// 0 .. N_OUT - 1, the other one the values N_OUT .. 2 N_OUT - 1 (an index >= N_IN is a padding zero).
+template <int N_IN, int OFFSET>
+__device__ __forceinline__ void fold_halve(float (&v)[kFoldSums], bool hi) {
+    constexpr int N_OUT = (N_IN + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < N_OUT; ++i) {
+        const float lo_v = v[i], hi_v = (i + N_OUT < N_IN) ? v[i + N_OUT] : 0.f;
+        const float send = hi ? lo_v : hi_v, keep = hi ? hi_v : lo_v;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFFSET);
+    }
+}
+
+// this CTA's slice of the fixed-point images (pairs of cells, 16-byte stores)
+__device__ __forceinline__ void clear_fix_slice(const BackwardFoldArgs& A) {
+    if (A.fix_clear == nullptr) return;
+    const uint32_t n2 = (uint32_t)((A.n_fix + 1) / 2), per = (n2 + gridDim.x - 1u) / gridDim.x;
+    const uint32_t lo = per * blockIdx.x, hi = min(n2, lo + per);
+    uint4* f4 = reinterpret_cast<uint4*>(A.fix_clear);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += 256u) f4[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+template <bool WRAP, int RB>
+__device__ __forceinline__ void backward_fold_body(const BackwardFoldArgs& A, float* dwin /* [RB][kWinCap] dynamic smem */) {
+    __shared__ double2 th_s[kKeysPerTile];
+    __shared__ Window swin[RB];
+    __shared__ CotCoefF scot[RB];
+    __shared__ float s_wy[kSortTile][4], s_wx[kSortTile][4];      // resize weights of the tile's rows / columns on taps base + 0..2
+    __shared__ int s_base[2];
+    __shared__ double s_red[8];
+    __shared__ bool s_last;
+    const int H = A.H, W = A.W, R = A.R;
+    const int HW = H * W;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_chunks = (int)__ldg(A.n_chunks_dev);
+    const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(dwin);
+    pdl_launch_dependents();
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const Chunk ch = A.chunks[c];
+        EventGroup ev;
+        load_chunk_events<false>(A.ev_xy, A.ev_t, ch, ev);
+        tile_theta(A.T, ch.origin, H, W, th_s);
+        // resize weights of the tile's rows (threads 0..15) and columns (16..31) on the taps base .. base + 2 (axis_weight of k_theta.cuh)
+        if (tid < 2 * kSortTile) {
+            const bool col = tid >= kSortTile;
+            const int k = tid & (kSortTile - 1);
+            const AxisTaps& t = col ? A.T.tx : A.T.ty;
+            const int o0 = col ? (int)(ch.origin & 0xffffu) : (int)(ch.origin >> 16), n_out = col ? W : H, o = o0 + k;
+            const int base = __ldg(t.i0 + o0);
+            float* dst = col ? s_wx[k] : s_wy[k];
+            dst[0] = 0.f; dst[1] = 0.f; dst[2] = 0.f; dst[3] = 0.f;
+            if (o < n_out) {
+                const int i0 = __ldg(t.i0 + o), i1 = __ldg(t.i1 + o);
+                const int a0 = min(max(i0 - base, 0), kFoldTaps - 1), a1 = min(max(i1 - base, 0), kFoldTaps - 1);
+                dst[a0] += (float)__ldg(t.w0 + o);
+                if (i1 != i0) dst[a1] += (float)__ldg(t.w1 + o);
+            }
+            if (k == 0) s_base[col ? 1 : 0] = base;
+        }
+        const bool active = 4u * (unsigned)tid < ch.count;
+        float ax[kEvK], ay[kEvK];
+#pragma unroll
+        for (int k = 0; k < kEvK; ++k) { ax[k] = 0.f; ay[k] = 0.f; }
+        if (c == (int)blockIdx.x) {
+            // first chunk of this CTA: everything above read per-window constants and the flow operand only; from here on the
+            // results of the image pass are read and the fixed-point images are cleared
+            pdl_wait();
+            clear_fix_slice(A);
+        }
+        for (int r0 = 0; r0 < R; r0 += RB) {
+            if (r0 > 0) __syncthreads();             // previous readers of swin / dwin are done
+            if (tid < RB) {
+                int4 q = make_int4(0, 0, 0, 0);
+                if (r0 + tid < R) { q = A.chunk_win[(int64_t)c * R + r0 + tid]; scot[tid] = cot_to_float(A.sc->cot[r0 + tid]); }
+                Window wn = slice_window(q, 0);      // a sliced rectangle (large flow): first slice here, the rest gathers from the global images
+                set_interior(wn, H, W);
+                swin[tid] = wn;
+            }
+            __syncthreads();                         // also: th_s / s_wy / s_wx of this chunk are visible
+            // window cells <- d loss / d IWE / (2 pi): one warp per window row, lanes along the row (coalesced, no per-cell index
+            // arithmetic); two rows per warp and round so that two loads per lane are in flight
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                if (r0 + r >= R) continue;
+                const Window wn = swin[r];
+                const CotCoefF cc = scot[r];
+                const CellRec* recr = A.rec + (int64_t)(r0 + r) * HW;
+                const float* img = A.dldi32 != nullptr ? A.dldi32 + (int64_t)(r0 + r) * HW : nullptr;
+                float* wr = dwin + r * kWinCap;
+                const bool interior = wn.interior != 0u;
+                for (int row = wid; row < wn.ph; row += 16) {
+                    int rr[2];
+                    bool rok[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        rr[u] = wn.oy + row + 8 * u;
+                        rok[u] = row + 8 * u < wn.ph;
+                        if (!interior) {
+                            if (WRAP && rr[u] < 0) rr[u] += H;
+                            rok[u] = rok[u] && rr[u] >= 0 && rr[u] < H;
+                        }
+                    }
+                    for (int col = lane; col < wn.pw; col += 32) {
+                        int cq = wn.ox + col;
+                        bool cok = true;
+                        if (!interior) {
+                            if (WRAP && cq < 0) cq += W;
+                            cok = cq >= 0 && cq < W;
+                        }
+                        float v[2] = {0.f, 0.f};
+                        if (img != nullptr) {                    // unfused fill: d loss / d IWE was materialised by k_image_grad
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) if (rok[u] && cok) v[u] = __ldg(img + rr[u] * W + cq);
+                        } else {
+                            CellRec cr[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                cr[u].I = 0.0; cr[u].adj = 0.f; cr[u].e = 0.f;
+                                if (rok[u] && cok) cr[u] = ld_rec(recr + rr[u] * W + cq);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) if (rok[u] && cok) v[u] = cotangent_value(cc, cr[u].I, cr[u].e, cr[u].adj);
+                        }
+                        wr[row * wn.pw + col] = v[0];
+                        if (row + 8 < wn.ph) wr[(row + 8) * wn.pw + col] = v[1];
+                    }
+                }
+            }
+            __syncthreads();
+            int n_hit = 0, n_valid = 0;
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) n_valid += ev.xy[k] != kNoEvent ? 1 : 0;
+                n_valid *= min(RB, R - r0);
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    if (r0 + r >= R) continue;
+                    const Window wn = swin[r];
+                    const uint32_t pitch4 = (uint32_t)wn.pw * 4u;
+                    const uint32_t wb = win_base + (uint32_t)(r * kWinCap - (wn.oy * wn.pw + wn.ox)) * 4u;
+                    const uint32_t safe = win_base + (uint32_t)(r * kWinCap) * 4u + pitch4 + 4u;
+                    const double tr = A.tref.t[r0 + r];
+#pragma unroll
+                    for (int k = 0; k < kEvK; ++k) {
+                        const uint32_t xy = ev.xy[k];
+                        const double dt = ev.t[k] - tr;
+                        const Hit2 hh = warp_hit2(xy, lds_theta(th_base, xy), dt);
+                        const bool valid = xy != kNoEvent;
+                        const bool hit = valid & (fabs(hh.xw - wn.cx) < wn.hx) & (fabs(hh.yw - wn.cy) < wn.hy);
+                        const uint32_t mid = hit ? wb + (uint32_t)(hh.ry * wn.pw + hh.rx) * 4u : safe;
+                        const uint32_t up = mid - pitch4, dn = mid + pitch4;
+                        float d[9];
+                        asm volatile("ld.shared.f32 %0, [%9 + -4];\n\tld.shared.f32 %1, [%9];\n\tld.shared.f32 %2, [%9 + 4];\n\t"
+                                     "ld.shared.f32 %3, [%10 + -4];\n\tld.shared.f32 %4, [%10];\n\tld.shared.f32 %5, [%10 + 4];\n\t"
+                                     "ld.shared.f32 %6, [%11 + -4];\n\tld.shared.f32 %7, [%11];\n\tld.shared.f32 %8, [%11 + 4];"
+                                     : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]), "=f"(d[8])
+                                     : "r"(up), "r"(mid), "r"(dn));
+                        float gx, gy;
+                        tap_gradient(d, hit ? hh.fx : 0.f, hit ? hh.fy : 0.f, gx, gy);
+                        const float ndt = -(float)dt;
+                        // a miss may have read anything (and a padding sentinel has no timestamp): select, do not multiply by zero
+                        ax[k] = hit ? fmaf(ndt, gx, ax[k]) : ax[k];
+                        ay[k] = hit ? fmaf(ndt, gy, ay[k]) : ay[k];
+                        n_hit += hit ? 1 : 0;
+                    }
+                }
+            }
+            if (n_hit != n_valid) {
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) {
+                    if (ev.xy[k] == kNoEvent) continue;
+                    const double2 th = lds_theta(th_base, ev.xy[k]);
+#pragma unroll 1
+                    for (int r = 0; r < RB && r0 + r < R; ++r) {
+                        const double dt = ev.t[k] - A.tref.t[r0 + r];
+                        const Hit2 hh = warp_hit2(ev.xy[k], th, dt);
+                        const Window& wn = swin[r];
+                        if (!((fabs(hh.xw - wn.cx) < wn.hx) & (fabs(hh.yw - wn.cy) < wn.hy))) {
+                            const int64_t off = (int64_t)(r0 + r) * HW;
+                            const float2 g = A.dldi32 != nullptr ? gather_fallback<WRAP>(A.dldi32 + off, ev.xy[k], th, dt, H, W)
+                                                                 : gather_fallback_fused<WRAP>(scot[r], A.rec + off, ev.xy[k], th, dt, H, W);
+                            ax[k] = fmaf(-(float)dt, g.x, ax[k]);
+                            ay[k] = fmaf(-(float)dt, g.y, ay[k]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- fold into the <= 3 x 3 theta elements of this tile: acc[(a, b, component)] += wy[a] wx[b] (ax, ay) -------------------
+        float acc[kFoldSums];
+#pragma unroll
+        for (int q = 0; q < kFoldSums; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kEvK; ++k) {
+            const uint32_t xy = ev.xy[k];                        // a padding sentinel indexes row / column 15 with zero sums
+            const float4 wx4 = *reinterpret_cast<const float4*>(s_wx[xy & 15u]);
+            const float4 wy4 = *reinterpret_cast<const float4*>(s_wy[(xy >> 16) & 15u]);
+            const float wxv[3] = {wx4.x, wx4.y, wx4.z}, wyv[3] = {wy4.x, wy4.y, wy4.z};
+#pragma unroll
+            for (int b = 0; b < kFoldTaps; ++b) {
+                const float ux = wxv[b] * ax[k], uy = wxv[b] * ay[k];
+#pragma unroll
+                for (int a = 0; a < kFoldTaps; ++a) {
+                    acc[(a * kFoldTaps + b) * 2 + 0] = fmaf(wyv[a], ux, acc[(a * kFoldTaps + b) * 2 + 0]);
+                    acc[(a * kFoldTaps + b) * 2 + 1] = fmaf(wyv[a], uy, acc[(a * kFoldTaps + b) * 2 + 1]);
+                }
+            }
+        }
+        // warp-wide reduce-scatter over the 18 sums: 18 -> 9 -> 5 -> 3 -> 2 -> 1 values per lane (20 shuffles, no shared memory, no
+        // barrier); lane l ends up with the warp total of sum q(l) = 9 b4 + 5 b3 + 3 b2 + 2 b1 + b0 when every partial index is in range
+        {
+            const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+            fold_halve<18, 16>(acc, b4);
+            fold_halve<9, 8>(acc, b3);
+            fold_halve<5, 4>(acc, b2);
+            fold_halve<3, 2>(acc, b1);
+            fold_halve<2, 1>(acc, b0);
+            const int i4 = b0 ? 1 : 0, i3 = i4 + (b1 ? 2 : 0), i2 = i3 + (b2 ? 3 : 0), i1 = i2 + (b3 ? 5 : 0), q = i1 + (b4 ? 9 : 0);
+            const bool valid = i3 < 3 && i2 < 5 && i1 < 9;
+            const float sum = acc[0];
+            if (valid && sum != 0.f) {
+                const int ab = q >> 1, a = ab / kFoldTaps, b = ab - a * kFoldTaps;
+                const int i = s_base[0] + a, j = s_base[1] + b;
+                if (i < A.T.h && j < A.T.w) atomicAdd(A.grad + (int64_t)(i * A.T.w + j) * 2 + (q & 1), (double)sum);
+            }
+        }
+        __syncthreads();                             // th_s / swin / dwin / weights are rewritten for the next chunk
+    }
+    if ((int)blockIdx.x >= n_chunks) {               // a CTA without a chunk: still clears its slice
+        pdl_wait();
+        clear_fix_slice(A);
+    }
+    // ---- last CTA: d loss / d alpha_handover = <grad, prev - theta> (losses.py:269) and delivery to the host -------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&A.sc->counters[kFoldTicket], 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n = A.T.h * A.T.w * 2;
+    double da = 0.0;
+    if (A.T.prev != nullptr)
+        for (int e = tid; e < n; e += 256) da += __ldcg(A.grad + e) * (A.T.prev[e] - A.T.theta[e]);
+    da = block_reduce<256>(da, OpSum(), s_red);
+    if (tid == 0) { A.sc->dalpha = da; A.sc->counters[kFoldTicket] = 0u; }
+    if (A.host_out != nullptr) {
+        if (A.host_grad)
+            for (int e = tid; e < n; e += 256) A.host_out[3 + e] = __ldcg(A.grad + e);
+        if (tid == 0) { A.host_out[1] = __ldcg(A.loss_dev); A.host_out[2] = da; }
+        __threadfence_system();
+        __syncthreads();
+        // sequence number of this evaluation, written after everything else is visible to the host: the host entry point polls it
+        // in its own memory instead of calling into the driver
+        if (tid == 0) {
+            const double seq = A.sc->eval_seq + 1.0;
+            A.sc->eval_seq = seq;
+            *reinterpret_cast<volatile double*>(A.host_out) = seq;
+            __threadfence_system();
+        }
+    }
+}
+
+template <bool WRAP, int RB>
+__global__ void __launch_bounds__(256, 4)
+k_backward_fold(const __grid_constant__ BackwardFoldArgs A) {
+    extern __shared__ __align__(16) float dwin_dyn[];
+    backward_fold_body<WRAP, RB>(A, dwin_dyn);
+}
+
+}  // namespace eincm

@@ -449,10 +449,15 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
     const int n_chunks = (int)__ldg(n_chunks_dev);
     const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(win);
     const int Rpad = (R + RB - 1) / RB * RB;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
         EventGroup ev;
         load_chunk_events<true>(ev_xy, ev_t, ch, ev);
+        // programmatic dependent launch: this kernel may have been scheduled while the previous kernel of the stream (the backward pass
+        // of the previous evaluation: it clears the fixed-point images and reads chunk_win) was still running - only the staged
+        // events were read so far
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         tile_theta_range(tile_theta(T, ch.origin, H, W, th_s), sbox);
         const bool active = (ev.xy[0] != kNoEvent);      // groups are padded at their end only
         if (tid == 0) s_sliced = 0;
@@ -636,11 +641,14 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
     const int tid = threadIdx.x, lane = tid & 31;
     const int n_chunks = (int)__ldg(n_chunks_dev);
     const uint32_t th_base = smem_addr(th_s), win_base = smem_addr(dwin);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
         EventGroup ev;
         load_chunk_events<false>(ev_xy, ev_t, ch, ev);
         tile_theta(T, ch.origin, H, W, th_s);
+        // programmatic dependent launch: everything above read the staged events and the flow operand only
+        if (c == (int)blockIdx.x) asm volatile("griddepcontrol.wait;" ::: "memory");
         const bool active = 4u * (unsigned)tid < ch.count;
         float ax[kEvK], ay[kEvK];
 #pragma unroll

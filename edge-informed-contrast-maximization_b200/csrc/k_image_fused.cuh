@@ -87,7 +87,13 @@ constexpr int kMaxCPT = 6;                          // columns per thread (templ
 constexpr int kBandRowsMax = 8;                     // rows of a sub-band (chosen by the host: ImageStatsArgs::band_rows)
 constexpr int kStatsTicket = 6;                     // DevScalars::counters slot of the "last CTA" ticket
 
+// One cell of the image pass as the fused backward fill reads it (k_backward_fold): ONE 16-byte load per window cell instead of
+// three loads from three images.
+struct __align__(16) CellRec { double I; float adj; float e; };   // image value, Scharr adjoint (up to coefA), float32 edge value
+
 struct ImageStatsArgs {
+    CellRec* rec;                   // non-null: write [R][H*W] cell records instead of the dense iwe / adj32 images
+    const float* e32;               // [R][H*W] float32 edge images (only read when rec != null)
     const unsigned long long* fix;  // [R][H*W] fixed-point images of warped events
     const double* edges;            // [R][H*W]
     double* iwe;                    // [R][H*W] float64 images (out)
@@ -159,9 +165,14 @@ k_image_stats(const ImageStatsArgs A) {
     const int row_begin = (int)(((long long)RH * b) / G), row_end = (int)(((long long)RH * (b + 1)) / G);
     const int r_first = row_begin < row_end ? row_begin / H : 0, r_last = row_begin < row_end ? (row_end - 1) / H : -1;
 
+    // programmatic dependent launch: the next kernel of the evaluation may be scheduled as soon as every CTA of this one is resident;
+    // this kernel itself may have been scheduled while the splat was still running - nothing but shared memory and per-window
+    // constants is touched before the wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // zero columns (never written afterwards), identity partials, accumulators of the event backward pass
     for (int k = tid; k < B + 4; k += kBandNT) { bandI[k * Wp] = 0.0; bandI[k * Wp + W + 1] = 0.0; }
     for (int k = tid; k < 2 * (B + 2); k += kBandNT) { gxs[k * Wp] = 0.f; gxs[k * Wp + W + 1] = 0.f; }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int k = tid; k < R * kFPart; k += kBandNT) {
         const int q = k / kFPart, f = k % kFPart;
         A.part[(q * G + b) * kFPart + f] = (f == 4) ? INFINITY : ((f == 6) ? -INFINITY : 0.0);
@@ -188,6 +199,8 @@ k_image_stats(const ImageStatsArgs A) {
         const double* Er = A.edges + r * HW;
         double* Ir = A.iwe + r * HW;
         float* Ar = A.adj32 + r * HW;
+        CellRec* Rr = A.rec != nullptr ? A.rec + r * HW : nullptr;
+        const float* E32r = A.e32 + r * HW;
         FusedAcc acc;
         acc.init();
         int cnt_mn = 0, cnt_mx = 0;                   // tie counts of the running min / max (integers: branch-free update)
@@ -248,7 +261,7 @@ k_image_stats(const ImageStatsArgs A) {
                         gxr[x] = (float)gx; gyr[x] = (float)gy;
                         if (own) {
                             const double I = mid[x];
-                            Ir[q * W + x] = I;
+                            if (Rr != nullptr) Rr[q * W + x].I = I; else Ir[q * W + x] = I;
                             acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += er[c] * I;
                             cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
                             cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
@@ -265,7 +278,11 @@ k_image_stats(const ImageStatsArgs A) {
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const int x = tid + c * kBandNT;
-                    if (x < W) Ar[y * W + x] = scharr_adjoint_rows_f32(xm - Wp + x, xm + x, xm + Wp + x, ym - Wp + x, ym + Wp + x);
+                    if (x < W) {
+                        const float a = scharr_adjoint_rows_f32(xm - Wp + x, xm + x, xm + Wp + x, ym - Wp + x, ym + Wp + x);
+                        if (Rr != nullptr) *reinterpret_cast<float2*>(&Rr[y * W + x].adj) = make_float2(a, __ldg(E32r + y * W + x));
+                        else Ar[y * W + x] = a;
+                    }
                 }
             }
         }
@@ -318,7 +335,22 @@ k_image_stats(const ImageStatsArgs A) {
         }
         __syncthreads();
         if (tid == 0) {
-            for (int q = 0; q < R; ++q) { A.sc->ref[q] = S.st[q]; A.sc->coefA[q] = S.coefA[q]; A.sc->coefB[q] = S.coefB[q]; A.sc->coefD[q] = 0.0; }
+            for (int q = 0; q < R; ++q) {
+                A.sc->ref[q] = S.st[q]; A.sc->coefA[q] = S.coefA[q]; A.sc->coefB[q] = S.coefB[q]; A.sc->coefD[q] = 0.0;
+                // coefficients of the per-cell cotangent for the fused backward fill (same terms as k_image_grad, scaled by 1 / 2 pi)
+                const Stats& st = S.st[q];
+                const double iD = 1.0 / st.D;
+                const double g_M = -st.s2 / (st.D * st.D);
+                const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
+                CotCoef c;
+                c.cA = S.coefA[q] * kInv2Pi;
+                c.a1 = S.coefB[q] * iD * kInv2Pi;
+                c.a2 = S.coefB[q] * iD * iD * kInv2Pi;
+                c.a3 = c.a2 * st.mn;
+                c.mn = st.mn; c.mx = st.mx;
+                c.tm = g_m / st.cnt_min * kInv2Pi; c.tM = g_M / st.cnt_max * kInv2Pi;
+                A.sc->cot[q] = c;
+            }
             // final loss (reference src/eincm/losses.py:171-193)
             double s_corr = 0.0, s_con = 0.0;
             for (int q = 0; q < R; ++q) {
@@ -355,6 +387,9 @@ struct ImageGradArgs {
 
 __global__ void __launch_bounds__(256)
 k_image_grad(const ImageGradArgs A) {
+    // programmatic dependent launch (no-ops when launched plainly): let the next kernel be scheduled, wait for the image statistics
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __shared__ double s_mn[kCoopMaxRefs], s_mx[kCoopMaxRefs], s_iD[kCoopMaxRefs], s_cA[kCoopMaxRefs], s_cB[kCoopMaxRefs], s_tm[kCoopMaxRefs], s_tM[kCoopMaxRefs];
     if (threadIdx.x < A.R && A.want_grad) {
         const Stats st = A.sc->ref[threadIdx.x];
@@ -399,13 +434,25 @@ k_image_grad(const ImageGradArgs A) {
     }
 }
 
+// cell records -> dense float64 image + float32 adjoint (debug taps and the unfused d loss / d IWE kernel, on demand)
+__global__ void k_unpack_records(const CellRec* __restrict__ rec, int64_t n, double* __restrict__ iwe, float* __restrict__ adj32) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const CellRec c = rec[i];
+        iwe[i] = c.I; adj32[i] = c.adj;
+    }
+}
+
 // per-window: sum E_r and sum E_r^2 (deterministic single-CTA-per-reference reduction; once per window)
 __global__ void __launch_bounds__(1024)
-k_edge_sums(const double* __restrict__ edges, int64_t HW, DevScalars* sc) {
+k_edge_sums(const double* __restrict__ edges, int64_t HW, DevScalars* sc, float* __restrict__ e32 /* float32 copy for the fused backward fill, or null */) {
     __shared__ double sh[32];
     const int r = blockIdx.x;
     double s = 0.0, s2 = 0.0;
-    for (int64_t p = threadIdx.x; p < HW; p += blockDim.x) { const double e = edges[r * HW + p]; s += e; s2 += e * e; }
+    for (int64_t p = threadIdx.x; p < HW; p += blockDim.x) {
+        const double e = edges[r * HW + p];
+        s += e; s2 += e * e;
+        if (e32 != nullptr) e32[r * HW + p] = (float)e;
+    }
     s = block_reduce<1024>(s, OpSum(), sh);
     s2 = block_reduce<1024>(s2, OpSum(), sh);
     if (threadIdx.x == 0) { sc->sumE[r] = s; sc->sumE2[r] = s2; }

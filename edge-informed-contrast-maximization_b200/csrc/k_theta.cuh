@@ -82,7 +82,10 @@ __global__ void __launch_bounds__(kTgWarps * 32)
 k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
              double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, AxisTaps ty, AxisTaps tx,
              const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */,
-             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad, double host_seq) {
+             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad) {
+    // programmatic dependent launch (no-ops when launched plainly)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kTgWarps + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -153,15 +156,20 @@ k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, Dev
     if (lane == 0) { sc->dalpha = da; sc->counters[5] = 0u; }
     // synchronous host entry points: the last warp delivers [gradient | loss | d/d alpha] straight into mapped pinned host
     // memory (no device -> host copy operation after the kernel)
-    if (host_out != nullptr) {
+    if (host_out != nullptr) {                  // layout: [sequence | loss | d alpha | gradient ...] (as k_backward_fold)
         const int n = host_grad ? h * w * 2 : 0;
-        for (int e = lane; e < n; e += 32) host_out[e] = __ldcg(grad + e);
-        if (lane == 0) { host_out[n] = __ldcg(loss_dev); host_out[n + 1] = da; }
+        for (int e = lane; e < n; e += 32) host_out[3 + e] = __ldcg(grad + e);
+        if (lane == 0) { host_out[1] = __ldcg(loss_dev); host_out[2] = da; }
         __threadfence_system();
         __syncwarp();
         // sequence number of this evaluation, written after everything else is visible to the host: the host entry point
         // polls it in its own memory instead of calling into the driver (no lock shared with threads that are launching)
-        if (lane == 0) { *reinterpret_cast<volatile double*>(host_out + n + 2) = host_seq; __threadfence_system(); }
+        if (lane == 0) {
+            const double seq = sc->eval_seq + 1.0;
+            sc->eval_seq = seq;
+            *reinterpret_cast<volatile double*>(host_out) = seq;
+            __threadfence_system();
+        }
     }
 }
 
