@@ -1,0 +1,297 @@
+// Batched evaluation (included by eincm_plan.cu inside extern "C"): B staged windows, ONE launch per kernel of the evaluation
+// (blockIdx.y = window) instead of B x 5 launches on B streams.  BASELINE.json configs[2] / [3] ("batch of windows on 1 x B200",
+// "windows sharded"): independent windows - different sequences, or windows evaluated without handover - have no data dependence, so
+// the small image-space kernels, which are latency-bound for one window, fill the GPU, and MVSEC-sized windows (30 k events, 86 k
+// pixels), which are launch-bound one at a time, become throughput-bound.  Same kernels bodies as the single-window path (the argument
+// record of the CTA's window is read from device memory), same results bit for bit.
+
+struct eincm_batch {
+    std::vector<eincm_plan*> plans;
+    int device = 0, H = 0, W = 0, R = 0;
+    bool wrap = true;
+    // argument records: one device blob [splat | stats | image grad | backward | theta grad] x B, two pinned host copies (alternating)
+    char* d_blob = nullptr;
+    char* h_blob[2] = {nullptr, nullptr};
+    cudaEvent_t h_free[2] = {nullptr, nullptr};     // recorded behind the upload of h_blob[i]
+    int next_blob = 0;
+    size_t off_splat = 0, off_stats = 0, off_igrad = 0, off_bwd = 0, off_tgrad = 0, blob_bytes = 0;
+    std::vector<uintptr_t> key;                     // operands of the last upload (unchanged operands are not uploaded again)
+    // host-operand form: staging for theta / gradient / loss of every window
+    double *d_theta = nullptr, *d_grad = nullptr, *d_loss = nullptr, *h_stage = nullptr;
+    size_t stage_n = 0;                             // doubles per window the staging buffers are sized for
+    int64_t launch_count = 0;
+    std::string error;
+};
+
+namespace {
+int bfail(eincm_batch* b, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (b) b->error = buf;
+    return code;
+}
+#define BCU(call)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return bfail(batch, e_ == cudaErrorMemoryAllocation ? EINCM_ENOMEM : EINCM_ECUDA, "%s: %s", #call, \
+                         cudaGetErrorString(e_));                                                              \
+    } while (0)
+}  // namespace
+
+const char* eincm_batch_last_error(const eincm_batch* batch) { return batch ? batch->error.c_str() : ""; }
+int64_t eincm_batch_launch_count(const eincm_batch* batch) { return batch ? batch->launch_count : 0; }
+
+void eincm_batch_destroy(eincm_batch* batch) {
+    if (!batch) return;
+    cudaSetDevice(batch->device);
+    if (batch->d_blob) cudaFree(batch->d_blob);
+    for (int i = 0; i < 2; ++i) {
+        if (batch->h_blob[i]) cudaFreeHost(batch->h_blob[i]);
+        if (batch->h_free[i]) cudaEventDestroy(batch->h_free[i]);
+    }
+    if (batch->d_theta) cudaFree(batch->d_theta);
+    if (batch->d_grad) cudaFree(batch->d_grad);
+    if (batch->d_loss) cudaFree(batch->d_loss);
+    if (batch->h_stage) cudaFreeHost(batch->h_stage);
+    delete batch;
+}
+
+int eincm_batch_create(eincm_batch** out, eincm_plan* const* plans, int n_plans) {
+    if (!out) return EINCM_EINVAL;
+    *out = nullptr;
+    if (!plans || n_plans < 1 || n_plans > 65535 || !plans[0]) return EINCM_EINVAL;
+    eincm_batch* batch = new (std::nothrow) eincm_batch();
+    if (!batch) return EINCM_ENOMEM;
+    eincm_plan* p0 = plans[0];
+    batch->device = p0->device; batch->H = p0->H; batch->W = p0->W; batch->wrap = p0->wrap;
+    auto bad = [&](int code, const char* msg) { p0->error = msg; delete batch; return code; };
+    for (int k = 0; k < n_plans; ++k) {
+        eincm_plan* p = plans[k];
+        if (!p) return bad(EINCM_EINVAL, "a plan of the batch is NULL");
+        if (p->device != p0->device || p->H != p0->H || p->W != p0->W || p->wrap != p0->wrap)
+            return bad(EINCM_EINVAL, "all plans of a batch share the device, the sensor size and the index rule");
+        if (p->exact || (p->flags & EINCM_FLAG_EVENT_SPLIT) || !p->coop_ok)
+            return bad(EINCM_EUNSUPPORTED, "batched evaluation runs the default path only (no EXACT_F64, no event split, W <= 1536)");
+        for (int q = 0; q < k; ++q) if (plans[q] == p) return bad(EINCM_EINVAL, "a plan appears twice in the batch");
+        batch->plans.push_back(p);
+    }
+    if (cudaSetDevice(batch->device) != cudaSuccess) return bad(EINCM_ECUDA, "cudaSetDevice failed");
+    const size_t B = (size_t)n_plans;
+    auto align = [](size_t v) { return (v + 255) / 256 * 256; };
+    batch->off_splat = 0;
+    batch->off_stats = align(batch->off_splat + B * sizeof(SplatArgs));
+    batch->off_igrad = align(batch->off_stats + B * sizeof(ImageStatsArgs));
+    batch->off_bwd = align(batch->off_igrad + B * sizeof(ImageGradArgs));
+    batch->off_tgrad = align(batch->off_bwd + B * sizeof(BackwardTileArgs));
+    batch->blob_bytes = align(batch->off_tgrad + B * sizeof(ThetaGradArgs));
+    cudaError_t e = cudaMalloc((void**)&batch->d_blob, batch->blob_bytes);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMallocHost((void**)&batch->h_blob[i], batch->blob_bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&batch->h_free[i], cudaEventDisableTiming);
+    }
+    // shared-memory opt-in of the batched kernels (the single-window instantiations were opted in by eincm_plan_create)
+    auto opt_in = [&](const void* fn, int bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    };
+#define OPT_IN_B(RB) opt_in((const void*)k_splat_tile_b<true, RB>, RB * kWinCap * 4); opt_in((const void*)k_splat_tile_b<false, RB>, RB * kWinCap * 4); \
+                     opt_in((const void*)k_backward_tile_b<true, RB>, RB * kWinCap * 4); opt_in((const void*)k_backward_tile_b<false, RB>, RB * kWinCap * 4)
+    OPT_IN_B(1); OPT_IN_B(2); OPT_IN_B(3); OPT_IN_B(4);
+#undef OPT_IN_B
+    opt_in((const void*)k_image_stats_b, 0);
+    if (e != cudaSuccess) {
+        p0->error = std::string("eincm_batch_create: ") + cudaGetErrorString(e);
+        eincm_batch_destroy(batch);
+        return e == cudaErrorMemoryAllocation ? EINCM_ENOMEM : EINCM_ECUDA;
+    }
+    *out = batch;
+    return EINCM_OK;
+}
+
+// device operands: thetas[k] [h][w][2], loss_out[k] (1 float64), grad_out[k] [h][w][2] (all device pointers; the arrays themselves are
+// host arrays).  Asynchronous on cuda_stream.
+int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, int h, int w, const eincm_hparams* hp,
+                               double* const* loss_out, double* const* grad_out, void* cuda_stream) {
+    if (!batch) return EINCM_EINVAL;
+    if (!thetas || !hp || !loss_out || !grad_out) return bfail(batch, EINCM_EINVAL, "NULL operand");
+    if (hp->method != EINCM_METHOD_BILINEAR) return bfail(batch, EINCM_EUNSUPPORTED, "only the bilinear resize is implemented");
+    if (hp->delta != 0.0 || (hp->gamma != 0.0 && hp->cur_pyr_lvl <= 0))
+        return bfail(batch, EINCM_EUNSUPPORTED, "batched evaluation: delta == 0 and no TV term (gamma == 0 or cur_pyr_lvl > 0); use the per-plan calls");
+    const int H = batch->H, W = batch->W, B = (int)batch->plans.size();
+    const int64_t HW = (int64_t)H * W;
+    if (h < 1 || w < 1 || h > H || w > W) return bfail(batch, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    const bool dense = (h == H && w == W);                  // identity resize: the dense field gradient IS the gradient
+    if (!dense && h * w > kGatherMaxTiles)
+        return bfail(batch, EINCM_EUNSUPPORTED, "batched evaluation: theta is a tile field of <= %d elements or the dense H x W field", kGatherMaxTiles);
+    BCU(cudaSetDevice(batch->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    eincm_plan* p0 = batch->plans[0];
+    const int R = p0->R;
+    int max_chunks = 1;
+    for (int k = 0; k < B; ++k) {
+        eincm_plan* p = batch->plans[k];
+        if (!p->window_set || !p->window_final) return bfail(batch, EINCM_ESTATE, "plan %d: no staged window", k);
+        if (p->R != R) return bfail(batch, EINCM_EINVAL, "all windows of a batch have the same number of reference times (%d vs %d)", p->R, R);
+        if (!thetas[k] || !loss_out[k] || !grad_out[k]) return bfail(batch, EINCM_EINVAL, "operand %d is NULL", k);
+        max_chunks = std::max(max_chunks, p->n_chunks);
+    }
+    AxisTaps ty, tx;
+    {
+        eincm_plan* plan = p0;                              // the taps are a function of (h, H) / (w, W) only: built on the first plan
+        int rc = build_axis_taps(plan, h, H, &ty);
+        if (!rc) rc = build_axis_taps(plan, w, W, &tx);
+        if (rc) return bfail(batch, rc, "%s", plan->error.c_str());
+    }
+    const int max_ny = std::min(H, 2 * ((H + h - 1) / h) + 2), max_nx = std::min(W, 2 * ((W + w - 1) / w) + 2);
+    const int SX = (max_nx + kTgCols - 1) / kTgCols, SY = (max_ny + kTgRows - 1) / kTgRows;
+    const int n_items = h * w * SY * SX;
+    // ---- argument records (uploaded only when an operand changed since the last call) ---------------------------------------------
+    std::vector<uintptr_t> key;
+    key.reserve(3 * (size_t)B + 12);
+    for (int k = 0; k < B; ++k) { key.push_back((uintptr_t)thetas[k]); key.push_back((uintptr_t)loss_out[k]); key.push_back((uintptr_t)grad_out[k]); }
+    for (int k = 0; k < B; ++k) { key.push_back((uintptr_t)batch->plans[k]->n_chunks); key.push_back((uintptr_t)batch->plans[k]->ev_t); }
+    key.push_back((uintptr_t)h); key.push_back((uintptr_t)w); key.push_back((uintptr_t)R);
+    { uint64_t a, b2; std::memcpy(&a, &hp->alpha, 8); std::memcpy(&b2, &hp->beta, 8); key.push_back((uintptr_t)a); key.push_back((uintptr_t)b2); }
+    for (int k = 0; k < B; ++k) for (int r = 0; r < R; ++r) { uint64_t a; std::memcpy(&a, &batch->plans[k]->tref.t[r], 8); key.push_back((uintptr_t)a); }
+    if (key != batch->key) {
+        const int hb = batch->next_blob;
+        batch->next_blob ^= 1;
+        BCU(cudaEventSynchronize(batch->h_free[hb]));       // the previous upload from this host copy has finished
+        char* hbuf = batch->h_blob[hb];
+        SplatArgs* sa = (SplatArgs*)(hbuf + batch->off_splat);
+        ImageStatsArgs* ia = (ImageStatsArgs*)(hbuf + batch->off_stats);
+        ImageGradArgs* ga = (ImageGradArgs*)(hbuf + batch->off_igrad);
+        BackwardTileArgs* ba = (BackwardTileArgs*)(hbuf + batch->off_bwd);
+        ThetaGradArgs* ta = (ThetaGradArgs*)(hbuf + batch->off_tgrad);
+        std::memset(hbuf, 0, batch->blob_bytes);
+        for (int k = 0; k < B; ++k) {
+            eincm_plan* p = batch->plans[k];
+            const ThetaSrc T{thetas[k], nullptr, 0.0, h, w, ty, tx};
+            double* Gk = dense ? grad_out[k] : p->G;
+            SplatArgs& s = sa[k];
+            s.ev_xy = p->ev_xy; s.ev_t = p->ev_t; s.chunks = p->chunks; s.chunk_tr = p->chunk_tr; s.n_chunks_dev = p->totals + 1;
+            s.T = T; s.H = H; s.W = W; s.R = R; s.tref = p->tref; s.dst.n = 1; s.dst.p[0] = p->iwe_fix; s.chunk_win = p->chunk_win;
+            ImageStatsArgs& i = ia[k];
+            i.rec = nullptr; i.e32 = p->e32; i.fix = p->iwe_fix; i.edges = p->edges; i.iwe = p->iwe; i.adj32 = p->adj32;
+            i.part = p->part; i.sc = p->sc; i.loss_out = loss_out[k];
+            i.zero_buf = Gk; i.n_zero = (int)(HW * 2);
+            i.zero_buf2 = dense ? nullptr : grad_out[k]; i.n_zero2 = dense ? 0 : h * w * 2;
+            i.H = H; i.W = W; i.R = R; i.alpha = hp->alpha; i.beta = hp->beta; i.gamma = hp->gamma; i.use_tv = 0;
+            ImageGradArgs& g = ga[k];
+            g.fix = p->iwe_fix; g.edges = p->edges; g.iwe = p->iwe; g.adj32 = p->adj32; g.sc = p->sc; g.dldi = nullptr; g.dldi32 = p->dldi32;
+            g.HW = (int)HW; g.R = R; g.want_grad = 1;
+            BackwardTileArgs& b = ba[k];
+            b.ev_xy = p->ev_xy; b.ev_t = p->ev_t; b.chunks = p->chunks; b.n_chunks_dev = p->totals + 1; b.T = T; b.H = H; b.W = W; b.R = R;
+            b.tref = p->tref; b.dldi32 = p->dldi32; b.chunk_win = p->chunk_win; b.G = Gk;
+            ThetaGradArgs& t = ta[k];
+            t.G = (const double2*)p->G; t.sc = p->sc; t.h = h; t.w = w; t.H = H; t.W = W; t.SY = SY; t.SX = SX; t.n_items = n_items; t.host_grad = 0;
+            t.ty = ty; t.tx = tx; t.prev = nullptr; t.theta = thetas[k]; t.grad = grad_out[k]; t.loss_dev = loss_out[k]; t.host_out = nullptr;
+        }
+        BCU(cudaMemcpyAsync(batch->d_blob, hbuf, batch->blob_bytes, cudaMemcpyHostToDevice, st));
+        BCU(cudaEventRecord(batch->h_free[hb], st));
+        batch->key.swap(key);
+    }
+    // the fixed-point images must be clean (a plan that was last evaluated through a path that leaves them dirty)
+    for (int k = 0; k < B; ++k) {
+        eincm_plan* p = batch->plans[k];
+        if (!p->fix_clean) BCU(cudaMemsetAsync(p->iwe_fix, 0, (size_t)p->max_refs * p->HW * sizeof(unsigned long long), st));
+        if (p->window_ev_valid && st != p->window_stream) BCU(cudaStreamWaitEvent(st, p->window_ev, 0));
+    }
+    // ---- five launches for the whole batch ----------------------------------------------------------------------------------------
+    const SplatArgs* d_sa = (const SplatArgs*)(batch->d_blob + batch->off_splat);
+    const ImageStatsArgs* d_ia = (const ImageStatsArgs*)(batch->d_blob + batch->off_stats);
+    const ImageGradArgs* d_ga = (const ImageGradArgs*)(batch->d_blob + batch->off_igrad);
+    const BackwardTileArgs* d_ba = (const BackwardTileArgs*)(batch->d_blob + batch->off_bwd);
+    const ThetaGradArgs* d_ta = (const ThetaGradArgs*)(batch->d_blob + batch->off_tgrad);
+    const int rb = std::min(R, kMaxRB);
+    const dim3 grid_ev(max_chunks, B);
+    cudaError_t le = cudaSuccess;
+#define LB(WR, RBV) le = launch_pdl(k_splat_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(uint32_t), st, d_sa)
+    if (batch->wrap) { switch (rb) { case 1: LB(true, 1); break; case 2: LB(true, 2); break; case 3: LB(true, 3); break; default: LB(true, 4); } }
+    else { switch (rb) { case 1: LB(false, 1); break; case 2: LB(false, 2); break; case 3: LB(false, 3); break; default: LB(false, 4); } }
+#undef LB
+    if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_splat_tile_b: %s", cudaGetErrorString(le));
+    le = launch_pdl(k_image_stats_b, dim3((image_stats_items(H, W, R) + kS2Warps - 1) / kS2Warps, B), dim3(kS2NT), 0, st, d_ia);
+    if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_image_stats_b: %s", cudaGetErrorString(le));
+    {
+        const int per = std::max(8, std::min((int)((HW + 1023) / 1024), (p0->sm_count * 8 + B - 1) / B));
+        le = launch_pdl(k_image_grad_b, dim3(per, B), dim3(256), 0, st, d_ga);
+        if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_image_grad_b: %s", cudaGetErrorString(le));
+    }
+#define LB(WR, RBV) le = launch_pdl(k_backward_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(float), st, d_ba)
+    if (batch->wrap) { switch (rb) { case 1: LB(true, 1); break; case 2: LB(true, 2); break; case 3: LB(true, 3); break; default: LB(true, 4); } }
+    else { switch (rb) { case 1: LB(false, 1); break; case 2: LB(false, 2); break; case 3: LB(false, 3); break; default: LB(false, 4); } }
+#undef LB
+    if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_backward_tile_b: %s", cudaGetErrorString(le));
+    batch->launch_count += 4;
+    if (!dense) {
+        le = launch_pdl(k_theta_grad_b, dim3((n_items + kTgWarps - 1) / kTgWarps, B), dim3(kTgWarps * 32), 0, st, d_ta);
+        if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_theta_grad_b: %s", cudaGetErrorString(le));
+        batch->launch_count += 1;
+    }
+    // per-plan state as after a single-window evaluation (read-outs and debug taps keep working)
+    for (int k = 0; k < B; ++k) {
+        eincm_plan* p = batch->plans[k];
+        p->tsrc = ThetaSrc{thetas[k], nullptr, 0.0, h, w, ty, tx};
+        p->theta_full_valid = false; p->fused_pending = false; p->rec_pending = false; p->fix_clean = true; p->dldi_stale = true;
+        p->forward_done = true; p->last_h = h; p->last_w = w; p->last_theta = thetas[k]; p->last_prev = nullptr; p->last_a_ho = 0.0;
+        p->host_delivered = false;
+    }
+    return EINCM_OK;
+}
+
+// host operands (synchronous): thetas_host[k] -> losses_out_host[k], grads_out_host[k] ([h][w][2] each; grads_out_host may be NULL:
+// values only are copied back, the gradient is still computed).  One host -> device copy, five launches, one device -> host copy.
+int eincm_batch_value_and_grad_host(eincm_batch* batch, const double* const* thetas_host, int h, int w, const eincm_hparams* hp,
+                                    double* losses_out_host, double* const* grads_out_host, void* cuda_stream) {
+    if (!batch) return EINCM_EINVAL;
+    if (!thetas_host || !losses_out_host) return bfail(batch, EINCM_EINVAL, "NULL operand");
+    if (h < 1 || w < 1 || h > batch->H || w > batch->W) return bfail(batch, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    BCU(cudaSetDevice(batch->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t B = batch->plans.size(), n = (size_t)h * w * 2;
+    if (n > batch->stage_n) {
+        BCU(cudaStreamSynchronize(st));
+        if (batch->d_theta) cudaFree(batch->d_theta);
+        if (batch->d_grad) cudaFree(batch->d_grad);
+        if (batch->d_loss) cudaFree(batch->d_loss);
+        if (batch->h_stage) cudaFreeHost(batch->h_stage);
+        batch->d_theta = batch->d_grad = batch->d_loss = batch->h_stage = nullptr;
+        batch->stage_n = 0;
+        BCU(cudaMalloc((void**)&batch->d_theta, B * n * sizeof(double)));
+        BCU(cudaMalloc((void**)&batch->d_grad, B * n * sizeof(double)));
+        BCU(cudaMalloc((void**)&batch->d_loss, B * sizeof(double)));
+        BCU(cudaMallocHost((void**)&batch->h_stage, (B * n + B) * sizeof(double)));
+        batch->stage_n = n;
+        batch->key.clear();
+    }
+    const size_t stride = batch->stage_n;
+    std::vector<const double*> th(B);
+    std::vector<double*> lo(B), gr(B);
+    for (size_t k = 0; k < B; ++k) {
+        if (!thetas_host[k]) return bfail(batch, EINCM_EINVAL, "theta %d is NULL", (int)k);
+        std::memcpy(batch->h_stage + k * n, thetas_host[k], n * sizeof(double));
+        th[k] = batch->d_theta + k * stride; lo[k] = batch->d_loss + k; gr[k] = batch->d_grad + k * stride;
+    }
+    // thetas are packed with stride n on the host and scattered to stride `stride` on the device (equal unless a larger shape was used before)
+    if (stride == n) BCU(cudaMemcpyAsync(batch->d_theta, batch->h_stage, B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    else BCU(cudaMemcpy2DAsync(batch->d_theta, stride * sizeof(double), batch->h_stage, n * sizeof(double), n * sizeof(double), B, cudaMemcpyHostToDevice, st));
+    const int rc = eincm_batch_value_and_grad(batch, th.data(), h, w, hp, lo.data(), gr.data(), st);
+    if (rc) return rc;
+    double* h_loss = batch->h_stage + B * n;
+    BCU(cudaMemcpyAsync(h_loss, batch->d_loss, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grads_out_host) {
+        if (stride == n) BCU(cudaMemcpyAsync(batch->h_stage, batch->d_grad, B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else BCU(cudaMemcpy2DAsync(batch->h_stage, n * sizeof(double), batch->d_grad, stride * sizeof(double), n * sizeof(double), B, cudaMemcpyDeviceToHost, st));
+    }
+    BCU(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < B; ++k) {
+        losses_out_host[k] = h_loss[k];
+        if (grads_out_host && grads_out_host[k]) std::memcpy(grads_out_host[k], batch->h_stage + k * n, n * sizeof(double));
+    }
+    return EINCM_OK;
+}

@@ -78,8 +78,6 @@ struct eincm_plan {
     double* h_mapped_dev = nullptr;   // device alias of h_pinned (cudaHostAllocMapped)
     bool dldi_stale = false;      // plan->dldi does not hold the last evaluation's d loss / d IWE yet (fused path: built on demand)
     bool fix_clean = false;       // every cell of iwe_fix is zero (the cooperative image pass clears what it reads)
-    struct CoopCfg { int ctas = 0, band_rows = 0; };
-    CoopCfg coop_cfg[EINCM_MAX_REFS + 1];   // grid / sub-band height of k_image_stats per number of reference images (lazy)
     bool coop_ok = false;         // the sensor is narrow enough for the row-band cooperative image pass
     bool fused_pending = false;   // the last forward left the fixed-point images for the fused image pass (no float64 copy yet)
     RefTimes tref{};
@@ -252,18 +250,6 @@ int build_axis_taps(eincm_plan* plan, int n_in, int n_out, AxisTaps* out) {
 
 __global__ void k_set_weights(DevScalars* sc, RefTimes w, int R) {
     if (threadIdx.x < EINCM_MAX_REFS) sc->weights[threadIdx.x] = threadIdx.x < R ? w.t[threadIdx.x] : 0.0;
-}
-
-// instantiation of the row-band image statistics kernel for a sensor width (columns per thread is a template parameter)
-const void* image_pass_kernel(int W) {
-    switch ((W + kBandNT - 1) / kBandNT) {
-        case 1: return (const void*)k_image_stats<1>;
-        case 2: return (const void*)k_image_stats<2>;
-        case 3: return (const void*)k_image_stats<3>;
-        case 4: return (const void*)k_image_stats<4>;
-        case 5: return (const void*)k_image_stats<5>;
-        default: return (const void*)k_image_stats<6>;
-    }
 }
 
 // dynamic shared memory of k_backward_fold: RB windows, reused as the [18][256] float reduction buffer of the theta fold
@@ -455,28 +441,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         }
         ia.H = H; ia.W = W; ia.R = R;
         ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0;
-        // grid and sub-band height: two CTAs per SM, each ideally holding its whole row band in shared memory (one sub-band)
-        eincm_plan::CoopCfg& cc = plan->coop_cfg[R];
-        if (cc.ctas == 0) {
-            const int k_per_sm = 2;
-            const int target = std::max(1, std::min(plan->sm_count * k_per_sm, (R * H + 1) / 2));          // >= 2 rows per CTA
-            int B = std::min(kBandRowsMax, std::max(2, (R * H + target - 1) / target));
-            int per_sm = 0;
-            for (;; --B) {
-                cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_pass_kernel(W), kBandNT, image_pass_smem_bytes(W, B));
-                if (eo != cudaSuccess) return fail(plan, EINCM_ECUDA, "occupancy query of the image pass: %s", cudaGetErrorString(eo));
-                if (per_sm >= k_per_sm || B <= 2) break;
-            }
-            if (per_sm < 1) return fail(plan, EINCM_ECUDA, "the image statistics kernel does not fit this device for W = %d", W);
-            cc.band_rows = B;
-            cc.ctas = target;
-        }
-        ia.band_rows = cc.band_rows;
-        {
-            typedef void (*stats_fn)(const ImageStatsArgs);
-            stats_fn fn = (stats_fn)image_pass_kernel(W);
-            LAUNCH("k_image_stats", launch_pdl(fn, dim3(cc.ctas), dim3(kBandNT), image_pass_smem_bytes(W, cc.band_rows), st, ia));
-        }
+        LAUNCH("k_image_stats", launch_pdl(k_image_stats, dim3((image_stats_items(H, W, R) + kS2Warps - 1) / kS2Warps), dim3(kS2NT), 0, st, ia));
         if (fold && !plan->fused_fill) {
             // d loss / d IWE materialised by its own (pointwise) kernel, which also clears the fixed-point images
             ImageGradArgs ga{};
@@ -656,8 +621,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         max_carveout((const void*)k_image_grad);
         max_carveout((const void*)k_theta_grad<false>); max_carveout((const void*)k_theta_grad<true>);
         max_carveout((const void*)k_theta_grad_scatter); max_carveout((const void*)k_tv); max_carveout((const void*)k_upsample_theta);
-        max_carveout((const void*)k_image_stats<1>); max_carveout((const void*)k_image_stats<2>); max_carveout((const void*)k_image_stats<3>);
-        max_carveout((const void*)k_image_stats<4>); max_carveout((const void*)k_image_stats<5>); max_carveout((const void*)k_image_stats<6>);
+        max_carveout((const void*)k_image_stats);
         if (ea != cudaSuccess) return fail(nullptr, EINCM_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
     }
     plan = new (std::nothrow) eincm_plan();
@@ -666,17 +630,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     plan->max_refs = max_refs; plan->flags = flags; plan->wrap = !(flags & EINCM_FLAG_NO_WRAP_NEGATIVE);
     plan->exact = (flags & EINCM_FLAG_EXACT_F64) != 0;
     plan->sm_count = prop.multiProcessorCount;
-    {
-        // the row-band image kernel keeps whole rows in shared memory; very wide sensors use the unfused image kernels
-        const size_t smem_img = image_pass_smem_bytes(W, 2);
-        plan->coop_ok = W <= kMaxCPT * kBandNT && smem_img <= (size_t)prop.sharedMemPerBlockOptin;
-        if (plan->coop_ok) {
-            if ((e = cudaFuncSetAttribute(image_pass_kernel(W), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess) {
-                delete plan;
-                return fail(nullptr, EINCM_ECUDA, "shared-memory opt-in of the image statistics kernel failed (%s)", cudaGetErrorString(e));
-            }
-        }
-    }
+    plan->coop_ok = true;            // the streaming image pass has no limit on the sensor width
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
     plan->n_tiles = plan->tiles_x * ((H + kSortTile - 1) / kSortTile);
     plan->n_keys = plan->n_tiles * kKeysPerTile;
@@ -684,7 +638,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     plan->chunk_cap = (int)(max_events / kChunkEvents) + plan->n_tiles + 1;
     const size_t HW = (size_t)plan->HW, NE = (size_t)max_events, RR = (size_t)max_refs;
     const int nbT = img_tiles_x(plan) * img_tiles_y(plan);
-    plan->part_doubles = 10 * max_refs * std::max(nbT, plan->sm_count * 4) + 4096;
+    plan->part_doubles = std::max(10 * max_refs * std::max(nbT, plan->sm_count * 4), image_stats_items(H, W, max_refs) * kFPart + 2 * nbT) + 4096;
     auto body = [&]() -> int {
         // sorted event stream: every tile segment padded to whole groups of kEvK events (k_prep.cuh)
         const size_t NP = (size_t)plan->stream_cap;
@@ -1560,6 +1514,7 @@ int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int
 }
 
 #include "eincm_edges.inl"
+#include "eincm_batch.inl"
 #include "eincm_ingest.inl"
 
 }  // extern "C"

@@ -432,12 +432,11 @@ __device__ __noinline__ float2 gather_fallback(const float* __restrict__ img, ui
 // window and is remembered in a bit mask; the rare misses are replayed through the out-of-line fallback afterwards.  Without
 // branches the compiler interleaves the independent (event, reference time) pairs of a thread.
 template <bool WRAP, int RB>
-__global__ void __launch_bounds__(256, 4)
-k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks,
+__device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks,
              const float2* __restrict__ chunk_tr, const unsigned int* __restrict__ n_chunks_dev,
-             const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
-             const __grid_constant__ FixDst dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
-    extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
+             const ThetaSrc& T, int H, int W, int R, const RefTimes& tref,
+             const FixDst& dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */,
+             uint32_t* win /* [RB][kWinCap] dynamic shared memory */) {
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ int sbox[8][4];
     __shared__ Window swin[RB];
@@ -618,6 +617,41 @@ k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t
     }
 }
 
+template <bool WRAP, int RB>
+__global__ void __launch_bounds__(256, 4)
+k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks,
+             const float2* __restrict__ chunk_tr, const unsigned int* __restrict__ n_chunks_dev,
+             const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
+             const __grid_constant__ FixDst dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
+    extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
+    splat_tile_body<WRAP, RB>(ev_xy, ev_t, chunks, chunk_tr, n_chunks_dev, T, H, W, R, tref, dst, chunk_win, win);
+}
+
+// ---- batched form: one launch for B windows (blockIdx.y = window), one argument record per window in device memory ------------------
+// BASELINE.json configs[2] / [3]: "batch of windows on 1 x B200".  The record of the CTA's window is copied into shared memory first.
+template <typename Args>
+__device__ __forceinline__ void load_args(Args& dst, const Args* __restrict__ src) {
+    static_assert(sizeof(Args) % 4 == 0, "argument records are copied word by word");
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (int)(sizeof(Args) / 4); i += blockDim.x * blockDim.y) d[i] = __ldg(s + i);
+    __syncthreads();
+}
+
+struct SplatArgs {
+    const uint32_t* ev_xy; const double* ev_t; const Chunk* chunks; const float2* chunk_tr; const unsigned int* n_chunks_dev;
+    ThetaSrc T; int H, W, R, pad; RefTimes tref; FixDst dst; int4* chunk_win;
+};
+
+template <bool WRAP, int RB>
+__global__ void __launch_bounds__(256, 4)
+k_splat_tile_b(const SplatArgs* __restrict__ args) {
+    extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
+    __shared__ SplatArgs sA;
+    load_args(sA, args + blockIdx.y);
+    splat_tile_body<WRAP, RB>(sA.ev_xy, sA.ev_t, sA.chunks, sA.chunk_tr, sA.n_chunks_dev, sA.T, sA.H, sA.W, sA.R, sA.tref, sA.dst, sA.chunk_win, win);
+}
+
 // fixed-point image -> float64 image (paths that need the plain image: zero-warp image, event split, delta != 0)
 __global__ void k_fix_to_f64(const unsigned long long* __restrict__ fix, int64_t n, double* __restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -629,12 +663,10 @@ __global__ void k_fix_to_f64(const unsigned long long* __restrict__ fix, int64_t
 // of the window cells, zero where the index rule drops the cell.  Same branch-free structure as the forward pass: a miss
 // reads a fixed cell and contributes zero, the rare misses are replayed through the out-of-line gather afterwards.
 template <bool WRAP, int RB>
-__global__ void __launch_bounds__(256, 4)
-k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
-                const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
+__device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
+                const ThetaSrc& T, int H, int W, int R, const RefTimes& tref,
                 const float* __restrict__ dldi32 /* [R][H][W], scaled by 1/(2 pi) */, const int4* __restrict__ chunk_win,
-                double* __restrict__ G /* [H][W][2] */) {
-    extern __shared__ __align__(16) float dwin[];            // [RB][kWinCap]
+                double* __restrict__ G /* [H][W][2] */, float* dwin /* [RB][kWinCap] dynamic shared memory */) {
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
@@ -771,6 +803,30 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
         if (head && run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
         __syncthreads();                             // th_s / swin / dwin are rewritten for the next chunk
     }
+}
+
+template <bool WRAP, int RB>
+__global__ void __launch_bounds__(256, 4)
+k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
+                const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
+                const float* __restrict__ dldi32 /* [R][H][W], scaled by 1/(2 pi) */, const int4* __restrict__ chunk_win,
+                double* __restrict__ G /* [H][W][2] */) {
+    extern __shared__ __align__(16) float dwin[];            // [RB][kWinCap]
+    backward_tile_body<WRAP, RB>(ev_xy, ev_t, chunks, n_chunks_dev, T, H, W, R, tref, dldi32, chunk_win, G, dwin);
+}
+
+struct BackwardTileArgs {
+    const uint32_t* ev_xy; const double* ev_t; const Chunk* chunks; const unsigned int* n_chunks_dev;
+    ThetaSrc T; int H, W, R, pad; RefTimes tref; const float* dldi32; const int4* chunk_win; double* G;
+};
+
+template <bool WRAP, int RB>
+__global__ void __launch_bounds__(256, 4)
+k_backward_tile_b(const BackwardTileArgs* __restrict__ args) {
+    extern __shared__ __align__(16) float dwin[];            // [RB][kWinCap]
+    __shared__ BackwardTileArgs sA;
+    load_args(sA, args + blockIdx.y);
+    backward_tile_body<WRAP, RB>(sA.ev_xy, sA.ev_t, sA.chunks, sA.n_chunks_dev, sA.T, sA.H, sA.W, sA.R, sA.tref, sA.dldi32, sA.chunk_win, sA.G, dwin);
 }
 
 // ---- debug tap: Xs_rounded (event_utils.py:33) of reference r, written back in the original event order ----

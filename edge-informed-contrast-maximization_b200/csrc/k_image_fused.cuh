@@ -72,19 +72,20 @@ __device__ __forceinline__ FusedAcc fused_block_reduce(FusedAcc a, double (*sh)[
 }
 
 // ---- k_image_stats ---------------------------------------------------------------------------------------------------------
-// Row-band formulation: a CTA owns a contiguous run of complete image rows (R*H rows laid end to end are split evenly over the
-// grid) and handles it in sub-bands of <= band_rows rows.  A sub-band (plus two halo rows on either side and a zero column on
-// either side) is brought into shared memory with one burst of asynchronous copies - all loads of the CTA in flight at once -
-// and then processed without further global reads: a thread owns the same CPT columns (tid, tid + 256, ...) in every row, so
-// the 3x3 stencils need no index arithmetic, global traffic is perfectly coalesced row segments, and every thread accumulates
-// its statistics over all its pixels before the single block reduction per (CTA, reference image).  The last CTA to finish
-// (ticket) reduces the per-CTA partials of every reference image in a fixed order (deterministic) and evaluates the loss;
-// the kernel boundary before k_image_grad replaces the grid-wide barrier of a cooperative formulation (measured: launch of a
-// cooperative kernel + barrier + redundant second-level reduction cost more than the second launch).
+// Streaming formulation, no shared memory and no block barrier in the main loop: one WARP owns a strip of kS2Cols columns x kS2Rows
+// rows of one reference image and marches down its rows.  Lanes are adjacent columns (two halo lanes on either side: the Scharr pair
+// and its adjoint are two chained 3x3 stencils), horizontal neighbours come from warp shuffles, vertical neighbours from a
+// three-row window in registers; rows are loaded kS2Pre at a time, one group ahead of the arithmetic (all loads of a group in flight
+// together).  Every warp accumulates the statistics of its own pixels and writes one partial record; the last CTA to finish
+// (ticket) reduces the records of every reference image in a fixed order (deterministic) and evaluates the loss.  The kernel
+// boundary before k_image_grad replaces a grid-wide barrier.  (The first version kept whole row bands in shared memory: two CTAs
+// per SM, phases separated by barriers - 27 us for 7.4 MB of L2-resident input, and no faster per window when windows were batched.)
 constexpr int kCoopMaxRefs = EINCM_MAX_REFS;
-constexpr int kBandNT = 256;
-constexpr int kMaxCPT = 6;                          // columns per thread (template parameter 1..6): sensors up to 1536 px wide
-constexpr int kBandRowsMax = 8;                     // rows of a sub-band (chosen by the host: ImageStatsArgs::band_rows)
+constexpr int kS2Warps = 4;                         // warps (work items) per CTA
+constexpr int kS2NT = kS2Warps * 32;
+constexpr int kS2Cols = 28;                         // own columns of a warp (lanes 2 .. 29)
+constexpr int kS2Rows = 12;                         // own rows of a warp (short bands: the kernel is bound by the serial latency of one warp's row loop)
+constexpr int kS2Pre = 4;                           // rows per load group
 constexpr int kStatsTicket = 6;                     // DevScalars::counters slot of the "last CTA" ticket
 
 // One cell of the image pass as the fused backward fill reads it (k_backward_fold): ONE 16-byte load per window cell instead of
@@ -98,7 +99,7 @@ struct ImageStatsArgs {
     const double* edges;            // [R][H*W]
     double* iwe;                    // [R][H*W] float64 images (out)
     float* adj32;                   // [R][H*W] adjoint of the Scharr pair applied to (Gx, Gy) (out; d contrast / d IWE up to cA)
-    double* part;                   // [R][grid][kFPart]
+    double* part;                   // [R][strips * bands][kFPart]
     DevScalars* sc;
     double* loss_out;
     double* zero_buf;               // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
@@ -107,8 +108,13 @@ struct ImageStatsArgs {
     int H, W, R;
     double alpha, beta, gamma;
     int use_tv;
-    int band_rows;                  // rows of a sub-band held in shared memory (<= kBandRowsMax; shared memory is sized for it)
+    int pad;
 };
+
+__host__ __device__ inline int image_stats_strips(int W) { return (W + kS2Cols - 1) / kS2Cols; }
+__host__ __device__ inline int image_stats_bands(int H) { return (H + kS2Rows - 1) / kS2Rows; }
+// work items (warps) of the image pass for R reference images
+__host__ __device__ inline int image_stats_items(int H, int W, int R) { return R * image_stats_strips(W) * image_stats_bands(H); }
 
 __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double sE, double sE2, double cb) {
     Stats st;
@@ -125,64 +131,35 @@ __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double
     return st;
 }
 
-// 8-byte asynchronous global -> shared copy; `valid == false` zero-fills (rows outside the image)
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-struct BandSmemTail {
-    double red[kBandNT / 32][kFPart];
+struct StatsTail {
     Stats st[kCoopMaxRefs];
     double coefA[kCoopMaxRefs], coefB[kCoopMaxRefs];
     double wts[kCoopMaxRefs], zero_mse[kCoopMaxRefs], sumE[kCoopMaxRefs], sumE2[kCoopMaxRefs], zero_contrast;
     int is_last;
 };
 
-// image rows (halo 2) + Scharr pair of rows (halo 1, float32) of a sub-band of B rows
-__host__ __device__ inline size_t image_pass_smem_bytes(int W, int B) {
-    return (size_t)((B + 4) + (B + 2)) * (W + 2) * sizeof(double) + sizeof(BandSmemTail);
-}
+__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn_d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-template <int CPT>
-__global__ void __launch_bounds__(kBandNT, 2)
-k_image_stats(const ImageStatsArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int H = A.H, W = A.W, R = A.R, Wp = W + 2;
-    const int B = A.band_rows;
-    double* bandI = reinterpret_cast<double*>(smem_raw);             // [B + 4][Wp]: image rows sa-2 .. sa+B+1
-    float* gxs = reinterpret_cast<float*>(bandI + (B + 4) * Wp);     // [B + 2][Wp] Scharr x of rows sa-1 .. sa+B
-    float* gys = gxs + (B + 2) * Wp;                                 // [B + 2][Wp] Scharr y
-    BandSmemTail& S = *reinterpret_cast<BandSmemTail*>(gys + (B + 2) * Wp);
+template <bool REC>
+__device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
+    __shared__ StatsTail S;
+    const int H = A.H, W = A.W, R = A.R;
     const int HW = H * W;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int strips = image_stats_strips(W), bands = image_stats_bands(H);
+    const int per_img = strips * bands, n_items = R * per_img;
     const int G = gridDim.x, b = blockIdx.x;
-    const int RH = R * H;
-    const int row_begin = (int)(((long long)RH * b) / G), row_end = (int)(((long long)RH * (b + 1)) / G);
-    const int r_first = row_begin < row_end ? row_begin / H : 0, r_last = row_begin < row_end ? (row_end - 1) / H : -1;
-
     // programmatic dependent launch: the next kernel of the evaluation may be scheduled as soon as every CTA of this one is resident;
-    // this kernel itself may have been scheduled while the splat was still running - nothing but shared memory and per-window
-    // constants is touched before the wait
+    // this kernel itself may have been scheduled while the splat was still running - nothing is read or written before the wait
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // zero columns (never written afterwards), identity partials, accumulators of the event backward pass
-    for (int k = tid; k < B + 4; k += kBandNT) { bandI[k * Wp] = 0.0; bandI[k * Wp + W + 1] = 0.0; }
-    for (int k = tid; k < 2 * (B + 2); k += kBandNT) { gxs[k * Wp] = 0.f; gxs[k * Wp + W + 1] = 0.f; }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int k = tid; k < R * kFPart; k += kBandNT) {
-        const int q = k / kFPart, f = k % kFPart;
-        A.part[(q * G + b) * kFPart + f] = (f == 4) ? INFINITY : ((f == 6) ? -INFINITY : 0.0);
-    }
+    // accumulators of the event backward pass
     if (A.zero_buf != nullptr)
-        for (int k = b * kBandNT + tid; k < A.n_zero; k += G * kBandNT) A.zero_buf[k] = 0.0;
+        for (int k = b * kS2NT + tid; k < A.n_zero; k += G * kS2NT) A.zero_buf[k] = 0.0;
     if (A.zero_buf2 != nullptr)
-        for (int k = b * kBandNT + tid; k < A.n_zero2; k += G * kBandNT) A.zero_buf2[k] = 0.0;
-    // per-window constants of the tail (cotangent scales from the zero-warp image, losses.py:176-177): fetched now, their
-    // latency hides behind the band loop
+        for (int k = b * kS2NT + tid; k < A.n_zero2; k += G * kS2NT) A.zero_buf2[k] = 0.0;
+    // per-window constants of the tail (cotangent scales from the zero-warp image, losses.py:176-177)
     if (tid < R) {
         const double w = A.sc->weights[tid], zc = A.sc->zero[0].contrast, zm = A.sc->zero[tid].mse;
         const double a_r = -A.alpha * w / ((zc + kEps) * R);
@@ -193,104 +170,94 @@ k_image_stats(const ImageStatsArgs A) {
         if (tid == 0) S.zero_contrast = zc;
     }
 
-    for (int r = r_first; r <= r_last; ++r) {
-        const int ya = max(row_begin - r * H, 0), yb = min(row_end - r * H, H);
-        const unsigned long long* Fr = A.fix + r * HW;
-        const double* Er = A.edges + r * HW;
+    for (int item = b * kS2Warps + wid; item < n_items; item += G * kS2Warps) {
+        const int r = item / per_img, rem = item - r * per_img;
+        const int band = rem / strips, strip = rem - band * strips;
+        const int x = strip * kS2Cols - 2 + lane;                 // this lane's column (lanes 0, 1, 30, 31: halo)
+        const int y0 = band * kS2Rows, y1 = min(H, y0 + kS2Rows);
+        const bool xin = x >= 0 && x < W;
+        const bool own_col = lane >= 2 && lane < 2 + kS2Cols && xin;
+        const unsigned long long* Fr = A.fix + r * HW + (xin ? x : 0);
+        const double* Er = A.edges + r * HW + (xin ? x : 0);
         double* Ir = A.iwe + r * HW;
         float* Ar = A.adj32 + r * HW;
-        CellRec* Rr = A.rec != nullptr ? A.rec + r * HW : nullptr;
+        CellRec* Rr = REC ? A.rec + r * HW : nullptr;
         const float* E32r = A.e32 + r * HW;
         FusedAcc acc;
         acc.init();
-        int cnt_mn = 0, cnt_mx = 0;                   // tie counts of the running min / max (integers: branch-free update)
-        for (int sa = ya; sa < yb; sa += B) {
-            const int sb = min(sa + B, yb);
-            __syncthreads();                           // previous readers of the band are done
-            for (int y = sa - 2; y < sb + 2; ++y) {    // fixed-point rows sa-2 .. sb+1 -> bandI, row y at slot y - sa + 2
-                double* dst = bandI + (y - sa + 2) * Wp + 1;
-                const bool in = y >= 0 && y < H;
+        int cnt_mn = 0, cnt_mx = 0;                    // tie counts of the running min / max (integers: branch-free update)
+        // three-row windows: image value and horizontal difference of input rows yi-2, yi-1 (yi: the row being consumed);
+        // Scharr x differences and Scharr y of rows yc-2, yc-1 (yc = yi - 1: the row whose Scharr pair is produced)
+        double I2 = 0.0, I1 = 0.0, Dx2 = 0.0, Dx1 = 0.0, E1 = 0.0;
+        float Ex2 = 0.f, Ex1 = 0.f, gy2 = 0.f, gy1 = 0.f;
+        // load groups: rows base .. base + kS2Pre - 1, one group ahead
+        unsigned long long fq[kS2Pre];
+        double eq[kS2Pre];
+        auto load_group = [&](int base) {
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    if (x < W) cp_async8(dst + x, in ? (const void*)(Fr + y * W + x) : (const void*)Fr, in);
-                }
+            for (int u = 0; u < kS2Pre; ++u) {
+                const int y = base + u;
+                const bool ok = xin && y >= 0 && y < H;
+                fq[u] = ok ? __ldcg(Fr + y * W) : 0ull;
+                eq[u] = (ok && y >= y0 && y < y1) ? __ldg(Er + y * W) : 0.0;
             }
-            double e_next[CPT];                        // edge row of the next own row: register prefetch, one row ahead
+        };
+        load_group(y0 - 2);
+        for (int base = y0 - 2; base <= y1 + 1; base += kS2Pre) {
+            unsigned long long fc[kS2Pre];
+            double ec[kS2Pre];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int x = tid + c * kBandNT;
-                e_next[c] = (x < W) ? __ldg(Er + sa * W + x) : 0.0;
-            }
-            cp_async_commit_wait_all();
-            for (int y = sa - 2; y < sb + 2; ++y) {    // fixed point -> float64, each thread the cells it copied
-                double* row = bandI + (y - sa + 2) * Wp + 1;
+            for (int u = 0; u < kS2Pre; ++u) { fc[u] = fq[u]; ec[u] = eq[u]; }
+            if (base + kS2Pre <= y1 + 1) load_group(base + kS2Pre);
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    // sums are far below 2^52: (2^52 | v) reinterpreted as float64 is exactly 2^52 + v
-                    if (x < W) row[x] = __dsub_rn(__longlong_as_double(0x4330000000000000ll | reinterpret_cast<const long long*>(row)[x]), 4503599627370496.0) * kFixToIwe;
+            for (int u = 0; u < kS2Pre; ++u) {
+                const int yi = base + u;
+                if (yi > y1 + 1) break;                                     // warp-uniform
+                // fixed point -> float64: sums are far below 2^52, (2^52 | v) reinterpreted as float64 is exactly 2^52 + v
+                const double I0 = __dsub_rn(__longlong_as_double(0x4330000000000000ll | (long long)fc[u]), 4503599627370496.0) * kFixToIwe;
+                const double Dx0 = __dsub_rn(shfl_dn_d(I0), shfl_up_d(I0));   // I[yi][x+1] - I[yi][x-1] (lanes 0 / 31: unused garbage)
+                // ---- Scharr pair of row yc = yi - 1 (zero outside the image: the 'same' output only exists inside)
+                const int yc = yi - 1;
+                const double Dy = __dsub_rn(I0, I2);                          // I[yc+1][x] - I[yc-1][x]
+                const double Dyl = shfl_up_d(Dy), Dyr = shfl_dn_d(Dy);
+                double gx = 0.0, gy = 0.0;
+                if (xin && yc >= 0 && yc < H) {
+                    gx = __dadd_rn(__dadd_rn(__dmul_rn(3.0, Dx0), __dmul_rn(10.0, Dx1)), __dmul_rn(3.0, Dx2));
+                    gy = __dadd_rn(__dadd_rn(__dmul_rn(3.0, Dyr), __dmul_rn(10.0, Dy)), __dmul_rn(3.0, Dyl));
                 }
-            }
-            __syncthreads();
-            // Scharr pair of rows sa-1 .. sb (zero outside the image: the 'same' output only exists inside); statistics of the
-            // rows this CTA owns; float32 copies for the adjoint
-            for (int q = sa - 1; q <= sb; ++q) {
-                const double* mid = bandI + (q - sa + 2) * Wp + 1;
-                const double* up = mid - Wp;
-                const double* dn = mid + Wp;
-                float* gxr = gxs + (q - sa + 1) * Wp + 1;
-                float* gyr = gys + (q - sa + 1) * Wp + 1;
-                const bool inside = q >= 0 && q < H, own = q >= sa && q < sb;
-                double er[CPT];
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) er[c] = e_next[c];
-                if (own && q + 1 < sb) {
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        const int x = tid + c * kBandNT;
-                        e_next[c] = (x < W) ? __ldg(Er + (q + 1) * W + x) : 0.0;
-                    }
+                if (own_col && yc >= y0 && yc < y1) {                         // statistics and image value of an own pixel
+                    const double I = I1;
+                    if (REC) Rr[yc * W + x].I = I; else Ir[yc * W + x] = I;
+                    acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += E1 * I;
+                    cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
+                    cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
+                    acc.mn = fmin(acc.mn, I);
+                    acc.mx = fmax(acc.mx, I);
                 }
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    if (x < W) {
-                        double gx = 0.0, gy = 0.0;
-                        if (inside) scharr_vals(dn[x + 1], dn[x - 1], mid[x + 1], mid[x - 1], up[x + 1], up[x - 1], dn[x], up[x], gx, gy);
-                        gxr[x] = (float)gx; gyr[x] = (float)gy;
-                        if (own) {
-                            const double I = mid[x];
-                            if (Rr != nullptr) Rr[q * W + x].I = I; else Ir[q * W + x] = I;
-                            acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += er[c] * I;
-                            cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
-                            cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
-                            acc.mn = fmin(acc.mn, I);
-                            acc.mx = fmax(acc.mx, I);
-                        }
-                    }
+                // ---- adjoint of the Scharr pair at row ya = yc - 1 from the float32 pair of rows yc-2, yc-1, yc
+                const float gx0 = (float)gx, gy0 = (float)gy;
+                const float Ex0 = __fsub_rn(__shfl_up_sync(0xffffffffu, gx0, 1), __shfl_down_sync(0xffffffffu, gx0, 1));   // gx[x-1] - gx[x+1]
+                const float Fy = __fsub_rn(gy2, gy0);                          // gy[ya-1] - gy[ya+1]
+                const float Fyl = __shfl_up_sync(0xffffffffu, Fy, 1), Fyr = __shfl_down_sync(0xffffffffu, Fy, 1);
+                const int ya = yc - 1;
+                if (own_col && ya >= y0 && ya < y1) {
+                    const float ax = __fadd_rn(__fadd_rn(__fmul_rn(3.f, Ex2), __fmul_rn(10.f, Ex1)), __fmul_rn(3.f, Ex0));
+                    const float ay = __fadd_rn(__fadd_rn(__fmul_rn(3.f, Fyl), __fmul_rn(10.f, Fy)), __fmul_rn(3.f, Fyr));
+                    const float adj = __fadd_rn(ax, ay);
+                    if (REC) *reinterpret_cast<float2*>(&Rr[ya * W + x].adj) = make_float2(adj, __ldg(E32r + ya * W + x));
+                    else Ar[ya * W + x] = adj;
                 }
-            }
-            __syncthreads();
-            for (int y = sa; y < sb; ++y) {
-                const float* xm = gxs + (y - sa + 1) * Wp + 1;
-                const float* ym = gys + (y - sa + 1) * Wp + 1;
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int x = tid + c * kBandNT;
-                    if (x < W) {
-                        const float a = scharr_adjoint_rows_f32(xm - Wp + x, xm + x, xm + Wp + x, ym - Wp + x, ym + Wp + x);
-                        if (Rr != nullptr) *reinterpret_cast<float2*>(&Rr[y * W + x].adj) = make_float2(a, __ldg(E32r + y * W + x));
-                        else Ar[y * W + x] = a;
-                    }
-                }
+                // shift the windows
+                I2 = I1; I1 = I0; Dx2 = Dx1; Dx1 = Dx0; E1 = ec[u];
+                Ex2 = Ex1; Ex1 = Ex0; gy2 = gy1; gy1 = gy0;
             }
         }
         acc.cmn = (double)cnt_mn; acc.cmx = (double)cnt_mx;
-        const FusedAcc a = fused_block_reduce(acc, S.red);
-        if (tid == 0) {
-            double* d = A.part + (r * G + b) * kFPart;
-            d[0] = a.sq; d[1] = a.sI; d[2] = a.sI2; d[3] = a.sEI; d[4] = a.mn; d[5] = a.cmn; d[6] = a.mx; d[7] = a.cmx;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc.merge(acc.shfl_xor(o));
+        if (lane == 0) {
+            double* d = A.part + (int64_t)item * kFPart;
+            d[0] = acc.sq; d[1] = acc.sI; d[2] = acc.sI2; d[3] = acc.sEI; d[4] = acc.mn; d[5] = acc.cmn; d[6] = acc.mx; d[7] = acc.cmx;
         }
     }
 
@@ -302,26 +269,22 @@ k_image_stats(const ImageStatsArgs A) {
     if (!S.is_last) return;
     __threadfence();
     {
-        const int lane = tid & 31;
-        for (int q = tid >> 5; q < R; q += kBandNT / 32) {
-            // only the CTAs whose rows intersect image q hold a non-identity partial: a contiguous range of CTAs.  Four records
-            // per lane and round, all loads of a round issued before the first merge (one L2 round trip per round)
-            const int k_lo = (int)(((long long)q * H * G) / RH);
-            const int k_hi = min(G, (int)((((long long)(q + 1) * H * G) + RH - 1) / RH) + 1);
+        for (int q = wid; q < R; q += kS2Warps) {
+            // four records per lane and round, all loads of a round issued before the first merge (one L2 round trip per round)
             FusedAcc a;
             a.init();
-            for (int k0 = k_lo + lane; k0 < k_hi; k0 += 4 * 32) {
+            for (int k0 = lane; k0 < per_img; k0 += 4 * 32) {
                 double v[4][kFPart];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int k = min(k0 + 32 * u, k_hi - 1);
-                    const double* d = A.part + (q * G + k) * kFPart;
+                    const int k = min(k0 + 32 * u, per_img - 1);
+                    const double* d = A.part + ((int64_t)q * per_img + k) * kFPart;
 #pragma unroll
                     for (int f = 0; f < kFPart; ++f) v[u][f] = __ldcg(d + f);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (k0 + 32 * u < k_hi) {
+                    if (k0 + 32 * u < per_img) {
                         FusedAcc o;
                         o.sq = v[u][0]; o.sI = v[u][1]; o.sI2 = v[u][2]; o.sEI = v[u][3];
                         o.mn = v[u][4]; o.cmn = v[u][5]; o.mx = v[u][6]; o.cmx = v[u][7];
@@ -368,6 +331,17 @@ k_image_stats(const ImageStatsArgs A) {
     }
 }
 
+__global__ void __launch_bounds__(kS2NT, 5)
+k_image_stats(const ImageStatsArgs A) { if (A.rec != nullptr) image_stats_body<true>(A); else image_stats_body<false>(A); }
+
+// batched form: blockIdx.y = window, one argument record per window in device memory
+__global__ void __launch_bounds__(kS2NT, 5)
+k_image_stats_b(const ImageStatsArgs* __restrict__ args) {
+    __shared__ ImageStatsArgs sA;
+    load_args(sA, args + blockIdx.y);
+    image_stats_body<false>(sA);
+}
+
 // ---- k_image_grad ----------------------------------------------------------------------------------------------------------
 // d loss / d IWE_r = cA_r * adjoint(Gx, Gy) + gN / D + (tie-split cotangents of min and max)   with   gN = cB_r (E - (I - m) / D)
 // (reverse mode of contrast_objectives.py:22-25, img_utils.py:24-25, correlation_objectives.py:25-26; min / max cotangents
@@ -385,8 +359,7 @@ struct ImageGradArgs {
     int want_grad;                  // 0: only clear the fixed-point images
 };
 
-__global__ void __launch_bounds__(256)
-k_image_grad(const ImageGradArgs A) {
+__device__ __forceinline__ void image_grad_body(const ImageGradArgs& A) {
     // programmatic dependent launch (no-ops when launched plainly): let the next kernel be scheduled, wait for the image statistics
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -432,6 +405,16 @@ k_image_grad(const ImageGradArgs A) {
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_image_grad(const ImageGradArgs A) { image_grad_body(A); }
+
+__global__ void __launch_bounds__(256)
+k_image_grad_b(const ImageGradArgs* __restrict__ args) {
+    __shared__ ImageGradArgs sA;
+    load_args(sA, args + blockIdx.y);
+    image_grad_body(sA);
 }
 
 // cell records -> dense float64 image + float32 adjoint (debug taps and the unfused d loss / d IWE kernel, on demand)

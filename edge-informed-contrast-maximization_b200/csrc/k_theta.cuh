@@ -78,9 +78,8 @@ __device__ __forceinline__ double axis_weight(const AxisTaps& t, int o, int i) {
 }
 
 template <bool HAS_TV>
-__global__ void __launch_bounds__(kTgWarps * 32)
-k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
-             double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, AxisTaps ty, AxisTaps tx,
+__device__ __forceinline__ void theta_grad_body(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
+             double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, const AxisTaps& ty, const AxisTaps& tx,
              const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */,
              const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad) {
     // programmatic dependent launch (no-ops when launched plainly)
@@ -171,6 +170,34 @@ k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, Dev
             __threadfence_system();
         }
     }
+}
+
+template <bool HAS_TV>
+__global__ void __launch_bounds__(kTgWarps * 32)
+k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
+             double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, AxisTaps ty, AxisTaps tx,
+             const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */,
+             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad) {
+    theta_grad_body<HAS_TV>(G, Gtv, sc, gamma, h, w, H, W, SY, SX, n_items, ty, tx, prev, theta, grad, loss_dev, host_out, host_grad);
+}
+
+// batched form (blockIdx.y = window; gamma == 0): one argument record per window in device memory
+struct ThetaGradArgs {
+    const double2* G; DevScalars* sc; int h, w, H, W, SY, SX, n_items, host_grad; AxisTaps ty, tx;
+    const double* prev; const double* theta; double* grad; const double* loss_dev; double* host_out;
+};
+
+__global__ void __launch_bounds__(kTgWarps * 32)
+k_theta_grad_b(const ThetaGradArgs* __restrict__ args) {
+    __shared__ ThetaGradArgs sA;
+    {   // (load_args of k_events_tile.cuh: this header comes first)
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(args + blockIdx.y);
+        uint32_t* d = reinterpret_cast<uint32_t*>(&sA);
+        for (int i = threadIdx.x; i < (int)(sizeof(ThetaGradArgs) / 4); i += blockDim.x) d[i] = __ldg(s + i);
+        __syncthreads();
+    }
+    theta_grad_body<false>(sA.G, nullptr, sA.sc, 0.0, sA.h, sA.w, sA.H, sA.W, sA.SY, sA.SX, sA.n_items, sA.ty, sA.tx, sA.prev, sA.theta, sA.grad,
+                           sA.loss_dev, sA.host_out, sA.host_grad);
 }
 
 // ---- backward of the resize, scatter form (large / dense theta) -----------------------------------------

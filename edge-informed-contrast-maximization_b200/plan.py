@@ -40,6 +40,8 @@ EXPORTED_SYMBOLS = (
     'eincm_edge_workspace_bytes', 'eincm_edge_maps', 'eincm_edge_maps_host',
     'eincm_nlm_workspace_bytes', 'eincm_nlm_denoise',
     'eincm_rectify_workspace_bytes', 'eincm_rectify_events', 'eincm_normalize_times', 'eincm_window_event_range',
+    'eincm_batch_create', 'eincm_batch_destroy', 'eincm_batch_last_error', 'eincm_batch_value_and_grad', 'eincm_batch_value_and_grad_host',
+    'eincm_batch_launch_count',
 )
 
 
@@ -169,6 +171,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_rectify_events': (i32, [i32, vp, vp, vp, vp, i64, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i64), vp, C.c_size_t, vp]),
         'eincm_normalize_times': (i32, [i32, vp, i64, i64, i64, vp, vp]),
         'eincm_window_event_range': (i32, [i64, i64, i64, i64, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        'eincm_batch_create': (i32, [C.POINTER(vp), C.POINTER(vp), i32]),
+        'eincm_batch_destroy': (None, [vp]),
+        'eincm_batch_last_error': (C.c_char_p, [vp]),
+        'eincm_batch_value_and_grad': (i32, [vp, C.POINTER(vp), i32, i32, hp, C.POINTER(vp), C.POINTER(vp), vp]),
+        'eincm_batch_value_and_grad_host': (i32, [vp, C.POINTER(vp), i32, i32, hp, C.POINTER(dbl), C.POINTER(vp), vp]),
+        'eincm_batch_launch_count': (i64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -237,6 +245,67 @@ class Group:
             self.close()
         except Exception:
             pass
+
+
+class Batch:
+    """``eincm_batch``: B staged windows (one ``Plan`` each) evaluated with one launch per kernel of the evaluation
+    (include/eincm.h, "batched evaluation").  Results are identical to the per-plan calls."""
+
+    def __init__(self, plans: Sequence['Plan']):
+        self.lib = plans[0].lib
+        self.plans = list(plans)
+        hs = (C.c_void_p * len(plans))(*[p._h.value for p in plans])
+        h = C.c_void_p()
+        rc = self.lib.eincm_batch_create(C.byref(h), hs, len(plans))
+        if rc != EINCM_OK:
+            raise EincmError(rc, (self.lib.eincm_last_error(plans[0]._h) or b'').decode())
+        self._h = h
+        self._keep = []
+
+    def _check(self, rc: int):
+        if rc != EINCM_OK:
+            raise EincmError(rc, (self.lib.eincm_batch_last_error(self._h) or b'').decode())
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.eincm_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def value_and_grad_device(self, thetas_d, hp: HParams, losses_d, grads_d, stream=None):
+        """Device operands (lists of CUDA tensors, one per window), asynchronous on the current (or given) stream."""
+        n = len(self.plans)
+        if not (len(thetas_d) == len(losses_d) == len(grads_d) == n):
+            raise EincmError(EINCM_EINVAL, 'one theta / loss / gradient tensor per window of the batch')
+        h, w = int(thetas_d[0].shape[0]), int(thetas_d[0].shape[1])
+        tp = (C.c_void_p * n)(*[t.data_ptr() for t in thetas_d])
+        lp = (C.c_void_p * n)(*[t.data_ptr() for t in losses_d])
+        gp = (C.c_void_p * n)(*[t.data_ptr() for t in grads_d])
+        self._keep = [thetas_d, losses_d, grads_d]
+        self._check(self.lib.eincm_batch_value_and_grad(self._h, tp, h, w, C.byref(hp), lp, gp, _stream_ptr(stream)))
+
+    def value_and_grad_host(self, thetas: Sequence[np.ndarray], hp: HParams, want_grad: bool = True, stream=None):
+        """Host operands, synchronous: returns ``(losses float64[n], grads list of (h, w, 2) arrays or None)``."""
+        n = len(self.plans)
+        ths = [np.ascontiguousarray(t, dtype=np.float64) for t in thetas]
+        shape = ths[0].shape
+        if len(ths) != n or len(shape) != 3 or shape[2] != 2 or any(t.shape != shape for t in ths):
+            raise EincmError(EINCM_EINVAL, 'one theta of shape (h, w, 2) per window of the batch')
+        tp = (C.c_void_p * n)(*[t.ctypes.data for t in ths])
+        losses = np.empty(n, dtype=np.float64)
+        grads = [np.empty_like(t) for t in ths] if want_grad else None
+        gp = (C.c_void_p * n)(*[g.ctypes.data for g in grads]) if want_grad else None
+        self._check(self.lib.eincm_batch_value_and_grad_host(self._h, tp, shape[0], shape[1], C.byref(hp),
+                                                             losses.ctypes.data_as(C.POINTER(C.c_double)), gp, _stream_ptr(stream)))
+        return losses, grads
+
+    def launch_count(self) -> int:
+        return int(self.lib.eincm_batch_launch_count(self._h))
 
 
 class _DevView:

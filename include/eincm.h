@@ -139,6 +139,28 @@ int eincm_handover_value_and_grad_host(eincm_plan* plan, double alpha_handover, 
  * (src/eincm/solver.py:209-216); independent sequences / windows without handover may be evaluated together. */
 int eincm_value_and_grad_host_batch(eincm_plan* const* plans, int n_plans, const double* const* thetas_host, int h, int w,
                                     const eincm_hparams* hp, double* losses_out_host, double* const* grads_out_host);
+/* ---- batched evaluation: B staged windows, ONE launch per kernel of the evaluation (blockIdx.y = window) ----------------------
+ * BASELINE.json configs[2] / [3] ("batch of windows on 1 x B200", windows sharded over the GPUs).  The reference evaluates one window
+ * at a time (src/eincm/solver.py:209-216); independent windows - different sequences, or windows solved without handover - have no
+ * data dependence, so their evaluations share launches here: five launches per BATCH instead of five per window, the small
+ * image-space kernels fill the GPU, and MVSEC-sized windows (30 k events on 256 x 336 pixels) stop being launch-bound.  Same kernel
+ * bodies as eincm_value_and_grad: results are identical bit for bit.  All plans on one device with one sensor size and the same
+ * number of reference times; default path only (no EINCM_FLAG_EXACT_F64 / EVENT_SPLIT); hp->delta == 0 and no TV term (gamma == 0
+ * or cur_pyr_lvl > 0); theta is a tile field of <= 4096 elements or the dense H x W field (EINCM_EUNSUPPORTED otherwise: use the
+ * per-plan calls).  The pointer ARRAYS are host arrays; thetas[k] / loss_out[k] / grad_out[k] are DEVICE pointers of window k
+ * ([h][w][2], 1, [h][w][2] float64).  Asynchronous on cuda_stream; one call in flight per batch. */
+typedef struct eincm_batch eincm_batch;
+int eincm_batch_create(eincm_batch** out, eincm_plan* const* plans, int n_plans);
+void eincm_batch_destroy(eincm_batch* batch);
+const char* eincm_batch_last_error(const eincm_batch* batch);
+int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, int h, int w, const eincm_hparams* hp,
+                               double* const* loss_out, double* const* grad_out, void* cuda_stream);
+/* the same with HOST operands (synchronous): one host -> device copy of all thetas, the launches, one device -> host copy of all
+ * losses and gradients.  grads_out_host (or entries of it) may be NULL. */
+int eincm_batch_value_and_grad_host(eincm_batch* batch, const double* const* thetas_host, int h, int w, const eincm_hparams* hp,
+                                    double* losses_out_host, double* const* grads_out_host, void* cuda_stream);
+int64_t eincm_batch_launch_count(const eincm_batch* batch);   /* kernels launched by this batch since creation */
+
 /* ---- native optimizers: what jaxopt's ScipyMinimize(method='BFGS').run / ScipyBoundedMinimize(method='L-BFGS-B').run do with
  * the objective (reference src/eincm/solver.py:165-183, :209-216, :325-335), without returning to Python between evaluations.
  * Same algorithms and default parameters as scipy.optimize.minimize (csrc/eincm_opt.h); status: 0 converged (max|grad| <= gtol),
