@@ -84,7 +84,7 @@ constexpr int kCoopMaxRefs = EINCM_MAX_REFS;
 constexpr int kS2Warps = 4;                         // warps (work items) per CTA
 constexpr int kS2NT = kS2Warps * 32;
 constexpr int kS2Cols = 28;                         // own columns of a warp (lanes 2 .. 29)
-constexpr int kS2Rows = 12;                         // own rows of a warp (short bands: the kernel is bound by the serial latency of one warp's row loop)
+constexpr int kS2Rows = 24;                         // own rows of a warp (measured: 12 rows -> 51 us, 24 rows -> 35 us at 640x480, R = 3)
 constexpr int kS2Pre = 4;                           // rows per load group
 constexpr int kStatsTicket = 6;                     // DevScalars::counters slot of the "last CTA" ticket
 
