@@ -61,8 +61,11 @@ def algorithmic_bytes(N, R, H, W):
     img = R * H * W * 8 * 5
     fld = H * W * 2 * 8 * 2
     return {'eval': ev + img + fld,
-            'k_splat': N * 12 + R * H * W * 8 + H * W * 16,
-            'k_backward_events': N * 12 + R * H * W * 8 + H * W * 16 + H * W * 16}
+            'k_splat': N * 12 + R * H * W * 8 + H * W * 16,                      # events, IWE written, dense theta field
+            'k_image_stats': R * H * W * 8 * 2,                                 # IWE read, edge image read
+            'k_image_grad': R * H * W * 8,                                      # dL/dIWE written
+            'k_backward_events': N * 12 + R * H * W * 8 + H * W * 16,           # events, dL/dIWE read, dense gradient field
+            'k_theta_grad': H * W * 16}
 
 
 class ClockSampler:
@@ -111,7 +114,8 @@ class ClockSampler:
 
 def workload_string(name, W, H, N, R, theta):
     """config.workload: the same string in both arms (the driver compares them)."""
-    return (f'{name}: DSEC-shaped {W}x{H}, N={N} events/window, R={R} reference times, theta {theta}x{theta}x2 '
+    shaped = 'DSEC-shaped ' if name.startswith(('dsec', 'e00')) else ''
+    return (f'{name}: {shaped}{W}x{H}, N={N} events/window, R={R} reference times, theta {theta}x{theta}x2 '
             f'(finest pyramid level)')
 
 
@@ -125,6 +129,130 @@ def make_windows(args, rank):
         wins.append(synth.make_workload(args.workload, seed=1000 * rank + k, n_events=args.events))
     return wins
 
+
+
+# --------------------------------------------------------------------------------------------------------------
+# batched evaluation: B windows per launch (BASELINE.json configs[2]: MVSEC-shaped windows, tile and dense theta)
+# --------------------------------------------------------------------------------------------------------------
+def batched_measure(workload, B, theta, dense, steps, warmup, min_time_s, cpu=True, n_distinct=16, n_check=2, cpu_budget=6.0):
+    """One batch of B staged windows on the current GPU: device-resident step (CUDA events), the host-operand call, per-kernel
+    spans, roofline of the dominant kernel, parity of the first windows against the CPU restatement and its timing."""
+    import torch
+    from eincm_b200 import plan as P, synth
+    wins = [synth.make_workload(workload, seed=100 + k) for k in range(min(n_distinct, B))]
+    H, W = wins[0].sensor_size
+    N, R = len(wins[0].xs), len(wins[0].edge_ts)
+    hpd = wins[0].hparams
+    hp = P.make_hparams(hpd['alpha'], hpd['beta'], 0.0, 0.0, 1)
+    shape = (H, W) if dense else (theta, theta)
+    plans, th_h, th_d, lo_d, gr_d = [], [], [], [], []
+    for k in range(B):
+        w = wins[k % len(wins)]
+        p = P.Plan((H, W), max_events=N, max_refs=max(R, 3))
+        p.set_window(*w.args())
+        plans.append(p)
+        t = synth.theta_test_points(w, shape, seed=k)['perturbed']
+        th_h.append(t)
+        th_d.append(torch.from_numpy(t).cuda())
+        lo_d.append(torch.zeros(1, dtype=torch.float64, device='cuda'))
+        gr_d.append(torch.zeros(shape + (2,), dtype=torch.float64, device='cuda'))
+    batch = P.Batch(plans)
+    for _ in range(warmup):
+        batch.value_and_grad_device(th_d, hp, lo_d, gr_d)
+    torch.cuda.synchronize()
+    block_ms = []
+    l0 = batch.launch_count()
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            batch.value_and_grad_device(th_d, hp, lo_d, gr_d)
+        e1.record()
+        torch.cuda.synchronize()
+        block_ms.append(e0.elapsed_time(e1))
+        if sum(block_ms) >= min_time_s * 1e3 or len(block_ms) >= 200:
+            break
+    launches = (batch.launch_count() - l0) // len(block_ms)
+    ms_step = float(np.median(block_ms)) / steps
+    # per-kernel spans (separate pass)
+    batch.set_timing(True)
+    for _ in range(max(3, steps // 2)):
+        batch.value_and_grad_device(th_d, hp, lo_d, gr_d)
+    kt = batch.get_timing()
+    batch.set_timing(False)
+    kern_ms = {k: v[0] / max(v[1], 1) for k, v in kt.items()}
+    # host operands: thetas of all windows in, losses + gradients out, one synchronous call per step
+    for _ in range(2):
+        batch.value_and_grad_host(th_h, hp)
+    n_e2e = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        losses_h, grads_h = batch.value_and_grad_host(th_h, hp)
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    theta_bytes = int(np.prod(shape)) * 2 * 8
+    alg = algorithmic_bytes(N, R, H, W)
+    peak, peak_src = _peaks()
+    dom = max(kern_ms, key=lambda k: kern_ms[k])
+    achieved = B * alg[dom] / (kern_ms[dom] * 1e-3) / 1e9
+    res = {'workload': f'{workload}: {W}x{H}, N={N} events/window, R={R} reference times, theta ' +
+                       (f'dense {H}x{W}x2' if dense else f'{theta}x{theta}x2') + f', batch of {B} windows per launch',
+           'value': B * N / (ms_step * 1e-3) / 1e9, 'unit': UNIT, 'ms_per_step': ms_step, 'us_per_window': ms_step / B * 1e3,
+           'evals_per_s': B / (ms_step * 1e-3), 'gpu_launches_per_step': launches // steps,
+           'e2e': {'value': B * N / e2e_s / 1e9, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3, 'h2d_bytes_per_step': B * theta_bytes,
+                   'd2h_bytes_per_step': B * (theta_bytes + 8), 'call': 'Batch.value_and_grad_host -> eincm_batch_value_and_grad_host'},
+           'kernels_ms_per_launch': {k: round(v, 5) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
+           'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                        'traffic': None, 'algorithmic_bytes_per_launch': B * alg[dom], 'kernel_ms': kern_ms[dom],
+                        'kernel_share_of_step': kern_ms[dom] / sum(kern_ms.values()), 'peak_source': peak_src},
+           'roofline_eval': {'bound': 'hbm', 'achieved': B * alg['eval'] / (ms_step * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                             'frac': B * alg['eval'] / (ms_step * 1e-3) / 1e9 / peak, 'algorithmic_bytes_per_eval': alg['eval']},
+           'l2': f'{B} windows x ~{(N * 16 + (3 * R + 6) * H * W * 8) / 1e6:.0f} MB = {B * (N * 16 + (3 * R + 6) * H * W * 8) / 1e6:.0f} MB working set'}
+    if cpu:
+        fn, kind, cores, label = cpu_eval_factory()
+        worst_l, worst_g = 0.0, 0.0
+        for k in range(min(n_check, B)):
+            l_ref, g_ref = fn(th_h[k], wins[k % len(wins)], dict(hpd, gamma=0.0), 1)
+            worst_l = max(worst_l, abs(losses_h[k] - l_ref) / abs(l_ref))
+            worst_g = max(worst_g, float(np.abs(grads_h[k] - g_ref).max() / np.abs(g_ref).max()))
+        res['check'] = {'windows': min(n_check, B), 'loss_rel': worst_l, 'grad_rel_inf': worst_g, 'tolerance': {'loss_rel': 1e-5, 'grad_rel_inf': 1e-4},
+                        'ok': bool(worst_l <= 1e-5 and worst_g <= 1e-4), 'checker': label}
+        # CPU restatement on the same windows: whole windows, as many evaluations as fit the budget
+        t0 = time.perf_counter()
+        n_cpu = 0
+        while n_cpu < 4 or (time.perf_counter() - t0 < cpu_budget and n_cpu < 4000):
+            k = n_cpu % min(B, len(wins))
+            fn(th_h[k], wins[k], dict(hpd, gamma=0.0), 1)
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        res['cpu_baseline'] = {'value': n_cpu * N / dt / 1e9, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                               'sample': f'{n_cpu} objective+grad evals of complete windows ({N} events each), {label}'}
+    batch.close()
+    for p in plans:
+        p.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_batched(args):
+    """bench.py --workload mvsec_dt1|mvsec_dt4|mvsec_raw_dt4 [--dense] [--batch B]: the batched evaluation as the main line."""
+    import torch
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    t0 = time.time()
+    r = batched_measure(args.workload, args.batch, args.theta, args.dense, args.steps, args.warmup, args.min_time_s, cpu=not args.no_cpu_baseline,
+                        cpu_budget=args.cpu_budget)
+    clocks = sampler.stop(t0, time.time())
+    line = {'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPE,
+            'data': 'synthetic', 'config': {'workload': r['workload'], 'l2': r['l2'], 'step': 'one objective+gradient evaluation of every window of the batch: five launches (four for dense theta)'},
+            'clocks': clocks, 'e2e': r['e2e'], 'gpu_launches': r['gpu_launches_per_step'] * args.steps, 'roofline': r['roofline'],
+            'roofline_eval': r['roofline_eval'], 'kernels_ms_per_launch': r['kernels_ms_per_launch'], 'cpu_baseline': r.get('cpu_baseline'),
+            'check': r.get('check'), 'us_per_window': r['us_per_window'], 'evals_per_s': r['evals_per_s']}
+    print(json.dumps(line))
+    if (r.get('check') or {}).get('ok') is False:
+        sys.exit(3)
 
 # --------------------------------------------------------------------------------------------------------------
 # reference arm: CPU restatement of the reference on the host cores
@@ -612,6 +740,18 @@ def run_own(args):
     if world == 1:
         edge = time_edge_maps(H, W, R, cpu=not args.no_cpu_baseline)
 
+    # ---- MVSEC-shaped windows (BASELINE.json configs[2]): batches of windows per launch, tile and dense theta ----------------------
+    mvsec = None
+    if world == 1 and not args.no_mvsec:
+        for p in plans:
+            p.close()
+        plans = []
+        torch.cuda.empty_cache()
+        mvsec = {}
+        for name, wl, Bn, dn in (('dt4_tile16_b512', 'mvsec_dt4', 512, False), ('dt1_tile16_b512', 'mvsec_dt1', 512, False),
+                                 ('dt4_dense_b64', 'mvsec_dt4', 64, True), ('dt1_dense_b64', 'mvsec_dt1', 64, True)):
+            mvsec[name] = batched_measure(wl, Bn, 16, dn, steps=5, warmup=3, min_time_s=0.2, cpu=not args.no_cpu_baseline, cpu_budget=3.0)
+
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -646,6 +786,7 @@ def run_own(args):
         'kernels_ms_per_launch': {k: round(v, 5) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
         'cpu_baseline': cpu,
         'check': check,
+        'mvsec_batched': mvsec,
         'exact_f64': exact,
         'timed_blocks': {'blocks': len(block_ms), 'steps_per_block': args.steps, 'ms_median': ms_total, 'ms_min': float(min(block_ms)),
                          'ms_max': float(max(block_ms)), 'ms_total': float(sum(block_ms))},
@@ -731,6 +872,9 @@ def main():
     ap.add_argument('--windows', type=int, default=4, help='distinct windows per GPU cycled round-robin')
     ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU work for the CPU baseline / reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--batch', type=int, default=512, help='windows per launch for the batched (MVSEC) workloads')
+    ap.add_argument('--dense', action='store_true', help='dense per-pixel theta (H x W x 2) instead of theta x theta tiles (batched workloads)')
+    ap.add_argument('--no-mvsec', action='store_true', help='skip the MVSEC-shaped batched sub-lines of the default run')
     ap.add_argument('--no-exact', action='store_true', help='skip the EINCM_FLAG_EXACT_F64 sub-line')
     ap.add_argument('--min-time-s', type=float, default=0.5, help='device time to accumulate over repeated blocks of --steps steps')
     ap.add_argument('--group-sequences', action='store_true', help='windows/s with the sequences of a GPU in one evaluation group even when host cores are plentiful')
@@ -744,6 +888,8 @@ def main():
     if args.impl == 'reference':
         args.cpu_budget = max(args.cpu_budget, 60.0)
         run_reference(args)
+    elif args.workload.startswith('mvsec') or args.workload in ('ecd', 'tiny'):
+        run_batched(args)
     else:
         run_own(args)
 

@@ -20,6 +20,8 @@ struct eincm_batch {
     double *d_theta = nullptr, *d_grad = nullptr, *d_loss = nullptr, *h_stage = nullptr;
     size_t stage_n = 0;                             // doubles per window the staging buffers are sized for
     int64_t launch_count = 0;
+    bool timing = false;                            // bracket every launch with CUDA events (measurement hook)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[5];   // per kernel: splat, image stats, image grad, backward, theta grad
     std::string error;
 };
 
@@ -41,6 +43,47 @@ int bfail(eincm_batch* b, int code, const char* fmt, ...) {
                          cudaGetErrorString(e_));                                                              \
     } while (0)
 }  // namespace
+
+namespace {
+struct BatchSpan {
+    eincm_batch* b; int k; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    BatchSpan(eincm_batch* b_, int k_, cudaStream_t st_) : b(b_), k(k_), st(st_) {
+        if (!b->timing) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, st);
+    }
+    ~BatchSpan() {
+        if (e0 == nullptr) return;
+        cudaEventRecord(e1, st);
+        b->spans[k].push_back({e0, e1});
+    }
+};
+}  // namespace
+
+int eincm_batch_set_timing(eincm_batch* batch, int enabled) {
+    if (!batch) return EINCM_EINVAL;
+    batch->timing = enabled != 0;
+    return EINCM_OK;
+}
+
+// synchronous: total milliseconds and launches per kernel (k_splat_tile_b, k_image_stats_b, k_image_grad_b, k_backward_tile_b,
+// k_theta_grad_b) since the last call
+int eincm_batch_get_timing(eincm_batch* batch, double* ms_out /* [5] */, int64_t* launches_out /* [5] */) {
+    if (!batch || !ms_out || !launches_out) return EINCM_EINVAL;
+    BCU(cudaSetDevice(batch->device));
+    BCU(cudaDeviceSynchronize());
+    for (int k = 0; k < 5; ++k) {
+        ms_out[k] = 0.0; launches_out[k] = 0;
+        for (auto& sp : batch->spans[k]) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, sp.first, sp.second) == cudaSuccess) ms_out[k] += t;
+            launches_out[k] += 1;
+            cudaEventDestroy(sp.first); cudaEventDestroy(sp.second);
+        }
+        batch->spans[k].clear();
+    }
+    return EINCM_OK;
+}
 
 const char* eincm_batch_last_error(const eincm_batch* batch) { return batch ? batch->error.c_str() : ""; }
 int64_t eincm_batch_launch_count(const eincm_batch* batch) { return batch ? batch->launch_count : 0; }
@@ -210,26 +253,26 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
     const int rb = std::min(R, kMaxRB);
     const dim3 grid_ev(max_chunks, B);
     cudaError_t le = cudaSuccess;
-#define LB(WR, RBV) le = launch_pdl(k_splat_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(uint32_t), st, d_sa)
+#define LB(WR, RBV) { BatchSpan sp_(batch, 0, st); le = launch_pdl(k_splat_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(uint32_t), st, d_sa); }
     if (batch->wrap) { switch (rb) { case 1: LB(true, 1); break; case 2: LB(true, 2); break; case 3: LB(true, 3); break; default: LB(true, 4); } }
     else { switch (rb) { case 1: LB(false, 1); break; case 2: LB(false, 2); break; case 3: LB(false, 3); break; default: LB(false, 4); } }
 #undef LB
     if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_splat_tile_b: %s", cudaGetErrorString(le));
-    le = launch_pdl(k_image_stats_b, dim3((image_stats_items(H, W, R) + kS2Warps - 1) / kS2Warps, B), dim3(kS2NT), 0, st, d_ia);
+    { BatchSpan sp_(batch, 1, st); le = launch_pdl(k_image_stats_b, dim3((image_stats_items(H, W, R) + kS2Warps - 1) / kS2Warps, B), dim3(kS2NT), 0, st, d_ia); }
     if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_image_stats_b: %s", cudaGetErrorString(le));
     {
         const int per = std::max(8, std::min((int)((HW + 1023) / 1024), (p0->sm_count * 8 + B - 1) / B));
-        le = launch_pdl(k_image_grad_b, dim3(per, B), dim3(256), 0, st, d_ga);
+        { BatchSpan sp_(batch, 2, st); le = launch_pdl(k_image_grad_b, dim3(per, B), dim3(256), 0, st, d_ga); }
         if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_image_grad_b: %s", cudaGetErrorString(le));
     }
-#define LB(WR, RBV) le = launch_pdl(k_backward_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(float), st, d_ba)
+#define LB(WR, RBV) { BatchSpan sp_(batch, 3, st); le = launch_pdl(k_backward_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(float), st, d_ba); }
     if (batch->wrap) { switch (rb) { case 1: LB(true, 1); break; case 2: LB(true, 2); break; case 3: LB(true, 3); break; default: LB(true, 4); } }
     else { switch (rb) { case 1: LB(false, 1); break; case 2: LB(false, 2); break; case 3: LB(false, 3); break; default: LB(false, 4); } }
 #undef LB
     if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_backward_tile_b: %s", cudaGetErrorString(le));
     batch->launch_count += 4;
     if (!dense) {
-        le = launch_pdl(k_theta_grad_b, dim3((n_items + kTgWarps - 1) / kTgWarps, B), dim3(kTgWarps * 32), 0, st, d_ta);
+        { BatchSpan sp_(batch, 4, st); le = launch_pdl(k_theta_grad_b, dim3((n_items + kTgWarps - 1) / kTgWarps, B), dim3(kTgWarps * 32), 0, st, d_ta); }
         if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_theta_grad_b: %s", cudaGetErrorString(le));
         batch->launch_count += 1;
     }

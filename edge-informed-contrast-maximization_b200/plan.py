@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = (
     'eincm_nlm_workspace_bytes', 'eincm_nlm_denoise',
     'eincm_rectify_workspace_bytes', 'eincm_rectify_events', 'eincm_normalize_times', 'eincm_window_event_range',
     'eincm_batch_create', 'eincm_batch_destroy', 'eincm_batch_last_error', 'eincm_batch_value_and_grad', 'eincm_batch_value_and_grad_host',
-    'eincm_batch_launch_count',
+    'eincm_batch_launch_count', 'eincm_batch_set_timing', 'eincm_batch_get_timing',
 )
 
 
@@ -177,6 +177,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_batch_value_and_grad': (i32, [vp, C.POINTER(vp), i32, i32, hp, C.POINTER(vp), C.POINTER(vp), vp]),
         'eincm_batch_value_and_grad_host': (i32, [vp, C.POINTER(vp), i32, i32, hp, C.POINTER(dbl), C.POINTER(vp), vp]),
         'eincm_batch_launch_count': (i64, [vp]),
+        'eincm_batch_set_timing': (i32, [vp, i32]),
+        'eincm_batch_get_timing': (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -306,6 +308,17 @@ class Batch:
 
     def launch_count(self) -> int:
         return int(self.lib.eincm_batch_launch_count(self._h))
+
+    KERNELS = ('k_splat', 'k_image_stats', 'k_image_grad', 'k_backward_events', 'k_theta_grad')
+
+    def set_timing(self, enabled: bool):
+        self._check(self.lib.eincm_batch_set_timing(self._h, 1 if enabled else 0))
+
+    def get_timing(self) -> Dict[str, Tuple[float, int]]:
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int64 * 5)()
+        self._check(self.lib.eincm_batch_get_timing(self._h, ms, cnt))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNELS) if cnt[i] > 0}
 
 
 class _DevView:

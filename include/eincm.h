@@ -160,6 +160,10 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
 int eincm_batch_value_and_grad_host(eincm_batch* batch, const double* const* thetas_host, int h, int w, const eincm_hparams* hp,
                                     double* losses_out_host, double* const* grads_out_host, void* cuda_stream);
 int64_t eincm_batch_launch_count(const eincm_batch* batch);   /* kernels launched by this batch since creation */
+/* measurement hooks: CUDA events around every launch of the batch; get_timing (synchronous) returns the milliseconds and launches per
+ * kernel - splat, image statistics, image gradient, backward, theta gradient - since the last call */
+int eincm_batch_set_timing(eincm_batch* batch, int enabled);
+int eincm_batch_get_timing(eincm_batch* batch, double* ms_out /* [5] */, int64_t* launches_out /* [5] */);
 
 /* ---- native optimizers: what jaxopt's ScipyMinimize(method='BFGS').run / ScipyBoundedMinimize(method='L-BFGS-B').run do with
  * the objective (reference src/eincm/solver.py:165-183, :209-216, :325-335), without returning to Python between evaluations.
