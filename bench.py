@@ -585,41 +585,37 @@ def run_own(args):
     if args.solve_windows > 0:
         from eincm_b200 import losses, solver as SV
 
-        def run_solves(backend, n_threads):
-            """n_threads independent sequences per GPU, each: warm-up solve, then args.solve_windows chained windows."""
-            # fewer host cores than driving threads (e.g. 8 GPUs x 4 sequences on 16 cores): the sequences of a GPU join an evaluation
-            # group - one thread launches the evaluations of all of them in a burst, the others sleep (include/eincm.h)
-            # (with cores to spare the group does not pay inside this bench: 10.6 - 11.8 windows/s grouped against 12.9 - 18.7 independent
-            # on one B200 with 4 sequences; --group-sequences forces it)
-            grouped = backend == 'native' and n_threads > 1 and (args.group_sequences or len(os.sched_getaffinity(0)) // world < n_threads + 1)
-            objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3))
+        def run_solves(backend, n_threads, wait, seqs):
+            """n_threads independent sequences per GPU, each: warm-up solve of its first window, then args.solve_windows chained
+            windows (handover prior from the previous window).  wait = 'block': the host entry points sleep on a blocking CUDA
+            event (EINCM_FLAG_BLOCKING_SYNC) instead of spinning, so the sequences per GPU do not depend on the host cores per rank."""
+            flags = P.FLAG_BLOCKING_SYNC if wait == 'block' else 0
+            objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3), flags=flags)
                     for _ in range(n_threads)]
-            group = P.Group() if grouped else None
-            for o in objs:
-                if group is not None:
-                    o.plan.set_group(group)
             sols = [SV.MultipleLevelEINCMSolver(o, backend=backend, own_stream=(backend == 'native')) for o in objs]
-            for t, sol in enumerate(sols):
-                sol.set_datasample(*wins[t % nw].args())
-                sol.solve()                            # warm-up solve (first sample: no handover)
             finals = [None] * n_threads
 
-            def work(t):
+            def work(t, first, last):
                 torch.cuda.set_device(local_rank)
-                for k in range(args.solve_windows):
-                    sols[t].set_datasample(*wins[(t + k + 1) % nw].args())
+                for k in range(first, last):
+                    sols[t].set_datasample(*seqs[t][k].args())
                     finals[t] = sols[t].solve()
 
+            n_rep = 3 if backend == 'native' else 1
             n_win = n_threads * args.solve_windows
-            runs = []                                  # the timed region is short (~0.5 s) and host scheduling noise is visible: median of 3
-            for rep in range(3 if backend == 'native' else 1):
+            runs = []
+            for rep in range(n_rep):
+                # every repeat starts from scratch: first window of the sequence untimed (no prior), then the chained windows
+                for t, sol in enumerate(sols):
+                    sols[t] = SV.MultipleLevelEINCMSolver(objs[t], backend=backend, own_stream=(backend == 'native'))
+                    work(t, 0, 1)
                 barrier()
                 n0 = sum(o.n_evals for o in objs)
                 t0 = time.perf_counter()
                 if n_threads == 1:
-                    work(0)
+                    work(0, 1, 1 + args.solve_windows)
                 else:
-                    ths = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+                    ths = [threading.Thread(target=work, args=(t, 1, 1 + args.solve_windows)) for t in range(n_threads)]
                     for th in ths:
                         th.start()
                     for th in ths:
@@ -627,27 +623,31 @@ def run_own(args):
                 torch.cuda.synchronize()
                 runs.append((max_over_ranks(time.perf_counter() - t0), sum(o.n_evals for o in objs) - n0))
             dt, n_ev = sorted(runs)[len(runs) // 2]
-            res = {'value': world * n_win / dt, 'unit': 'windows/s', 'repeats_windows_per_s': [round(world * n_win / r[0], 2) for r in runs],
-                   'repeats_evals_per_window': [round(r[1] / n_win, 1) for r in runs], 'sequences_per_gpu': n_threads, 'windows_per_sequence': args.solve_windows,
-                   'ms_per_window': dt / args.solve_windows * 1e3, 'evals_per_window': n_ev / n_win,
-                   'final_loss': finals[0]['theta_opt_state_pyr']['pyr_lvl_0'].fun_val, 'host_threads': 'evaluation group (one launching thread per GPU)' if grouped else 'independent (one spinning thread per sequence)'}
+            rates = [world * n_win / r[0] for r in runs]
+            res = {'value': world * n_win / dt, 'unit': 'windows/s', 'repeats_windows_per_s': [round(x, 2) for x in rates],
+                   'repeat_spread': (max(rates) - min(rates)) / float(np.median(rates)),
+                   'repeats_evals_per_window': [round(r[1] / n_win, 1) for r in runs], 'sequences_per_gpu': n_threads,
+                   'windows_per_sequence': args.solve_windows, 'ms_per_window': dt / args.solve_windows * 1e3, 'evals_per_window': n_ev / n_win,
+                   'final_loss': finals[0]['theta_opt_state_pyr']['pyr_lvl_0'].fun_val,
+                   'host_wait': 'sleeping on a blocking CUDA event (EINCM_FLAG_BLOCKING_SYNC)' if wait == 'block' else 'spinning on mapped pinned memory'}
             for o in objs:
                 o.close()
-            if group is not None:
-                group.close()
             return res
 
-        # Sequences per GPU: four when every driving thread can have a core of its own (each spins on its evaluation), fewer on hosts
-        # with fewer cores per rank - one sequence alone already keeps a B200 > 90 % busy (profiles/solve_breakdown.py: 15 windows/s),
-        # while 4 sequences per GPU squeezed onto 2 cores per rank measured 4.5 windows/s per GPU on 8 GPUs (profiles/r1_bench_8gpu.json).
-        cores_per_rank = max(1, len(os.sched_getaffinity(0)) // world)
-        n_seq = max(1, min(4, nw, cores_per_rank - 1)) if not args.group_sequences else min(4, nw)
-        solve = run_solves('native', n_seq)
+        # synthetic SEQUENCES: same scene, slowly drifting flow, fresh events (synth.make_sequence) - the handover prior of window k
+        # is the solution of window k - 1, as on consecutive DSEC windows
+        n_seq = max(1, args.solve_seqs)
+        seqs = [synth.make_sequence(args.workload, 1 + args.solve_windows, seed=100 * rank + t, n_events=args.events) for t in range(n_seq)]
+        solve = run_solves('native', n_seq, args.solve_wait, seqs)
         solve['note'] = ('eincm_b200.solver.MultipleLevelEINCMSolver (mirror of reference src/eincm/solver.py, main.yaml defaults: 5 levels, '
                          'BFGS 40/28/19/11/8 iterations, retries, handover solved at levels 1/0); optimizers native '
                          '(eincm_minimize_bfgs_host / eincm_minimize_handover_host), one host thread and one CUDA stream per '
-                         'sequence, windows of a sequence chained by handover, set_datasample (staging) inside the timed region')
-        solve['scipy_single_sequence'] = run_solves('scipy', 1)
+                         'sequence, windows of a sequence chained by handover, set_datasample (staging) inside the timed region; '
+                         'sequences: same scene, truth flow drifting 8 % of the flow magnitude per window')
+        if args.solve_compare and world == 1:
+            solve['spinning'] = run_solves('native', n_seq, 'spin' if args.solve_wait == 'block' else 'block', seqs)
+            solve['scipy_single_sequence'] = run_solves('scipy', 1, args.solve_wait, seqs[:1])
+        del seqs
 
     # ---- stateless: stage the whole window from pinned host memory every step ---------------------------------
     pin = []
@@ -877,8 +877,10 @@ def main():
     ap.add_argument('--no-mvsec', action='store_true', help='skip the MVSEC-shaped batched sub-lines of the default run')
     ap.add_argument('--no-exact', action='store_true', help='skip the EINCM_FLAG_EXACT_F64 sub-line')
     ap.add_argument('--min-time-s', type=float, default=0.5, help='device time to accumulate over repeated blocks of --steps steps')
-    ap.add_argument('--group-sequences', action='store_true', help='windows/s with the sequences of a GPU in one evaluation group even when host cores are plentiful')
-    ap.add_argument('--solve-windows', type=int, default=2, help='complete multi-level solves per GPU for the windows/s figure (0: skip)')
+    ap.add_argument('--solve-seqs', type=int, default=3, help='sequences solved concurrently per GPU for the windows/s figure (3: the spinning driver threads of 8 ranks fit a 32-core box)')
+    ap.add_argument('--solve-wait', default='spin', choices=['block', 'spin'], help='how the host entry points wait for an evaluation')
+    ap.add_argument('--solve-compare', action='store_true', help='also measure the other wait mode and the scipy-driven solve (N = 1)')
+    ap.add_argument('--solve-windows', type=int, default=3, help='complete multi-level solves per GPU for the windows/s figure (0: skip)')
     ap.add_argument('--event-split', action='store_true', help='ONE window split over the GPUs (configs[4]) instead of windows sharded')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

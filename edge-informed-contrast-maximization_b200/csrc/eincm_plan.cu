@@ -1091,8 +1091,7 @@ int eincm_minimize_handover_host(eincm_plan* plan, double* alpha_inout_host, dou
     eincm_opt::Objective fun = [&](const double* a, double* f, double* g) -> int {
         const int rc = eincm_handover_value_and_grad(plan, *a, plan->prev_stage, plan->theta_stage, h, w, hp, plan->out_stage, plan->out_stage + 1, st);
         if (rc) return rc;
-        if (cudaMemcpyAsync(h_out, plan->out_stage, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess)
+        if (cudaMemcpyAsync(h_out, plan->out_stage, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess || host_wait(plan, st) != EINCM_OK)
             return fail(plan, EINCM_ECUDA, "copy of the handover result failed");
         *f = h_out[0]; *g = h_out[1];
         return EINCM_OK;

@@ -75,17 +75,22 @@ def _box_blur3(img: np.ndarray) -> np.ndarray:
 
 def make_window(H: int, W: int, N: int, edge_ts=(0.0, 0.5, 1.0), seed: int = 0, n_segments: int = 200,
                 flow_mag: float = 20.0, truth_tiles: Tuple[int, int] = (2, 2), noise_frac: float = 0.1,
-                hparams: Optional[Dict[str, float]] = None) -> Window:
+                hparams: Optional[Dict[str, float]] = None, scene_seed: Optional[int] = None,
+                truth_theta: Optional[np.ndarray] = None) -> Window:
+    """``scene_seed`` / ``truth_theta``: windows of one SEQUENCE share the scene (line segments, drawn from ``scene_seed``) and are
+    given a slowly varying truth flow, while events and noise are fresh per window (``seed``) - see ``make_sequence``."""
     rng = np.random.default_rng(seed)
+    rs = rng if scene_seed is None else np.random.default_rng(scene_seed)
     edge_ts = np.asarray(edge_ts, dtype=np.float64)
     R = len(edge_ts)
-    truth_theta = rng.uniform(-flow_mag, flow_mag, size=(truth_tiles[0], truth_tiles[1], 2))
+    drawn = rs.uniform(-flow_mag, flow_mag, size=(truth_tiles[0], truth_tiles[1], 2))
+    truth_theta = drawn if truth_theta is None else np.asarray(truth_theta, dtype=np.float64)
     flow = _bilinear_field(truth_theta, H, W)                      # (H, W, 2) px / window
 
     # edge points: dense samples along random segments (sub-pixel positions at t = 0)
-    seg_len = rng.uniform(0.05, 0.4, size=n_segments) * min(H, W)
-    cx = rng.uniform(0, W, size=n_segments); cy = rng.uniform(0, H, size=n_segments)
-    ang = rng.uniform(0, np.pi, size=n_segments)
+    seg_len = rs.uniform(0.05, 0.4, size=n_segments) * min(H, W)
+    cx = rs.uniform(0, W, size=n_segments); cy = rs.uniform(0, H, size=n_segments)
+    ang = rs.uniform(0, np.pi, size=n_segments)
     pts_per_seg = np.maximum(4, (seg_len * 2).astype(int))
     seg_id = np.repeat(np.arange(n_segments), pts_per_seg)
     u = rng.uniform(-0.5, 0.5, size=seg_id.size)
@@ -123,14 +128,28 @@ def make_window(H: int, W: int, N: int, edge_ts=(0.0, 0.5, 1.0), seed: int = 0, 
                   truth_theta=truth_theta, hparams=dict(hparams or {}))
 
 
-def make_workload(name: str, seed: int = 0, n_events: Optional[int] = None) -> Window:
+def make_workload(name: str, seed: int = 0, n_events: Optional[int] = None, scene_seed: Optional[int] = None,
+                  truth_theta: Optional[np.ndarray] = None) -> Window:
     cfg = dict(WORKLOADS[name])
     N = n_events if n_events is not None else cfg['N']
     hp = dict(alpha=cfg['alpha'], beta=cfg['beta'], gamma=cfg['gamma'], delta=0.0)
     n_seg = max(20, int(200 * (cfg['H'] * cfg['W']) / (480 * 640)))
     mag = 20.0 * min(1.0, cfg['W'] / 640 + 0.25)
     return make_window(cfg['H'], cfg['W'], N, cfg['edge_ts'], seed=seed, n_segments=n_seg,
-                       flow_mag=mag, hparams=hp)
+                       flow_mag=mag, hparams=hp, scene_seed=scene_seed, truth_theta=truth_theta)
+
+
+def make_sequence(name: str, n_windows: int, seed: int = 0, n_events: Optional[int] = None, drift: float = 0.08):
+    """``n_windows`` consecutive windows of one synthetic SEQUENCE: the same scene, a truth flow that drifts slowly from window to
+    window (a random direction per truth tile, ``drift`` x the flow magnitude per window: consecutive DSEC windows have similar
+    flow, which is what the reference's handover prior - src/eincm/solver.py:302-347 - relies on), fresh events and noise."""
+    cfg = WORKLOADS[name]
+    mag = 20.0 * min(1.0, cfg['W'] / 640 + 0.25)
+    rs = np.random.default_rng(10_000 + seed)
+    theta0 = rs.uniform(-mag, mag, size=(2, 2, 2))
+    step = rs.normal(0.0, 1.0, size=(2, 2, 2)) * drift * mag
+    return [make_workload(name, seed=1000 * seed + k + 1, n_events=n_events, scene_seed=20_000 + seed, truth_theta=theta0 + k * step)
+            for k in range(n_windows)]
 
 
 def theta_test_points(win: Window, shape: Tuple[int, int], seed: int = 0) -> Dict[str, np.ndarray]:
