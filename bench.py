@@ -254,6 +254,56 @@ def run_batched(args):
     if (r.get('check') or {}).get('ok') is False:
         sys.exit(3)
 
+
+def event_split_measure(world, rank, local_rank, total_events, steps=5, warmup=3, theta=16):
+    """BASELINE.json configs[4]: ONE very large window (1280x720) whose events are split over the ranks (strong scaling: the same
+    total at every N).  Every rank synthesises ITS share of the events on the shared scene (same edge images, own events), so
+    the union over the ranks is one window of `total_events` events.  Two forms (eincm_b200.parallel.EventSplitObjective): NCCL
+    all-reduce of the float64 images, and the splat fused with the reduction over peer memory (NVLink reductions into every
+    rank's fixed-point image)."""
+    import torch
+    import torch.distributed as dist
+    from eincm_b200 import parallel as PAR, plan as P, synth
+    n_local = total_events // world
+    win = synth.make_workload('large', seed=500 + rank, n_events=n_local, scene_seed=4242)
+    H, W = win.sensor_size
+    R = len(win.edge_ts)
+    hpd = win.hparams
+    shape = (theta, theta)
+    th = torch.from_numpy(synth.theta_test_points(win, shape, seed=0)['perturbed']).cuda()
+    if world > 1:
+        dist.broadcast(th, 0)                               # one theta for all ranks
+    res = {'workload': f'large: ONE window of {W}x{H}, N={n_local * world} events split over {world} GPU(s), R={R}, theta {theta}x{theta}x2',
+           'scaling': 'strong', 'unit': UNIT}
+    for mode, p2p in (('nccl_allreduce_of_images', False), ('peer_fused_splat', True)):
+        plan = P.Plan((H, W), max_events=n_local, max_refs=max(R, 3), flags=P.FLAG_EVENT_SPLIT)
+        obj = PAR.EventSplitObjective(plan, lambda lvl: P.make_hparams(hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], lvl), p2p=p2p)
+        obj.set_datasample(win.xs, win.ys, win.ts, win.edges, win.edge_ts, need_mask=False)
+        loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+        grad = torch.zeros_like(th)
+        for _ in range(warmup):
+            obj.value_and_grad(th, 0, loss, grad)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = obj.collective_bytes
+        e0.record()
+        for _ in range(steps):
+            obj.value_and_grad(th, 0, loss, grad)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item()) / steps
+        # the objective must be identical on every rank (same complete images everywhere)
+        lo = torch.stack([loss.detach().clone().reshape(()), -loss.detach().clone().reshape(())])
+        dist.all_reduce(lo, op=dist.ReduceOp.MAX)
+        res[mode] = {'value': n_local * world / (ms * 1e-3) / 1e9, 'ms_per_eval': ms, 'loss': float(loss.item()),
+                     'loss_identical_on_all_ranks': bool(float(lo[0]) == float(loss.item()) and -float(lo[1]) == float(loss.item())),
+                     'collective_bytes_per_eval_per_rank': (obj.collective_bytes - c0) // steps}
+        plan.close()
+        torch.cuda.empty_cache()
+    return res
+
 # --------------------------------------------------------------------------------------------------------------
 # reference arm: CPU restatement of the reference on the host cores
 # --------------------------------------------------------------------------------------------------------------
@@ -671,8 +721,21 @@ def run_own(args):
     sl_value = world * N * n_sl / sl_s / 1e9
     window_bytes = N * 12 + R * H * W * 8 + R * 8
 
+    # ---- event split of ONE very large window over the ranks (BASELINE.json configs[4]); at N = 1 the same window on one GPU ------
+    esplit = None
+    if not args.no_event_split:
+        if world == 1 and not dist.is_initialized():
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29533')
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', local_rank))
+            finally:
+                sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+        esplit = event_split_measure(world, rank, local_rank, args.split_events)
+
     if rank != 0:
-        if world > 1:
+        if dist.is_initialized():
             dist.destroy_process_group()
         return
 
@@ -787,12 +850,13 @@ def run_own(args):
         'cpu_baseline': cpu,
         'check': check,
         'mvsec_batched': mvsec,
+        'event_split': esplit,
         'exact_f64': exact,
         'timed_blocks': {'blocks': len(block_ms), 'steps_per_block': args.steps, 'ms_median': ms_total, 'ms_min': float(min(block_ms)),
                          'ms_max': float(max(block_ms)), 'ms_total': float(sum(block_ms))},
     }
     print(json.dumps(line))
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
     if check.get('ok') is False:
         sys.exit(3)
@@ -874,6 +938,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--batch', type=int, default=512, help='windows per launch for the batched (MVSEC) workloads')
     ap.add_argument('--dense', action='store_true', help='dense per-pixel theta (H x W x 2) instead of theta x theta tiles (batched workloads)')
+    ap.add_argument('--no-event-split', action='store_true', help='skip the event-split measurement of one very large window')
+    ap.add_argument('--split-events', type=int, default=50_000_000, help='events of the large window that is split over the GPUs')
     ap.add_argument('--no-mvsec', action='store_true', help='skip the MVSEC-shaped batched sub-lines of the default run')
     ap.add_argument('--no-exact', action='store_true', help='skip the EINCM_FLAG_EXACT_F64 sub-line')
     ap.add_argument('--min-time-s', type=float, default=0.5, help='device time to accumulate over repeated blocks of --steps steps')
