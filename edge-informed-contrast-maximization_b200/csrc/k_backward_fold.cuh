@@ -125,7 +125,7 @@ __device__ __forceinline__ void backward_fold_body(const BackwardFoldArgs& A, fl
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ Window swin[RB];
     __shared__ CotCoefF scot[RB];
-    __shared__ float s_wy[kSortTile][4], s_wx[kSortTile][4];      // resize weights of the tile's rows / columns on taps base + 0..2
+    __shared__ __align__(16) float s_wy[kSortTile][4], s_wx[kSortTile][4];      // resize weights of the tile's rows / columns on taps base + 0..2
     __shared__ int s_base[2];
     __shared__ double s_red[8];
     __shared__ bool s_last;
