@@ -220,13 +220,14 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
             s.T = T; s.H = H; s.W = W; s.R = R; s.tref = p->tref; s.dst.n = 1; s.dst.p[0] = p->iwe_fix; s.chunk_win = p->chunk_win;
             ImageStatsArgs& i = ia[k];
             i.rec = nullptr; i.e32 = p->e32; i.fix = p->iwe_fix; i.edges = p->edges; i.iwe = p->iwe; i.adj32 = p->adj32;
-            i.part = p->part; i.sc = p->sc; i.loss_out = loss_out[k];
+            i.part = p->part; i.tail_here = 0; i.sc = p->sc; i.loss_out = loss_out[k];
             i.zero_buf = Gk; i.n_zero = (int)(HW * 2);
             i.zero_buf2 = dense ? nullptr : grad_out[k]; i.n_zero2 = dense ? 0 : h * w * 2;
             i.H = H; i.W = W; i.R = R; i.alpha = hp->alpha; i.beta = hp->beta; i.gamma = hp->gamma; i.use_tv = 0;
             ImageGradArgs& g = ga[k];
             g.fix = p->iwe_fix; g.edges = p->edges; g.iwe = p->iwe; g.adj32 = p->adj32; g.sc = p->sc; g.dldi = nullptr; g.dldi32 = p->dldi32;
             g.HW = (int)HW; g.R = R; g.want_grad = 1;
+            g.publish = 1; g.loss_out = loss_out[k]; g.alpha = hp->alpha; g.beta = hp->beta; g.gamma = hp->gamma; g.use_tv = 0;
             BackwardTileArgs& b = ba[k];
             b.ev_xy = p->ev_xy; b.ev_t = p->ev_t; b.chunks = p->chunks; b.n_chunks_dev = p->totals + 1; b.T = T; b.H = H; b.W = W; b.R = R;
             b.tref = p->tref; b.dldi32 = p->dldi32; b.chunk_win = p->chunk_win; b.G = Gk;
@@ -258,11 +259,11 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
     else { switch (rb) { case 1: LB(false, 1); break; case 2: LB(false, 2); break; case 3: LB(false, 3); break; default: LB(false, 4); } }
 #undef LB
     if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_splat_tile_b: %s", cudaGetErrorString(le));
-    { BatchSpan sp_(batch, 1, st); le = launch_pdl(k_image_stats_b, dim3((image_stats_items(H, W, R) + kS2Warps - 1) / kS2Warps, B), dim3(kS2NT), 0, st, d_ia); }
+    { BatchSpan sp_(batch, 1, st); le = launch_pdl(k_image_stats_b, dim3(R * image_stats_ctas(H, W), B), dim3(kS2NT), 0, st, d_ia); }
     if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_image_stats_b: %s", cudaGetErrorString(le));
     {
         const int per = std::max(8, std::min((int)((HW + 1023) / 1024), (p0->sm_count * 8 + B - 1) / B));
-        { BatchSpan sp_(batch, 2, st); le = launch_pdl(k_image_grad_b, dim3(per, B), dim3(256), 0, st, d_ga); }
+        { BatchSpan sp_(batch, 2, st); le = launch_pdl(k_image_grad_b, dim3(per + 1, B), dim3(256), 0, st, d_ga); }
         if (le != cudaSuccess) return bfail(batch, EINCM_ECUDA, "launch k_image_grad_b: %s", cudaGetErrorString(le));
     }
 #define LB(WR, RBV) { BatchSpan sp_(batch, 3, st); le = launch_pdl(k_backward_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(float), st, d_ba); }

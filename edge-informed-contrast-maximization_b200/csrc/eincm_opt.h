@@ -1,15 +1,14 @@
-// Host-side optimizers that drive the objective natively (no Python between two evaluations): BFGS with a More-Thuente
-// strong-Wolfe line search for the flow parameters, and a projected quasi-Newton method for the scalar, box-bounded handover
-// weight.  They follow the structure and the default parameters of what the reference calls through jaxopt
-// (scipy.optimize.minimize(method='BFGS') / (method='L-BFGS-B'), reference src/eincm/solver.py:165-183):
-//   BFGS     : H0 = I, p = -H g, strong Wolfe line search (c1 = 1e-4, c2 = 0.9, first trial step
-//              min(1, 1.01 * 2 (f_k - f_{k-1}) / g.p), with f_{-1} = f_0 + |g_0| / 2), inverse-Hessian BFGS update,
-//              stop when max|g| <= gtol or after maxiter iterations; a failed line search ends the run with status 2
-//              ("precision loss"), maxiter with status 1 - the codes scipy reports and solver.py:218-239 reacts to.
-//   bounded  : n = 1 case of L-BFGS-B: projected gradient test (pgtol), relative decrease test (factr * eps), direction
-//              -g / B (secant B, steepest descent first), step capped by the bounds, line search c1 = 1e-3, c2 = 0.9.
-// Iterates are not bit-identical to scipy's (different interpolation safeguards); the solves converge to the same minima
-// within the tolerances tested in tests/.
+// Host-side optimizers that drive the objective natively (no Python between two evaluations): scipy's BFGS for the flow parameters
+// and the n = 1 case of L-BFGS-B for the scalar, box-bounded handover weight - what the reference calls through jaxopt
+// (scipy.optimize.minimize(method='BFGS') / (method='L-BFGS-B'), reference src/eincm/solver.py:165-183), restated with scipy's
+// structure, parameters, line-search policy and status codes so that solver.py:218-239 (retries on status != 0) sees the same schedule:
+//   BFGS     : H0 = I, p = -H g, _line_search_wolfe12 = MINPACK-2 dcsrch (c1 = 1e-4, c2 = 0.9, xtol = 1e-14, first trial step
+//              min(1, 1.01 * 2 (f_k - f_{k-1}) / g.p) with f_{-1} = f_0 + |g_0| / 2, <= 100 trials), on failure scalar_search_wolfe2
+//              (bracketing + zoom with cubic / quadratic interpolation, <= 10 + 10 trials); inverse-Hessian BFGS update; stop when
+//              max|g| <= gtol or after maxiter iterations; status 1 maxiter, 2 both searches failed or non-finite objective, 3 NaN.
+//   bounded  : see bounded_scalar.
+// Iterates are not guaranteed bit-identical to scipy's (floating-point summation order of the n^2 products); tests/test_native_opt.py
+// pins minima, statuses and evaluation counts against scipy on closed-form objectives.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -158,40 +157,141 @@ inline double dot8(const double* a, const double* b, int n) {
 inline double max_abs(const double* a, int n) { double m = 0.0; for (int i = 0; i < n; ++i) m = std::max(m, std::fabs(a[i])); return m; }
 inline double norm2(const double* a, int n) { return std::sqrt(dot(a, a, n)); }
 
-// Strong-Wolfe search along p from x; on success x_new, f_new, g_new hold the accepted point.
-inline bool wolfe_search(const Objective& fun, int n, const double* x, const double* p, double f0, const double* g0, double old_f,
-                         double c1, double c2, double stpmax, double first_step, double* x_new, double* f_new, double* g_new,
-                         int& nfev, int& err, int max_trials = 100) {
-    const double derphi0 = dot(g0, p, n);
-    if (!(derphi0 < 0.0)) return false;
-    double stp = first_step;
-    if (!(stp > 0.0)) {
-        stp = 1.0;
-        if (std::isfinite(old_f)) {
-            stp = std::min(1.0, 1.01 * 2.0 * (f0 - old_f) / derphi0);
-            if (stp < 0.0) stp = 1.0;
-        }
-    }
-    stp = std::min(stp, stpmax);
-    LineSearch ls{c1, c2, 1e-14, 1e-100, stpmax};
-    if (ls.start(stp, f0, derphi0) != LineSearch::FG) return false;
-    for (int trial = 0; trial < max_trials; ++trial) {
-        for (int i = 0; i < n; ++i) x_new[i] = x[i] + stp * p[i];
+// phi(a) = f(x + a p) with its derivative phi'(a) = g(x + a p) . p; one objective evaluation per distinct step (scipy memoises
+// value-and-gradient per point the same way, so the evaluation counts agree).  x_new / g_new hold the last evaluated point.
+struct Phi {
+    const Objective& fun; int n; const double* x; const double* p; double* x_new; double* f_new; double* g_new; int& nfev; int& err;
+    bool eval(double a, double* phi, double* dphi) {
+        for (int i = 0; i < n; ++i) x_new[i] = x[i] + a * p[i];
         if ((err = fun(x_new, f_new, g_new)) != 0) return false;
         ++nfev;
-        if (!std::isfinite(*f_new)) { *f_new = std::numeric_limits<double>::infinity(); }
-        const double dphi = dot(g_new, p, n);
-        const double stp_eval = stp;
-        const LineSearch::Task t = ls.update(stp, *f_new, std::isfinite(dphi) ? dphi : 0.0);
+        *phi = *f_new;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += g_new[i] * p[i];
+        *dphi = s;
+        return true;
+    }
+};
+
+// first trial step of scipy's scalar_search_wolfe1 / wolfe2: min(1, 1.01 * 2 (phi0 - old_phi0) / derphi0), 1 when that is negative
+inline double first_trial_step(double f0, double old_f, double derphi0) {
+    double stp = 1.0;
+    if (std::isfinite(old_f) && derphi0 != 0.0) {
+        stp = std::min(1.0, 1.01 * 2.0 * (f0 - old_f) / derphi0);
+        if (stp < 0.0) stp = 1.0;
+    }
+    return stp;
+}
+
+// scipy.optimize._linesearch.scalar_search_wolfe1 (MINPACK-2 dcsrch, xtol as given, at most 100 trials).  On success x_new, f_new,
+// g_new hold the accepted point.  `first_step` > 0 overrides the first trial step (L-BFGS-B).  A non-finite trial step or a
+// WARNING / ERROR task of dcsrch is a failure, as in DCSRCH.__call__ (`accept_warning`: L-BFGS-B's lnsrlb takes the step on a WARNING).
+inline bool wolfe_search(const Objective& fun, int n, const double* x, const double* p, double f0, const double* g0, double old_f,
+                         double c1, double c2, double stpmax, double first_step, double* x_new, double* f_new, double* g_new,
+                         int& nfev, int& err, int max_trials = 100, double xtol = 1e-14, double stpmin = 1e-100, bool accept_warning = false) {
+    const double derphi0 = dot(g0, p, n);
+    if (!(derphi0 < 0.0)) return false;
+    double stp = first_step > 0.0 ? first_step : first_trial_step(f0, old_f, derphi0);
+    stp = std::min(stp, stpmax);
+    LineSearch ls{c1, c2, xtol, stpmin, stpmax};
+    if (ls.start(stp, f0, derphi0) != LineSearch::FG) return false;
+    Phi phi{fun, n, x, p, x_new, f_new, g_new, nfev, err};
+    for (int trial = 0; trial < max_trials; ++trial) {
+        double f, d;
+        if (!phi.eval(stp, &f, &d)) return false;
+        const LineSearch::Task t = ls.update(stp, f, d);
         if (t == LineSearch::CONVERGED) return true;
-        if (t != LineSearch::FG) {
-            (void)stp_eval;
-            return false;
-        }
+        if (t == LineSearch::WARNING && accept_warning) return true;      // lnsrlb of L-BFGS-B: "CONV" and "WARN" both end the search at the current step
+        if (t != LineSearch::FG) return false;
+        if (!std::isfinite(stp)) return false;           // DCSRCH.__call__: a non-finite step ends the search with a warning
     }
     return false;
 }
 
+// ---- scipy.optimize._linesearch.scalar_search_wolfe2 (+ _zoom, _cubicmin, _quadmin): the fallback of _line_search_wolfe12 ------------
+inline bool cubicmin(double a, double fa, double fpa, double b, double fb, double c, double fc, double* xmin) {
+    const double C = fpa, db = b - a, dc = c - a;
+    const double denom = (db * dc) * (db * dc) * (db - dc);
+    if (denom == 0.0 || !std::isfinite(denom)) return false;
+    const double r0 = fb - fa - C * db, r1 = fc - fa - C * dc;
+    const double A = (dc * dc * r0 - db * db * r1) / denom;
+    const double B = (-dc * dc * dc * r0 + db * db * db * r1) / denom;
+    const double radical = B * B - 3.0 * A * C;
+    if (!(radical >= 0.0) || A == 0.0) return false;
+    *xmin = a + (-B + std::sqrt(radical)) / (3.0 * A);
+    return std::isfinite(*xmin);
+}
+
+inline bool quadmin(double a, double fa, double fpa, double b, double fb, double* xmin) {
+    const double db = b - a;
+    if (db == 0.0) return false;
+    const double B = (fb - fa - fpa * db) / (db * db);
+    if (B == 0.0 || !std::isfinite(B)) return false;
+    *xmin = a - fpa / (2.0 * B);
+    return std::isfinite(*xmin);
+}
+
+// returns true with *a_star when a point satisfying the strong Wolfe conditions was found inside the bracket (<= 10 + 1 trials)
+inline bool zoom(Phi& phi, double a_lo, double a_hi, double phi_lo, double phi_hi, double derphi_lo, double phi0, double derphi0,
+                 double c1, double c2, double* a_star) {
+    const double delta1 = 0.2, delta2 = 0.1;
+    double phi_rec = phi0, a_rec = 0.0;
+    for (int i = 0;; ++i) {
+        const double dalpha = a_hi - a_lo;
+        const double a = dalpha < 0.0 ? a_hi : a_lo, b = dalpha < 0.0 ? a_lo : a_hi;
+        double a_j = 0.0;
+        bool have = false;
+        if (i > 0) {
+            const double cchk = delta1 * dalpha;
+            have = cubicmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi, a_rec, phi_rec, &a_j) && !(a_j > b - cchk) && !(a_j < a + cchk);
+        }
+        if (!have) {
+            const double qchk = delta2 * dalpha;
+            have = quadmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi, &a_j) && !(a_j > b - qchk) && !(a_j < a + qchk);
+            if (!have) a_j = a_lo + 0.5 * dalpha;
+        }
+        double phi_aj, derphi_aj;
+        if (!phi.eval(a_j, &phi_aj, &derphi_aj)) return false;
+        if (phi_aj > phi0 + c1 * a_j * derphi0 || phi_aj >= phi_lo) {
+            phi_rec = phi_hi; a_rec = a_hi; a_hi = a_j; phi_hi = phi_aj;
+        } else {
+            if (std::fabs(derphi_aj) <= -c2 * derphi0) { *a_star = a_j; return true; }
+            if (derphi_aj * (a_hi - a_lo) >= 0.0) { phi_rec = phi_hi; a_rec = a_hi; a_hi = a_lo; phi_hi = phi_lo; }
+            else { phi_rec = phi_lo; a_rec = a_lo; }
+            a_lo = a_j; phi_lo = phi_aj; derphi_lo = derphi_aj;
+        }
+        if (i + 1 > 10) return false;
+    }
+}
+
+// On success x_new, f_new, g_new hold the accepted point (always the last one evaluated).  Like scipy, a search that exhausts its ten
+// bracketing steps still returns the last trial step (with a warning there; BFGS takes the step).
+inline bool wolfe2_search(const Objective& fun, int n, const double* x, const double* p, double f0, const double* g0, double old_f,
+                          double c1, double c2, double amax, double* x_new, double* f_new, double* g_new, int& nfev, int& err) {
+    const double derphi0 = dot(g0, p, n);
+    Phi phi{fun, n, x, p, x_new, f_new, g_new, nfev, err};
+    double alpha0 = 0.0, alpha1 = std::min(first_trial_step(f0, old_f, derphi0), amax);
+    double phi_a0 = f0, derphi_a0 = derphi0, phi_a1, derphi_a1;
+    if (!phi.eval(alpha1, &phi_a1, &derphi_a1)) return false;
+    for (int i = 0; i < 10; ++i) {
+        if (alpha1 == 0.0 || alpha0 > amax) return false;
+        double a_star;
+        if (phi_a1 > f0 + c1 * alpha1 * derphi0 || (phi_a1 >= phi_a0 && i > 0))
+            return zoom(phi, alpha0, alpha1, phi_a0, phi_a1, derphi_a0, f0, derphi0, c1, c2, &a_star);
+        if (std::fabs(derphi_a1) <= -c2 * derphi0) return true;
+        if (derphi_a1 >= 0.0)
+            return zoom(phi, alpha1, alpha0, phi_a1, phi_a0, derphi_a1, f0, derphi0, c1, c2, &a_star);
+        const double alpha2 = std::min(2.0 * alpha1, amax);
+        alpha0 = alpha1; alpha1 = alpha2;
+        phi_a0 = phi_a1; derphi_a0 = derphi_a1;
+        if (!phi.eval(alpha1, &phi_a1, &derphi_a1)) return false;
+    }
+    return true;
+}
+
+// scipy.optimize._optimize._minimize_bfgs (H0 = I, c1 = 1e-4, c2 = 0.9, gradient norm = inf-norm, xrtol = 0), including its line
+// search policy (_line_search_wolfe12: dcsrch first, scalar_search_wolfe2 when that fails) and its status codes: 0 converged, 1
+// maxiter, 2 precision loss (both line searches failed, or a non-finite objective), 3 NaN in the result.
 inline Result bfgs(const Objective& fun, int n, double* x, int maxiter, double gtol, int* err_out) {
     Result r;
     std::vector<double> g(n), gn(n), xn(n), p(n), s(n), y(n), Hy(n), H((size_t)n * n, 0.0);
@@ -206,15 +306,19 @@ inline Result bfgs(const Objective& fun, int n, double* x, int maxiter, double g
     r.status = 0;
     for (int i = 0; i < n; ++i) p[i] = -g[i];                        // H0 = I
     while (gnorm > gtol && r.nit < maxiter) {
-        const bool ok = wolfe_search(fun, n, x, p.data(), f, g.data(), old_f, 1e-4, 0.9, 1e100, 0.0, xn.data(), &fn, gn.data(), r.nfev, err);
+        bool ok = wolfe_search(fun, n, x, p.data(), f, g.data(), old_f, 1e-4, 0.9, 1e100, 0.0, xn.data(), &fn, gn.data(), r.nfev, err);
         if (err) { *err_out = err; break; }
+        if (!ok) {
+            ok = wolfe2_search(fun, n, x, p.data(), f, g.data(), old_f, 1e-4, 0.9, 1e100, xn.data(), &fn, gn.data(), r.nfev, err);
+            if (err) { *err_out = err; break; }
+        }
         if (!ok) { r.status = 2; break; }
         for (int i = 0; i < n; ++i) { s[i] = xn[i] - x[i]; y[i] = gn[i] - g[i]; x[i] = xn[i]; g[i] = gn[i]; }
         old_f = f; f = fn;
         ++r.nit;
         gnorm = max_abs(g.data(), n);
         if (gnorm <= gtol) break;
-        if (!std::isfinite(f)) { r.status = 3; break; }
+        if (!std::isfinite(f)) { r.status = 2; break; }
         const double ys = dot(y.data(), s.data(), n);
         const double rho = (ys == 0.0) ? 1000.0 : 1.0 / ys;
         // H <- (I - rho s y^T) H (I - rho y s^T) + rho s s^T  =  H - rho (s (Hy)^T + (Hy) s^T) + rho (rho y^T H y + 1) s s^T
@@ -230,48 +334,64 @@ inline Result bfgs(const Objective& fun, int n, double* x, int maxiter, double g
         }
     }
     if (r.status == 0 && gnorm > gtol && r.nit >= maxiter) r.status = 1;
+    else if (r.status == 0) {
+        bool nan = std::isnan(gnorm) || std::isnan(f);
+        for (int i = 0; i < n && !nan; ++i) nan = std::isnan(x[i]);
+        if (nan) r.status = 3;
+    }
     r.fun = f;
     return r;
 }
 
-// scalar box-bounded minimisation (n = 1 case of L-BFGS-B): x in [lo, hi]
+// scalar box-bounded minimisation: the n = 1 case of L-BFGS-B 3.0 as scipy drives it (x in [lo, hi]).
+//   direction   : d = P(x - g / B) - x (generalised Cauchy point + subspace minimisation collapse to the projected quasi-Newton
+//                 step in one dimension; B = 1 until a curvature pair exists, then the secant y / s - the 1-D BFGS matrix)
+//   line search : dcsrch with ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmin = 0, stpmax = largest feasible step (1 in the first iteration),
+//                 first step 1 (min(1 / |d|, stpmax) in the first iteration of a problem that is not boxed), at most 20 evaluations (lnsrlb)
+//   failure     : the previous iterate is restored; with a curvature pair the matrix is reset and the iteration restarts from
+//                 steepest descent, without one the run ends with status 2 (ABNORMAL_TERMINATION_IN_LNSRCH)
+//   stop        : projected gradient <= pgtol, (f_k - f_{k+1}) / max(|f_k|, |f_{k+1}|, 1) <= factr * eps, maxiter (status 1)
 inline Result bounded_scalar(const Objective& fun, double* x, double lo, double hi, int maxiter, double pgtol, double factr, int* err_out) {
     Result r;
     *err_out = 0;
     const double eps = std::numeric_limits<double>::epsilon();
+    const bool boxed = std::isfinite(lo) && std::isfinite(hi), cnstnd = std::isfinite(lo) || std::isfinite(hi);
     double xa = std::min(std::max(*x, lo), hi), f = 0.0, g = 0.0;
     int err = 0;
     if ((err = fun(&xa, &f, &g)) != 0) { *err_out = err; return r; }
     r.nfev = 1;
     auto proj_grad = [&](double xv, double gv) { return std::fabs(std::min(std::max(xv - gv, lo), hi) - xv); };
-    double B = 0.0;                                   // secant curvature; 0 = none yet
+    double B = 1.0;                                   // theta of L-BFGS-B until a pair is stored
+    bool have_pair = false;
     r.status = 1;
     if (proj_grad(xa, g) <= pgtol) { r.status = 0; }
     while (r.status == 1 && r.nit < maxiter) {
-        double d = (B > 0.0) ? -g / B : -g;
-        const double target = std::min(std::max(xa + d, lo), hi);      // projected step
-        d = target - xa;
+        double d = std::min(std::max(xa - g / B, lo), hi) - xa;
         if (d == 0.0) { r.status = 0; break; }
-        const double dnorm = std::fabs(d);
-        // first iteration of L-BFGS-B: step 1/|d|; later: 1
-        double stp0 = (r.nit == 0 && B == 0.0) ? std::min(1.0 / dnorm, 1.0) : 1.0;
+        double stpmx = 1e10;
+        if (cnstnd) {
+            if (r.nit == 0) stpmx = 1.0;
+            else if (d > 0.0 && std::isfinite(hi)) stpmx = (hi - xa) / d;
+            else if (d < 0.0 && std::isfinite(lo)) stpmx = (lo - xa) / d;
+        }
+        const double stp0 = (r.nit == 0 && !boxed) ? std::min(1.0 / std::fabs(d), stpmx) : 1.0;
         double xn = xa, fn = f, gn = g;
         int e2 = 0;
-        Objective f1 = fun;
-        const bool ok = wolfe_search(f1, 1, &xa, &d, f, &g, std::numeric_limits<double>::quiet_NaN(), 1e-3, 0.9, 1.0, stp0, &xn, &fn, &gn, r.nfev, e2, 20);
+        const bool ok = wolfe_search(fun, 1, &xa, &d, f, &g, std::numeric_limits<double>::quiet_NaN(), 1e-3, 0.9, stpmx, std::min(stp0, stpmx),
+                                     &xn, &fn, &gn, r.nfev, e2, 20, 0.1, 0.0, true);
         if (e2) { *err_out = e2; break; }
         if (!ok) {
-            if (fn < f) { xa = xn; f = fn; g = gn; }      // keep an improving point even when the Wolfe test failed
-            r.status = 2;
-            break;
+            if (!have_pair) { r.status = 2; break; }     // x, f, g still hold the previous iterate
+            have_pair = false; B = 1.0;                  // refresh the matrix and restart the iteration
+            continue;
         }
         const double s = xn - xa, yv = gn - g;
-        const double f_prev = f;
+        const double f_prev = f, g_prev = g;
         xa = xn; f = fn; g = gn;
         ++r.nit;
-        if (s * yv > eps * yv * yv) B = yv / s;
         if (proj_grad(xa, g) <= pgtol) { r.status = 0; break; }
         if ((f_prev - f) <= factr * eps * std::max({std::fabs(f_prev), std::fabs(f), 1.0})) { r.status = 0; break; }
+        if (yv * s > eps * (-g_prev * s)) { B = yv / s; have_pair = true; }      // matupd is skipped when the curvature is not positive
     }
     *x = xa;
     r.fun = f;

@@ -16,6 +16,8 @@
 #include <condition_variable>
 #include <map>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <tuple>
@@ -433,6 +435,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         plan->rec_pending = ia.rec != nullptr;
         ia.part = plan->part + 2 * tvb;                          // k_tv's partials live at the start of `part`
         ia.sc = plan->sc; ia.loss_out = loss_out;
+        ia.tail_here = (fold && plan->fused_fill) ? 1 : 0;               // no k_image_grad follows: the statistics tail runs in the last CTA
         ia.zero_buf = (want_grad && !fold) ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
         g_zeroed = want_grad;
         if (want_grad && h * w <= kGatherMaxTiles) {
@@ -441,13 +444,18 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         }
         ia.H = H; ia.W = W; ia.R = R;
         ia.alpha = hp->alpha; ia.beta = hp->beta; ia.gamma = hp->gamma; ia.use_tv = use_tv ? 1 : 0;
-        LAUNCH("k_image_stats", launch_pdl(k_image_stats, dim3((image_stats_items(H, W, R) + kS2Warps - 1) / kS2Warps), dim3(kS2NT), 0, st, ia));
+        LAUNCH("k_image_stats", launch_pdl(k_image_stats, dim3(R * image_stats_ctas(H, W)), dim3(kS2NT), 0, st, ia));
+        // the loss is evaluated by a spare CTA of k_image_grad (publish_loss), off the critical path of the evaluation
+        auto tail_args = [&](ImageGradArgs& ga) {
+            ga.publish = 1; ga.loss_out = loss_out; ga.alpha = hp->alpha; ga.beta = hp->beta; ga.gamma = hp->gamma; ga.use_tv = use_tv ? 1 : 0;
+        };
         if (fold && !plan->fused_fill) {
             // d loss / d IWE materialised by its own (pointwise) kernel, which also clears the fixed-point images
             ImageGradArgs ga{};
             ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
             ga.dldi = nullptr; ga.dldi32 = plan->dldi32; ga.HW = (int)plan->HW; ga.R = R; ga.want_grad = 1;
-            LAUNCH("k_image_grad", launch_pdl(k_image_grad, dim3(std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8))), dim3(256), 0, st, ga));
+            tail_args(ga);
+            LAUNCH("k_image_grad", launch_pdl(k_image_grad, dim3(std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8)) + 1), dim3(256), 0, st, ga));   // + 1: the publishing CTA
         }
         if (fold) {
             BackwardFoldArgs ba{};
@@ -476,8 +484,9 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         ImageGradArgs ga{};
         ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
         ga.dldi = nullptr; ga.dldi32 = plan->dldi32; ga.HW = (int)plan->HW; ga.R = R; ga.want_grad = want_grad ? 1 : 0;
+        tail_args(ga);
         plan->dldi_stale = want_grad;                            // the float64 copy (debug tap) is produced on demand: eincm_dldi_ptr
-        LAUNCH("k_image_grad", launch_pdl(k_image_grad, dim3(std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8))), dim3(256), 0, st, ga));
+        LAUNCH("k_image_grad", launch_pdl(k_image_grad, dim3(std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8)) + 1), dim3(256), 0, st, ga));   // + 1: the publishing CTA
         plan->fused_pending = false;
         plan->fix_clean = true;                                  // the pass clears the cells it has read
         if (!want_grad) return EINCM_OK;
@@ -1051,6 +1060,11 @@ int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host, int h, 
     if (!plan) return EINCM_EINVAL;
     if (!theta_inout_host || !result_out) return fail(plan, EINCM_EINVAL, "NULL operand");
     if (maxiter < 0) return fail(plan, EINCM_EINVAL, "maxiter must be >= 0");
+    if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    // BFGS keeps a dense n x n inverse Hessian on the host: tile theta only (the reference solves 1x1 .. 16x16 with it, main.yaml:25-59)
+    if ((int64_t)h * w > kGatherMaxTiles)
+        return fail(plan, EINCM_EINVAL, "eincm_minimize_bfgs_host: theta %dx%d needs a dense %lld^2 inverse Hessian; the limit is %d elements",
+                    h, w, (long long)h * w * 2, kGatherMaxTiles);
     cudaStream_t st = cuda_stream == (void*)(intptr_t)-1 ? plan->own_stream : (cudaStream_t)cuda_stream;
     const int n = h * w * 2;
     eincm_group* grp = plan->group;
@@ -1064,8 +1078,18 @@ int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host, int h, 
         return host_collect(plan, f, g, st);
     };
     int err = 0;
+    eincm_opt::Result r;
     if (grp != nullptr) grp->enter();
-    const eincm_opt::Result r = eincm_opt::bfgs(fun, n, theta_inout_host, maxiter, gtol, &err);
+    // no C++ exception may cross the C boundary (std::bad_alloc of the optimizer's work space, std::function)
+    try {
+        r = eincm_opt::bfgs(fun, n, theta_inout_host, maxiter, gtol, &err);
+    } catch (const std::bad_alloc&) {
+        if (grp != nullptr) grp->leave();
+        return fail(plan, EINCM_ENOMEM, "eincm_minimize_bfgs_host: out of host memory for n = %d", n);
+    } catch (const std::exception& e) {
+        if (grp != nullptr) grp->leave();
+        return fail(plan, EINCM_ECUDA, "eincm_minimize_bfgs_host: %s", e.what());
+    }
     if (grp != nullptr) grp->leave();
     if (err) return err;
     result_out->fun = r.fun; result_out->nit = r.nit; result_out->nfev = r.nfev; result_out->status = r.status; result_out->reserved = 0;
@@ -1097,7 +1121,12 @@ int eincm_minimize_handover_host(eincm_plan* plan, double* alpha_inout_host, dou
         return EINCM_OK;
     };
     int err = 0;
-    const eincm_opt::Result r = eincm_opt::bounded_scalar(fun, alpha_inout_host, lo, hi, maxiter, pgtol, 1e7, &err);
+    eincm_opt::Result r;
+    try {
+        r = eincm_opt::bounded_scalar(fun, alpha_inout_host, lo, hi, maxiter, pgtol, 1e7, &err);
+    } catch (const std::exception& e) {
+        return fail(plan, EINCM_ECUDA, "eincm_minimize_handover_host: %s", e.what());
+    }
     if (err) return err;
     result_out->fun = r.fun; result_out->nit = r.nit; result_out->nfev = r.nfev; result_out->status = r.status; result_out->reserved = 0;
     return EINCM_OK;

@@ -50,27 +50,6 @@ struct FusedAcc {
     }
 };
 
-// block-wide merge of FusedAcc (kFNT threads); result valid in thread 0.  Fixed order: deterministic.
-__device__ __forceinline__ FusedAcc fused_block_reduce(FusedAcc a, double (*sh)[kFPart]) {
-    const int tid = linear_tid();
-#pragma unroll
-    for (int o = 16; o; o >>= 1) a.merge(a.shfl_xor(o));
-    __syncthreads();     // sh may still be read from a previous call
-    if ((tid & 31) == 0) {
-        double* d = sh[tid >> 5];
-        d[0] = a.sq; d[1] = a.sI; d[2] = a.sI2; d[3] = a.sEI; d[4] = a.mn; d[5] = a.cmn; d[6] = a.mx; d[7] = a.cmx;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int k = 1; k < kFNT / 32; ++k) {
-            FusedAcc o;
-            o.sq = sh[k][0]; o.sI = sh[k][1]; o.sI2 = sh[k][2]; o.sEI = sh[k][3]; o.mn = sh[k][4]; o.cmn = sh[k][5]; o.mx = sh[k][6]; o.cmx = sh[k][7];
-            a.merge(o);
-        }
-    }
-    return a;
-}
-
 // ---- k_image_stats ---------------------------------------------------------------------------------------------------------
 // Streaming formulation, no shared memory and no block barrier in the main loop: one WARP owns a strip of kS2Cols columns x kS2Rows
 // rows of one reference image and marches down its rows.  Lanes are adjacent columns (two halo lanes on either side: the Scharr pair
@@ -78,13 +57,20 @@ __device__ __forceinline__ FusedAcc fused_block_reduce(FusedAcc a, double (*sh)[
 // three-row window in registers; rows are loaded kS2Pre at a time, one group ahead of the arithmetic (all loads of a group in flight
 // together).  Every warp accumulates the statistics of its own pixels and writes one partial record; the last CTA to finish
 // (ticket) reduces the records of every reference image in a fixed order (deterministic) and evaluates the loss.  The kernel
-// boundary before k_image_grad replaces a grid-wide barrier.  (The first version kept whole row bands in shared memory: two CTAs
-// per SM, phases separated by barriers - 27 us for 7.4 MB of L2-resident input, and no faster per window when windows were batched.)
+// boundary before k_image_grad replaces a grid-wide barrier.  Every CTA writes ONE partial record (its warps merged in warp order); the
+// last CTA to finish reduces the records, one warp per reference image, and publishes only what k_image_grad needs (stats_tail); the
+// loss is evaluated by a spare CTA of k_image_grad.  History (640x480, R = 3): whole row bands in shared memory, two CTAs per SM,
+// barriers between phases: 27 us; streaming warps, one record per WARP and a serial tail that also evaluated the loss: 45 us, more
+// than 20 of them in the tail (ncu: 14 % of the warp slots active); the tail replicated in the prologue of every CTA of k_image_grad:
+// 21 + 25 us (and slower with four windows in flight: 300 CTAs repeat it); this form: 29 us, k_image_grad 10.8 us.
 constexpr int kCoopMaxRefs = EINCM_MAX_REFS;
 constexpr int kS2Warps = 4;                         // warps (work items) per CTA
 constexpr int kS2NT = kS2Warps * 32;
 constexpr int kS2Cols = 28;                         // own columns of a warp (lanes 2 .. 29)
-constexpr int kS2Rows = 24;                         // own rows of a warp (measured: 12 rows -> 51 us, 24 rows -> 35 us at 640x480, R = 3)
+#ifndef EINCM_S2_ROWS
+#define EINCM_S2_ROWS 12
+#endif
+constexpr int kS2Rows = EINCM_S2_ROWS;                         // own rows of a warp (640x480, R = 3: 12 rows 140.8 us per evaluation on one stream, 24 rows 144.9; kernel 29 us either way)
 constexpr int kS2Pre = 4;                           // rows per load group
 constexpr int kStatsTicket = 6;                     // DevScalars::counters slot of the "last CTA" ticket
 
@@ -99,7 +85,9 @@ struct ImageStatsArgs {
     const double* edges;            // [R][H*W]
     double* iwe;                    // [R][H*W] float64 images (out)
     float* adj32;                   // [R][H*W] adjoint of the Scharr pair applied to (Gx, Gy) (out; d contrast / d IWE up to cA)
-    double* part;                   // [R][strips * bands][kFPart]
+    double* part;                   // [R][image_stats_ctas(H, W)][kFPart]: one record per CTA
+    int tail_here;                  // != 0: the last CTA also publishes the loss (fused backward without k_image_grad); 0: a spare CTA of
+                                    // k_image_grad does (default)
     DevScalars* sc;
     double* loss_out;
     double* zero_buf;               // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
@@ -115,6 +103,8 @@ __host__ __device__ inline int image_stats_strips(int W) { return (W + kS2Cols -
 __host__ __device__ inline int image_stats_bands(int H) { return (H + kS2Rows - 1) / kS2Rows; }
 // work items (warps) of the image pass for R reference images
 __host__ __device__ inline int image_stats_items(int H, int W, int R) { return R * image_stats_strips(W) * image_stats_bands(H); }
+// CTAs per reference image: kS2Warps work items each, never items of two images (one partial record per CTA)
+__host__ __device__ inline int image_stats_ctas(int H, int W) { return (image_stats_strips(W) * image_stats_bands(H) + kS2Warps - 1) / kS2Warps; }
 
 __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double sE, double sE2, double cb) {
     Stats st;
@@ -132,11 +122,82 @@ __device__ __forceinline__ Stats fused_stats(const FusedAcc& a, double n, double
 }
 
 struct StatsTail {
-    Stats st[kCoopMaxRefs];
-    double coefA[kCoopMaxRefs], coefB[kCoopMaxRefs];
-    double wts[kCoopMaxRefs], zero_mse[kCoopMaxRefs], sumE[kCoopMaxRefs], sumE2[kCoopMaxRefs], zero_contrast;
+    double wacc[kS2Warps][kFPart];     // per-warp partials of one CTA of k_image_stats
     int is_last;
 };
+
+// Tail of the image statistics, run by the last CTA of k_image_stats to finish: reduces the per-CTA records of every reference image
+// - one WARP per image, records in lane order, butterfly merge (commutative operations: every lane holds the same bits, the result
+// does not depend on which CTA runs it) - and publishes the per-image statistics and cotangent scales k_image_grad needs.  Nothing
+// else: the loss and the coefficients of the fused backward fill are a serial chain of float64 divisions that nothing before
+// k_theta_grad waits for (publish_loss, run by a spare CTA of k_image_grad next to the pointwise pass).
+template <int NT>
+__device__ __forceinline__ void stats_tail(const double* __restrict__ part, DevScalars* sc, int R, int cpi, int HW, double alpha, double beta) {
+    const int tid = linear_tid(), lane = tid & 31, wid = tid >> 5;
+    for (int q = wid; q < R; q += NT / 32) {
+        // per-window constants of the image (cotangent scales from the zero-warp image, losses.py:176-177): loads in flight with the records
+        const double w = sc->weights[q], zc = sc->zero[0].contrast, zm = sc->zero[q].mse, sE = sc->sumE[q], sE2 = sc->sumE2[q];
+        FusedAcc a;
+        a.init();
+        for (int k0 = lane; k0 < cpi; k0 += 4 * 32) {
+            double v[4][kFPart];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double* d = part + ((int64_t)q * cpi + min(k0 + 32 * u, cpi - 1)) * kFPart;
+#pragma unroll
+                for (int f = 0; f < kFPart; ++f) v[u][f] = __ldcg(d + f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + 32 * u < cpi) {
+                    FusedAcc o;
+                    o.sq = v[u][0]; o.sI = v[u][1]; o.sI2 = v[u][2]; o.sEI = v[u][3];
+                    o.mn = v[u][4]; o.cmn = v[u][5]; o.mx = v[u][6]; o.cmx = v[u][7];
+                    a.merge(o);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a.merge(a.shfl_xor(o));
+        if (lane == 0) {
+            const double a_r = -alpha * w / ((zc + kEps) * R);
+            const double b_r = beta * w / ((-zm + kEps) * R);
+            const double cA = a_r * (2.0 / (double)HW), cB = b_r * (-2.0 / (double)HW);
+            sc->ref[q] = fused_stats(a, (double)HW, sE, sE2, cB);
+            sc->coefA[q] = cA; sc->coefB[q] = cB; sc->coefD[q] = 0.0;
+        }
+    }
+}
+
+// Loss and fused-fill coefficients from the published statistics (one thread; reference src/eincm/losses.py:171-193).
+__device__ __forceinline__ void publish_loss(DevScalars* sc, int R, double alpha, double beta, double gamma, int use_tv, double* loss_out) {
+    double s_corr = 0.0, s_con = 0.0;
+    const double zc = sc->zero[0].contrast;
+    for (int q = 0; q < R; ++q) {
+        const Stats st = sc->ref[q];
+        const double cA = sc->coefA[q], cB = sc->coefB[q], w = sc->weights[q];
+        // coefficients of the per-cell cotangent for the fused backward fill (same terms as k_image_grad, scaled by 1 / 2 pi)
+        const double iD = 1.0 / st.D;
+        const double g_M = -st.s2 / (st.D * st.D);
+        const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
+        CotCoef c;
+        c.cA = cA * kInv2Pi;
+        c.a1 = cB * iD * kInv2Pi;
+        c.a2 = cB * iD * iD * kInv2Pi;
+        c.a3 = c.a2 * st.mn;
+        c.mn = st.mn; c.mx = st.mx;
+        c.tm = g_m / st.cnt_min * kInv2Pi; c.tM = g_M / st.cnt_max * kInv2Pi;
+        sc->cot[q] = c;
+        s_corr += (w * (-st.mse)) / ((-sc->zero[q].mse) + kEps);                         // losses.py:176
+        s_con += (w * st.contrast) / (zc + kEps);                                        // losses.py:177
+    }
+    const double mean_rel_corr = s_corr / R, mean_rel_contrast = s_con / R;
+    const double tv = use_tv ? sc->tv_sum / (sc->tv_cnt + kEps) : 0.0;                  // regularizers.py:31-36, losses.py:171
+    const double loss = (alpha * (mean_rel_contrast * (-1.0)) + beta * (mean_rel_corr * (-1.0))) + (gamma * tv + 0.0);
+    sc->loss = loss; sc->mean_rel_corr = mean_rel_corr; sc->mean_rel_contrast = mean_rel_contrast;
+    sc->mean_rel_div = 0.0; sc->tv = tv;
+    if (loss_out != nullptr) *loss_out = loss;
+}
 
 __device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn_d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
@@ -148,7 +209,7 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
     const int HW = H * W;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int strips = image_stats_strips(W), bands = image_stats_bands(H);
-    const int per_img = strips * bands, n_items = R * per_img;
+    const int per_img = strips * bands, cpi = image_stats_ctas(H, W);
     const int G = gridDim.x, b = blockIdx.x;
     // programmatic dependent launch: the next kernel of the evaluation may be scheduled as soon as every CTA of this one is resident;
     // this kernel itself may have been scheduled while the splat was still running - nothing is read or written before the wait
@@ -159,19 +220,13 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
         for (int k = b * kS2NT + tid; k < A.n_zero; k += G * kS2NT) A.zero_buf[k] = 0.0;
     if (A.zero_buf2 != nullptr)
         for (int k = b * kS2NT + tid; k < A.n_zero2; k += G * kS2NT) A.zero_buf2[k] = 0.0;
-    // per-window constants of the tail (cotangent scales from the zero-warp image, losses.py:176-177)
-    if (tid < R) {
-        const double w = A.sc->weights[tid], zc = A.sc->zero[0].contrast, zm = A.sc->zero[tid].mse;
-        const double a_r = -A.alpha * w / ((zc + kEps) * R);
-        const double b_r = A.beta * w / ((-zm + kEps) * R);
-        S.coefA[tid] = a_r * (2.0 / (double)HW);
-        S.coefB[tid] = b_r * (-2.0 / (double)HW);
-        S.wts[tid] = w; S.zero_mse[tid] = zm; S.sumE[tid] = A.sc->sumE[tid]; S.sumE2[tid] = A.sc->sumE2[tid];
-        if (tid == 0) S.zero_contrast = zc;
-    }
 
-    for (int item = b * kS2Warps + wid; item < n_items; item += G * kS2Warps) {
-        const int r = item / per_img, rem = item - r * per_img;
+    for (int cta = b; cta < R * cpi; cta += G) {
+        const int r = cta / cpi, ci = cta - r * cpi;
+        const int rem = ci * kS2Warps + wid;                      // work item of this warp inside image r (idle beyond per_img)
+        FusedAcc acc;
+        acc.init();
+        if (rem < per_img) {
         const int band = rem / strips, strip = rem - band * strips;
         const int x = strip * kS2Cols - 2 + lane;                 // this lane's column (lanes 0, 1, 30, 31: halo)
         const int y0 = band * kS2Rows, y1 = min(H, y0 + kS2Rows);
@@ -183,8 +238,6 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
         float* Ar = A.adj32 + r * HW;
         CellRec* Rr = REC ? A.rec + r * HW : nullptr;
         const float* E32r = A.e32 + r * HW;
-        FusedAcc acc;
-        acc.init();
         int cnt_mn = 0, cnt_mx = 0;                    // tie counts of the running min / max (integers: branch-free update)
         // three-row windows: image value and horizontal difference of input rows yi-2, yi-1 (yi: the row being consumed);
         // Scharr x differences and Scharr y of rows yc-2, yc-1 (yc = yi - 1: the row whose Scharr pair is produced)
@@ -253,81 +306,41 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
             }
         }
         acc.cmn = (double)cnt_mn; acc.cmx = (double)cnt_mx;
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) acc.merge(acc.shfl_xor(o));
+        // one record per CTA: the warps' partials merged in warp order
+        __syncthreads();                               // S.wacc of the previous round has been read
         if (lane == 0) {
-            double* d = A.part + (int64_t)item * kFPart;
+            double* d = S.wacc[wid];
             d[0] = acc.sq; d[1] = acc.sI; d[2] = acc.sI2; d[3] = acc.sEI; d[4] = acc.mn; d[5] = acc.cmn; d[6] = acc.mx; d[7] = acc.cmx;
         }
+        __syncthreads();
+        if (tid == 0) {
+            FusedAcc a;
+            a.init();
+            for (int k = 0; k < kS2Warps; ++k) {
+                FusedAcc o;
+                o.sq = S.wacc[k][0]; o.sI = S.wacc[k][1]; o.sI2 = S.wacc[k][2]; o.sEI = S.wacc[k][3];
+                o.mn = S.wacc[k][4]; o.cmn = S.wacc[k][5]; o.mx = S.wacc[k][6]; o.cmx = S.wacc[k][7];
+                a.merge(o);
+            }
+            double* d = A.part + (int64_t)cta * kFPart;
+            d[0] = a.sq; d[1] = a.sI; d[2] = a.sI2; d[3] = a.sEI; d[4] = a.mn; d[5] = a.cmn; d[6] = a.mx; d[7] = a.cmx;
+        }
     }
-
-    // ---- tail: the last CTA reduces the partials of every reference image (one WARP per image, fixed order) -----------------
+    // ---- tail: the last CTA to finish reduces the records (one warp per reference image) --------------------------------------------
     __threadfence();
     __syncthreads();
     if (tid == 0) S.is_last = atomicAdd(&A.sc->counters[kStatsTicket], 1u) == (unsigned)(G - 1);
     __syncthreads();
     if (!S.is_last) return;
     __threadfence();
-    {
-        for (int q = wid; q < R; q += kS2Warps) {
-            // four records per lane and round, all loads of a round issued before the first merge (one L2 round trip per round)
-            FusedAcc a;
-            a.init();
-            for (int k0 = lane; k0 < per_img; k0 += 4 * 32) {
-                double v[4][kFPart];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int k = min(k0 + 32 * u, per_img - 1);
-                    const double* d = A.part + ((int64_t)q * per_img + k) * kFPart;
-#pragma unroll
-                    for (int f = 0; f < kFPart; ++f) v[u][f] = __ldcg(d + f);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + 32 * u < per_img) {
-                        FusedAcc o;
-                        o.sq = v[u][0]; o.sI = v[u][1]; o.sI2 = v[u][2]; o.sEI = v[u][3];
-                        o.mn = v[u][4]; o.cmn = v[u][5]; o.mx = v[u][6]; o.cmx = v[u][7];
-                        a.merge(o);
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) a.merge(a.shfl_xor(o));
-            if (lane == 0) S.st[q] = fused_stats(a, (double)HW, S.sumE[q], S.sumE2[q], S.coefB[q]);
-        }
+    stats_tail<kS2NT>(A.part, A.sc, R, cpi, HW, A.alpha, A.beta);
+    if (tid == 0) A.sc->counters[kStatsTicket] = 0u;
+    if (A.tail_here) {                   // no k_image_grad follows (fused backward fill): the loss is published here as well
         __syncthreads();
-        if (tid == 0) {
-            for (int q = 0; q < R; ++q) {
-                A.sc->ref[q] = S.st[q]; A.sc->coefA[q] = S.coefA[q]; A.sc->coefB[q] = S.coefB[q]; A.sc->coefD[q] = 0.0;
-                // coefficients of the per-cell cotangent for the fused backward fill (same terms as k_image_grad, scaled by 1 / 2 pi)
-                const Stats& st = S.st[q];
-                const double iD = 1.0 / st.D;
-                const double g_M = -st.s2 / (st.D * st.D);
-                const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
-                CotCoef c;
-                c.cA = S.coefA[q] * kInv2Pi;
-                c.a1 = S.coefB[q] * iD * kInv2Pi;
-                c.a2 = S.coefB[q] * iD * iD * kInv2Pi;
-                c.a3 = c.a2 * st.mn;
-                c.mn = st.mn; c.mx = st.mx;
-                c.tm = g_m / st.cnt_min * kInv2Pi; c.tM = g_M / st.cnt_max * kInv2Pi;
-                A.sc->cot[q] = c;
-            }
-            // final loss (reference src/eincm/losses.py:171-193)
-            double s_corr = 0.0, s_con = 0.0;
-            for (int q = 0; q < R; ++q) {
-                s_corr += (S.wts[q] * (-S.st[q].mse)) / ((-S.zero_mse[q]) + kEps);          // losses.py:176
-                s_con += (S.wts[q] * S.st[q].contrast) / (S.zero_contrast + kEps);          // losses.py:177
-            }
-            const double mean_rel_corr = s_corr / R, mean_rel_contrast = s_con / R;
-            const double tv = A.use_tv ? A.sc->tv_sum / (A.sc->tv_cnt + kEps) : 0.0;        // regularizers.py:31-36, losses.py:171
-            const double loss = (A.alpha * (mean_rel_contrast * (-1.0)) + A.beta * (mean_rel_corr * (-1.0))) + (A.gamma * tv + 0.0);
-            A.sc->loss = loss; A.sc->mean_rel_corr = mean_rel_corr; A.sc->mean_rel_contrast = mean_rel_contrast;
-            A.sc->mean_rel_div = 0.0; A.sc->tv = tv;
-            if (A.loss_out != nullptr) *A.loss_out = loss;
-            A.sc->counters[kStatsTicket] = 0u;
-        }
+        if (tid == 0) publish_loss(A.sc, R, A.alpha, A.beta, A.gamma, A.use_tv, A.loss_out);
     }
 }
 
@@ -352,7 +365,11 @@ struct ImageGradArgs {
     const double* edges;
     const double* iwe;
     const float* adj32;
-    const DevScalars* sc;
+    DevScalars* sc;
+    int publish;                    // != 0: the grid has one CTA more than the pointwise pass needs; it publishes the loss (publish_loss)
+    int use_tv;
+    double* loss_out;
+    double alpha, beta, gamma;
     double* dldi;                   // [R][H*W] float64 d loss / d IWE (debug tap) or null
     float* dldi32;                  // [R][H*W] float32 d loss / d IWE / (2 pi) or null
     int HW, R;
@@ -364,6 +381,12 @@ __device__ __forceinline__ void image_grad_body(const ImageGradArgs& A) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __shared__ double s_mn[kCoopMaxRefs], s_mx[kCoopMaxRefs], s_iD[kCoopMaxRefs], s_cA[kCoopMaxRefs], s_cB[kCoopMaxRefs], s_tm[kCoopMaxRefs], s_tM[kCoopMaxRefs];
+    // The last CTA of a publishing launch only evaluates the loss from the statistics (a serial chain of float64 divisions that nothing
+    // before k_theta_grad waits for) and leaves; the pointwise pass belongs to the other CTAs.
+    if (A.publish && blockIdx.x == gridDim.x - 1) {
+        if (threadIdx.x == 0) publish_loss(A.sc, A.R, A.alpha, A.beta, A.gamma, A.use_tv, A.loss_out);
+        return;
+    }
     if (threadIdx.x < A.R && A.want_grad) {
         const Stats st = A.sc->ref[threadIdx.x];
         s_mn[threadIdx.x] = st.mn; s_mx[threadIdx.x] = st.mx; s_iD[threadIdx.x] = 1.0 / st.D;
@@ -373,7 +396,7 @@ __device__ __forceinline__ void image_grad_body(const ImageGradArgs& A) {
         s_tm[threadIdx.x] = g_m / st.cnt_min; s_tM[threadIdx.x] = g_M / st.cnt_max;
     }
     __syncthreads();
-    const int T = gridDim.x * blockDim.x;
+    const int T = (A.publish ? gridDim.x - 1 : gridDim.x) * blockDim.x;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     for (int r = 0; r < A.R; ++r) {
         // 1 / D is a per-image constant: the two divisions of the reference formula become multiplications (one rounding more)

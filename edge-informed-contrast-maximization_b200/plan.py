@@ -13,7 +13,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, 'lib', 'libeincm_b200.so')
+LIB_PATH = os.environ.get('EINCM_B200_LIB') or os.path.join(_PKG_DIR, 'lib', 'libeincm_b200.so')     # the override is for A/B builds
 
 EINCM_OK = 0
 EINCM_EINVAL, EINCM_ECUDA, EINCM_ENOMEM, EINCM_ESTATE, EINCM_ERANGE, EINCM_EUNSUPPORTED = -1, -2, -3, -4, -5, -6

@@ -167,8 +167,12 @@ int eincm_batch_get_timing(eincm_batch* batch, double* ms_out /* [5] */, int64_t
 
 /* ---- native optimizers: what jaxopt's ScipyMinimize(method='BFGS').run / ScipyBoundedMinimize(method='L-BFGS-B').run do with
  * the objective (reference src/eincm/solver.py:165-183, :209-216, :325-335), without returning to Python between evaluations.
- * Same algorithms and default parameters as scipy.optimize.minimize (csrc/eincm_opt.h); status: 0 converged (max|grad| <= gtol),
- * 1 maxiter reached, 2 line search failed ("precision loss"), 3 non-finite objective - the codes solver.py:218-239 reacts to.
+ * scipy.optimize.minimize restated (csrc/eincm_opt.h): BFGS with scipy's line-search policy (MINPACK-2 dcsrch, then scalar_search_wolfe2
+ * when that fails) and the n = 1 case of L-BFGS-B 3.0 (dcsrch with xtol 0.1, restart from steepest descent after a failed search);
+ * tests/test_native_opt.py holds them to scipy's iterations, evaluations and final points.  status as scipy reports it: 0 converged
+ * (max|grad| <= gtol), 1 maxiter reached, 2 "precision loss" (both line searches failed or the objective is not finite; L-BFGS-B:
+ * abnormal termination in the line search), 3 NaN in the result - the codes solver.py:218-239 reacts to.
+ * eincm_minimize_bfgs_host keeps a dense (2hw)^2 inverse Hessian on the host: h * w <= 4096, EINCM_EINVAL beyond.
  * cuda_stream == (void*)-1 selects the plan's own stream (several plans solved concurrently from several host threads). */
 typedef struct eincm_opt_result { double fun; int32_t nit, nfev, status, reserved; } eincm_opt_result;
 int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host /* [h][w][2] */, int h, int w, const eincm_hparams* hp,

@@ -44,6 +44,25 @@ int bfgs_quartic(int n, double* x, int maxiter, double gtol, Out* out) {
     return err;
 }
 
+// log barrier at v_i = 1 (NaN beyond it): the first trial step of a line search lands outside the domain, dcsrch gives up on the
+// non-finite value and the wolfe2 fallback has to bisect back into the domain
+int bfgs_barrier(int n, double* x, int maxiter, double gtol, Out* out) {
+    eincm_opt::Objective f = [n](const double* v, double* fv, double* g) -> int {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double c = 1.0 + i;
+            s += c * (v[i] - 2.0) * (v[i] - 2.0) - std::log(1.0 - v[i]);
+            g[i] = 2.0 * c * (v[i] - 2.0) + 1.0 / (1.0 - v[i]);
+        }
+        *fv = s;
+        return 0;
+    };
+    int err = 0;
+    const eincm_opt::Result r = eincm_opt::bfgs(f, n, x, maxiter, gtol, &err);
+    out->fun = r.fun; out->nit = r.nit; out->nfev = r.nfev; out->status = r.status; out->pad = 0;
+    return err;
+}
+
 // scalar: f(a) = (a - m)^2 + 0.3 sin(5 a), a in [lo, hi]
 int bounded_scalar_wavy(double m, double* a, double lo, double hi, int maxiter, double pgtol, Out* out) {
     eincm_opt::Objective f = [m](const double* v, double* fv, double* g) -> int {

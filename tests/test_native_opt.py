@@ -83,3 +83,53 @@ def test_bounded_scalar_matches_lbfgsb(lib, m, lo, hi, a0):
     assert lo <= a.value <= hi
     assert out.fun <= ref.fun + 1e-7                            # at least as good a point as L-BFGS-B finds
     assert abs(a.value - ref.x[0]) <= 1e-3 or out.fun < ref.fun - 1e-9
+
+
+@pytest.mark.parametrize('n', [1, 4])
+@pytest.mark.parametrize('start', [0.0, 0.5, 0.9, 0.99, -3.0])
+def test_bfgs_falls_back_to_wolfe2_like_scipy(lib, n, start):
+    """scipy's _line_search_wolfe12: when dcsrch fails (here: a trial step leaves the domain of a log barrier, the objective is NaN)
+    scalar_search_wolfe2 takes over - it bisects back into the domain, or, like scipy, walks on into the NaN region and ends with
+    status 2.  Same status, iterations, final point and evaluations as scipy either way (the first version stopped with
+    status 2 at the first dcsrch failure)."""
+    def f(v):
+        c = 1.0 + np.arange(n)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            return float((c * (v - 2.0) ** 2 - np.log(1.0 - v)).sum()), 2.0 * c * (v - 2.0) + 1.0 / (1.0 - v)
+
+    x0 = np.full(n, start)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = scipy.optimize.minimize(f, x0, jac=True, method='BFGS', options={'gtol': 1e-7, 'maxiter': 200})
+    x = x0.copy()
+    out = Out()
+    assert lib.bfgs_barrier(n, x.ctypes.data_as(C.POINTER(C.c_double)), 200, C.c_double(1e-7), C.byref(out)) == 0
+    assert (out.status, out.nit) == (ref.status, ref.nit)
+    assert abs(out.nfev - ref.nfev) <= 1                       # one more evaluation of a NaN point on some failing searches
+    np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-12)
+    assert (np.isnan(out.fun) and np.isnan(ref.fun)) or abs(out.fun - ref.fun) <= 1e-12 * abs(ref.fun)
+
+
+@pytest.mark.parametrize('n', [2, 8])
+def test_bfgs_same_schedule_as_scipy(lib, n):
+    """Same line-search policy and parameters: the native BFGS takes the iterations and evaluations scipy takes."""
+    x0 = np.linspace(-1.2, 1.0, n)
+    ref = scipy.optimize.minimize(_rosen, x0, jac=True, method='BFGS', options={'gtol': 1e-7, 'maxiter': 2000})
+    x = x0.copy()
+    out = Out()
+    lib.bfgs_rosenbrock(n, x.ctypes.data_as(C.POINTER(C.c_double)), 2000, C.c_double(1e-7), C.byref(out))
+    assert abs(out.nit - ref.nit) <= max(1, ref.nit // 20) and abs(out.nfev - ref.nfev) <= max(2, ref.nfev // 20)
+
+
+@pytest.mark.parametrize('m,lo,hi,a0', [(0.3, 0.0, 1.0, 0.5), (1.7, 0.0, 1.0, 0.5), (-0.4, 0.0, 1.0, 0.5), (0.6, 0.0, 1.0, 0.0), (0.45, 0.0, 1.0, 0.9)])
+def test_bounded_scalar_same_schedule_as_lbfgsb(lib, m, lo, hi, a0):
+    def f(a):
+        return float((a[0] - m) ** 2 + 0.3 * np.sin(5 * a[0])), np.array([2 * (a[0] - m) + 1.5 * np.cos(5 * a[0])])
+
+    ref = scipy.optimize.minimize(f, np.array([a0]), jac=True, method='L-BFGS-B', bounds=[(lo, hi)], options={'gtol': 1e-6, 'maxiter': 20})
+    a = C.c_double(a0)
+    out = Out()
+    assert lib.bounded_scalar_wavy(C.c_double(m), C.byref(a), C.c_double(lo), C.c_double(hi), 20, C.c_double(1e-6), C.byref(out)) == 0
+    assert abs(a.value - ref.x[0]) <= 1e-6
+    assert (out.nit, out.nfev) == (ref.nit, ref.nfev)
