@@ -736,6 +736,20 @@ int eincm_plan_info(const eincm_plan* plan, int* H, int* W, int64_t* n_events, i
     return EINCM_OK;
 }
 
+int eincm_plan_set_window_device_ts(eincm_plan* plan, const int16_t* xs, const int16_t* ys, const double* ts, int64_t n, const double* edges,
+                                    const double* edge_ts_dev, int R, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (R < 1 || R > plan->max_refs) return fail(plan, EINCM_EINVAL, "n_refs %d outside 1..max_refs=%d", R, plan->max_refs);
+    if (!edge_ts_dev) return fail(plan, EINCM_EINVAL, "NULL operand");
+    CU(cudaSetDevice(plan->device));
+    double t_host[EINCM_MAX_REFS];
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // the reference times become kernel constants: one small copy and one synchronisation per window (set_window synchronises anyway)
+    CU(cudaMemcpyAsync(t_host, edge_ts_dev, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return eincm_plan_set_window(plan, xs, ys, ts, n, edges, t_host, R, cuda_stream);
+}
+
 int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys, const double* ts, int64_t n, const double* edges,
                           const double* edge_ts_host, int R, void* cuda_stream) {
     if (!plan) return EINCM_EINVAL;

@@ -28,6 +28,7 @@ S_HEADER = 8
 # every symbol include/eincm.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     'eincm_plan_create', 'eincm_plan_destroy', 'eincm_last_error', 'eincm_abi_version', 'eincm_plan_set_window',
+    'eincm_plan_set_window_device_ts',
     'eincm_value_and_grad', 'eincm_handover_value_and_grad', 'eincm_value_and_grad_host',
     'eincm_handover_value_and_grad_host', 'eincm_value_and_grad_stateless_host', 'eincm_value_and_grad_host_batch',
     'eincm_window_finalize',
@@ -126,6 +127,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_last_error': (C.c_char_p, [vp]),
         'eincm_abi_version': (i32, []),
         'eincm_plan_set_window': (i32, [vp, vp, vp, vp, i64, vp, C.POINTER(dbl), i32, vp]),
+        'eincm_plan_set_window_device_ts': (i32, [vp, vp, vp, vp, i64, vp, vp, i32, vp]),
         'eincm_value_and_grad': (i32, [vp, vp, i32, i32, hp, vp, vp, vp]),
         'eincm_handover_value_and_grad': (i32, [vp, dbl, vp, vp, i32, i32, hp, vp, vp, vp]),
         'eincm_value_and_grad_host': (i32, [vp, vp, i32, i32, hp, C.POINTER(dbl), vp, vp]),

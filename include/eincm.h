@@ -6,7 +6,7 @@
  * (reference src/eincm/solver.py:165-183, invoked :209-216, :227-234, :325-335).  Every entry point cites
  * the reference interface it replaces.  The reference is pure Python on JAX; its "FFI" for this path is a
  * JAX custom call (`jax.ffi.ffi_call`) whose handler forwards to the functions below - see INTEGRATION.md
- * for the binding a maintainer would add on the reference side, and csrc/eincm_xla_ffi.cc for the handler.
+ * for the binding a maintainer would add on the reference side, and integration/xla_ffi/eincm_xla_ffi.cc for the handler.
  *
  * Conventions
  *   - plain C, no torch / JAX / C++ types; `cuda_stream` is a `cudaStream_t` passed as `void*`.
@@ -110,6 +110,11 @@ int eincm_abi_version(void);
  * every objective evaluation.  edge_ts_host: R float64 on the HOST (they become kernel constants). */
 int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys, const double* ts, int64_t n_events,
                           const double* edges, const double* edge_ts_host, int n_refs, void* cuda_stream);
+/* Same with the reference times in DEVICE memory, as a JAX custom call receives them: `edge_ts` is a traced operand of the
+ * jitted objective (reference src/eincm/solver.py:209-216), so the XLA FFI handler (integration/xla_ffi/eincm_xla_ffi.cc)
+ * only ever sees a device buffer.  One small device-to-host copy and one more synchronisation of `cuda_stream` per window. */
+int eincm_plan_set_window_device_ts(eincm_plan* plan, const int16_t* xs, const int16_t* ys, const double* ts, int64_t n_events,
+                                    const double* edges, const double* edge_ts, int n_refs, void* cuda_stream);
 
 /* ---- per evaluation: replaces jit(value_and_grad(partial(loss_func, cur_pyr_lvl=l)))(theta, xs, ys, ts, edges, edge_ts)
  * (reference src/eincm/losses.py:108-205 differentiated w.r.t. argument 0; built by jaxopt from solver.py:165-173).
