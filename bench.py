@@ -275,9 +275,11 @@ def event_split_measure(world, rank, local_rank, total_events, steps=5, warmup=3
         dist.broadcast(th, 0)                               # one theta for all ranks
     res = {'workload': f'large: ONE window of {W}x{H}, N={n_local * world} events split over {world} GPU(s), R={R}, theta {theta}x{theta}x2',
            'scaling': 'strong', 'unit': UNIT}
-    for mode, p2p in (('nccl_allreduce_of_images', False), ('peer_fused_splat', True)):
+    for mode, p2p, fixed in (('nccl_allreduce_of_images', False, False), ('nccl_allreduce_of_fixed_point_images', False, True),
+                             ('peer_fused_splat', True, False)):
         plan = P.Plan((H, W), max_events=n_local, max_refs=max(R, 3), flags=P.FLAG_EVENT_SPLIT)
-        obj = PAR.EventSplitObjective(plan, lambda lvl: P.make_hparams(hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], lvl), p2p=p2p)
+        obj = PAR.EventSplitObjective(plan, lambda lvl: P.make_hparams(hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], lvl), p2p=p2p,
+                                      fixed_point=fixed)
         obj.set_datasample(win.xs, win.ys, win.ts, win.edges, win.edge_ts, need_mask=False)
         loss = torch.zeros(1, dtype=torch.float64, device='cuda')
         grad = torch.zeros_like(th)

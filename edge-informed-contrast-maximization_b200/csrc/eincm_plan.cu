@@ -68,7 +68,8 @@ struct eincm_plan {
     bool theta_full_valid = false;
     unsigned long long* peer_fix[kMaxPeers] = {};   // event split with peer access: fixed-point images of all ranks (own included)
     void* peer_opened[kMaxPeers] = {};              // pointers obtained from cudaIpcOpenMemHandle (closed on destroy)
-    int n_peers = 0;                                // 0: no peer access (the caller all-reduces the float64 images)
+    int n_peers = 0;                                // 0: no peer access (the caller all-reduces the images)
+    bool split_fixed = false;                       // event split without peer access: the caller all-reduces the FIXED-POINT images (int64)
     eincm_group* group = nullptr;        // evaluation group this plan rendezvous with inside eincm_minimize_bfgs_host (or null)
     cudaEvent_t wait_ev = nullptr;       // EINCM_FLAG_BLOCKING_SYNC: blocking-sync event the host entry points sleep on
     cudaStream_t own_stream = nullptr;   // for the batched host call: every plan of a batch runs on its own stream
@@ -386,7 +387,7 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
     // default path (single GPU, delta == 0): the fixed-point images are consumed by the fused image pass directly
     // single GPU, or event split with peer access (every rank then holds the complete fixed-point images after the barrier)
     plan->rec_pending = false;
-    plan->fused_pending = !plan->exact && plan->coop_ok && (!(plan->flags & EINCM_FLAG_EVENT_SPLIT) || plan->n_peers > 0) && hp->delta == 0.0;
+    plan->fused_pending = !plan->exact && plan->coop_ok && (!(plan->flags & EINCM_FLAG_EVENT_SPLIT) || plan->n_peers > 0 || plan->split_fixed) && hp->delta == 0.0;
     if ((rc = splat_images(plan, plan->tsrc, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
     plan->forward_done = true;
@@ -1305,6 +1306,14 @@ int eincm_plan_set_event_split(eincm_plan* plan, int rank, int world) {
     if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return fail(plan, EINCM_ESTATE, "plan was not created with EINCM_FLAG_EVENT_SPLIT");
     if (world < 1 || rank < 0 || rank >= world) return fail(plan, EINCM_EINVAL, "rank %d outside 0..%d", rank, world - 1);
     plan->split_rank = rank; plan->split_world = world;
+    return EINCM_OK;
+}
+
+int eincm_plan_set_split_fixed_point(eincm_plan* plan, int on) {
+    if (!plan) return EINCM_EINVAL;
+    if (!(plan->flags & EINCM_FLAG_EVENT_SPLIT)) return fail(plan, EINCM_ESTATE, "plan was not created with EINCM_FLAG_EVENT_SPLIT");
+    if (plan->exact || !plan->iwe_fix) return fail(plan, EINCM_ESTATE, "the fixed-point all-reduce needs the default (fixed-point) path");
+    plan->split_fixed = on != 0;
     return EINCM_OK;
 }
 

@@ -379,6 +379,9 @@ template <bool WRAP>
 __device__ __noinline__ void splat_fallback(const FixDst& dst, int64_t img_off, uint32_t xy, double2 th, double dt, int H, int W) {
     const Hit2 h = warp_hit2(xy, th, dt);
     if (!((fabs(h.xw) < 1.0e9) && (fabs(h.yw) < 1.0e9))) return;
+    // the whole patch is out of range under the index rule (line-search trial steps of BFGS reach flows of thousands of pixels,
+    // where that is every event): nothing to add, no tap values needed
+    if (h.rx + 1 < (WRAP ? -W : 0) || h.rx - 1 >= W || h.ry + 1 < (WRAP ? -H : 0) || h.ry - 1 >= H) return;
     const TapsFix t = taps_fix(h.fx, h.fy);
     for (int j = 0; j < 3; ++j)
         for (int i = 0; i < 3; ++i) {
@@ -414,6 +417,7 @@ template <bool WRAP>
 __device__ __noinline__ float2 gather_fallback(const float* __restrict__ img, uint32_t xy, double2 th, double dt, int H, int W) {
     const Hit2 h = warp_hit2(xy, th, dt);
     if (!((fabs(h.xw) < 1.0e9) && (fabs(h.yw) < 1.0e9))) return make_float2(0.f, 0.f);
+    if (h.rx + 1 < (WRAP ? -W : 0) || h.rx - 1 >= W || h.ry + 1 < (WRAP ? -H : 0) || h.ry - 1 >= H) return make_float2(0.f, 0.f);
     float d[9];
     for (int j = -1; j <= 1; ++j)
         for (int i = -1; i <= 1; ++i) {

@@ -57,13 +57,16 @@ class EventSplitObjective:
     methods - the CPU tests drive this class with an oracle-backed stand-in over gloo).  Every rank passes ITS events to
     ``set_datasample``; ``value_and_grad`` returns the same ``(loss, grad)`` on every rank.
 
+    ``fixed_point=True``: the per-evaluation all-reduce runs on the int64 fixed-point images (same bytes, order-independent sums, the
+    fused image pass follows directly).
+
     ``p2p=True`` (GPUs of one NVLink domain, NCCL group): the ranks exchange the CUDA IPC handles of their fixed-point image
     buffers once, and from then on every splat adds its votes to the images of ALL ranks over NVLink - the all-reduce of the
     ``R*H*W`` images is fused into the splat kernel (``include/eincm.h``); the only collectives left per evaluation are two
     one-element barriers and the all-reduce of the small flow gradient."""
 
     def __init__(self, plan, make_hparams: Callable, group=None, rank: Optional[int] = None, world: Optional[int] = None,
-                 p2p: bool = False):
+                 p2p: bool = False, fixed_point: bool = False):
         import torch.distributed as dist
         self.dist = dist
         self.plan = plan
@@ -75,6 +78,11 @@ class EventSplitObjective:
         self.n_collectives = 0
         self.collective_bytes = 0
         self.p2p = bool(p2p)
+        # all-reduce the int64 fixed-point images instead of the float64 ones: bit-identical sums on every rank whatever the reduction
+        # order, and the fused image pass runs on them directly (include/eincm.h: eincm_plan_set_split_fixed_point)
+        self.fixed_point = bool(fixed_point) and not self.p2p
+        if self.fixed_point:
+            plan.set_split_fixed_point(True)
         self._token = None
         if self.p2p:
             handles = [None] * self.world
@@ -124,7 +132,7 @@ class EventSplitObjective:
             self._barrier()                                              # all votes have landed: images complete everywhere
         else:
             self.plan.forward_events(theta, hp)
-            self._allreduce(self.plan.iwe())                             # C1: partial images of warped events
+            self._allreduce(self.plan.iwe_fix() if self.fixed_point else self.plan.iwe())    # C1: partial images of warped events
         self.plan.backward(hp, loss_out, grad_out)
         self._allreduce(grad_out)                                        # C2: partial flow-parameter gradients
         return loss_out, grad_out

@@ -28,7 +28,7 @@ S_HEADER = 8
 # every symbol include/eincm.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     'eincm_plan_create', 'eincm_plan_destroy', 'eincm_last_error', 'eincm_abi_version', 'eincm_plan_set_window',
-    'eincm_plan_set_window_device_ts',
+    'eincm_plan_set_window_device_ts', 'eincm_plan_set_split_fixed_point',
     'eincm_value_and_grad', 'eincm_handover_value_and_grad', 'eincm_value_and_grad_host',
     'eincm_handover_value_and_grad_host', 'eincm_value_and_grad_stateless_host', 'eincm_value_and_grad_host_batch',
     'eincm_window_finalize',
@@ -145,6 +145,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_get_scalars': (i32, [vp, C.POINTER(dbl), i32, vp]),
         'eincm_debug_rounded_pixels': (i32, [vp, i32, vp, vp, vp]),
         'eincm_plan_set_event_split': (i32, [vp, i32, i32]),
+        'eincm_plan_set_split_fixed_point': (i32, [vp, i32]),
         'eincm_plan_ipc_handle': (i32, [vp, vp, i32]),
         'eincm_plan_set_peers': (i32, [vp, vp, i32]),
         'eincm_plan_set_peer_pointers': (i32, [vp, C.POINTER(vp), i32]),
@@ -400,6 +401,14 @@ class Plan:
 
     def set_event_split(self, rank: int, world: int):
         self._check(self.lib.eincm_plan_set_event_split(self._h, int(rank), int(world)))
+
+    def set_split_fixed_point(self, on: bool = True):
+        """The caller all-reduces ``iwe_fix()`` (int64) instead of ``iwe()`` (float64) between forward_events and backward."""
+        self._check(self.lib.eincm_plan_set_split_fixed_point(self._h, 1 if on else 0))
+
+    def iwe_fix(self):
+        """(R, H, W) int64 CUDA tensor aliasing the fixed-point images of warped events (2^21 * 2 pi * value)."""
+        return self._view(self.lib.eincm_iwe_fix_ptr(self._h), (self.n_refs, self.H, self.W), '<i8')
 
     # -- event split with peer access (fused splat + all-reduce over NVLink) ---------------------------------------
     IPC_HANDLE_BYTES = 64

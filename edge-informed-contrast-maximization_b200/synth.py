@@ -76,7 +76,7 @@ def _box_blur3(img: np.ndarray) -> np.ndarray:
 def make_window(H: int, W: int, N: int, edge_ts=(0.0, 0.5, 1.0), seed: int = 0, n_segments: int = 200,
                 flow_mag: float = 20.0, truth_tiles: Tuple[int, int] = (2, 2), noise_frac: float = 0.1,
                 hparams: Optional[Dict[str, float]] = None, scene_seed: Optional[int] = None,
-                truth_theta: Optional[np.ndarray] = None) -> Window:
+                truth_theta: Optional[np.ndarray] = None, jitter_px: float = 0.35) -> Window:
     """``scene_seed`` / ``truth_theta``: windows of one SEQUENCE share the scene (line segments, drawn from ``scene_seed``) and are
     given a slowly varying truth flow, while events and noise are fresh per window (``seed``) - see ``make_sequence``."""
     rng = np.random.default_rng(seed)
@@ -93,7 +93,7 @@ def make_window(H: int, W: int, N: int, edge_ts=(0.0, 0.5, 1.0), seed: int = 0, 
     ang = rs.uniform(0, np.pi, size=n_segments)
     pts_per_seg = np.maximum(4, (seg_len * 2).astype(int))
     seg_id = np.repeat(np.arange(n_segments), pts_per_seg)
-    u = rng.uniform(-0.5, 0.5, size=seg_id.size)
+    u = rs.uniform(-0.5, 0.5, size=seg_id.size)                    # part of the scene: ranks of an event split share the edge images
     px = cx[seg_id] + u * seg_len[seg_id] * np.cos(ang[seg_id])
     py = cy[seg_id] + u * seg_len[seg_id] * np.sin(ang[seg_id])
     keep = (px >= 1) & (px < W - 1) & (py >= 1) & (py < H - 1)
@@ -114,7 +114,7 @@ def make_window(H: int, W: int, N: int, edge_ts=(0.0, 0.5, 1.0), seed: int = 0, 
     n_sig = N - n_noise
     which = rng.integers(0, px.size, size=n_sig)
     t_sig = rng.uniform(0.0, 1.0, size=n_sig)
-    jitter = rng.normal(0.0, 0.35, size=(n_sig, 2))
+    jitter = rng.normal(0.0, jitter_px, size=(n_sig, 2))
     ex = px[which] + pf[which, 0] * t_sig + jitter[:, 0]
     ey = py[which] + pf[which, 1] * t_sig + jitter[:, 1]
     xs = np.concatenate([np.rint(ex), rng.integers(0, W, size=n_noise).astype(np.float64)])
@@ -129,26 +129,31 @@ def make_window(H: int, W: int, N: int, edge_ts=(0.0, 0.5, 1.0), seed: int = 0, 
 
 
 def make_workload(name: str, seed: int = 0, n_events: Optional[int] = None, scene_seed: Optional[int] = None,
-                  truth_theta: Optional[np.ndarray] = None) -> Window:
+                  truth_theta: Optional[np.ndarray] = None, **scene) -> Window:
     cfg = dict(WORKLOADS[name])
     N = n_events if n_events is not None else cfg['N']
     hp = dict(alpha=cfg['alpha'], beta=cfg['beta'], gamma=cfg['gamma'], delta=0.0)
-    n_seg = max(20, int(200 * (cfg['H'] * cfg['W']) / (480 * 640)))
+    n_seg = scene.pop('n_segments', None) or max(20, int(200 * (cfg['H'] * cfg['W']) / (480 * 640)))
     mag = 20.0 * min(1.0, cfg['W'] / 640 + 0.25)
     return make_window(cfg['H'], cfg['W'], N, cfg['edge_ts'], seed=seed, n_segments=n_seg,
-                       flow_mag=mag, hparams=hp, scene_seed=scene_seed, truth_theta=truth_theta)
+                       flow_mag=mag, hparams=hp, scene_seed=scene_seed, truth_theta=truth_theta, **scene)
 
 
-def make_sequence(name: str, n_windows: int, seed: int = 0, n_events: Optional[int] = None, drift: float = 0.08):
+def make_sequence(name: str, n_windows: int, seed: int = 0, n_events: Optional[int] = None, drift: float = 0.08, **scene):
     """``n_windows`` consecutive windows of one synthetic SEQUENCE: the same scene, a truth flow that drifts slowly from window to
     window (a random direction per truth tile, ``drift`` x the flow magnitude per window: consecutive DSEC windows have similar
     flow, which is what the reference's handover prior - src/eincm/solver.py:302-347 - relies on), fresh events and noise."""
     cfg = WORKLOADS[name]
     mag = 20.0 * min(1.0, cfg['W'] / 640 + 0.25)
+    # Edge-dense scene (four times the line segments of the single-window workloads), like the driving scenes of DSEC.  On a sparse
+    # scene the reference objective is unbounded below in practice: its correlation term, mean(w_r * MSE_r / MSE_zero) with a NEGATIVE
+    # sign (src/eincm/losses.py:176, 186), rewards smearing the events into a flat image, and with few edge pixels MSE_zero is so small
+    # that this outweighs the contrast term - scipy's BFGS then runs to flows of thousands of pixels (profiles/r2_objective_landscape.txt).
+    scene.setdefault('n_segments', 4 * max(20, int(200 * (cfg['H'] * cfg['W']) / (480 * 640))))
     rs = np.random.default_rng(10_000 + seed)
     theta0 = rs.uniform(-mag, mag, size=(2, 2, 2))
     step = rs.normal(0.0, 1.0, size=(2, 2, 2)) * drift * mag
-    return [make_workload(name, seed=1000 * seed + k + 1, n_events=n_events, scene_seed=20_000 + seed, truth_theta=theta0 + k * step)
+    return [make_workload(name, seed=1000 * seed + k + 1, n_events=n_events, scene_seed=20_000 + seed, truth_theta=theta0 + k * step, **scene)
             for k in range(n_windows)]
 
 

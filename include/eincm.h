@@ -207,6 +207,12 @@ int eincm_window_finalize(eincm_plan* plan, void* cuda_stream);
 int eincm_plan_set_event_split(eincm_plan* plan, int rank, int world);
 int eincm_forward_events(eincm_plan* plan, const double* theta, int h, int w, const eincm_hparams* hp, void* cuda_stream);
 int eincm_backward(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, double* grad_out, void* cuda_stream);
+/* Fixed-point form of the per-evaluation collective (on != 0): eincm_forward_events leaves this rank's votes in the FIXED-POINT images
+ * and the caller all-reduces(sum, int64) eincm_iwe_fix_ptr [R*H*W] instead of the float64 images.  Integer sums do not depend on the
+ * order of the reduction: every rank holds bit-identical complete images whatever algorithm the collective uses, eincm_backward runs
+ * the fused image pass on them directly (no float64 copy, two image kernels instead of five), and the objective is bit-identical on
+ * all ranks and equal to the single-GPU value.  (delta != 0 falls back to the float64 images.) */
+int eincm_plan_set_split_fixed_point(eincm_plan* plan, int on);
 /* ---- event split with peer access: the all-reduce of the partial images fused into the splat --------------------
  * One process per GPU of one NVLink / NVSwitch domain.  Every rank publishes the CUDA IPC handle of its fixed-point image
  * buffer (eincm_plan_ipc_handle, 64 bytes), the caller exchanges the handles (torch.distributed all-gather) and hands all of

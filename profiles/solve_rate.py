@@ -19,10 +19,12 @@ ap.add_argument('--repeat', type=int, default=3)
 ap.add_argument('--blocking', action='store_true')
 ap.add_argument('--group', action='store_true', help='rendezvous the evaluations of the sequences (eincm_group)')
 ap.add_argument('--burst', type=int, default=100)
+ap.add_argument('--main-thread', action='store_true', help='threads == 1: run the sequence in the main thread')
 a = ap.parse_args()
 dev = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(dev)
-wins = [synth.make_workload(a.workload, seed=k) for k in range(4)]
+seqs = [synth.make_sequence(a.workload, 1 + a.windows * a.repeat, seed=t) for t in range(a.threads)]       # the bench's drifting sequences
+wins = seqs[0]
 H, W = wins[0].sensor_size
 hpd = wins[0].hparams
 N, R = len(wins[0].xs), len(wins[0].edge_ts)
@@ -34,8 +36,9 @@ if grp is not None:
         o.plan.set_group(grp)
 sols = [SV.MultipleLevelEINCMSolver(o, backend='native', own_stream=True) for o in objs]
 for t, sol in enumerate(sols):
-    sol.set_datasample(*wins[t % 4].args())
+    sol.set_datasample(*seqs[t][0].args())
     sol.solve()
+cursor = [1] * a.threads
 per_thread = [0.0] * a.threads
 
 
@@ -43,7 +46,8 @@ def work(t):
     torch.cuda.set_device(dev)
     t0 = time.perf_counter()
     for k in range(a.windows):
-        sols[t].set_datasample(*wins[(t + k + 1) % 4].args())
+        sols[t].set_datasample(*seqs[t][cursor[t]].args())
+        cursor[t] += 1
         sols[t].solve()
     per_thread[t] = time.perf_counter() - t0
 
@@ -68,11 +72,14 @@ def probes():
 for rep in range(a.repeat):
     n0 = sum(o.n_evals for o in objs)
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(t,)) for t in range(a.threads)]
-    for th in ths:
-        th.start()
-    for th in ths:
-        th.join()
+    if a.main_thread and a.threads == 1:
+        work(0)
+    else:
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(a.threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     n_ev = sum(o.n_evals for o in objs) - n0
