@@ -44,8 +44,8 @@ def _peaks():
 
 
 def measured_traffic():
-    """DRAM bytes per launch from the committed ncu capture of this command (profiles/r1_traffic.json)."""
-    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    """DRAM bytes per launch from the committed ncu capture of this command (profiles/r2_traffic.json)."""
+    p = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     try:
         with open(p) as f:
             return json.load(f)['dram_bytes_per_launch']
