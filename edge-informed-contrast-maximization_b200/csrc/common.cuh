@@ -21,10 +21,6 @@ struct Stats {
     double div;        // iwe_divergence                 event_collapse_objectives.py:8-20
 };
 
-// Per-reference coefficients of d loss / d IWE / (2 pi) as the fused backward fill evaluates it per cell (k_backward_fold):
-//   cA * adjoint + a1 * E - a2 * I + a3 + [I == mn] * tm + [I == mx] * tM      (see k_image_grad for the derivation)
-struct CotCoef { double cA, a1, a2, a3, mn, mx, tm, tM; };
-
 struct DevScalars {
     Stats ref[EINCM_MAX_REFS];    // warped IWE_r
     Stats zero[EINCM_MAX_REFS];   // zero-IWE against edge_r (contrast/min/max/div live in zero[0])
@@ -35,7 +31,6 @@ struct DevScalars {
     double coefB[EINCM_MAX_REFS]; // b_r * -2/HW  (correlation cotangent scale)
     double coefD[EINCM_MAX_REFS]; // d_r / HW     (divergence cotangent scale)
     double sumE[EINCM_MAX_REFS], sumE2[EINCM_MAX_REFS];   // per-window sums of edge_r and edge_r^2 (fused image pass)
-    CotCoef cot[EINCM_MAX_REFS];  // written by the last CTA of k_image_stats
     double eval_seq;              // evaluations delivered to the host so far (incremented by the kernel that delivers a result)
     unsigned int counters[16];    // "last block done" tickets
     int error_flag;               // set by kernels on invalid input (event outside the sensor)

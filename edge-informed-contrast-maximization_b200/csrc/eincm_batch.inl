@@ -219,8 +219,8 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
             s.ev_xy = p->ev_xy; s.ev_t = p->ev_t; s.chunks = p->chunks; s.chunk_tr = p->chunk_tr; s.n_chunks_dev = p->totals + 1;
             s.T = T; s.H = H; s.W = W; s.R = R; s.tref = p->tref; s.dst.n = 1; s.dst.p[0] = p->iwe_fix; s.chunk_win = p->chunk_win;
             ImageStatsArgs& i = ia[k];
-            i.rec = nullptr; i.e32 = p->e32; i.fix = p->iwe_fix; i.edges = p->edges; i.iwe = p->iwe; i.adj32 = p->adj32;
-            i.part = p->part; i.tail_here = 0; i.sc = p->sc; i.loss_out = loss_out[k];
+            i.fix = p->iwe_fix; i.edges = p->edges; i.iwe = p->iwe; i.adj32 = p->adj32;
+            i.part = p->part; i.sc = p->sc; i.loss_out = loss_out[k];
             i.zero_buf = Gk; i.n_zero = (int)(HW * 2);
             i.zero_buf2 = dense ? nullptr : grad_out[k]; i.n_zero2 = dense ? 0 : h * w * 2;
             i.H = H; i.W = W; i.R = R; i.alpha = hp->alpha; i.beta = hp->beta; i.gamma = hp->gamma; i.use_tv = 0;
@@ -281,7 +281,7 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
     for (int k = 0; k < B; ++k) {
         eincm_plan* p = batch->plans[k];
         p->tsrc = ThetaSrc{thetas[k], nullptr, 0.0, h, w, ty, tx};
-        p->theta_full_valid = false; p->fused_pending = false; p->rec_pending = false; p->fix_clean = true; p->dldi_stale = true;
+        p->theta_full_valid = false; p->fused_pending = false; p->fix_clean = true; p->dldi_stale = true;
         p->forward_done = true; p->last_h = h; p->last_w = w; p->last_theta = thetas[k]; p->last_prev = nullptr; p->last_a_ho = 0.0;
         p->host_delivered = false;
     }

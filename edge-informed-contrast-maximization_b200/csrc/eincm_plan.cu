@@ -35,7 +35,6 @@
 #include "k_image.cuh"
 #include "k_eval.cuh"
 #include "k_image_fused.cuh"
-#include "k_backward_fold.cuh"
 #include "eincm_opt.h"
 
 using namespace eincm;
@@ -107,11 +106,6 @@ struct eincm_plan {
     double2 *theta_full = nullptr, *Gtv = nullptr, *partial = nullptr;
     double *G = nullptr, *iwe = nullptr, *zero_iwe = nullptr, *dldi = nullptr, *edges = nullptr;
     float* dldi32 = nullptr;                           // default path: float32 copy of dL/dIWE, scaled by 1/(2 pi)
-    bool fused_fill = true;                            // EINCM_FUSED_FILL=0: d loss / d IWE by k_image_grad instead of inside the backward window fill
-    bool no_fold = true;                               // the fused backward is opt-in (EINCM_FLAG_FOLD_BACKWARD or EINCM_FOLD=1)
-    CellRec* rec = nullptr;                            // [max_refs][H*W] cell records of the image pass (fused backward fill)
-    bool rec_pending = false;                          // the last evaluation left its images in `rec`: iwe / adj32 are unpacked on demand
-    float* e32 = nullptr;                              // [max_refs][H*W] float32 copy of the edge images (fused backward fill)
     cudaEvent_t window_ev = nullptr;                   // recorded behind the last kernel of set_window / window_finalize
     cudaStream_t window_stream = nullptr;              // ... on this stream; evaluations on another stream wait for it once
     bool window_ev_valid = false;
@@ -255,9 +249,6 @@ __global__ void k_set_weights(DevScalars* sc, RefTimes w, int R) {
     if (threadIdx.x < EINCM_MAX_REFS) sc->weights[threadIdx.x] = threadIdx.x < R ? w.t[threadIdx.x] : 0.0;
 }
 
-// dynamic shared memory of k_backward_fold: RB windows, reused as the [18][256] float reduction buffer of the theta fold
-size_t fold_smem_bytes(int rb) { return std::max<size_t>((size_t)rb * kWinCap * sizeof(float), (size_t)2 * kFoldTaps * kFoldTaps * 256 * sizeof(float)); }
-
 int event_grid(const eincm_plan* p, int64_t n, int threads) {
     const int64_t want = (n + threads - 1) / threads;
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 8));
@@ -386,7 +377,6 @@ int forward_events_impl(eincm_plan* plan, const double* theta, const double* pre
     }
     // default path (single GPU, delta == 0): the fixed-point images are consumed by the fused image pass directly
     // single GPU, or event split with peer access (every rank then holds the complete fixed-point images after the barrier)
-    plan->rec_pending = false;
     plan->fused_pending = !plan->exact && plan->coop_ok && (!(plan->flags & EINCM_FLAG_EVENT_SPLIT) || plan->n_peers > 0 || plan->split_fixed) && hp->delta == 0.0;
     if ((rc = splat_images(plan, plan->tsrc, plan->theta_full, plan->R, plan->tref, plan->iwe, "k_splat", st, !plan->fused_pending, true))) return rc;
     plan->last_h = h; plan->last_w = w; plan->last_theta = theta; plan->last_prev = prev; plan->last_a_ho = a_ho;
@@ -418,11 +408,6 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         LAUNCH("k_fix_to_f64", k_fix_to_f64<<<(int)std::min<int64_t>((cells + 255) / 256, plan->sm_count * 8), 256, 0, st>>>(plan->iwe_fix, cells, plan->iwe));
         plan->fused_pending = false;
     }
-    // Tile flow whose cells are at least one source tile wide (every pyramid level of the shipped recipes): the backward pass folds
-    // the per-event sums into the <= 3 x 3 theta elements of the source tile and evaluates d loss / d IWE inside its window fill -
-    // three launches per evaluation (k_backward_fold.cuh).  Otherwise: k_image_grad + k_backward_tile + k_theta_grad(_scatter).
-    const bool fold = plan->fused_pending && !use_div && !use_tv && want_grad && h * w <= kGatherMaxTiles && H >= kSortTile * h && W >= kSortTile * w &&
-                      !(plan->flags & EINCM_FLAG_EVENT_SPLIT) && plan->n_events > 0 && !plan->no_fold;
     if (plan->fused_pending) {
         if (use_tv) {
             const dim3 gridV((W + kTvTX - 1) / kTvTX, (H + kTvTY - 1) / kTvTY), blockV(kTvTX, kTvTY);
@@ -432,12 +417,9 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         const int tvb = ((W + kTvTX - 1) / kTvTX) * ((H + kTvTY - 1) / kTvTY);
         ImageStatsArgs ia{};
         ia.fix = plan->iwe_fix; ia.edges = plan->edges; ia.iwe = plan->iwe; ia.adj32 = plan->adj32;
-        ia.rec = (fold && plan->fused_fill) ? plan->rec : nullptr; ia.e32 = plan->e32;
-        plan->rec_pending = ia.rec != nullptr;
         ia.part = plan->part + 2 * tvb;                          // k_tv's partials live at the start of `part`
         ia.sc = plan->sc; ia.loss_out = loss_out;
-        ia.tail_here = (fold && plan->fused_fill) ? 1 : 0;               // no k_image_grad follows: the statistics tail runs in the last CTA
-        ia.zero_buf = (want_grad && !fold) ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
+        ia.zero_buf = want_grad ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
         g_zeroed = want_grad;
         if (want_grad && h * w <= kGatherMaxTiles) {
             ia.zero_buf2 = grad_out ? grad_out : plan->grad_buf; ia.n_zero2 = h * w * 2;
@@ -450,38 +432,6 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         auto tail_args = [&](ImageGradArgs& ga) {
             ga.publish = 1; ga.loss_out = loss_out; ga.alpha = hp->alpha; ga.beta = hp->beta; ga.gamma = hp->gamma; ga.use_tv = use_tv ? 1 : 0;
         };
-        if (fold && !plan->fused_fill) {
-            // d loss / d IWE materialised by its own (pointwise) kernel, which also clears the fixed-point images
-            ImageGradArgs ga{};
-            ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
-            ga.dldi = nullptr; ga.dldi32 = plan->dldi32; ga.HW = (int)plan->HW; ga.R = R; ga.want_grad = 1;
-            tail_args(ga);
-            LAUNCH("k_image_grad", launch_pdl(k_image_grad, dim3(std::max(1, std::min((int)((plan->HW + 1023) / 1024), plan->sm_count * 8)) + 1), dim3(256), 0, st, ga));   // + 1: the publishing CTA
-        }
-        if (fold) {
-            BackwardFoldArgs ba{};
-            ba.dldi32 = plan->fused_fill ? nullptr : plan->dldi32;
-            ba.ev_xy = plan->ev_xy; ba.ev_t = plan->ev_t; ba.chunks = plan->chunks; ba.n_chunks_dev = plan->totals + 1;
-            ba.T = plan->tsrc; ba.H = H; ba.W = W; ba.R = R; ba.tref = plan->tref;
-            ba.rec = plan->rec; ba.chunk_win = plan->chunk_win; ba.sc = plan->sc;
-            ba.grad = grad_out ? grad_out : plan->grad_buf;
-            ba.loss_dev = loss_out ? loss_out : &plan->sc->loss; ba.host_out = host_out; ba.host_grad = grad_out != nullptr ? 1 : 0;
-            ba.fix_clear = plan->fused_fill ? plan->iwe_fix : nullptr; ba.n_fix = (int64_t)R * plan->HW;
-            const int gridF = std::max(1, plan->n_chunks);
-#define BFOLD(WR, RB) LAUNCH("k_backward_fold", launch_pdl(k_backward_fold<WR, RB>, dim3(gridF), dim3(256), fold_smem_bytes(RB), st, ba))
-#define BFOLD_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BFOLD(WR, 1); break; case 2: BFOLD(WR, 2); break; \
-                                                           case 3: BFOLD(WR, 3); break; default: BFOLD(WR, 4); } } while (0)
-            if (plan->wrap) BFOLD_RB(true); else BFOLD_RB(false);
-#undef BFOLD_RB
-#undef BFOLD
-            plan->dldi_stale = true;                                 // the float64 d loss / d IWE (debug tap) is built on demand
-            plan->fused_pending = false;
-            // cells of images R .. max_refs - 1 were never written: the whole buffer is clean again
-            plan->fix_clean = true;
-            plan->host_delivered = host_out != nullptr;
-            if (dalpha_out) CU(cudaMemcpyAsync(dalpha_out, &plan->sc->dalpha, sizeof(double), cudaMemcpyDeviceToDevice, st));
-            return EINCM_OK;
-        }
         ImageGradArgs ga{};
         ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
         ga.dldi = nullptr; ga.dldi32 = plan->dldi32; ga.HW = (int)plan->HW; ga.R = R; ga.want_grad = want_grad ? 1 : 0;
@@ -621,13 +571,6 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
                       opt_in((const void*)k_backward_tile<true, RB>, RB); opt_in((const void*)k_backward_tile<false, RB>, RB)
         OPT_IN_RB(1); OPT_IN_RB(2); OPT_IN_RB(3); OPT_IN_RB(4);
 #undef OPT_IN_RB
-        auto opt_in_fold = [&](const void* fn, int rb) {
-            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fold_smem_bytes(rb));
-            max_carveout(fn);
-        };
-#define OPT_IN_FOLD(RB) opt_in_fold((const void*)k_backward_fold<true, RB>, RB); opt_in_fold((const void*)k_backward_fold<false, RB>, RB)
-        OPT_IN_FOLD(1); OPT_IN_FOLD(2); OPT_IN_FOLD(3); OPT_IN_FOLD(4);
-#undef OPT_IN_FOLD
         max_carveout((const void*)k_image_grad);
         max_carveout((const void*)k_theta_grad<false>); max_carveout((const void*)k_theta_grad<true>);
         max_carveout((const void*)k_theta_grad_scatter); max_carveout((const void*)k_tv); max_carveout((const void*)k_upsample_theta);
@@ -671,8 +614,6 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         if (!plan->exact) {
             CU(dmalloc(&plan->dldi32, RR * HW));
             CU(dmalloc(&plan->adj32, RR * HW));
-            CU(dmalloc(&plan->e32, RR * HW));
-            CU(dmalloc(&plan->rec, RR * HW));
             CU(dmalloc(&plan->iwe_fix, RR * HW));
             CU(dmalloc(&plan->chunk_win, (size_t)plan->chunk_cap * RR));
         }
@@ -688,10 +629,6 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
         CU(cudaHostGetDevicePointer((void**)&plan->h_mapped_dev, plan->h_pinned, 0));
         CU(cudaStreamCreateWithFlags(&plan->own_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&plan->window_ev, cudaEventDisableTiming));
-        // the fused backward (k_backward_fold.cuh) is opt-in: measured on a B200 it is no faster than the unfused kernels, whose small
-        // launches overlap with the event kernels of concurrently evaluated windows (profiles/r2_fold_ab.txt)
-        { const char* nf = std::getenv("EINCM_FOLD"); plan->no_fold = !((flags & EINCM_FLAG_FOLD_BACKWARD) || (nf != nullptr && nf[0] == '1')); }
-        { const char* ff = std::getenv("EINCM_FUSED_FILL"); plan->fused_fill = !(ff != nullptr && ff[0] == '0'); }
         if (flags & EINCM_FLAG_BLOCKING_SYNC) CU(cudaEventCreateWithFlags(&plan->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&plan->h_flag, sizeof(int) * 4));
         return EINCM_OK;
@@ -710,7 +647,7 @@ void eincm_plan_destroy(eincm_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
     if (plan->window_ev) cudaEventDestroy(plan->window_ev);
-    void* bufs[] = {plan->rec, plan->e32, plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
+    void* bufs[] = {plan->ev_xy, plan->ev_t, plan->perm, plan->ev_t2, plan->perm2, plan->counts, plan->cursor, plan->tile_cnt, plan->tile_start,
                     plan->chunk_first, plan->totals, plan->adj32, plan->chunks, plan->chunks2, plan->chunk_tr, plan->chunk_win, plan->iwe_fix, plan->mask, plan->theta_full,
                     plan->Gtv, plan->partial, plan->G, plan->iwe, plan->zero_iwe, plan->dldi, plan->edges, plan->sbar, plan->gNdiv,
                     plan->part, plan->sc, plan->dldi32, plan->theta_stage, plan->prev_stage, plan->grad_stage, plan->grad_buf, plan->out_stage,
@@ -810,7 +747,7 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
                                                                                                           plan->totals + 1, plan->chunk_tr));
     }
     CU(cudaMemcpyAsync(plan->edges, edges, (size_t)R * plan->HW * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc, plan->e32));
+    LAUNCH("k_edge_sums", k_edge_sums<<<R, 1024, 0, st>>>(plan->edges, plan->HW, plan->sc));
     // zero-warp IWE (losses.py:54): theta = 0 => x' = x for every reference time
     {
         RefTimes z{};
@@ -1228,25 +1165,13 @@ int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_ho
 double* eincm_zero_iwe_ptr(eincm_plan* plan) { return plan ? plan->zero_iwe : nullptr; }
 
 // debug taps: the fused path keeps the images of the last evaluation as cell records - unpack them (synchronous)
-static bool unpack_records(eincm_plan* plan) {
-    if (!plan->rec_pending) return true;
-    if (cudaSetDevice(plan->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return false;
-    const int64_t n = (int64_t)plan->R * plan->HW;
-    k_unpack_records<<<(int)std::min<int64_t>((n + 255) / 256, plan->sm_count * 8), 256>>>(plan->rec, n, plan->iwe, plan->adj32);
-    if (cudaDeviceSynchronize() != cudaSuccess) return false;
-    plan->rec_pending = false;
-    return true;
-}
-
 double* eincm_iwe_ptr(eincm_plan* plan) {
-    if (!plan || !unpack_records(plan)) return nullptr;
-    return plan->iwe;
+    return plan ? plan->iwe : nullptr;
 }
 uint8_t* eincm_mask_ptr(eincm_plan* plan) { return plan ? plan->mask : nullptr; }
 double* eincm_dldi_ptr(eincm_plan* plan) {
     if (!plan) return nullptr;
     if (plan->dldi_stale) {
-        if (!unpack_records(plan)) return nullptr;
         // the fused image pass only writes the float32 copy the event kernels read: rebuild the float64 image of the last evaluation
         // from the same operands (debug tap: synchronous)
         if (cudaSetDevice(plan->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return nullptr;

@@ -77,8 +77,9 @@ __device__ __forceinline__ void red_G(double* __restrict__ G, int W, uint32_t xy
 }
 
 
-constexpr int kChunk = (int)kChunkEvents;   // events per chunk = kEvK events per thread x 256 threads
-static_assert(kChunk == kEvK * 256 && kStreamAlign == kEvK, "one chunk = one CTA pass of kEvK events per thread");
+constexpr int kSubChunk = kEvK * 256;       // events a CTA holds in registers at a time (kEvK per thread): a chunk is processed in sub-chunks
+static_assert(kChunkEvents % kEvK == 0 && kStreamAlign == kEvK, "chunks are made of groups of kEvK events");
+static_assert((unsigned long long)kChunkEvents << 21 < (1ull << 32), "a uint32 window cell holds the votes of a whole chunk (kFixShift = 21)");
 constexpr int kWinCap = 4096;         // window cells per reference time (16 KB of uint32 / float)
 constexpr int kFixShift = 21;
 constexpr double kFixToIwe = kInv2Pi / 2097152.0;        // fixed-point sum -> image value
@@ -112,21 +113,26 @@ __device__ __forceinline__ TapsFix taps_fix(float fx, float fy) {
     return t;
 }
 
-// Thread -> event group (kEvK consecutive events of the sorted stream).  The backward pass gives consecutive groups to consecutive
-// lanes (neighbouring lanes hold the same or neighbouring source pixels: its per-pixel segmented sums run over lanes, and equal
-// shared-memory addresses are broadcasts for loads).  The splat spreads the lanes of a warp over the chunk - with nw = warps
-// needed for the chunk's groups, lane l of warp w < nw takes group nw * l + w: consecutive events land on the same or
-// neighbouring destination cells, and equal addresses inside one shared-memory ATOMIC instruction are serialised.
+// Thread -> event group (kEvK consecutive events of the sorted stream) of one SUB-CHUNK.  A chunk of up to kChunkEvents events is
+// processed kSubChunk events at a time (its groups split evenly over the sub-chunks).  The backward pass gives consecutive groups to
+// consecutive lanes (neighbouring lanes hold the same or neighbouring source pixels: its per-pixel segmented sums run over lanes, and
+// equal shared-memory addresses are broadcasts for loads).  The splat spreads the lanes of a warp over the sub-chunk - with nw = warps
+// needed for its groups, lane l of warp w < nw takes group nw * l + w: consecutive events land on the same or neighbouring destination
+// cells, and equal addresses inside one shared-memory ATOMIC instruction are serialised.
+__device__ __forceinline__ int n_subs(const Chunk ch) { return (int)((ch.count + kSubChunk - 1) / kSubChunk); }
+
 template <bool SPREAD>
-__device__ __forceinline__ void load_chunk_events(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk ch,
-                                                  EventGroup& ev) {
+__device__ __forceinline__ void load_sub_events(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk ch, int sub,
+                                                EventGroup& ev) {
+    const uint32_t G = ch.count >> 2, ns = (uint32_t)n_subs(ch), per = (G + ns - 1u) / max(ns, 1u);     // groups per sub-chunk (<= 256)
+    const uint32_t g0 = min(G, (uint32_t)sub * per), ng = min(G, g0 + per) - g0;
     uint32_t g = threadIdx.x;
     if (SPREAD) {
-        const uint32_t nw = (ch.count + 127u) >> 7, w = threadIdx.x >> 5;       // 128 events per full warp
+        const uint32_t nw = (ng + 31u) >> 5, w = threadIdx.x >> 5;                  // 32 groups (128 events) per full warp
         g = w < nw ? nw * (threadIdx.x & 31u) + w : 0xffffu;
     }
-    if (4u * g < ch.count) {
-        load_group(ev_xy, ev_t, (int64_t)(ch.start >> 2) + g, ev);
+    if (g < ng) {
+        load_group(ev_xy, ev_t, (int64_t)(ch.start >> 2) + g0 + g, ev);
     } else {
 #pragma unroll
         for (int k = 0; k < kEvK; ++k) { ev.xy[k] = kNoEvent; ev.t[k] = 0.0; }
@@ -277,17 +283,19 @@ k_chunk_trange(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev
     const int n_chunks = (int)__ldg(n_chunks_dev);
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
-        EventGroup ev;
-        load_chunk_events<false>(ev_xy, ev_t, ch, ev);
         float lo = INFINITY, hi = -INFINITY;
         bool nan = false;                       // fminf / fmaxf drop NaN operands: a NaN timestamp must poison the range instead
+        for (int sub = 0; sub < n_subs(ch); ++sub) {
+            EventGroup ev;
+            load_sub_events<false>(ev_xy, ev_t, ch, sub, ev);
 #pragma unroll
-        for (int k = 0; k < kEvK; ++k)
-            if (ev.xy[k] != kNoEvent) {
-                nan |= ev.t[k] != ev.t[k];
-                lo = fminf(lo, __double2float_rd(ev.t[k]));
-                hi = fmaxf(hi, __double2float_ru(ev.t[k]));
-            }
+            for (int k = 0; k < kEvK; ++k)
+                if (ev.xy[k] != kNoEvent) {
+                    nan |= ev.t[k] != ev.t[k];
+                    lo = fminf(lo, __double2float_rd(ev.t[k]));
+                    hi = fmaxf(hi, __double2float_ru(ev.t[k]));
+                }
+        }
         const float qnan = __int_as_float(0x7fc00000);
         const int rl = __reduce_min_sync(0xffffffffu, ordered_int(nan ? -qnan : lo));     // -NaN orders below -inf
         const int rh = __reduce_max_sync(0xffffffffu, ordered_int(nan ? qnan : hi));      // +NaN orders above +inf
@@ -455,18 +463,20 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
+        const int ns = n_subs(ch);                   // sub-chunks of <= kSubChunk events: one in registers at a time
         EventGroup ev;
-        load_chunk_events<true>(ev_xy, ev_t, ch, ev);
+        int cur_sub = 0;
+        load_sub_events<true>(ev_xy, ev_t, ch, 0, ev);
         // programmatic dependent launch: this kernel may have been scheduled while the previous kernel of the stream (the backward pass
         // of the previous evaluation: it clears the fixed-point images and reads chunk_win) was still running - only the staged
         // events were read so far
         asm volatile("griddepcontrol.wait;" ::: "memory");
         tile_theta_range(tile_theta(T, ch.origin, H, W, th_s), sbox);
-        const bool active = (ev.xy[0] != kNoEvent);      // groups are padded at their end only
         if (tid == 0) s_sliced = 0;
         int n_pairs = 0;                             // only used by the passes over further slices
         // misses are rare: the hot loop only counts hits; a thread whose count falls short repeats the window tests below
-        int n_hit = 0;
+        int n_hit = 0, n_valid_ev = 0;               // over all sub-chunks of the thread
+        bool counted = false;
         // One pass over the chunk for the windows of pairs p0 .. p0 + RB - 1.  PLAIN: pair j is reference time j (p0 < Rpad).
         auto pass = [&](auto plain_tag, const int p0) {
             constexpr bool PLAIN = decltype(plain_tag)::value;
@@ -478,8 +488,14 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
                 for (int i = tid; i < n4; i += 256) reinterpret_cast<uint4*>(win + r * kWinCap)[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             __syncthreads();
-            // votes
-            if (active) {
+            // votes: every sub-chunk of the chunk into the same windows
+            for (int sub = 0; sub < ns; ++sub) {
+            if (sub != cur_sub) { load_sub_events<true>(ev_xy, ev_t, ch, sub, ev); cur_sub = sub; }
+            if (!counted) {
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) n_valid_ev += ev.xy[k] != kNoEvent ? 1 : 0;
+            }
+            if (ev.xy[0] != kNoEvent) {              // groups are padded at their end only
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     if (p0 + r >= p_end) continue;
@@ -516,6 +532,8 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
                     if (acc_addr != kNone) emit9(acc_addr, pitch4, acc);
                 }
             }
+            }
+            counted = true;
             __syncthreads();
             // flush: non-zero window cells -> global fixed-point image (index rule applied here unless the window is interior).
             // Four cells per thread and round (one 128-bit load); most cells of a window are zero.
@@ -550,12 +568,7 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
                 }
             }
         };
-        auto count_valid = [&]() {                   // event-reference pairs of the thread
-            int n = 0;
-#pragma unroll
-            for (int k = 0; k < kEvK; ++k) n += ev.xy[k] != kNoEvent ? 1 : 0;
-            return active ? n * R : 0;
-        };
+        auto count_valid = [&]() { return n_valid_ev * R; };      // event-reference pairs of the thread (after the first pass)
         // first slice of every reference time, RB reference times per pass (no rectangle is sliced in the common case)
         for (int r0 = 0; r0 < R; r0 += RB) {
             __syncthreads();                         // th_s / sbox ready (first pass); previous flush done
@@ -604,16 +617,20 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
             }
         }
         if (n_hit != count_valid()) {                // events outside the (possibly cropped) rectangles, non-finite warps
-#pragma unroll
-            for (int k = 0; k < kEvK; ++k) {
-                if (ev.xy[k] == kNoEvent) continue;
-                const double2 th = lds_theta(th_base, ev.xy[k]);
 #pragma unroll 1
-                for (int r = 0; r < R; ++r) {
-                    const double dt = ev.t[k] - tref.t[r];
-                    const Hit2 h = warp_hit2(ev.xy[k], th, dt);
-                    if (!hits_rect(srect[r], h.xw, h.yw, slices_done))
-                        splat_fallback<WRAP>(dst, (int64_t)r * HW, ev.xy[k], th, dt, H, W);
+            for (int sub = 0; sub < ns; ++sub) {
+                if (sub != cur_sub) { load_sub_events<true>(ev_xy, ev_t, ch, sub, ev); cur_sub = sub; }
+#pragma unroll
+                for (int k = 0; k < kEvK; ++k) {
+                    if (ev.xy[k] == kNoEvent) continue;
+                    const double2 th = lds_theta(th_base, ev.xy[k]);
+#pragma unroll 1
+                    for (int r = 0; r < R; ++r) {
+                        const double dt = ev.t[k] - tref.t[r];
+                        const Hit2 h = warp_hit2(ev.xy[k], th, dt);
+                        if (!hits_rect(srect[r], h.xw, h.yw, slices_done))
+                            splat_fallback<WRAP>(dst, (int64_t)r * HW, ev.xy[k], th, dt, H, W);
+                    }
                 }
             }
         }
@@ -680,17 +697,26 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const Chunk ch = chunks[c];
+        const int ns = n_subs(ch);                   // sub-chunks of <= kSubChunk events: one in registers at a time
         EventGroup ev;
-        load_chunk_events<false>(ev_xy, ev_t, ch, ev);
+        load_sub_events<false>(ev_xy, ev_t, ch, 0, ev);
         tile_theta(T, ch.origin, H, W, th_s);
         // programmatic dependent launch: everything above read the staged events and the flow operand only
         if (c == (int)blockIdx.x) asm volatile("griddepcontrol.wait;" ::: "memory");
-        const bool active = 4u * (unsigned)tid < ch.count;
+        // With R <= RB (one group of reference times: the shipped recipes up to R = 4) the windows are filled once and every sub-chunk
+        // gathers from them; otherwise they are refilled per (sub-chunk, group).
+        const bool one_group = R <= RB;
+        bool filled = false;
+        for (int sub = 0; sub < ns; ++sub) {
+        if (sub > 0) load_sub_events<false>(ev_xy, ev_t, ch, sub, ev);
+        const bool active = ev.xy[0] != kNoEvent;    // groups are padded at their end only
         float ax[kEvK], ay[kEvK];
 #pragma unroll
         for (int k = 0; k < kEvK; ++k) { ax[k] = 0.f; ay[k] = 0.f; }
         for (int r0 = 0; r0 < R; r0 += RB) {
-            if (r0 > 0) __syncthreads();             // previous readers of swin / dwin are done
+            if (!(one_group && filled)) {
+            if (filled) __syncthreads();             // previous readers of swin / dwin are done
+            filled = true;
             if (tid < RB) {
                 int4 q = make_int4(0, 0, 0, 0);
                 if (r0 + tid < R) q = chunk_win[(int64_t)c * R + r0 + tid];
@@ -726,6 +752,7 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
                 }
             }
             __syncthreads();
+            }
             int n_hit = 0, n_valid = 0;
             if (active) {
 #pragma unroll
@@ -805,6 +832,7 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
         const uint32_t prev = __shfl_up_sync(0xffffffffu, run_xy, 1);
         const bool head = (lane == 0) || (prev != run_xy);
         if (head && run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
+        }
         __syncthreads();                             // th_s / swin / dwin are rewritten for the next chunk
     }
 }

@@ -74,20 +74,12 @@ constexpr int kS2Rows = EINCM_S2_ROWS;                         // own rows of a 
 constexpr int kS2Pre = 4;                           // rows per load group
 constexpr int kStatsTicket = 6;                     // DevScalars::counters slot of the "last CTA" ticket
 
-// One cell of the image pass as the fused backward fill reads it (k_backward_fold): ONE 16-byte load per window cell instead of
-// three loads from three images.
-struct __align__(16) CellRec { double I; float adj; float e; };   // image value, Scharr adjoint (up to coefA), float32 edge value
-
 struct ImageStatsArgs {
-    CellRec* rec;                   // non-null: write [R][H*W] cell records instead of the dense iwe / adj32 images
-    const float* e32;               // [R][H*W] float32 edge images (only read when rec != null)
     const unsigned long long* fix;  // [R][H*W] fixed-point images of warped events
     const double* edges;            // [R][H*W]
     double* iwe;                    // [R][H*W] float64 images (out)
     float* adj32;                   // [R][H*W] adjoint of the Scharr pair applied to (Gx, Gy) (out; d contrast / d IWE up to cA)
     double* part;                   // [R][image_stats_ctas(H, W)][kFPart]: one record per CTA
-    int tail_here;                  // != 0: the last CTA also publishes the loss (fused backward without k_image_grad); 0: a spare CTA of
-                                    // k_image_grad does (default)
     DevScalars* sc;
     double* loss_out;
     double* zero_buf;               // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
@@ -129,8 +121,8 @@ struct StatsTail {
 // Tail of the image statistics, run by the last CTA of k_image_stats to finish: reduces the per-CTA records of every reference image
 // - one WARP per image, records in lane order, butterfly merge (commutative operations: every lane holds the same bits, the result
 // does not depend on which CTA runs it) - and publishes the per-image statistics and cotangent scales k_image_grad needs.  Nothing
-// else: the loss and the coefficients of the fused backward fill are a serial chain of float64 divisions that nothing before
-// k_theta_grad waits for (publish_loss, run by a spare CTA of k_image_grad next to the pointwise pass).
+// else: the loss is a serial chain of float64 divisions that nothing before k_theta_grad waits for (publish_loss, run by a spare CTA of
+// k_image_grad next to the pointwise pass).
 template <int NT>
 __device__ __forceinline__ void stats_tail(const double* __restrict__ part, DevScalars* sc, int R, int cpi, int HW, double alpha, double beta) {
     const int tid = linear_tid(), lane = tid & 31, wid = tid >> 5;
@@ -169,25 +161,13 @@ __device__ __forceinline__ void stats_tail(const double* __restrict__ part, DevS
     }
 }
 
-// Loss and fused-fill coefficients from the published statistics (one thread; reference src/eincm/losses.py:171-193).
+// Loss from the published statistics (one thread; reference src/eincm/losses.py:171-193).
 __device__ __forceinline__ void publish_loss(DevScalars* sc, int R, double alpha, double beta, double gamma, int use_tv, double* loss_out) {
     double s_corr = 0.0, s_con = 0.0;
     const double zc = sc->zero[0].contrast;
     for (int q = 0; q < R; ++q) {
         const Stats st = sc->ref[q];
-        const double cA = sc->coefA[q], cB = sc->coefB[q], w = sc->weights[q];
-        // coefficients of the per-cell cotangent for the fused backward fill (same terms as k_image_grad, scaled by 1 / 2 pi)
-        const double iD = 1.0 / st.D;
-        const double g_M = -st.s2 / (st.D * st.D);
-        const double g_m = -st.s1 / st.D + st.s2 / (st.D * st.D);
-        CotCoef c;
-        c.cA = cA * kInv2Pi;
-        c.a1 = cB * iD * kInv2Pi;
-        c.a2 = cB * iD * iD * kInv2Pi;
-        c.a3 = c.a2 * st.mn;
-        c.mn = st.mn; c.mx = st.mx;
-        c.tm = g_m / st.cnt_min * kInv2Pi; c.tM = g_M / st.cnt_max * kInv2Pi;
-        sc->cot[q] = c;
+        const double w = sc->weights[q];
         s_corr += (w * (-st.mse)) / ((-sc->zero[q].mse) + kEps);                         // losses.py:176
         s_con += (w * st.contrast) / (zc + kEps);                                        // losses.py:177
     }
@@ -202,7 +182,6 @@ __device__ __forceinline__ void publish_loss(DevScalars* sc, int R, double alpha
 __device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn_d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-template <bool REC>
 __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
     __shared__ StatsTail S;
     const int H = A.H, W = A.W, R = A.R;
@@ -236,8 +215,6 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
         const double* Er = A.edges + r * HW + (xin ? x : 0);
         double* Ir = A.iwe + r * HW;
         float* Ar = A.adj32 + r * HW;
-        CellRec* Rr = REC ? A.rec + r * HW : nullptr;
-        const float* E32r = A.e32 + r * HW;
         int cnt_mn = 0, cnt_mx = 0;                    // tie counts of the running min / max (integers: branch-free update)
         // three-row windows: image value and horizontal difference of input rows yi-2, yi-1 (yi: the row being consumed);
         // Scharr x differences and Scharr y of rows yc-2, yc-1 (yc = yi - 1: the row whose Scharr pair is produced)
@@ -280,7 +257,7 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
                 }
                 if (own_col && yc >= y0 && yc < y1) {                         // statistics and image value of an own pixel
                     const double I = I1;
-                    if (REC) Rr[yc * W + x].I = I; else Ir[yc * W + x] = I;
+                    Ir[yc * W + x] = I;
                     acc.sq += gx * gx + gy * gy; acc.sI += I; acc.sI2 += I * I; acc.sEI += E1 * I;
                     cnt_mn = (I < acc.mn) ? 1 : cnt_mn + (I == acc.mn ? 1 : 0);
                     cnt_mx = (I > acc.mx) ? 1 : cnt_mx + (I == acc.mx ? 1 : 0);
@@ -297,8 +274,7 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
                     const float ax = __fadd_rn(__fadd_rn(__fmul_rn(3.f, Ex2), __fmul_rn(10.f, Ex1)), __fmul_rn(3.f, Ex0));
                     const float ay = __fadd_rn(__fadd_rn(__fmul_rn(3.f, Fyl), __fmul_rn(10.f, Fy)), __fmul_rn(3.f, Fyr));
                     const float adj = __fadd_rn(ax, ay);
-                    if (REC) *reinterpret_cast<float2*>(&Rr[ya * W + x].adj) = make_float2(adj, __ldg(E32r + ya * W + x));
-                    else Ar[ya * W + x] = adj;
+                    Ar[ya * W + x] = adj;
                 }
                 // shift the windows
                 I2 = I1; I1 = I0; Dx2 = Dx1; Dx1 = Dx0; E1 = ec[u];
@@ -338,21 +314,17 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
     __threadfence();
     stats_tail<kS2NT>(A.part, A.sc, R, cpi, HW, A.alpha, A.beta);
     if (tid == 0) A.sc->counters[kStatsTicket] = 0u;
-    if (A.tail_here) {                   // no k_image_grad follows (fused backward fill): the loss is published here as well
-        __syncthreads();
-        if (tid == 0) publish_loss(A.sc, R, A.alpha, A.beta, A.gamma, A.use_tv, A.loss_out);
-    }
 }
 
 __global__ void __launch_bounds__(kS2NT, 5)
-k_image_stats(const ImageStatsArgs A) { if (A.rec != nullptr) image_stats_body<true>(A); else image_stats_body<false>(A); }
+k_image_stats(const ImageStatsArgs A) { image_stats_body(A); }
 
 // batched form: blockIdx.y = window, one argument record per window in device memory
 __global__ void __launch_bounds__(kS2NT, 5)
 k_image_stats_b(const ImageStatsArgs* __restrict__ args) {
     __shared__ ImageStatsArgs sA;
     load_args(sA, args + blockIdx.y);
-    image_stats_body<false>(sA);
+    image_stats_body(sA);
 }
 
 // ---- k_image_grad ----------------------------------------------------------------------------------------------------------
@@ -440,24 +412,15 @@ k_image_grad_b(const ImageGradArgs* __restrict__ args) {
     image_grad_body(sA);
 }
 
-// cell records -> dense float64 image + float32 adjoint (debug taps and the unfused d loss / d IWE kernel, on demand)
-__global__ void k_unpack_records(const CellRec* __restrict__ rec, int64_t n, double* __restrict__ iwe, float* __restrict__ adj32) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const CellRec c = rec[i];
-        iwe[i] = c.I; adj32[i] = c.adj;
-    }
-}
-
 // per-window: sum E_r and sum E_r^2 (deterministic single-CTA-per-reference reduction; once per window)
 __global__ void __launch_bounds__(1024)
-k_edge_sums(const double* __restrict__ edges, int64_t HW, DevScalars* sc, float* __restrict__ e32 /* float32 copy for the fused backward fill, or null */) {
+k_edge_sums(const double* __restrict__ edges, int64_t HW, DevScalars* sc) {
     __shared__ double sh[32];
     const int r = blockIdx.x;
     double s = 0.0, s2 = 0.0;
     for (int64_t p = threadIdx.x; p < HW; p += blockDim.x) {
         const double e = edges[r * HW + p];
         s += e; s2 += e * e;
-        if (e32 != nullptr) e32[r * HW + p] = (float)e;
     }
     s = block_reduce<1024>(s, OpSum(), sh);
     s2 = block_reduce<1024>(s2, OpSum(), sh);

@@ -31,7 +31,10 @@ __global__ void k_histogram(const int16_t* __restrict__ xs, const int16_t* __res
 // <= kChunkEvents events - the work items of the tile-privatised event kernels (k_events_tile.cuh).
 constexpr int kKeysPerTile = kSortTile * kSortTile;     // 256 sort keys (pixels) per tile
 constexpr unsigned int kStreamAlign = 4;
-constexpr unsigned int kChunkEvents = 1024;
+// Two CTA passes of 1024 events (4 per thread) share one window set-up, one zeroing and one flush: most tiles of a DSEC window hold
+// more than 1024 events, and the per-chunk overhead was half of the splat's instructions.  2044, not 2048: a window cell
+// is a uint32 of 2^21-scaled votes, 2044 * 2^21 < 2^32 even if every event of the chunk put a full centre tap on one cell.
+constexpr unsigned int kChunkEvents = 2044;
 
 struct Chunk { uint32_t start, count, origin, pad; };   // count: multiple of kStreamAlign, <= kChunkEvents; origin: tile corner x | y << 16
 

@@ -21,7 +21,6 @@ FLAG_NO_WRAP_NEGATIVE = 0x1
 FLAG_EVENT_SPLIT = 0x2
 FLAG_EXACT_F64 = 0x4
 FLAG_BLOCKING_SYNC = 0x8
-FLAG_FOLD_BACKWARD = 0x10
 METHOD_BILINEAR = 0
 S_HEADER = 8
 

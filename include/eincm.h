@@ -56,11 +56,6 @@ extern "C" {
                                               cudaStreamSynchronize: for hosts with fewer cores than driving threads (one thread per
                                               sequence, several sequences per GPU); costs some wake-up latency per call */
 
-#define EINCM_FLAG_FOLD_BACKWARD      0x10u /* tile flow fields: ONE backward kernel (k_backward_fold) evaluates d loss / d IWE inside its
-                                              window fill and folds the per-event sums into the <= 3 x 3 theta elements of the source tile
-                                              (no dense gradient field, three launches per evaluation).  Same results; measured no faster
-                                              than the default unfused kernels on a B200, hence opt-in */
-
 /* theta -> sensor-size resize method (reference configs/main.yaml:27 `scale_theta_to_sensor_size_method`) */
 #define EINCM_METHOD_BILINEAR 0
 

@@ -1,9 +1,7 @@
-"""The fused backward pass (k_backward_fold: d loss / d IWE evaluated in the window fill, per-event sums folded into the <= 3 x 3
-theta elements of the source tile, delivery by its last CTA) against (a) the unfused path of the same library
-(the default: k_image_grad + k_backward_tile + k_theta_grad), (b) the oracle, on the shapes where the fold applies and on the
-ones where it must fall back; plus the stream-ordering contract of set_window / window_finalize."""
-import os
-
+"""Evaluation-path contracts that are not plain parity: several pyramid-level shapes against the oracle through the host calls (with
+the handover gradient), device-resident evaluations queued back to back on one stream (programmatic dependent launches chain the five
+kernels of consecutive evaluations), flows that push patches over every border and beyond one shared-memory window, and the
+stream-ordering contract of set_window / window_finalize."""
 import numpy as np
 import pytest
 
@@ -20,43 +18,33 @@ def _rel_inf(a, b):
     return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
 
 
-def _plan(P, win, no_fold, max_refs=None):
-    """no_fold False: the fused backward (EINCM_FLAG_FOLD_BACKWARD); True: the default unfused kernels."""
-    return P.Plan(win.sensor_size, max_events=len(win.xs), max_refs=max_refs or max(3, len(win.edge_ts)),
-                  flags=0 if no_fold else P.FLAG_FOLD_BACKWARD)
-
-
 @pytest.mark.parametrize('name,shape', [('tiny', (1, 1)), ('tiny', (2, 2)), ('tiny', (3, 4)), ('mvsec_dt4', (16, 16)), ('mvsec_raw_dt4', (16, 16)),
                                         ('mvsec_dt1', (8, 8)), ('ecd', (8, 8)), ('ecd', (16, 16))])
-def test_fold_equals_unfused_path_and_oracle(name, shape):
+def test_levels_and_handover_against_oracle(name, shape):
     from eincm_b200 import plan as P
     win = S.make_workload(name, seed=3)
     hp = win.hparams
     hpc = P.make_hparams(hp['alpha'], hp['beta'], 0.0, 0.0, 1)
     pts = S.theta_test_points(win, shape)
-    pa, pb = _plan(P, win, False), _plan(P, win, True)
+    p = P.Plan(win.sensor_size, max_events=len(win.xs), max_refs=max(3, len(win.edge_ts)))
     try:
-        pa.set_window(*win.args()); pb.set_window(*win.args())
+        p.set_window(*win.args())
         for th in (pts['perturbed'], pts['zero'], pts['truth']):
-            la, ga = pa.value_and_grad_host(th, hpc)
-            lb, gb = pb.value_and_grad_host(th, hpc)
-            assert la == lb                                        # same forward pass: bit-identical objective
-            assert _rel_inf(ga, gb) <= 2e-6                        # float32 partial sums in a different order
+            la, ga = p.value_and_grad_host(th, hpc)
             l_ref, g_ref = O.value_and_grad(th, *win.args(), hp['alpha'], hp['beta'], 0.0, 0.0, 1, 5, win.sensor_size)
             assert abs(la - l_ref) <= OBJ_RTOL * abs(l_ref)
             assert _rel_inf(ga, g_ref) <= GRAD_RTOL
         # handover: d / d alpha = <grad(theta_ho), prev - theta>, delivered by the same kernel
         a0 = 0.3
-        l_ho, da = pa.handover_value_and_grad_host(a0, pts['truth'], pts['perturbed'], hpc)
-        l_hb, db = pb.handover_value_and_grad_host(a0, pts['truth'], pts['perturbed'], hpc)
-        assert l_ho == l_hb and abs(da - db) <= 1e-5 * max(abs(db), 1e-300)
-        _, da_ref = O.handover_value_and_grad(a0, pts['truth'], pts['perturbed'], *win.args(), hp['alpha'], hp['beta'], 0.0, 0.0, 1, 5, win.sensor_size)
+        l_ho, da = p.handover_value_and_grad_host(a0, pts['truth'], pts['perturbed'], hpc)
+        l_ref, da_ref = O.handover_value_and_grad(a0, pts['truth'], pts['perturbed'], *win.args(), hp['alpha'], hp['beta'], 0.0, 0.0, 1, 5, win.sensor_size)
+        assert abs(l_ho - l_ref) <= OBJ_RTOL * abs(l_ref)
         assert abs(da - da_ref) <= GRAD_RTOL * abs(da_ref)
     finally:
-        pa.close(); pb.close()
+        p.close()
 
 
-def test_fold_device_operands_and_repeated_evaluations():
+def test_device_operands_and_repeated_evaluations():
     """Device-resident form (eincm_value_and_grad): the caller's gradient buffer is the accumulator; evaluations queued back to
     back on one stream (programmatic dependent launches chain them) give the same answer as one at a time."""
     import torch
@@ -65,7 +53,7 @@ def test_fold_device_operands_and_repeated_evaluations():
     hp = win.hparams
     hpc = P.make_hparams(hp['alpha'], hp['beta'], 0.0, 0.0, 0)
     ths = [S.theta_test_points(win, (4, 4), seed=s)['perturbed'] for s in range(6)]
-    p = P.Plan(win.sensor_size, max_events=len(win.xs), max_refs=3, flags=P.FLAG_FOLD_BACKWARD)
+    p = P.Plan(win.sensor_size, max_events=len(win.xs), max_refs=3)
     try:
         p.set_window(*win.args())
         ref = [p.value_and_grad_host(th, hpc) for th in ths]
@@ -83,25 +71,23 @@ def test_fold_device_operands_and_repeated_evaluations():
         p.close()
 
 
-def test_fold_large_flow_and_border_wrap():
+def test_large_flow_and_border_wrap():
     """Flows that push patches over every border (wrap / drop index rule) and rectangles beyond one shared-memory window."""
     from eincm_b200 import plan as P
-    win = S.make_workload('ecd', seed=1, n_events=20_000)          # 176 x 240: 2 x 2 and 4 x 4 tiles fold, larger ones do not
+    win = S.make_workload('ecd', seed=1, n_events=20_000)          # 176 x 240
     hp = win.hparams
     hpc = P.make_hparams(hp['alpha'], hp['beta'], 0.0, 0.0, 2)
     th = np.full((2, 2, 2), 37.0)
     th[0, 0] = (-81.0, 95.0)
     th[1, 1] = (140.0, -20.0)
-    pa, pb = _plan(P, win, False), _plan(P, win, True)
+    p = P.Plan(win.sensor_size, max_events=len(win.xs), max_refs=max(3, len(win.edge_ts)))
     try:
-        pa.set_window(*win.args()); pb.set_window(*win.args())
-        la, ga = pa.value_and_grad_host(th, hpc)
-        lb, gb = pb.value_and_grad_host(th, hpc)
-        assert la == lb and _rel_inf(ga, gb) <= 2e-6
+        p.set_window(*win.args())
+        la, ga = p.value_and_grad_host(th, hpc)
         l_ref, g_ref = O.value_and_grad(th, *win.args(), hp['alpha'], hp['beta'], 0.0, 0.0, 2, 5, win.sensor_size)
         assert abs(la - l_ref) <= OBJ_RTOL * abs(l_ref) and _rel_inf(ga, g_ref) <= GRAD_RTOL
     finally:
-        pa.close(); pb.close()
+        p.close()
 
 
 def test_evaluation_on_another_stream_waits_for_window_finalize():
