@@ -79,12 +79,12 @@ __device__ __forceinline__ void red_G(double* __restrict__ G, int W, uint32_t xy
 
 constexpr int kSubChunk = kEvK * 256;       // events a CTA holds in registers at a time (kEvK per thread): a chunk is processed in sub-chunks
 static_assert(kChunkEvents % kEvK == 0 && kStreamAlign == kEvK, "chunks are made of groups of kEvK events");
-static_assert((unsigned long long)kChunkEvents << 21 < (1ull << 32), "a uint32 window cell holds the votes of a whole chunk (kFixShift = 21)");
+static_assert((unsigned long long)kChunkEvents << kFixShift < (1ull << 32), "a uint32 window cell holds the votes of a whole chunk");
 constexpr int kWinCap = 4096;         // window cells per reference time (16 KB of uint32 / float)
-constexpr int kFixShift = 21;
-constexpr double kFixToIwe = kInv2Pi / 2097152.0;        // fixed-point sum -> image value
+constexpr double kFixToIwe = kInv2Pi / (double)(1u << kFixShift);        // fixed-point sum -> image value
 // float -> fixed point by mantissa alignment: for 0 <= p <= 1, the float 6 + p lies in [4, 8) where one ulp is 2^-21, so
 // bits(fma(ex, ey, 6.0f)) - bits(6.0f) == round(2^21 * ex * ey) (round to nearest even), no scaling multiply
+static_assert(kFixShift == 21, "the rounding constant below is chosen for 2^-21");
 constexpr float kRoundMagic = 6.0f;
 constexpr int kRoundMagicBits = 0x40C00000;
 

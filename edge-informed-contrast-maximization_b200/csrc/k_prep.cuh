@@ -31,10 +31,12 @@ __global__ void k_histogram(const int16_t* __restrict__ xs, const int16_t* __res
 // <= kChunkEvents events - the work items of the tile-privatised event kernels (k_events_tile.cuh).
 constexpr int kKeysPerTile = kSortTile * kSortTile;     // 256 sort keys (pixels) per tile
 constexpr unsigned int kStreamAlign = 4;
-// Two CTA passes of 1024 events (4 per thread) share one window set-up, one zeroing and one flush: most tiles of a DSEC window hold
-// more than 1024 events, and the per-chunk overhead was half of the splat's instructions.  2044, not 2048: a window cell
-// is a uint32 of 2^21-scaled votes, 2044 * 2^21 < 2^32 even if every event of the chunk put a full centre tap on one cell.
-constexpr unsigned int kChunkEvents = 2044;
+// Several CTA passes of 1024 events (4 per thread) share one window set-up, one zeroing and one flush: most tiles of a DSEC window hold
+// more than 1024 events, and the per-chunk overhead was half of the splat's instructions.  A window cell is a uint32 of
+// 2^kFixShift-scaled votes: a chunk holds at most 2^(32 - kFixShift) - 4 events, so that the cell cannot overflow even if every event of
+// the chunk put a full centre tap on it.
+constexpr int kFixShift = 21;     // (20 would allow 4092-event chunks: measured 2 us of 128 per DSEC evaluation, for half the vote resolution)
+constexpr unsigned int kChunkEvents = (1u << (32 - kFixShift)) - 4u;
 
 struct Chunk { uint32_t start, count, origin, pad; };   // count: multiple of kStreamAlign, <= kChunkEvents; origin: tile corner x | y << 16
 
