@@ -190,7 +190,7 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
         if (rc) return bfail(batch, rc, "%s", plan->error.c_str());
     }
     const int max_ny = std::min(H, 2 * ((H + h - 1) / h) + 2), max_nx = std::min(W, 2 * ((W + w - 1) / w) + 2);
-    const int SX = (max_nx + kTgCols - 1) / kTgCols, SY = (max_ny + kTgRows - 1) / kTgRows;
+    const int SX = (max_nx + kTgCols - 1) / kTgCols, SY = (max_ny + kTgTrips * kTgRows - 1) / (kTgTrips * kTgRows);
     const int n_items = h * w * SY * SX;
     // ---- argument records (uploaded only when an operand changed since the last call) ---------------------------------------------
     std::vector<uintptr_t> key;

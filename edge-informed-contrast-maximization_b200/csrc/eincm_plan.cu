@@ -506,7 +506,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         // support of one theta element: <= 2 cells of the resize (+ rounding) per axis
         const int max_ny = std::min(H, 2 * ((H + h - 1) / h) + 2), max_nx = std::min(W, 2 * ((W + w - 1) / w) + 2);
         const int SX = (max_nx + kTgCols - 1) / kTgCols;
-        const int SY = (max_ny + kTgRows - 1) / kTgRows;
+        const int SY = (max_ny + kTgTrips * kTgRows - 1) / (kTgTrips * kTgRows);
         const int n_items = n_el * SY * SX;
         const int gridG = (n_items + kTgWarps - 1) / kTgWarps;
         if (Gtv != nullptr)

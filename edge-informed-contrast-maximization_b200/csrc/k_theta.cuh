@@ -69,6 +69,11 @@ __global__ void k_upsample_theta(const ThetaSrc T, int H, int W, double2* __rest
 // gradient, so the whole theta backward is one launch.
 constexpr int kGatherMaxTiles = 4096;
 constexpr int kTgWarps = 4;              // warps (work items) per CTA
+#ifndef EINCM_TG_TRIPS
+#define EINCM_TG_TRIPS 2
+#endif
+constexpr int kTgTrips = EINCM_TG_TRIPS;   // row groups a work item walks through, one after the other (16x16 theta on 640x480: 1 -> 14.9 us in two
+                                           // waves of CTAs, 2 -> 12.8 us in one, 4 -> 14.6 us)
 constexpr int kTgRows = 4, kTgCols = 96;  // rows x columns per work item: 12 independent 16-byte loads in flight per lane
 
 __device__ __forceinline__ double axis_weight(const AxisTaps& t, int o, int i) {
