@@ -948,7 +948,7 @@ def main():
     ap.add_argument('--solve-seqs', type=int, default=3, help='sequences solved concurrently per GPU for the windows/s figure (3: the spinning driver threads of 8 ranks fit a 32-core box)')
     ap.add_argument('--solve-wait', default='spin', choices=['block', 'spin'], help='how the host entry points wait for an evaluation')
     ap.add_argument('--solve-compare', action='store_true', help='also measure the other wait mode and the scipy-driven solve (N = 1)')
-    ap.add_argument('--solve-windows', type=int, default=3, help='complete multi-level solves per GPU for the windows/s figure (0: skip)')
+    ap.add_argument('--solve-windows', type=int, default=6, help='chained windows per sequence for the windows/s figure (0: skip); the evaluations per window vary (430 - 560), and the figure is the slowest rank\'s: more windows per sequence average that out')
     ap.add_argument('--event-split', action='store_true', help='ONE window split over the GPUs (configs[4]) instead of windows sharded')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
