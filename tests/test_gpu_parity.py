@@ -365,6 +365,44 @@ def test_hot_pixel_and_ragged_tiles(L):
     assert _rel_inf(grad, g_ref) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize('n_tile', [1, 3, 4, 1023, 1024, 1025, 1028, 2043, 2044, 2045, 2048, 4088, 4089, 6133])
+def test_chunk_and_sub_chunk_boundaries(L, n_tile):
+    """All events of one 16x16 source tile, at counts around the sub-chunk (1024) and chunk (2044) capacities: a chunk is voted in
+    register-resident sub-chunks into one window; sentinels pad the last group; the IWE of every reference time must equal the
+    oracle's and the objective must be bit-identical however the events are cut (integer votes)."""
+    from eincm_b200 import plan as P
+    rng = np.random.default_rng(n_tile)
+    H, W = 64, 96
+    base = S.make_window(H, W, 64, seed=2)                               # edges + a few events elsewhere (other tiles: 1 chunk each)
+    xs = np.concatenate([base.xs, rng.integers(32, 48, n_tile).astype(np.int16)])
+    ys = np.concatenate([base.ys, rng.integers(16, 32, n_tile).astype(np.int16)])
+    ts = np.concatenate([base.ts, rng.uniform(0, 1, n_tile)])
+    order = np.argsort(ts, kind='stable')
+    xs, ys, ts = np.ascontiguousarray(xs[order]), np.ascontiguousarray(ys[order]), np.ascontiguousarray(ts[order])
+    kw = dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, cur_pyr_lvl=1, n_pyr_lvls=5, sensor_size=(H, W),
+              scale_to_sensor_size_method='bilinear')
+    th = rng.normal(0.0, 5.0, size=(2, 3, 2))
+    loss, grad = L.value_and_grad(L.loss_func)(th, xs, ys, ts, base.edges, base.edge_ts, **kw)
+    l_ref, g_ref, inter = O.value_and_grad(th, xs, ys, ts, base.edges, base.edge_ts, **kw, return_intermediates=True)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= GRAD_RTOL
+    # the same events in another order of arrival (ties in the per-pixel time order aside, another cut into groups): same bits
+    perm = rng.permutation(len(xs))
+    p = P.Plan((H, W), max_events=len(xs), max_refs=3)
+    try:
+        hp = P.make_hparams(20.0, 35.0, 0.0, 0.0, 1)
+        p.set_window(xs, ys, ts, base.edges, base.edge_ts)
+        la, _ = p.value_and_grad_host(th, hp)
+        iwe_a = p.iwe().cpu().numpy().copy()
+        np.testing.assert_allclose(iwe_a, inter['iwes'], rtol=2e-5, atol=1e-7)          # votes quantised to 2^-21 of the centre tap
+        p.set_window(np.ascontiguousarray(xs[perm]), np.ascontiguousarray(ys[perm]), np.ascontiguousarray(ts[perm]), base.edges, base.edge_ts)
+        lb, _ = p.value_and_grad_host(th, hp)
+        assert la == lb == loss
+        np.testing.assert_array_equal(iwe_a, p.iwe().cpu().numpy())
+    finally:
+        p.close()
+
+
 def test_batched_host_call_matches_single_calls(tiny):
     """eincm_value_and_grad_host_batch: independent windows evaluated concurrently, each on its own stream, give the results
     of one-at-a-time calls (objective bit-identical: it does not depend on scheduling)."""
