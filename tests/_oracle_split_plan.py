@@ -6,10 +6,18 @@ import torch
 from oracle import eincm_oracle as O
 
 
+FIX_SCALE = float(2 ** 21) * 2.0 * np.pi          # the library's fixed-point images: 2^21 * 2 pi * value (include/eincm.h)
+
+
 class OracleSplitPlan:
     def __init__(self, sensor_size):
         self.sensor_size = tuple(sensor_size)
         self.rank, self.world = 0, 1
+        self.fixed = False
+
+    def set_split_fixed_point(self, on=True):
+        """The collective then runs on int64 images (iwe_fix); backward() takes the complete image from there."""
+        self.fixed = bool(on)
 
     def set_event_split(self, rank, world):
         self.rank, self.world = rank, world
@@ -34,12 +42,20 @@ class OracleSplitPlan:
         assert self.final
         self.theta = theta.numpy()
         self._iwe = torch.from_numpy(O.partial_images(self.theta, self.xs, self.ys, self.ts, self.edge_ts, self.sensor_size))
+        if self.fixed:            # quantised like the library's votes (here per cell, not per vote: a stand-in for the SEQUENCE, not the kernels)
+            self._fix = torch.from_numpy(np.rint(self._iwe.numpy() * FIX_SCALE).astype(np.int64))
 
     def iwe(self):
+        assert not self.fixed, 'fixed-point split: the caller must all-reduce iwe_fix(), not iwe()'
         return self._iwe
 
+    def iwe_fix(self):
+        assert self.fixed
+        return self._fix
+
     def backward(self, hp, loss_out, grad_out):
-        loss, grad = O.split_value_and_grad(self.theta, self._iwe.numpy(), self._zero.numpy(), self._mask.numpy().astype(bool),
+        iwe = self._fix.numpy().astype(np.float64) / FIX_SCALE if self.fixed else self._iwe.numpy()
+        loss, grad = O.split_value_and_grad(self.theta, iwe, self._zero.numpy(), self._mask.numpy().astype(bool),
                                             self.xs, self.ys, self.ts, self.edges, self.edge_ts, hp['alpha'], hp['beta'], hp['gamma'],
                                             hp['delta'], hp['cur_pyr_lvl'], 5, self.sensor_size,
                                             include_replicated_grad=(self.rank == 0))
