@@ -16,6 +16,8 @@
 #include <limits>
 #include <vector>
 
+#include "eincm_linesearch.h"
+
 namespace eincm_opt {
 
 struct Result {
@@ -25,119 +27,6 @@ struct Result {
 
 // value and gradient of the objective at x (n doubles); returns non-zero on a hard error (propagated)
 using Objective = std::function<int(const double* x, double* f, double* g)>;
-
-// ---- More-Thuente line search (after MINPACK-2 dcsrch / dcstep) ------------------------------------------------------------
-struct LineSearch {
-    double ftol, gtol, xtol, stpmin, stpmax;
-    // state
-    bool brackt = false;
-    int stage = 1;
-    double ginit = 0, gtest = 0, gx = 0, gy = 0, finit = 0, fx = 0, fy = 0, stx = 0, sty = 0, stmin = 0, stmax = 0, width = 0, width1 = 0;
-    enum Task { FG, CONVERGED, WARNING, ERROR };
-
-    Task start(double stp, double f, double g) {
-        if (stp < stpmin || stp > stpmax || g >= 0.0) return ERROR;
-        brackt = false; stage = 1; finit = f; ginit = g; gtest = ftol * ginit;
-        width = stpmax - stpmin; width1 = 2.0 * width;
-        stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
-        stmin = 0.0; stmax = stp + 4.0 * stp;
-        return FG;
-    }
-
-    static void step(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp, double fp, double dp,
-                     bool& brackt, double stpmin, double stpmax) {
-        const double sgnd = dp * (dx / std::fabs(dx));
-        double stpf;
-        if (fp > fx) {                                            // case 1: higher function value: the minimum is bracketed
-            const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-            const double s = std::max({std::fabs(theta), std::fabs(dx), std::fabs(dp)});
-            double gamma = s * std::sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-            if (stp < stx) gamma = -gamma;
-            const double p = (gamma - dx) + theta, q = ((gamma - dx) + gamma) + dp, r = p / q;
-            const double stpc = stx + r * (stp - stx);
-            const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
-            stpf = (std::fabs(stpc - stx) < std::fabs(stpq - stx)) ? stpc : stpc + (stpq - stpc) / 2.0;
-            brackt = true;
-        } else if (sgnd < 0.0) {                                  // case 2: derivatives of opposite sign: bracketed
-            const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-            const double s = std::max({std::fabs(theta), std::fabs(dx), std::fabs(dp)});
-            double gamma = s * std::sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-            if (stp > stx) gamma = -gamma;
-            const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dx, r = p / q;
-            const double stpc = stp + r * (stx - stp);
-            const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
-            stpf = (std::fabs(stpc - stp) > std::fabs(stpq - stp)) ? stpc : stpq;
-            brackt = true;
-        } else if (std::fabs(dp) < std::fabs(dx)) {               // case 3: same sign, derivative decreases in magnitude
-            const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-            const double s = std::max({std::fabs(theta), std::fabs(dx), std::fabs(dp)});
-            double gamma = s * std::sqrt(std::max(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
-            if (stp > stx) gamma = -gamma;
-            const double p = (gamma - dp) + theta, q = (gamma + (dx - dp)) + gamma, r = p / q;
-            double stpc;
-            if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
-            else stpc = (stp > stx) ? stpmax : stpmin;
-            const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
-            if (brackt) {
-                stpf = (std::fabs(stpc - stp) < std::fabs(stpq - stp)) ? stpc : stpq;
-                if (stp > stx) stpf = std::min(stp + 0.66 * (sty - stp), stpf);
-                else stpf = std::max(stp + 0.66 * (sty - stp), stpf);
-            } else {
-                stpf = (std::fabs(stpc - stp) > std::fabs(stpq - stp)) ? stpc : stpq;
-                stpf = std::min(stpmax, stpf);
-                stpf = std::max(stpmin, stpf);
-            }
-        } else {                                                  // case 4: same sign, derivative does not decrease
-            if (brackt) {
-                const double theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-                const double s = std::max({std::fabs(theta), std::fabs(dy), std::fabs(dp)});
-                double gamma = s * std::sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
-                if (stp > sty) gamma = -gamma;
-                const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dy, r = p / q;
-                stpf = stp + r * (sty - stp);
-            } else {
-                stpf = (stp > stx) ? stpmax : stpmin;
-            }
-        }
-        if (fp > fx) { sty = stp; fy = fp; dy = dp; }
-        else {
-            if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
-            stx = stp; fx = fp; dx = dp;
-        }
-        stp = stpf;
-    }
-
-    // feeds phi(stp) = f, phi'(stp) = g; returns the task and, for FG, the next trial step in `stp`
-    Task update(double& stp, double f, double g) {
-        const double ftest = finit + stp * gtest;
-        if (stage == 1 && f <= ftest && g >= 0.0) stage = 2;
-        Task task = FG;
-        if (brackt && (stp <= stmin || stp >= stmax)) task = WARNING;              // rounding errors prevent progress
-        if (brackt && stmax - stmin <= xtol * stmax) task = WARNING;               // xtol test satisfied
-        if (stp == stpmax && f <= ftest && g <= gtest) task = WARNING;             // stp = stpmax
-        if (stp == stpmin && (f > ftest || g >= gtest)) task = WARNING;            // stp = stpmin
-        if (f <= ftest && std::fabs(g) <= gtol * (-ginit)) task = CONVERGED;
-        if (task != FG) return task;
-        if (stage == 1 && f <= fx && f > ftest) {                                   // modified function in stage 1
-            double fm = f - stp * gtest, fxm = fx - stx * gtest, fym = fy - sty * gtest;
-            double gm = g - gtest, gxm = gx - gtest, gym = gy - gtest;
-            step(stx, fxm, gxm, sty, fym, gym, stp, fm, gm, brackt, stmin, stmax);
-            fx = fxm + stx * gtest; fy = fym + sty * gtest; gx = gxm + gtest; gy = gym + gtest;
-        } else {
-            step(stx, fx, gx, sty, fy, gy, stp, f, g, brackt, stmin, stmax);
-        }
-        if (brackt) {
-            if (std::fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
-            width1 = width; width = std::fabs(sty - stx);
-            stmin = std::min(stx, sty); stmax = std::max(stx, sty);
-        } else {
-            stmin = stp + 1.1 * (stp - stx); stmax = stp + 4.0 * (stp - stx);
-        }
-        stp = std::max(stp, stpmin); stp = std::min(stp, stpmax);
-        if ((brackt && (stp <= stmin || stp >= stmax)) || (brackt && stmax - stmin <= xtol * stmax)) stp = stx;
-        return FG;
-    }
-};
 
 inline double dot(const double* a, const double* b, int n) { double s = 0.0; for (int i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
 // Row of a dense matrix-vector product with eight independent partial sums in a fixed order: the plain loop above is one serial
@@ -173,16 +62,6 @@ struct Phi {
     }
 };
 
-// first trial step of scipy's scalar_search_wolfe1 / wolfe2: min(1, 1.01 * 2 (phi0 - old_phi0) / derphi0), 1 when that is negative
-inline double first_trial_step(double f0, double old_f, double derphi0) {
-    double stp = 1.0;
-    if (std::isfinite(old_f) && derphi0 != 0.0) {
-        stp = std::min(1.0, 1.01 * 2.0 * (f0 - old_f) / derphi0);
-        if (stp < 0.0) stp = 1.0;
-    }
-    return stp;
-}
-
 // scipy.optimize._linesearch.scalar_search_wolfe1 (MINPACK-2 dcsrch, xtol as given, at most 100 trials).  On success x_new, f_new,
 // g_new hold the accepted point.  `first_step` > 0 overrides the first trial step (L-BFGS-B).  A non-finite trial step or a
 // WARNING / ERROR task of dcsrch is a failure, as in DCSRCH.__call__ (`accept_warning`: L-BFGS-B's lnsrlb takes the step on a WARNING).
@@ -193,7 +72,8 @@ inline bool wolfe_search(const Objective& fun, int n, const double* x, const dou
     if (!(derphi0 < 0.0)) return false;
     double stp = first_step > 0.0 ? first_step : first_trial_step(f0, old_f, derphi0);
     stp = std::min(stp, stpmax);
-    LineSearch ls{c1, c2, xtol, stpmin, stpmax};
+    LineSearch ls;
+    ls.configure(c1, c2, xtol, stpmin, stpmax);
     if (ls.start(stp, f0, derphi0) != LineSearch::FG) return false;
     Phi phi{fun, n, x, p, x_new, f_new, g_new, nfev, err};
     for (int trial = 0; trial < max_trials; ++trial) {
@@ -206,87 +86,6 @@ inline bool wolfe_search(const Objective& fun, int n, const double* x, const dou
         if (!std::isfinite(stp)) return false;           // DCSRCH.__call__: a non-finite step ends the search with a warning
     }
     return false;
-}
-
-// ---- scipy.optimize._linesearch.scalar_search_wolfe2 (+ _zoom, _cubicmin, _quadmin): the fallback of _line_search_wolfe12 ------------
-inline bool cubicmin(double a, double fa, double fpa, double b, double fb, double c, double fc, double* xmin) {
-    const double C = fpa, db = b - a, dc = c - a;
-    const double denom = (db * dc) * (db * dc) * (db - dc);
-    if (denom == 0.0 || !std::isfinite(denom)) return false;
-    const double r0 = fb - fa - C * db, r1 = fc - fa - C * dc;
-    const double A = (dc * dc * r0 - db * db * r1) / denom;
-    const double B = (-dc * dc * dc * r0 + db * db * db * r1) / denom;
-    const double radical = B * B - 3.0 * A * C;
-    if (!(radical >= 0.0) || A == 0.0) return false;
-    *xmin = a + (-B + std::sqrt(radical)) / (3.0 * A);
-    return std::isfinite(*xmin);
-}
-
-inline bool quadmin(double a, double fa, double fpa, double b, double fb, double* xmin) {
-    const double db = b - a;
-    if (db == 0.0) return false;
-    const double B = (fb - fa - fpa * db) / (db * db);
-    if (B == 0.0 || !std::isfinite(B)) return false;
-    *xmin = a - fpa / (2.0 * B);
-    return std::isfinite(*xmin);
-}
-
-// returns true with *a_star when a point satisfying the strong Wolfe conditions was found inside the bracket (<= 10 + 1 trials)
-inline bool zoom(Phi& phi, double a_lo, double a_hi, double phi_lo, double phi_hi, double derphi_lo, double phi0, double derphi0,
-                 double c1, double c2, double* a_star) {
-    const double delta1 = 0.2, delta2 = 0.1;
-    double phi_rec = phi0, a_rec = 0.0;
-    for (int i = 0;; ++i) {
-        const double dalpha = a_hi - a_lo;
-        const double a = dalpha < 0.0 ? a_hi : a_lo, b = dalpha < 0.0 ? a_lo : a_hi;
-        double a_j = 0.0;
-        bool have = false;
-        if (i > 0) {
-            const double cchk = delta1 * dalpha;
-            have = cubicmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi, a_rec, phi_rec, &a_j) && !(a_j > b - cchk) && !(a_j < a + cchk);
-        }
-        if (!have) {
-            const double qchk = delta2 * dalpha;
-            have = quadmin(a_lo, phi_lo, derphi_lo, a_hi, phi_hi, &a_j) && !(a_j > b - qchk) && !(a_j < a + qchk);
-            if (!have) a_j = a_lo + 0.5 * dalpha;
-        }
-        double phi_aj, derphi_aj;
-        if (!phi.eval(a_j, &phi_aj, &derphi_aj)) return false;
-        if (phi_aj > phi0 + c1 * a_j * derphi0 || phi_aj >= phi_lo) {
-            phi_rec = phi_hi; a_rec = a_hi; a_hi = a_j; phi_hi = phi_aj;
-        } else {
-            if (std::fabs(derphi_aj) <= -c2 * derphi0) { *a_star = a_j; return true; }
-            if (derphi_aj * (a_hi - a_lo) >= 0.0) { phi_rec = phi_hi; a_rec = a_hi; a_hi = a_lo; phi_hi = phi_lo; }
-            else { phi_rec = phi_lo; a_rec = a_lo; }
-            a_lo = a_j; phi_lo = phi_aj; derphi_lo = derphi_aj;
-        }
-        if (i + 1 > 10) return false;
-    }
-}
-
-// On success x_new, f_new, g_new hold the accepted point (always the last one evaluated).  Like scipy, a search that exhausts its ten
-// bracketing steps still returns the last trial step (with a warning there; BFGS takes the step).
-inline bool wolfe2_search(const Objective& fun, int n, const double* x, const double* p, double f0, const double* g0, double old_f,
-                          double c1, double c2, double amax, double* x_new, double* f_new, double* g_new, int& nfev, int& err) {
-    const double derphi0 = dot(g0, p, n);
-    Phi phi{fun, n, x, p, x_new, f_new, g_new, nfev, err};
-    double alpha0 = 0.0, alpha1 = std::min(first_trial_step(f0, old_f, derphi0), amax);
-    double phi_a0 = f0, derphi_a0 = derphi0, phi_a1, derphi_a1;
-    if (!phi.eval(alpha1, &phi_a1, &derphi_a1)) return false;
-    for (int i = 0; i < 10; ++i) {
-        if (alpha1 == 0.0 || alpha0 > amax) return false;
-        double a_star;
-        if (phi_a1 > f0 + c1 * alpha1 * derphi0 || (phi_a1 >= phi_a0 && i > 0))
-            return zoom(phi, alpha0, alpha1, phi_a0, phi_a1, derphi_a0, f0, derphi0, c1, c2, &a_star);
-        if (std::fabs(derphi_a1) <= -c2 * derphi0) return true;
-        if (derphi_a1 >= 0.0)
-            return zoom(phi, alpha1, alpha0, phi_a1, phi_a0, derphi_a1, f0, derphi0, c1, c2, &a_star);
-        const double alpha2 = std::min(2.0 * alpha1, amax);
-        alpha0 = alpha1; alpha1 = alpha2;
-        phi_a0 = phi_a1; derphi_a0 = derphi_a1;
-        if (!phi.eval(alpha1, &phi_a1, &derphi_a1)) return false;
-    }
-    return true;
 }
 
 // scipy.optimize._optimize._minimize_bfgs (H0 = I, c1 = 1e-4, c2 = 0.9, gradient norm = inf-norm, xrtol = 0), including its line
@@ -306,12 +105,18 @@ inline Result bfgs(const Objective& fun, int n, double* x, int maxiter, double g
     r.status = 0;
     for (int i = 0; i < n; ++i) p[i] = -g[i];                        // H0 = I
     while (gnorm > gtol && r.nit < maxiter) {
-        bool ok = wolfe_search(fun, n, x, p.data(), f, g.data(), old_f, 1e-4, 0.9, 1e100, 0.0, xn.data(), &fn, gn.data(), r.nfev, err);
-        if (err) { *err_out = err; break; }
-        if (!ok) {
-            ok = wolfe2_search(fun, n, x, p.data(), f, g.data(), old_f, 1e-4, 0.9, 1e100, xn.data(), &fn, gn.data(), r.nfev, err);
-            if (err) { *err_out = err; break; }
+        // _line_search_wolfe12 as a resumable machine (eincm_linesearch.h): the same code drives the device-side loop
+        Wolfe12 w;
+        Phi phi{fun, n, x, p.data(), xn.data(), &fn, gn.data(), r.nfev, err};
+        double alpha = 0.0;
+        Wolfe12::Status st = w.begin(f, dot(g.data(), p.data(), n), old_f, 1e-4, 0.9, 1e100, &alpha);
+        while (st == Wolfe12::NEED_EVAL) {
+            double ph, dph;
+            if (!phi.eval(alpha, &ph, &dph)) break;
+            st = w.feed(ph, dph, &alpha);
         }
+        if (err) { *err_out = err; break; }
+        const bool ok = st == Wolfe12::OK;
         if (!ok) { r.status = 2; break; }
         for (int i = 0; i < n; ++i) { s[i] = xn[i] - x[i]; y[i] = gn[i] - g[i]; x[i] = xn[i]; g[i] = gn[i]; }
         old_f = f; f = fn;
