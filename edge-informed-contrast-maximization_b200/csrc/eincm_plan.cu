@@ -30,6 +30,7 @@
 #include "k_ingest.cuh"
 #include "k_prep.cuh"
 #include "k_theta.cuh"
+#include "k_opt.cuh"
 #include "k_events.cuh"
 #include "k_events_tile.cuh"
 #include "k_image.cuh"
@@ -123,6 +124,15 @@ struct eincm_plan {
     double* h_pinned = nullptr;     // [2*H*W + 1024]
     int* h_flag = nullptr;
     std::map<std::pair<int, int>, AxisTapsOwner> taps_cache;
+    // device-side solve loop (eincm_minimize_bfgs_graph_host, k_opt.cuh): state, vectors, dense inverse Hessian, one graph per level key
+    BfgsDev* bfgs_state = nullptr;
+    double* bfgs_vec = nullptr;          // x, g, p, s, y, Hy, x_trial, g_trial [n each], f_trial, result [4 + n]
+    double* bfgs_H = nullptr;
+    int bfgs_cap_n = 0;
+    uint64_t window_gen = 0;             // staged windows so far: graphs bake per-window kernel parameters (reference times, chunk count)
+    struct LevelGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; uint64_t gen = 0; };
+    std::map<std::vector<double>, LevelGraph> bfgs_graphs;
+    bool graph_no_pdl = false;           // programmatic dependent launches could not be captured into the loop body: plain launches there
     std::string error;
     // launch accounting / optional per-kernel timing
     int64_t launch_count = 0;
@@ -165,6 +175,8 @@ int fail(eincm_plan* p, int code, const char* fmt, ...) {
 
 // Launch with programmatic stream serialization (PDL): the kernel may be scheduled while the previous kernel of the stream drains;
 // it calls griddepcontrol.wait before it touches anything the previous kernel produces.
+thread_local bool t_plain_launches = false;      // set while a loop body is captured without programmatic edges
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
@@ -172,7 +184,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = t_plain_launches ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -657,6 +669,13 @@ void eincm_plan_destroy(eincm_plan* plan) {
     for (auto& sp : plan->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& e : plan->event_pool) cudaEventDestroy(e);
     for (void* q : plan->peer_opened) if (q) cudaIpcCloseMemHandle(q);
+    for (auto& kv : plan->bfgs_graphs) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    if (plan->bfgs_state) cudaFree(plan->bfgs_state);
+    if (plan->bfgs_vec) cudaFree(plan->bfgs_vec);
+    if (plan->bfgs_H) cudaFree(plan->bfgs_H);
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     if (plan->h_pinned) cudaFreeHost(plan->h_pinned);
     if (plan->h_flag) cudaFreeHost(plan->h_flag);
@@ -771,6 +790,7 @@ int eincm_plan_set_window(eincm_plan* plan, const int16_t* xs, const int16_t* ys
     plan->n_stream = (int64_t)(unsigned int)plan->h_flag[1];
     plan->n_chunks = (int)(unsigned int)plan->h_flag[2];
     plan->window_set = true;
+    ++plan->window_gen;
     plan->window_ev_valid = false;           // everything is complete (synchronised above): nothing to wait for
     plan->window_waited_valid = false;
     return EINCM_OK;
@@ -1081,6 +1101,141 @@ int eincm_minimize_handover_host(eincm_plan* plan, double* alpha_inout_host, dou
     }
     if (err) return err;
     result_out->fun = r.fun; result_out->nit = r.nit; result_out->nfev = r.nfev; result_out->status = r.status; result_out->reserved = 0;
+    return EINCM_OK;
+}
+
+namespace {
+
+// Builds the graph of one level solve: k_bfgs_init -> WHILE { evaluation at x_trial ; k_bfgs_step } -> result to pinned host memory.
+int build_level_graph(eincm_plan* plan, eincm_plan::LevelGraph& lg, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
+                      cudaStream_t st, bool plain_launches) {
+    const int n = h * w * 2;
+    double* v = plan->bfgs_vec;
+    BfgsBufs B{};
+    B.x = v; B.g = v + n; B.p = v + 2 * n; B.s = v + 3 * n; B.y = v + 4 * n; B.Hy = v + 5 * n; B.x_trial = v + 6 * n;
+    double* g_trial = v + 7 * n;
+    double* f_trial = v + 8 * n;
+    B.g_trial = g_trial; B.f_trial = f_trial; B.result = v + 8 * n + 8; B.H = plan->bfgs_H;
+    cudaGraph_t graph = nullptr;
+    CU(cudaGraphCreate(&graph, 0));
+    auto bail = [&](int rc) { cudaGraphDestroy(graph); return rc; };
+    // node 1: state
+    cudaGraphNode_t n_init = nullptr;
+    {
+        BfgsDev* S = plan->bfgs_state;
+        int nn = n, mi = maxiter;
+        double gt = gtol;
+        void* args[] = {&S, &nn, &mi, &gt};
+        cudaKernelNodeParams kp{};
+        kp.func = (void*)k_bfgs_init; kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+        if (cudaGraphAddKernelNode(&n_init, graph, nullptr, 0, &kp) != cudaSuccess) return bail(fail(plan, EINCM_ECUDA, "cudaGraphAddKernelNode: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    // node 2: the loop
+    cudaGraphConditionalHandle handle;
+    if (cudaGraphConditionalHandleCreate(&handle, graph, 1u, cudaGraphCondAssignDefault) != cudaSuccess)
+        return bail(fail(plan, EINCM_ECUDA, "cudaGraphConditionalHandleCreate: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaGraphNodeParams cp{};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+    cudaGraphNode_t n_loop = nullptr;
+    if (cudaGraphAddNode(&n_loop, graph, &n_init, 1, &cp) != cudaSuccess)
+        return bail(fail(plan, EINCM_ECUDA, "conditional graph node: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    // body: the evaluation exactly as eincm_value_and_grad enqueues it (device operands), then the optimizer step
+    if (cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        return bail(fail(plan, EINCM_ECUDA, "cudaStreamBeginCaptureToGraph: %s", cudaGetErrorString(cudaGetLastError())));
+    t_plain_launches = plain_launches;
+    int rc = forward_events_impl(plan, B.x_trial, nullptr, 0.0, h, w, hp, st);
+    if (rc == EINCM_OK) rc = backward_impl(plan, hp, f_trial, g_trial, nullptr, st);
+    t_plain_launches = false;
+    if (rc == EINCM_OK) {
+        k_bfgs_step<<<1, kOptNT, 0, st>>>(plan->bfgs_state, B, handle);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(plan, EINCM_ECUDA, "launch k_bfgs_step");
+    }
+    cudaGraph_t captured = nullptr;
+    const cudaError_t ec = cudaStreamEndCapture(st, &captured);
+    if (rc != EINCM_OK) return bail(rc);
+    if (ec != cudaSuccess) { cudaGetLastError(); return bail(fail(plan, EINCM_ECUDA, "capture of the loop body: %s", cudaGetErrorString(ec))); }
+    // node 3: result record [fun, nit, nfev, status, x] -> pinned host memory
+    cudaGraphNode_t n_out = nullptr;
+    if (cudaGraphAddMemcpyNode1D(&n_out, graph, &n_loop, 1, plan->h_pinned, B.result, (size_t)(4 + n) * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return bail(fail(plan, EINCM_ECUDA, "cudaGraphAddMemcpyNode1D: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    if (ei != cudaSuccess) { cudaGetLastError(); return bail(fail(plan, EINCM_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei))); }
+    if (lg.exec) cudaGraphExecDestroy(lg.exec);
+    if (lg.graph) cudaGraphDestroy(lg.graph);
+    lg.graph = graph; lg.exec = exec; lg.gen = plan->window_gen;
+    return EINCM_OK;
+}
+
+}  // namespace
+
+int eincm_minimize_bfgs_graph_host(eincm_plan* plan, double* theta_inout_host, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
+                                   eincm_opt_result* result_out, void* cuda_stream) {
+    if (!plan) return EINCM_EINVAL;
+    if (!theta_inout_host || !result_out || !hp) return fail(plan, EINCM_EINVAL, "NULL operand");
+    if (maxiter < 0) return fail(plan, EINCM_EINVAL, "maxiter must be >= 0");
+    if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
+    const int n = h * w * 2;
+    if (n > kOptMaxN) return fail(plan, EINCM_EINVAL, "the device-side loop holds up to %d flow parameters (theta %dx%d has %d): use eincm_minimize_bfgs_host", kOptMaxN, h, w, n);
+    if (plan->flags & EINCM_FLAG_EVENT_SPLIT) return fail(plan, EINCM_ESTATE, "event-split plans use the split-phase calls");
+    if (plan->exact || !plan->coop_ok || hp->delta != 0.0) return fail(plan, EINCM_ESTATE, "the device-side loop runs the default (fused) evaluation path only");
+    if (!plan->window_set) return fail(plan, EINCM_ESTATE, "minimize before set_window");
+    int rc = check_hp(plan, hp);
+    if (rc) return rc;
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = (cuda_stream == (void*)(intptr_t)-1 || cuda_stream == nullptr) ? plan->own_stream : (cudaStream_t)cuda_stream;   // never the legacy stream: it cannot be captured
+    if (plan->bfgs_cap_n < n) {
+        if (plan->bfgs_vec) { CU(cudaStreamSynchronize(st)); cudaFree(plan->bfgs_vec); cudaFree(plan->bfgs_H); plan->bfgs_vec = nullptr; plan->bfgs_H = nullptr; }
+        for (auto& kv : plan->bfgs_graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); if (kv.second.graph) cudaGraphDestroy(kv.second.graph); }
+        plan->bfgs_graphs.clear();
+        const int cap = std::max(n, 512);
+        CU(dmalloc(&plan->bfgs_vec, (size_t)9 * cap + 16 + 4 + cap));
+        CU(dmalloc(&plan->bfgs_H, (size_t)cap * cap));
+        if (!plan->bfgs_state) CU(dmalloc(&plan->bfgs_state, 1));
+        plan->bfgs_cap_n = cap;
+    }
+    const std::vector<double> key = {(double)h, (double)w, (double)maxiter, gtol, hp->alpha, hp->beta, hp->gamma, hp->delta, (double)hp->cur_pyr_lvl,
+                                     (double)hp->n_pyr_lvls, (double)hp->method};
+    eincm_plan::LevelGraph& lg = plan->bfgs_graphs[key];
+    if (lg.exec == nullptr || lg.gen != plan->window_gen) {
+        // everything the captured calls would do synchronously or across streams happens here, outside the capture
+        AxisTaps ty, tx;
+        if ((rc = build_axis_taps(plan, h, plan->H, &ty))) return rc;
+        if ((rc = build_axis_taps(plan, w, plan->W, &tx))) return rc;
+        if (plan->window_ev_valid && st != plan->window_stream && !(plan->window_waited_valid && plan->window_waited == st)) {
+            CU(cudaStreamWaitEvent(st, plan->window_ev, 0));
+            plan->window_waited = st; plan->window_waited_valid = true;
+        }
+        if (!plan->fix_clean) {
+            CU(cudaMemsetAsync(plan->iwe_fix, 0, (size_t)plan->max_refs * plan->HW * sizeof(unsigned long long), st));
+            plan->fix_clean = true;
+        }
+        const bool was_timing = plan->timing;
+        plan->timing = false;                        // event records are not part of a loop body
+        rc = build_level_graph(plan, lg, h, w, hp, maxiter, gtol, st, plan->graph_no_pdl);
+        if (rc != EINCM_OK && !plan->graph_no_pdl) {                     // once more without programmatic edges in the body
+            plan->graph_no_pdl = true;
+            plan->fix_clean = true;
+            rc = build_level_graph(plan, lg, h, w, hp, maxiter, gtol, st, true);
+        }
+        plan->timing = was_timing;
+        if (rc != EINCM_OK) return rc;
+    }
+    // run: theta in through the pinned staging area, the whole level on the device, one synchronisation
+    const size_t nb = (size_t)n * sizeof(double);
+    std::memcpy(plan->h_pinned + 4 + n, theta_inout_host, nb);
+    CU(cudaMemcpyAsync(plan->bfgs_vec + 6 * (size_t)n, plan->h_pinned + 4 + n, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaGraphLaunch(lg.exec, st));
+    rc = host_wait(plan, st);
+    if (rc) return rc;
+    // the graph ran the evaluation at least once: the plan's bookkeeping is the one the captured calls left behind
+    plan->fix_clean = true; plan->forward_done = true; plan->host_delivered = false;
+    const double* r = plan->h_pinned;
+    result_out->fun = r[0]; result_out->nit = (int32_t)r[1]; result_out->nfev = (int32_t)r[2]; result_out->status = (int32_t)r[3]; result_out->reserved = 0;
+    std::memcpy(theta_inout_host, r + 4, nb);
+    plan->host_evals += result_out->nfev;
     return EINCM_OK;
 }
 

@@ -244,6 +244,12 @@ class WindowObjective:
         self.n_evals += int(res.nfev)
         return theta, res
 
+    def minimize_bfgs_graph(self, theta0, cur_pyr_lvl: int, maxiter: int, gtol: float):
+        """The level solve as ONE CUDA graph with the loop on the device (eincm_minimize_bfgs_graph_host)."""
+        theta, res = self.plan.minimize_bfgs_graph_host(_as_theta(theta0), self.hparams(cur_pyr_lvl), maxiter, gtol)
+        self.n_evals += int(res.nfev)
+        return theta, res
+
     def minimize_handover(self, alpha0, bounds, prev_theta, theta, cur_pyr_lvl: int, maxiter: int, pgtol: float, own_stream: bool = False):
         a, res = self.plan.minimize_handover_host(alpha0, bounds, _as_theta(prev_theta), _as_theta(theta), self.hparams(cur_pyr_lvl),
                                                   maxiter, pgtol, own_stream=own_stream)

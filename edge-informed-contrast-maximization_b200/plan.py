@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     'eincm_theta_full_ptr', 'eincm_mask_ptr', 'eincm_get_scalars', 'eincm_debug_rounded_pixels', 'eincm_plan_info',
     'eincm_plan_set_event_split', 'eincm_plan_launch_count', 'eincm_plan_set_timing', 'eincm_plan_get_timing',
     'eincm_plan_ipc_handle', 'eincm_plan_set_peers', 'eincm_plan_set_peer_pointers', 'eincm_iwe_fix_ptr', 'eincm_split_prepare',
-    'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_handover_host', 'eincm_sparse_flow_error',
+    'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_bfgs_graph_host', 'eincm_minimize_handover_host', 'eincm_sparse_flow_error',
     'eincm_evaluate_theta', 'eincm_group_create', 'eincm_group_destroy', 'eincm_plan_set_group', 'eincm_group_set_burst_percent', 'eincm_plan_host_times',
     'eincm_edge_workspace_bytes', 'eincm_edge_maps', 'eincm_edge_maps_host',
     'eincm_nlm_workspace_bytes', 'eincm_nlm_denoise',
@@ -152,6 +152,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_split_prepare': (i32, [vp, vp]),
         'eincm_split_window_images': (i32, [vp, vp]),
         'eincm_minimize_bfgs_host': (i32, [vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
+        'eincm_minimize_bfgs_graph_host': (i32, [vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
         'eincm_minimize_handover_host': (i32, [vp, C.POINTER(dbl), dbl, dbl, vp, vp, i32, i32, hp, i32, dbl, C.POINTER(OptResult), vp]),
         'eincm_sparse_flow_error': (i32, [i32, i32, i32, vp, vp, vp, C.POINTER(FlowErrors), vp]),
         'eincm_evaluate_theta': (i32, [vp, vp, i32, i32, hp, vp, vp, C.POINTER(EvalMetrics), vp]),
@@ -498,6 +499,18 @@ class Plan:
         st = OWN_STREAM if own_stream else _stream_ptr(stream)
         self._check(self.lib.eincm_minimize_bfgs_host(self._h, theta.ctypes.data, theta.shape[0], theta.shape[1], C.byref(hp),
                                                       int(maxiter), float(gtol), C.byref(res), st))
+        return theta, res
+
+    def minimize_bfgs_graph_host(self, theta0: np.ndarray, hp: HParams, maxiter: int, gtol: float, stream=None):
+        """The same level solve with the loop on the device (one CUDA graph, no host round trip per evaluation): returns
+        ``(theta, OptResult)``.  ``stream`` None: the plan's own stream."""
+        theta = np.array(theta0, dtype=np.float64, order='C', copy=True)
+        if theta.ndim != 3 or theta.shape[2] != 2:
+            raise EincmError(EINCM_EINVAL, f'theta must have shape (h, w, 2), got {theta.shape}')
+        res = OptResult()
+        st = OWN_STREAM if stream is None else _stream_ptr(stream)
+        self._check(self.lib.eincm_minimize_bfgs_graph_host(self._h, theta.ctypes.data, theta.shape[0], theta.shape[1], C.byref(hp),
+                                                            int(maxiter), float(gtol), C.byref(res), st))
         return theta, res
 
     def minimize_handover_host(self, alpha0: float, bounds, prev_theta: np.ndarray, theta: np.ndarray, hp: HParams, maxiter: int,

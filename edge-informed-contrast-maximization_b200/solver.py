@@ -128,7 +128,7 @@ class MultipleLevelEINCMSolver:
         optimizers inside the library (``eincm_minimize_bfgs_host`` / ``eincm_minimize_handover_host``), one host call per
         level - per-iteration callbacks are not invoked.  ``own_stream``: run on the plan's own CUDA stream (several solvers
         driven from several host threads overlap on the GPU; the native calls release the GIL)."""
-        assert backend in ('scipy', 'native')
+        assert backend in ('scipy', 'native', 'graph')
         self.backend, self.own_stream = backend, own_stream
         self.objective = objective
         self.n_pyr_lvls = n_pyr_lvls
@@ -188,7 +188,12 @@ class MultipleLevelEINCMSolver:
     def _run_theta_solver(self, pyr_lvl: int, theta0: np.ndarray):
         """ScipyMinimize.run (solver.py:165-173, :209-216): BFGS on the raveled theta, jac=True."""
         key = f'pyr_lvl_{pyr_lvl}'
-        if self.backend == 'native':
+        if self.backend == 'graph' and int(np.prod(np.shape(theta0))) <= 1024:
+            # the whole level as one CUDA graph: the BFGS loop runs on the device (levels beyond 1024 parameters: native host loop)
+            theta, r = self.objective.minimize_bfgs_graph(theta0, pyr_lvl, self.theta_opt_maxiters[key],
+                                                          self.theta_opt_solver_params['options']['gtol'])
+            return theta, OptState(float(r.fun), r.status == 0, int(r.status), int(r.nit), int(r.nfev))
+        if self.backend in ('native', 'graph'):
             theta, r = self.objective.minimize_bfgs(theta0, pyr_lvl, self.theta_opt_maxiters[key],
                                                     self.theta_opt_solver_params['options']['gtol'], own_stream=self.own_stream)
             return theta, OptState(float(r.fun), r.status == 0, int(r.status), int(r.nit), int(r.nfev))
@@ -205,7 +210,7 @@ class MultipleLevelEINCMSolver:
     def _run_handover_solver(self, pyr_lvl: int, alpha0: float, bounds, prior_theta, theta):
         """ScipyBoundedMinimize.run (solver.py:175-183, :325-335): L-BFGS-B on the scalar handover weight."""
         key = f'pyr_lvl_{pyr_lvl}'
-        if self.backend == 'native':
+        if self.backend in ('native', 'graph'):
             a, r = self.objective.minimize_handover(alpha0, bounds, prior_theta, theta, pyr_lvl, self.handover_opt_maxiters[key],
                                                     self.handover_opt_solver_params['options']['gtol'], own_stream=self.own_stream)
             return a, OptState(float(r.fun), r.status == 0, int(r.status), int(r.nit), int(r.nfev))
