@@ -644,7 +644,7 @@ def run_own(args):
             flags = P.FLAG_BLOCKING_SYNC if wait == 'block' else 0
             objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(R, 3), flags=flags)
                     for _ in range(n_threads)]
-            sols = [SV.MultipleLevelEINCMSolver(o, backend=backend, own_stream=(backend == 'native')) for o in objs]
+            sols = [SV.MultipleLevelEINCMSolver(o, backend=backend, own_stream=(backend != 'scipy')) for o in objs]
             finals = [None] * n_threads
 
             def work(t, first, last):
@@ -653,13 +653,13 @@ def run_own(args):
                     sols[t].set_datasample(*seqs[t][k].args())
                     finals[t] = sols[t].solve()
 
-            n_rep = 3 if backend == 'native' else 1
+            n_rep = 3 if backend != 'scipy' else 1
             n_win = n_threads * args.solve_windows
             runs = []
             for rep in range(n_rep):
                 # every repeat starts from scratch: first window of the sequence untimed (no prior), then the chained windows
                 for t, sol in enumerate(sols):
-                    sols[t] = SV.MultipleLevelEINCMSolver(objs[t], backend=backend, own_stream=(backend == 'native'))
+                    sols[t] = SV.MultipleLevelEINCMSolver(objs[t], backend=backend, own_stream=(backend != 'scipy'))
                     work(t, 0, 1)
                 barrier()
                 n0 = sum(o.n_evals for o in objs)
@@ -696,6 +696,16 @@ def run_own(args):
                          '(eincm_minimize_bfgs_host / eincm_minimize_handover_host), one host thread and one CUDA stream per '
                          'sequence, windows of a sequence chained by handover, set_datasample (staging) inside the timed region; '
                          'sequences: same scene, truth flow drifting 8 % of the flow magnitude per window')
+        # one sequence per GPU: the host-driven loop against the loop on the device (one CUDA graph per pyramid level, no host round trip
+        # per evaluation; the scalar handover solves stay host-driven).  Several concurrent device loops do not overlap on the GPU the way
+        # host-driven streams do (profiles/r2_graph_solve.txt), so the headline above keeps three host-driven sequences per GPU.
+        one_native = run_solves('native', 1, args.solve_wait, seqs[:1])
+        one_graph = run_solves('graph', 1, args.solve_wait, seqs[:1])
+        solve['one_sequence_per_gpu'] = {
+            'host_loop': {'value': one_native['value'], 'repeats_windows_per_s': one_native['repeats_windows_per_s'], 'evals_per_window': one_native['evals_per_window']},
+            'device_graph_loop': {'value': one_graph['value'], 'repeats_windows_per_s': one_graph['repeats_windows_per_s'], 'evals_per_window': one_graph['evals_per_window'],
+                                  'call': 'eincm_minimize_bfgs_graph_host: WHILE conditional graph node { evaluation kernels ; k_bfgs_step } per pyramid level'},
+            'unit': 'windows/s'}
         if args.solve_compare and world == 1:
             solve['spinning'] = run_solves('native', n_seq, 'spin' if args.solve_wait == 'block' else 'block', seqs)
             solve['scipy_single_sequence'] = run_solves('scipy', 1, args.solve_wait, seqs[:1])
