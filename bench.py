@@ -696,16 +696,17 @@ def run_own(args):
                          '(eincm_minimize_bfgs_host / eincm_minimize_handover_host), one host thread and one CUDA stream per '
                          'sequence, windows of a sequence chained by handover, set_datasample (staging) inside the timed region; '
                          'sequences: same scene, truth flow drifting 8 % of the flow magnitude per window')
-        # one sequence per GPU: the host-driven loop against the loop on the device (one CUDA graph per pyramid level, no host round trip
-        # per evaluation; the scalar handover solves stay host-driven).  Several concurrent device loops do not overlap on the GPU the way
-        # host-driven streams do (profiles/r2_graph_solve.txt), so the headline above keeps three host-driven sequences per GPU.
-        one_native = run_solves('native', 1, args.solve_wait, seqs[:1])
-        one_graph = run_solves('graph', 1, args.solve_wait, seqs[:1])
-        solve['one_sequence_per_gpu'] = {
-            'host_loop': {'value': one_native['value'], 'repeats_windows_per_s': one_native['repeats_windows_per_s'], 'evals_per_window': one_native['evals_per_window']},
-            'device_graph_loop': {'value': one_graph['value'], 'repeats_windows_per_s': one_graph['repeats_windows_per_s'], 'evals_per_window': one_graph['evals_per_window'],
-                                  'call': 'eincm_minimize_bfgs_graph_host: WHILE conditional graph node { evaluation kernels ; k_bfgs_step } per pyramid level'},
-            'unit': 'windows/s'}
+        # The loop on the device (eincm_minimize_bfgs_graph_host: unrolled CUDA graphs of 8 x { evaluation ; k_bfgs_step }, the host relaunches
+        # ~7 times per pyramid level; the scalar handover solves stay host-driven): the same sequences, spinning and asleep between launches -
+        # asleep, the rate does not depend on host cores (profiles/r2_graph_solve.txt) - and one sequence per GPU against the host loop.
+        def brief(r):
+            return {'value': r['value'], 'repeats_windows_per_s': r['repeats_windows_per_s'], 'evals_per_window': r['evals_per_window']}
+        solve['device_graph_loop'] = {
+            'call': 'eincm_minimize_bfgs_graph_host per pyramid level (solver backend "graph")', 'unit': 'windows/s', 'sequences_per_gpu': n_seq,
+            'spinning_wait': brief(run_solves('graph', n_seq, 'spin', seqs)),
+            'blocking_wait': brief(run_solves('graph', n_seq, 'block', seqs)),
+            'one_sequence_per_gpu': {'device_graph_loop': brief(run_solves('graph', 1, args.solve_wait, seqs[:1])),
+                                     'host_loop': brief(run_solves('native', 1, args.solve_wait, seqs[:1]))}}
         if args.solve_compare and world == 1:
             solve['spinning'] = run_solves('native', n_seq, 'spin' if args.solve_wait == 'block' else 'block', seqs)
             solve['scipy_single_sequence'] = run_solves('scipy', 1, args.solve_wait, seqs[:1])

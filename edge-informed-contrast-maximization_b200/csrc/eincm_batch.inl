@@ -220,14 +220,14 @@ int eincm_batch_value_and_grad(eincm_batch* batch, const double* const* thetas, 
             s.T = T; s.H = H; s.W = W; s.R = R; s.tref = p->tref; s.dst.n = 1; s.dst.p[0] = p->iwe_fix; s.chunk_win = p->chunk_win;
             ImageStatsArgs& i = ia[k];
             i.fix = p->iwe_fix; i.edges = p->edges; i.iwe = p->iwe; i.adj32 = p->adj32;
-            i.part = p->part; i.sc = p->sc; i.loss_out = loss_out[k];
+            i.part = p->part; i.skip = nullptr; i.sc = p->sc; i.loss_out = loss_out[k];
             i.zero_buf = Gk; i.n_zero = (int)(HW * 2);
             i.zero_buf2 = dense ? nullptr : grad_out[k]; i.n_zero2 = dense ? 0 : h * w * 2;
             i.H = H; i.W = W; i.R = R; i.alpha = hp->alpha; i.beta = hp->beta; i.gamma = hp->gamma; i.use_tv = 0;
             ImageGradArgs& g = ga[k];
             g.fix = p->iwe_fix; g.edges = p->edges; g.iwe = p->iwe; g.adj32 = p->adj32; g.sc = p->sc; g.dldi = nullptr; g.dldi32 = p->dldi32;
             g.HW = (int)HW; g.R = R; g.want_grad = 1;
-            g.publish = 1; g.loss_out = loss_out[k]; g.alpha = hp->alpha; g.beta = hp->beta; g.gamma = hp->gamma; g.use_tv = 0;
+            g.publish = 1; g.skip = nullptr; g.loss_out = loss_out[k]; g.alpha = hp->alpha; g.beta = hp->beta; g.gamma = hp->gamma; g.use_tv = 0;
             BackwardTileArgs& b = ba[k];
             b.ev_xy = p->ev_xy; b.ev_t = p->ev_t; b.chunks = p->chunks; b.n_chunks_dev = p->totals + 1; b.T = T; b.H = H; b.W = W; b.R = R;
             b.tref = p->tref; b.dldi32 = p->dldi32; b.chunk_win = p->chunk_win; b.G = Gk;

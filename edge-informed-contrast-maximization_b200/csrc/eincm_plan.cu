@@ -132,6 +132,8 @@ struct eincm_plan {
     uint64_t window_gen = 0;             // staged windows so far: graphs bake per-window kernel parameters (reference times, chunk count)
     struct LevelGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; uint64_t gen = 0; };
     std::map<std::vector<double>, LevelGraph> bfgs_graphs;
+    const int* eval_skip = nullptr;      // while a solve graph is captured: the level's "done" flag, handed to the evaluation kernels
+    int graph_unroll = 8;                // evaluations per launch of an unrolled solve graph; 0: the WHILE conditional form (EINCM_GRAPH_UNROLL)
     bool graph_no_pdl = false;           // programmatic dependent launches could not be captured into the loop body: plain launches there
     std::string error;
     // launch accounting / optional per-kernel timing
@@ -343,7 +345,7 @@ int splat_images(eincm_plan* plan, const ThetaSrc& T, const double2* theta_full,
         if (plan->n_peers > 0) { dst.n = plan->n_peers; for (int q = 0; q < dst.n; ++q) dst.p[q] = plan->peer_fix[q]; }
         else { dst.n = 1; dst.p[0] = plan->iwe_fix; }
 #define SPLATT(WR, RB) LAUNCH(tag, launch_pdl(k_splat_tile<WR, RB>, dim3(grid), dim3(256), RB * kWinCap * sizeof(uint32_t), st, (const uint32_t*)plan->ev_xy, \
-                               (const double*)plan->ev_t, (const Chunk*)plan->chunks, (const float2*)plan->chunk_tr, (const unsigned int*)(plan->totals + 1), T, H, W, n_img, tref, dst, cw))
+                               (const double*)plan->ev_t, (const Chunk*)plan->chunks, (const float2*)plan->chunk_tr, (const unsigned int*)(plan->totals + 1), T, H, W, n_img, tref, dst, cw, plan->eval_skip))
 #define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
                                                              case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
         if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
@@ -431,6 +433,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         ia.fix = plan->iwe_fix; ia.edges = plan->edges; ia.iwe = plan->iwe; ia.adj32 = plan->adj32;
         ia.part = plan->part + 2 * tvb;                          // k_tv's partials live at the start of `part`
         ia.sc = plan->sc; ia.loss_out = loss_out;
+        ia.skip = plan->eval_skip;
         ia.zero_buf = want_grad ? plan->G : nullptr; ia.n_zero = (int)(plan->HW * 2);     // cleared for the event backward pass
         g_zeroed = want_grad;
         if (want_grad && h * w <= kGatherMaxTiles) {
@@ -442,7 +445,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         LAUNCH("k_image_stats", launch_pdl(k_image_stats, dim3(R * image_stats_ctas(H, W)), dim3(kS2NT), 0, st, ia));
         // the loss is evaluated by a spare CTA of k_image_grad (publish_loss), off the critical path of the evaluation
         auto tail_args = [&](ImageGradArgs& ga) {
-            ga.publish = 1; ga.loss_out = loss_out; ga.alpha = hp->alpha; ga.beta = hp->beta; ga.gamma = hp->gamma; ga.use_tv = use_tv ? 1 : 0;
+            ga.publish = 1; ga.skip = plan->eval_skip; ga.loss_out = loss_out; ga.alpha = hp->alpha; ga.beta = hp->beta; ga.gamma = hp->gamma; ga.use_tv = use_tv ? 1 : 0;
         };
         ImageGradArgs ga{};
         ga.fix = plan->iwe_fix; ga.edges = plan->edges; ga.iwe = plan->iwe; ga.adj32 = plan->adj32; ga.sc = plan->sc;
@@ -497,7 +500,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
             const int gridT2 = std::max(1, plan->n_chunks);
 #define BWDT(WR, RB) LAUNCH("k_backward_events", launch_pdl(k_backward_tile<WR, RB>, dim3(gridT2), dim3(256), RB * kWinCap * sizeof(float), st, (const uint32_t*)plan->ev_xy, \
                                    (const double*)plan->ev_t, (const Chunk*)plan->chunks, (const unsigned int*)(plan->totals + 1), plan->tsrc, H, W, R, plan->tref, \
-                                   (const float*)plan->dldi32, (const int4*)plan->chunk_win, plan->G))
+                                   (const float*)plan->dldi32, (const int4*)plan->chunk_win, plan->G, plan->eval_skip))
 #define BWDT_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BWDT(WR, 1); break; case 2: BWDT(WR, 2); break; \
                                                            case 3: BWDT(WR, 3); break; default: BWDT(WR, 4); } } while (0)
             if (plan->wrap) BWDT_RB(true); else BWDT_RB(false);
@@ -524,11 +527,12 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
         if (Gtv != nullptr)
             LAUNCH("k_theta_grad", k_theta_grad<true><<<gridG, kTgWarps * 32, 0, st>>>(
                 (const double2*)plan->G, Gtv, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0));
+                handover ? plan->last_prev : nullptr, plan->last_theta, gout, loss_out, host_out, grad_out != nullptr ? 1 : 0, plan->eval_skip));
         else
             LAUNCH("k_theta_grad", launch_pdl(k_theta_grad<false>, dim3(gridG), dim3(kTgWarps * 32), 0, st,
                 (const double2*)plan->G, (const double2*)nullptr, plan->sc, hp->gamma, h, w, H, W, SY, SX, n_items, ty, tx,
-                (const double*)(handover ? plan->last_prev : nullptr), plan->last_theta, gout, (const double*)loss_out, host_out, grad_out != nullptr ? 1 : 0));
+                (const double*)(handover ? plan->last_prev : nullptr), plan->last_theta, gout, (const double*)loss_out, host_out, grad_out != nullptr ? 1 : 0,
+                plan->eval_skip));
         plan->host_delivered = host_out != nullptr;
     } else {
         CU(cudaMemsetAsync(&plan->sc->dalpha, 0, sizeof(double), st));
@@ -594,6 +598,7 @@ int eincm_plan_create(eincm_plan** out, int device, int H, int W, int64_t max_ev
     plan->device = device; plan->H = H; plan->W = W; plan->HW = (int64_t)H * W; plan->max_events = max_events;
     plan->max_refs = max_refs; plan->flags = flags; plan->wrap = !(flags & EINCM_FLAG_NO_WRAP_NEGATIVE);
     plan->exact = (flags & EINCM_FLAG_EXACT_F64) != 0;
+    { const char* gu = std::getenv("EINCM_GRAPH_UNROLL"); if (gu != nullptr) plan->graph_unroll = std::max(0, std::min(64, std::atoi(gu))); }
     plan->sm_count = prop.multiProcessorCount;
     plan->coop_ok = true;            // the streaming image pass has no limit on the sensor width
     plan->tiles_x = (W + kSortTile - 1) / kSortTile;
@@ -1108,7 +1113,7 @@ namespace {
 
 // Builds the graph of one level solve: k_bfgs_init -> WHILE { evaluation at x_trial ; k_bfgs_step } -> result to pinned host memory.
 int build_level_graph(eincm_plan* plan, eincm_plan::LevelGraph& lg, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
-                      cudaStream_t st, bool plain_launches) {
+                      cudaStream_t st, bool plain_launches, int unroll) {
     const int n = h * w * 2;
     double* v = plan->bfgs_vec;
     BfgsBufs B{};
@@ -1117,6 +1122,38 @@ int build_level_graph(eincm_plan* plan, eincm_plan::LevelGraph& lg, int h, int w
     double* f_trial = v + 8 * n;
     B.g_trial = g_trial; B.f_trial = f_trial; B.result = v + 8 * n + 8; B.H = plan->bfgs_H;
     cudaGraph_t graph = nullptr;
+    if (unroll > 0) {
+        // Unrolled form: `unroll` x { evaluation ; k_bfgs_step } + the result copy, captured as an ordinary graph; k_bfgs_init runs before
+        // the first launch and the host relaunches until the record says done.  Once the level has ended, the remaining evaluations and
+        // steps of a launch return at once (skip flag).  Ordinary kernel nodes: graphs of different plans overlap like streams do.
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+            return fail(plan, EINCM_ECUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(cudaGetLastError()));
+        t_plain_launches = plain_launches;
+        plan->eval_skip = &plan->bfgs_state->done;
+        int rcu = EINCM_OK;
+        for (int k = 0; k < unroll && rcu == EINCM_OK; ++k) {
+            rcu = forward_events_impl(plan, B.x_trial, nullptr, 0.0, h, w, hp, st);
+            if (rcu == EINCM_OK) rcu = backward_impl(plan, hp, f_trial, g_trial, nullptr, st);
+            if (rcu == EINCM_OK) {
+                k_bfgs_step<<<1, kOptNT, 0, st>>>(plan->bfgs_state, B, (cudaGraphConditionalHandle)0, 0);
+                if (cudaGetLastError() != cudaSuccess) rcu = fail(plan, EINCM_ECUDA, "launch k_bfgs_step");
+            }
+        }
+        plan->eval_skip = nullptr;
+        t_plain_launches = false;
+        if (rcu == EINCM_OK && cudaMemcpyAsync(plan->h_pinned, B.result, (size_t)(5 + n) * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rcu = fail(plan, EINCM_ECUDA, "capture of the result copy");
+        const cudaError_t ecu = cudaStreamEndCapture(st, &graph);
+        if (rcu != EINCM_OK) { if (graph) cudaGraphDestroy(graph); return rcu; }
+        if (ecu != cudaSuccess) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return fail(plan, EINCM_ECUDA, "capture of the unrolled level: %s", cudaGetErrorString(ecu)); }
+        cudaGraphExec_t exec_u = nullptr;
+        const cudaError_t eiu = cudaGraphInstantiate(&exec_u, graph, 0);
+        if (eiu != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); return fail(plan, EINCM_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(eiu)); }
+        if (lg.exec) cudaGraphExecDestroy(lg.exec);
+        if (lg.graph) cudaGraphDestroy(lg.graph);
+        lg.graph = graph; lg.exec = exec_u; lg.gen = plan->window_gen;
+        return EINCM_OK;
+    }
     CU(cudaGraphCreate(&graph, 0));
     auto bail = [&](int rc) { cudaGraphDestroy(graph); return rc; };
     // node 1: state
@@ -1149,7 +1186,7 @@ int build_level_graph(eincm_plan* plan, eincm_plan::LevelGraph& lg, int h, int w
     if (rc == EINCM_OK) rc = backward_impl(plan, hp, f_trial, g_trial, nullptr, st);
     t_plain_launches = false;
     if (rc == EINCM_OK) {
-        k_bfgs_step<<<1, kOptNT, 0, st>>>(plan->bfgs_state, B, handle);
+        k_bfgs_step<<<1, kOptNT, 0, st>>>(plan->bfgs_state, B, handle, 1);
         if (cudaGetLastError() != cudaSuccess) rc = fail(plan, EINCM_ECUDA, "launch k_bfgs_step");
     }
     cudaGraph_t captured = nullptr;
@@ -1158,7 +1195,7 @@ int build_level_graph(eincm_plan* plan, eincm_plan::LevelGraph& lg, int h, int w
     if (ec != cudaSuccess) { cudaGetLastError(); return bail(fail(plan, EINCM_ECUDA, "capture of the loop body: %s", cudaGetErrorString(ec))); }
     // node 3: result record [fun, nit, nfev, status, x] -> pinned host memory
     cudaGraphNode_t n_out = nullptr;
-    if (cudaGraphAddMemcpyNode1D(&n_out, graph, &n_loop, 1, plan->h_pinned, B.result, (size_t)(4 + n) * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (cudaGraphAddMemcpyNode1D(&n_out, graph, &n_loop, 1, plan->h_pinned, B.result, (size_t)(5 + n) * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
         return bail(fail(plan, EINCM_ECUDA, "cudaGraphAddMemcpyNode1D: %s", cudaGetErrorString(cudaGetLastError())));
     cudaGraphExec_t exec = nullptr;
     const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
@@ -1191,13 +1228,17 @@ int eincm_minimize_bfgs_graph_host(eincm_plan* plan, double* theta_inout_host, i
         for (auto& kv : plan->bfgs_graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); if (kv.second.graph) cudaGraphDestroy(kv.second.graph); }
         plan->bfgs_graphs.clear();
         const int cap = std::max(n, 512);
-        CU(dmalloc(&plan->bfgs_vec, (size_t)9 * cap + 16 + 4 + cap));
+        CU(dmalloc(&plan->bfgs_vec, (size_t)9 * cap + 16 + 8 + cap));
         CU(dmalloc(&plan->bfgs_H, (size_t)cap * cap));
         if (!plan->bfgs_state) CU(dmalloc(&plan->bfgs_state, 1));
         plan->bfgs_cap_n = cap;
     }
-    const std::vector<double> key = {(double)h, (double)w, (double)maxiter, gtol, hp->alpha, hp->beta, hp->gamma, hp->delta, (double)hp->cur_pyr_lvl,
-                                     (double)hp->n_pyr_lvls, (double)hp->method};
+    // the unrolled form needs the skip flag in every kernel of the evaluation: the TV kernels (gamma != 0 at level 0) do not take one
+    const bool use_tv = hp->gamma != 0.0 && hp->cur_pyr_lvl <= 0;
+    const int unroll = use_tv ? 0 : plan->graph_unroll;
+    // the WHILE form bakes maxiter and gtol into its init node; the unrolled form takes them at run time
+    const std::vector<double> key = {(double)h, (double)w, unroll > 0 ? -1.0 : (double)maxiter, unroll > 0 ? -1.0 : gtol, hp->alpha, hp->beta, hp->gamma,
+                                     hp->delta, (double)hp->cur_pyr_lvl, (double)hp->n_pyr_lvls, (double)hp->method, (double)unroll};
     eincm_plan::LevelGraph& lg = plan->bfgs_graphs[key];
     if (lg.exec == nullptr || lg.gen != plan->window_gen) {
         // everything the captured calls would do synchronously or across streams happens here, outside the capture
@@ -1214,27 +1255,43 @@ int eincm_minimize_bfgs_graph_host(eincm_plan* plan, double* theta_inout_host, i
         }
         const bool was_timing = plan->timing;
         plan->timing = false;                        // event records are not part of a loop body
-        rc = build_level_graph(plan, lg, h, w, hp, maxiter, gtol, st, plan->graph_no_pdl);
+        rc = build_level_graph(plan, lg, h, w, hp, maxiter, gtol, st, plan->graph_no_pdl, unroll);
         if (rc != EINCM_OK && !plan->graph_no_pdl) {                     // once more without programmatic edges in the body
             plan->graph_no_pdl = true;
             plan->fix_clean = true;
-            rc = build_level_graph(plan, lg, h, w, hp, maxiter, gtol, st, true);
+            rc = build_level_graph(plan, lg, h, w, hp, maxiter, gtol, st, true, unroll);
         }
         plan->timing = was_timing;
         if (rc != EINCM_OK) return rc;
     }
     // run: theta in through the pinned staging area, the whole level on the device, one synchronisation
     const size_t nb = (size_t)n * sizeof(double);
-    std::memcpy(plan->h_pinned + 4 + n, theta_inout_host, nb);
-    CU(cudaMemcpyAsync(plan->bfgs_vec + 6 * (size_t)n, plan->h_pinned + 4 + n, nb, cudaMemcpyHostToDevice, st));
-    CU(cudaGraphLaunch(lg.exec, st));
-    rc = host_wait(plan, st);
-    if (rc) return rc;
+    double* stage = plan->h_pinned + 8 + n;                          // behind the result record [done, fun, nit, nfev, status, theta]
+    std::memcpy(stage, theta_inout_host, nb);
+    CU(cudaMemcpyAsync(plan->bfgs_vec + 6 * (size_t)n, stage, nb, cudaMemcpyHostToDevice, st));
+    if (unroll > 0) {
+        k_bfgs_init<<<1, 32, 0, st>>>(plan->bfgs_state, n, maxiter, gtol);
+        if (cudaGetLastError() != cudaSuccess) return fail(plan, EINCM_ECUDA, "launch k_bfgs_init");
+        // every launch runs up to `unroll` evaluations; a line search takes at most 100 + 21 of them per iteration
+        const long max_launches = ((long)maxiter + 1) * 122 / unroll + 2;
+        plan->h_pinned[0] = 0.0;
+        for (long l = 0;; ++l) {
+            CU(cudaGraphLaunch(lg.exec, st));
+            rc = host_wait(plan, st);
+            if (rc) return rc;
+            if (plan->h_pinned[0] != 0.0) break;
+            if (l >= max_launches) return fail(plan, EINCM_ECUDA, "the device-side loop did not end within %ld launches", max_launches);
+        }
+    } else {
+        CU(cudaGraphLaunch(lg.exec, st));
+        rc = host_wait(plan, st);
+        if (rc) return rc;
+    }
     // the graph ran the evaluation at least once: the plan's bookkeeping is the one the captured calls left behind
     plan->fix_clean = true; plan->forward_done = true; plan->host_delivered = false;
     const double* r = plan->h_pinned;
-    result_out->fun = r[0]; result_out->nit = (int32_t)r[1]; result_out->nfev = (int32_t)r[2]; result_out->status = (int32_t)r[3]; result_out->reserved = 0;
-    std::memcpy(theta_inout_host, r + 4, nb);
+    result_out->fun = r[1]; result_out->nit = (int32_t)r[2]; result_out->nfev = (int32_t)r[3]; result_out->status = (int32_t)r[4]; result_out->reserved = 0;
+    std::memcpy(theta_inout_host, r + 5, nb);
     plan->host_evals += result_out->nfev;
     return EINCM_OK;
 }

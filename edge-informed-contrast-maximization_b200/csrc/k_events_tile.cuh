@@ -448,7 +448,7 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
              const float2* __restrict__ chunk_tr, const unsigned int* __restrict__ n_chunks_dev,
              const ThetaSrc& T, int H, int W, int R, const RefTimes& tref,
              const FixDst& dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */,
-             uint32_t* win /* [RB][kWinCap] dynamic shared memory */) {
+             uint32_t* win /* [RB][kWinCap] dynamic shared memory */, const int* __restrict__ skip = nullptr) {
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ int sbox[8][4];
     __shared__ Window swin[RB];
@@ -471,6 +471,8 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
         // of the previous evaluation: it clears the fixed-point images and reads chunk_win) was still running - only the staged
         // events were read so far
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        // unrolled solve graphs (eincm_minimize_bfgs_graph_host): the level ended in an earlier step of this launch - nothing to do
+        if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;
         tile_theta_range(tile_theta(T, ch.origin, H, W, th_s), sbox);
         if (tid == 0) s_sliced = 0;
         int n_pairs = 0;                             // only used by the passes over further slices
@@ -643,9 +645,10 @@ __global__ void __launch_bounds__(256, 4)
 k_splat_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks,
              const float2* __restrict__ chunk_tr, const unsigned int* __restrict__ n_chunks_dev,
              const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
-             const __grid_constant__ FixDst dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */) {
+             const __grid_constant__ FixDst dst /* [R][H*W] each */, int4* __restrict__ chunk_win /* [n_chunks][R] or null */,
+             const int* __restrict__ skip /* non-zero: return at once (or null) */) {
     extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
-    splat_tile_body<WRAP, RB>(ev_xy, ev_t, chunks, chunk_tr, n_chunks_dev, T, H, W, R, tref, dst, chunk_win, win);
+    splat_tile_body<WRAP, RB>(ev_xy, ev_t, chunks, chunk_tr, n_chunks_dev, T, H, W, R, tref, dst, chunk_win, win, skip);
 }
 
 // ---- batched form: one launch for B windows (blockIdx.y = window), one argument record per window in device memory ------------------
@@ -687,7 +690,7 @@ template <bool WRAP, int RB>
 __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
                 const ThetaSrc& T, int H, int W, int R, const RefTimes& tref,
                 const float* __restrict__ dldi32 /* [R][H][W], scaled by 1/(2 pi) */, const int4* __restrict__ chunk_win,
-                double* __restrict__ G /* [H][W][2] */, float* dwin /* [RB][kWinCap] dynamic shared memory */) {
+                double* __restrict__ G /* [H][W][2] */, float* dwin /* [RB][kWinCap] dynamic shared memory */, const int* __restrict__ skip = nullptr) {
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ Window swin[RB];
     const int64_t HW = (int64_t)H * W;
@@ -702,7 +705,10 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
         load_sub_events<false>(ev_xy, ev_t, ch, 0, ev);
         tile_theta(T, ch.origin, H, W, th_s);
         // programmatic dependent launch: everything above read the staged events and the flow operand only
-        if (c == (int)blockIdx.x) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (c == (int)blockIdx.x) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;
+        }
         // With R <= RB (one group of reference times: the shipped recipes up to R = 4) the windows are filled once and every sub-chunk
         // gathers from them; otherwise they are refilled per (sub-chunk, group).
         const bool one_group = R <= RB;
@@ -842,9 +848,9 @@ __global__ void __launch_bounds__(256, 4)
 k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk* __restrict__ chunks, const unsigned int* __restrict__ n_chunks_dev,
                 const ThetaSrc T, int H, int W, int R, const __grid_constant__ RefTimes tref,
                 const float* __restrict__ dldi32 /* [R][H][W], scaled by 1/(2 pi) */, const int4* __restrict__ chunk_win,
-                double* __restrict__ G /* [H][W][2] */) {
+                double* __restrict__ G /* [H][W][2] */, const int* __restrict__ skip /* non-zero: return at once (or null) */) {
     extern __shared__ __align__(16) float dwin[];            // [RB][kWinCap]
-    backward_tile_body<WRAP, RB>(ev_xy, ev_t, chunks, n_chunks_dev, T, H, W, R, tref, dldi32, chunk_win, G, dwin);
+    backward_tile_body<WRAP, RB>(ev_xy, ev_t, chunks, n_chunks_dev, T, H, W, R, tref, dldi32, chunk_win, G, dwin, skip);
 }
 
 struct BackwardTileArgs {

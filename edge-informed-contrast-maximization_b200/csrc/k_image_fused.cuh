@@ -82,6 +82,7 @@ struct ImageStatsArgs {
     double* part;                   // [R][image_stats_ctas(H, W)][kFPart]: one record per CTA
     DevScalars* sc;
     double* loss_out;
+    const int* skip;                // non-zero: return at once (unrolled solve graphs), or null
     double* zero_buf;               // buffers cleared for the event backward pass (dense flow-field gradient, theta gradient) or null
     double* zero_buf2;
     int n_zero, n_zero2;
@@ -194,6 +195,7 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
     // this kernel itself may have been scheduled while the splat was still running - nothing is read or written before the wait
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (A.skip != nullptr && *reinterpret_cast<const volatile int*>(A.skip) != 0) return;
     // accumulators of the event backward pass
     if (A.zero_buf != nullptr)
         for (int k = b * kS2NT + tid; k < A.n_zero; k += G * kS2NT) A.zero_buf[k] = 0.0;
@@ -338,6 +340,7 @@ struct ImageGradArgs {
     const double* iwe;
     const float* adj32;
     DevScalars* sc;
+    const int* skip;                // non-zero: return at once (unrolled solve graphs), or null
     int publish;                    // != 0: the grid has one CTA more than the pointwise pass needs; it publishes the loss (publish_loss)
     int use_tv;
     double* loss_out;
@@ -352,6 +355,7 @@ __device__ __forceinline__ void image_grad_body(const ImageGradArgs& A) {
     // programmatic dependent launch (no-ops when launched plainly): let the next kernel be scheduled, wait for the image statistics
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (A.skip != nullptr && *reinterpret_cast<const volatile int*>(A.skip) != 0) return;
     __shared__ double s_mn[kCoopMaxRefs], s_mx[kCoopMaxRefs], s_iD[kCoopMaxRefs], s_cA[kCoopMaxRefs], s_cB[kCoopMaxRefs], s_tm[kCoopMaxRefs], s_tM[kCoopMaxRefs];
     // The last CTA of a publishing launch only evaluates the loss from the statistics (a serial chain of float64 divisions that nothing
     // before k_theta_grad waits for) and leaves; the pointwise pass belongs to the other CTAs.

@@ -1,10 +1,10 @@
 // Device-side solve loop: scipy's BFGS for one pyramid level without a host round trip per evaluation.
-// The level solve is ONE CUDA graph: [k_bfgs_init] -> WHILE (conditional node) { the evaluation kernels at x_trial ; k_bfgs_step } ->
-// copies of the result.  k_bfgs_step consumes the loss and gradient of the evaluation that just ran, advances the line search
-// (eincm_linesearch.h: the same resumable machines as the host optimizer, so the same schedule as scipy - reference
-// src/eincm/solver.py:165-173 calls scipy.optimize.minimize(method='BFGS') through jaxopt), applies the inverse-Hessian update when a
-// step is accepted, writes the next trial point, and clears the loop condition when the solve ends.  One CTA: n <= kOptMaxN flow
-// parameters (512 at the finest shipped level), the dense inverse Hessian (2 MB at n = 512) lives in global memory.
+// k_bfgs_step consumes the loss and gradient of the evaluation that just ran at x_trial, advances the line search (eincm_linesearch.h: the
+// same resumable machines as the host optimizer, so the same schedule as scipy - reference src/eincm/solver.py:165-173 calls
+// scipy.optimize.minimize(method='BFGS') through jaxopt), applies the inverse-Hessian update when a step is accepted, writes the next trial
+// point, and marks the level done.  eincm_plan.cu puts it into CUDA graphs: K x { evaluation kernels ; k_bfgs_step } relaunched until done
+// (the kernels behind the end of the level read `done` as their skip flag), or one WHILE conditional node whose condition the step clears.
+// One CTA: n <= kOptMaxN flow parameters (512 at the finest shipped level), the dense inverse Hessian (2 MB at n = 512) in global memory.
 #pragma once
 #include "common.cuh"
 #include "eincm_linesearch.h"
@@ -17,7 +17,8 @@ constexpr int kOptMaxN = 1024;
 struct BfgsDev {
     eincm_opt::Wolfe12 w;
     double f, old_f, gnorm, gtol;
-    int n, nit, nfev, status, maxiter, phase, pad0, pad1;
+    int n, nit, nfev, status, maxiter, phase;
+    int done, pad;                           // done: the level has ended (the evaluation kernels of an unrolled graph read it as their skip flag)
 };
 
 struct BfgsBufs {
@@ -25,12 +26,12 @@ struct BfgsBufs {
     double* x_trial;                         // [n] theta operand of the evaluation kernels
     const double* g_trial;                   // [n] their gradient
     const double* f_trial;                   // their loss
-    double* result;                          // [4 + n]: fun, nit, nfev, status, x
+    double* result;                          // [5 + n]: done, fun, nit, nfev, status, x
 };
 
 __global__ void k_bfgs_init(BfgsDev* S, int n, int maxiter, double gtol) {
     if (threadIdx.x == 0) {
-        S->n = n; S->maxiter = maxiter; S->gtol = gtol; S->phase = 0; S->nit = 0; S->nfev = 0; S->status = 0;
+        S->n = n; S->maxiter = maxiter; S->gtol = gtol; S->phase = 0; S->nit = 0; S->nfev = 0; S->status = 0; S->done = 0;
         S->f = 0.0; S->old_f = 0.0; S->gnorm = 0.0;
     }
 }
@@ -47,7 +48,10 @@ __device__ __forceinline__ double opt_block_all(double v, Op op, double* sh /* 3
 }
 
 __global__ void __launch_bounds__(kOptNT)
-k_bfgs_step(BfgsDev* __restrict__ S, const BfgsBufs B, cudaGraphConditionalHandle handle) {
+k_bfgs_step(BfgsDev* __restrict__ S, const BfgsBufs B, cudaGraphConditionalHandle handle, int use_handle) {
+    // use_handle: the step is the tail of a WHILE conditional node and ends the loop through `handle`; otherwise it is one of the K steps of
+    // an unrolled graph that the host relaunches until `done` (the steps and evaluations behind the last one return at once)
+    if (S->done != 0) return;
     __shared__ double sh[33];
     __shared__ double s_alpha;
     __shared__ int s_act;
@@ -148,19 +152,22 @@ k_bfgs_step(BfgsDev* __restrict__ S, const BfgsBufs B, cudaGraphConditionalHandl
     }
     if (act == ACT_TRIAL) {
         if (in) B.x_trial[tid] = B.x[tid] + s_alpha * B.p[tid];
+        if (tid == 0) B.result[0] = 0.0;
         return;
     }
     // the level is solved: status as scipy reports it, result record, loop condition off
     const double xi = in ? B.x[tid] : 0.0;
     const double bad = opt_block_all((in && xi != xi) ? 1.0 : 0.0, OpMax(), sh);
-    if (in) B.result[4 + tid] = xi;
+    if (in) B.result[5 + tid] = xi;
     if (tid == 0) {
         int status = S->status;
         if (status == 0 && S->gnorm > S->gtol && S->nit >= S->maxiter) status = 1;
         else if (status == 0 && (bad != 0.0 || S->gnorm != S->gnorm || S->f != S->f)) status = 3;
         S->status = status;
-        B.result[0] = S->f; B.result[1] = (double)S->nit; B.result[2] = (double)S->nfev; B.result[3] = (double)status;
-        cudaGraphSetConditional(handle, 0u);
+        B.result[1] = S->f; B.result[2] = (double)S->nit; B.result[3] = (double)S->nfev; B.result[4] = (double)status;
+        B.result[0] = 1.0;
+        S->done = 1;
+        if (use_handle) cudaGraphSetConditional(handle, 0u);
     }
 }
 

@@ -86,10 +86,12 @@ template <bool HAS_TV>
 __device__ __forceinline__ void theta_grad_body(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
              double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, const AxisTaps& ty, const AxisTaps& tx,
              const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */,
-             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad) {
+             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad,
+             const int* __restrict__ skip = nullptr) {
     // programmatic dependent launch (no-ops when launched plainly)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (skip != nullptr && *reinterpret_cast<const volatile int*>(skip) != 0) return;
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kTgWarps + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -182,8 +184,9 @@ __global__ void __launch_bounds__(kTgWarps * 32)
 k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, DevScalars* __restrict__ sc,
              double gamma, int h, int w, int H, int W, int SY, int SX, int n_items, AxisTaps ty, AxisTaps tx,
              const double* __restrict__ prev, const double* __restrict__ theta, double* __restrict__ grad /* [h][w][2] */,
-             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad) {
-    theta_grad_body<HAS_TV>(G, Gtv, sc, gamma, h, w, H, W, SY, SX, n_items, ty, tx, prev, theta, grad, loss_dev, host_out, host_grad);
+             const double* __restrict__ loss_dev, double* __restrict__ host_out /* mapped pinned memory or null */, int host_grad,
+             const int* __restrict__ skip /* non-zero: return at once (or null) */) {
+    theta_grad_body<HAS_TV>(G, Gtv, sc, gamma, h, w, H, W, SY, SX, n_items, ty, tx, prev, theta, grad, loss_dev, host_out, host_grad, skip);
 }
 
 // batched form (blockIdx.y = window; gamma == 0): one argument record per window in device memory

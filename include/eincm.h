@@ -180,15 +180,17 @@ int eincm_minimize_bfgs_host(eincm_plan* plan, double* theta_inout_host /* [h][w
 int eincm_minimize_handover_host(eincm_plan* plan, double* alpha_inout_host, double lo, double hi, const double* prev_theta_host,
                                  const double* theta_host, int h, int w, const eincm_hparams* hp, int maxiter, double pgtol,
                                  eincm_opt_result* result_out, void* cuda_stream);
-/* The same BFGS level solve with the loop ON THE DEVICE: one CUDA graph per level - a WHILE conditional node whose
- * body is the evaluation (the kernels eincm_value_and_grad enqueues, at a trial point in device memory) followed by k_bfgs_step, which
- * advances scipy's line search (the same resumable machines as eincm_minimize_bfgs_host: csrc/eincm_linesearch.h), applies the
- * inverse-Hessian update and clears the loop condition when the level ends.  No host round trip per evaluation: theta in, one launch, one
- * synchronisation, [fun, nit, nfev, status, theta] out.  Same arguments, results and status codes as eincm_minimize_bfgs_host (iterates
- * agree to rounding: the reductions run in another order); h * w * 2 <= 1024 flow parameters, default evaluation path only (no
- * EINCM_FLAG_EXACT_F64, delta == 0), EINCM_EINVAL / EINCM_ESTATE otherwise.  cuda_stream: NULL or (void*)-1 select the plan's own stream
- * (the legacy default stream cannot be captured).  The graph of a level is rebuilt once per staged window (it bakes the window's
- * reference times and chunk count) and re-used for repeated solves of that window. */
+/* The same BFGS level solve with the loop ON THE DEVICE.  k_bfgs_step consumes the loss and gradient of the evaluation
+ * that just ran at a trial point in device memory, advances scipy's line search (the same resumable machines as eincm_minimize_bfgs_host:
+ * csrc/eincm_linesearch.h), applies the inverse-Hessian update and writes the next trial point.  Two CUDA-graph forms: unrolled (default) -
+ * 8 x { evaluation kernels ; k_bfgs_step } as an ordinary graph that the call relaunches until the level is done (~7 launches per level;
+ * the kernels behind the end of the level return at once), graphs of several plans overlap like streams; or one WHILE conditional node
+ * around { evaluation ; k_bfgs_step } (environment EINCM_GRAPH_UNROLL=0, and whenever the TV regulariser is active): one launch per level.
+ * Same arguments, results and status codes as eincm_minimize_bfgs_host (iterates agree to rounding: the reductions run in another order);
+ * h * w * 2 <= 1024 flow parameters, default evaluation path only (no EINCM_FLAG_EXACT_F64, delta == 0), EINCM_EINVAL / EINCM_ESTATE
+ * otherwise.  cuda_stream: NULL or (void*)-1 select the plan's own stream (the legacy default stream cannot be captured).  With
+ * EINCM_FLAG_BLOCKING_SYNC the host sleeps between launches: no spinning core per sequence.  The graph of a level is rebuilt once per
+ * staged window (it bakes the window's reference times and chunk count) and re-used for repeated solves of that window. */
 int eincm_minimize_bfgs_graph_host(eincm_plan* plan, double* theta_inout_host /* [h][w][2] */, int h, int w, const eincm_hparams* hp,
                                    int maxiter, double gtol, eincm_opt_result* result_out, void* cuda_stream);
 /* Stateless single shot with the exact operand list of loss_func (losses.py:108-114), every operand on the host:

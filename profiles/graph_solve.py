@@ -7,6 +7,8 @@ from eincm_b200 import losses, plan as P, solver as SV, synth
 ap = argparse.ArgumentParser()
 ap.add_argument('--threads', type=int, default=1)
 ap.add_argument('--windows', type=int, default=4)
+ap.add_argument('--blocking', action='store_true', help='EINCM_FLAG_BLOCKING_SYNC: the host waits asleep on an event')
+ap.add_argument('--skip-levels', action='store_true')
 a = ap.parse_args()
 torch.cuda.set_device(0)
 seq = synth.make_sequence('dsec', 1 + a.windows, seed=0)
@@ -16,7 +18,7 @@ N = len(seq[0].xs)
 # one level at a time
 p = P.Plan((H, W), max_events=N, max_refs=3)
 p.set_window(*seq[0].args())
-for shape, lvl, maxiter in (((1, 1), 4, 8), ((4, 4), 2, 19), ((16, 16), 0, 40)):
+for shape, lvl, maxiter in (() if a.skip_levels else (((1, 1), 4, 8), ((4, 4), 2, 19), ((16, 16), 0, 40))):
     hp = P.make_hparams(hpd['alpha'], hpd['beta'], 0.0, 0.0, lvl)
     th0 = 0.5 * synth.theta_test_points(seq[0], shape)['truth']
     for name, fn in (('host loop ', lambda: p.minimize_bfgs_host(th0, hp, maxiter, 1e-7, own_stream=True)), ('graph loop', lambda: p.minimize_bfgs_graph_host(th0, hp, maxiter, 1e-7))):
@@ -27,7 +29,7 @@ p.close()
 # complete solves
 for backend in ('native', 'graph'):
     seqs = [synth.make_sequence('dsec', 1 + a.windows, seed=t) for t in range(a.threads)]
-    objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=3) for _ in range(a.threads)]
+    objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=3, flags=P.FLAG_BLOCKING_SYNC if a.blocking else 0) for _ in range(a.threads)]
     sols = [SV.MultipleLevelEINCMSolver(o, backend=backend, own_stream=True) for o in objs]
     for t in range(a.threads):
         sols[t].set_datasample(*seqs[t][0].args()); sols[t].solve()
@@ -42,5 +44,5 @@ for backend in ('native', 'graph'):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ne = sum(o.n_evals for o in objs) - n0
-    print(f'backend {backend:6s}: {a.threads} sequence(s) x {a.windows} windows: {a.threads * a.windows / dt:6.2f} windows/s, {ne / (a.threads * a.windows):5.0f} evaluations per window, {dt / ne * 1e6:6.1f} us of wall time per evaluation')
+    print(f'backend {backend:6s} {"blocking wait" if a.blocking else "spinning wait"}: {a.threads} sequence(s) x {a.windows} windows: {a.threads * a.windows / dt:6.2f} windows/s, {ne / (a.threads * a.windows):5.0f} evaluations per window, {dt / ne * 1e6:6.1f} us of wall time per evaluation')
     for o in objs: o.close()
