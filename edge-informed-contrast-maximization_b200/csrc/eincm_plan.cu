@@ -1208,9 +1208,26 @@ int build_level_graph(eincm_plan* plan, eincm_plan::LevelGraph& lg, int h, int w
 
 }  // namespace
 
+namespace {
+int minimize_bfgs_graph_impl(eincm_plan* plan, double* theta_inout_host, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
+                             eincm_opt_result* result_out, void* cuda_stream);
+}
+
 int eincm_minimize_bfgs_graph_host(eincm_plan* plan, double* theta_inout_host, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
                                    eincm_opt_result* result_out, void* cuda_stream) {
     if (!plan) return EINCM_EINVAL;
+    try {                                    // no C++ exception crosses the C boundary (the graph table allocates)
+        return minimize_bfgs_graph_impl(plan, theta_inout_host, h, w, hp, maxiter, gtol, result_out, cuda_stream);
+    } catch (const std::bad_alloc&) {
+        return fail(plan, EINCM_ENOMEM, "eincm_minimize_bfgs_graph_host: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(plan, EINCM_ECUDA, "eincm_minimize_bfgs_graph_host: %s", e.what());
+    }
+}
+
+namespace {
+int minimize_bfgs_graph_impl(eincm_plan* plan, double* theta_inout_host, int h, int w, const eincm_hparams* hp, int maxiter, double gtol,
+                             eincm_opt_result* result_out, void* cuda_stream) {
     if (!theta_inout_host || !result_out || !hp) return fail(plan, EINCM_EINVAL, "NULL operand");
     if (maxiter < 0) return fail(plan, EINCM_EINVAL, "maxiter must be >= 0");
     if (h < 1 || w < 1 || h > plan->H || w > plan->W) return fail(plan, EINCM_EINVAL, "theta shape (%d,%d) outside the sensor", h, w);
@@ -1295,6 +1312,7 @@ int eincm_minimize_bfgs_graph_host(eincm_plan* plan, double* theta_inout_host, i
     plan->host_evals += result_out->nfev;
     return EINCM_OK;
 }
+}  // namespace
 
 int eincm_value_and_grad_host_batch(eincm_plan* const* plans, int n_plans, const double* const* thetas_host, int h, int w,
                                     const eincm_hparams* hp, double* losses_out_host, double* const* grads_out_host) {
