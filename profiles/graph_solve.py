@@ -7,16 +7,17 @@ from eincm_b200 import losses, plan as P, solver as SV, synth
 ap = argparse.ArgumentParser()
 ap.add_argument('--threads', type=int, default=1)
 ap.add_argument('--windows', type=int, default=4)
+ap.add_argument('--workload', default='dsec')
 ap.add_argument('--blocking', action='store_true', help='EINCM_FLAG_BLOCKING_SYNC: the host waits asleep on an event')
 ap.add_argument('--skip-levels', action='store_true')
 a = ap.parse_args()
 torch.cuda.set_device(0)
-seq = synth.make_sequence('dsec', 1 + a.windows, seed=0)
+seq = synth.make_sequence(a.workload, 1 + a.windows, seed=0)
 H, W = seq[0].sensor_size
 hpd = seq[0].hparams
 N = len(seq[0].xs)
 # one level at a time
-p = P.Plan((H, W), max_events=N, max_refs=3)
+p = P.Plan((H, W), max_events=N, max_refs=max(3, len(seq[0].edge_ts)))
 p.set_window(*seq[0].args())
 for shape, lvl, maxiter in (() if a.skip_levels else (((1, 1), 4, 8), ((4, 4), 2, 19), ((16, 16), 0, 40))):
     hp = P.make_hparams(hpd['alpha'], hpd['beta'], 0.0, 0.0, lvl)
@@ -28,8 +29,8 @@ for shape, lvl, maxiter in (() if a.skip_levels else (((1, 1), 4, 8), ((4, 4), 2
 p.close()
 # complete solves
 for backend in ('native', 'graph'):
-    seqs = [synth.make_sequence('dsec', 1 + a.windows, seed=t) for t in range(a.threads)]
-    objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=3, flags=P.FLAG_BLOCKING_SYNC if a.blocking else 0) for _ in range(a.threads)]
+    seqs = [synth.make_sequence(a.workload, 1 + a.windows, seed=t) for t in range(a.threads)]
+    objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], hpd['gamma'], hpd['delta'], max_events=N, max_refs=max(3, len(seq[0].edge_ts)), flags=P.FLAG_BLOCKING_SYNC if a.blocking else 0) for _ in range(a.threads)]
     sols = [SV.MultipleLevelEINCMSolver(o, backend=backend, own_stream=True) for o in objs]
     for t in range(a.threads):
         sols[t].set_datasample(*seqs[t][0].args()); sols[t].solve()
