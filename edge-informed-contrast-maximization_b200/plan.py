@@ -378,7 +378,14 @@ class Plan:
         if isinstance(a, torch.Tensor):
             t = a
         else:
-            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+            arr = np.ascontiguousarray(np.asarray(a))
+            if not arr.flags.writeable:          # a read-only mapping (eincm_b200.shards): only read here, on its way to the device
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    t = torch.from_numpy(arr)
+            else:
+                t = torch.from_numpy(arr)
         return t.to(device=f'cuda:{self.device}', dtype=dtype).contiguous()
 
     # -- window -----------------------------------------------------------------------------------------------
