@@ -828,6 +828,13 @@ def run_own(args):
                                  ('dt4_dense_b64', 'mvsec_dt4', 64, True), ('dt1_dense_b64', 'mvsec_dt1', 64, True)):
             mvsec[name] = batched_measure(wl, Bn, 16, dn, steps=5, warmup=3, min_time_s=0.2, cpu=not args.no_cpu_baseline, cpu_budget=3.0)
 
+        # complete 5-level solves of 64 MVSEC-shaped sequences in LOCKSTEP: per pyramid level one batched device-side BFGS solve of all
+        # windows (eincm_batch_minimize_bfgs_graph_host), beside one device loop per sequence on 3 host threads
+        try:
+            mvsec['lockstep_solve'] = mvsec_lockstep_solve('mvsec_dt4', 64, 2, local_rank)
+        except Exception as e:                                 # a sub-line never takes the headline down
+            mvsec['lockstep_solve'] = {'error': f'{type(e).__name__}: {e}'}
+
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -932,6 +939,67 @@ def run_event_split(args):
                           'config': {'workload': f'{args.workload}: ONE window of {W}x{H}, N={N} events split over {world} GPU(s), R={R}, '
                                                  f'theta {shape[0]}x{shape[1]}x2'}, 'scaling': 'strong', **res}))
     dist.destroy_process_group()
+
+
+def mvsec_lockstep_solve(workload, n_seq, n_windows, device):
+    """windows/s of complete multi-level solves of n_seq MVSEC-shaped sequences solved in lockstep (solver.BatchedMultipleLevelEINCMSolver)
+    and, for comparison, of 3 of them with one device-side loop per sequence on its own host thread."""
+    import torch
+    from eincm_b200 import losses, solver as SV, synth
+    seqs = [synth.make_sequence(workload, 1 + n_windows, seed=1000 + t) for t in range(n_seq)]
+    w0 = seqs[0][0]
+    H, W = w0.sensor_size
+    hpd = w0.hparams
+    N, R = len(w0.xs), len(w0.edge_ts)
+
+    def make_objs(n):
+        return [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], 0.0, hpd['delta'], max_events=N, max_refs=max(R, 3)) for _ in range(n)]
+
+    objs = make_objs(n_seq)
+    lock = SV.BatchedMultipleLevelEINCMSolver(objs)
+    lock.set_datasamples([s[0].args() for s in seqs])
+    lock.solve()                                              # first windows untimed: no prior, graphs built
+    torch.cuda.synchronize()
+    n0, l0 = sum(o.n_evals for o in objs), lock.graph_launches
+    t0 = time.perf_counter()
+    for k in range(1, 1 + n_windows):
+        lock.set_datasamples([s[k].args() for s in seqs])
+        lock.solve()
+    dt = time.perf_counter() - t0
+    n_win = n_seq * n_windows
+    n_ev = sum(o.n_evals for o in objs) - n0
+    out = {'value': n_win / dt, 'unit': 'windows/s', 'workload': workload_string(workload, W, H, N, R, 16), 'sequences': n_seq,
+           'windows_per_sequence': n_windows, 'evals_per_window': n_ev / n_win, 'us_per_evaluation': dt / n_ev * 1e6,
+           'graph_launches_per_batch': (lock.graph_launches - l0) / n_windows,
+           'call': 'eincm_batch_minimize_bfgs_graph_host per pyramid level (solver.BatchedMultipleLevelEINCMSolver); the scalar handover '
+                   'solves per window and set_datasample (staging) are inside the timed region'}
+    lock.close()
+    for o in objs:
+        o.close()
+    T = 3
+    objs = make_objs(T)
+    sols = [SV.MultipleLevelEINCMSolver(o, backend='graph', own_stream=True) for o in objs]
+    for t, sol in enumerate(sols):
+        sol.set_datasample(*seqs[t][0].args())
+        sol.solve()
+
+    def work(t):
+        torch.cuda.set_device(device)
+        for k in range(1, 1 + n_windows):
+            sols[t].set_datasample(*seqs[t][k].args())
+            sols[t].solve()
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    out['one_device_loop_per_sequence'] = {'value': T * n_windows / (time.perf_counter() - t0), 'unit': 'windows/s', 'sequences': T}
+    for o in objs:
+        o.close()
+    return out
 
 
 def main():

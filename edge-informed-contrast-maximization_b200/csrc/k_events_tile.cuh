@@ -665,15 +665,18 @@ __device__ __forceinline__ void load_args(Args& dst, const Args* __restrict__ sr
 struct SplatArgs {
     const uint32_t* ev_xy; const double* ev_t; const Chunk* chunks; const float2* chunk_tr; const unsigned int* n_chunks_dev;
     ThetaSrc T; int H, W, R, pad; RefTimes tref; FixDst dst; int4* chunk_win;
+    const int* skip;                // non-zero: the window's CTAs return at once (batched solve graphs), or null
 };
 
 template <bool WRAP, int RB>
 __global__ void __launch_bounds__(256, 4)
-k_splat_tile_b(const SplatArgs* __restrict__ args) {
+k_splat_tile_b(const SplatArgs* __restrict__ args, const int* __restrict__ order) {
     extern __shared__ __align__(16) uint32_t win[];          // [RB][kWinCap]
     __shared__ SplatArgs sA;
-    load_args(sA, args + blockIdx.y);
-    splat_tile_body<WRAP, RB>(sA.ev_xy, sA.ev_t, sA.chunks, sA.chunk_tr, sA.n_chunks_dev, sA.T, sA.H, sA.W, sA.R, sA.tref, sA.dst, sA.chunk_win, win);
+    const int bw = batch_window(order);
+    if (bw < 0) return;
+    load_args(sA, args + bw);
+    splat_tile_body<WRAP, RB>(sA.ev_xy, sA.ev_t, sA.chunks, sA.chunk_tr, sA.n_chunks_dev, sA.T, sA.H, sA.W, sA.R, sA.tref, sA.dst, sA.chunk_win, win, sA.skip);
 }
 
 // fixed-point image -> float64 image (paths that need the plain image: zero-warp image, event split, delta != 0)
@@ -856,15 +859,18 @@ k_backward_tile(const uint32_t* __restrict__ ev_xy, const double* __restrict__ e
 struct BackwardTileArgs {
     const uint32_t* ev_xy; const double* ev_t; const Chunk* chunks; const unsigned int* n_chunks_dev;
     ThetaSrc T; int H, W, R, pad; RefTimes tref; const float* dldi32; const int4* chunk_win; double* G;
+    const int* skip;                // as in SplatArgs
 };
 
 template <bool WRAP, int RB>
 __global__ void __launch_bounds__(256, 4)
-k_backward_tile_b(const BackwardTileArgs* __restrict__ args) {
+k_backward_tile_b(const BackwardTileArgs* __restrict__ args, const int* __restrict__ order) {
     extern __shared__ __align__(16) float dwin[];            // [RB][kWinCap]
     __shared__ BackwardTileArgs sA;
-    load_args(sA, args + blockIdx.y);
-    backward_tile_body<WRAP, RB>(sA.ev_xy, sA.ev_t, sA.chunks, sA.n_chunks_dev, sA.T, sA.H, sA.W, sA.R, sA.tref, sA.dldi32, sA.chunk_win, sA.G, dwin);
+    const int bw = batch_window(order);
+    if (bw < 0) return;
+    load_args(sA, args + bw);
+    backward_tile_body<WRAP, RB>(sA.ev_xy, sA.ev_t, sA.chunks, sA.n_chunks_dev, sA.T, sA.H, sA.W, sA.R, sA.tref, sA.dldi32, sA.chunk_win, sA.G, dwin, sA.skip);
 }
 
 // ---- debug tap: Xs_rounded (event_utils.py:33) of reference r, written back in the original event order ----

@@ -323,9 +323,11 @@ k_image_stats(const ImageStatsArgs A) { image_stats_body(A); }
 
 // batched form: blockIdx.y = window, one argument record per window in device memory
 __global__ void __launch_bounds__(kS2NT, 5)
-k_image_stats_b(const ImageStatsArgs* __restrict__ args) {
+k_image_stats_b(const ImageStatsArgs* __restrict__ args, const int* __restrict__ order) {
     __shared__ ImageStatsArgs sA;
-    load_args(sA, args + blockIdx.y);
+    const int bw = batch_window(order);
+    if (bw < 0) return;
+    load_args(sA, args + bw);
     image_stats_body(sA);
 }
 
@@ -410,9 +412,11 @@ __global__ void __launch_bounds__(256)
 k_image_grad(const ImageGradArgs A) { image_grad_body(A); }
 
 __global__ void __launch_bounds__(256)
-k_image_grad_b(const ImageGradArgs* __restrict__ args) {
+k_image_grad_b(const ImageGradArgs* __restrict__ args, const int* __restrict__ order) {
     __shared__ ImageGradArgs sA;
-    load_args(sA, args + blockIdx.y);
+    const int bw = batch_window(order);
+    if (bw < 0) return;
+    load_args(sA, args + bw);
     image_grad_body(sA);
 }
 

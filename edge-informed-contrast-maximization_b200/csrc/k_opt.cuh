@@ -47,8 +47,9 @@ __device__ __forceinline__ double opt_block_all(double v, Op op, double* sh /* 3
     return out;
 }
 
-__global__ void __launch_bounds__(kOptNT)
-k_bfgs_step(BfgsDev* __restrict__ S, const BfgsBufs B, cudaGraphConditionalHandle handle, int use_handle) {
+// `left` (or null): number of windows of a batched solve that have not ended yet, decremented when this one does
+__device__ __forceinline__ void bfgs_step_body(BfgsDev* __restrict__ S, const BfgsBufs& B, cudaGraphConditionalHandle handle, int use_handle,
+                                               int* __restrict__ left) {
     // use_handle: the step is the tail of a WHILE conditional node and ends the loop through `handle`; otherwise it is one of the K steps of
     // an unrolled graph that the host relaunches until `done` (the steps and evaluations behind the last one return at once)
     if (S->done != 0) return;
@@ -168,7 +169,59 @@ k_bfgs_step(BfgsDev* __restrict__ S, const BfgsBufs B, cudaGraphConditionalHandl
         B.result[0] = 1.0;
         S->done = 1;
         if (use_handle) cudaGraphSetConditional(handle, 0u);
+        if (left != nullptr) atomicSub(left, 1);
     }
+}
+
+__global__ void __launch_bounds__(kOptNT)
+k_bfgs_step(BfgsDev* __restrict__ S, const BfgsBufs B, cudaGraphConditionalHandle handle, int use_handle) {
+    bfgs_step_body(S, B, handle, use_handle, nullptr);
+}
+
+// ---- batched form: B windows solved in lockstep (blockIdx.x = window), one state and one buffer record per window ---------------------
+// The evaluation kernels of the batch (eincm_batch.inl) read S[b].done as window b's skip flag, so a window whose level has ended costs
+// nothing in the remaining steps; `left` counts the windows still running (the host relaunches the unrolled graph until it reads 0).
+// active (or null = all): windows that take part in this solve; the others start out done (*left was preset to the number of active windows)
+__global__ void k_bfgs_init_b(BfgsDev* S, int n_windows, int n, int maxiter, double gtol, const int* __restrict__ active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_windows) return;
+    BfgsDev* s = S + b;
+    s->n = n; s->maxiter = maxiter; s->gtol = gtol; s->phase = 0; s->nit = 0; s->nfev = 0; s->status = 0;
+    s->done = (active == nullptr || active[b] != 0) ? 0 : 1;
+    s->f = 0.0; s->old_f = 0.0; s->gnorm = 0.0;
+}
+
+// order[0] = number of windows whose level has not ended, order[1 ..] = their indices (ascending): the batched evaluation kernels of the
+// steps that follow launch CTAs for these windows only (batch_window, k_theta.cuh).  One CTA, first node of every launch of a batched solve graph.
+__global__ void __launch_bounds__(1024)
+k_bfgs_compact(const BfgsDev* __restrict__ S, int n_windows, int* __restrict__ order) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_windows; b0 += 1024) {
+        const int b = b0 + (int)threadIdx.x;
+        const bool on = b < n_windows && S[b].done == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        int before = 0;
+        for (int q = 0; q < wid; ++q) before += warp_tot[q];
+        if (on) order[1 + base + before + __popc(m & ((1u << lane) - 1u))] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 32; ++q) t += warp_tot[q]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) order[0] = base;
+}
+
+__global__ void __launch_bounds__(kOptNT)
+k_bfgs_step_b(BfgsDev* __restrict__ S, const BfgsBufs* __restrict__ Bs, int* __restrict__ left) {
+    __shared__ BfgsBufs sB;
+    if (threadIdx.x == 0) sB = Bs[blockIdx.x];
+    __syncthreads();
+    bfgs_step_body(S + blockIdx.x, sB, (cudaGraphConditionalHandle)0, 0, left);
 }
 
 }  // namespace eincm

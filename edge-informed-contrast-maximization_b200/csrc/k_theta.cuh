@@ -193,19 +193,33 @@ k_theta_grad(const double2* __restrict__ G, const double2* __restrict__ Gtv, Dev
 struct ThetaGradArgs {
     const double2* G; DevScalars* sc; int h, w, H, W, SY, SX, n_items, host_grad; AxisTaps ty, tx;
     const double* prev; const double* theta; double* grad; const double* loss_dev; double* host_out;
+    const int* skip;                // non-zero: the window's CTAs return at once (batched solve graphs), or null
 };
 
+// Window of a CTA of the batched kernels: blockIdx.y, or - when a batched solve graph hands over the list of windows whose level has not
+// ended (order[0] = their number, order[1 ..] = their indices: k_bfgs_compact) - the blockIdx.y-th of those; -1: no window, return at once.
+__device__ __forceinline__ int batch_window(const int* __restrict__ order) {
+    int win = (int)blockIdx.y;
+    if (order != nullptr) {
+        if (win >= order[0]) return -1;
+        win = order[1 + win];
+    }
+    return win;
+}
+
 __global__ void __launch_bounds__(kTgWarps * 32)
-k_theta_grad_b(const ThetaGradArgs* __restrict__ args) {
+k_theta_grad_b(const ThetaGradArgs* __restrict__ args, const int* __restrict__ order) {
     __shared__ ThetaGradArgs sA;
+    const int win = batch_window(order);
+    if (win < 0) return;
     {   // (load_args of k_events_tile.cuh: this header comes first)
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(args + blockIdx.y);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(args + win);
         uint32_t* d = reinterpret_cast<uint32_t*>(&sA);
         for (int i = threadIdx.x; i < (int)(sizeof(ThetaGradArgs) / 4); i += blockDim.x) d[i] = __ldg(s + i);
         __syncthreads();
     }
     theta_grad_body<false>(sA.G, nullptr, sA.sc, 0.0, sA.h, sA.w, sA.H, sA.W, sA.SY, sA.SX, sA.n_items, sA.ty, sA.tx, sA.prev, sA.theta, sA.grad,
-                           sA.loss_dev, sA.host_out, sA.host_grad);
+                           sA.loss_dev, sA.host_out, sA.host_grad, sA.skip);
 }
 
 // ---- backward of the resize, scatter form (large / dense theta) -----------------------------------------

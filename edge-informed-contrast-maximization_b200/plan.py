@@ -41,7 +41,8 @@ EXPORTED_SYMBOLS = (
     'eincm_nlm_workspace_bytes', 'eincm_nlm_denoise',
     'eincm_rectify_workspace_bytes', 'eincm_rectify_events', 'eincm_normalize_times', 'eincm_window_event_range',
     'eincm_batch_create', 'eincm_batch_destroy', 'eincm_batch_last_error', 'eincm_batch_value_and_grad', 'eincm_batch_value_and_grad_host',
-    'eincm_batch_launch_count', 'eincm_batch_set_timing', 'eincm_batch_get_timing',
+    'eincm_batch_launch_count', 'eincm_batch_set_timing', 'eincm_batch_get_timing', 'eincm_batch_minimize_bfgs_graph_host',
+    'eincm_batch_solve_launches',
 )
 
 
@@ -182,6 +183,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_batch_launch_count': (i64, [vp]),
         'eincm_batch_set_timing': (i32, [vp, i32]),
         'eincm_batch_get_timing': (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
+        'eincm_batch_minimize_bfgs_graph_host': (i32, [vp, vp, i32, i32, hp, i32, dbl, vp, vp, vp]),
+        'eincm_batch_solve_launches': (i64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -311,6 +314,27 @@ class Batch:
 
     def launch_count(self) -> int:
         return int(self.lib.eincm_batch_launch_count(self._h))
+
+    def minimize_bfgs_graph_host(self, thetas0, hp: HParams, maxiter: int, gtol: float, active=None, stream=None):
+        """One BFGS level solve for every window of the batch, in lockstep, with the loop on the device (``eincm_batch_minimize_bfgs_graph_host``):
+        ``thetas0`` is ``(B, h, w, 2)``; returns ``(thetas (B, h, w, 2), [OptResult] * B)``.  ``active``: optional ``B`` flags, windows with a
+        zero flag take no part (theta returned unchanged, result zero).  ``stream`` None: the first plan's own stream."""
+        n = len(self.plans)
+        thetas = np.array(thetas0, dtype=np.float64, order='C', copy=True)
+        if thetas.ndim != 4 or thetas.shape[0] != n or thetas.shape[3] != 2:
+            raise EincmError(EINCM_EINVAL, f'thetas must have shape ({n}, h, w, 2), got {thetas.shape}')
+        res = (OptResult * n)()
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.int32)
+        if act is not None and act.shape != (n,):
+            raise EincmError(EINCM_EINVAL, f'active must have {n} entries')
+        st = OWN_STREAM if stream is None else _stream_ptr(stream)
+        self._check(self.lib.eincm_batch_minimize_bfgs_graph_host(self._h, thetas.ctypes.data, thetas.shape[1], thetas.shape[2], C.byref(hp),
+                                                                  int(maxiter), float(gtol), None if act is None else act.ctypes.data,
+                                                                  C.cast(res, C.c_void_p), st))
+        return thetas, list(res)
+
+    def solve_launches(self) -> int:
+        return int(self.lib.eincm_batch_solve_launches(self._h))
 
     KERNELS = ('k_splat', 'k_image_stats', 'k_image_grad', 'k_backward_events', 'k_theta_grad')
 

@@ -322,3 +322,78 @@ def solve_sequence(objective, windows, solver_kwargs: Optional[dict] = None, n_r
             res = solver.solve()
         out.append(res)
     return out
+
+
+class BatchedMultipleLevelEINCMSolver:
+    """B independent windows (different sequences, or windows solved without handover between them) taken through the level schedule
+    of ``MultipleLevelEINCMSolver.solve`` (reference src/eincm/solver.py:197-267) in LOCKSTEP: per pyramid level ONE call solves the level
+    for every window on the device (``eincm_batch_minimize_bfgs_graph_host``: batched evaluation kernels + one optimizer CTA per window inside
+    a CUDA graph).  Each window keeps its own ``MultipleLevelEINCMSolver`` state (pyramids, priors, handover weights), so
+    consecutive batches chain through the handover prior exactly like consecutive windows of a sequence; retries (solver.py:218-226) re-solve
+    the subset of windows that asked for one; the scalar handover solves stay per window."""
+
+    def __init__(self, objectives, **solver_kwargs):
+        from . import plan as _plan
+        solver_kwargs = dict(solver_kwargs, backend='graph')
+        self.solvers = [MultipleLevelEINCMSolver(o, **solver_kwargs) for o in objectives]
+        self.objectives = list(objectives)
+        self.batch = _plan.Batch([o.plan for o in objectives])
+        self.n_pyr_lvls = self.solvers[0].n_pyr_lvls
+        self.graph_launches = 0
+
+    def close(self):
+        self.batch.close()
+
+    def set_datasamples(self, windows):
+        """``windows[k]``: the ``(xs, ys, ts, edges, edge_ts)`` operands of window k."""
+        for s, w in zip(self.solvers, windows):
+            s.set_datasample(*w)
+
+    def _run_theta_solvers(self, pyr_lvl: int, thetas0, active=None):
+        s0 = self.solvers[0]
+        key = f'pyr_lvl_{pyr_lvl}'
+        thetas, res = self.batch.minimize_bfgs_graph_host(np.stack(thetas0), self.objectives[0].hparams(pyr_lvl), s0.theta_opt_maxiters[key],
+                                                          s0.theta_opt_solver_params['options']['gtol'], active=active)
+        self.graph_launches += self.batch.solve_launches()
+        states = [OptState(float(r.fun), r.status == 0, int(r.status), int(r.nit), int(r.nfev)) for r in res]
+        for k, (o, r) in enumerate(zip(self.objectives, res)):
+            if active is None or active[k]:
+                o.n_evals += int(r.nfev)
+        return thetas, states
+
+    def solve(self):
+        sv = self.solvers
+        for s in sv:
+            s._pre_solve()
+        extra = sv[0].theta_opt_solver_params.get('n_extra_attempts', {})
+        for pyr_lvl in reversed(range(self.n_pyr_lvls)):
+            key, next_key = f'pyr_lvl_{pyr_lvl}', f'pyr_lvl_{pyr_lvl - 1}'
+            for s in sv:
+                s._update_callback_pyr_lvl(pyr_lvl)
+            thetas, states = self._run_theta_solvers(pyr_lvl, [s.pre_opt_theta_pyr[key] for s in sv])
+            for k, s in enumerate(sv):
+                s.opt_theta_pyr[key], s.theta_opt_state_pyr[key] = thetas[k], states[k]
+            n_extra_attempts = 0
+            while key in extra and n_extra_attempts < extra[key]:
+                again = np.array([(not s.theta_opt_state_pyr[key].success) and s.theta_opt_state_pyr[key].iter_num > 0 for s in sv], dtype=np.int32)
+                if not again.any():
+                    break
+                n_extra_attempts += 1
+                thetas, states = self._run_theta_solvers(pyr_lvl, [s.opt_theta_pyr[key] for s in sv], active=again)
+                for k, s in enumerate(sv):
+                    if again[k]:
+                        s.opt_theta_pyr[key], s.theta_opt_state_pyr[key] = thetas[k], states[k]
+            for s in sv:
+                s.handover_opt_theta_pyr[key] = s._perform_handover_at_level(pyr_lvl)
+                if pyr_lvl != 0:
+                    s.pre_opt_theta_pyr[next_key] = s._upscale_theta(s.handover_opt_theta_pyr[key], base=s.pyramid_bases[-pyr_lvl])
+        out = []
+        for s in sv:
+            old_prior = dict(s.prior_theta_pyr)
+            s.prior_theta_pyr = dict(s.handover_opt_theta_pyr)
+            s._IS_FIRST_SAMPLE = False
+            out.append({'prior_theta_pyr': old_prior, 'pre_opt_theta_pyr': dict(s.pre_opt_theta_pyr),
+                        'theta_opt_state_pyr': dict(s.theta_opt_state_pyr), 'pre_handover_theta_pyr': dict(s.opt_theta_pyr),
+                        'ho_opt_state_pyr': dict(s.ho_opt_state_pyr), 'final_handover_weight_pyr': dict(s.final_handover_weight_pyr),
+                        'final_theta_pyr': dict(s.handover_opt_theta_pyr)})
+        return out

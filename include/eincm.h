@@ -193,6 +193,18 @@ int eincm_minimize_handover_host(eincm_plan* plan, double* alpha_inout_host, dou
  * staged window (it bakes the window's reference times and chunk count) and re-used for repeated solves of that window. */
 int eincm_minimize_bfgs_graph_host(eincm_plan* plan, double* theta_inout_host /* [h][w][2] */, int h, int w, const eincm_hparams* hp,
                                    int maxiter, double gtol, eincm_opt_result* result_out, void* cuda_stream);
+/* The BATCHED form of the device-side loop ("batched BFGS driver for many windows"; reference src/eincm/solver.py:165-173,
+ * 209-216 runs one scipy BFGS per window): all windows of an eincm_batch solve one pyramid level in lockstep - an unrolled graph of
+ * 8 x { the five batched evaluation kernels (blockIdx.y = window) ; k_bfgs_step_b (one CTA per window) } relaunched until no window is left.
+ * Every window follows the schedule eincm_minimize_bfgs_graph_host would run for it alone; a window whose level has ended is skipped by
+ * the remaining kernels (they read its `done` word), so the GPU time of a step is proportional to the windows still running.  The graph
+ * depends on (theta shape, R, grid size) only - the windows' operands live in the batch's argument records - and is re-used across
+ * batches of windows.  thetas_inout_host: [n_plans][h][w][2] contiguous; results_out: [n_plans]; active: NULL, or [n_plans] flags -
+ * windows with a zero flag take no part (their theta and result are left untouched: the retries of solver.py:218-226 re-solve a subset).
+ * Same limits as the single-window loop and as eincm_batch_value_and_grad (gamma == 0 or cur_pyr_lvl > 0, delta == 0).  Synchronous. */
+int eincm_batch_minimize_bfgs_graph_host(eincm_batch* batch, double* thetas_inout_host, int h, int w, const eincm_hparams* hp, int maxiter,
+                                         double gtol, const int32_t* active, eincm_opt_result* results_out, void* cuda_stream);
+int64_t eincm_batch_solve_launches(const eincm_batch* batch);   /* graph launches of the last batched solve */
 /* Stateless single shot with the exact operand list of loss_func (losses.py:108-114), every operand on the host:
  * set_window + value_and_grad + copies. */
 int eincm_value_and_grad_stateless_host(eincm_plan* plan, const double* theta_host, int h, int w,
