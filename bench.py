@@ -396,6 +396,16 @@ def time_edge_maps(H, W, R, cpu=True, reps=20):
     b2.record()
     torch.cuda.synchronize()
     nlm = {'ms_per_window_device': a2.elapsed_time(b2) / reps, 'params': 'h 4, template 3, search 11 (denoise/default.yaml)'}
+    # CLAHE + Gaussian sharpen of preprocess_image (img_utils.py:159-178) chained on the denoised frames
+    for _ in range(2):
+        shp = img_utils.sharpen(img_utils.clahe_apply(den, 5, (10, 10)), 3, 1.5, -0.5)
+    a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a3.record()
+    for _ in range(reps):
+        shp = img_utils.sharpen(img_utils.clahe_apply(den, 5, (10, 10)), 3, 1.5, -0.5)
+    b3.record()
+    torch.cuda.synchronize()
+    cs = {'ms_per_window_device': a3.elapsed_time(b3) / reps, 'params': 'CLAHE clip 5, 10 x 10 tiles; GaussianBlur sigma 3 (19 taps), addWeighted 1.5 / -0.5'}
     res = {'ms_per_window_e2e': gpu_ms, 'ms_per_window_device': a.elapsed_time(b) / reps, 'frames': f'{R} x {W}x{H} uint8',
            'h2d_bytes': int(frames.nbytes), 'stages': 'Canny (3x3 Sobel, L2, 30/80) + Gaussian sigma 1 (9 taps) + normalise',
            'edge_pixels': int((out > 0.5).sum().item())}
@@ -433,9 +443,24 @@ def time_edge_maps(H, W, R, cpu=True, reps=20):
             nlm['cpu_ms_per_window'] = (time.perf_counter() - t0) * 1e3
             nlm['cpu_kind'] = f'reference (OpenCV {cv.__version__}, {cv.getNumThreads()} threads)'
             nlm['identical_to_cpu'] = bool(np.array_equal(den.cpu().numpy(), ref_den))
+
+            def ref_cs():
+                out_ = []
+                for f in ref_den:
+                    c_ = cv.createCLAHE(clipLimit=5, tileGridSize=(10, 10)).apply(f)
+                    out_.append(cv.addWeighted(c_, 1.5, cv.GaussianBlur(c_, None, 3, 2, 0), -0.5, 0))
+                return np.stack(out_)
+            ref_cs()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ref_shp = ref_cs()
+            cs['cpu_ms_per_window'] = (time.perf_counter() - t0) / 5 * 1e3
+            cs['cpu_kind'] = nlm['cpu_kind']
+            cs['identical_to_cpu'] = bool(np.array_equal(shp.cpu().numpy(), ref_shp))
         except ImportError:
             pass
     res['nlm_denoise'] = nlm
+    res['clahe_sharpen'] = cs
     return res
 
 

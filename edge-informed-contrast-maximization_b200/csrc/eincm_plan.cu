@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "k_edges.cuh"
+#include "k_preproc.cuh"
 #include "k_ingest.cuh"
 #include "k_prep.cuh"
 #include "k_theta.cuh"
@@ -1720,6 +1721,7 @@ int eincm_debug_rounded_pixels(eincm_plan* plan, int ref, int32_t* cols_out, int
 }
 
 #include "eincm_edges.inl"
+#include "eincm_preproc.inl"
 #include "eincm_batch.inl"
 #include "eincm_ingest.inl"
 

@@ -114,21 +114,81 @@ def fast_nl_means_denoising(images, h=4, template_win_size=3, search_win_size=11
     return out[0] if single else out
 
 
+def _device_frames(images, device=None):
+    """uint8 frames ``(H, W)`` or ``(R, H, W)`` on the host or the device -> (contiguous CUDA tensor ``(n, H, W)``, was a single frame)."""
+    import torch
+    if isinstance(images, torch.Tensor) and images.is_cuda:
+        if images.dtype != torch.uint8:
+            raise _plan.EincmError(_plan.EINCM_EINVAL, 'frames must be uint8')
+        single = images.dim() == 2
+        return (images.contiguous()[None] if single else images.contiguous()), single
+    single = np.asarray(images).ndim == 2
+    dev = f'cuda:{torch.cuda.current_device() if device is None else device}'
+    return torch.from_numpy(_u8_frames(images)).to(dev), single
+
+
+def clahe_apply(images, clip_limit=5, tile_grid_size=(10, 10), device=None, stream=None):
+    """``cv.createCLAHE(clipLimit=clip_limit, tileGridSize=tile_grid_size).apply(img)`` (src/utils/img_utils.py:159-161) for uint8 frames
+    ``(H, W)`` or ``(R, H, W)``, bit-exact with OpenCV: uint8 CUDA tensor of the same shape.  Asynchronous on the current stream."""
+    import torch
+    d_img, single = _device_frames(images, device)
+    n, H, W = (int(v) for v in d_img.shape)
+    tx, ty = int(tile_grid_size[0]), int(tile_grid_size[1])
+    lib = _plan.load_library()
+    wsb = int(lib.eincm_clahe_workspace_bytes(n, tx, ty))
+    if wsb == 0:
+        raise _plan.EincmError(_plan.EINCM_EINVAL, 'the tile grid must be at least 1 x 1')
+    ws = torch.empty(wsb, dtype=torch.uint8, device=d_img.device)
+    out = torch.empty_like(d_img)
+    with torch.cuda.device(d_img.device):
+        s = stream if stream is not None else torch.cuda.current_stream()
+        rc = lib.eincm_clahe(d_img.device.index, d_img.data_ptr(), n, H, W, float(clip_limit), tx, ty, out.data_ptr(), ws.data_ptr(), wsb,
+                             int(s.cuda_stream))
+        ws.record_stream(s)
+        d_img.record_stream(s)
+    if rc != 0:
+        raise _plan.EincmError(rc, 'eincm_clahe failed')
+    return out[0] if single else out
+
+
+def sharpen(images, sigma=3, alpha=1.5, beta=-0.5, gamma=0.0, return_blur=False, device=None, stream=None):
+    """The sharpening step of ``preprocess_image`` (src/utils/img_utils.py:163-178): ``blur = cv.GaussianBlur(img, None, sigma, ...)`` on
+    the uint8 frame, then ``cv.addWeighted(img, alpha, blur, beta, gamma)``; bit-exact with OpenCV.  uint8 CUDA tensor(s)."""
+    import torch
+    d_img, single = _device_frames(images, device)
+    n, H, W = (int(v) for v in d_img.shape)
+    lib = _plan.load_library()
+    out = torch.empty_like(d_img)
+    blur = torch.empty_like(d_img) if return_blur else None
+    with torch.cuda.device(d_img.device):
+        s = stream if stream is not None else torch.cuda.current_stream()
+        rc = lib.eincm_sharpen(d_img.device.index, d_img.data_ptr(), n, H, W, float(sigma), float(alpha), float(beta), float(gamma),
+                               blur.data_ptr() if return_blur else None, out.data_ptr(), int(s.cuda_stream))
+        d_img.record_stream(s)
+    if rc != 0:
+        raise _plan.EincmError(rc, 'eincm_sharpen failed (Gaussian kernels of up to 63 taps: sigma <= 10)')
+    if return_blur:
+        return (out[0], blur[0]) if single else (out, blur)
+    return out[0] if single else out
+
+
 def preprocess_image(img, denoise_h=4, denoise_template_win_size=3, denoise_search_win_size=11, clahe_clip_limit=5,
                      clahe_tile_grid_size=(10, 10), sharpen_kernel_size=3, sharpen_sigma_x=2, sharpen_alpha=1.5, sharpen_beta=-0.5,
                      bilateral_filter_neigh_diameter=5, bilateral_filter_sigma_color=15, bilateral_filter_sigma_space=15) -> np.ndarray:
-    """src/utils/img_utils.py:131-191 with the non-local-means denoise (99 % of its run time: ~110 ms of ~112 ms per 640x480 frame
-    with OpenCV on 8 host threads) on the device; CLAHE, the Gaussian sharpen and the bilateral filter stay OpenCV calls, made exactly
-    as the reference makes them (they need ``cv2``, like the reference does).  uint8 in (or a [0, 1] float image like the
-    reference accepts), uint8 out, identical to the reference's result."""
+    """src/utils/img_utils.py:131-191 with the non-local-means denoise (99 % of its run time with OpenCV: ~110 ms of ~112 ms per
+    640x480 frame on 8 host threads), CLAHE and the Gaussian sharpen on the device, chained there (one copy in, one out); the bilateral
+    filter stays an OpenCV call, made exactly as the reference makes it (it needs ``cv2``, like the reference does: in the opencv-python
+    build its output is a property of the build, see include/eincm.h).  uint8 in (or a [0, 1] float image like the reference accepts),
+    uint8 out, identical to the reference's result.  ``sharpen_sigma_x`` is accepted and unused, as in the reference's call: OpenCV reads
+    ``cv.GaussianBlur(img, None, kernel_size, sigma_x, sigma_y)`` as sigmaX = kernel_size, dst = sigma_x."""
     import cv2 as cv
+    del sharpen_sigma_x
     a = np.asarray(img)
     if a.dtype != np.uint8:
         a = jnp_to_ocv_n255(a)
-    d_img = fast_nl_means_denoising(a, denoise_h, denoise_template_win_size, denoise_search_win_size).cpu().numpy()
-    clahe_img = cv.createCLAHE(clipLimit=clahe_clip_limit, tileGridSize=tuple(clahe_tile_grid_size)).apply(d_img)
-    blur = cv.GaussianBlur(clahe_img, None, sharpen_kernel_size, sharpen_sigma_x, 0)                  # positional like img_utils.py:165-169
-    sharp = cv.addWeighted(clahe_img, sharpen_alpha, blur, sharpen_beta, 0)
+    d_img = fast_nl_means_denoising(a, denoise_h, denoise_template_win_size, denoise_search_win_size)
+    clahe_img = clahe_apply(d_img, clahe_clip_limit, clahe_tile_grid_size)
+    sharp = sharpen(clahe_img, sharpen_kernel_size, sharpen_alpha, sharpen_beta).cpu().numpy()
     return cv.bilateralFilter(sharp, bilateral_filter_neigh_diameter, bilateral_filter_sigma_color, bilateral_filter_sigma_space)
 
 

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = (
     'eincm_split_window_images', 'eincm_minimize_bfgs_host', 'eincm_minimize_bfgs_graph_host', 'eincm_minimize_handover_host', 'eincm_sparse_flow_error',
     'eincm_evaluate_theta', 'eincm_group_create', 'eincm_group_destroy', 'eincm_plan_set_group', 'eincm_group_set_burst_percent', 'eincm_plan_host_times',
     'eincm_edge_workspace_bytes', 'eincm_edge_maps', 'eincm_edge_maps_host',
-    'eincm_nlm_workspace_bytes', 'eincm_nlm_denoise',
+    'eincm_nlm_workspace_bytes', 'eincm_nlm_denoise', 'eincm_clahe_workspace_bytes', 'eincm_clahe', 'eincm_sharpen',
     'eincm_rectify_workspace_bytes', 'eincm_rectify_events', 'eincm_normalize_times', 'eincm_window_event_range',
     'eincm_batch_create', 'eincm_batch_destroy', 'eincm_batch_last_error', 'eincm_batch_value_and_grad', 'eincm_batch_value_and_grad_host',
     'eincm_batch_launch_count', 'eincm_batch_set_timing', 'eincm_batch_get_timing', 'eincm_batch_minimize_bfgs_graph_host',
@@ -171,6 +171,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         'eincm_edge_maps_host': (i32, [i32, vp, i32, i32, i32, C.POINTER(EdgeParams), vp, vp]),
         'eincm_nlm_workspace_bytes': (C.c_size_t, [i32, i32]),
         'eincm_nlm_denoise': (i32, [i32, vp, i32, i32, i32, C.c_float, i32, i32, vp, vp, C.c_size_t, vp]),
+        'eincm_clahe_workspace_bytes': (C.c_size_t, [i32, i32, i32]),
+        'eincm_clahe': (i32, [i32, vp, i32, i32, i32, dbl, i32, i32, vp, vp, C.c_size_t, vp]),
+        'eincm_sharpen': (i32, [i32, vp, i32, i32, i32, dbl, dbl, dbl, dbl, vp, vp, vp]),
         'eincm_rectify_workspace_bytes': (C.c_size_t, [i64]),
         'eincm_rectify_events': (i32, [i32, vp, vp, vp, vp, i64, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i64), vp, C.c_size_t, vp]),
         'eincm_normalize_times': (i32, [i32, vp, i64, i64, i64, vp, vp]),

@@ -362,6 +362,21 @@ size_t eincm_nlm_workspace_bytes(int template_window_size, int search_window_siz
 int eincm_nlm_denoise(int device, const uint8_t* images, int n_images, int H, int W, float h, int template_window_size,
                       int search_window_size, uint8_t* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* ---- image pre-processing between the denoise and the bilateral filter (src/utils/img_utils.py:159-181) --------
+ * uint8 frames, DEVICE [n_images][H][W], bit-exact with OpenCV 4.x (restated and pinned against cv2 in oracle/edge_oracle.py).
+ * eincm_clahe: cv.createCLAHE(clipLimit, tileGridSize = (tiles_x, tiles_y)).apply (img_utils.py:159-161) - per-tile histogram, clip +
+ * redistribution, LUT, float32 bilinear blend of the four neighbouring LUTs; workspace: DEVICE, eincm_clahe_workspace_bytes (the LUTs).
+ * eincm_sharpen: cv.GaussianBlur of the uint8 frame (8-bit fixed-point kernel of size round(6 sigma + 1) | 1 <= 63, BORDER_REFLECT_101)
+ * followed by cv.addWeighted(frame, alpha, blur, beta, gamma) in float32 (img_utils.py:163-178; as OpenCV reads the reference's positional
+ * call, sigma is `sharpen_kernel_size`); blur_out: optional copy of the blurred frame; out must not alias images.
+ * The bilateral filter that follows (img_utils.py:183-189) stays an OpenCV call: in the opencv-python build its interior comes from Intel
+ * IPP and its border columns from OpenCV's own code, so its output is a property of the build.  Asynchronous on cuda_stream. */
+size_t eincm_clahe_workspace_bytes(int n_images, int tiles_x, int tiles_y);
+int eincm_clahe(int device, const uint8_t* images, int n_images, int H, int W, double clip_limit, int tiles_x, int tiles_y, uint8_t* out,
+                void* workspace, size_t workspace_bytes, void* cuda_stream);
+int eincm_sharpen(int device, const uint8_t* images, int n_images, int H, int W, double sigma, double alpha, double beta, double gamma,
+                  uint8_t* blur_out, uint8_t* out, void* cuda_stream);
+
 /* ---- event ingest before staging --------
  * What the reference's DSEC loader / experiment manager do in NumPy between the h5 event stream and loss_func's operands.
  * All pointers DEVICE unless suffixed _host. */

@@ -10,6 +10,9 @@ src/experiments/e00/exp_mgr.py:343-350):
     gauss  = normalize_to_unit_range(cv.GaussianBlur(canny.astype(float64), None, 1, 1, 0))
     iedt   = normalize_to_unit_range(eincm_inv_exp_dist_transform(canny, alpha))
     nlm    = cv.fastNlMeansDenoising(img, None, 4, 3, 11)              (first step of preprocess_image, img_utils.py:147-157)
+    clahe  = cv.createCLAHE(clipLimit=5, tileGridSize=(10, 10)).apply(nlm)                              (img_utils.py:159-161)
+    blur   = cv.GaussianBlur(clahe, None, 3, 2, 0)                      (img_utils.py:165-169, positional like the reference)
+    sharp  = cv.addWeighted(clahe, 1.5, blur, -0.5, 0)                                                  (img_utils.py:171-178)
 
 They pin the NumPy restatement (oracle/edge_oracle.py, tests/test_edge_oracle.py) and the CUDA path (tests/test_gpu_edges.py).
 """
@@ -58,7 +61,11 @@ def main():
         gauss = np.stack([normalize_to_unit_range(cv.GaussianBlur(c.astype(np.float64), None, 1, 1, 0)) for c in canny])
         iedt = np.stack([normalize_to_unit_range(ref_iedt(c, ALPHA)) for c in canny])
         nlm = np.stack([cv.fastNlMeansDenoising(f, None, 4, 3, 11) for f in frames])     # denoise/default.yaml: h 4, template 3, search 11
+        clahe = np.stack([cv.createCLAHE(clipLimit=5, tileGridSize=(10, 10)).apply(f) for f in nlm])
+        blur = np.stack([cv.GaussianBlur(f, None, 3, 2, 0) for f in clahe])
+        sharp = np.stack([cv.addWeighted(a, 1.5, b, -0.5, 0) for a, b in zip(clahe, blur)])
         np.savez_compressed(os.path.join(out_dir, name + '.npz'), frames=frames, canny=canny, gauss=gauss, iedt=iedt, nlm=nlm,
+                            clahe=clahe, blur=blur, sharp=sharp,
                             th=np.array([th1, th2], np.float64), alpha=np.float64(ALPHA), cv_version=np.array(cv.__version__))
         print(name, frames.shape, 'edge pixels', int((canny > 0).sum()))
 

@@ -30,6 +30,17 @@ def test_oracle_matches_opencv_fixtures(path):
 
 
 @pytest.mark.parametrize('path', GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_clahe_sharpen_oracle_matches_opencv_fixtures(path):
+    """CLAHE / uint8 Gaussian blur / addWeighted as preprocess_image calls them (img_utils.py:159-178), against the committed OpenCV outputs
+    (frame sizes that do and do not divide by the 10 x 10 tile grid): bit-exact, no cv2 needed."""
+    z = np.load(path)
+    for f, clahe, blur, sharp in zip(z['nlm'], z['clahe'], z['blur'], z['sharp']):
+        assert np.array_equal(E.clahe_apply(f, 5, (10, 10)), clahe)
+        assert np.array_equal(E.gaussian_blur_u8(clahe, 3.0), blur)
+        assert np.array_equal(E.add_weighted_u8(clahe, 1.5, blur, -0.5), sharp)
+
+
+@pytest.mark.parametrize('path', GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_nlm_oracle_matches_opencv_fixtures(path):
     z = np.load(path)
     for f, ref in zip(z['frames'], z['nlm']):
@@ -99,7 +110,7 @@ def test_nlm_oracle_matches_live_opencv(shape, h, t, sw):
 @pytest.mark.parametrize('H,W,seed', [(480, 640, 0), (96, 128, 1), (61, 83, 2), (100, 100, 3)])
 def test_clahe_sharpen_restatements_match_live_opencv(H, W, seed):
     """The steps of preprocess_image between the denoise and the bilateral filter (img_utils.py:159-181), called as the reference calls
-    them.  Restated for the next build step (no CUDA counterpart yet): bit-exact."""
+    them (CUDA counterparts: eincm_clahe / eincm_sharpen, tests/test_gpu_edges.py): bit-exact."""
     f = S.make_frames(H, W, 1, seed=seed, noise_sigma=4.0)[0]
     clahe = cv.createCLAHE(clipLimit=5, tileGridSize=(10, 10)).apply(f)
     assert np.array_equal(E.clahe_apply(f, 5, (10, 10)), clahe)

