@@ -332,9 +332,13 @@ class BatchedMultipleLevelEINCMSolver:
     consecutive batches chain through the handover prior exactly like consecutive windows of a sequence; retries (solver.py:218-226) re-solve
     the subset of windows that asked for one; the scalar handover solves stay per window."""
 
-    def __init__(self, objectives, **solver_kwargs):
+    def __init__(self, objectives, handover_threads: int = 4, **solver_kwargs):
+        """``handover_threads``: host threads that run the per-window scalar handover solves of a level side by side (each on its plan's own
+        stream; the native call releases the GIL) - they are independent, and one at a time they are bound by the latency of a small evaluation."""
         from . import plan as _plan
-        solver_kwargs = dict(solver_kwargs, backend='graph')
+        solver_kwargs = dict(solver_kwargs, backend='graph', own_stream=True)
+        self.handover_threads = max(1, int(handover_threads))
+        self._pool = None
         self.solvers = [MultipleLevelEINCMSolver(o, **solver_kwargs) for o in objectives]
         self.objectives = list(objectives)
         self.batch = _plan.Batch([o.plan for o in objectives])
@@ -342,7 +346,29 @@ class BatchedMultipleLevelEINCMSolver:
         self.graph_launches = 0
 
     def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         self.batch.close()
+
+    def _handover_all(self, pyr_lvl: int):
+        """``_perform_handover_at_level`` of every window; the scalar solves (first window / unsolved levels: a blend, no solve) in parallel."""
+        sv = self.solvers
+        key = f'pyr_lvl_{pyr_lvl}'
+        solved = (not sv[0]._IS_FIRST_SAMPLE) and sv[0].use_handover and sv[0].solve_handover_switch_per_level[key]
+        if not solved or self.handover_threads == 1 or len(sv) == 1:
+            return [s._perform_handover_at_level(pyr_lvl) for s in sv]
+        if self._pool is None:
+            import concurrent.futures
+            self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=self.handover_threads)
+        dev = self.objectives[0].plan.device
+
+        def one(s):
+            import torch
+            torch.cuda.set_device(dev)
+            return s._perform_handover_at_level(pyr_lvl)
+
+        return list(self._pool.map(one, sv))
 
     def set_datasamples(self, windows):
         """``windows[k]``: the ``(xs, ys, ts, edges, edge_ts)`` operands of window k."""
@@ -383,8 +409,8 @@ class BatchedMultipleLevelEINCMSolver:
                 for k, s in enumerate(sv):
                     if again[k]:
                         s.opt_theta_pyr[key], s.theta_opt_state_pyr[key] = thetas[k], states[k]
-            for s in sv:
-                s.handover_opt_theta_pyr[key] = s._perform_handover_at_level(pyr_lvl)
+            for s, th_ho in zip(sv, self._handover_all(pyr_lvl)):
+                s.handover_opt_theta_pyr[key] = th_ho
                 if pyr_lvl != 0:
                     s.pre_opt_theta_pyr[next_key] = s._upscale_theta(s.handover_opt_theta_pyr[key], base=s.pyramid_bases[-pyr_lvl])
         out = []
