@@ -296,7 +296,7 @@ int batch_launch(eincm_batch* batch, const BatchShape& sh, cudaStream_t st) {
     const ImageGradArgs* d_ga = (const ImageGradArgs*)(batch->d_blob + batch->off_igrad);
     const BackwardTileArgs* d_ba = (const BackwardTileArgs*)(batch->d_blob + batch->off_bwd);
     const ThetaGradArgs* d_ta = (const ThetaGradArgs*)(batch->d_blob + batch->off_tgrad);
-    const int rb = std::min(R, kMaxRB);
+    const int rb = refs_per_pass(R);
     const dim3 grid_ev(sh.max_chunks, B);
     cudaError_t le = cudaSuccess;
 #define LB(WR, RBV) { BatchSpan sp_(batch, 0, st); le = launch_pdl(k_splat_tile_b<WR, RBV>, grid_ev, dim3(256), (size_t)RBV * kWinCap * sizeof(uint32_t), st, d_sa, batch->cur_order); }

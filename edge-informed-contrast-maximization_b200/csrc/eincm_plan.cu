@@ -347,7 +347,7 @@ int splat_images(eincm_plan* plan, const ThetaSrc& T, const double2* theta_full,
         else { dst.n = 1; dst.p[0] = plan->iwe_fix; }
 #define SPLATT(WR, RB) LAUNCH(tag, launch_pdl(k_splat_tile<WR, RB>, dim3(grid), dim3(256), RB * kWinCap * sizeof(uint32_t), st, (const uint32_t*)plan->ev_xy, \
                                (const double*)plan->ev_t, (const Chunk*)plan->chunks, (const float2*)plan->chunk_tr, (const unsigned int*)(plan->totals + 1), T, H, W, n_img, tref, dst, cw, plan->eval_skip))
-#define SPLATT_RB(WR) do { switch (std::min(n_img, kMaxRB)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
+#define SPLATT_RB(WR) do { switch (refs_per_pass(n_img)) { case 1: SPLATT(WR, 1); break; case 2: SPLATT(WR, 2); break; \
                                                              case 3: SPLATT(WR, 3); break; default: SPLATT(WR, 4); } } while (0)
         if (plan->wrap) SPLATT_RB(true); else SPLATT_RB(false);
 #undef SPLATT_RB
@@ -502,7 +502,7 @@ int backward_impl(eincm_plan* plan, const eincm_hparams* hp, double* loss_out, d
 #define BWDT(WR, RB) LAUNCH("k_backward_events", launch_pdl(k_backward_tile<WR, RB>, dim3(gridT2), dim3(256), RB * kWinCap * sizeof(float), st, (const uint32_t*)plan->ev_xy, \
                                    (const double*)plan->ev_t, (const Chunk*)plan->chunks, (const unsigned int*)(plan->totals + 1), plan->tsrc, H, W, R, plan->tref, \
                                    (const float*)plan->dldi32, (const int4*)plan->chunk_win, plan->G, plan->eval_skip))
-#define BWDT_RB(WR) do { switch (std::min(R, kMaxRB)) { case 1: BWDT(WR, 1); break; case 2: BWDT(WR, 2); break; \
+#define BWDT_RB(WR) do { switch (refs_per_pass(R)) { case 1: BWDT(WR, 1); break; case 2: BWDT(WR, 2); break; \
                                                            case 3: BWDT(WR, 3); break; default: BWDT(WR, 4); } } while (0)
             if (plan->wrap) BWDT_RB(true); else BWDT_RB(false);
 #undef BWDT_RB

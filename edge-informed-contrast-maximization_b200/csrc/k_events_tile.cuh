@@ -34,6 +34,12 @@ namespace eincm {
 constexpr int kEvK = 4;                    // events per thread (one 128-bit load of packed coordinates, two of timestamps)
 constexpr uint32_t kNoEvent = 0xffffffffu; // padding sentinel of the sorted stream
 constexpr int kMaxRB = 4;                  // reference times processed per pass over a chunk
+// reference times per pass for R reference times: the passes a kMaxRB-wide kernel would need, evenly filled (R = 5: two passes of 3 instead of
+// 4 + 1 - the same number of passes with 48 KB instead of 64 KB of windows per CTA, i.e. four resident CTAs per SM instead of three)
+inline int refs_per_pass(int R) {
+    const int passes = (R + kMaxRB - 1) / kMaxRB;
+    return passes > 0 ? (R + passes - 1) / passes : 1;
+}
 
 // Warp of one event to one reference time on the default path.  Same float64 arithmetic, in the same order, as warp_event
 // (event_warpers.py:34-35: x' = x - (theta * dt) * 1.0), but rint() and the int conversion use the 2^52 magic constant
