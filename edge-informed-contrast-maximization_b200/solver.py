@@ -378,6 +378,19 @@ class BatchedMultipleLevelEINCMSolver:
     def _run_theta_solvers(self, pyr_lvl: int, thetas0, active=None):
         s0 = self.solvers[0]
         key = f'pyr_lvl_{pyr_lvl}'
+        hp = self.objectives[0].hparams(pyr_lvl)
+        if hp.delta != 0.0 or (hp.gamma != 0.0 and pyr_lvl <= 0) or int(np.prod(np.shape(thetas0[0]))) > 1024:
+            # what the batched kernels do not evaluate (the TV regulariser at the finest level - gamma != 0: MVSEC outdoor, run.sh:85 -, delta != 0)
+            # or hold (more than 1024 parameters): one window at a time through the single-window solver
+            thetas, states = [], []
+            for k, s in enumerate(self.solvers):
+                if active is None or active[k]:
+                    th, st = s._run_theta_solver(pyr_lvl, thetas0[k])
+                else:
+                    th, st = np.asarray(thetas0[k]), None
+                thetas.append(th)
+                states.append(st)
+            return thetas, states
         thetas, res = self.batch.minimize_bfgs_graph_host(np.stack(thetas0), self.objectives[0].hparams(pyr_lvl), s0.theta_opt_maxiters[key],
                                                           s0.theta_opt_solver_params['options']['gtol'], active=active)
         self.graph_launches += self.batch.solve_launches()

@@ -151,3 +151,29 @@ def test_lockstep_solver_matches_one_solver_per_window():
         lock.close()
         for o in oa + ob:
             o.close()
+
+
+def test_lockstep_solver_hands_the_tv_level_to_the_single_window_solver():
+    """gamma != 0 (MVSEC outdoor, run.sh:85): the TV regulariser is active at the finest level, which the batched kernels do not evaluate -
+    that level runs per window, the coarser levels in lockstep."""
+    from eincm_b200 import losses, solver as SV
+    wins = [S.make_workload('tiny', seed=s) for s in (21, 22)]
+    H, W = wins[0].sensor_size
+    hpd = wins[0].hparams
+    objs = [losses.WindowObjective((H, W), hpd['alpha'], hpd['beta'], 0.0025, 0.0, max_events=max(len(w.xs) for w in wins), max_refs=max(3, len(wins[0].edge_ts)))
+            for _ in wins]
+    lock = SV.BatchedMultipleLevelEINCMSolver(objs)
+    try:
+        lock.set_datasamples([w.args() for w in wins])
+        res = lock.solve()
+        assert lock.graph_launches > 0                                          # levels 4 .. 1 in lockstep
+        for k, r in enumerate(res):
+            st = r['theta_opt_state_pyr']['pyr_lvl_0']
+            assert st.status in (0, 1, 2) and st.n_evals >= 1
+            th = r['final_theta_pyr']['pyr_lvl_0']
+            assert th.shape == (16, 16, 2) and np.isfinite(th).all()
+            assert objs[k].value(th, 0) == st.fun_val                            # the finest level's value includes the TV term
+    finally:
+        lock.close()
+        for o in objs:
+            o.close()
