@@ -149,7 +149,12 @@ def make_sequence(name: str, n_windows: int, seed: int = 0, n_events: Optional[i
     # scene the reference objective is unbounded below in practice: its correlation term, mean(w_r * MSE_r / MSE_zero) with a NEGATIVE
     # sign (src/eincm/losses.py:176, 186), rewards smearing the events into a flat image, and with few edge pixels MSE_zero is so small
     # that this outweighs the contrast term - scipy's BFGS then runs to flows of thousands of pixels (profiles/r2_objective_landscape.txt).
-    scene.setdefault('n_segments', 4 * max(20, int(200 * (cfg['H'] * cfg['W']) / (480 * 640))))
+    # Windows with fewer events than pixels (MVSEC: 30 000 events on 86 016 pixels) leave the image of warped events sparse, and the same
+    # happens along the truth ray at 8 - 32 x the truth flow unless the scene is denser still (twelve times: the truth is then the minimum
+    # along the ray for every seed tried; at four times the solves wandered to ~40 px of end-point error).
+    n_ev = n_events if n_events is not None else cfg['N']
+    dense = 4 if n_ev >= cfg['H'] * cfg['W'] else 12
+    scene.setdefault('n_segments', dense * max(20, int(200 * (cfg['H'] * cfg['W']) / (480 * 640))))
     rs = np.random.default_rng(10_000 + seed)
     theta0 = rs.uniform(-mag, mag, size=(2, 2, 2))
     step = rs.normal(0.0, 1.0, size=(2, 2, 2)) * drift * mag
