@@ -145,6 +145,31 @@ __device__ __forceinline__ void load_sub_events(const uint32_t* __restrict__ ev_
     }
 }
 
+// Small chunks (sparse windows: MVSEC has ~90 events per source tile) give every thread ONE event instead of kEvK: the serial work of a thread
+// between two barriers of the chunk - the critical path of a CTA in which seven of eight warps would otherwise wait at the barrier for one
+// (ncu, profiles/r2_ncu_metrics_mvsec_batch.txt: 9.9 barrier stalls per issue in k_backward_tile_b) - shrinks by kEvK.  Slot 0 of the
+// group holds the event, the loops over the slots stop after it.  Same lane order as load_sub_events.
+#ifndef EINCM_SINGLE_MAX
+#define EINCM_SINGLE_MAX 256
+#endif
+constexpr uint32_t kSingleMax = EINCM_SINGLE_MAX;   // 0: never (A/B builds)
+__device__ __forceinline__ bool single_mode(const Chunk ch) { return ch.count <= kSingleMax; }
+
+template <bool SPREAD>
+__device__ __forceinline__ void load_single_events(const uint32_t* __restrict__ ev_xy, const double* __restrict__ ev_t, const Chunk ch, EventGroup& ev) {
+    uint32_t e = threadIdx.x;
+    if (SPREAD) {
+        const uint32_t nw = (ch.count + 31u) >> 5, w = threadIdx.x >> 5;
+        e = w < nw ? nw * (threadIdx.x & 31u) + w : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < kEvK; ++k) { ev.xy[k] = kNoEvent; ev.t[k] = 0.0; }
+    if (e < ch.count) {
+        ev.xy[0] = __ldg(ev_xy + (int64_t)ch.start + e);
+        ev.t[0] = __ldg(ev_t + (int64_t)ch.start + e);
+    }
+}
+
 // Window of one reference time inside the destination image: origin (ox, oy), pw x ph cells, row pitch pw.  A warped event
 // votes into the window when its rounded centre lies in [ox + 1, ox + pw - 2] x [oy + 1, oy + ph - 2]; the kernels test that on
 // the float64 warped coordinate itself, |x' - cx| < hx (strict: a coordinate exactly on the rounding boundary takes the
@@ -472,7 +497,8 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
         const int ns = n_subs(ch);                   // sub-chunks of <= kSubChunk events: one in registers at a time
         EventGroup ev;
         int cur_sub = 0;
-        load_sub_events<true>(ev_xy, ev_t, ch, 0, ev);
+        const bool single = single_mode(ch);         // one event per thread (one sub-chunk)
+        if (single) load_single_events<true>(ev_xy, ev_t, ch, ev); else load_sub_events<true>(ev_xy, ev_t, ch, 0, ev);
         // programmatic dependent launch: this kernel may have been scheduled while the previous kernel of the stream (the backward pass
         // of the previous evaluation: it clears the fixed-point images and reads chunk_win) was still running - only the staged
         // events were read so far
@@ -523,6 +549,7 @@ __device__ __forceinline__ void splat_tile_body(const uint32_t* __restrict__ ev_
                     for (int q = 0; q < 9; ++q) acc[q] = 0;
 #pragma unroll
                     for (int k = 0; k < kEvK; ++k) {
+                        if (k == 1 && single) break;                             // CTA-uniform
                         const uint32_t xy = ev.xy[k];
                         const Hit2 h = warp_hit2(xy, lds_theta(th_base, xy), ev.t[k] - tr);
                         const bool valid = xy != kNoEvent;
@@ -702,6 +729,8 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
                 double* __restrict__ G /* [H][W][2] */, float* dwin /* [RB][kWinCap] dynamic shared memory */, const int* __restrict__ skip = nullptr) {
     __shared__ double2 th_s[kKeysPerTile];
     __shared__ Window swin[RB];
+    __shared__ uint32_t c_xy[8], c_last[8];                  // single mode: first / last pixel of every warp's events ...
+    __shared__ float c_sx[8], c_sy[8];                       // ... and the sums of the run that starts at lane 0
     const int64_t HW = (int64_t)H * W;
     const int tid = threadIdx.x, lane = tid & 31;
     const int n_chunks = (int)__ldg(n_chunks_dev);
@@ -711,7 +740,8 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
         const Chunk ch = chunks[c];
         const int ns = n_subs(ch);                   // sub-chunks of <= kSubChunk events: one in registers at a time
         EventGroup ev;
-        load_sub_events<false>(ev_xy, ev_t, ch, 0, ev);
+        const bool single = single_mode(ch);         // one event per thread (one sub-chunk)
+        if (single) load_single_events<false>(ev_xy, ev_t, ch, ev); else load_sub_events<false>(ev_xy, ev_t, ch, 0, ev);
         tile_theta(T, ch.origin, H, W, th_s);
         // programmatic dependent launch: everything above read the staged events and the flow operand only
         if (c == (int)blockIdx.x) {
@@ -783,6 +813,7 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
                     const double tr = tref.t[r0 + r];
 #pragma unroll
                     for (int k = 0; k < kEvK; ++k) {
+                        if (k == 1 && single) break;                             // CTA-uniform
                         const uint32_t xy = ev.xy[k];
                         const double dt = ev.t[k] - tr;
                         const Hit2 h = warp_hit2(xy, lds_theta(th_base, xy), dt);
@@ -828,12 +859,14 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
         // per-thread runs of equal source pixel: all but the last run go straight to G
         uint32_t run_xy = ev.xy[0];
         float sx = ax[0], sy = ay[0];
+        if (!single) {
 #pragma unroll
-        for (int k = 1; k < kEvK; ++k) {
-            if (ev.xy[k] == run_xy) { sx += ax[k]; sy += ay[k]; }
-            else {
-                if (run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
-                run_xy = ev.xy[k]; sx = ax[k]; sy = ay[k];
+            for (int k = 1; k < kEvK; ++k) {
+                if (ev.xy[k] == run_xy) { sx += ax[k]; sy += ay[k]; }
+                else {
+                    if (run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
+                    run_xy = ev.xy[k]; sx = ax[k]; sy = ay[k];
+                }
             }
         }
         // last runs of the warp's threads: segmented (by source pixel) suffix sum, one reduction pair per run
@@ -845,8 +878,28 @@ __device__ __forceinline__ void backward_tile_body(const uint32_t* __restrict__ 
             if (lane + o < 32 && oxy == run_xy) { sx += ox; sy += oy; }
         }
         const uint32_t prev = __shfl_up_sync(0xffffffffu, run_xy, 1);
-        const bool head = (lane == 0) || (prev != run_xy);
-        if (head && run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
+        if (single) {
+            // one event per thread, sorted by pixel: a pixel's run may cross warps.  The run's first warp collects the sums of the warps
+            // it continues into (fixed order) and issues the ONE reduction pair of the pixel: the gradient of a window whose tiles hold a
+            // single chunk each does not depend on the order of any atomics.
+            const int wid = tid >> 5;
+            if (lane == 0) { c_xy[wid] = run_xy; c_sx[wid] = sx; c_sy[wid] = sy; }
+            if (lane == 31) c_last[wid] = run_xy;
+            __syncthreads();
+            const bool head = (lane == 0) ? (wid == 0 || c_last[wid - 1] != run_xy) : (prev != run_xy);
+            if (head && run_xy != kNoEvent) {
+                if (c_last[wid] == run_xy) {                        // the run reaches the end of this warp
+                    for (int q = wid + 1; q < 8 && c_xy[q] == run_xy; ++q) {
+                        sx += c_sx[q]; sy += c_sy[q];
+                        if (c_last[q] != run_xy) break;
+                    }
+                }
+                red_G(G, W, run_xy, sx, sy);
+            }
+        } else {
+            const bool head = (lane == 0) || (prev != run_xy);
+            if (head && run_xy != kNoEvent) red_G(G, W, run_xy, sx, sy);
+        }
         }
         __syncthreads();                             // th_s / swin / dwin are rewritten for the next chunk
     }

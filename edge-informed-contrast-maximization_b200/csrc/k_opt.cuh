@@ -152,7 +152,7 @@ __device__ __forceinline__ void bfgs_step_body(BfgsDev* __restrict__ S, const Bf
         }
     }
     if (act == ACT_TRIAL) {
-        if (in) B.x_trial[tid] = B.x[tid] + s_alpha * B.p[tid];
+        if (in) B.x_trial[tid] = __dadd_rn(B.x[tid], __dmul_rn(s_alpha, B.p[tid]));      // no FMA contraction: the host loop rounds the product
         if (tid == 0) B.result[0] = 0.0;
         return;
     }

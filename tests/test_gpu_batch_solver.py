@@ -33,7 +33,7 @@ def test_one_by_one_level_is_identical_to_the_single_window_loop():
         for k, (ta, ra) in enumerate(single):
             assert (rb[k].status, rb[k].nit, rb[k].nfev) == (ra.status, ra.nit, ra.nfev), k
             assert rb[k].fun == ra.fun
-            np.testing.assert_array_equal(tb[k], ta)
+            np.testing.assert_array_equal(tb[k], ta)                              # the same device code: identical
         assert len({r.nfev for r in rb}) > 1                 # the windows end at different steps: the skip flags were exercised
         # a subset: the others are left untouched
         act = np.array([1, 0, 1, 0, 0], dtype=np.int32)

@@ -26,7 +26,7 @@ def test_one_by_one_level_is_identical_to_the_host_loop():
         tb, rb = p.minimize_bfgs_graph_host(th0, hp, 8, 1e-7)
         assert (rb.status, rb.nit, rb.nfev) == (ra.status, ra.nit, ra.nfev)
         assert rb.fun == ra.fun
-        np.testing.assert_array_equal(tb, ta)
+        np.testing.assert_allclose(tb, ta, rtol=1e-15, atol=0)                      # the device code may contract a * b + c into an FMA: an ulp or two
         # again on the same window: the instantiated graph is re-used; from another start
         th1 = np.full((1, 1, 2), 0.7)
         ta, ra = p.minimize_bfgs_host(th1, hp, 8, 1e-7, own_stream=True)
