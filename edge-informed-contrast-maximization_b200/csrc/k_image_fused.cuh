@@ -71,6 +71,9 @@ constexpr int kS2Cols = 28;                         // own columns of a warp (la
 #define EINCM_S2_ROWS 12
 #endif
 constexpr int kS2Rows = EINCM_S2_ROWS;                         // own rows of a warp (640x480, R = 3: 12 rows 140.8 us per evaluation on one stream, 24 rows 144.9; kernel 29 us either way)
+#ifndef EINCM_S2_MINB
+#define EINCM_S2_MINB 5
+#endif
 constexpr int kS2Pre = 4;                           // rows per load group
 constexpr int kStatsTicket = 6;                     // DevScalars::counters slot of the "last CTA" ticket
 
@@ -318,11 +321,11 @@ __device__ __forceinline__ void image_stats_body(const ImageStatsArgs& A) {
     if (tid == 0) A.sc->counters[kStatsTicket] = 0u;
 }
 
-__global__ void __launch_bounds__(kS2NT, 5)
+__global__ void __launch_bounds__(kS2NT, EINCM_S2_MINB)
 k_image_stats(const ImageStatsArgs A) { image_stats_body(A); }
 
 // batched form: blockIdx.y = window, one argument record per window in device memory
-__global__ void __launch_bounds__(kS2NT, 5)
+__global__ void __launch_bounds__(kS2NT, EINCM_S2_MINB)
 k_image_stats_b(const ImageStatsArgs* __restrict__ args, const int* __restrict__ order) {
     __shared__ ImageStatsArgs sA;
     const int bw = batch_window(order);
