@@ -13,6 +13,7 @@ The solver is the CALLER of the hot path: it stays host Python in
 from __future__ import annotations
 
 import collections
+import functools
 import math
 from typing import Dict, Optional, Sequence
 
@@ -56,8 +57,10 @@ def _kernel(method: str):
     raise NotImplementedError(f'resize method "{method}" is not implemented')
 
 
+@functools.lru_cache(maxsize=256)
 def compute_weight_mat(input_size: int, output_size: int, scale: float, method: str, antialias: bool = True) -> np.ndarray:
-    """``jax._src.image.scale.compute_weight_mat`` with translation 0: ``(input_size, output_size)`` float64."""
+    """``jax._src.image.scale.compute_weight_mat`` with translation 0: ``(input_size, output_size)`` float64 (cached per shape: the
+    solver resizes the same five pyramid shapes for every window; treat the result as read-only)."""
     inv_scale = 1.0 / scale
     kernel_scale = max(inv_scale, 1.0) if antialias else 1.0
     sample_f = (np.arange(output_size) + 0.5) * inv_scale - 0.5
@@ -66,7 +69,9 @@ def compute_weight_mat(input_size: int, output_size: int, scale: float, method: 
     total = weights.sum(axis=0, keepdims=True)
     weights = np.where(np.abs(total) > 1000.0 * np.finfo(np.float32).eps, weights / np.where(total != 0, total, 1.0), 0.0)
     ok = (sample_f >= -0.5) & (sample_f <= input_size - 0.5)
-    return np.where(ok[None, :], weights, 0.0)
+    out = np.where(ok[None, :], weights, 0.0)
+    out.setflags(write=False)
+    return out
 
 
 def scale_and_translate(theta: np.ndarray, shape: Sequence[int], method: str) -> np.ndarray:
