@@ -403,6 +403,45 @@ def test_chunk_and_sub_chunk_boundaries(L, n_tile):
         p.close()
 
 
+@pytest.mark.parametrize('n_hot,n_other', [(1, 0), (31, 0), (32, 1), (33, 40), (64, 0), (100, 30), (200, 55), (255, 0), (256, 0), (252, 4), (257, 0), (300, 20)])
+def test_small_chunks_one_event_per_thread(L, n_hot, n_other):
+    """Chunks of at most 256 events take one event per thread (sparse windows): the run of a pixel with many events crosses warps, and the
+    run's first warp collects the sums of the warps it continues into (k_events_tile.cuh, backward pass).  n_hot events on ONE pixel
+    (+ n_other on its tile) at counts around the warp size and the mode's limit: objective and gradient against the oracle, and the
+    gradient bit-identical from call to call (one reduction pair per pixel: no order of atomics to depend on)."""
+    from eincm_b200 import plan as P
+    rng = np.random.default_rng(1000 * n_hot + n_other)
+    H, W = 64, 96
+    base = S.make_window(H, W, 48, seed=3)                               # edges + a few events elsewhere (other tiles: small chunks too)
+    keep = ~((base.xs >= 32) & (base.xs < 48) & (base.ys >= 16) & (base.ys < 32))       # the hot tile holds exactly n_hot + n_other events
+    xs = np.concatenate([base.xs[keep], np.full(n_hot, 40, np.int16), rng.integers(32, 48, n_other).astype(np.int16)])
+    ys = np.concatenate([base.ys[keep], np.full(n_hot, 21, np.int16), rng.integers(16, 32, n_other).astype(np.int16)])
+    ts = np.concatenate([base.ts[keep], rng.uniform(0, 1, n_hot + n_other)])
+    order = np.argsort(ts, kind='stable')
+    xs, ys, ts = np.ascontiguousarray(xs[order]), np.ascontiguousarray(ys[order]), np.ascontiguousarray(ts[order])
+    kw = dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, cur_pyr_lvl=1, n_pyr_lvls=5, sensor_size=(H, W),
+              scale_to_sensor_size_method='bilinear')
+    th = rng.normal(0.0, 4.0, size=(2, 3, 2))
+    loss, grad = L.value_and_grad(L.loss_func)(th, xs, ys, ts, base.edges, base.edge_ts, **kw)
+    l_ref, g_ref = O.value_and_grad(th, xs, ys, ts, base.edges, base.edge_ts, **kw)
+    assert abs(loss - l_ref) <= OBJ_RTOL * abs(l_ref)
+    assert _rel_inf(grad, g_ref) <= 1e-5                                 # float32 per-event gradients: far inside GRAD_RTOL (a lost carry is > 10 %)
+    p = P.Plan((H, W), max_events=len(xs), max_refs=3)
+    try:
+        hp = P.make_hparams(20.0, 35.0, 0.0, 0.0, 1)
+        p.set_window(xs, ys, ts, base.edges, base.edge_ts)
+        la, ga = p.value_and_grad_host(th, hp)
+        for _ in range(3):
+            lb, gb = p.value_and_grad_host(th, hp)
+            assert la == lb == loss
+            if n_hot + n_other <= 256:
+                np.testing.assert_array_equal(ga, gb)
+            else:                                                        # four events per thread: a pixel's run may end in three reductions
+                np.testing.assert_allclose(ga, gb, rtol=1e-11, atol=1e-300)
+    finally:
+        p.close()
+
+
 def test_batched_host_call_matches_single_calls(tiny):
     """eincm_value_and_grad_host_batch: independent windows evaluated concurrently, each on its own stream, give the results
     of one-at-a-time calls (objective bit-identical: it does not depend on scheduling)."""
