@@ -200,9 +200,9 @@ struct ThetaGradArgs {
 // ended (order[0] = their number, order[1 ..] = their indices: k_bfgs_compact) - the blockIdx.y-th of those; -1: no window, return at once.
 __device__ __forceinline__ int batch_window(const int* __restrict__ order) {
     int win = (int)blockIdx.y;
-    if (order != nullptr) {
-        if (win >= order[0]) return -1;
-        win = order[1 + win];
+    if (order != nullptr) {                          // written by an earlier kernel of the same graph launch: read through L2, never the read-only path
+        if (win >= __ldcg(order)) return -1;
+        win = __ldcg(order + 1 + win);
     }
     return win;
 }
