@@ -1,0 +1,33 @@
+"""CUDA path (through the C-ABI) against the vectors of the reference's own source (tests/golden/refsrc/*.npz: the reference's
+unmodified eincm.losses executed over the float64 JAX stand-in of tests/_jaxshim, see tests/golden/make_golden_refsrc.py).
+Tolerances are BASELINE.json's: objective 1e-5, gradient 1e-4 relative (inf-norm); the event -> pixel index stream bit-exact."""
+import numpy as np
+import pytest
+
+from tests import _golden as G
+from tests.test_reference_source import load_refsrc, _rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('exact', [False, True])
+@pytest.mark.parametrize('name', G.NAMES)
+def test_cuda_matches_reference_source_vectors(name, exact):
+    from eincm_b200 import plan as P
+    g, ref = G.load(name), load_refsrc(name)
+    hp = P.make_hparams(**g['hp'])
+    R = len(g['edge_ts'])
+    p = P.Plan(g['sensor_size'], max_events=len(g['xs']), max_refs=max(R, 3), flags=P.FLAG_EXACT_F64 if exact else 0)
+    p.set_window(*g['args'])
+    loss, grad = p.value_and_grad_host(g['theta'], hp)
+    rl, rg = (1e-11, 1e-9) if exact else (1e-5, 1e-4)
+    assert abs(loss - float(ref['loss'])) <= rl * abs(float(ref['loss']))
+    assert _rel_inf(grad, ref['grad']) <= rg
+    for r in range(R):
+        cols, rows = p.rounded_pixels(r)
+        np.testing.assert_array_equal(cols, np.rint(ref['obj_warped_xs'][r]).astype(np.int32))
+        np.testing.assert_array_equal(rows, np.rint(ref['obj_warped_ys'][r]).astype(np.int32))
+    hl, hd = p.handover_value_and_grad_host(float(g['alpha_handover']), g['prev_theta'], g['theta'], hp)
+    assert abs(hl - float(ref['handover_loss'])) <= rl * abs(float(ref['handover_loss']))
+    assert abs(hd - float(ref['handover_dalpha'])) <= rg * max(abs(float(ref['handover_dalpha'])), np.abs(ref['grad']).max())
+    p.close()

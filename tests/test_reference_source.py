@@ -1,0 +1,168 @@
+"""The reference's OWN source against the oracle.
+
+tests/golden/refsrc/*.npz hold the outputs of the reference's unmodified ``eincm.losses`` (loss_func, compute_loss_objectives,
+handover_loss_func - src/eincm/losses.py:49-276 and everything they import) executed over the float64 torch-backed JAX stand-in
+``tests/_jaxshim`` on the inputs of the committed fixtures (tests/golden/make_golden_refsrc.py).  They pin the oracle's restatement of
+the reference's composition, forward and reverse; the JAX primitives themselves stay restated (listed in tests/_jaxshim/jax/__init__.py).
+
+Where /root/reference is present (this container, not the GPU box) the same is repeated live on further windows: events leaving the
+frame on every side (negative-index wrap before mode='drop'), TV / divergence terms, 2 - 5 reference times, dense theta.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import eincm_b200.synth as S
+from oracle import eincm_oracle as O
+from tests import _golden as G
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFSRC_DIR = os.path.join(G.GOLDEN_DIR, 'refsrc')
+REFERENCE_SRC = '/root/reference/src'
+
+
+def load_refsrc(name):
+    z = np.load(os.path.join(REFSRC_DIR, name + '.npz'))
+    return {k: z[k] for k in z.files}
+
+
+def _rel_inf(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def test_every_fixture_has_reference_source_vectors():
+    assert G.NAMES and sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(REFSRC_DIR, '*.npz'))) == G.NAMES
+
+
+def _check_against_oracle(theta, prev, a_ho, args, hp, sensor_size, ref, tight=1e-11):
+    kw = dict(n_pyr_lvls=5, sensor_size=sensor_size, scale_to_sensor_size_method='bilinear', **hp)
+    loss, grad, inter = O.value_and_grad(theta, *args, return_intermediates=True, **kw)
+    assert abs(loss - float(ref['loss'])) <= tight * abs(float(ref['loss']))
+    assert _rel_inf(grad, ref['grad']) <= 1e-9
+    np.testing.assert_allclose(O.scale_theta_to_sensor_size(theta, sensor_size), ref['scaled_theta'], rtol=1e-13, atol=1e-15)
+    obj = inter['objectives']
+    # the warped coordinates decide the event -> pixel index stream: their rint must agree exactly
+    for k in ('warped_xs', 'warped_ys'):
+        np.testing.assert_allclose(obj[k], ref['obj_' + k], rtol=0, atol=1e-11)
+        np.testing.assert_array_equal(np.rint(obj[k]), np.rint(ref['obj_' + k]))
+    for k in ('correlations', 'zero_correlations', 'contrasts', 'zero_contrast', 'theta_total_variation', 'theta_divergence',
+              'iwe_divergences', 'zero_iwe_divergence', 'flow_warp_losses', 'multi_ref_weights'):
+        if k == 'theta_total_variation' and hp['gamma'] == 0.0:
+            continue    # unused by the loss; on (piecewise) constant flow its count of EXACTLY non-zero gradients depends on the
+                        # summation order of the convolution (test_tv_count_depends_on_summation_order below)
+        if k in obj:
+            np.testing.assert_allclose(np.asarray(obj[k], dtype=np.float64), ref['obj_' + k], rtol=1e-10, atol=1e-14, err_msg=k)
+    ho_loss, ho_dalpha = O.handover_value_and_grad(a_ho, prev, theta, *args, **kw)
+    assert abs(ho_loss - float(ref['handover_loss'])) <= tight * abs(float(ref['handover_loss']))
+    assert abs(ho_dalpha - float(ref['handover_dalpha'])) <= 1e-9 * max(abs(float(ref['handover_dalpha'])), np.abs(ref['grad']).max())
+
+
+@pytest.mark.parametrize('name', G.NAMES)
+def test_oracle_matches_reference_source_vectors(name):
+    g, ref = G.load(name), load_refsrc(name)
+    hp = dict(g['hp'])
+    _check_against_oracle(g['theta'], g['prev_theta'], float(g['alpha_handover']), g['args'], hp, g['sensor_size'], ref)
+
+
+@pytest.mark.parametrize('name', G.NAMES)
+def test_committed_fixtures_match_reference_source_vectors(name):
+    """the fixtures the C oracle and the CUDA path are tested against (tests/golden/*.npz) carry the reference source's numbers"""
+    g, ref = G.load(name), load_refsrc(name)
+    assert abs(float(g['loss']) - float(ref['loss'])) <= 1e-12 * abs(float(ref['loss']))
+    assert _rel_inf(g['grad'], ref['grad']) <= 1e-10
+    assert abs(float(g['handover_loss']) - float(ref['handover_loss'])) <= 1e-12 * abs(float(ref['handover_loss']))
+    R = len(g['edge_ts'])
+    for r in range(R):
+        np.testing.assert_array_equal(g['rounded'][r, 0], np.rint(ref['obj_warped_xs'][r]).astype(np.int32))
+        np.testing.assert_array_equal(g['rounded'][r, 1], np.rint(ref['obj_warped_ys'][r]).astype(np.int32))
+
+
+@pytest.mark.parametrize('name', G.NAMES)
+def test_c_oracle_matches_reference_source_vectors(name):
+    from oracle import c_oracle as C
+    if not C.available():
+        subprocess.run(['make', '-C', os.path.join(os.path.dirname(HERE), 'oracle')], check=True, stdout=subprocess.DEVNULL)
+    g, ref = G.load(name), load_refsrc(name)
+    hp = g['hp']
+    lc, gc = C.value_and_grad_raw(g['theta'], *g['args'], hp['alpha'], hp['beta'], hp['gamma'], hp['delta'], hp['cur_pyr_lvl'], g['sensor_size'])[:2]
+    assert abs(lc - float(ref['loss'])) <= 1e-11 * abs(float(ref['loss']))
+    assert _rel_inf(gc, ref['grad']) <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# live: the reference source executed now (only where /root/reference exists)
+# ---------------------------------------------------------------------------------------------------------------------------------
+
+LIVE = [  # H, W, N, edge_ts, theta shape, point, flow scale, hyper-parameters
+    (40, 56, 3000, (0.0, 0.5, 1.0), (2, 2), 'perturbed', 1.0, dict(alpha=2000.0, beta=4000.0, gamma=0.0, delta=0.0, cur_pyr_lvl=3)),
+    (40, 56, 3000, (0.0, 1.0), (8, 8), 'truth', 1.0, dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.3, cur_pyr_lvl=1)),
+    (33, 47, 2500, (0.0, 0.25, 0.5, 0.75, 1.0), (16, 16), 'perturbed', 1.0, dict(alpha=60.0, beta=60.0, gamma=0.0025, delta=0.3, cur_pyr_lvl=0)),
+    (33, 47, 2000, (0.0, 0.5, 1.0), (33, 47), 'perturbed', 1.0, dict(alpha=20.0, beta=35.0, gamma=0.0025, delta=0.0, cur_pyr_lvl=0)),
+    # flows far larger than the frame: events leave on every side; rows / columns -1 ... -H wrap before mode='drop' drops the rest
+    (40, 56, 3000, (0.0, 0.5, 1.0), (4, 4), 'perturbed', 25.0, dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, cur_pyr_lvl=2)),
+    (40, 56, 3000, (0.0, 0.5, 1.0), (4, 4), 'perturbed', -40.0, dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.3, cur_pyr_lvl=2)),
+]
+
+
+@pytest.fixture(scope='module')
+def reference():
+    if not os.path.isdir(REFERENCE_SRC):
+        pytest.skip('/root/reference is not on this machine (the committed tests/golden/refsrc vectors stand in)')
+    saved_path, saved_mods = list(sys.path), set(sys.modules)
+    sys.path.insert(0, os.path.join(G.GOLDEN_DIR))
+    import make_golden_refsrc as M
+    jax, L = M.import_reference()
+    yield M, jax, L
+    sys.path[:] = saved_path
+    for m in set(sys.modules) - saved_mods:          # the stand-in must not stay importable as "jax" for other tests
+        del sys.modules[m]
+
+
+@pytest.mark.parametrize('case', range(len(LIVE)))
+def test_oracle_matches_reference_source_live(reference, case):
+    M, jax, L = reference
+    H, W, N, edge_ts, shape, point, fscale, hp = LIVE[case]
+    win = S.make_window(seed=900 + case, H=H, W=W, N=N, edge_ts=edge_ts)
+    pts = S.theta_test_points(win, shape, seed=case)
+    theta = pts[point] * fscale
+    prev = pts['zero'] if point == 'truth' else pts['truth']
+    g = dict(xs=win.xs, ys=win.ys, ts=win.ts, edges=win.edges, edge_ts=np.asarray(win.edge_ts), theta=theta, prev_theta=prev, alpha_handover=0.61,
+             hp_names=np.array(sorted(hp)), hp_values=np.array([float(hp[n]) for n in sorted(hp)]))
+    ref = M.run_case(jax, L, g)
+    if abs(fscale) > 1.0:   # the case must exercise what it is there for
+        wx, wy = ref['obj_warped_xs'], ref['obj_warped_ys']
+        assert (np.rint(wx) < -1).any() and (np.rint(wx) > W).any() and (np.rint(wy) < -1).any() and (np.rint(wy) > H).any()
+    _check_against_oracle(theta, prev, 0.61, win.args(), hp, win.sensor_size, ref)
+
+
+def test_tv_count_depends_on_summation_order(reference, monkeypatch):
+    """regularizers.py:26-29 counts pixels whose flow gradient is exactly non-zero.  On a constant flow field the reference source yields
+    the oracle's value when antisymmetric taps are differenced first (the canonical order of the oracle and the kernels) and another one
+    when the nine taps are accumulated in turn: XLA's order is not knowable from the source, which is why the order is fixed by decree."""
+    M, jax, L = reference
+    import jax.numpy as jnp
+    win = S.make_window(seed=77, H=40, W=56, N=3000, edge_ts=(0.0, 1.0))
+    theta_full = np.broadcast_to(np.array([3.7, -1.3]), (40, 56, 2)).copy()
+    want = O.per_pix_total_variation(theta_full, win.xs, win.ys, win.ts)
+    import eincm.regularizers as Rg
+    monkeypatch.setenv('JAX_SHIM_CONV', 'pairs')
+    got_pairs = float(Rg.per_pix_total_variation(jnp.array(theta_full), jnp.array(win.xs), jnp.array(win.ys), jnp.array(win.ts)))
+    monkeypatch.delenv('JAX_SHIM_CONV')
+    got_turn = float(Rg.per_pix_total_variation(jnp.array(theta_full), jnp.array(win.xs), jnp.array(win.ys), jnp.array(win.ts)))
+    assert got_pairs == pytest.approx(want, rel=1e-12)
+    assert got_turn != pytest.approx(want, rel=1e-3)
+
+
+def test_reference_source_vectors_are_current(reference):
+    """the committed vectors are what the reference source yields today"""
+    M, jax, L = reference
+    for name in G.NAMES:
+        z = np.load(os.path.join(G.GOLDEN_DIR, name + '.npz'))
+        out = M.run_case(jax, L, {k: z[k] for k in z.files})
+        ref = load_refsrc(name)
+        assert out['loss'] == float(ref['loss'])
+        np.testing.assert_array_equal(out['grad'], ref['grad'])
