@@ -123,6 +123,9 @@ class Array:
     def __bool__(self):
         return bool(self.t)
 
+    def __format__(self, spec):
+        return format(self.t.detach().item(), spec)
+
     def __repr__(self):
         return f'ShimArray({self.t!r})'
 
@@ -157,6 +160,8 @@ class Array:
 
     def __getitem__(self, idx):
         tup = idx if isinstance(idx, tuple) else (idx,)
+        if len(tup) == 1 and isinstance(tup[0], (Array, torch.Tensor)) and _unwrap(tup[0]).dtype == torch.bool:
+            return _wrap(self.t[_unwrap(tup[0])])          # boolean mask over the leading axes
         if any(isinstance(i, (Array, torch.Tensor, np.ndarray, list)) for i in tup):
             dims = [d for d, i in enumerate(tup)]
             assert Ellipsis not in tup and len(tup) == self.t.dim(), 'advanced index must name every axis in this stand-in'
@@ -190,5 +195,6 @@ class Array:
     __le__ = lambda s, o: s._bin(o, torch.le)
     __or__ = lambda s, o: s._bin(o, torch.logical_or)
     __and__ = lambda s, o: s._bin(o, torch.logical_and)
+    __invert__ = lambda s: _wrap(~s.t)
     __neg__ = lambda s: _wrap(-s.t)
     __abs__ = lambda s: _wrap(s.t.abs())

@@ -67,3 +67,22 @@ def sqrt(x):
 
 def exp(x):
     return _wrap(_unwrap(x).exp())
+
+
+def logical_and(a, b):
+    return _wrap(_torch.logical_and(_unwrap(a), _unwrap(b)))
+
+
+def logical_or(a, b):
+    return _wrap(_torch.logical_or(_unwrap(a), _unwrap(b)))
+
+
+def isinf(x):
+    return _wrap(_torch.isinf(_unwrap(x)))
+
+
+class linalg:
+    @staticmethod
+    def norm(x, axis=None):
+        t = _unwrap(x).to(float64)
+        return _wrap(_torch.sqrt((t * t).sum() if axis is None else (t * t).sum(dim=axis)))

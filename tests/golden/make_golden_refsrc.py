@@ -65,6 +65,13 @@ def run_case(jax, L, g):
                handover_loss=float(ho_loss), handover_dalpha=float(ho_dalpha))
     for k, v in obj.items():
         out['obj_' + k] = np.asarray(v, dtype=np.float64)
+    if 'gt_flow' in g:
+        # src/evaluations/theta_eval.py:14-97 (and flow_eval.py:14-75 through it) on the fixture's synthetic ground truth
+        import evaluations.theta_eval as TE
+        _, _, ev, _ = TE.evaluate_theta_array(aux['scaled_theta'], xs, ys, ts, edges, edge_ts, jnp.array(g['gt_flow']), hp['alpha'], hp['beta'],
+                                              hp['gamma'], hp['delta'], (int(H), int(W)), err_eval_event_mask=jnp.array(g['err_mask']))
+        for k, v in ev.items():
+            out['eval_' + k] = np.asarray(v, dtype=np.float64)
     return out
 
 

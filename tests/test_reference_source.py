@@ -82,6 +82,28 @@ def test_committed_fixtures_match_reference_source_vectors(name):
 
 
 @pytest.mark.parametrize('name', G.NAMES)
+def test_evaluation_metrics_match_reference_source_vectors(name):
+    """src/evaluations/theta_eval.py:14-97 / flow_eval.py:14-75 executed as they are, against the oracle's evaluate_theta_array and the
+    numbers stored in the fixtures (which the CUDA evaluation kernels are tested against, tests/test_gpu_golden_eval.py)"""
+    g, ref = G.load(name), load_refsrc(name)
+    hp = g['hp']
+    theta_full = O.scale_theta_to_sensor_size(g['theta'], g['sensor_size'])
+    ev = O.evaluate_theta_array(theta_full, *g['args'], g['gt_flow'], hp['alpha'], hp['beta'], hp['gamma'], hp['delta'], g['sensor_size'],
+                                err_eval_event_mask=g['err_mask'])
+    keys = [k[5:] for k in ref if k.startswith('eval_')]
+    assert {'AEE', 'AREE', 'A1PE', 'A20PE', 'n_ee', 'n_pred', 'n_gt', 'n_pixels', 'loss', 'iwe_var', 'fwl', 'rel_contrasts'} <= set(keys)
+    for k in keys:
+        if k == 'theta_tot_var' and hp['gamma'] == 0.0:
+            continue        # constant / linear stretches of a coarse theta: the count of exactly non-zero flow gradients depends on
+                            # the summation order of the convolution (test_tv_count_depends_on_summation_order); not in the loss here
+        np.testing.assert_allclose(np.asarray(ev[k], dtype=np.float64), ref['eval_' + k], rtol=1e-10, atol=1e-13, err_msg=k)
+        if k in g['eval']:
+            np.testing.assert_allclose(g['eval'][k], ref['eval_' + k], rtol=1e-10, atol=1e-13, err_msg=k)
+    for k in ('n_ee', 'n_pred', 'n_gt', 'n_pixels'):
+        assert int(ev[k]) == int(ref['eval_' + k])
+
+
+@pytest.mark.parametrize('name', G.NAMES)
 def test_c_oracle_matches_reference_source_vectors(name):
     from oracle import c_oracle as C
     if not C.available():
@@ -137,6 +159,29 @@ def test_oracle_matches_reference_source_live(reference, case):
         wx, wy = ref['obj_warped_xs'], ref['obj_warped_ys']
         assert (np.rint(wx) < -1).any() and (np.rint(wx) > W).any() and (np.rint(wy) < -1).any() and (np.rint(wy) > H).any()
     _check_against_oracle(theta, prev, 0.61, win.args(), hp, win.sensor_size, ref)
+
+
+@pytest.mark.parametrize('seed,H,W', [(0, 48, 64), (1, 61, 83), (2, 120, 160)])
+def test_edge_oracle_matches_reference_img_utils_live(reference, seed, H, W):
+    """the reference's own utils.img_utils functions (importable over the stand-in; they run OpenCV / SciPy, both in this image), called
+    the way exp_mgr.py:343-350 chains them, against oracle/edge_oracle.py - which tests/test_gpu_edges.py holds the device kernels to"""
+    from oracle import edge_oracle as E
+    import utils.img_utils as IU
+    assert os.path.realpath(IU.__file__).startswith(os.path.realpath(REFERENCE_SRC))
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[:H, :W]
+    f = (127 + 90 * np.sin(xx / 7.0 + seed) * np.cos(yy / 5.0) + rng.normal(0, 6, (H, W))).clip(0, 255).astype(np.uint8)
+    edge = IU.image_to_edge(f)                                                             # img_utils.py:192-207
+    assert np.array_equal(E.canny(f, 30, 80), edge)
+    np.testing.assert_allclose(E.smoothen_edges(edge), IU.smoothen_edges(edge), rtol=0, atol=1e-10)            # :210-220
+    np.testing.assert_allclose(E.eincm_inv_exp_dist_transform(edge, 6 / 5.541), IU.eincm_inv_exp_dist_transform(edge, 6 / 5.541), rtol=0, atol=1e-12)  # :229-235
+    np.testing.assert_allclose(E.edge_map(f), IU.normalize_to_unit_range(IU.smoothen_edges(IU.image_to_edge(f))), rtol=0, atol=1e-10)
+    # preprocess_image up to (not including) the bilateral filter, :147-181, in the reference's positional argument order
+    import cv2 as cv
+    d = E.fast_nl_means_denoising(f, 4, 3, 11)
+    c = E.clahe_apply(d, 5.0, (10, 10))
+    sharp = E.add_weighted_u8(c, 1.5, E.gaussian_blur_u8(c, 3), -0.5)
+    assert np.array_equal(cv.bilateralFilter(sharp, 5, 15, 15), IU.preprocess_image(f))
 
 
 def test_tv_count_depends_on_summation_order(reference, monkeypatch):
