@@ -5,14 +5,26 @@ only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import it, and only as the checker (or the timed
 CPU baseline), never as a fallback for the CUDA path.
 
-PARITY UNPINNED: the reference (robotic-vision-lab/Edge-Informed-Contrast-
-Maximization) is pure Python on JAX/jaxopt, ships no tests, golden vectors or
-fixtures for this path, and JAX/jaxlib/jaxopt are not installable in this image
-(no network), so neither the reference itself nor reference-owned vectors can
-pin this restatement.  It is pinned instead by (tests/test_oracle_*.py):
-known answers derived by hand from the reference source, scipy/torch cross
-checks of every JAX primitive restated here, an independent torch-autograd
-re-derivation of the gradient, and central finite differences.
+PARITY: the reference (robotic-vision-lab/Edge-Informed-Contrast-Maximization)
+is pure Python on JAX/jaxopt and ships no tests, golden vectors or fixtures for
+this path; JAX/jaxlib/jaxopt are not installable in this image (no network).
+Two layers:
+
+* pinned against the reference's OWN SOURCE: its unmodified ``eincm.losses``,
+  ``evaluations.theta_eval`` and ``eincm.solver`` are imported from
+  /root/reference and executed over a float64 torch stand-in for the JAX entry
+  points they call (tests/_jaxshim); the outputs are committed under
+  tests/golden/refsrc/ (tests/golden/make_golden_refsrc.py) and this file is
+  held to them - loss 1e-11, gradient 1e-9, every intermediate
+  (tests/test_reference_source.py, tests/test_reference_solver_source.py);
+* PARITY UNPINNED for the JAX primitives themselves (list below): the stand-in
+  and this file both restate them from published JAX behaviour; only vectors
+  from a real JAX can settle those.
+
+Older pins, kept (tests/test_oracle_*.py): known answers derived by hand from
+the reference source, scipy/torch cross checks of every JAX primitive restated
+here, an independent torch-autograd re-derivation of the gradient, and central
+finite differences.
 
 Every function cites the reference file:line (relative to the reference repo
 root) that it restates.  JAX semantics that are not visible in the reference

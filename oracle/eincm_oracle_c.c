@@ -3,8 +3,10 @@
  * TEST INFRASTRUCTURE ONLY - not part of the product.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
  * `--impl reference` legs may load it, as the checker or as the timed CPU baseline; the CUDA path never calls it.
  *
- * PARITY UNPINNED by the reference (no tests / golden vectors upstream, JAX not installable here): this file is pinned to
- * oracle/eincm_oracle.py (tests/test_oracle_c.py), which carries the hand-derived pins.  It follows the SAME reference
+ * PARITY: no tests / golden vectors upstream and JAX is not installable here.  This file is pinned to oracle/eincm_oracle.py
+ * (tests/test_oracle_c.py) and, like it, to the outputs of the reference's own source executed over a float64 stand-in for the JAX
+ * primitives (tests/golden/refsrc/, tests/test_reference_source.py); PARITY UNPINNED for those primitives themselves (negative-index
+ * wrap of mode='drop', scale_and_translate weights, tie split of min / max cotangents).  It follows the SAME reference
  * lines; each function cites them (paths relative to the reference repository root).  Like the reference it recomputes
  * the zero-warp image of events on every evaluation (src/eincm/losses.py:54) - that is what the CPU baseline must time.
  *

@@ -61,8 +61,9 @@ class _AtIndex:
             i = torch.where(i < 0, i + n, i)        # NumPy rule for negative indices, BEFORE the bounds test
             ok &= (i >= 0) & (i < n)
             idx[d] = i
-        idx = [i[ok] for i in idx]
-        vals = vals[ok]
+        if not bool(ok.all()):
+            idx = [i[ok] for i in idx]
+            vals = vals[ok]
         if not accumulate and idx[0].numel():
             # .set with duplicate targets: ONE update wins and it alone receives the cotangent (JAX's scatter transpose masks the
             # losers; torch.index_put would hand the cotangent to every duplicate).  The last update in index order is taken.

@@ -16,7 +16,17 @@ def _keys_cubic(x):
     return _torch.where(x >= 2.0, _torch.zeros_like(x), out)
 
 
-_KERNELS = {'linear': _triangle, 'bilinear': _triangle, 'trilinear': _triangle, 'triangle': _triangle,
+def _lanczos(radius):
+    def k(x):
+        x = x.abs()
+        y = radius * _torch.sin(_np.pi * x) * _torch.sin(_np.pi * x / radius)
+        out = _torch.where(x > 1e-3, y / _torch.where(x != 0, _np.pi ** 2 * x ** 2, _torch.ones_like(x)), _torch.ones_like(x))
+        return _torch.where(x > radius, _torch.zeros_like(x), out)
+    return k
+
+
+_KERNELS = {'lanczos3': _lanczos(3.0), 'lanczos5': _lanczos(5.0),
+            'linear': _triangle, 'bilinear': _triangle, 'trilinear': _triangle, 'triangle': _triangle,
             'cubic': _keys_cubic, 'bicubic': _keys_cubic, 'tricubic': _keys_cubic}
 
 

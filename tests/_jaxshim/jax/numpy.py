@@ -86,3 +86,11 @@ class linalg:
     def norm(x, axis=None):
         t = _unwrap(x).to(float64)
         return _wrap(_torch.sqrt((t * t).sum() if axis is None else (t * t).sum(dim=axis)))
+
+
+def repeat(x, repeats, axis=None):
+    return _wrap(_torch.repeat_interleave(_unwrap(x), int(repeats), dim=axis))
+
+
+def clip(x, lo=None, hi=None):
+    return _wrap(_torch.clamp(_unwrap(x), min=lo, max=hi))

@@ -12,6 +12,5 @@ class multivariate_normal:
         x, mean, cov = (_unwrap(v).to(_torch.float64) for v in (x, mean, cov))
         d = x - mean
         k = d.shape[-1]
-        sol = _torch.linalg.solve(cov, d.T).T
-        q = (d * sol).sum(-1)
+        q = ((d @ _torch.linalg.inv(cov)) * d).sum(-1)
         return _wrap(_torch.exp(-0.5 * q) / math.sqrt((2.0 * math.pi) ** k * float(_torch.linalg.det(cov))))

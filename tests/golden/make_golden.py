@@ -5,7 +5,9 @@
 PARITY UNPINNED: the reference is pure Python on JAX / jaxopt, which cannot be imported in this image (no jax, jaxlib, jaxopt
 wheels; no network), so these vectors are outputs of the float64 NumPy restatement (oracle/eincm_oracle.py), NOT of the reference
 itself.  They pin the restatement against regressions and give the C oracle and the CUDA path fixed targets that do not depend
-on the oracle code at test time.  If a machine with JAX becomes available, regenerate them from the real
+on the oracle code at test time.  Since round 2 they are cross-checked against the reference's own source executed over a float64 stand-in for the JAX primitives
+(tests/golden/make_golden_refsrc.py -> tests/golden/refsrc/, tests/test_reference_source.py): same numbers to 1e-16.  That pins the
+composition, not JAX's primitives.  If a machine with JAX becomes available, regenerate them from the real
 ``jit(value_and_grad(loss_func))`` with the same seeds (the inputs are stored in the files) and commit the result.
 
 Each case stores its inputs (xs, ys int16; ts float64; edges; edge_ts; theta; hyper-parameters) and, from the oracle: loss, gradient,
