@@ -5,8 +5,11 @@ The reference code for this step is plain NumPy / jax.numpy (no third-party algo
   rectify_events        src/dataloaders/dsec_loader.py:145-170
   get_sample (range)    src/dataloaders/dsec_loader.py:293-311
   time normalisation    src/experiments/e00/exp_mgr.py:313-321
-The loader module itself cannot be imported here (it needs h5py / hdf5plugin, which are not installed): parity unpinned by an
-executed reference, pinned by hand-derived known answers in tests/test_ingest_oracle.py.
+Pinned by hand-derived known answers (tests/test_ingest_oracle.py) and, since round 2, by the reference's own loader methods
+(DSECDataLoader.rectify_events / precompute_eval_event_indices / get_sample, MVSECDataLoader.load_left_data) executed on in-memory arrays:
+the loader modules import over empty h5py / imageio stand-ins (tests/_jaxshim) and the objects are made without their file-opening
+constructors (tests/test_reference_source.py::test_ingest_oracle_matches_reference_loaders_live, build container only).  The time
+normalisation (exp_mgr.py, needs hydra / omegaconf / matplotlib to import) stays pinned by known answers only.
 """
 import sys
 

@@ -184,6 +184,67 @@ def test_edge_oracle_matches_reference_img_utils_live(reference, seed, H, W):
     assert np.array_equal(cv.bilateralFilter(sharp, 5, 15, 15), IU.preprocess_image(f))
 
 
+def test_ingest_oracle_matches_reference_loaders_live(reference, capsys):
+    """the reference's own loader methods (dsec_loader.py:145-186, 285-349; mvsec_loader.py:100-135), run on in-memory arrays - the
+    loader objects are made without their file-opening constructors - against oracle/ingest_oracle.py, which tests/test_gpu_ingest.py
+    holds the device kernels to"""
+    from oracle import ingest_oracle as I
+    import dataloaders.dsec_loader as DL
+    import dataloaders.mvsec_loader as ML
+    assert os.path.realpath(DL.__file__).startswith(os.path.realpath(REFERENCE_SRC))
+    rng = np.random.default_rng(3)
+    H, W, n = 48, 64, 20000
+    ev = {'x': rng.integers(0, W, n).astype(np.uint16), 'y': rng.integers(0, H, n).astype(np.uint16),
+          't': np.sort(rng.integers(0, 2_000_000, n)).astype(np.int64), 'p': rng.integers(0, 2, n).astype(np.uint8)}
+    yy, xx = np.mgrid[:H, :W].astype(np.float32)
+    rmap = np.stack([xx * 1.07 - 2.3 + 0.5 * np.sin(yy / 5), yy * 0.94 + 1.8 + rng.choice([0.0, 0.5], (H, W))], axis=-1).astype(np.float32)  # ties: .5
+    ld = object.__new__(DL.DSECDataLoader)
+    ld.rectify_map, ld.height, ld.width = rmap, H, W
+    ld.l_events = {k: v.copy() for k, v in ev.items()}
+    ld.rectify_events()
+    want = I.rectify_events(ev['x'], ev['y'], ev['t'], ev['p'], rmap, H, W)
+    for got, w_ in zip((ld.l_events['x'], ld.l_events['y'], ld.l_events['t'], ld.l_events['p']), want):
+        assert got.dtype == w_.dtype and np.array_equal(got, w_)
+    assert 0 < len(want[0]) < n                                                  # some events left the sensor
+
+    # fixed-N window rule through get_sample: event "x" = its own index, so the slice tells (start, end)
+    m = len(ld.l_events['x'])
+    ld.l_events['x'] = np.arange(m)
+    ld.t_offset, ld.data_split = 1_000, 'test'
+    ld.eval_ts_us = np.array([[1_000, 101_000, 0], [500_000, 600_000, 1], [1_900_000, 2_001_000, 2], [700_000, 1_500_000, 3]], dtype=np.int64)
+    ld.l_image_ts_us, ld.l_image_paths = np.array([0, 50_000, 2_100_000]), []
+    ld.precompute_eval_event_indices()
+    ld.precompute_eval_image_indices()
+    for des, latest in [(None, False), (1500, False), (1500, True), (12000, False), (30000, True)]:
+        ld.des_n_events, ld.prefer_latest_events, ld.n_event_deficiency = des, latest, 0
+        for k in range(len(ld.eval_ts_us)):
+            s_ = ld.get_sample(k)
+            a0, a1 = int(ld.eval_event_start_idxs[k]), int(ld.eval_event_end_idxs[k])
+            assert a0 == int(np.searchsorted(ld.l_events['t'], ld.eval_ts_us[k, 0] - ld.t_offset, side='left'))
+            b0, b1, deficiency = I.window_event_range(a0, a1, m, des, latest)
+            got = s_['events']['x']
+            assert (int(got[0]), int(got[-1]) + 1) == (b0, b1) and len(got) == b1 - b0, (des, latest, k)
+            if des is not None:
+                assert int(s_['n_event_deficiency']) == deficiency
+            np.testing.assert_array_equal(s_['events']['t'], ld.l_events['t'][b0:b1] + ld.t_offset)
+
+    # MVSEC crop
+    class Reader:
+        def open_file(self): pass
+        def close_file(self): pass
+        def read_h5_dataset(self, name):
+            return {'davis/left/events': raw, 'davis/left/image_raw': np.zeros((2, 260, 346), np.uint8)}.get(name, np.zeros(3))
+    raw = np.stack([rng.integers(0, 346, 5000), rng.integers(0, 260, 5000), np.sort(rng.random(5000)) * 10, rng.choice([-1, 1], 5000)], axis=-1).astype(np.float64)
+    mv = object.__new__(ML.MVSECDataLoader)
+    mv.mvsec_h5_rdr = Reader()
+    mv.load_left_data()
+    want = I.crop_events(*raw.T)
+    for k, w_ in zip('xytp', want):
+        assert mv.l_events[k].dtype == w_.dtype and np.array_equal(mv.l_events[k], w_)
+    assert mv.l_image_raw.shape == (2, 256, 336)
+    capsys.readouterr()
+
+
 def test_tv_count_depends_on_summation_order(reference, monkeypatch):
     """regularizers.py:26-29 counts pixels whose flow gradient is exactly non-zero.  On a constant flow field the reference source yields
     the oracle's value when antisymmetric taps are differenced first (the canonical order of the oracle and the kernels) and another one
