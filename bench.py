@@ -809,6 +809,21 @@ def run_own(args):
                  'loss_rel': abs(l0 - l_ref) / abs(l_ref), 'grad_rel_inf': float(np.abs(g0 - g_ref).max() / np.abs(g_ref).max()),
                  'tolerance': {'loss_rel': 1e-5, 'grad_rel_inf': 1e-4}, 'checker': label}
         check['ok'] = bool(check['loss_rel'] <= 1e-5 and check['grad_rel_inf'] <= 1e-4)
+        # The same window and theta against the committed output of the reference's OWN source (its unmodified eincm.losses executed over
+        # a float64 stand-in for the JAX primitives: tests/golden/make_golden_refsrc_fullsize.py).  Reported, never fatal: the vector
+        # exists for the default workload only and the regenerated window must carry the stored checksum.
+        try:
+            z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tests', 'golden', 'refsrc_fullsize', 'dsec_2m_theta16.npz'))
+            w0 = wins[0]
+            cs = np.array([float(np.asarray(w0.xs, dtype=np.float64).sum()), float(np.asarray(w0.ys, dtype=np.float64).sum()),
+                           float(np.asarray(w0.ts).sum()), float(np.asarray(w0.edges).sum()), float(len(w0.xs))])
+            if (args.workload == 'dsec' and z['theta'].shape == np.shape(thetas_h[0]) and np.array_equal(z['theta'], thetas_h[0])
+                    and np.allclose(cs, z['checksum'], rtol=1e-12, atol=0)):
+                check['reference_source'] = {'loss_ref': float(z['loss']), 'loss_rel': abs(l0 - float(z['loss'])) / abs(float(z['loss'])),
+                                             'grad_rel_inf': float(np.abs(g0 - z['grad']).max() / np.abs(z['grad']).max()),
+                                             'vector': 'tests/golden/refsrc_fullsize/dsec_2m_theta16.npz'}
+        except Exception as e:  # noqa: BLE001
+            check['reference_source'] = {'error': repr(e)[:120]}
 
     # ---- the same device-resident step with EINCM_FLAG_EXACT_F64 plans (float64 taps and float64 scatter-adds: `dtype` f64 throughout)
     exact = None

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from tests import _golden as G
-from tests.test_reference_source import load_refsrc, _rel_inf
+from tests.test_reference_source import FULLSIZE, load_fullsize, load_refsrc, _rel_inf
 
 pytestmark = pytest.mark.gpu
 
@@ -31,3 +31,21 @@ def test_cuda_matches_reference_source_vectors(name, exact):
     assert abs(hl - float(ref['handover_loss'])) <= rl * abs(float(ref['handover_loss']))
     assert abs(hd - float(ref['handover_dalpha'])) <= rg * max(abs(float(ref['handover_dalpha'])), np.abs(ref['grad']).max())
     p.close()
+
+
+@pytest.mark.parametrize('name', FULLSIZE)
+def test_cuda_matches_reference_source_at_bench_configurations(name):
+    """the BENCH line's configuration (dsec, N = 2 M, R = 3, theta 16 x 16, window of seed 0, the 'perturbed' point bench.py evaluates) and
+    MVSEC dt4 with dense theta, against loss and gradient of the reference's own source (tests/golden/refsrc_fullsize/)"""
+    from eincm_b200 import plan as P
+    win, z = load_fullsize(name)
+    hp = win.hparams
+    R = len(win.edge_ts)
+    p = P.Plan(win.sensor_size, max_events=len(win.xs), max_refs=max(R, 3))
+    try:
+        p.set_window(*win.args())
+        loss, grad = p.value_and_grad_host(z['theta'], P.make_hparams(hp['alpha'], hp['beta'], hp['gamma'], hp['delta'], int(z['cur_pyr_lvl'])))
+    finally:
+        p.close()
+    assert abs(loss - float(z['loss'])) <= 1e-5 * abs(float(z['loss'])), (loss, float(z['loss']))
+    assert _rel_inf(grad, z['grad']) <= 1e-4

@@ -115,6 +115,35 @@ def test_c_oracle_matches_reference_source_vectors(name):
     assert _rel_inf(gc, ref['grad']) <= 1e-9
 
 
+FULLSIZE_DIR = os.path.join(G.GOLDEN_DIR, 'refsrc_fullsize')
+FULLSIZE = ['dsec_2m_theta16', 'mvsec_dt4_dense']
+
+
+def load_fullsize(name):
+    """(window regenerated from its seed, stored vector) - skips if the regenerated operands do not carry the stored checksum"""
+    z = np.load(os.path.join(FULLSIZE_DIR, name + '.npz'))
+    win = S.make_workload(str(z['workload']), seed=int(z['seed']))
+    cs = np.array([float(np.asarray(win.xs, dtype=np.float64).sum()), float(np.asarray(win.ys, dtype=np.float64).sum()),
+                   float(np.asarray(win.ts).sum()), float(np.asarray(win.edges).sum()), float(len(win.xs))])
+    if not np.allclose(cs, z['checksum'], rtol=1e-12, atol=0):
+        pytest.skip('eincm_b200.synth regenerates a different window on this machine (NumPy version?)')
+    return win, z
+
+
+@pytest.mark.parametrize('name', FULLSIZE)
+def test_c_oracle_matches_reference_source_at_bench_configurations(name):
+    """the checker of bench.py's `check` and of tests/test_gpu_fullsize.py, at the BENCH line's configuration (dsec, N = 2 M, theta 16 x 16,
+    seed 0) and at MVSEC dt4 with dense theta, against the reference's own source (tests/golden/make_golden_refsrc_fullsize.py)"""
+    from oracle import c_oracle as C
+    if not C.available():
+        subprocess.run(['make', '-C', os.path.join(os.path.dirname(HERE), 'oracle')], check=True, stdout=subprocess.DEVNULL)
+    win, z = load_fullsize(name)
+    hp = win.hparams
+    lc, gc = C.value_and_grad_raw(z['theta'], *win.args(), hp['alpha'], hp['beta'], hp['gamma'], hp['delta'], int(z['cur_pyr_lvl']), win.sensor_size)[:2]
+    assert abs(lc - float(z['loss'])) <= 1e-10 * abs(float(z['loss']))
+    assert _rel_inf(gc, z['grad']) <= 1e-8
+
+
 # ---------------------------------------------------------------------------------------------------------------------------------
 # live: the reference source executed now (only where /root/reference exists)
 # ---------------------------------------------------------------------------------------------------------------------------------
