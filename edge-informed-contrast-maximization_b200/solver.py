@@ -167,8 +167,8 @@ class MultipleLevelEINCMSolver:
 
         self.pre_opt_theta_pyr, self.opt_theta_pyr, self.handover_opt_theta_pyr, self.prior_theta_pyr = {}, {}, {}, {}
         self._initialize_theta_pyramids()
-        self.init_handover_weight_pyr = {f'pyr_lvl_{l}': 0.5 for l in range(n_pyr_lvls)}         # solver.py:151-155
-        self.final_handover_weight_pyr = {f'pyr_lvl_{l}': 0.5 for l in range(n_pyr_lvls)}
+        self.init_handover_weight_pyr, self.final_handover_weight_pyr = {}, {}
+        self._initialize_handover_weights()
         self.theta_opt_state_pyr, self.ho_opt_state_pyr = {}, {}
         self._IS_FIRST_SAMPLE = True
 
@@ -176,15 +176,26 @@ class MultipleLevelEINCMSolver:
     def not_first_sample(self):
         self._IS_FIRST_SAMPLE = False
 
-    def _initialize_theta_pyramids(self):                                                         # solver.py:129-148
+    def _initialize_theta_pyramids(self, theta_pyr_init=None):                                    # solver.py:129-148
+        """``theta_pyr_init``: a prior pyramid to start from (a resumed run hands in the last solved one) instead of zeros."""
         top = f'pyr_lvl_{self.n_pyr_lvls - 1}'
-        for pyr in (self.pre_opt_theta_pyr, self.opt_theta_pyr, self.handover_opt_theta_pyr, self.prior_theta_pyr):
+        pyrs = [self.pre_opt_theta_pyr, self.opt_theta_pyr, self.handover_opt_theta_pyr]
+        if theta_pyr_init is not None:
+            self.prior_theta_pyr = theta_pyr_init
+        else:
+            pyrs.append(self.prior_theta_pyr)
+        for pyr in pyrs:
             pyr[top] = np.zeros((1, 1, 2))
         for pyr_lvl in reversed(range(self.n_pyr_lvls - 1)):
             key, key_coarser = f'pyr_lvl_{pyr_lvl}', f'pyr_lvl_{pyr_lvl + 1}'
             base = self.pyramid_bases[-pyr_lvl - 1]
-            for pyr in (self.pre_opt_theta_pyr, self.opt_theta_pyr, self.handover_opt_theta_pyr, self.prior_theta_pyr):
+            for pyr in pyrs:
                 pyr[key] = self._upscale_theta(pyr[key_coarser], base=base)
+
+    def _initialize_handover_weights(self):                                                       # solver.py:151-155
+        for pyr_lvl in range(self.n_pyr_lvls):
+            self.init_handover_weight_pyr[f'pyr_lvl_{pyr_lvl}'] = 0.5
+            self.final_handover_weight_pyr[f'pyr_lvl_{pyr_lvl}'] = 0.5
 
     def set_datasample(self, xs, ys, ts, edges, edge_ts):                                         # solver.py:185-194
         self.objective.set_datasample(xs, ys, ts, edges, edge_ts)

@@ -274,6 +274,40 @@ def test_ingest_oracle_matches_reference_loaders_live(reference, capsys):
     capsys.readouterr()
 
 
+def test_mirror_interfaces_match_the_reference_signatures(reference):
+    """drop-in boundary: the host-side mirror takes the reference's argument names, order and defaults - read off the
+    reference's own function objects, not restated"""
+    import inspect
+    import eincm.losses as RL
+    import eincm.solver as RS
+    import evaluations.theta_eval as RTE
+    import evaluations.flow_eval as RFE
+    import utils.img_utils as RIU
+    from eincm_b200 import evaluations as ME, img_utils as MIU, losses as ML, solver as MS
+
+    def params(f):
+        return [(n, p.default) for n, p in inspect.signature(f).parameters.items()]
+
+    for name in ('loss_func', 'handover_loss_func', 'compute_weights_for_multi_reference', 'compute_loss_objectives'):
+        assert params(getattr(ML, name)) == params(getattr(RL, name)), name
+    assert params(ME.sparse_flow_error) == params(RFE.sparse_flow_error)
+    ref_eval, mir_eval = params(RTE.evaluate_theta_array), params(ME.evaluate_theta_array)
+    assert mir_eval[:len(ref_eval)] == ref_eval                                  # the mirror may append device / stream keywords
+    for name in ('image_to_edge', 'smoothen_edges', 'eincm_inv_exp_dist_transform', 'preprocess_image'):
+        r, m = params(getattr(RIU, name)), params(getattr(MIU, name))
+        assert m[:len(r)] == r, name
+    # solver: constructor keywords (the mirror takes an objective in place of the two loss partials), state and result keys
+    r = [n for n, _ in params(RS.MultipleLevelEINCMSolver.__init__)]
+    m = [n for n, _ in params(MS.MultipleLevelEINCMSolver.__init__)]
+    dropped = {'theta_loss_pfunc', 'handover_loss_pfunc'}
+    assert [n for n in r if n not in dropped] == [n for n in m if n in r]
+    for meth in ('set_datasample', 'solve', 'not_first_sample', '_pre_solve', '_stage_prior_theta_pyr', '_perform_handover_at_level', '_upscale_theta',
+                 '_downscale_theta', '_initialize_theta_pyramids', '_initialize_handover_weights'):
+        assert hasattr(MS.MultipleLevelEINCMSolver, meth), meth
+    for meth in ('set_datasample', '_initialize_theta_pyramids', '_upscale_theta', '_downscale_theta', '_perform_handover_at_level'):
+        assert params(getattr(MS.MultipleLevelEINCMSolver, meth)) == params(getattr(RS.MultipleLevelEINCMSolver, meth)), meth
+
+
 def test_tv_count_depends_on_summation_order(reference, monkeypatch):
     """regularizers.py:26-29 counts pixels whose flow gradient is exactly non-zero.  On a constant flow field the reference source yields
     the oracle's value when antisymmetric taps are differenced first (the canonical order of the oracle and the kernels) and another one

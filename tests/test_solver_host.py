@@ -92,3 +92,16 @@ def test_two_window_solve_with_handover():
     # the priors of the coarser levels are the lanczos3-downscaled finest prior (solver.py:283-289)
     np.testing.assert_allclose(r1['prior_theta_pyr']['pyr_lvl_1'],
                                SV.scale_and_translate(r0['final_theta_pyr']['pyr_lvl_0'], (2, 2), 'lanczos3'), rtol=1e-12)
+
+
+def test_theta_pyramids_can_start_from_a_given_prior():
+    """solver.py:129-148: `theta_pyr_init` replaces the zero prior pyramid (how a resumed run hands in its last solved pyramid,
+    exp_mgr.py:236-243 does the same by assignment); the other three pyramids start from zeros"""
+    sol = SV.MultipleLevelEINCMSolver(OracleObjective((48, 64), 20.0, 35.0), n_pyr_lvls=3)
+    prior = {f'pyr_lvl_{k}': np.full((4 >> k, 4 >> k, 2), 1.5 + k) for k in range(3)}
+    sol._initialize_theta_pyramids(theta_pyr_init=prior)
+    assert sol.prior_theta_pyr is prior
+    for pyr in (sol.pre_opt_theta_pyr, sol.opt_theta_pyr, sol.handover_opt_theta_pyr):
+        assert [pyr[f'pyr_lvl_{k}'].shape for k in range(3)] == [(4, 4, 2), (2, 2, 2), (1, 1, 2)]
+        assert all(not pyr[f'pyr_lvl_{k}'].any() for k in range(3))
+    assert sol.init_handover_weight_pyr == {f'pyr_lvl_{k}': 0.5 for k in range(3)} == sol.final_handover_weight_pyr
