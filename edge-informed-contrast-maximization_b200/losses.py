@@ -102,7 +102,10 @@ def _as_theta(theta) -> np.ndarray:
 
 
 def _aux_from_plan(p: _plan.Plan, loss: float) -> Dict[str, object]:
-    """aux_info of reference src/eincm/losses.py:195-203 ('scaled_theta' stays on the device)."""
+    """aux_info of reference src/eincm/losses.py:195-203 ('scaled_theta' stays on the device).  One deviation: a regulariser whose
+    weight is zero is not evaluated on the device, so 'mean_rel_iwe_divergence' (delta == 0) and 'theta_total_variation' (gamma == 0)
+    read 0.0 here where the reference reports the value it goes on to multiply by zero; the loss and its gradient are unaffected
+    (tests/test_gpu_reference_source.py).  eincm_b200.evaluations.evaluate_theta_array reports both regardless of the weights."""
     s = p.scalars()
     return {'final_loss': loss, 'scaled_theta': p.theta_full(), 'mean_rel_corr': s['mean_rel_corr'],
             'mean_rel_contrast': s['mean_rel_contrast'], 'mean_rel_iwe_divergence': s['mean_rel_iwe_divergence'],
