@@ -65,6 +65,9 @@ def run_case(jax, L, g):
                handover_loss=float(ho_loss), handover_dalpha=float(ho_dalpha))
     for k, v in obj.items():
         out['obj_' + k] = np.asarray(v, dtype=np.float64)
+    # the images themselves (losses.py:54, 61: what compute_loss_objectives builds and reduces)
+    out['zero_iwe'] = np.asarray(L.events_to_pdf_frame(xs, ys, (int(H), int(W))))
+    out['iwes'] = np.asarray(L.vmapped_events_to_pdf_frame(obj['warped_xs'], obj['warped_ys'], (int(H), int(W))))
     if 'gt_flow' in g:
         # src/evaluations/theta_eval.py:14-97 (and flow_eval.py:14-75 through it) on the fixture's synthetic ground truth
         import evaluations.theta_eval as TE

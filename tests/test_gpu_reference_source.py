@@ -27,6 +27,10 @@ def test_cuda_matches_reference_source_vectors(name, exact):
         cols, rows = p.rounded_pixels(r)
         np.testing.assert_array_equal(cols, np.rint(ref['obj_warped_xs'][r]).astype(np.int32))
         np.testing.assert_array_equal(rows, np.rint(ref['obj_warped_ys'][r]).astype(np.int32))
+    rt, at = (1e-10, 1e-13) if exact else (2e-5, 1e-7)                            # the images of (warped) events themselves
+    np.testing.assert_allclose(p.zero_iwe().cpu().numpy(), ref['zero_iwe'], rtol=rt, atol=at)
+    if exact or g['hp']['delta'] != 0.0:                                          # default mode keeps fixed-point images unless delta needs them
+        np.testing.assert_allclose(p.iwe().cpu().numpy(), ref['iwes'], rtol=rt, atol=at)
     hl, hd = p.handover_value_and_grad_host(float(g['alpha_handover']), g['prev_theta'], g['theta'], hp)
     assert abs(hl - float(ref['handover_loss'])) <= rl * abs(float(ref['handover_loss']))
     assert abs(hd - float(ref['handover_dalpha'])) <= rg * max(abs(float(ref['handover_dalpha'])), np.abs(ref['grad']).max())

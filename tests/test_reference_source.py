@@ -56,6 +56,8 @@ def _check_against_oracle(theta, prev, a_ho, args, hp, sensor_size, ref, tight=1
                         # summation order of the convolution (test_tv_count_depends_on_summation_order below)
         if k in obj:
             np.testing.assert_allclose(np.asarray(obj[k], dtype=np.float64), ref['obj_' + k], rtol=1e-10, atol=1e-14, err_msg=k)
+    np.testing.assert_allclose(inter['zero_iwe'], ref['zero_iwe'], rtol=1e-12, atol=1e-15)           # the images of (warped) events
+    np.testing.assert_allclose(inter['iwes'], ref['iwes'], rtol=1e-11, atol=1e-14)
     ho_loss, ho_dalpha = O.handover_value_and_grad(a_ho, prev, theta, *args, **kw)
     assert abs(ho_loss - float(ref['handover_loss'])) <= tight * abs(float(ref['handover_loss']))
     assert abs(ho_dalpha - float(ref['handover_dalpha'])) <= 1e-9 * max(abs(float(ref['handover_dalpha'])), np.abs(ref['grad']).max())
@@ -76,6 +78,8 @@ def test_committed_fixtures_match_reference_source_vectors(name):
     assert _rel_inf(g['grad'], ref['grad']) <= 1e-10
     assert abs(float(g['handover_loss']) - float(ref['handover_loss'])) <= 1e-12 * abs(float(ref['handover_loss']))
     R = len(g['edge_ts'])
+    np.testing.assert_allclose(g['zero_iwe'], ref['zero_iwe'], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(g['iwes'], ref['iwes'], rtol=1e-11, atol=1e-14)
     for r in range(R):
         np.testing.assert_array_equal(g['rounded'][r, 0], np.rint(ref['obj_warped_xs'][r]).astype(np.int32))
         np.testing.assert_array_equal(g['rounded'][r, 1], np.rint(ref['obj_warped_ys'][r]).astype(np.int32))
