@@ -160,6 +160,9 @@ LIVE = [  # H, W, N, edge_ts, theta shape, point, flow scale, hyper-parameters
     # flows far larger than the frame: events leave on every side; rows / columns -1 ... -H wrap before mode='drop' drops the rest
     (40, 56, 3000, (0.0, 0.5, 1.0), (4, 4), 'perturbed', 25.0, dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, cur_pyr_lvl=2)),
     (40, 56, 3000, (0.0, 0.5, 1.0), (4, 4), 'perturbed', -40.0, dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.3, cur_pyr_lvl=2)),
+    # the shipped shapes at a tenth of their events: DSEC 480 x 640 with theta 16 x 16 (main.yaml weights), MVSEC 260 x 346 with dense theta, R = 5
+    (480, 640, 200000, (0.0, 0.5, 1.0), (16, 16), 'perturbed', 1.0, dict(alpha=2000.0, beta=4000.0, gamma=0.0, delta=0.0, cur_pyr_lvl=0)),
+    (260, 346, 30000, (0.0, 0.25, 0.5, 0.75, 1.0), (260, 346), 'perturbed', 1.0, dict(alpha=60.0, beta=60.0, gamma=0.0025, delta=0.0, cur_pyr_lvl=0)),
 ]
 
 
