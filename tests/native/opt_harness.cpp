@@ -76,4 +76,23 @@ int bounded_scalar_wavy(double m, double* a, double lo, double hi, int maxiter, 
     return err;
 }
 
+// any objective behind a C function pointer (pytest hands in the EINCM objective evaluated by the CPU oracle)
+typedef int (*objective_fn)(const double* x, double* f, double* g);
+
+int bfgs_callback(int n, double* x, int maxiter, double gtol, objective_fn fn, Out* out) {
+    eincm_opt::Objective f = [fn](const double* v, double* fv, double* g) -> int { return fn(v, fv, g); };
+    int err = 0;
+    const eincm_opt::Result r = eincm_opt::bfgs(f, n, x, maxiter, gtol, &err);
+    out->fun = r.fun; out->nit = r.nit; out->nfev = r.nfev; out->status = r.status; out->pad = 0;
+    return err;
+}
+
+int bounded_scalar_callback(double* a, double lo, double hi, int maxiter, double pgtol, objective_fn fn, Out* out) {
+    eincm_opt::Objective f = [fn](const double* v, double* fv, double* g) -> int { return fn(v, fv, g); };
+    int err = 0;
+    const eincm_opt::Result r = eincm_opt::bounded_scalar(f, a, lo, hi, maxiter, pgtol, 1e7, &err);
+    out->fun = r.fun; out->nit = r.nit; out->nfev = r.nfev; out->status = r.status; out->pad = 0;
+    return err;
+}
+
 }  // extern "C"

@@ -133,3 +133,80 @@ def test_bounded_scalar_same_schedule_as_lbfgsb(lib, m, lo, hi, a0):
     assert lib.bounded_scalar_wavy(C.c_double(m), C.byref(a), C.c_double(lo), C.c_double(hi), 20, C.c_double(1e-6), C.byref(out)) == 0
     assert abs(a.value - ref.x[0]) <= 1e-6
     assert (out.nit, out.nfev) == (ref.nit, ref.nfev)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# on the EINCM objective itself (evaluated by the CPU oracle): what the 'native' and 'graph' solver backends run inside the library,
+# against the scipy calls jaxopt makes for the reference (src/eincm/solver.py:165-183)
+# ---------------------------------------------------------------------------------------------------------------------------------
+OBJ = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+@pytest.fixture(scope='module')
+def window():
+    import eincm_b200.synth as S
+    rs = np.random.default_rng(5)
+    return S.make_window(32, 48, 4000, seed=300, n_segments=40, scene_seed=77, truth_theta=rs.uniform(-4, 4, size=(2, 2, 2)))
+
+
+@pytest.mark.parametrize('shape,lvl,maxiter', [((1, 1), 2, 8), ((2, 2), 1, 6), ((4, 4), 0, 5)])
+def test_native_bfgs_follows_scipy_on_the_eincm_objective(lib, window, shape, lvl, maxiter):
+    from oracle import eincm_oracle as O
+    kw = dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, cur_pyr_lvl=lvl, n_pyr_lvls=3, sensor_size=window.sensor_size,
+              scale_to_sensor_size_method='bilinear')
+    n = shape[0] * shape[1] * 2
+    calls = []
+
+    def fun(x):
+        v, g = O.value_and_grad(np.asarray(x, dtype=np.float64).reshape(shape + (2,)), *window.args(), **kw)
+        calls.append(v)
+        return v, g.ravel()
+
+    @OBJ
+    def cfun(xp, fp, gp):
+        v, g = fun(np.ctypeslib.as_array(xp, shape=(n,)).copy())
+        fp[0] = v
+        np.ctypeslib.as_array(gp, shape=(n,))[:] = g
+        return 0
+
+    x0 = np.zeros(n)
+    ref = scipy.optimize.minimize(fun, x0, jac=True, method='BFGS', options={'gtol': 1e-7, 'maxiter': maxiter})
+    scipy_calls, calls[:] = list(calls), []          # what jaxopt's scipy_fun is really called with (scipy's nfev / njev count separately)
+    x = x0.copy()
+    out = Out()
+    assert lib.bfgs_callback(n, x.ctypes.data_as(C.POINTER(C.c_double)), maxiter, C.c_double(1e-7), cfun, C.byref(out)) == 0
+    assert (out.nit, out.status) == (ref.nit, ref.status)
+    assert out.nfev == len(calls)
+    print(f'evaluations: native {len(calls)}, scipy {len(scipy_calls)} (nfev {ref.nfev}, njev {ref.njev})')
+    assert abs(len(calls) - len(scipy_calls)) <= max(3, len(scipy_calls) // 20)
+    k = min(len(calls), len(scipy_calls), 10)
+    np.testing.assert_allclose(calls[:k], scipy_calls[:k], rtol=1e-9)          # the same trial points from the start
+    assert out.fun == pytest.approx(ref.fun, rel=1e-8)          # same algorithm, other summation order in the dot products
+    np.testing.assert_allclose(x, ref.x, rtol=1e-5, atol=1e-6)
+
+
+def test_native_bounded_scalar_follows_scipy_on_the_handover_objective(lib, window):
+    from oracle import eincm_oracle as O
+    import eincm_b200.synth as S
+    kw = dict(alpha=20.0, beta=35.0, gamma=0.0, delta=0.0, cur_pyr_lvl=0, n_pyr_lvls=3, sensor_size=window.sensor_size,
+              scale_to_sensor_size_method='bilinear')
+    pts = S.theta_test_points(window, (4, 4))
+    prev, cur = pts['truth'], pts['perturbed']
+
+    def fun(a):
+        v, da = O.handover_value_and_grad(float(a[0]), prev, cur, *window.args(), **kw)
+        return v, np.array([da])
+
+    @OBJ
+    def cfun(xp, fp, gp):
+        v, g = fun([xp[0]])
+        fp[0], gp[0] = v, g[0]
+        return 0
+
+    ref = scipy.optimize.minimize(fun, np.array([0.5]), jac=True, method='L-BFGS-B', bounds=[(0.0, 1.0)], options={'maxiter': 6, 'gtol': 1e-6})
+    a = C.c_double(0.5)
+    out = Out()
+    assert lib.bounded_scalar_callback(C.byref(a), C.c_double(0.0), C.c_double(1.0), 6, C.c_double(1e-6), cfun, C.byref(out)) == 0
+    assert a.value == pytest.approx(float(ref.x[0]), abs=1e-8)
+    assert out.fun == pytest.approx(float(ref.fun), rel=1e-10)
+    assert (out.nit, out.nfev) == (ref.nit, ref.nfev)
