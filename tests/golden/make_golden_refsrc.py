@@ -13,6 +13,10 @@ The reference (pure Python on JAX) cannot be imported here as it stands: jax / j
 on the INPUTS of the committed fixtures tests/golden/*.npz, forward and (``jax.value_and_grad`` of the stand-in = torch autograd) reverse.
 What these vectors pin is the reference's composition of the primitives as executed - not the primitives, which the stand-in restates
 from JAX's published behaviour (tests/_jaxshim/jax/__init__.py lists them).  No reference source is copied: it is imported where it lies.
+
+With a real JAX at hand, ``EINCM_REAL_JAX=1 python tests/golden/make_golden_refsrc.py`` (and ..._fullsize.py) runs the same calls on
+it and rewrites the vectors; every test that reads them then checks the oracle and the CUDA path against JAX itself, which is what
+closes "parity unpinned" (DESIGN.md section 2).
 """
 import glob
 import os
@@ -30,12 +34,15 @@ def import_reference():
     """the reference's eincm.losses on top of the stand-in; raises ImportError when the reference tree is absent"""
     if not os.path.isdir(REF_SRC):
         raise ImportError(f'{REF_SRC} not present')
-    for p in (REF_SRC, os.path.join(TESTS, '_jaxshim')):
+    real = os.environ.get('EINCM_REAL_JAX') == '1'      # a machine with jax / jaxlib (/ jaxopt): the same script, no stand-in
+    for p in (REF_SRC,) + (() if real else (os.path.join(TESTS, '_jaxshim'),)):
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
     import jax
-    assert 'TEST INFRASTRUCTURE ONLY' in (jax.__doc__ or ''), 'a real jax is importable: use tests/golden/make_golden.py notes to regenerate from it'
+    if real:
+        jax.config.update('jax_enable_x64', True)       # src/experiments/e00/configs/jax_config/default.yaml:2
+    assert real != ('TEST INFRASTRUCTURE ONLY' in (jax.__doc__ or '')), 'stand-in / real jax mix-up'
     import eincm.losses as L
     assert os.path.realpath(L.__file__).startswith(os.path.realpath(REF_SRC))
     return jax, L

@@ -340,5 +340,5 @@ def test_reference_source_vectors_are_current(reference):
         z = np.load(os.path.join(G.GOLDEN_DIR, name + '.npz'))
         out = M.run_case(jax, L, {k: z[k] for k in z.files})
         ref = load_refsrc(name)
-        assert out['loss'] == float(ref['loss'])
-        np.testing.assert_array_equal(out['grad'], ref['grad'])
+        assert out['loss'] == pytest.approx(float(ref['loss']), rel=1e-13)          # not bitwise: torch's reductions split by thread count
+        np.testing.assert_allclose(out['grad'], ref['grad'], rtol=1e-11, atol=1e-15)
